@@ -1,0 +1,129 @@
+"""TEST INFRASTRUCTURE — regenerate tests/golden/*.npz from the REAL reference (container only).
+
+    python -m oracle.make_golden
+
+VQGAN fixtures are produced by the unmodified reference modules loaded from /root/reference
+(oracle/ref_loader.py); weights and inputs come from oracle/synth.py so that the GPU box (which has no
+/root/reference) can rebuild the same state_dict and compare its outputs with these files.
+MIGT fixtures come from the restatement (oracle/migt_oracle.py) — the TF reference cannot run —
+and are regression pins only ("parity unpinned").
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import synth, ref_loader, migt_oracle  # noqa: E402
+from viewformer_b200.config import VQGANConfig, MIGTConfig  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SMALL_VQ = dict(ch=32, ch_mult=[1, 2, 2], attn_resolutions=[8], image_size=32, embed_dim=16,
+                z_channels=16, n_embed=64)
+SMALL_MIGT = dict(n_layer=2, n_head=4, d_model=128, sequence_size=4, n_loss_skip=1)
+
+
+def vq_images(n, size, seed):
+    u8 = synth.make_images_uint8(1, n, size=size, seed=seed)[0]            # [n,H,W,3]
+    return migt_oracle.images_to_float(u8).permute(0, 3, 1, 2).contiguous()
+
+
+def golden_vqgan(tag, overrides, n_images, seed):
+    cfg = VQGANConfig(**overrides)
+    sd = synth.make_vqgan_state_dict(cfg, seed)
+    ref = ref_loader.build_reference_vqgan(sd, **overrides)
+    x = vq_images(n_images, cfg.image_size, 1000 + seed)
+    with torch.no_grad():
+        z = ref.quant_conv(ref.encoder(x))
+        quant, diff, codes = ref.encode(x)
+        dec = ref.decode_code(codes)
+        rec, diff2, _, _ = ref(x)
+    full = tag == "small"
+    np.savez_compressed(
+        os.path.join(OUT, f"vqgan_{tag}.npz"),
+        seed=seed, n_images=n_images,
+        z=z.numpy(), codes=codes.numpy(), diff=diff.numpy(),
+        quant_sample=quant[:1].numpy(),
+        dec=(dec if full else dec[:, :, ::4, ::4]).numpy(), dec0=dec[0].numpy(),
+        dec_mean=dec.mean().numpy(), dec_std=dec.std().numpy(),
+        rec_absmean=(rec - x).abs().mean().numpy())
+    print(tag, "codes", codes.shape, "diff", float(diff), "dec std", float(dec.std()))
+
+
+def golden_quantizer():
+    """QuantizeEMA training branch + Quantize(beta=.25) on a seeded z (utils_th.py:46-64, 93-120)."""
+    _, uth, _ = ref_loader.load_reference_modules()
+    g = torch.Generator().manual_seed(7)
+    D, K = 16, 64
+    q = uth.QuantizeEMA(D, K)
+    E = synth._uniform((D, K), 3 ** 0.5, g)
+    q.embeddings.copy_(E)
+    z = torch.randn((3, D, 4, 4), generator=g)
+    q.train()
+    outs = {}
+    for step in range(2):
+        quant, diff, ids = q(z)
+        outs[f"ids{step}"] = ids.numpy()
+        outs[f"diff{step}"] = diff.detach().numpy()
+        outs[f"emb{step}"] = q.embeddings.clone().numpy()
+        outs[f"cs{step}"] = q.ema_cluster_size_hidden.clone().numpy()
+        outs[f"dw{step}"] = q.ema_dw_hidden.clone().numpy()
+    q2 = uth.Quantize(D, K)
+    with torch.no_grad():
+        q2.embeddings.copy_(E)
+    quant, loss, ids = q2(z)
+    np.savez_compressed(os.path.join(OUT, "quantizer.npz"), E=E.numpy(), z=z.numpy(),
+                        commit_loss=loss.detach().numpy(), commit_ids=ids.numpy(), **outs)
+    print("quantizer ok")
+
+
+def golden_lookup():
+    """Nearest-neighbour indices of the reference's own expression (utils_th.py:36-41) on seeded rows,
+    including adversarial near-ties (midpoints of two codes)."""
+    g = torch.Generator().manual_seed(11)
+    D, K = 256, 1024
+    E = synth._uniform((D, K), 3 ** 0.5, g)
+    z = torch.randn((4096, D), generator=g)
+    a = torch.randint(0, K, (512,), generator=g)
+    b = torch.randint(0, K, (512,), generator=g)
+    mid = 0.5 * (E[:, a] + E[:, b]).t() + 1e-3 * torch.randn((512, D), generator=g)
+    z = torch.cat([z, mid, E[:, :64].t().contiguous()], 0)
+    dist = z.pow(2).sum(1, keepdim=True) - 2 * z @ E + E.pow(2).sum(0, keepdim=True)
+    idx = (-dist).max(1)[1]
+    d64 = (z.double()[:, :, None] - E.double()[None]).pow(2).sum(1)
+    top2 = d64.topk(2, dim=1, largest=False)
+    np.savez_compressed(os.path.join(OUT, "vq_lookup.npz"), seed=11, idx=idx.numpy(),
+                        idx_f64=top2.indices[:, 0].numpy(), gap_f64=(top2.values[:, 1] - top2.values[:, 0]).numpy())
+    print("lookup: fp32 vs fp64 mismatches", int((idx != top2.indices[:, 0]).sum()))
+
+
+def golden_migt():
+    for tag, overrides, B, T in (("small", SMALL_MIGT, 2, 4), ("full", {}, 1, 10)):
+        cfg = MIGTConfig(**overrides)
+        sd = synth.make_migt_state_dict(cfg, 3)
+        codes = synth.make_codes(B, T, seed=5)
+        cams = migt_oracle.normalize_cameras(migt_oracle.to_relative_cameras(synth.make_cameras(B, T, seed=6))[0])
+        ids = torch.cat([codes[:, :-1], torch.full_like(codes[:, :1], cfg.n_embeddings)], 1)
+        with torch.no_grad():
+            o = migt_oracle.forward(sd, cfg, dict(input_ids=ids, poses=cams))
+            o2 = migt_oracle.forward(sd, cfg, dict(input_ids=codes, poses=cams[:, :-1]))
+        last = o["logits"][:, -1]
+        np.savez_compressed(os.path.join(OUT, f"migt_{tag}.npz"), B=B, T=T,
+                            logits_last=last[:1].numpy().astype(np.float32),
+                            argmax_last=last.argmax(-1).numpy(),
+                            pose_last=migt_oracle.reduce_cameras(o2["pose_prediction"][:, -1:], -2).numpy())
+        print("migt", tag, "logit std", float(last.std()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    golden_lookup()
+    golden_quantizer()
+    golden_vqgan("small", SMALL_VQ, 2, 0)
+    golden_vqgan("full", {}, 4, 0)
+    golden_migt()
