@@ -1,0 +1,168 @@
+/* vf_b200.h — C-ABI of libvf_b200.so, the sm_100a kernel library underneath
+ * viewformer_b200.{VQGAN,MIGT}.
+ *
+ * The reference (jkulhanek/viewformer) has no FFI layer: its hot path is Python calling
+ * torch / TensorFlow library ops.  Each entry point below therefore names the reference
+ * *library-call site* it replaces (file:line in the reference tree).  All functions are
+ * extern "C", take raw device pointers, plain sizes and a cudaStream_t (as void*), never
+ * allocate persistent memory, never synchronise the stream, and return 0 on success or a
+ * negative code (message via vf_last_error()).  No torch types cross this boundary.
+ *
+ * Layout conventions: activations are NHWC ("pixel rows x channels"), i.e. every image
+ * tensor is a row-major matrix [N*H*W, C]; transformer activations are [B*T*64, d].
+ */
+#ifndef VF_B200_H
+#define VF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vf_stream_t; /* cudaStream_t */
+
+enum { VF_F32 = 0, VF_BF16 = 1 };
+enum { VF_ACT_NONE = 0, VF_ACT_GELU_ERF = 1 };
+enum { VF_BIAS_NONE = 0, VF_BIAS_N = 1, VF_BIAS_M = 2 };
+enum { VF_OK = 0, VF_ERR_ARG = -1, VF_ERR_CUDA = -2, VF_ERR_UNSUPPORTED = -3 };
+
+const char* vf_last_error(void);
+int vf_version(void);
+/* struct sizes, so a foreign-language binding can verify its mirror of the parameter structs */
+int vf_sizeof_simt_gemm(void);
+int vf_sizeof_tc_gemm(void);
+/* 0 when the current device is compute capability 10.x (B200); negative otherwise. */
+int vf_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Pixel / layout conversion
+ * replaces: evaluate/evaluate_transformer.py:106-108 (uint8 -> f32, *2-1), :128-129 (clip, ->uint8),
+ *           the NCHW<->NHWC permutes of models/utils_th.py:34,72 and utils/convert.py:61-67.
+ * ---------------------------------------------------------------------------------------- */
+int vf_u8_to_unit_f32(const uint8_t* in, float* out, int64_t n, vf_stream_t s);      /* x*(1/255)*2-1 */
+int vf_unit_f32_to_u8(const float* in, uint8_t* out, int64_t n, vf_stream_t s);      /* clip[-1,1]/2+.5 -> trunc(x*255.5) */
+int vf_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, vf_stream_t s);
+int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups) [+ swish] [+ nearest x2 upsample] [+ cast]
+ * replaces: models/vqgan_th.py:11-17 (Normalize, nonlinearity), :29-30 (F.interpolate nearest)
+ * x f32 [N, HW, C].  stats: double [N, groups, 2] scratch, zeroed and filled by vf_groupnorm_stats.
+ * vf_groupnorm_apply: y = ((x-mean)*rstd*gamma+beta) [swish]; normalize=0 -> plain cast/upsample.
+ *   upsample2x=1 writes y as [N, 2H, 2W, C] (needs H, W).  y_dtype VF_F32 | VF_BF16.
+ * ---------------------------------------------------------------------------------------- */
+int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, double* stats, vf_stream_t s);
+int vf_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta,
+                       int N, int H, int W, int C, int groups, float eps, int normalize, int swish,
+                       int upsample2x, void* y, int y_dtype, vf_stream_t s);
+
+/* LayerNorm over the last dim — replaces tf.keras LayerNormalization at models/migt.py:225-227,292. */
+int vf_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps,
+                 void* y, int y_dtype, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic fp32 CUDA-core implicit GEMM ("exact" path + the small-channel convs)
+ * replaces: torch.nn.Conv2d at models/vqgan_th.py:23-49,60-76,98-117,159-163,197-201,249-253,285-289,
+ *           332-333; torch.bmm at :128-140; tf.matmul at models/migt.py:93 and branching_attention.py:7,18.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    /* A operand: conv gather (conv=1) or dense strided matrix (conv=0) */
+    const void* A; int a_dtype; int conv;
+    int N, H, W, Cin;            /* conv: input NHWC dims */
+    int OH, OW, KH, KW, stride, pad_t, pad_l, upsample2x;
+    int64_t a_sm, a_sk;          /* dense: element strides of A(m,k) */
+    /* B operand (weights / second matrix): element (k,n) at k*b_sk + n*b_sn, fp32 or bf16 */
+    const void* B; int b_dtype; int64_t b_sk, b_sn;
+    /* problem */
+    int M, Ncols, K;             /* per batch */
+    int batch1, batch2;          /* grid.z = batch1*batch2 */
+    int64_t a_sb1, a_sb2, b_sb1, b_sb2, c_sb1, c_sb2;   /* batch strides (elements) */
+    /* epilogue: C = act(alpha*acc + bias) + residual */
+    float alpha; const float* bias; int bias_mode; int act;
+    const float* residual;       /* f32, same indexing as C */
+    float* C_f32; void* C_bf16;  /* either or both */
+    int64_t ldc;
+} vf_simt_gemm_t;
+int vf_simt_gemm(const vf_simt_gemm_t* p, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 tensor-core GEMM / implicit-GEMM conv (TMA -> 128B-swizzled smem -> tcgen05.mma -> TMEM)
+ * replaces the same call sites as vf_simt_gemm on the fast path.
+ *   GEMM:  C[b1,b2][m,n] = act(alpha * sum_k A[b1,b2][m,k] * B[b1,b2][n,k] + bias) + residual
+ *          A and B are K-major (k contiguous), 16-byte aligned rows, dtype bf16 (or f32 -> TF32).
+ *   CONV:  A is an NHWC activation tensor [N,H,W,Cin] (Cin % (128/elsize) == 0); taps describe the
+ *          filter footprint: tap t reads pixel (oy+dy[t], ox+dx[t]) and channels coff[t]..coff[t]+Cin-1
+ *          of a [N,H,W,Ctot] tensor; weights B are [Cout, ntaps*Cin] K-major.  Out-of-image taps are
+ *          zero (TMA out-of-bounds fill), which implements both the symmetric pad-1 and the
+ *          reference's asymmetric (0,1,0,1) pad.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int conv;                    /* 0 gemm, 1 conv */
+    int ab_dtype;                /* VF_BF16 | VF_F32 (TF32 math) */
+    const void* A; const void* B;
+    /* gemm geometry */
+    int M, Ncols, K; int batch1, batch2;
+    int64_t lda, ldb;            /* row strides (elements) */
+    int64_t a_sb1, a_sb2, b_sb1, b_sb2;
+    /* conv geometry */
+    int N, H, W, Ctot, Cin, OH, OW, ntaps;
+    int tap_dy[9], tap_dx[9], tap_coff[9];
+    /* k-range limit for block-causal attention: if causal_block > 0, output row tile [m0, m0+128) only
+       accumulates k < round_up(((m0+127)/causal_block + 1) * causal_block, BK); for the QK^T GEMM
+       (causal_skip_n=1) column tiles that start at or beyond that bound are skipped entirely. */
+    int causal_block, causal_skip_n;
+    /* epilogue */
+    float alpha; const float* bias; int bias_mode; int act; const float* residual;
+    float* C_f32; void* C_bf16; int64_t ldc, c_sb1, c_sb2;
+} vf_tc_gemm_t;
+int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Codebook
+ * replaces: models/utils_th.py:34-44 (distance, argmax(-dist), gather), :66 (diff), :70-72 (embed_code)
+ *   z [M,D] f32 rows; codebook given TRANSPOSED as Et [K,D] (built once at weight load) with esq[K]=|e|^2.
+ *   idx int64 [M]; quant (nullable) f32 [M,D]; diff_sum (nullable) double[1], += sum((e-z)^2).
+ * ---------------------------------------------------------------------------------------- */
+int vf_vq_lookup(const float* z, const float* Et, const float* esq, int64_t M, int D, int K,
+                 int64_t* idx, float* quant, double* diff_sum, vf_stream_t s);
+int vf_gather_rows(const float* table, const int64_t* idx, int64_t M, int D, int64_t n_rows, float* out, vf_stream_t s);
+/* training statistics of QuantizeEMA (utils_th.py:47-48): counts[K] += onehot, embed_sum[D,K] += z^T onehot */
+int vf_vq_ema_stats(const float* z, const int64_t* idx, int64_t M, int D, int K,
+                    float* counts, float* embed_sum_dk, vf_stream_t s);
+/* EMA update + Laplace-smoothed renormalisation (utils_th.py:55-64).  alpha = float32(1 - decay);
+ * corr = 1 - decay^counter (post-increment counter), both computed by the host exactly as torch does.
+ * Updates cs_hidden[K], dw_hidden[D,K], embeddings[D,K] and the derived Et[K,D], esq[K]. */
+int vf_vq_ema_update(const float* counts, const float* embed_sum_dk, int D, int K, float alpha, float corr, float eps,
+                     float* cs_hidden, float* dw_hidden, float* embeddings_dk, float* Et, float* esq, vf_stream_t s);
+/* Et[K,D], esq[K] from embeddings[D,K] (weight-load time) */
+int vf_vq_prepare_codebook(const float* embeddings_dk, int D, int K, float* Et, float* esq, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Transformer glue
+ * ---------------------------------------------------------------------------------------- */
+/* h[b,t,l,:] = wte[ids[b,t,l]] + wpe[l] + pose[b,t,:]   (models/migt.py:358-392).
+ * ids int32 (negative id -> use fixed_token, e.g. MASK for stream 1); pose f32 [B*T, d]. */
+int vf_migt_embed(const int32_t* ids, int fixed_token, const float* wte, const float* wpe, const float* pose,
+                  int64_t BT, int L, int d, float* out, vf_stream_t s);
+/* Row softmax of fp32 scores -> probabilities (bf16 or f32), written over the first `cols` columns.
+ *   mask_mode 0: none.  1: block-causal (branching_attention.py:41-61): row r (view (row0+r)/block)
+ *   keeps columns < (view+1)*block; masked entries get probability 0 (reference: logit -1e4 -> exp underflows
+ *   to exactly 0 in fp32).  2: multi-end (:82-126): columns [0,half) are stream-0 keys kept when
+ *   key view < query view, columns [half, 2*half) are own-stream keys kept when key view == query view. */
+int vf_softmax_rows(const float* scores, int64_t rows_total, int rows_per_batch, int cols, int64_t ld_in,
+                    int mask_mode, int block, int row0, void* P, int p_dtype, int64_t ld_out, vf_stream_t s);
+/* argmax over the last dim (first index wins) — tf.argmax at evaluate/evaluate_transformer.py:123 */
+int vf_argmax_rows(const float* x, int64_t rows, int cols, int64_t ld, int64_t* out, vf_stream_t s);
+/* pose head post-processing (models/migt.py:159-164): in [rows,7] raw MLP output ->
+ * xyz/pose_multiplier | normalised, sign-fixed quaternion */
+int vf_pose_postprocess(const float* raw, int64_t rows, float pose_multiplier, float* out, vf_stream_t s);
+/* plain dtype casts / strided copies used between ops */
+int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s);
+/* sum(|a-b|) and sum((a-b)^2) into double[2] (training losses, vqgan_th.py:401) */
+int vf_l1_l2_sums(const float* a, const float* b, int64_t n, double* out2, vf_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VF_B200_H */

@@ -1,0 +1,60 @@
+"""Host-side logic that needs no GPU: config parsing, registry, strict state-dict checks, camera maths."""
+import json
+
+import pytest
+import torch
+
+from oracle import synth, migt_oracle as mo
+from viewformer_b200 import config as C
+from viewformer_b200 import generate as G
+
+
+def test_config_defaults_match_reference():
+    v, m = C.VQGANConfig(), C.MIGTConfig()
+    assert (v.model, v.stride, v.n_embed, v.embed_dim, v.ch_mult, v.attn_resolutions) == ("vqgan", 16, 1024, 256, [1, 1, 2, 2, 4], [16])
+    assert (m.model, m.n_layer, m.n_head, m.d_model, m.sequence_size, m.n_loss_skip) == ("migt", 12, 12, 768, 20, 4)
+    assert m.use_localization and m.model_type == "transformer" and v.model_type == "codebook"
+
+
+def test_load_config_roundtrip(tmp_path):
+    d = C.MIGTConfig(n_layer=3, localization_weight="0").asdict()
+    p = tmp_path / "config.json"
+    p.write_text(json.dumps(d))
+    cfg = C.load_config(str(p))
+    assert isinstance(cfg, C.MIGTConfig) and cfg.n_layer == 3 and not cfg.use_localization
+    with pytest.raises(C.ModelNotFoundError):
+        C.load_config({"model": "nope"})
+
+
+def test_strict_state_dict_errors_before_touching_the_device():
+    from viewformer_b200 import VQGAN, MIGT
+    m = VQGAN(ch=32, ch_mult=[1, 2], image_size=16, attn_resolutions=[8], embed_dim=16, z_channels=16, n_embed=32)
+    sd = synth.make_vqgan_state_dict(m.config, 0)
+    bad = dict(sd); bad.pop("quant_conv.bias")
+    with pytest.raises(RuntimeError, match="Missing keys"):
+        m.load_state_dict(bad)
+    bad = dict(sd); bad["foo.bar"] = torch.zeros(1)
+    with pytest.raises(RuntimeError, match="Unexpected keys"):
+        m.load_state_dict(bad)
+    ok = dict(sd); ok["perceptual_loss.net.weight"] = torch.zeros(1)   # ignored like the reference (vqgan_th.py:322)
+    assert set(k for k in ok if not k.startswith("perceptual_loss")) == set(m.expected_keys())
+    t = MIGT(n_layer=1, d_model=64, n_head=2)
+    with pytest.raises(RuntimeError, match="Missing keys"):
+        t.load_state_dict({})
+
+
+def test_registry_picks_b200_classes():
+    from viewformer_b200 import AutoModel, AutoModelTH, VQGAN, MIGT
+    assert isinstance(AutoModelTH.from_config({"model": "vqgan"}), VQGAN)
+    assert isinstance(AutoModel.from_config({"model": "migt", "n_layer": 2}), MIGT)
+
+
+def test_camera_helpers_equal_oracle():
+    cams = synth.make_cameras(4, 6, seed=9)
+    r1, t1 = G.to_relative_cameras(cams)
+    r2, t2 = mo.to_relative_cameras(cams)
+    assert torch.allclose(r1, r2, atol=1e-6) and torch.equal(t1, t2)
+    assert torch.allclose(G.normalize_cameras(r1), mo.normalize_cameras(r2), atol=1e-7)
+    assert torch.allclose(G.from_relative_cameras(r1, t1), mo.from_relative_cameras(r2, t2), atol=1e-6)
+    x = torch.randn(2, 3, 64, 7)
+    assert torch.allclose(G.reduce_cameras(x, -2), mo.reduce_cameras(x, -2), atol=1e-6)

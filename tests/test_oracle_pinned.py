@@ -1,0 +1,137 @@
+"""Pins the CPU oracle: restatement == golden vectors produced by the REAL reference (tests/golden/*.npz,
+oracle/make_golden.py), restatement == real reference module when /root/reference is present, and the
+structural invariants that stand in for the (un-runnable) TensorFlow transformer."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, vqgan_oracle as vo, migt_oracle as mo, ref_loader
+from oracle.make_golden import SMALL_VQ, SMALL_MIGT, vq_images
+from viewformer_b200.config import VQGANConfig, MIGTConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_vqgan_small_matches_reference_golden(golden_dir):
+    g = _g(golden_dir, "vqgan_small.npz")
+    cfg = VQGANConfig(**SMALL_VQ)
+    sd = synth.make_vqgan_state_dict(cfg, int(g["seed"]))
+    x = vq_images(int(g["n_images"]), cfg.image_size, 1000 + int(g["seed"]))
+    with torch.no_grad():
+        quant, diff, codes, z = vo.encode(sd, cfg, x, return_pre_quant=True)
+        dec = vo.decode_code(sd, cfg, codes)
+    assert np.array_equal(codes.numpy(), g["codes"])                       # bit-exact indices
+    np.testing.assert_allclose(z.numpy(), g["z"], atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(float(diff), float(g["diff"]), rtol=1e-6)
+    np.testing.assert_allclose(dec.numpy(), g["dec"], atol=1e-6, rtol=1e-6)
+
+
+def test_vqgan_full_matches_reference_golden(golden_dir):
+    g = _g(golden_dir, "vqgan_full.npz")
+    cfg = VQGANConfig()
+    sd = synth.make_vqgan_state_dict(cfg, int(g["seed"]))
+    x = vq_images(int(g["n_images"]), cfg.image_size, 1000 + int(g["seed"]))
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        quant, diff, codes, z = vo.encode(sd, cfg, x, return_pre_quant=True)
+        dec = vo.decode_code(sd, cfg, codes)
+    assert np.array_equal(codes.numpy(), g["codes"])
+    np.testing.assert_allclose(z.numpy(), g["z"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(dec[0].numpy(), g["dec0"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(dec[:, :, ::4, ::4].numpy(), g["dec"], atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_vqgan_restatement_equals_real_reference():
+    cfg = VQGANConfig(**SMALL_VQ)
+    sd = synth.make_vqgan_state_dict(cfg, 5)
+    ref = ref_loader.build_reference_vqgan(sd, **SMALL_VQ)
+    x = torch.rand(3, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    with torch.no_grad():
+        q, d, c = ref.encode(x)
+        dec, d2, q2, c2 = ref(x)
+        qo, do, co = vo.encode(sd, cfg, x)
+        deco, *_ = vo.forward(sd, cfg, x)
+    assert torch.equal(c, co) and torch.equal(q, qo) and torch.equal(dec, deco)
+    assert float(d) == float(do)
+
+
+def test_quantizer_training_branch_matches_reference_golden(golden_dir):
+    g = _g(golden_dir, "quantizer.npz")
+    E, z = torch.from_numpy(g["E"]), torch.from_numpy(g["z"])
+    sd = {"quantize.embeddings": E.clone(), "quantize.ema_cluster_size_hidden": torch.zeros(E.shape[1]),
+          "quantize.ema_dw_hidden": torch.zeros_like(E), "quantize.counter": torch.tensor(0)}
+    for step in range(2):
+        q, diff, ids, new = vo.quantize_ema(sd, z, training=True)
+        sd.update(new)
+        assert np.array_equal(ids.numpy(), g[f"ids{step}"])
+        np.testing.assert_allclose(float(diff), float(g[f"diff{step}"]), rtol=1e-6)
+        np.testing.assert_allclose(sd["quantize.embeddings"].numpy(), g[f"emb{step}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(sd["quantize.ema_dw_hidden"].numpy(), g[f"dw{step}"], rtol=1e-6, atol=1e-7)
+    q, loss, ids = vo.quantize_commit(E, z)
+    assert np.array_equal(ids.numpy(), g["commit_ids"])
+    np.testing.assert_allclose(float(loss), float(g["commit_loss"]), rtol=1e-6)
+
+
+def _lookup_inputs(seed=11):
+    g = torch.Generator().manual_seed(seed)
+    D, K = 256, 1024
+    E = synth._uniform((D, K), 3 ** 0.5, g)
+    z = torch.randn((4096, D), generator=g)
+    a = torch.randint(0, K, (512,), generator=g)
+    b = torch.randint(0, K, (512,), generator=g)
+    mid = 0.5 * (E[:, a] + E[:, b]).t() + 1e-3 * torch.randn((512, D), generator=g)
+    return E, torch.cat([z, mid, E[:, :64].t().contiguous()], 0).contiguous()
+
+
+def test_c_lookup_oracle_matches_reference_expression(golden_dir):
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvq_oracle.so"))
+    g = _g(golden_dir, "vq_lookup.npz")
+    E, z = _lookup_inputs(int(g["seed"]))
+    z = z[:1024].contiguous()                     # bounded: the scalar C loop is slow
+    idx = np.empty(z.shape[0], dtype=np.int64)
+    lib.vq_oracle_lookup(ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(E.data_ptr()), ctypes.c_int64(z.shape[0]),
+                         ctypes.c_int(256), ctypes.c_int(1024), idx.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(0))
+    assert np.array_equal(idx, g["idx"][:1024])
+    assert np.array_equal(vo.vq_lookup(E, z).numpy(), g["idx"][:1024])
+
+
+def test_migt_restatement_regression_and_invariants(golden_dir):
+    g = _g(golden_dir, "migt_small.npz")
+    cfg = MIGTConfig(**SMALL_MIGT)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    B, T = int(g["B"]), int(g["T"])
+    codes = synth.make_codes(B, T, seed=5)
+    cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(B, T, seed=6))[0])
+    ids = torch.cat([codes[:, :-1], torch.full_like(codes[:, :1], cfg.n_embeddings)], 1)
+    with torch.no_grad():
+        o1 = mo.forward(sd, cfg, dict(input_ids=ids, poses=cams))
+        np.testing.assert_allclose(o1["logits"][:1, -1].numpy(), g["logits_last"], atol=1e-5, rtol=1e-5)
+        assert np.array_equal(o1["logits"][:, -1].argmax(-1).numpy(), g["argmax_last"])
+        # invariant (i): single-stream logits at the last view == 3-stream stream-1 logits at the last slot
+        ctx_c = torch.cat([cams[:, :-1], torch.zeros_like(cams[:, :1])], 1)
+        o3 = mo.forward(sd, cfg, dict(input_ids=ids, poses=ctx_c, output_poses=cams[:, -1:].repeat(1, T, 1),
+                                      localization_tokens=codes[:, -1:].repeat(1, T, 1, 1)))
+        assert (o1["logits"][:, -1] - o3["logits"][:, -1]).abs().max() < 1e-4
+        # invariant (ii): context hidden states do not depend on the query view => KV cache is exact
+        cams2 = cams.clone()
+        cams2[:, -1, :3] += 1.0
+        o2 = mo.forward(sd, cfg, dict(input_ids=ids, poses=cams2))
+        assert torch.equal(o1["hidden_states"][0][:, :-1], o2["hidden_states"][0][:, :-1])
+
+
+def test_camera_helpers_round_trip():
+    cams = synth.make_cameras(3, 5)
+    rel, tr = mo.to_relative_cameras(cams)
+    assert rel[:, 0, :3].abs().max() < 1e-6 and (rel[:, 0, 3] - 1).abs().max() < 1e-6
+    back = mo.from_relative_cameras(rel, tr)
+    assert (back - cams).abs().max() < 1e-5

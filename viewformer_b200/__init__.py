@@ -1,0 +1,19 @@
+"""viewformer_b200 — B200-native (sm_100a) implementation of ViewFormer's novel-view-synthesis hot path:
+VQGAN codebook encode/decode + MIGT context-view transformer, behind the reference's model surface."""
+from .config import VQGANConfig, MIGTConfig, load_config, ModelNotFoundError  # noqa: F401
+
+
+def __getattr__(name):   # lazy: importing the package must not require the built library
+    if name in ("VQGAN",):
+        from .vqgan import VQGAN
+        return VQGAN
+    if name in ("MIGT",):
+        from .migt import MIGT
+        return MIGT
+    if name in ("AutoModel", "AutoModelTH", "load_model"):
+        from . import registry
+        return getattr(registry, name)
+    if name in ("generate_batch_predictions",):
+        from .generate import generate_batch_predictions
+        return generate_batch_predictions
+    raise AttributeError(name)

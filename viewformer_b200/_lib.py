@@ -1,0 +1,416 @@
+"""ctypes binding of libvf_b200.so (include/vf_b200.h) + thin tensor-level helpers.
+
+torch is used here only as the device-memory / stream plumbing: every helper passes raw
+``data_ptr()`` values and the current CUDA stream handle across the C-ABI.  There is no CPU or
+PyTorch fallback: if the shared library is missing or the device is not sm_100, calls raise.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvf_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+BIAS_NONE, BIAS_N, BIAS_M = 0, 1, 2
+
+EXPORTS = [
+    "vf_last_error", "vf_version", "vf_sizeof_simt_gemm", "vf_sizeof_tc_gemm", "vf_device_check", "vf_u8_to_unit_f32", "vf_unit_f32_to_u8",
+    "vf_nchw_to_nhwc_f32", "vf_nhwc_to_nchw_f32", "vf_groupnorm_stats", "vf_groupnorm_apply", "vf_layernorm",
+    "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
+    "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
+    "vf_cast_f32_to_bf16", "vf_l1_l2_sums",
+]
+
+
+class SimtGemm(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_dtype", C.c_int), ("conv", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int),
+        ("OH", C.c_int), ("OW", C.c_int), ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int),
+        ("pad_t", C.c_int), ("pad_l", C.c_int), ("upsample2x", C.c_int),
+        ("a_sm", C.c_int64), ("a_sk", C.c_int64),
+        ("B", C.c_void_p), ("b_dtype", C.c_int), ("b_sk", C.c_int64), ("b_sn", C.c_int64),
+        ("M", C.c_int), ("Ncols", C.c_int), ("K", C.c_int), ("batch1", C.c_int), ("batch2", C.c_int),
+        ("a_sb1", C.c_int64), ("a_sb2", C.c_int64), ("b_sb1", C.c_int64), ("b_sb2", C.c_int64),
+        ("c_sb1", C.c_int64), ("c_sb2", C.c_int64),
+        ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_mode", C.c_int), ("act", C.c_int),
+        ("residual", C.c_void_p), ("C_f32", C.c_void_p), ("C_bf16", C.c_void_p), ("ldc", C.c_int64),
+    ]
+
+
+class TcGemm(C.Structure):
+    _fields_ = [
+        ("conv", C.c_int), ("ab_dtype", C.c_int), ("A", C.c_void_p), ("B", C.c_void_p),
+        ("M", C.c_int), ("Ncols", C.c_int), ("K", C.c_int), ("batch1", C.c_int), ("batch2", C.c_int),
+        ("lda", C.c_int64), ("ldb", C.c_int64),
+        ("a_sb1", C.c_int64), ("a_sb2", C.c_int64), ("b_sb1", C.c_int64), ("b_sb2", C.c_int64),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ctot", C.c_int), ("Cin", C.c_int),
+        ("OH", C.c_int), ("OW", C.c_int), ("ntaps", C.c_int),
+        ("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("tap_coff", C.c_int * 9),
+        ("causal_block", C.c_int), ("causal_skip_n", C.c_int),
+        ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_mode", C.c_int), ("act", C.c_int),
+        ("residual", C.c_void_p), ("C_f32", C.c_void_p), ("C_bf16", C.c_void_p),
+        ("ldc", C.c_int64), ("c_sb1", C.c_int64), ("c_sb2", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+class LibraryError(RuntimeError):
+    pass
+
+
+def load(require_device=False):
+    """dlopen the in-tree library.  Fails loudly — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryError(f"{LIB_PATH} not found — run `python -m viewformer_b200.build` (no CPU/PyTorch fallback exists)")
+        lib = C.CDLL(LIB_PATH)
+        lib.vf_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise LibraryError(f"{LIB_PATH} does not export {name}")
+            if name != "vf_last_error":
+                getattr(lib, name).restype = C.c_int
+        if lib.vf_sizeof_simt_gemm() != C.sizeof(SimtGemm) or lib.vf_sizeof_tc_gemm() != C.sizeof(TcGemm):
+            raise LibraryError("parameter struct layout mismatch between _lib.py and include/vf_b200.h")
+        _lib = lib
+    if require_device:
+        if not torch.cuda.is_available():
+            raise LibraryError("viewformer_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        rc = _lib.vf_device_check()
+        if rc != 0:
+            raise LibraryError(_lib.vf_last_error().decode())
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise LibraryError(f"libvf_b200 error {rc}: {_lib.vf_last_error().decode()}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _dev(t, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor expected"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+# ----------------------------------------------------------------------------------------------- pixels / layout
+def u8_to_unit(x_u8):
+    lib = load(True)
+    _dev(x_u8, torch.uint8)
+    out = torch.empty(x_u8.shape, dtype=torch.float32, device=x_u8.device)
+    _check(lib.vf_u8_to_unit_f32(_p(x_u8), _p(out), C.c_int64(x_u8.numel()), _stream()))
+    return out
+
+
+def unit_to_u8(x):
+    lib = load(True)
+    _dev(x, torch.float32)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _check(lib.vf_unit_f32_to_u8(_p(x), _p(out), C.c_int64(x.numel()), _stream()))
+    return out
+
+
+def nchw_to_nhwc(x):
+    lib = load(True)
+    _dev(x, torch.float32)
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    _check(lib.vf_nchw_to_nhwc_f32(_p(x), _p(out), n, c, h, w, _stream()))
+    return out
+
+
+def nhwc_to_nchw(x):
+    lib = load(True)
+    _dev(x, torch.float32)
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _check(lib.vf_nhwc_to_nchw_f32(_p(x), _p(out), n, c, h, w, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- norms
+def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample=False, normalize=True):
+    """x f32 [N,H,W,C] -> GroupNorm(32) [+swish] [+nearest x2] as out_dtype (vqgan_th.py:11-17,29-30)."""
+    lib = load(True)
+    _dev(x, torch.float32)
+    n, h, w, c = x.shape
+    stats = None
+    if normalize:
+        stats = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+        _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, _p(stats), _stream()))
+    oshape = (n, 2 * h, 2 * w, c) if upsample else (n, h, w, c)
+    y = torch.empty(oshape, dtype=out_dtype, device=x.device)
+    _check(lib.vf_groupnorm_apply(_p(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
+                                  int(normalize), int(swish), int(upsample), _p(y), _dt(y), _stream()))
+    return y
+
+
+def layernorm(x, gamma, beta, out_dtype, eps=1e-5):
+    lib = load(True)
+    _dev(x, torch.float32)
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    _check(lib.vf_layernorm(_p(x), _p(gamma), _p(beta), C.c_int64(rows), d, C.c_float(eps), _p(y), _dt(y), _stream()))
+    return y
+
+
+# ----------------------------------------------------------------------------------------------- GEMM / conv
+def _outs(out):
+    f32 = out if (out is not None and out.dtype == torch.float32) else None
+    b16 = out if (out is not None and out.dtype == torch.bfloat16) else None
+    return f32, b16
+
+
+def simt_conv(x, w_kn, bias, *, kh, stride=1, pad=(1, 1), upsample=False, residual=None, out_dtype=torch.float32, out=None):
+    """fp32 CUDA-core convolution.  x [N,H,W,Cin] f32|bf16, w_kn [kh*kh*Cin, Cout] f32."""
+    lib = load(True)
+    _dev(x)
+    n, h, w, cin = x.shape
+    cout = w_kn.shape[1]
+    vh, vw = (2 * h, 2 * w) if upsample else (h, w)
+    if stride == 1:
+        oh, ow = vh, vw
+    else:
+        oh, ow = vh // 2, vw // 2
+    if out is None:
+        out = torch.empty((n, oh, ow, cout), dtype=out_dtype, device=x.device)
+    p = SimtGemm()
+    p.A, p.a_dtype, p.conv = x.data_ptr(), _dt(x), 1
+    p.N, p.H, p.W, p.Cin = n, h, w, cin
+    p.OH, p.OW, p.KH, p.KW, p.stride = oh, ow, kh, kh, stride
+    p.pad_t, p.pad_l, p.upsample2x = pad[0], pad[1], int(upsample)
+    p.B, p.b_dtype, p.b_sk, p.b_sn = w_kn.data_ptr(), _dt(w_kn), cout, 1
+    p.M, p.Ncols, p.K, p.batch1, p.batch2 = n * oh * ow, cout, kh * kh * cin, 1, 1
+    p.alpha = 1.0
+    p.bias, p.bias_mode = (bias.data_ptr(), BIAS_N) if bias is not None else (None, BIAS_NONE)
+    p.act = ACT_NONE
+    p.residual = residual.data_ptr() if residual is not None else None
+    f32, b16 = _outs(out)
+    p.C_f32 = f32.data_ptr() if f32 is not None else None
+    p.C_bf16 = b16.data_ptr() if b16 is not None else None
+    p.ldc = cout
+    _check(lib.vf_simt_gemm(C.byref(p), _stream()))
+    return out
+
+
+def simt_gemm(A, B, out, *, M, N, K, a_strides, b_strides, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0),
+              alpha=1.0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0):
+    """Dense strided fp32 GEMM: C[m,n] = act(alpha*sum_k A(m,k) B(k,n) + bias) + residual.
+    a_strides = (stride_m, stride_k), b_strides = (stride_k, stride_n) in elements; *_off element offsets."""
+    lib = load(True)
+    p = SimtGemm()
+    p.A, p.a_dtype, p.conv = A.data_ptr() + a_off * A.element_size(), _dt(A), 0
+    p.a_sm, p.a_sk = a_strides
+    p.B, p.b_dtype = B.data_ptr() + b_off * B.element_size(), _dt(B)
+    p.b_sk, p.b_sn = b_strides
+    p.M, p.Ncols, p.K, p.batch1, p.batch2 = M, N, K, batch[0], batch[1]
+    p.a_sb1, p.a_sb2 = a_bs
+    p.b_sb1, p.b_sb2 = b_bs
+    p.c_sb1, p.c_sb2 = c_bs
+    p.alpha = alpha
+    p.bias, p.bias_mode = (bias.data_ptr(), bias_mode) if bias is not None else (None, BIAS_NONE)
+    p.act = act
+    p.residual = (residual.data_ptr() + c_off * 4) if residual is not None else None
+    f32, b16 = _outs(out)
+    p.C_f32 = (f32.data_ptr() + c_off * 4) if f32 is not None else None
+    p.C_bf16 = (b16.data_ptr() + c_off * 2) if b16 is not None else None
+    p.ldc = ldc
+    _check(lib.vf_simt_gemm(C.byref(p), _stream()))
+    return out
+
+
+def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), alpha=1.0,
+            bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0, causal_block=0,
+            causal_skip_n=False, out2=None):
+    """tcgen05 GEMM: C[m,n] = act(alpha*sum_k A[m,k] B[n,k] + bias) + residual; A,B K-major bf16 (or f32 -> TF32).
+    ``out2`` optionally receives a second copy in the other dtype (f32 + bf16 from one epilogue)."""
+    lib = load(True)
+    assert A.dtype == B.dtype
+    p = TcGemm()
+    p.conv, p.ab_dtype = 0, _dt(A)
+    p.A = A.data_ptr() + a_off * A.element_size()
+    p.B = B.data_ptr() + b_off * B.element_size()
+    p.M, p.Ncols, p.K, p.batch1, p.batch2 = M, N, K, batch[0], batch[1]
+    p.lda, p.ldb = lda, ldb
+    p.a_sb1, p.a_sb2 = a_bs
+    p.b_sb1, p.b_sb2 = b_bs
+    p.c_sb1, p.c_sb2 = c_bs
+    p.causal_block, p.causal_skip_n = causal_block, int(causal_skip_n)
+    p.alpha = alpha
+    p.bias, p.bias_mode = (bias.data_ptr(), bias_mode) if bias is not None else (None, BIAS_NONE)
+    p.act = act
+    p.residual = (residual.data_ptr() + c_off * 4) if residual is not None else None
+    for o in (out, out2):
+        if o is None:
+            continue
+        if o.dtype == torch.float32:
+            p.C_f32 = o.data_ptr() + c_off * 4
+        else:
+            p.C_bf16 = o.data_ptr() + c_off * 2
+    p.ldc = ldc
+    _check(lib.vf_tc_gemm(C.byref(p), _stream()))
+    return out
+
+
+TAPS_3x3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, residual=None, out=None,
+            out_dtype=torch.float32, out2=None):
+    """tcgen05 implicit-GEMM conv.  x [N,H,W,Ctot] bf16|f32 NHWC; w_nk [Cout, ntaps*Cin] (K-major, same dtype)."""
+    lib = load(True)
+    _dev(x)
+    n, h, w, ctot = x.shape
+    cin = ctot if cin is None else cin
+    cout = w_nk.shape[0]
+    oh, ow = (h, w) if out_hw is None else out_hw
+    if out is None:
+        out = torch.empty((n, oh, ow, cout), dtype=out_dtype, device=x.device)
+    p = TcGemm()
+    p.conv, p.ab_dtype = 1, _dt(x)
+    assert w_nk.dtype == x.dtype and w_nk.shape[1] == len(taps) * cin
+    p.A, p.B = x.data_ptr(), w_nk.data_ptr()
+    p.Ncols = cout
+    p.N, p.H, p.W, p.Ctot, p.Cin, p.OH, p.OW, p.ntaps = n, h, w, ctot, cin, oh, ow, len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        p.tap_dy[i], p.tap_dx[i] = dy, dx
+        p.tap_coff[i] = 0 if coffs is None else coffs[i]
+    p.alpha = 1.0
+    p.bias, p.bias_mode = (bias.data_ptr(), BIAS_N) if bias is not None else (None, BIAS_NONE)
+    p.act = ACT_NONE
+    p.residual = residual.data_ptr() if residual is not None else None
+    for o in (out, out2):
+        if o is None:
+            continue
+        if o.dtype == torch.float32:
+            p.C_f32 = o.data_ptr()
+        else:
+            p.C_bf16 = o.data_ptr()
+    p.ldc = cout
+    _check(lib.vf_tc_gemm(C.byref(p), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- codebook
+def vq_prepare_codebook(emb_dk):
+    lib = load(True)
+    _dev(emb_dk, torch.float32)
+    d, k = emb_dk.shape
+    et = torch.empty((k, d), dtype=torch.float32, device=emb_dk.device)
+    esq = torch.empty((k,), dtype=torch.float32, device=emb_dk.device)
+    _check(lib.vf_vq_prepare_codebook(_p(emb_dk), d, k, _p(et), _p(esq), _stream()))
+    return et, esq
+
+
+def vq_lookup(z_rows, et, esq, want_quant=True, want_diff=True):
+    """z_rows f32 [M,D] -> (idx int64 [M], quant f32 [M,D] | None, diff_sum f64[1] | None)."""
+    lib = load(True)
+    _dev(z_rows, torch.float32)
+    m, d = z_rows.shape
+    k = et.shape[0]
+    idx = torch.empty((m,), dtype=torch.int64, device=z_rows.device)
+    quant = torch.empty((m, d), dtype=torch.float32, device=z_rows.device) if want_quant else None
+    dsum = torch.zeros((1,), dtype=torch.float64, device=z_rows.device) if want_diff else None
+    _check(lib.vf_vq_lookup(_p(z_rows), _p(et), _p(esq), C.c_int64(m), d, k, _p(idx), _p(quant), _p(dsum), _stream()))
+    return idx, quant, dsum
+
+
+def gather_rows(table, idx):
+    lib = load(True)
+    _dev(table, torch.float32)
+    _dev(idx, torch.int64)
+    m = idx.numel()
+    d = table.shape[1]
+    out = torch.empty((m, d), dtype=torch.float32, device=table.device)
+    _check(lib.vf_gather_rows(_p(table), _p(idx), C.c_int64(m), d, C.c_int64(table.shape[0]), _p(out), _stream()))
+    return out
+
+
+def vq_ema_stats(z_rows, idx, k):
+    lib = load(True)
+    m, d = z_rows.shape
+    counts = torch.zeros((k,), dtype=torch.float32, device=z_rows.device)
+    esum = torch.zeros((d, k), dtype=torch.float32, device=z_rows.device)
+    _check(lib.vf_vq_ema_stats(_p(z_rows), _p(idx), C.c_int64(m), d, k, _p(counts), _p(esum), _stream()))
+    return counts, esum
+
+
+def vq_ema_update(counts, esum, alpha, corr, eps, cs_hidden, dw_hidden, emb_dk, et, esq):
+    lib = load(True)
+    d, k = emb_dk.shape
+    _check(lib.vf_vq_ema_update(_p(counts), _p(esum), d, k, C.c_float(alpha), C.c_float(corr), C.c_float(eps),
+                                _p(cs_hidden), _p(dw_hidden), _p(emb_dk), _p(et), _p(esq), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------- transformer glue
+def migt_embed(ids_i32, fixed_token, wte, wpe, pose_rows, BT, L):
+    lib = load(True)
+    d = wte.shape[1]
+    out = torch.empty((BT * L, d), dtype=torch.float32, device=wte.device)
+    _check(lib.vf_migt_embed(_p(ids_i32), int(fixed_token), _p(wte), _p(wpe), _p(pose_rows), C.c_int64(BT), L, d, _p(out),
+                             _stream()))
+    return out
+
+
+def softmax_rows(scores, P, *, rows_total, rows_per_batch, cols, ld_in, ld_out, mask_mode=0, block=0, row0=0):
+    lib = load(True)
+    _check(lib.vf_softmax_rows(_p(scores), C.c_int64(rows_total), rows_per_batch, cols, C.c_int64(ld_in), mask_mode, block,
+                               row0, _p(P), _dt(P), C.c_int64(ld_out), _stream()))
+    return P
+
+
+def argmax_rows(x_rows):
+    lib = load(True)
+    _dev(x_rows, torch.float32)
+    rows, cols = x_rows.shape
+    out = torch.empty((rows,), dtype=torch.int64, device=x_rows.device)
+    _check(lib.vf_argmax_rows(_p(x_rows), C.c_int64(rows), cols, C.c_int64(cols), _p(out), _stream()))
+    return out
+
+
+def pose_postprocess(raw_rows, mult):
+    lib = load(True)
+    _dev(raw_rows, torch.float32)
+    out = torch.empty_like(raw_rows)
+    _check(lib.vf_pose_postprocess(_p(raw_rows), C.c_int64(raw_rows.shape[0]), C.c_float(mult), _p(out), _stream()))
+    return out
+
+
+def cast_bf16(x):
+    lib = load(True)
+    _dev(x, torch.float32)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _check(lib.vf_cast_f32_to_bf16(_p(x), _p(out), C.c_int64(x.numel()), _stream()))
+    return out
+
+
+def l1_l2_sums(a, b):
+    lib = load(True)
+    out = torch.zeros((2,), dtype=torch.float64, device=a.device)
+    _check(lib.vf_l1_l2_sums(_p(a), _p(b), C.c_int64(a.numel()), _p(out), _stream()))
+    return out

@@ -1,0 +1,229 @@
+// GroupNorm (two-phase: statistics, then normalise [+swish] [+nearest x2] [+cast]) and LayerNorm.
+// HBM-bound kernels: 128-bit loads, one pass each.  NHWC layout: x is [N, HW, C] fp32.
+#include "vf_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Statistics: per (n, group) sum and sum of squares in double.
+// grid = (chunks, N), block = 256.  Each thread owns one channel quad (4 consecutive channels; a quad
+// never straddles a group because C/groups is a multiple of 4) and strides over the chunk's pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, int groups,
+                                                       int pix_per_block, double* __restrict__ stats) {
+    extern __shared__ double sh[];   // [groups][2]
+    const int n = blockIdx.y;
+    const int quads = C >> 2;
+    const int lanes = 256 / quads;              // pixel lanes per block (quads in {8..128})
+    const int cq = threadIdx.x % quads;
+    const int pl = threadIdx.x / quads;
+    for (int i = threadIdx.x; i < groups * 2; i += 256) sh[i] = 0.0;
+    __syncthreads();
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pl < lanes) {
+        const float4* base = reinterpret_cast<const float4*>(x + (int64_t)n * HW * C) + cq;
+        for (int p = p0 + pl; p < p1; p += lanes) {
+            const float4 v = __ldg(base + (int64_t)p * quads);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+        }
+        const int cpg = C / groups;
+        if ((cpg & 3) == 0) {        // the quad lies inside one group
+            const int g = (cq * 4) / cpg;
+            atomicAdd(&sh[g * 2 + 0], (double)((s[0] + s[1]) + (s[2] + s[3])));
+            atomicAdd(&sh[g * 2 + 1], (double)((ss[0] + ss[1]) + (ss[2] + ss[3])));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g = (cq * 4 + j) / cpg;
+                atomicAdd(&sh[g * 2 + 0], (double)s[j]);
+                atomicAdd(&sh[g * 2 + 1], (double)ss[j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 2; i += 256) atomicAdd(&stats[(int64_t)n * groups * 2 + i], sh[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Apply: one thread per channel quad of one pixel.
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int N, int H, int W, int C, int groups, float eps, int normalize,
+                                                       int swish, int up, OutT* __restrict__ y) {
+    const int quads = C >> 2;
+    const int64_t total = (int64_t)N * H * W * quads;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int cq = (int)(i % quads);
+    const int64_t pix = i / quads;                 // n*H*W + y*W + x
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    if (normalize) {
+        const int n = (int)(pix / ((int64_t)H * W));
+        const int cpg = C / groups;
+        const double cnt = (double)H * W * cpg;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+        float mu[4], rs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j > 0 && (cpg & 3) == 0) { mu[j] = mu[0]; rs[j] = rs[0]; continue; }
+            const int g = (cq * 4 + j) / cpg;
+            const double su = stats[((int64_t)n * groups + g) * 2 + 0];
+            const double sq = stats[((int64_t)n * groups + g) * 2 + 1];
+            const double mean = su / cnt;
+            double var = sq / cnt - mean * mean;
+            if (var < 0) var = 0;
+            rs[j] = (float)(1.0 / sqrt(var + (double)eps));
+            mu[j] = (float)mean;
+        }
+        v.x = (v.x - mu[0]) * rs[0] * ga.x + be.x;
+        v.y = (v.y - mu[1]) * rs[1] * ga.y + be.y;
+        v.z = (v.z - mu[2]) * rs[2] * ga.z + be.z;
+        v.w = (v.w - mu[3]) * rs[3] * ga.w + be.w;
+    }
+    if (swish) {
+        v.x = vf_swish(v.x); v.y = vf_swish(v.y); v.z = vf_swish(v.z); v.w = vf_swish(v.w);
+    }
+    if (!up) {
+        store4<OutT>(y + i * 4, v.x, v.y, v.z, v.w);
+    } else {
+        const int xx = (int)(pix % W);
+        const int64_t t = pix / W;
+        const int yy = (int)(t % H);
+        const int64_t n = t / H;
+        const int64_t W2 = 2 * (int64_t)W;
+        const int64_t o = ((n * 2 * H + 2 * yy) * W2 + 2 * xx) * C + cq * 4;
+        store4<OutT>(y + o, v.x, v.y, v.z, v.w);
+        store4<OutT>(y + o + C, v.x, v.y, v.z, v.w);
+        store4<OutT>(y + o + W2 * C, v.x, v.y, v.z, v.w);
+        store4<OutT>(y + o + W2 * C + C, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row cached in registers (D <= 1024, D % 4 == 0).
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t rows, int D, float eps,
+                                                        OutT* __restrict__ y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const int quads = D >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = lane + i * 32;
+        if (q < quads) {
+            v[i] = __ldg(xr + q);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = lane + i * 32;
+        if (q < quads) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = lane + i * 32;
+        if (q < quads) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
+            store4<OutT>(y + row * D + q * 4, (v[i].x - mean) * rstd * ga.x + be.x, (v[i].y - mean) * rstd * ga.y + be.y,
+                         (v[i].z - mean) * rstd * ga.z + be.z, (v[i].w - mean) * rstd * ga.w + be.w);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, double* stats, vf_stream_t s) {
+    VF_CHECK_ARG(x && stats, "vf_groupnorm_stats: null pointer");
+    VF_CHECK_ARG(C % groups == 0 && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0,
+                 "vf_groupnorm_stats: unsupported C=%d groups=%d", C, groups);
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * N, vf_s(s));
+    if (e != cudaSuccess) { vf_set_error("vf_groupnorm_stats: memset: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+    // enough blocks to fill the machine, at least 64 pixels per block
+    int chunks = (HW + 63) / 64;
+    const int target = (148 * 8 + N - 1) / N;
+    if (chunks > target) chunks = target;
+    if (chunks < 1) chunks = 1;
+    const int ppb = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppb - 1) / ppb;
+    dim3 grid(chunks, N);
+    gn_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, vf_s(s)>>>(x, HW, C, groups, ppb, stats);
+    VF_CHECK_LAUNCH("vf_groupnorm_stats");
+    return VF_OK;
+}
+
+extern "C" int vf_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, int N,
+                                  int H, int W, int C, int groups, float eps, int normalize, int swish, int upsample2x,
+                                  void* y, int y_dtype, vf_stream_t s) {
+    VF_CHECK_ARG(x && y, "vf_groupnorm_apply: null pointer");
+    VF_CHECK_ARG(C % 4 == 0, "vf_groupnorm_apply: C %% 4");
+    if (normalize) {
+        VF_CHECK_ARG(stats && gamma && beta, "vf_groupnorm_apply: normalize needs stats/gamma/beta");
+        VF_CHECK_ARG(C % groups == 0, "vf_groupnorm_apply: unsupported C=%d groups=%d", C, groups);
+    }
+    const int64_t total = (int64_t)N * H * W * (C / 4);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (y_dtype == VF_F32)
+        gn_apply_kernel<float><<<blocks, 256, 0, vf_s(s)>>>(x, stats, gamma, beta, N, H, W, C, groups, eps, normalize, swish,
+                                                            upsample2x, reinterpret_cast<float*>(y));
+    else if (y_dtype == VF_BF16)
+        gn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, vf_s(s)>>>(x, stats, gamma, beta, N, H, W, C, groups, eps, normalize,
+                                                                    swish, upsample2x, reinterpret_cast<__nv_bfloat16*>(y));
+    else
+        VF_CHECK_ARG(false, "vf_groupnorm_apply: bad dtype");
+    VF_CHECK_LAUNCH("vf_groupnorm_apply");
+    return VF_OK;
+}
+
+extern "C" int vf_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps, void* y,
+                            int y_dtype, vf_stream_t s) {
+    VF_CHECK_ARG(x && gamma && beta && y, "vf_layernorm: null pointer");
+    VF_CHECK_ARG(D % 4 == 0 && D <= 1024, "vf_layernorm: unsupported D=%d", D);
+    if (rows == 0) return VF_OK;
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    if (y_dtype == VF_F32)
+        layernorm_kernel<float><<<blocks, 256, 0, vf_s(s)>>>(x, gamma, beta, rows, D, eps, reinterpret_cast<float*>(y));
+    else if (y_dtype == VF_BF16)
+        layernorm_kernel<__nv_bfloat16><<<blocks, 256, 0, vf_s(s)>>>(x, gamma, beta, rows, D, eps,
+                                                                     reinterpret_cast<__nv_bfloat16*>(y));
+    else
+        VF_CHECK_ARG(false, "vf_layernorm: bad dtype");
+    VF_CHECK_LAUNCH("vf_layernorm");
+    return VF_OK;
+}

@@ -1,0 +1,499 @@
+// tcgen05 tensor-core GEMM and implicit-GEMM convolution for sm_100a.
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  smem ring (kStages x [A 128x128B | B BLOCK_N x128B])
+//   -> tcgen05.mma.cta_group::1 (one elected thread, fp32 accumulator in TMEM, M=128, N=BLOCK_N)
+//   -> tcgen05.ld epilogue (4 warps, one TMEM lane quarter each): alpha, bias, GELU, residual, f32/bf16 stores.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+// One CTA computes one 128 x BLOCK_N output tile.  GEMM operands are K-major; the convolution reads its A
+// operand straight from the NHWC activation tensor with a 4-D tensor map: for every filter tap the box
+// [TN images x TH rows x TW cols x 64 channels] shifted by (dy,dx) lands in shared memory as a 128-row K-major
+// tile, out-of-image pixels zero-filled by TMA — no im2col buffer exists anywhere.
+//
+// Replaces: torch.nn.Conv2d sites of viewformer/models/vqgan_th.py (3x3 stride-1 convs, 1x1 convs),
+//           tf.matmul sites of viewformer/models/migt.py:93 (Conv1D), :54 (tied LM head) and
+//           viewformer/models/branching_attention.py:7,18 (QK^T, PV) on the fast path.
+#include "vf_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int ROW_BYTES = 128;                 // one swizzle-128B row = one K block
+constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+    CUtensorMap tmA, tmB;
+    int conv;
+    int M, Ncols;
+    int num_k_blocks;          // total K blocks (gemm: ceil(K/BKe); conv: ntaps * cin_blocks)
+    int batch2;
+    int a_bm1, a_bm2, b_bm1, b_bm2;   // 0 => operand is shared by all batches along that batch dim
+    // conv tiling
+    int TW, TH, TN, tiles_x, tiles_y, OH, OW, Nimg, cin_blocks, bk_elems;
+    int tap_dy[9], tap_dx[9], tap_coff[9];
+    int causal_block, causal_skip_n;
+    float alpha;
+    const float* bias;
+    int bias_mode, act;
+    const float* residual;
+    float* C_f32;
+    __nv_bfloat16* C_bf16;
+    long long ldc, c_sb1, c_sb2;
+    unsigned idesc;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 26); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    printf("vf_tc_gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+    __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers bf16/f16 inputs, kind::tf32 fp32 inputs
+template <bool kTF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kTF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128B = 1024B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// 32 lanes x 32 columns of fp32 accumulator -> 32 registers per thread (thread i <- lane base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int kBlockN, int kStages, bool kTF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+    constexpr int B_STAGE_BYTES = kBlockN * ROW_BYTES;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int UMMA_K_BYTES = 32;           // 16 bf16 or 8 tf32 per instruction
+    constexpr int MMAS_PER_STAGE = ROW_BYTES / UMMA_K_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    // 1024B alignment required by the 128B swizzle atoms (descriptor base_offset = 0)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y, bz = blockIdx.z;
+    const int b1 = bz / p.batch2, b2 = bz % p.batch2;
+    const int m0 = m_tile * BLOCK_M;
+    const int n0 = n_tile * kBlockN;
+
+    // k-range (block-causal attention support)
+    int nkb = p.num_k_blocks;
+    if (p.causal_block > 0) {
+        const int lim = ((m0 + BLOCK_M - 1) / p.causal_block + 1) * p.causal_block;   // keys visible to the tile's last row
+        if (p.causal_skip_n) {
+            if (n0 >= lim) return;                                                    // whole tile masked: never read
+        } else {
+            const int kb = (lim + p.bk_elems - 1) / p.bk_elems;
+            if (kb < nkb) nkb = kb;
+        }
+    }
+
+    // conv tile origin
+    int img0 = 0, oy0 = 0, ox0 = 0;
+    if (p.conv) {
+        const int tx = m_tile % p.tiles_x;
+        const int t = m_tile / p.tiles_x;
+        const int ty = t % p.tiles_y;
+        img0 = (t / p.tiles_y) * p.TN;
+        oy0 = ty * p.TH;
+        ox0 = tx * p.TW;
+    }
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // whole warp allocates kBlockN TMEM columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kBlockN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                if (p.conv) {
+                    const int tap = kb / p.cin_blocks;
+                    const int cb = kb - tap * p.cin_blocks;
+                    tma_load_4d(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ox0 + p.tap_dx[tap],
+                                oy0 + p.tap_dy[tap], img0);
+                } else {
+                    tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, m0, b2 * p.a_bm2, b1 * p.a_bm1);
+                }
+                tma_load_4d(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, n0, b2 * p.b_bm2, b1 * p.b_bm1);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t sb = sa + A_STAGE_BYTES;
+                const uint64_t adesc = make_sw128_desc(sa);
+                const uint64_t bdesc = make_sw128_desc(sb);
+#pragma unroll
+                for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                    // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
+                    umma<kTF32>(tmem_base, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                tcgen05_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            tcgen05_commit(tmem_full_bar);                // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                     // TMEM lanes [32q, 32q+32) are only visible to warps with id%4 == q
+        const int row = quarter * 32 + lane;              // row of the tile this thread owns
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+
+        long long out_row_off;
+        bool row_ok;
+        int gm;                                            // logical row index (for bias_mode M)
+        if (p.conv) {
+            const int lx = row % p.TW;
+            const int t = row / p.TW;
+            const int ly = t % p.TH;
+            const int ln = t / p.TH;
+            const int img = img0 + ln, oy = oy0 + ly, ox = ox0 + lx;
+            row_ok = (img < p.Nimg) && (oy < p.OH) && (ox < p.OW);
+            gm = (img * p.OH + oy) * p.OW + ox;
+            out_row_off = (long long)gm * p.ldc;
+        } else {
+            gm = m0 + row;
+            row_ok = gm < p.M;
+            out_row_off = (long long)b1 * p.c_sb1 + (long long)b2 * p.c_sb2 + (long long)gm * p.ldc;
+        }
+        const float bias_m = (p.bias_mode == VF_BIAS_M && row_ok) ? __ldg(p.bias + gm) : 0.f;
+
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            if (!row_ok) continue;
+            const int nbase = n0 + c0;
+            if (nbase >= p.Ncols) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(r[j]) * p.alpha;
+                if (p.bias_mode == VF_BIAS_N) x += (nbase + j < p.Ncols) ? __ldg(p.bias + nbase + j) : 0.f;
+                else x += bias_m;
+                if (p.act == VF_ACT_GELU_ERF) x = vf_gelu_erf(x);
+                v[j] = x;
+            }
+            const long long off = out_row_off + nbase;
+            const bool full = (nbase + 32 <= p.Ncols);
+            if (p.residual) {
+                if (full && ((off & 3) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + off + j));
+                        v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+                    }
+                } else {
+                    for (int j = 0; j < 32 && nbase + j < p.Ncols; ++j) v[j] += __ldg(p.residual + off + j);
+                }
+            }
+            if (p.C_f32) {
+                if (full && ((off & 3) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(p.C_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 32 && nbase + j < p.Ncols; ++j) p.C_f32[off + j] = v[j];
+                }
+            }
+            if (p.C_bf16) {
+                if (full && ((off & 7) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+                        u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(p.C_bf16 + off + j) = u;
+                    }
+                } else {
+                    for (int j = 0; j < 32 && nbase + j < p.Ncols; ++j) p.C_bf16[off + j] = __float2bfloat16(v[j]);
+                }
+            }
+        }
+    }
+
+    // ---- teardown: everyone done with TMEM, then the allocating warp frees it
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBlockN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 4-D tensor map, dims innermost first, 128B swizzle, zero OOB fill.  strides[i] = byte stride of dim i+1.
+int make_tmap(CUtensorMap* tm, int dtype, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+              const uint32_t box[4]) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { vf_set_error("vf_tc_gemm: cuTensorMapEncodeTiled unavailable"); return VF_ERR_CUDA; }
+    cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, dtype == VF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        vf_set_error("vf_tc_gemm: cuTensorMapEncodeTiled failed (%d): dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+                     (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                     (unsigned long long)dims[3], (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+                     (unsigned long long)strides_bytes[2], box[0], box[1], box[2], box[3]);
+        return VF_ERR_CUDA;
+    }
+    return VF_OK;
+}
+
+// cute::UMMA::InstrDescriptor: [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt (0 f16, 1 bf16, 2 tf32)
+// | [15] A major (0=K) | [16] B major (0=K) | [17,23) N>>3 | [24,29) M>>4
+unsigned make_idesc(bool tf32, int M, int N) {
+    unsigned d = 0;
+    d |= 1u << 4;
+    const unsigned fmt = tf32 ? 2u : 1u;
+    d |= fmt << 7;
+    d |= fmt << 10;
+    d |= (unsigned)(N >> 3) << 17;
+    d |= (unsigned)(M >> 4) << 24;
+    return d;
+}
+
+template <int kBlockN, int kStages, bool kTF32>
+int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
+    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+        configured = true;
+    }
+    tc_gemm_kernel<kBlockN, kStages, kTF32><<<grid, NUM_THREADS, smem, st>>>(prm);
+    VF_CHECK_LAUNCH("vf_tc_gemm");
+    return VF_OK;
+}
+
+}  // namespace
+
+extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
+    VF_CHECK_ARG(q && q->A && q->B, "vf_tc_gemm: null operand");
+    VF_CHECK_ARG(q->C_f32 || q->C_bf16, "vf_tc_gemm: no output");
+    VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32, "vf_tc_gemm: bad dtype");
+    VF_CHECK_ARG(q->bias_mode == VF_BIAS_NONE || q->bias, "vf_tc_gemm: bias pointer missing");
+    const bool tf32 = q->ab_dtype == VF_F32;
+    const int es = tf32 ? 4 : 2;
+    const int bk = ROW_BYTES / es;                       // K elements per block: 64 bf16 / 32 tf32
+
+    TcParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.conv = q->conv;
+    prm.Ncols = q->Ncols;
+    prm.bk_elems = bk;
+    prm.alpha = q->alpha;
+    prm.bias = q->bias;
+    prm.bias_mode = q->bias_mode;
+    prm.act = q->act;
+    prm.residual = q->residual;
+    prm.C_f32 = q->C_f32;
+    prm.C_bf16 = reinterpret_cast<__nv_bfloat16*>(q->C_bf16);
+    prm.ldc = q->ldc;
+    prm.causal_block = q->causal_block;
+    prm.causal_skip_n = q->causal_skip_n;
+
+    // N tile: 128 when the problem is wide enough, else 64 (fewer wasted MMA columns / TMEM)
+    const int block_n = (q->Ncols > 64) ? 128 : 64;
+    dim3 grid;
+    int rc;
+    if (q->conv) {
+        VF_CHECK_ARG(q->ntaps >= 1 && q->ntaps <= 9, "vf_tc_gemm: ntaps");
+        VF_CHECK_ARG(q->Cin % bk == 0 && q->Ctot % (16 / es) == 0, "vf_tc_gemm: conv Cin=%d must be a multiple of %d", q->Cin, bk);
+        VF_CHECK_ARG(q->causal_block == 0, "vf_tc_gemm: causal with conv");
+        // output tile = TN images x TH rows x TW cols = 128 pixels
+        int TW = q->OW >= 16 ? 16 : (q->OW >= 8 ? 8 : (q->OW >= 4 ? 4 : (q->OW >= 2 ? 2 : 1)));
+        int TH = 128 / TW;
+        if (TH > q->OH) { TH = 1; while (TH * 2 <= q->OH) TH *= 2; }
+        int TN = 128 / (TW * TH);
+        VF_CHECK_ARG(TW * TH * TN == 128 && TN <= 256, "vf_tc_gemm: cannot tile %dx%d output", q->OH, q->OW);
+        prm.TW = TW; prm.TH = TH; prm.TN = TN;
+        prm.tiles_x = (q->OW + TW - 1) / TW;
+        prm.tiles_y = (q->OH + TH - 1) / TH;
+        prm.OH = q->OH; prm.OW = q->OW; prm.Nimg = q->N;
+        prm.cin_blocks = q->Cin / bk;
+        prm.num_k_blocks = q->ntaps * prm.cin_blocks;
+        prm.M = q->N * q->OH * q->OW;
+        prm.batch2 = 1;
+        for (int t = 0; t < q->ntaps; ++t) { prm.tap_dy[t] = q->tap_dy[t]; prm.tap_dx[t] = q->tap_dx[t]; prm.tap_coff[t] = q->tap_coff[t]; }
+        const uint64_t dimsA[4] = {(uint64_t)q->Ctot, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->N};
+        const uint64_t strA[3] = {(uint64_t)q->Ctot * es, (uint64_t)q->W * q->Ctot * es, (uint64_t)q->H * q->W * q->Ctot * es};
+        const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+        if ((rc = make_tmap(&prm.tmA, q->ab_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
+        const uint64_t Ktot = (uint64_t)q->ntaps * q->Cin;
+        const uint64_t dimsB[4] = {Ktot, (uint64_t)q->Ncols, 1, 1};
+        const uint64_t strB[3] = {Ktot * es, Ktot * es * q->Ncols, Ktot * es * q->Ncols};
+        const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)block_n, 1, 1};
+        if ((rc = make_tmap(&prm.tmB, q->ab_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
+        const int ntiles_img = (q->N + TN - 1) / TN;
+        grid = dim3(prm.tiles_x * prm.tiles_y * ntiles_img, (q->Ncols + block_n - 1) / block_n, 1);
+    } else {
+        VF_CHECK_ARG(q->M > 0 && q->Ncols > 0 && q->K > 0 && q->batch1 > 0 && q->batch2 > 0, "vf_tc_gemm: bad shape");
+        VF_CHECK_ARG((q->lda * es) % 16 == 0 && (q->ldb * es) % 16 == 0, "vf_tc_gemm: row strides must be 16-byte multiples");
+        VF_CHECK_ARG((q->a_sb1 * es) % 16 == 0 && (q->a_sb2 * es) % 16 == 0 && (q->b_sb1 * es) % 16 == 0 && (q->b_sb2 * es) % 16 == 0,
+                     "vf_tc_gemm: batch strides must be 16-byte multiples");
+        prm.M = q->M;
+        prm.batch2 = q->batch2;
+        prm.num_k_blocks = (q->K + bk - 1) / bk;
+        prm.c_sb1 = q->c_sb1; prm.c_sb2 = q->c_sb2;
+        // an operand with batch stride 0 is shared by every batch: its tensor map gets a size-1 batch dim and the
+        // kernel multiplies the batch coordinate by 0
+        prm.a_bm1 = (q->batch1 > 1 && q->a_sb1 != 0) ? 1 : 0;
+        prm.a_bm2 = (q->batch2 > 1 && q->a_sb2 != 0) ? 1 : 0;
+        prm.b_bm1 = (q->batch1 > 1 && q->b_sb1 != 0) ? 1 : 0;
+        prm.b_bm2 = (q->batch2 > 1 && q->b_sb2 != 0) ? 1 : 0;
+        const uint64_t fbA = (uint64_t)q->lda * es * (uint64_t)q->M, fbB = (uint64_t)q->ldb * es * (uint64_t)q->Ncols;
+        const uint64_t dimsA[4] = {(uint64_t)q->K, (uint64_t)q->M, prm.a_bm2 ? (uint64_t)q->batch2 : 1, prm.a_bm1 ? (uint64_t)q->batch1 : 1};
+        const uint64_t strA[3] = {(uint64_t)q->lda * es, prm.a_bm2 ? (uint64_t)q->a_sb2 * es : fbA, prm.a_bm1 ? (uint64_t)q->a_sb1 * es : fbA};
+        const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)BLOCK_M, 1, 1};
+        if ((rc = make_tmap(&prm.tmA, q->ab_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
+        const uint64_t dimsB[4] = {(uint64_t)q->K, (uint64_t)q->Ncols, prm.b_bm2 ? (uint64_t)q->batch2 : 1, prm.b_bm1 ? (uint64_t)q->batch1 : 1};
+        const uint64_t strB[3] = {(uint64_t)q->ldb * es, prm.b_bm2 ? (uint64_t)q->b_sb2 * es : fbB, prm.b_bm1 ? (uint64_t)q->b_sb1 * es : fbB};
+        const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)block_n, 1, 1};
+        if ((rc = make_tmap(&prm.tmB, q->ab_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
+        VF_CHECK_ARG(q->causal_block == 0 || (q->causal_block % bk == 0 || bk % q->causal_block == 0), "vf_tc_gemm: causal block");
+        grid = dim3((q->M + BLOCK_M - 1) / BLOCK_M, (q->Ncols + block_n - 1) / block_n, q->batch1 * q->batch2);
+    }
+    VF_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "vf_tc_gemm: grid too large");
+    prm.idesc = make_idesc(tf32, BLOCK_M, block_n);
+    cudaStream_t st = vf_s(s);
+    if (block_n == 128) return tf32 ? launch<128, 6, true>(prm, grid, st) : launch<128, 6, false>(prm, grid, st);
+    return tf32 ? launch<64, 8, true>(prm, grid, st) : launch<64, 8, false>(prm, grid, st);
+}

@@ -1,0 +1,118 @@
+"""``generate()`` — the reference's novel-view synthesis entry point, B200-native.
+
+Mirrors ``generate_batch_predictions(transformer_model, codebook_model, images, cameras)`` of
+viewformer/evaluate/evaluate_transformer.py:97-146 (same argument meaning, same result dict), so that
+evaluate_co3d.py:33,74 / evaluate_sevenscenes.py:14,262 / generate_images.py:7,29 keep working when the
+models are the viewformer_b200 ones.  Camera pre/post-processing (a few floats per scene) is host-side
+torch on whatever device the cameras live on; all image / token work runs in libvf_b200 kernels.
+"""
+import torch
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------- quaternion helpers (utils/geometry_tf.py:6-13,44-91)
+def quaternion_multiply(q1, q2):
+    w1, x1, y1, z1 = q1.unbind(-1)
+    w2, x2, y2, z2 = q2.unbind(-1)
+    return torch.stack((-x1 * x2 - y1 * y2 - z1 * z2 + w1 * w2,
+                        x1 * w2 + y1 * z2 - z1 * y2 + w1 * x2,
+                        -x1 * z2 + y1 * w2 + z1 * x2 + w1 * y2,
+                        x1 * y2 - y1 * x2 + z1 * w2 + w1 * z2), -1)
+
+
+def quaternion_conjugate(q):
+    return torch.cat((q[..., :1], -q[..., 1:]), -1)
+
+
+def quaternion_rotate(point, q):
+    p = torch.cat([torch.zeros_like(point[..., :1]), point], -1)
+    return quaternion_multiply(quaternion_multiply(q, p), quaternion_conjugate(q))[..., 1:]
+
+
+def quaternion_normalize(x, epsilon=1e-12):
+    return x * torch.rsqrt(torch.clamp((x * x).sum(-1, keepdim=True), min=epsilon))
+
+
+def quaternion_remove_sign(x):
+    return x * (2 * (x[..., :1] >= 0).to(x.dtype) - 1)
+
+
+def reduce_cameras(x, axis=-2):
+    """migt.py:150-154 + 123-129."""
+    x = torch.as_tensor(x)
+    q = quaternion_remove_sign(quaternion_normalize(x[..., 3:])).mean(axis)
+    q = quaternion_remove_sign(quaternion_normalize(q))
+    return torch.cat((x[..., :3].mean(axis), q), -1)
+
+
+def to_relative_cameras(cameras):
+    """evaluate_transformer.py:70-78."""
+    xyz, quat = cameras[..., :3], cameras[..., 3:]
+    t_xyz, t_q = xyz[..., :1, :], quat[..., :1, :]
+    inv = quaternion_conjugate(t_q).expand_as(quat)
+    return torch.cat((quaternion_rotate(xyz - t_xyz, inv), quaternion_multiply(inv, quat)), -1), torch.cat((t_xyz, t_q), -1)
+
+
+def from_relative_cameras(cameras, transform):
+    """evaluate_transformer.py:81-87."""
+    t_xyz, t_q = transform[..., :3], transform[..., 3:]
+    xyz, quat = cameras[..., :3], cameras[..., 3:]
+    t_qe = t_q.expand_as(quat)
+    return torch.cat((quaternion_rotate(xyz, t_qe) + t_xyz, quaternion_multiply(t_qe, quat)), -1)
+
+
+def normalize_cameras(cameras):
+    """evaluate_transformer.py:90-94."""
+    return torch.cat((cameras[..., :3], quaternion_remove_sign(quaternion_normalize(cameras[..., 3:]))), -1)
+
+
+# --------------------------------------------------------------------------- generate
+def generate_batch_predictions(transformer_model, codebook_model, images, cameras, *, encode_target=None):
+    """images uint8 [B,T,H,W,3] (host or device), cameras f32 [B,T,7] ->
+    dict(ground_truth_images [B,H,W,3] u8, generated_images [B,H,W,3] u8, ground_truth_cameras [B,7],
+         generated_cameras [B,7]) — evaluate_transformer.py:97-146.
+
+    ``encode_target``: the reference encodes all T views and, when the model localises, runs a second
+    forward on the true codes of the target view (:134-136).  Default: encode the target only when that
+    second forward is needed (skipping it does not change any returned value).
+    """
+    dev = transformer_model.device
+    images = torch.as_tensor(images)
+    cameras = torch.as_tensor(cameras)
+    if cameras.dtype != torch.float32:
+        cameras = cameras.to(torch.float32)
+    gt_cam = cameras[:, -1]
+    transform = None
+    if transformer_model.config.augment_poses == "relative":
+        cameras, transform = to_relative_cameras(cameras)
+    cameras = normalize_cameras(cameras)
+
+    B, T = images.shape[:2]
+    size = codebook_model.config.image_size
+    if images.shape[2] != size or images.shape[3] != size:
+        raise NotImplementedError("resize_tf (data/_common.py:19-62) is outside this round's scope: feed %dx%d images" % (size, size))
+    use_loc = transformer_model.use_localization
+    if encode_target is None:
+        encode_target = use_loc
+    img_dev = images.to(device=dev, non_blocking=True) if images.device != dev else images
+    side = transformer_model.token_image_size
+    n_enc = T if encode_target else T - 1
+    enc_in = img_dev[:, :n_enc].reshape((B * n_enc,) + tuple(img_dev.shape[2:]))
+    if not enc_in.is_contiguous():
+        enc_in = enc_in.contiguous()
+    codes = codebook_model.encode_u8(enc_in).reshape(B, n_enc, side, side)
+
+    cams_dev = cameras.to(dev)
+    gen_codes = transformer_model.generate_codes(codes[:, : T - 1], cams_dev)
+    gen_images = codebook_model.decode_code_u8(gen_codes)
+
+    if use_loc:
+        out = transformer_model(dict(input_ids=codes, poses=cams_dev[:, :-1].contiguous()))
+        gen_cam = reduce_cameras(out["pose_prediction"][:, -1:], -2)
+    else:
+        gen_cam = cams_dev[:, :1]
+    if transform is not None:
+        gen_cam = from_relative_cameras(gen_cam, transform.to(gen_cam.device))
+    return dict(ground_truth_images=images[:, -1], generated_images=gen_images, ground_truth_cameras=gt_cam,
+                generated_cameras=gen_cam[:, -1], generated_codes=gen_codes)

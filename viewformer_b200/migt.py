@@ -1,0 +1,301 @@
+"""MIGT context-view transformer — B200-native drop-in for the reference's Keras ``MIGT``.
+
+Surface (viewformer/models/migt.py:241-455, 532-533):
+    MIGT(config).load_state_dict(sd)
+    model(dict(input_ids=int[B,T,8,8], poses=f32[B,T|T-1,7] [, output_poses=f32[B,T,7]]
+               [, localization_tokens=int[B,T,8,8]]), training=False)
+        -> dict(logits [B,T,8,8,n_embeddings], pose_prediction [B,T,64,7] (if use_localization), ...)
+    .mask_token / .localization_token / .use_localization / .config / .reduce_cameras(x, axis)
+plus the inference entry points the reference spreads over evaluate/*.py:
+    .generate_codes(codes_ctx, poses)                 last-view argmax codes only (evaluate_transformer.py:118-123)
+    .prefill_context(...) / .query(...)               context K/V cache (exact: block-causality makes context
+                                                      states independent of the query view)
+
+Weight names follow the reference's layer names (``h.<i>.attn.c_attn.weight`` [in,out], ``wte.weight`` [1026,d],
+``wpe.embeddings`` [256,d] ...; see INTEGRATION.md for the TF checkpoint variable map).  c_attn columns are
+[v | q | k] (migt.py:207-213); attention logits are NOT scaled by 1/sqrt(dh) (branching_attention.py:7).
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import _lib as L
+from .config import MIGTConfig, load_config
+from .ops import Precision, Linear, gemm_nt, linear
+
+LN_EPS = 1e-5   # migt.py:14
+
+
+class MIGT:
+    def __init__(self, config=None, precision="bf16", device="cuda", **config_overrides):
+        if config is None:
+            config = MIGTConfig(**config_overrides)
+        self.config = load_config(config)
+        cfg = self.config
+        self.prec = Precision(precision)
+        self.exact = Precision("fp32")
+        self.device = torch.device(device)
+        self.n_image_tokens = cfg.token_image_size ** 2
+        self.n_embeddings = cfg.n_embeddings
+        self.token_image_size = cfg.token_image_size
+        self.d_model = cfg.d_model
+        self.mask_token = cfg.n_embeddings                 # migt.py:256
+        self.localization_token = cfg.n_embeddings + 1     # migt.py:257
+        self.use_localization = cfg.use_localization       # migt.py:268-269
+        self._codebook_model = None
+        self._sd = None
+        self._w = None
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def codebook_model(self):
+        return self._codebook_model
+
+    @codebook_model.setter
+    def codebook_model(self, model):
+        self._codebook_model = model
+
+    def expected_keys(self):
+        cfg = self.config
+        keys = ["wte.weight", "wpe.embeddings"]
+        for n in ("pose_embedding.c_fc", "pose_embedding.c_proj", "pose_classifier.c_fc", "pose_classifier.c_proj"):
+            keys += [n + ".weight", n + ".bias"]
+        for i in range(cfg.n_layer):
+            p = f"h.{i}."
+            keys += [p + "ln_1.gamma", p + "ln_1.beta", p + "ln_2.gamma", p + "ln_2.beta"]
+            for n in ("attn.c_attn", "attn.c_proj", "mlp.c_fc", "mlp.c_proj"):
+                keys += [p + n + ".weight", p + n + ".bias"]
+        keys += ["ln_f.gamma", "ln_f.beta"]
+        return keys
+
+    def load_state_dict(self, state_dict, strict=True):
+        sd = OrderedDict(state_dict.items())
+        if strict:
+            want, got = set(self.expected_keys()), set(sd.keys())
+            if want - got:
+                raise RuntimeError(f"Missing keys: {want - got}")
+            if got - want:
+                raise RuntimeError(f"Unexpected keys: {got - want}")
+        self._sd = OrderedDict((k, torch.as_tensor(v).detach().to("cpu").clone()) for k, v in sd.items())
+        self._build()
+        return self
+
+    def state_dict(self):
+        return OrderedDict((k, v.clone()) for k, v in self._sd.items())
+
+    def _build(self):
+        L.load(require_device=True)
+        sd, prec, dev, cfg = self._sd, self.prec, self.device, self.config
+        d = cfg.d_model
+        f32 = lambda t: t.to(dev, torch.float32).contiguous()
+        w = dict(wte=f32(sd["wte.weight"]), wpe=f32(sd["wpe.embeddings"]))
+        w["lm"] = Linear(sd["wte.weight"][: cfg.n_embeddings], None, prec, dev)        # tied head, first n_embeddings rows (:417)
+        # pose MLPs stay fp32 (reference: dtype='float32' islands, migt.py:136,291); pose_multiplier folded into c_fc rows 0..2
+        fc = sd["pose_embedding.c_fc.weight"].clone()
+        fc[:3] = fc[:3] * cfg.pose_multiplier
+        w["pe_fc"] = Linear(fc.t(), sd["pose_embedding.c_fc.bias"], self.exact, dev)
+        w["pe_proj"] = Linear(sd["pose_embedding.c_proj.weight"].t(), sd["pose_embedding.c_proj.bias"], self.exact, dev)
+        w["pc_fc"] = Linear(sd["pose_classifier.c_fc.weight"].t(), sd["pose_classifier.c_fc.bias"], self.exact, dev)
+        w["pc_proj"] = Linear(sd["pose_classifier.c_proj.weight"].t(), sd["pose_classifier.c_proj.bias"], self.exact, dev)
+        layers = []
+        for i in range(cfg.n_layer):
+            p = f"h.{i}."
+            ca_w, ca_b = sd[p + "attn.c_attn.weight"], sd[p + "attn.c_attn.bias"].reshape(-1)    # [d,3d] cols = v|q|k
+            layers.append(dict(
+                ln1=(f32(sd[p + "ln_1.gamma"]), f32(sd[p + "ln_1.beta"])),
+                ln2=(f32(sd[p + "ln_2.gamma"]), f32(sd[p + "ln_2.beta"])),
+                qk=Linear(ca_w[:, d:].t(), ca_b[d:], prec, dev),              # [2d, d]: rows 0..d-1 -> q, d..2d-1 -> k
+                v=Linear(ca_w[:, :d].t(), ca_b[:d], prec, dev),               # [d, d]
+                proj=Linear(sd[p + "attn.c_proj.weight"].t(), sd[p + "attn.c_proj.bias"], prec, dev),
+                fc=Linear(sd[p + "mlp.c_fc.weight"].t(), sd[p + "mlp.c_fc.bias"], prec, dev),
+                fc2=Linear(sd[p + "mlp.c_proj.weight"].t(), sd[p + "mlp.c_proj.bias"], prec, dev)))
+        w["layers"] = layers
+        w["lnf"] = (f32(sd["ln_f.gamma"]), f32(sd["ln_f.beta"]))
+        self._w = w
+
+    def _in(self, x, dtype):
+        t = torch.as_tensor(x)
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+        return t
+
+    # ------------------------------------------------------------------ embeddings
+    def _pose_embed(self, poses_rows):
+        """pose MLP 7 -> 2d (GELU erf) -> d in fp32 (migt.py:139-145, 291, 354)."""
+        h = linear(self.exact, poses_rows, self._w["pe_fc"], torch.float32, act=L.ACT_GELU)
+        return linear(self.exact, h, self._w["pe_proj"], torch.float32)
+
+    def _embed_stream(self, ids, fixed_token, pose_rows, B, T):
+        Lt = self.n_image_tokens
+        return L.migt_embed(ids, fixed_token, self._w["wte"], self._w["wpe"], pose_rows, B * T, Lt)
+
+    # ------------------------------------------------------------------ transformer body
+    def _attention(self, lw, a_list, B, T, kv=None):
+        """BranchingAttention (migt.py:211-217 -> branching_attention.py:82-126) on normalised streams ``a_list``
+        (each [B*S, d] in operand dtype).  Stream 0 is block-causal over its own keys; stream s>=1 attends to
+        stream-0 keys of strictly earlier views plus its own view in its own stream.  Returns per-stream
+        attention outputs [B*S, d] (operand dtype) before c_proj."""
+        prec, cfg = self.prec, self.config
+        d, H = cfg.d_model, cfg.n_head
+        dh = d // H
+        Lt = self.n_image_tokens
+        S = T * Lt
+        dev = a_list[0].device
+        ns = len(a_list)
+        # q|k rows and V^T of every stream, laid side by side: keys [B, ns*S, 2d], V^T [B, d, ns*S]
+        qk = torch.empty((B, ns * S, 2 * d), dtype=prec.opd, device=dev)
+        vt = torch.empty((B, d, ns * S), dtype=prec.opd, device=dev)
+        for s, a in enumerate(a_list):
+            gemm_nt(prec, a, lw["qk"].w, qk, M=S, N=2 * d, K=d, lda=d, ldb=d, ldc=2 * d, batch=(B, 1), a_bs=(S * d, 0),
+                    b_bs=(0, 0), c_bs=(ns * S * 2 * d, 0), c_off=s * S * 2 * d, bias=lw["qk"].b, bias_mode=L.BIAS_N)
+            gemm_nt(prec, lw["v"].w, a, vt, M=d, N=S, K=d, lda=d, ldb=d, ldc=ns * S, batch=(B, 1), a_bs=(0, 0),
+                    b_bs=(S * d, 0), c_bs=(d * ns * S, 0), c_off=s * S, bias=lw["v"].b, bias_mode=L.BIAS_M)
+        outs = []
+        for s in range(ns):
+            if s == 0:
+                kc, koff, mask_mode = S, 0, 1                     # keys: stream 0 only, block-causal (>=)
+            else:
+                kc, koff, mask_mode = 2 * S, 0, 2                 # keys: [stream 0 | stream s]
+            o = torch.empty((B * S, d), dtype=prec.opd, device=dev)
+            scores = torch.empty((B, H, S, kc), dtype=torch.float32, device=dev)
+            p = torch.empty((B, H, S, kc), dtype=prec.opd, device=dev)
+            if s == 0:
+                gemm_nt(prec, qk, qk, scores, M=S, N=S, K=dh, lda=2 * d, ldb=2 * d, ldc=S, batch=(B, H),
+                        a_bs=(ns * S * 2 * d, dh), b_bs=(ns * S * 2 * d, dh), c_bs=(H * S * S, S * S), a_off=0, b_off=d,
+                        causal_block=Lt, causal_skip_n=True)
+                L.softmax_rows(scores, p, rows_total=B * H * S, rows_per_batch=S, cols=S, ld_in=S, ld_out=S, mask_mode=1, block=Lt)
+                gemm_nt(prec, p, vt, o, M=S, N=dh, K=S, lda=S, ldb=ns * S, ldc=d, batch=(B, H), a_bs=(H * S * S, S * S),
+                        b_bs=(d * ns * S, dh * ns * S), c_bs=(S * d, dh), causal_block=Lt)
+            else:
+                # logits vs stream-0 keys -> columns [0,S); vs own-stream keys -> columns [S,2S)
+                for half, key_stream in ((0, 0), (1, s)):
+                    gemm_nt(prec, qk, qk, scores, M=S, N=S, K=dh, lda=2 * d, ldb=2 * d, ldc=2 * S, batch=(B, H),
+                            a_bs=(ns * S * 2 * d, dh), b_bs=(ns * S * 2 * d, dh), c_bs=(H * S * 2 * S, S * 2 * S),
+                            a_off=s * S * 2 * d, b_off=key_stream * S * 2 * d + d, c_off=half * S)
+                L.softmax_rows(scores, p, rows_total=B * H * S, rows_per_batch=S, cols=2 * S, ld_in=2 * S, ld_out=2 * S,
+                               mask_mode=2, block=Lt)
+                # P[:, :S] . V0 + P[:, S:] . Vs : two accumulating passes would need beta=1; instead gather the two
+                # V^T panels side by side (they already are when s == 1; otherwise copy panel s next to panel 0)
+                if s == 1:
+                    vcat, ldv = vt, ns * S
+                else:
+                    vcat = torch.empty((B, d, 2 * S), dtype=prec.opd, device=dev)
+                    vcat[:, :, :S].copy_(vt[:, :, :S]); vcat[:, :, S:].copy_(vt[:, :, s * S:(s + 1) * S])
+                    ldv = 2 * S
+                gemm_nt(prec, p, vcat, o, M=S, N=dh, K=2 * S, lda=2 * S, ldb=ldv, ldc=d, batch=(B, H),
+                        a_bs=(H * S * 2 * S, S * 2 * S), b_bs=(d * ldv, dh * ldv), c_bs=(S * d, dh))
+            outs.append(o)
+        return outs
+
+    def _block(self, lw, xs, B, T):
+        """Block.call (migt.py:230-238): pre-LN attention + pre-LN MLP over a list of streams (shared weights)."""
+        prec = self.prec
+        a = [L.layernorm(x, *lw["ln1"], out_dtype=prec.opd, eps=LN_EPS) for x in xs]
+        att = self._attention(lw, a, B, T)
+        xs = [linear(prec, o, lw["proj"], torch.float32, residual=x) for o, x in zip(att, xs)]
+        out = []
+        for x in xs:
+            m = L.layernorm(x, *lw["ln2"], out_dtype=prec.opd, eps=LN_EPS)
+            hmid = linear(prec, m, lw["fc"], prec.opd, act=L.ACT_GELU)
+            out.append(linear(prec, hmid, lw["fc2"], torch.float32, residual=x))
+        return out
+
+    def _body(self, xs, B, T):
+        for lw in self._w["layers"]:
+            xs = self._block(lw, xs, B, T)
+        return xs
+
+    def _lm_logits(self, h_rows_f32):
+        """ln_f -> tied-embedding logits, first n_embeddings classes (migt.py:408, 417)."""
+        hn = L.layernorm(h_rows_f32, *self._w["lnf"], out_dtype=self.prec.opd, eps=LN_EPS)
+        return linear(self.prec, hn, self._w["lm"], torch.float32)
+
+    def _lm_logits_last(self, h_rows_f32, B, T):
+        """Same, for the last view's rows only — read in place through the GEMM's batch stride (no gather copy)."""
+        cfg, Lt, d = self.config, self.n_image_tokens, self.config.d_model
+        hn = L.layernorm(h_rows_f32, *self._w["lnf"], out_dtype=self.prec.opd, eps=LN_EPS)
+        logits = torch.empty((B * Lt, cfg.n_embeddings), dtype=torch.float32, device=hn.device)
+        lm = self._w["lm"]
+        gemm_nt(self.prec, hn, lm.w, logits, M=Lt, N=lm.n, K=d, lda=d, ldb=d, ldc=lm.n, batch=(B, 1), a_bs=(T * Lt * d, 0),
+                b_bs=(0, 0), c_bs=(Lt * lm.n, 0), a_off=(T - 1) * Lt * d)
+        return logits
+
+    def _pose_head(self, h_rows_f32):
+        """QuaternionPoseRepresentation.call without targets (migt.py:156-164), fp32."""
+        hn = L.layernorm(h_rows_f32, *self._w["lnf"], out_dtype=torch.float32, eps=LN_EPS)
+        raw = linear(self.exact, linear(self.exact, hn, self._w["pc_fc"], torch.float32, act=L.ACT_GELU), self._w["pc_proj"], torch.float32)
+        return L.pose_postprocess(raw, self.config.pose_multiplier)
+
+    # ------------------------------------------------------------------ reference call surface
+    def __call__(self, inputs, training=False, compute_losses=False, last_only=False, **kwargs):
+        """MIGT.call (migt.py:338-455), inference semantics (training=False; dropout inactive).
+        ``last_only=True`` computes logits for the last view only (what evaluate_transformer.py:123 consumes)."""
+        if training or compute_losses:
+            raise NotImplementedError("MIGT training / loss computation is not part of this round; see DESIGN.md")
+        if self._w is None:
+            raise RuntimeError("MIGT has no weights: call load_state_dict() first")
+        cfg = self.config
+        ids_in = torch.as_tensor(inputs["input_ids"])
+        orig_shape = list(ids_in.shape)
+        B, T = orig_shape[0], orig_shape[1]
+        Lt, d = self.n_image_tokens, cfg.d_model
+        ids = self._in(ids_in.reshape(B, T, -1), torch.int32)
+        assert ids.shape[2] == Lt, "input_ids must hold token_image_size**2 tokens per view"
+        poses = torch.as_tensor(inputs["poses"])
+        if poses.dtype != torch.float32:
+            raise AssertionError("poses must be float32")            # tf.debugging.assert_type, migt.py:346
+        poses = self._in(poses, torch.float32)
+        Tp = poses.shape[1]
+        out_poses = inputs.get("output_poses")
+        loc_tokens = inputs.get("localization_tokens")
+        wte = self._w["wte"]
+
+        pose_rows = torch.empty((B, T, d), dtype=torch.float32, device=self.device)
+        pe = self._pose_embed(poses.reshape(B * Tp, 7)).reshape(B, Tp, d)
+        if Tp == T:
+            pose_rows = pe
+        else:
+            if not self.use_localization:
+                raise AssertionError("poses has fewer views than input_ids and the model has no localization token")
+            pose_rows[:, :Tp].copy_(pe)
+            pose_rows[:, Tp:].copy_(wte[self.localization_token])       # migt.py:387-390
+        xs = [self._embed_stream(ids, 0, pose_rows.reshape(B * T, d), B, T)]
+        gen_ptr = pose_ptr = 0
+        if out_poses is not None:
+            op = self._in(out_poses, torch.float32)
+            ope = self._pose_embed(op.reshape(B * T, 7))
+            xs.append(self._embed_stream(None, self.mask_token, ope, B, T))          # migt.py:393-396
+            gen_ptr = len(xs) - 1
+        if loc_tokens is not None:
+            lt = self._in(torch.as_tensor(loc_tokens).reshape(B, T, -1), torch.int32)
+            loc_rows = wte[self.localization_token].reshape(1, d).expand(B * T, d).contiguous()
+            xs.append(self._embed_stream(lt, 0, loc_rows, B, T))                     # migt.py:398-401
+            pose_ptr = len(xs) - 1
+        xs = self._body(xs, B, T)
+
+        out = {}
+        if last_only:
+            out["logits"] = self._lm_logits_last(xs[gen_ptr], B, T).reshape(B, 1, *orig_shape[2:], cfg.n_embeddings)
+        else:
+            out["logits"] = self._lm_logits(xs[gen_ptr]).reshape(orig_shape + [cfg.n_embeddings])
+        if self.use_localization:
+            out["pose_prediction"] = self._pose_head(xs[pose_ptr]).reshape(B, T, Lt, 7)
+        out["loss"] = 0
+        return out
+
+    def reduce_cameras(self, cameras, axis=-2):
+        """QuaternionPoseRepresentation.reduce (migt.py:150-154, 123-129): host-side, a handful of floats."""
+        from .generate import reduce_cameras
+        return reduce_cameras(cameras, axis)
+
+    # ------------------------------------------------------------------ fast inference entry points
+    def generate_codes(self, codes_ctx, poses):
+        """Context codes [B,T-1,8,8] + poses [B,T,7] (already relative/normalised) -> argmax codes of view T
+        (evaluate_transformer.py:118-123 without materialising logits of the context views)."""
+        codes_ctx = torch.as_tensor(codes_ctx)
+        B = codes_ctx.shape[0]
+        side = self.token_image_size
+        mask = torch.full((B, 1, side, side), self.mask_token, dtype=codes_ctx.dtype, device=codes_ctx.device)
+        ids = torch.cat([codes_ctx.reshape(B, -1, side, side), mask], 1)
+        logits = self({"input_ids": ids, "poses": poses}, last_only=True)["logits"]
+        return L.argmax_rows(logits.reshape(-1, self.n_embeddings)).reshape(B, side, side)

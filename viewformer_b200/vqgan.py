@@ -1,0 +1,419 @@
+"""VQGAN codebook model — B200-native drop-in for the reference's torch ``VQGAN``.
+
+Surface (same names / argument meaning / return tuples as viewformer/models/vqgan_th.py:321-398):
+    VQGAN(config).load_state_dict(sd)         reference key names, [Cout,Cin,kh,kw] conv weights, [D,K] codebook
+    .encode(x)        x f32 NCHW in [-1,1]  ->  (quant NCHW f32, diff scalar, codes int64 [N,h,w])   (:379-383)
+    .decode(quant)    NCHW f32              ->  NCHW f32                                               (:385-388)
+    .decode_code(codes)                     ->  NCHW f32                                               (:390-393)
+    .__call__(x)                            ->  (dec, diff, quant, codes)                              (:395-398)
+plus NHWC ("TF twin" convention, viewformer/models/vqgan.py:291-301) entry points ``encode_nhwc`` /
+``decode_code_nhwc`` and the uint8 end-to-end helpers used by ``generate``.
+
+Everything between the input and output tensors runs in libvf_b200 kernels on NHWC activations:
+fp32 residual stream, GroupNorm statistics in fp64, operands of the tensor-core convolutions in the
+precision's operand dtype.  No torch compute op is on the forward path (torch only allocates buffers).
+"""
+import re
+from collections import OrderedDict
+
+import torch
+
+from . import _lib as L
+from .config import VQGANConfig, load_config
+from .ops import Precision, Linear, gemm_nt, linear
+
+_IGNORE = re.compile(r"(perceptual_loss\..*)|(loss\..*)")   # vqgan_th.py:322
+
+
+class _Conv3:
+    """3x3 (or 1x1) convolution weights in both kernel layouts."""
+
+    def __init__(self, w, b, prec, device, *, exact=False):
+        cout, cin, kh, kw = w.shape
+        self.cout, self.cin, self.k = cout, cin, kh
+        w = w.to(device=device, dtype=torch.float32)
+        self.bias = b.to(device=device, dtype=torch.float32).contiguous()
+        self.tc = (not exact) and prec.use_tc and kh == 3 and cin % prec.k_align == 0 and cout % 16 == 0 and cout >= 64
+        if self.tc:
+            self.w_nk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(prec.opd).contiguous()   # [Cout, tap*Cin+c]
+        else:
+            self.w_kn = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()                # [tap*Cin+c, Cout]
+
+
+class VQGAN:
+    _ignore_checkpoint_attributes = [r"perceptual_loss\..*", r"loss\..*"]
+
+    def __init__(self, config=None, precision="bf16", device="cuda", **config_overrides):
+        if config is None:
+            config = VQGANConfig(**config_overrides)
+        self.config = load_config(config)
+        self.prec = Precision(precision)
+        self.exact = Precision("fp32")
+        self.device = torch.device(device)
+        self.training = False
+        self.learning_rate = self.config.learning_rate
+        self._sd = None
+        self._w = None
+        self.decay, self.eps = 0.99, 1e-5          # utils_th.py:9
+        self.dist_world_size = 1
+
+    # ------------------------------------------------------------------ torch-module-like plumbing
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.LibraryError("viewformer_b200.VQGAN runs on CUDA (sm_100a) only; there is no CPU path")
+        if self._sd is not None and device != self.device:
+            self.device = device
+            self.load_state_dict(self._sd)
+        self.device = device
+        return self
+
+    def cuda(self):
+        return self.to("cuda")
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def parameters(self):
+        return [v for k, v in self.state_dict().items() if not k.startswith("quantize.")]
+
+    def expected_keys(self):
+        cfg = self.config
+        keys = []
+        nres = len(cfg.ch_mult)
+        res = [cfg.image_size // 2 ** i for i in range(nres)]
+
+        def conv(n): keys.extend([n + ".weight", n + ".bias"])
+        def rb(n, cin, cout):
+            for p in ("norm1", "conv1", "norm2", "conv2"):
+                conv(n + "." + p)
+            if cin != cout:
+                conv(n + ".nin_shortcut")
+        def at(n):
+            for p in ("norm", "q", "k", "v", "proj_out"):
+                conv(n + "." + p)
+        conv("encoder.conv_in")
+        cin = cfg.ch
+        for lv in range(nres):
+            cout = cfg.ch * cfg.ch_mult[lv]
+            na = 0
+            for b in range(cfg.num_res_blocks):
+                rb(f"encoder.down.{lv}.block.{b}", cin, cout)
+                cin = cout
+                if res[lv] in cfg.attn_resolutions:
+                    at(f"encoder.down.{lv}.attn.{na}")
+                    na += 1
+            if lv != nres - 1:
+                conv(f"encoder.down.{lv}.downsample.conv")
+        rb("encoder.mid.block_1", cin, cin); at("encoder.mid.attn_1"); rb("encoder.mid.block_2", cin, cin)
+        conv("encoder.norm_out"); conv("encoder.conv_out")
+        cin = cfg.ch * cfg.ch_mult[-1]
+        conv("decoder.conv_in")
+        rb("decoder.mid.block_1", cin, cin); at("decoder.mid.attn_1"); rb("decoder.mid.block_2", cin, cin)
+        for lv in reversed(range(nres)):
+            cout = cfg.ch * cfg.ch_mult[lv]
+            na = 0
+            for b in range(cfg.num_res_blocks + 1):
+                rb(f"decoder.up.{lv}.block.{b}", cin, cout)
+                cin = cout
+                if res[lv] in cfg.attn_resolutions:
+                    at(f"decoder.up.{lv}.attn.{na}")
+                    na += 1
+            if lv != 0:
+                conv(f"decoder.up.{lv}.upsample.conv")
+        conv("decoder.norm_out"); conv("decoder.conv_out")
+        keys += ["quantize.embeddings", "quantize.ema_cluster_size_hidden", "quantize.ema_dw_hidden", "quantize.counter"]
+        conv("quant_conv"); conv("post_quant_conv")
+        return keys
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Strict key check with the reference's ignore patterns (vqgan_th.py:346-359)."""
+        sd = OrderedDict((k, v) for k, v in state_dict.items() if not _IGNORE.match(k))
+        if strict:
+            want, got = set(self.expected_keys()), set(sd.keys())
+            if want - got:
+                raise RuntimeError(f"Missing keys: {want - got}")
+            if got - want:
+                raise RuntimeError(f"Unexpected keys: {got - want}")
+        self._sd = OrderedDict((k, torch.as_tensor(v).detach().to("cpu").clone()) for k, v in sd.items())
+        self._build()
+        return self
+
+    def state_dict(self):
+        sd = OrderedDict((k, v.clone()) for k, v in self._sd.items())
+        if self._w is not None:     # training mutates the quantizer buffers on the device
+            q = self._w["q"]
+            sd["quantize.embeddings"] = q["emb"].detach().cpu().clone()
+            sd["quantize.ema_cluster_size_hidden"] = q["cs"].detach().cpu().clone()
+            sd["quantize.ema_dw_hidden"] = q["dw"].detach().cpu().clone()
+            sd["quantize.counter"] = torch.tensor(q["counter"], dtype=torch.int64)
+        return sd
+
+    # ------------------------------------------------------------------ weight preparation (load time only)
+    def _build(self):
+        L.load(require_device=True)
+        sd, prec, dev = self._sd, self.prec, self.device
+        cfg = self.config
+        w = {}
+
+        def gn(n):
+            return (sd[n + ".weight"].to(dev, torch.float32).contiguous(), sd[n + ".bias"].to(dev, torch.float32).contiguous())
+
+        def conv(n, exact=False):
+            return _Conv3(sd[n + ".weight"], sd[n + ".bias"], prec, dev, exact=exact)
+
+        def lin(n, p=None):
+            wt = sd[n + ".weight"]
+            return Linear(wt.reshape(wt.shape[0], wt.shape[1]), sd[n + ".bias"], p or prec, dev)
+
+        def rb(n):
+            d = dict(n1=gn(n + ".norm1"), c1=conv(n + ".conv1"), n2=gn(n + ".norm2"), c2=conv(n + ".conv2"))
+            if (n + ".nin_shortcut.weight") in sd:
+                d["sc"] = lin(n + ".nin_shortcut")
+            return d
+
+        def at(n):
+            wq, wk, wv = (sd[f"{n}.{p}.weight"] for p in ("q", "k", "v"))
+            c = wq.shape[0]
+            qk = Linear(torch.cat([wq.reshape(c, c), wk.reshape(c, c)], 0), torch.cat([sd[n + ".q.bias"], sd[n + ".k.bias"]]), prec, dev)
+            return dict(norm=gn(n + ".norm"), qk=qk, v=Linear(wv.reshape(c, c), sd[n + ".v.bias"], prec, dev),
+                        proj=lin(n + ".proj_out"), c=c)
+
+        nres = len(cfg.ch_mult)
+        res = [cfg.image_size // 2 ** i for i in range(nres)]
+        enc = dict(conv_in=conv("encoder.conv_in", exact=True), levels=[])
+        for lv in range(nres):
+            blocks, attns = [], []
+            for b in range(cfg.num_res_blocks):
+                blocks.append(rb(f"encoder.down.{lv}.block.{b}"))
+                if res[lv] in cfg.attn_resolutions:
+                    attns.append(at(f"encoder.down.{lv}.attn.{len(attns)}"))
+            down = conv(f"encoder.down.{lv}.downsample.conv", exact=True) if lv != nres - 1 else None
+            enc["levels"].append(dict(blocks=blocks, attns=attns, down=down))
+        enc.update(mid1=rb("encoder.mid.block_1"), mida=at("encoder.mid.attn_1"), mid2=rb("encoder.mid.block_2"),
+                   norm_out=gn("encoder.norm_out"), conv_out=conv("encoder.conv_out"))
+        dec = dict(conv_in=conv("decoder.conv_in"), mid1=rb("decoder.mid.block_1"), mida=at("decoder.mid.attn_1"),
+                   mid2=rb("decoder.mid.block_2"), levels={})
+        for lv in reversed(range(nres)):
+            blocks, attns = [], []
+            for b in range(cfg.num_res_blocks + 1):
+                blocks.append(rb(f"decoder.up.{lv}.block.{b}"))
+                if res[lv] in cfg.attn_resolutions:
+                    attns.append(at(f"decoder.up.{lv}.attn.{len(attns)}"))
+            up = conv(f"decoder.up.{lv}.upsample.conv") if lv != 0 else None
+            dec["levels"][lv] = dict(blocks=blocks, attns=attns, up=up)
+        dec.update(norm_out=gn("decoder.norm_out"), conv_out=conv("decoder.conv_out", exact=True))
+        w["enc"], w["dec"] = enc, dec
+        # 1x1 quant convs always run in exact fp32: their output feeds the bit-exact argmin
+        w["quant_conv"] = lin("quant_conv", self.exact)
+        w["post_quant_conv"] = lin("post_quant_conv", self.exact)
+        emb = sd["quantize.embeddings"].to(dev, torch.float32).contiguous()             # [D,K] (utils_th.py:17-18)
+        et, esq = L.vq_prepare_codebook(emb)
+        w["q"] = dict(emb=emb, et=et, esq=esq,
+                      cs=sd["quantize.ema_cluster_size_hidden"].to(dev, torch.float32).contiguous(),
+                      dw=sd["quantize.ema_dw_hidden"].to(dev, torch.float32).contiguous(),
+                      counter=int(sd["quantize.counter"]))
+        self._w = w
+        self._refresh_decode_table()
+
+    def _refresh_decode_table(self):
+        """decode_code only ever sees K distinct inputs to post_quant_conv: table[k] = post_quant_conv(E[:,k])."""
+        q = self._w["q"]
+        self._w["pq_table"] = linear(self.exact, q["et"], self._w["post_quant_conv"], torch.float32)
+
+    # ------------------------------------------------------------------ building blocks (NHWC f32 in / out)
+    def _conv(self, cw, x_opd_or_f32, *, residual=None, stride=1, upsample=False):
+        if cw.tc:
+            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, residual=residual)
+        pad = (1, 1) if stride == 1 else (0, 0)     # Downsample: pad (0,1,0,1) then VALID stride-2 (vqgan_th.py:45-49)
+        return L.simt_conv(x_opd_or_f32, cw.w_kn, cw.bias, kh=cw.k, stride=stride, pad=pad if cw.k == 3 else (0, 0),
+                           upsample=upsample, residual=residual)
+
+    def _act_dtype(self, cw):
+        return self.prec.opd if cw.tc else torch.float32
+
+    def _resblock(self, rbw, x):
+        a = L.groupnorm(x, *rbw["n1"], swish=True, out_dtype=self._act_dtype(rbw["c1"]))
+        h = self._conv(rbw["c1"], a)
+        a = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"]))
+        if "sc" in rbw:
+            n, hh, ww, c = x.shape
+            xs = x if self.prec.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=self.prec.opd, normalize=False)
+            res = linear(self.prec, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
+        else:
+            res = x
+        return self._conv(rbw["c2"], a, residual=res)
+
+    def _attn(self, aw, x):
+        """AttnBlock (vqgan_th.py:120-144): single head over HW tokens, logits scaled by C^-0.5."""
+        prec = self.prec
+        n, hh, ww, c = x.shape
+        hw = hh * ww
+        a = L.groupnorm(x, *aw["norm"], swish=False, out_dtype=prec.opd).reshape(n * hw, c)
+        qk = linear(prec, a, aw["qk"], prec.opd)                                      # [n*hw, 2c] = q | k
+        vt = torch.empty((n, c, hw), dtype=prec.opd, device=x.device)                 # V^T per image (K-major for P.V)
+        gemm_nt(prec, aw["v"].w, a, vt, M=c, N=hw, K=c, lda=c, ldb=c, ldc=hw, batch=(n, 1), a_bs=(0, 0),
+                b_bs=(hw * c, 0), c_bs=(c * hw, 0), bias=aw["v"].b, bias_mode=L.BIAS_M)
+        scores = torch.empty((n, hw, hw), dtype=torch.float32, device=x.device)
+        gemm_nt(prec, qk, qk, scores, M=hw, N=hw, K=c, lda=2 * c, ldb=2 * c, ldc=hw, batch=(n, 1),
+                a_bs=(hw * 2 * c, 0), b_bs=(hw * 2 * c, 0), c_bs=(hw * hw, 0), b_off=c, alpha=float(int(c) ** (-0.5)))
+        p = torch.empty((n, hw, hw), dtype=prec.opd, device=x.device)
+        L.softmax_rows(scores, p, rows_total=n * hw, rows_per_batch=hw, cols=hw, ld_in=hw, ld_out=hw)
+        o = torch.empty((n * hw, c), dtype=prec.opd, device=x.device)
+        gemm_nt(prec, p, vt, o, M=hw, N=c, K=hw, lda=hw, ldb=hw, ldc=c, batch=(n, 1), a_bs=(hw * hw, 0),
+                b_bs=(c * hw, 0), c_bs=(hw * c, 0))
+        out = linear(prec, o, aw["proj"], torch.float32, residual=x.reshape(n * hw, c))
+        return out.reshape(n, hh, ww, c)
+
+    # ------------------------------------------------------------------ encoder / decoder (NHWC)
+    def _encoder(self, x):
+        """Encoder.forward (vqgan_th.py:203-225); x f32 [N,H,W,3] -> f32 [N,h,w,z_channels]."""
+        e = self._w["enc"]
+        h = self._conv(e["conv_in"], x)
+        for lvw in e["levels"]:
+            for i, rbw in enumerate(lvw["blocks"]):
+                h = self._resblock(rbw, h)
+                if lvw["attns"]:
+                    h = self._attn(lvw["attns"][i], h)
+            if lvw["down"] is not None:
+                h = self._conv(lvw["down"], h, stride=2)
+        h = self._resblock(e["mid1"], h)
+        h = self._attn(e["mida"], h)
+        h = self._resblock(e["mid2"], h)
+        a = L.groupnorm(h, *e["norm_out"], swish=True, out_dtype=self._act_dtype(e["conv_out"]))
+        return self._conv(e["conv_out"], a)
+
+    def _decoder(self, z):
+        """Decoder.forward (vqgan_th.py:291-318); z f32 [N,h,w,z_channels] (post_quant_conv applied) -> f32 [N,H,W,3]."""
+        d = self._w["dec"]
+        cw = d["conv_in"]
+        zin = z if self._act_dtype(cw) == torch.float32 else L.groupnorm(z, None, None, swish=False, out_dtype=self.prec.opd, normalize=False)
+        h = self._conv(cw, zin)
+        h = self._resblock(d["mid1"], h)
+        h = self._attn(d["mida"], h)
+        h = self._resblock(d["mid2"], h)
+        for lv in reversed(range(len(self.config.ch_mult))):
+            lvw = d["levels"][lv]
+            for i, rbw in enumerate(lvw["blocks"]):
+                h = self._resblock(rbw, h)
+                if lvw["attns"]:
+                    h = self._attn(lvw["attns"][i], h)
+            if lvw["up"] is not None:
+                up = lvw["up"]
+                if up.tc:      # nearest x2 materialised once in the operand dtype, then the tensor-core conv
+                    hu = L.groupnorm(h, None, None, swish=False, out_dtype=self.prec.opd, normalize=False, upsample=True)
+                    h = self._conv(up, hu)
+                else:          # exact path: upsampling folded into the conv's address arithmetic
+                    h = self._conv(up, h, upsample=True)
+        a = L.groupnorm(h, *d["norm_out"], swish=True, out_dtype=self._act_dtype(d["conv_out"]))
+        return self._conv(d["conv_out"], a)
+
+    # ------------------------------------------------------------------ quantizer
+    def _quantize(self, z_rows, want_quant=True):
+        """QuantizeEMA.forward (utils_th.py:32-68) on rows [M,D]; returns (quant rows | None, diff, idx)."""
+        q = self._w["q"]
+        idx, quant, dsum = L.vq_lookup(z_rows, q["et"], q["esq"], want_quant=want_quant, want_diff=True)
+        if self.training:
+            self._ema_update(z_rows, idx)
+        diff = (dsum / float(z_rows.numel())).to(torch.float32).reshape(())
+        return quant, diff, idx
+
+    def _ema_update(self, z_rows, idx):
+        """Training branch, utils_th.py:46-64: counts / embed_sum (+ one packed all-reduce), EMA, renormalise."""
+        q = self._w["q"]
+        d, k = q["emb"].shape
+        counts, esum = L.vq_ema_stats(z_rows, idx, k)
+        if self.dist_world_size > 1:
+            packed = torch.cat([counts, esum.reshape(-1)])          # one NCCL call instead of the reference's two
+            torch.distributed.all_reduce(packed)
+            counts, esum = packed[:k].contiguous(), packed[k:].reshape(d, k).contiguous()
+        q["counter"] += 1
+        corr = float(1.0 - torch.pow(torch.tensor(self.decay), torch.tensor(q["counter"], dtype=torch.int64)))
+        alpha = 1 - self.decay
+        L.vq_ema_update(counts, esum, alpha, corr, self.eps, q["cs"], q["dw"], q["emb"], q["et"], q["esq"])
+        self._refresh_decode_table()
+
+    # ------------------------------------------------------------------ NHWC entry points (TF-twin convention)
+    def _in(self, x, dtype=torch.float32):
+        t = torch.as_tensor(x)
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+        return t
+
+    def encode_rows(self, x_nhwc):
+        """f32 NHWC images -> (z rows [N*h*w, D], h, w)"""
+        z = self._encoder(x_nhwc)
+        n, hh, ww, c = z.shape
+        zr = linear(self.exact, z.reshape(n * hh * ww, c), self._w["quant_conv"], torch.float32)
+        return zr, hh, ww
+
+    def encode_nhwc(self, x_nhwc):
+        """TF-twin convention (viewformer/models/vqgan.py:291-295): NHWC in, (quant NHWC, diff, codes [N,h,w])."""
+        self._need_weights()
+        x = self._in(x_nhwc)
+        zr, hh, ww = self.encode_rows(x)
+        n = x.shape[0]
+        quant, diff, idx = self._quantize(zr)
+        return quant.reshape(n, hh, ww, -1), diff, idx.reshape(n, hh, ww)
+
+    def encode_u8(self, images_u8_nhwc):
+        """uint8 NHWC images -> codes int64 [N,h,w] (evaluate_transformer.py:105-110 in one device pass)."""
+        self._need_weights()
+        x = L.u8_to_unit(self._in(images_u8_nhwc, torch.uint8))
+        zr, hh, ww = self.encode_rows(x)
+        _, _, idx = self._quantize(zr, want_quant=False)
+        return idx.reshape(x.shape[0], hh, ww)
+
+    def decode_code_nhwc(self, codes):
+        self._need_weights()
+        codes = self._in(codes, torch.int64)
+        n, hh, ww = codes.shape
+        z = L.gather_rows(self._w["pq_table"], codes.reshape(-1)).reshape(n, hh, ww, -1)
+        return self._decoder(z)
+
+    def decode_code_u8(self, codes):
+        """codes -> uint8 NHWC images (clip, /2+.5, ->uint8; evaluate_transformer.py:127-129)."""
+        return L.unit_to_u8(self.decode_code_nhwc(codes))
+
+    # ------------------------------------------------------------------ torch-flavour (NCHW) surface
+    def _need_weights(self):
+        if self._w is None:
+            raise RuntimeError("VQGAN has no weights: call load_state_dict() first")
+
+    def encode(self, x):
+        self._need_weights()
+        x = L.nchw_to_nhwc(self._in(x))
+        zr, hh, ww = self.encode_rows(x)
+        n = x.shape[0]
+        quant, diff, idx = self._quantize(zr)
+        return L.nhwc_to_nchw(quant.reshape(n, hh, ww, -1)), diff, idx.reshape(n, hh, ww)
+
+    def decode(self, quant):
+        self._need_weights()
+        q = L.nchw_to_nhwc(self._in(quant))
+        n, hh, ww, c = q.shape
+        z = linear(self.exact, q.reshape(-1, c), self._w["post_quant_conv"], torch.float32).reshape(n, hh, ww, -1)
+        return L.nhwc_to_nchw(self._decoder(z))
+
+    def decode_code(self, code_b):
+        return L.nhwc_to_nchw(self.decode_code_nhwc(code_b))
+
+    def forward(self, input):
+        quant, diff, idx = self.encode(input)
+        return self.decode(quant), diff, quant, idx
+
+    __call__ = forward
+
+    def embed_code(self, embed_id):
+        """utils_th.py:70-72: ids [N,h,w] -> [N,D,h,w]."""
+        ids = self._in(embed_id, torch.int64)
+        n, hh, ww = ids.shape
+        return L.nhwc_to_nchw(L.gather_rows(self._w["q"]["et"], ids.reshape(-1)).reshape(n, hh, ww, -1))
+
+    def configure_optimizers(self):
+        raise NotImplementedError("codebook training (VQGAN.training_step) is not part of this round; see DESIGN.md")
