@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — novel views/sec of the ViewFormer hot path on B200 (BASELINE.json metric, config 2).
+
+One "step" = one pass of generate() over a batch of synthetic scenes:
+    uint8 images [B, 10, 128, 128, 3] + cameras [B, 10, 7]
+      -> VQ-encode the 9 context views -> MIGT forward (mask tokens in view 10) -> argmax -> VQ-decode
+      -> uint8 novel view [B, 128, 128, 3]                     (evaluate/evaluate_transformer.py:97-146)
+B = 32 scenes per GPU (BASELINE.json configs[1]); N GPUs run N independent shards (weak scaling, no collective on
+the data path — scenes are independent).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...     # the reference algorithm on the host CPU cores (torch-CPU oracle)
+
+Prints ONE JSON line (rank 0).  `value` = views/s with inputs resident in HBM; `e2e` = same metric through the public
+generate() call with pinned-host inputs, H2D/D2H inside the timed region; `roofline` = the dominant kernel
+(tcgen05 implicit-GEMM 3x3 conv 128->128 @128x128) timed alone with CUDA events against the measured bf16 peak;
+`cpu_baseline` = the oracle timed on a bounded sample on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_CTX = 9
+T_VIEWS = N_CTX + 1
+IMG = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenes", type=int, default=32, help="scenes per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- helpers
+def synth_inputs(n_scenes, seed):
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.rand((n_scenes * T_VIEWS, 3, IMG // 8, IMG // 8), generator=g)
+    x = torch.nn.functional.interpolate(lo, size=(IMG, IMG), mode="bilinear", align_corners=False)
+    x = x + 0.08 * torch.randn(x.shape, generator=g)
+    images = (x.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).reshape(n_scenes, T_VIEWS, IMG, IMG, 3).contiguous()
+    xyz = torch.randn((n_scenes, T_VIEWS, 3), generator=g)
+    q = torch.randn((n_scenes, T_VIEWS, 4), generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    q = q * torch.where(q[..., :1] >= 0, 1.0, -1.0)
+    return images, torch.cat([xyz, q], -1).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_views_per_s(n_scenes, steps, warmup, vq_sd, migt_sd, vcfg, tcfg):
+    """The reference's algorithm (oracle restatement; the real torch/TF reference cannot travel to the GPU box) on the
+    host cores: generate_batch_predictions, 10 encodes + dense masked attention + full-sequence LM head as the
+    reference executes them (evaluate_transformer.py:97-146)."""
+    from oracle import vqgan_oracle as vo, migt_oracle as mo
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    images, cams = synth_inputs(n_scenes, 777)
+    fwd = lambda d: mo.forward(migt_sd, tcfg, d, use_localization=False)
+    enc = lambda x: vo.encode(vq_sd, vcfg, x)[2]
+    dec = lambda c: vo.decode_code(vq_sd, vcfg, c)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            mo.generate_batch_predictions(fwd, enc, dec, tcfg, images, cams, use_localization=False)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return n_scenes * len(times) / total, total / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from viewformer_b200.config import VQGANConfig, MIGTConfig
+    from oracle import synth
+    vcfg, tcfg = VQGANConfig(), MIGTConfig(localization_weight="0")
+    vq_sd, migt_sd = synth.make_vqgan_state_dict(vcfg, 0), synth.make_migt_state_dict(tcfg, 0)
+    n = max(1, args.cpu_scenes)
+    vps, sec, cores = cpu_reference_views_per_s(n, args.steps, min(args.warmup, 1), vq_sd, migt_sd, vcfg, tcfg)
+    sample = f"{n} scenes x {T_VIEWS} views per step (bounded sample of the {args.scenes}-scene workload), torch-CPU fp32 oracle"
+    print(json.dumps({
+        "impl": "reference", "metric": "novel views/sec (128x128, 9-ctx)", "value": vps, "unit": "views/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "interiornet-transformer generate(), 9 context views (BASELINE configs[1])", "scenes_per_step": n,
+                   "localization": False},
+        "cpu_baseline": {"value": vps, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    from viewformer_b200 import VQGAN, MIGT, generate_batch_predictions, _lib
+    from viewformer_b200.config import VQGANConfig, MIGTConfig
+    vcfg, tcfg = VQGANConfig(), MIGTConfig(localization_weight="0")
+    codebook = VQGAN(vcfg, precision=args.precision, device=dev).init_weights(0)
+    transformer = MIGT(tcfg, precision=args.precision, device=dev).init_weights(0)
+
+    B = args.scenes
+    images_h, cams_h = synth_inputs(B, 1234 + rank)
+    images_pin, cams_pin = images_h.pin_memory(), cams_h.pin_memory()
+    images_d, cams_d = images_h.to(dev), cams_h.to(dev)
+    out_pin = torch.empty((B, IMG, IMG, 3), dtype=torch.uint8).pin_memory()
+
+    def step_resident():
+        return generate_batch_predictions(transformer, codebook, images_d, cams_d)
+
+    def step_e2e():
+        img = images_pin.to(dev, non_blocking=True)
+        cam = cams_pin.to(dev, non_blocking=True)
+        r = generate_batch_predictions(transformer, codebook, img, cam)
+        out_pin.copy_(r["generated_images"], non_blocking=True)
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    _lib.reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    views = world * B * args.steps
+    value = views / (ms_total / 1e3)
+    e2e_value = views / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: tcgen05 implicit-GEMM conv 128->128 3x3 at 128x128, the launch the encoder issues
+    roof = None
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    if world == 1 or True:
+        n_img = B * N_CTX
+        opd = torch.bfloat16 if args.precision == "bf16" else torch.float32
+        if args.precision != "fp32":
+            x = torch.randn((n_img, IMG, IMG, 128), device=dev).to(opd)
+            w = (torch.randn((128, 9 * 128), device=dev) / 34.0).to(opd)
+            b = torch.zeros(128, device=dev)
+            o = torch.empty((n_img, IMG, IMG, 128), device=dev)
+            for _ in range(3):
+                _lib.tc_conv(x, w, b, out=o)
+            reps = 5
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                _lib.tc_conv(x, w, b, out=o)
+            e1.record()
+            torch.cuda.synchronize()
+            sec = e0.elapsed_time(e1) / 1e3 / reps
+            flops = 2.0 * n_img * IMG * IMG * 128 * 9 * 128          # 2*M*N*K of the implicit GEMM
+            ach = flops / sec / 1e12
+            if args.precision == "tf32":
+                peak_tf = peak_tf / 2
+            roof = {"kernel": "tc_gemm_kernel<128,6> (3x3 conv 128->128 @128x128, %d images/launch)" % n_img, "bound": "tensor",
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": peak_src, "launch_ms": sec * 1e3,
+                    "algorithmic_bytes_per_launch": n_img * IMG * IMG * 128 * (opd.itemsize + 4)}
+            del x, w, o
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        vq_sd, migt_sd = codebook.state_dict(), transformer.state_dict()
+        n = max(1, args.cpu_scenes)
+        vps, sec, cores = cpu_reference_views_per_s(n, 1, 1, vq_sd, migt_sd, vcfg, tcfg)
+        cpu = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
+               "sample": f"{n} scenes x {T_VIEWS} views, 1 timed pass after 1 warm-up, torch-CPU fp32 oracle of the reference algorithm "
+                         f"(10 encodes, dense masked attention, full LM head)"}
+
+    in_bytes = images_pin.numel() + cams_pin.numel() * 4
+    print(json.dumps({
+        "metric": "novel views/sec (128x128, 9-ctx)", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "interiornet-transformer generate(), 9 context views, batch 32 scenes per GPU (BASELINE configs[1]): "
+                               "uint8 images -> VQ-encode 9 ctx -> MIGT -> argmax -> VQ-decode -> uint8 view",
+                   "scenes_per_gpu": B, "views": T_VIEWS, "image": IMG, "localization": False, "parallelism": f"dp{world} (independent shards)",
+                   "l2": "inputs larger than L2 (15.7 MB images + 2.4 GB activations per step); no flush needed"},
+        "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(in_bytes),
+                "d2h_bytes_per_step": int(out_pin.numel())},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -225,3 +225,15 @@ def make_cameras(n_scenes, n_views, seed=4321):
 def make_codes(n_scenes, n_views, n_embed=1024, side=8, seed=99):
     g = _gen(seed)
     return torch.randint(0, n_embed, (n_scenes, n_views, side, side), generator=g, dtype=torch.int64)
+
+
+def make_lookup_inputs(seed=11, D=256, K=1024):
+    """Codebook E [D,K] and rows z for the nearest-neighbour fixtures (tests/golden/vq_lookup.npz):
+    4096 gaussian rows, 512 adversarial near-ties (midpoints of two codes + 1e-3 noise), 64 exact codes."""
+    g = _gen(seed)
+    E = _uniform((D, K), math.sqrt(3.0), g)
+    z = torch.randn((4096, D), generator=g)
+    a = torch.randint(0, K, (512,), generator=g)
+    b = torch.randint(0, K, (512,), generator=g)
+    mid = 0.5 * (E[:, a] + E[:, b]).t() + 1e-3 * torch.randn((512, D), generator=g)
+    return E, torch.cat([z, mid, E[:, :64].t().contiguous()], 0).contiguous()

@@ -1,0 +1,326 @@
+"""Per-kernel parity (GPU): every libvf_b200 entry point against a plain PyTorch fp32/fp64 CPU computation of the
+same op, called through the C-ABI (viewformer_b200._lib helpers pass raw pointers + stream)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L(lib):
+    from viewformer_b200 import _lib
+    _lib.load(require_device=True)
+    return _lib
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def report(name, got, want, atol, rtol):
+    got, want = got.double().cpu(), want.double().cpu()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = int((err > tol).sum())
+    print(f"[{name}] max_abs_err={err.max():.3e} ref_scale={want.abs().mean():.3e} bad={bad}/{err.numel()}")
+    if bad:
+        i = int((err - tol).argmax())
+        print(f"   worst at flat index {i}: got {got.reshape(-1)[i]:.6f} want {want.reshape(-1)[i]:.6f}")
+    assert bad == 0, f"{name}: {bad} elements out of tolerance (max err {err.max():.3e})"
+
+
+# ----------------------------------------------------------------------------- pixels / layout
+def test_pixel_conversions(L):
+    u8 = torch.randint(0, 256, (3, 16, 16, 3), generator=g(0), dtype=torch.uint8)
+    got = L.u8_to_unit(u8.cuda())
+    want = u8.float() * torch.tensor(1.0 / 255.0) * 2 - 1
+    assert torch.equal(got.cpu(), want)
+    x = torch.randn(5, 7, 9, 3, generator=g(1)) * 0.8
+    got = L.unit_to_u8(x.cuda())
+    want = ((x.clamp(-1, 1) / 2 + 0.5) * 255.5).clamp(0, 255).to(torch.uint8)
+    assert torch.equal(got.cpu(), want)
+    y = torch.randn(2, 5, 6, 7, generator=g(2))
+    assert torch.equal(L.nchw_to_nhwc(y.cuda()).cpu(), y.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(L.nhwc_to_nchw(y.permute(0, 2, 3, 1).contiguous().cuda()).cpu(), y)
+
+
+# ----------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("C,H,W", [(128, 16, 16), (256, 8, 8), (512, 4, 4), (32, 8, 8), (64, 5, 7)])
+def test_groupnorm(L, C, H, W):
+    x = torch.randn(3, C, H, W, generator=g(C)) * 2 + 0.5
+    ga, be = 1 + 0.1 * torch.randn(C, generator=g(1)), 0.1 * torch.randn(C, generator=g(2))
+    want = F.group_norm(x.double(), 32, ga.double(), be.double(), eps=1e-6)
+    want_s = want * torch.sigmoid(want)
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got = L.groupnorm(xh, ga.cuda(), be.cuda(), swish=False, out_dtype=torch.float32)
+    report("gn", got.permute(0, 3, 1, 2), want, 2e-5, 1e-5)
+    got = L.groupnorm(xh, ga.cuda(), be.cuda(), swish=True, out_dtype=torch.float32)
+    report("gn+swish", got.permute(0, 3, 1, 2), want_s, 2e-5, 1e-5)
+    got = L.groupnorm(xh, ga.cuda(), be.cuda(), swish=True, out_dtype=torch.bfloat16)
+    report("gn+swish bf16", got.float().permute(0, 3, 1, 2), want_s, 2e-2, 1e-2)
+    got = L.groupnorm(xh, None, None, swish=False, out_dtype=torch.float32, normalize=False, upsample=True)
+    report("upsample", got.permute(0, 3, 1, 2), F.interpolate(x, scale_factor=2.0, mode="nearest"), 0, 0)
+
+
+def test_layernorm(L):
+    x = torch.randn(70, 768, generator=g(3)) * 3 + 1
+    ga, be = 1 + 0.1 * torch.randn(768, generator=g(4)), 0.1 * torch.randn(768, generator=g(5))
+    want = F.layer_norm(x.double(), (768,), ga.double(), be.double(), 1e-5)
+    report("ln f32", L.layernorm(x.cuda(), ga.cuda(), be.cuda(), torch.float32), want, 2e-5, 1e-5)
+    report("ln bf16", L.layernorm(x.cuda(), ga.cuda(), be.cuda(), torch.bfloat16).float(), want, 2e-2, 1e-2)
+    x = torch.randn(9, 128, generator=g(6))
+    want = F.layer_norm(x.double(), (128,), ga[:128].double(), be[:128].double(), 1e-5)
+    report("ln d128", L.layernorm(x.cuda(), ga[:128].contiguous().cuda(), be[:128].contiguous().cuda(), torch.float32), want, 2e-5, 1e-5)
+
+
+# ----------------------------------------------------------------------------- SIMT conv / gemm
+def _w_kn(w):
+    return w.permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,hw,k,mode", [(3, 128, 20, 3, "same"), (128, 3, 12, 3, "same"), (64, 96, 9, 3, "same"),
+                                                 (64, 64, 10, 3, "down"), (32, 48, 6, 3, "up"), (72, 40, 7, 1, "same")])
+def test_simt_conv(L, cin, cout, hw, k, mode):
+    x = torch.randn(2, cin, hw, hw, generator=g(cin + cout))
+    w = torch.randn(cout, cin, k, k, generator=g(7)) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g(8))
+    xd = x.double()
+    if mode == "down":
+        want = F.conv2d(F.pad(xd, (0, 1, 0, 1)), w.double(), b.double(), stride=2)
+        kw = dict(stride=2, pad=(0, 0))
+    elif mode == "up":
+        want = F.conv2d(F.interpolate(xd, scale_factor=2.0, mode="nearest"), w.double(), b.double(), padding=1)
+        kw = dict(upsample=True)
+    else:
+        want = F.conv2d(xd, w.double(), b.double(), padding=k // 2)
+        kw = dict(pad=(k // 2, k // 2))
+    res = torch.randn(want.shape, generator=g(9))
+    got = L.simt_conv(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w).cuda(), b.cuda(), kh=k,
+                      residual=res.permute(0, 2, 3, 1).contiguous().cuda(), **kw)
+    report(f"simt_conv {mode}", got.permute(0, 3, 1, 2), want + res.double(), 2e-5, 1e-5)
+
+
+def test_simt_gemm_batched_strided(L):
+    B1, B2, M, N, K = 2, 3, 70, 50, 37
+    A = torch.randn(B1, B2, M, K, generator=g(10))
+    Bm = torch.randn(B1, B2, N, K, generator=g(11))
+    bias = torch.randn(M, generator=g(12))
+    want = torch.einsum("abmk,abnk->abmn", A.double(), Bm.double()) * 0.5 + bias.double()[None, None, :, None]
+    out = torch.empty(B1, B2, M, N, device="cuda")
+    L.simt_gemm(A.cuda(), Bm.cuda(), out, M=M, N=N, K=K, a_strides=(K, 1), b_strides=(1, K), ldc=N, batch=(B1, B2),
+                a_bs=(B2 * M * K, M * K), b_bs=(B2 * N * K, N * K), c_bs=(B2 * M * N, M * N), alpha=0.5, bias=bias.cuda(),
+                bias_mode=L.BIAS_M)
+    report("simt_gemm", out, want, 2e-5, 1e-5)
+
+
+# ----------------------------------------------------------------------------- tcgen05 GEMM
+def _tc_case(L, dtype, M, N, K, batch=(1, 1), bias_mode=0, act=0, residual=False, alpha=1.0, out_dtype=torch.float32, seed=0):
+    B1, B2 = batch
+    A = torch.randn(B1, B2, M, K, generator=g(seed))
+    Bm = torch.randn(B1, B2, N, K, generator=g(seed + 1)) / K ** 0.5
+    Aq, Bq = A.to(dtype).cuda(), Bm.to(dtype).cuda()
+    Ar, Br = Aq.double().cpu(), Bq.double().cpu()
+    if dtype == torch.float32:      # TF32 truncates mantissas to 10 bits inside the tensor core
+        def trunc(t):
+            return (t.float().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        Ar, Br = trunc(Ar), trunc(Br)
+    want = torch.einsum("abmk,abnk->abmn", Ar, Br) * alpha
+    bias = None
+    if bias_mode == 1:
+        bias = torch.randn(N, generator=g(seed + 2)); want = want + bias.double()
+    elif bias_mode == 2:
+        bias = torch.randn(M, generator=g(seed + 2)); want = want + bias.double()[:, None]
+    if act:
+        want = F.gelu(want)
+    res = None
+    if residual:
+        res = torch.randn(B1, B2, M, N, generator=g(seed + 3)); want = want + res.double()
+    out = torch.full((B1, B2, M, N), float("nan"), dtype=out_dtype, device="cuda")
+    L.tc_gemm(Aq, Bq, out, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, batch=batch, a_bs=(B2 * M * K, M * K), b_bs=(B2 * N * K, N * K),
+              c_bs=(B2 * M * N, M * N), alpha=alpha, bias=None if bias is None else bias.cuda(), bias_mode=bias_mode, act=act,
+              residual=None if res is None else res.cuda())
+    torch.cuda.synchronize()
+    tol = 2e-2 if out_dtype == torch.bfloat16 else (2e-3 if dtype == torch.bfloat16 else 2e-3)
+    report(f"tc_gemm {dtype} M{M} N{N} K{K} b{batch} bias{bias_mode} act{act} res{residual}", out.float(), want, tol, tol)
+
+
+def test_tc_gemm_single_tile_bf16(L):
+    _tc_case(L, torch.bfloat16, 128, 128, 64)
+
+
+def test_tc_gemm_k_loop_bf16(L):
+    _tc_case(L, torch.bfloat16, 128, 128, 1024, seed=3)      # > kStages k-blocks: exercises ring wrap + phases
+
+
+def test_tc_gemm_multi_tile_bf16(L):
+    _tc_case(L, torch.bfloat16, 512, 384, 256, seed=5)
+
+
+def test_tc_gemm_tails_bf16(L):
+    _tc_case(L, torch.bfloat16, 200, 72, 136, seed=7)          # M, N, K tails
+    _tc_case(L, torch.bfloat16, 64, 40, 64, seed=8)            # BLOCK_N = 64 variant, M < 128
+
+
+def test_tc_gemm_epilogues_bf16(L):
+    _tc_case(L, torch.bfloat16, 256, 256, 192, bias_mode=1, act=1, seed=9)
+    _tc_case(L, torch.bfloat16, 256, 128, 192, bias_mode=2, residual=True, alpha=0.25, seed=10)
+    _tc_case(L, torch.bfloat16, 256, 128, 192, bias_mode=1, out_dtype=torch.bfloat16, seed=11)
+
+
+def test_tc_gemm_batched_bf16(L):
+    _tc_case(L, torch.bfloat16, 192, 128, 128, batch=(2, 3), bias_mode=1, seed=12)
+
+
+def test_tc_gemm_tf32(L):
+    _tc_case(L, torch.float32, 128, 128, 32, seed=13)
+    _tc_case(L, torch.float32, 300, 200, 416, bias_mode=1, residual=True, seed=14)
+
+
+def test_tc_gemm_broadcast_and_offsets(L):
+    """shared A (weights) across the batch, bias along M, column-offset output: the V^T projection pattern."""
+    Bn, d, S = 3, 128, 192
+    W = (torch.randn(d, d, generator=g(20)) / d ** 0.5).bfloat16().cuda()
+    X = torch.randn(Bn, S, d, generator=g(21)).bfloat16().cuda()
+    bias = torch.randn(d, generator=g(22))
+    out = torch.zeros(Bn, d, 2 * S, dtype=torch.bfloat16, device="cuda")
+    L.tc_gemm(W, X, out, M=d, N=S, K=d, lda=d, ldb=d, ldc=2 * S, batch=(Bn, 1), a_bs=(0, 0), b_bs=(S * d, 0),
+              c_bs=(d * 2 * S, 0), c_off=S, bias=bias.cuda(), bias_mode=L.BIAS_M)
+    want = torch.einsum("mk,bnk->bmn", W.double().cpu(), X.double().cpu()) + bias.double()[None, :, None]
+    report("tc_gemm bcast", out[:, :, S:].float(), want, 3e-2, 2e-2)
+    assert float(out[:, :, :S].abs().max()) == 0.0
+
+
+def test_tc_gemm_causal(L):
+    """block-causal k-limit (P.V) and n-tile skipping (QK^T) give the same visible values as the dense product."""
+    S, dh, blk = 384, 64, 64
+    q = torch.randn(S, dh, generator=g(30)).bfloat16().cuda()
+    k = torch.randn(S, dh, generator=g(31)).bfloat16().cuda()
+    sc = torch.full((S, S), float("nan"), device="cuda")
+    L.tc_gemm(q, k, sc, M=S, N=S, K=dh, lda=dh, ldb=dh, ldc=S, causal_block=blk, causal_skip_n=True)
+    want = q.double().cpu() @ k.double().cpu().t()
+    view = torch.arange(S) // blk
+    vis = view[:, None] >= view[None, :]
+    got = sc.cpu().double()
+    assert torch.isfinite(got[vis]).all()
+    report("qk causal", torch.where(vis, got, torch.zeros_like(got)), torch.where(vis, want, torch.zeros_like(want)), 2e-2, 1e-2)
+    p = torch.rand(S, S, generator=g(32)) * vis
+    vt = torch.randn(dh, S, generator=g(33)).bfloat16().cuda()
+    o = torch.empty(S, dh, device="cuda")
+    L.tc_gemm(p.bfloat16().cuda(), vt, o, M=S, N=dh, K=S, lda=S, ldb=S, ldc=dh, causal_block=blk)
+    report("pv causal", o, p.bfloat16().double() @ vt.double().cpu().t(), 2e-2, 1e-2)
+
+
+# ----------------------------------------------------------------------------- tcgen05 conv
+@pytest.mark.parametrize("dtype,cin,cout,n,hw", [(torch.bfloat16, 64, 128, 2, 16), (torch.bfloat16, 128, 128, 1, 32),
+                                                  (torch.bfloat16, 256, 64, 3, 8), (torch.bfloat16, 128, 256, 2, 4),
+                                                  (torch.float32, 64, 128, 2, 16), (torch.bfloat16, 128, 128, 1, 20)])
+def test_tc_conv3x3(L, dtype, cin, cout, n, hw):
+    x = torch.randn(n, cin, hw, hw, generator=g(cin + hw)).to(dtype)
+    w = (torch.randn(cout, cin, 3, 3, generator=g(40)) / (9 * cin) ** 0.5).to(dtype)
+    b = torch.randn(cout, generator=g(41))
+    res = torch.randn(n, cout, hw, hw, generator=g(42))
+    xr, wr = x.double(), w.double()
+    if dtype == torch.float32:
+        tr = lambda t: (t.float().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        xr, wr = tr(x), tr(w)
+    want = F.conv2d(xr, wr, b.double(), padding=1) + res.double()
+    w_nk = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous().cuda()
+    got = L.tc_conv(x.permute(0, 2, 3, 1).contiguous().cuda(), w_nk, b.cuda(), residual=res.permute(0, 2, 3, 1).contiguous().cuda())
+    torch.cuda.synchronize()
+    report(f"tc_conv {dtype} {cin}->{cout} n{n} hw{hw}", got.permute(0, 3, 1, 2), want, 3e-3, 3e-3)
+
+
+# ----------------------------------------------------------------------------- codebook
+def test_vq_lookup_bit_exact_vs_reference_golden(L, golden_dir):
+    import os
+    from oracle import synth
+    gd = np.load(os.path.join(golden_dir, "vq_lookup.npz"))
+    E, z = synth.make_lookup_inputs(int(gd["seed"]))
+    et, esq = L.vq_prepare_codebook(E.cuda())
+    assert torch.equal(et.cpu(), E.t().contiguous())
+    idx, quant, dsum = L.vq_lookup(z.cuda(), et, esq)
+    idx = idx.cpu().numpy()
+    mism = int((idx != gd["idx"]).sum())
+    print(f"[vq_lookup] mismatches vs reference fp32 expression: {mism}/{idx.size}; vs fp64: {int((idx != gd['idx_f64']).sum())}")
+    assert np.array_equal(idx, gd["idx"])
+    e = E.t()[torch.from_numpy(idx)]
+    assert torch.equal(quant.cpu(), z + (e - z))                        # straight-through value, utils_th.py:67
+    want = float(((e - z).double() ** 2).sum())
+    assert abs(float(dsum) - want) / want < 1e-6
+    # ragged M (not a multiple of the 64-row tile) and M = 0
+    idx2, _, _ = L.vq_lookup(z[:77].contiguous().cuda(), et, esq)
+    assert np.array_equal(idx2.cpu().numpy(), gd["idx"][:77])
+    idx0, _, _ = L.vq_lookup(z[:0].contiguous().cuda(), et, esq)
+    assert idx0.numel() == 0
+
+
+def test_gather_rows(L):
+    t = torch.randn(50, 64, generator=g(50))
+    i = torch.randint(0, 50, (33,), generator=g(51))
+    assert torch.equal(L.gather_rows(t.cuda(), i.cuda()).cpu(), t[i])
+
+
+def test_vq_ema_matches_reference_golden(L, golden_dir):
+    import os
+    gd = np.load(os.path.join(golden_dir, "quantizer.npz"))
+    E, z = torch.from_numpy(gd["E"]).cuda(), torch.from_numpy(gd["z"])
+    D, K = E.shape
+    zr = z.permute(0, 2, 3, 1).reshape(-1, D).contiguous().cuda()
+    emb = E.clone()
+    et, esq = L.vq_prepare_codebook(emb)
+    cs, dw = torch.zeros(K, device="cuda"), torch.zeros(D, K, device="cuda")
+    for step in range(2):
+        idx, _, dsum = L.vq_lookup(zr, et, esq)
+        assert np.array_equal(idx.cpu().numpy().reshape(gd[f"ids{step}"].shape), gd[f"ids{step}"])
+        np.testing.assert_allclose(float(dsum) / zr.numel(), float(gd[f"diff{step}"]), rtol=1e-5)
+        counts, esum = L.vq_ema_stats(zr, idx, K)
+        corr = float(1.0 - torch.pow(torch.tensor(0.99), torch.tensor(step + 1)))
+        L.vq_ema_update(counts, esum, 1 - 0.99, corr, 1e-5, cs, dw, emb, et, esq)
+        np.testing.assert_allclose(cs.cpu().numpy(), gd[f"cs{step}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(dw.cpu().numpy(), gd[f"dw{step}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(emb.cpu().numpy(), gd[f"emb{step}"], rtol=2e-5, atol=1e-5)
+        assert torch.equal(et.cpu(), emb.t().contiguous().cpu())
+
+
+# ----------------------------------------------------------------------------- transformer glue
+def test_softmax_masks_and_argmax(L):
+    S, blk = 192, 64
+    sc = torch.randn(2 * S, S, generator=g(60)) * 4
+    view = torch.arange(S) // blk
+    m = (view[:, None] >= view[None, :]).float().repeat(2, 1)
+    w = sc * m - 1e4 * (1 - m)                       # branching_attention.py:13
+    want = F.softmax(w.double(), -1)
+    p = torch.empty(2 * S, S, device="cuda")
+    L.softmax_rows(sc.cuda(), p, rows_total=2 * S, rows_per_batch=S, cols=S, ld_in=S, ld_out=S, mask_mode=1, block=blk)
+    report("softmax causal", p, want, 1e-6, 1e-5)
+    # multi-end mask (branching_attention.py:96-124)
+    sc2 = torch.randn(S, 2 * S, generator=g(61)) * 3
+    m_old = (view[:, None] > view[None, :]).float()
+    m_new = (view[:, None] == view[None, :]).float()
+    w2 = torch.cat([sc2[:, :S] * m_old - 1e4 * (1 - m_old), torch.where(m_new > 0, sc2[:, S:], torch.full_like(sc2[:, S:], -1e30))], 1)
+    want2 = F.softmax(w2.double(), -1)
+    p2 = torch.empty(S, 2 * S, device="cuda")
+    L.softmax_rows(sc2.cuda(), p2, rows_total=S, rows_per_batch=S, cols=2 * S, ld_in=2 * S, ld_out=2 * S, mask_mode=2, block=blk)
+    report("softmax multiend", p2, want2, 1e-6, 1e-5)
+    x = torch.randn(37, 1024, generator=g(62))
+    x[3, 10] = x[3, 900] = 50.0                       # tie -> first index
+    assert torch.equal(L.argmax_rows(x.cuda()).cpu(), x.argmax(-1))
+    assert int(L.argmax_rows(x.cuda())[3]) == 10
+
+
+def test_embed_and_pose_post(L):
+    from oracle import migt_oracle as mo
+    wte, wpe = torch.randn(1026, 64, generator=g(70)), torch.randn(256, 64, generator=g(71))
+    ids = torch.randint(0, 1026, (3, 2, 64), generator=g(72), dtype=torch.int32)
+    pose = torch.randn(6, 64, generator=g(73))
+    got = L.migt_embed(ids.cuda(), 0, wte.cuda(), wpe.cuda(), pose.cuda(), 6, 64)
+    want = wte[ids.long()] + wpe[:64][None, None] + pose.reshape(3, 2, 1, 64)
+    assert torch.equal(got.cpu().reshape(3, 2, 64, 64), want)
+    got = L.migt_embed(None, 1024, wte.cuda(), wpe.cuda(), pose.cuda(), 6, 64)
+    assert torch.equal(got.cpu().reshape(3, 2, 64, 64), wte[1024] + wpe[:64][None, None] + pose.reshape(3, 2, 1, 64))
+    raw = torch.randn(40, 7, generator=g(74))
+    got = L.pose_postprocess(raw.cuda(), 2.0).cpu()
+    want = torch.cat([raw[:, :3] / 2.0, mo.quaternion_remove_sign(mo.quaternion_normalize(raw[:, 3:]))], -1)
+    report("pose_post", got, want, 1e-6, 1e-6)

@@ -80,23 +80,12 @@ def test_quantizer_training_branch_matches_reference_golden(golden_dir):
     np.testing.assert_allclose(float(loss), float(g["commit_loss"]), rtol=1e-6)
 
 
-def _lookup_inputs(seed=11):
-    g = torch.Generator().manual_seed(seed)
-    D, K = 256, 1024
-    E = synth._uniform((D, K), 3 ** 0.5, g)
-    z = torch.randn((4096, D), generator=g)
-    a = torch.randint(0, K, (512,), generator=g)
-    b = torch.randint(0, K, (512,), generator=g)
-    mid = 0.5 * (E[:, a] + E[:, b]).t() + 1e-3 * torch.randn((512, D), generator=g)
-    return E, torch.cat([z, mid, E[:, :64].t().contiguous()], 0).contiguous()
-
-
 def test_c_lookup_oracle_matches_reference_expression(golden_dir):
     import subprocess
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvq_oracle.so"))
     g = _g(golden_dir, "vq_lookup.npz")
-    E, z = _lookup_inputs(int(g["seed"]))
+    E, z = synth.make_lookup_inputs(int(g["seed"]))
     z = z[:1024].contiguous()                     # bounded: the scalar C loop is slow
     idx = np.empty(z.shape[0], dtype=np.int64)
     lib.vq_oracle_lookup(ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(E.data_ptr()), ctypes.c_int64(z.shape[0]),

@@ -89,7 +89,22 @@ def load(require_device=False):
     return _lib
 
 
+_launches = 0
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    """Number of libvf_b200 kernel-launching C-ABI calls since the last reset (bench.py's gpu_launches)."""
+    return _launches
+
+
 def _check(rc):
+    global _launches
+    _launches += 1
     if rc != 0:
         raise LibraryError(f"libvf_b200 error {rc}: {_lib.vf_last_error().decode()}")
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 26); ++i)
+    for (uint32_t i = 0; i < (1u << 22); ++i)
         if (mbar_try_wait(bar, parity)) return;
     printf("vf_tc_gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
     __trap();

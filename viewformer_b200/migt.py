@@ -55,18 +55,44 @@ class MIGT:
     def codebook_model(self, model):
         self._codebook_model = model
 
-    def expected_keys(self):
-        cfg = self.config
-        keys = ["wte.weight", "wpe.embeddings"]
-        for n in ("pose_embedding.c_fc", "pose_embedding.c_proj", "pose_classifier.c_fc", "pose_classifier.c_proj"):
-            keys += [n + ".weight", n + ".bias"]
+    def param_shapes(self):
+        """Ordered {name: shape}; names follow the reference's Keras layer names (migt.py:84-87, 288-315)."""
+        cfg, d = self.config, self.config.d_model
+        out = OrderedDict()
+        out["wte.weight"] = (cfg.n_embeddings + 2, d)
+        out["wpe.embeddings"] = (256, d)
+        for n, (nx, nf) in (("pose_embedding.c_fc", (7, 2 * d)), ("pose_embedding.c_proj", (2 * d, d)),
+                            ("pose_classifier.c_fc", (d, 2 * d)), ("pose_classifier.c_proj", (2 * d, 7))):
+            out[n + ".weight"] = (nx, nf)
+            out[n + ".bias"] = (1, nf)
         for i in range(cfg.n_layer):
             p = f"h.{i}."
-            keys += [p + "ln_1.gamma", p + "ln_1.beta", p + "ln_2.gamma", p + "ln_2.beta"]
-            for n in ("attn.c_attn", "attn.c_proj", "mlp.c_fc", "mlp.c_proj"):
-                keys += [p + n + ".weight", p + n + ".bias"]
-        keys += ["ln_f.gamma", "ln_f.beta"]
-        return keys
+            for ln in ("ln_1", "ln_2"):
+                out[p + ln + ".gamma"] = (d,)
+                out[p + ln + ".beta"] = (d,)
+            for n, (nx, nf) in (("attn.c_attn", (d, 3 * d)), ("attn.c_proj", (d, d)), ("mlp.c_fc", (d, 4 * d)), ("mlp.c_proj", (4 * d, d))):
+                out[p + n + ".weight"] = (nx, nf)
+                out[p + n + ".bias"] = (1, nf)
+        out["ln_f.gamma"] = (d,)
+        out["ln_f.beta"] = (d,)
+        return out
+
+    def expected_keys(self):
+        return list(self.param_shapes().keys())
+
+    def init_weights(self, seed=0):
+        """Reference initialisers: TruncatedNormal(0.02) for wte / wpe / Conv1D weights (migt.py:26,85,314),
+        zero biases, LayerNorm gamma 1 / beta 0."""
+        g = torch.Generator().manual_seed(int(seed))
+        sd = OrderedDict()
+        for k, shp in self.param_shapes().items():
+            if k.endswith("gamma"):
+                sd[k] = torch.ones(shp)
+            elif k.endswith("beta") or k.endswith("bias"):
+                sd[k] = torch.zeros(shp)
+            else:
+                sd[k] = torch.nn.init.trunc_normal_(torch.empty(shp), std=0.02, a=-0.04, b=0.04, generator=g)
+        return self.load_state_dict(sd)
 
     def load_state_dict(self, state_dict, strict=True):
         sd = OrderedDict(state_dict.items())

@@ -82,22 +82,32 @@ class VQGAN:
     def parameters(self):
         return [v for k, v in self.state_dict().items() if not k.startswith("quantize.")]
 
-    def expected_keys(self):
+    def param_shapes(self):
+        """Ordered {name: shape} of the reference state_dict (vqgan_th.py:147-201, 228-289, 321-336)."""
         cfg = self.config
-        keys = []
+        out = OrderedDict()
         nres = len(cfg.ch_mult)
         res = [cfg.image_size // 2 ** i for i in range(nres)]
 
-        def conv(n): keys.extend([n + ".weight", n + ".bias"])
+        def conv(n, cout, cin, k):
+            out[n + ".weight"] = (cout, cin, k, k)
+            out[n + ".bias"] = (cout,)
+
+        def norm(n, c):
+            out[n + ".weight"] = (c,)
+            out[n + ".bias"] = (c,)
+
         def rb(n, cin, cout):
-            for p in ("norm1", "conv1", "norm2", "conv2"):
-                conv(n + "." + p)
+            norm(n + ".norm1", cin); conv(n + ".conv1", cout, cin, 3); norm(n + ".norm2", cout); conv(n + ".conv2", cout, cout, 3)
             if cin != cout:
-                conv(n + ".nin_shortcut")
-        def at(n):
-            for p in ("norm", "q", "k", "v", "proj_out"):
-                conv(n + "." + p)
-        conv("encoder.conv_in")
+                conv(n + ".nin_shortcut", cout, cin, 1)
+
+        def at(n, c):
+            norm(n + ".norm", c)
+            for p in ("q", "k", "v", "proj_out"):
+                conv(n + "." + p, c, c, 1)
+
+        conv("encoder.conv_in", cfg.ch, cfg.in_channels, 3)
         cin = cfg.ch
         for lv in range(nres):
             cout = cfg.ch * cfg.ch_mult[lv]
@@ -106,15 +116,15 @@ class VQGAN:
                 rb(f"encoder.down.{lv}.block.{b}", cin, cout)
                 cin = cout
                 if res[lv] in cfg.attn_resolutions:
-                    at(f"encoder.down.{lv}.attn.{na}")
+                    at(f"encoder.down.{lv}.attn.{na}", cin)
                     na += 1
             if lv != nres - 1:
-                conv(f"encoder.down.{lv}.downsample.conv")
-        rb("encoder.mid.block_1", cin, cin); at("encoder.mid.attn_1"); rb("encoder.mid.block_2", cin, cin)
-        conv("encoder.norm_out"); conv("encoder.conv_out")
+                conv(f"encoder.down.{lv}.downsample.conv", cin, cin, 3)
+        rb("encoder.mid.block_1", cin, cin); at("encoder.mid.attn_1", cin); rb("encoder.mid.block_2", cin, cin)
+        norm("encoder.norm_out", cin); conv("encoder.conv_out", cfg.z_channels, cin, 3)
         cin = cfg.ch * cfg.ch_mult[-1]
-        conv("decoder.conv_in")
-        rb("decoder.mid.block_1", cin, cin); at("decoder.mid.attn_1"); rb("decoder.mid.block_2", cin, cin)
+        conv("decoder.conv_in", cin, cfg.z_channels, 3)
+        rb("decoder.mid.block_1", cin, cin); at("decoder.mid.attn_1", cin); rb("decoder.mid.block_2", cin, cin)
         for lv in reversed(range(nres)):
             cout = cfg.ch * cfg.ch_mult[lv]
             na = 0
@@ -122,14 +132,42 @@ class VQGAN:
                 rb(f"decoder.up.{lv}.block.{b}", cin, cout)
                 cin = cout
                 if res[lv] in cfg.attn_resolutions:
-                    at(f"decoder.up.{lv}.attn.{na}")
+                    at(f"decoder.up.{lv}.attn.{na}", cin)
                     na += 1
             if lv != 0:
-                conv(f"decoder.up.{lv}.upsample.conv")
-        conv("decoder.norm_out"); conv("decoder.conv_out")
-        keys += ["quantize.embeddings", "quantize.ema_cluster_size_hidden", "quantize.ema_dw_hidden", "quantize.counter"]
-        conv("quant_conv"); conv("post_quant_conv")
-        return keys
+                conv(f"decoder.up.{lv}.upsample.conv", cin, cin, 3)
+        norm("decoder.norm_out", cin); conv("decoder.conv_out", cfg.out_ch, cin, 3)
+        out["quantize.embeddings"] = (cfg.embed_dim, cfg.n_embed)
+        out["quantize.ema_cluster_size_hidden"] = (cfg.n_embed,)
+        out["quantize.ema_dw_hidden"] = (cfg.embed_dim, cfg.n_embed)
+        out["quantize.counter"] = ()
+        conv("quant_conv", cfg.embed_dim, cfg.z_channels, 1); conv("post_quant_conv", cfg.z_channels, cfg.embed_dim, 1)
+        return out
+
+    def expected_keys(self):
+        return list(self.param_shapes().keys())
+
+    def init_weights(self, seed=0):
+        """Random initialisation with the reference's initialisers: torch Conv2d default U(+-1/sqrt(fan_in)) for
+        weights and biases, GroupNorm 1/0, codebook U(+-sqrt 3) (utils_th.py:17), EMA buffers 0."""
+        g = torch.Generator().manual_seed(int(seed))
+        sd = OrderedDict()
+        shapes = self.param_shapes()
+        for k, shp in shapes.items():
+            if k == "quantize.embeddings":
+                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * 3 ** 0.5
+            elif k == "quantize.counter":
+                sd[k] = torch.tensor(0, dtype=torch.int64)
+            elif k.startswith("quantize."):
+                sd[k] = torch.zeros(shp)
+            elif len(shp) == 4:
+                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / (shp[1] * shp[2] * shp[3]) ** 0.5
+            elif ".norm" in k or "norm_out" in k:
+                sd[k] = torch.ones(shp) if k.endswith("weight") else torch.zeros(shp)
+            else:
+                w = shapes[k[:-4] + "weight"]
+                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / (w[1] * w[2] * w[3]) ** 0.5
+        return self.load_state_dict(sd)
 
     def load_state_dict(self, state_dict, strict=True):
         """Strict key check with the reference's ignore patterns (vqgan_th.py:346-359)."""
