@@ -40,7 +40,9 @@ int vf_device_check(void);
  * replaces: evaluate/evaluate_transformer.py:106-108 (uint8 -> f32, *2-1), :128-129 (clip, ->uint8),
  *           the NCHW<->NHWC permutes of models/utils_th.py:34,72 and utils/convert.py:61-67.
  * ---------------------------------------------------------------------------------------- */
-int vf_u8_to_unit_f32(const uint8_t* in, float* out, int64_t n, vf_stream_t s);      /* x*(1/255)*2-1 */
+/* out[r, :] = in[r*in_row_stride : +row_len] * (1/255) * 2 - 1 for r < rows (rows=1: flat array; rows=B with
+ * in_row_stride = T*H*W*3 selects the first views of every scene without a gather copy) */
+int vf_u8_to_unit_f32(const uint8_t* in, float* out, int64_t rows, int64_t row_len, int64_t in_row_stride, vf_stream_t s);
 int vf_unit_f32_to_u8(const float* in, uint8_t* out, int64_t n, vf_stream_t s);      /* clip[-1,1]/2+.5 -> trunc(x*255.5) */
 int vf_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, vf_stream_t s);
 int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, vf_stream_t s);
@@ -48,12 +50,14 @@ int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W,
 /* ------------------------------------------------------------------------------------------
  * GroupNorm(32 groups) [+ swish] [+ nearest x2 upsample] [+ cast]
  * replaces: models/vqgan_th.py:11-17 (Normalize, nonlinearity), :29-30 (F.interpolate nearest)
- * x f32 [N, HW, C].  stats: double [N, groups, 2] scratch, zeroed and filled by vf_groupnorm_stats.
+ * x f32 [N, HW, C].  vf_groupnorm_stats: sums = double [N, groups, 2] scratch (zeroed + accumulated here),
+ * mean_rstd = float [N, groups, 2] result (mean, 1/sqrt(var+eps)) consumed by vf_groupnorm_apply.
  * vf_groupnorm_apply: y = ((x-mean)*rstd*gamma+beta) [swish]; normalize=0 -> plain cast/upsample.
  *   upsample2x=1 writes y as [N, 2H, 2W, C] (needs H, W).  y_dtype VF_F32 | VF_BF16.
  * ---------------------------------------------------------------------------------------- */
-int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, double* stats, vf_stream_t s);
-int vf_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta,
+int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* sums, float* mean_rstd,
+                       vf_stream_t s);
+int vf_groupnorm_apply(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
                        int N, int H, int W, int C, int groups, float eps, int normalize, int swish,
                        int upsample2x, void* y, int y_dtype, vf_stream_t s);
 
@@ -157,6 +161,13 @@ int vf_argmax_rows(const float* x, int64_t rows, int cols, int64_t ld, int64_t* 
 /* pose head post-processing (models/migt.py:159-164): in [rows,7] raw MLP output ->
  * xyz/pose_multiplier | normalised, sign-fixed quaternion */
 int vf_pose_postprocess(const float* raw, int64_t rows, float pose_multiplier, float* out, vf_stream_t s);
+/* camera pre-processing of generate() in one launch (evaluate/evaluate_transformer.py:70-78, 90-94):
+ * cams f32 [B,T,7] (xyz | wxyz).  relative != 0: express every pose relative to view 0 (rotate by the conjugate of
+ * view 0's quaternion), then L2-normalise the quaternion (eps 1e-12) and flip it to w >= 0.
+ * out [B,T,7]; transform (nullable) [B,7] receives view 0's original pose. */
+int vf_cameras_prepare(const float* cams, int B, int T, int relative, float* out, float* transform, vf_stream_t s);
+/* inverse map (evaluate_transformer.py:81-87): out[b,i] = transform[b] o cams[b,i];  cams [B,n,7], transform [B,7] */
+int vf_cameras_from_relative(const float* cams, const float* transform, int B, int n, float* out, vf_stream_t s);
 /* plain dtype casts / strided copies used between ops */
 int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s);
 /* sum(|a-b|) and sum((a-b)^2) into double[2] (training losses, vqgan_th.py:401) */

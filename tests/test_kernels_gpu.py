@@ -324,3 +324,21 @@ def test_embed_and_pose_post(L):
     got = L.pose_postprocess(raw.cuda(), 2.0).cpu()
     want = torch.cat([raw[:, :3] / 2.0, mo.quaternion_remove_sign(mo.quaternion_normalize(raw[:, 3:]))], -1)
     report("pose_post", got, want, 1e-6, 1e-6)
+
+
+def test_camera_kernels_and_strided_u8(L):
+    from oracle import synth, migt_oracle as mo
+    cams = synth.make_cameras(5, 4, seed=80)
+    cams[:, :, 3:] *= 1.7                                   # un-normalised quaternions on purpose
+    got, tr = L.cameras_prepare(cams.cuda(), True)
+    rel, tr_want = mo.to_relative_cameras(cams)
+    report("cams relative", got, mo.normalize_cameras(rel), 2e-6, 1e-5)
+    assert torch.equal(tr.cpu(), tr_want[:, 0])
+    got2, _ = L.cameras_prepare(cams.cuda(), False)
+    report("cams normalise", got2, mo.normalize_cameras(cams), 1e-6, 1e-6)
+    back = L.cameras_from_relative(rel.contiguous().cuda(), tr)
+    report("cams from_relative", back, mo.from_relative_cameras(rel, tr_want), 2e-6, 1e-5)
+    u8 = torch.randint(0, 256, (3, 4, 8, 8, 3), generator=g(81), dtype=torch.uint8)
+    got = L.u8_to_unit(u8.cuda(), first_views=3).cpu()
+    want = (u8[:, :3].float() * torch.tensor(1.0 / 255.0) * 2 - 1).reshape(9, 8, 8, 3)
+    assert torch.equal(got, want)

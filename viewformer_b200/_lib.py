@@ -21,7 +21,7 @@ EXPORTS = [
     "vf_nchw_to_nhwc_f32", "vf_nhwc_to_nchw_f32", "vf_groupnorm_stats", "vf_groupnorm_apply", "vf_layernorm",
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
-    "vf_cast_f32_to_bf16", "vf_l1_l2_sums",
+    "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
 ]
 
 
@@ -58,6 +58,7 @@ class TcGemm(C.Structure):
 
 
 _lib = None
+_device_ok = []
 
 
 class LibraryError(RuntimeError):
@@ -80,12 +81,13 @@ def load(require_device=False):
         if lib.vf_sizeof_simt_gemm() != C.sizeof(SimtGemm) or lib.vf_sizeof_tc_gemm() != C.sizeof(TcGemm):
             raise LibraryError("parameter struct layout mismatch between _lib.py and include/vf_b200.h")
         _lib = lib
-    if require_device:
+    if require_device and not _device_ok:
         if not torch.cuda.is_available():
             raise LibraryError("viewformer_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
         rc = _lib.vf_device_check()
         if rc != 0:
             raise LibraryError(_lib.vf_last_error().decode())
+        _device_ok.append(True)          # checked once per process (cudaGetDeviceProperties is slow)
     return _lib
 
 
@@ -133,11 +135,19 @@ def _dev(t, dtype=None):
 
 
 # ----------------------------------------------------------------------------------------------- pixels / layout
-def u8_to_unit(x_u8):
+def u8_to_unit(x_u8, first_views=None):
+    """uint8 -> f32 x*(1/255)*2-1.  ``first_views=n`` on a [B,T,H,W,3] tensor converts views 0..n-1 of every scene
+    into a contiguous [B*n,H,W,3] tensor (strided read, no gather copy)."""
     lib = load(True)
     _dev(x_u8, torch.uint8)
-    out = torch.empty(x_u8.shape, dtype=torch.float32, device=x_u8.device)
-    _check(lib.vf_u8_to_unit_f32(_p(x_u8), _p(out), C.c_int64(x_u8.numel()), _stream()))
+    if first_views is None:
+        out = torch.empty(x_u8.shape, dtype=torch.float32, device=x_u8.device)
+        _check(lib.vf_u8_to_unit_f32(_p(x_u8), _p(out), C.c_int64(1), C.c_int64(x_u8.numel()), C.c_int64(0), _stream()))
+        return out
+    b, t = x_u8.shape[:2]
+    per_view = x_u8[0, 0].numel()
+    out = torch.empty((b * first_views,) + tuple(x_u8.shape[2:]), dtype=torch.float32, device=x_u8.device)
+    _check(lib.vf_u8_to_unit_f32(_p(x_u8), _p(out), C.c_int64(b), C.c_int64(first_views * per_view), C.c_int64(t * per_view), _stream()))
     return out
 
 
@@ -175,8 +185,9 @@ def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample
     n, h, w, c = x.shape
     stats = None
     if normalize:
-        stats = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
-        _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, _p(stats), _stream()))
+        sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+        stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)      # (mean, rstd)
+        _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
     oshape = (n, 2 * h, 2 * w, c) if upsample else (n, h, w, c)
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
     _check(lib.vf_groupnorm_apply(_p(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
@@ -413,6 +424,26 @@ def pose_postprocess(raw_rows, mult):
     _dev(raw_rows, torch.float32)
     out = torch.empty_like(raw_rows)
     _check(lib.vf_pose_postprocess(_p(raw_rows), C.c_int64(raw_rows.shape[0]), C.c_float(mult), _p(out), _stream()))
+    return out
+
+
+def cameras_prepare(cams, relative):
+    """cams f32 [B,T,7] (device) -> (relative+normalised cams [B,T,7], transform [B,7]) in one launch."""
+    lib = load(True)
+    _dev(cams, torch.float32)
+    b, t, _ = cams.shape
+    out = torch.empty_like(cams)
+    tr = torch.empty((b, 7), dtype=torch.float32, device=cams.device)
+    _check(lib.vf_cameras_prepare(_p(cams), b, t, int(relative), _p(out), _p(tr), _stream()))
+    return out, tr
+
+
+def cameras_from_relative(cams, transform):
+    lib = load(True)
+    _dev(cams, torch.float32)
+    b, n, _ = cams.shape
+    out = torch.empty_like(cams)
+    _check(lib.vf_cameras_from_relative(_p(cams), _p(transform), b, n, _p(out), _stream()))
     return out
 
 

@@ -33,9 +33,11 @@ extern "C" int vf_device_check(void) {
 namespace {
 
 // ------------------------------------------------------------------------------------------ pixels
-__global__ void u8_to_unit_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+__global__ void u8_to_unit_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n, int64_t in_row_stride) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
+    in += (int64_t)blockIdx.y * in_row_stride;
+    out += (int64_t)blockIdx.y * n;
     const float k = 1.0f / 255.0f;   // tf.image.convert_image_dtype: multiply by float32(1/255)
     if (i + 3 < n && ((reinterpret_cast<uintptr_t>(in + i) & 3) == 0)) {
         const uchar4 v = *reinterpret_cast<const uchar4*>(in + i);
@@ -179,6 +181,60 @@ __global__ void pose_post_kernel(const float* __restrict__ raw, int64_t rows, fl
     o[3] = qw * sg; o[4] = qx * sg; o[5] = qy * sg; o[6] = qz * sg;
 }
 
+// quaternion helpers, (w,x,y,z) order — viewformer/utils/geometry_tf.py:6-13, 53-91
+struct Quat { float w, x, y, z; };
+__device__ __forceinline__ Quat qmul(Quat a, Quat b) {
+    Quat r;
+    r.x = a.x * b.w + a.y * b.z - a.z * b.y + a.w * b.x;
+    r.y = -a.x * b.z + a.y * b.w + a.z * b.x + a.w * b.y;
+    r.z = a.x * b.y - a.y * b.x + a.z * b.w + a.w * b.z;
+    r.w = -a.x * b.x - a.y * b.y - a.z * b.z + a.w * b.w;
+    return r;
+}
+__global__ void cameras_prepare_kernel(const float* __restrict__ cams, int B, int T, int relative, float* __restrict__ out,
+                                       float* __restrict__ transform) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int b = i / T, t = i % T;
+    const float* c = cams + (int64_t)i * 7;
+    const float* c0 = cams + (int64_t)b * T * 7;
+    float px = c[0], py = c[1], pz = c[2];
+    Quat q = {c[3], c[4], c[5], c[6]};
+    if (relative) {
+        const Quat inv = {c0[3], -c0[4], -c0[5], -c0[6]};          // conjugate of view 0's rotation
+        const Quat p = {0.f, px - c0[0], py - c0[1], pz - c0[2]};
+        const Quat conj_inv = {inv.w, -inv.x, -inv.y, -inv.z};
+        const Quat r = qmul(qmul(inv, p), conj_inv);               // quaternion_rotate(xyz - t, inv)
+        px = r.x; py = r.y; pz = r.z;
+        q = qmul(inv, q);
+        if (t == 0 && transform) {
+            float* tr = transform + (int64_t)b * 7;
+            for (int j = 0; j < 7; ++j) tr[j] = c0[j];
+        }
+    }
+    const float n2 = fmaxf(((q.w * q.w + q.x * q.x) + q.y * q.y) + q.z * q.z, 1e-12f);
+    const float inv_n = rsqrtf(n2);
+    q.w *= inv_n; q.x *= inv_n; q.y *= inv_n; q.z *= inv_n;
+    const float sg = (q.w >= 0.f) ? 1.f : -1.f;
+    float* o = out + (int64_t)i * 7;
+    o[0] = px; o[1] = py; o[2] = pz; o[3] = q.w * sg; o[4] = q.x * sg; o[5] = q.y * sg; o[6] = q.z * sg;
+}
+
+__global__ void cameras_from_relative_kernel(const float* __restrict__ cams, const float* __restrict__ transform, int B, int n,
+                                             float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * n) return;
+    const float* c = cams + (int64_t)i * 7;
+    const float* t = transform + (int64_t)(i / n) * 7;
+    const Quat tq = {t[3], t[4], t[5], t[6]};
+    const Quat q = qmul(tq, Quat{c[3], c[4], c[5], c[6]});
+    const Quat p = {0.f, c[0], c[1], c[2]};
+    const Quat r = qmul(qmul(tq, p), Quat{tq.w, -tq.x, -tq.y, -tq.z});
+    float* o = out + (int64_t)i * 7;
+    o[0] = r.x + t[0]; o[1] = r.y + t[1]; o[2] = r.z + t[2];
+    o[3] = q.w; o[4] = q.x; o[5] = q.y; o[6] = q.z;
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
@@ -222,10 +278,12 @@ __global__ void __launch_bounds__(256) l1_l2_kernel(const float* __restrict__ a,
 
 static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-extern "C" int vf_u8_to_unit_f32(const uint8_t* in, float* out, int64_t n, vf_stream_t s) {
-    VF_CHECK_ARG(in && out && n >= 0, "vf_u8_to_unit_f32: bad args");
-    if (n == 0) return VF_OK;
-    u8_to_unit_kernel<<<nblk(n, 1024), 256, 0, vf_s(s)>>>(in, out, n);
+extern "C" int vf_u8_to_unit_f32(const uint8_t* in, float* out, int64_t rows, int64_t row_len, int64_t in_row_stride,
+                                 vf_stream_t s) {
+    VF_CHECK_ARG(in && out && rows >= 0 && row_len >= 0 && rows <= 65535, "vf_u8_to_unit_f32: bad args");
+    if (rows == 0 || row_len == 0) return VF_OK;
+    dim3 grid(nblk(row_len, 1024), (unsigned)rows);
+    u8_to_unit_kernel<<<grid, 256, 0, vf_s(s)>>>(in, out, row_len, in_row_stride);
     VF_CHECK_LAUNCH("vf_u8_to_unit_f32");
     return VF_OK;
 }
@@ -288,6 +346,20 @@ extern "C" int vf_pose_postprocess(const float* raw, int64_t rows, float pose_mu
     if (rows == 0) return VF_OK;
     pose_post_kernel<<<nblk(rows, 256), 256, 0, vf_s(s)>>>(raw, rows, pose_multiplier, out);
     VF_CHECK_LAUNCH("vf_pose_postprocess");
+    return VF_OK;
+}
+extern "C" int vf_cameras_prepare(const float* cams, int B, int T, int relative, float* out, float* transform, vf_stream_t s) {
+    VF_CHECK_ARG(cams && out && B >= 0 && T > 0, "vf_cameras_prepare: bad args");
+    if (B == 0) return VF_OK;
+    cameras_prepare_kernel<<<(B * T + 127) / 128, 128, 0, vf_s(s)>>>(cams, B, T, relative, out, transform);
+    VF_CHECK_LAUNCH("vf_cameras_prepare");
+    return VF_OK;
+}
+extern "C" int vf_cameras_from_relative(const float* cams, const float* transform, int B, int n, float* out, vf_stream_t s) {
+    VF_CHECK_ARG(cams && transform && out && B >= 0 && n > 0, "vf_cameras_from_relative: bad args");
+    if (B == 0) return VF_OK;
+    cameras_from_relative_kernel<<<(B * n + 127) / 128, 128, 0, vf_s(s)>>>(cams, transform, B, n, out);
+    VF_CHECK_LAUNCH("vf_cameras_from_relative");
     return VF_OK;
 }
 extern "C" int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s) {

@@ -47,6 +47,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     for (int i = threadIdx.x; i < groups * 2; i += 256) atomicAdd(&stats[(int64_t)n * groups * 2 + i], sh[i]);
 }
 
+// sums (double) -> (mean, rstd) floats, one thread per (n, group): keeps fp64 math out of the streaming kernel
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, int total, double cnt, float eps, float* __restrict__ mr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double mean = sums[2 * i] / cnt;
+    double var = sums[2 * i + 1] / cnt - mean * mean;
+    if (var < 0) var = 0;
+    mr[2 * i] = (float)mean;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Apply: one thread per channel quad of one pixel.
 // ---------------------------------------------------------------------------------------------
@@ -66,7 +77,7 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a,
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int N, int H, int W, int C, int groups, float eps, int normalize,
                                                        int swish, int up, OutT* __restrict__ y) {
@@ -80,7 +91,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     if (normalize) {
         const int n = (int)(pix / ((int64_t)H * W));
         const int cpg = C / groups;
-        const double cnt = (double)H * W * cpg;
         const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
         float mu[4], rs[4];
@@ -88,13 +98,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         for (int j = 0; j < 4; ++j) {
             if (j > 0 && (cpg & 3) == 0) { mu[j] = mu[0]; rs[j] = rs[0]; continue; }
             const int g = (cq * 4 + j) / cpg;
-            const double su = stats[((int64_t)n * groups + g) * 2 + 0];
-            const double sq = stats[((int64_t)n * groups + g) * 2 + 1];
-            const double mean = su / cnt;
-            double var = sq / cnt - mean * mean;
-            if (var < 0) var = 0;
-            rs[j] = (float)(1.0 / sqrt(var + (double)eps));
-            mu[j] = (float)mean;
+            const float2 m = __ldg(reinterpret_cast<const float2*>(mr) + (int64_t)n * groups + g);
+            mu[j] = m.x;
+            rs[j] = m.y;
         }
         v.x = (v.x - mu[0]) * rs[0] * ga.x + be.x;
         v.y = (v.y - mu[1]) * rs[1] * ga.y + be.y;
@@ -169,8 +175,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, double* stats, vf_stream_t s) {
-    VF_CHECK_ARG(x && stats, "vf_groupnorm_stats: null pointer");
+extern "C" int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* stats, float* mean_rstd,
+                                  vf_stream_t s) {
+    VF_CHECK_ARG(x && stats && mean_rstd, "vf_groupnorm_stats: null pointer");
     VF_CHECK_ARG(C % groups == 0 && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0,
                  "vf_groupnorm_stats: unsupported C=%d groups=%d", C, groups);
     cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * N, vf_s(s));
@@ -185,10 +192,12 @@ extern "C" int vf_groupnorm_stats(const float* x, int N, int HW, int C, int grou
     dim3 grid(chunks, N);
     gn_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, vf_s(s)>>>(x, HW, C, groups, ppb, stats);
     VF_CHECK_LAUNCH("vf_groupnorm_stats");
+    gn_finalize_kernel<<<(N * groups + 127) / 128, 128, 0, vf_s(s)>>>(stats, N * groups, (double)HW * (C / groups), eps, mean_rstd);
+    VF_CHECK_LAUNCH("vf_groupnorm_stats(finalize)");
     return VF_OK;
 }
 
-extern "C" int vf_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, int N,
+extern "C" int vf_groupnorm_apply(const float* x, const float* stats, const float* gamma, const float* beta, int N,
                                   int H, int W, int C, int groups, float eps, int normalize, int swish, int upsample2x,
                                   void* y, int y_dtype, vf_stream_t s) {
     VF_CHECK_ARG(x && y, "vf_groupnorm_apply: null pointer");

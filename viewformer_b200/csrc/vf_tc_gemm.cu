@@ -29,6 +29,7 @@ struct TcParams {
     int M, Ncols;
     int num_k_blocks;          // total K blocks (gemm: ceil(K/BKe); conv: ntaps * cin_blocks)
     int batch2;
+    int tiles_m, tiles_n, total_tiles;
     int a_bm1, a_bm2, b_bm1, b_bm2;   // 0 => operand is shared by all batches along that batch dim
     // conv tiling
     int TW, TH, TN, tiles_x, tiles_y, OH, OW, Nimg, cin_blocks, bk_elems;
@@ -132,50 +133,73 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+struct TileInfo {
+    int m0, n0, b1, b2, img0, oy0, ox0, nkb;
+    bool skip;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t, int block_n) {
+    TileInfo ti;
+    const int n_tile = t % p.tiles_n;
+    const int r = t / p.tiles_n;
+    const int m_tile = r % p.tiles_m;
+    const int bz = r / p.tiles_m;
+    ti.b1 = bz / p.batch2;
+    ti.b2 = bz % p.batch2;
+    ti.m0 = m_tile * BLOCK_M;
+    ti.n0 = n_tile * block_n;
+    ti.nkb = p.num_k_blocks;
+    ti.skip = false;
+    if (p.causal_block > 0) {
+        const int lim = ((ti.m0 + BLOCK_M - 1) / p.causal_block + 1) * p.causal_block;   // keys visible to the tile's last row
+        if (p.causal_skip_n) {
+            ti.skip = ti.n0 >= lim;                                                      // whole tile masked: never read
+        } else {
+            const int kb = (lim + p.bk_elems - 1) / p.bk_elems;
+            if (kb < ti.nkb) ti.nkb = kb;
+        }
+    }
+    ti.img0 = ti.oy0 = ti.ox0 = 0;
+    if (p.conv) {
+        const int tx = m_tile % p.tiles_x;
+        const int q = m_tile / p.tiles_x;
+        ti.img0 = (q / p.tiles_y) * p.TN;
+        ti.oy0 = (q % p.tiles_y) * p.TH;
+        ti.ox0 = tx * p.TW;
+    }
+    return ti;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+//   warp 0      TMA producer   — smem ring runs continuously across tiles
+//   warp 1      MMA issuer     — accumulates tile i into TMEM stage (i & 1) while the epilogue drains stage (i-1) & 1
+//   warps 2..5  epilogue       — TMEM -> registers (alpha, bias, GELU) -> per-warp smem staging -> TMEM stage released
+//                                -> coalesced row-wise residual loads / global stores
 template <int kBlockN, int kStages, bool kTF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_STAGE_BYTES = kBlockN * ROW_BYTES;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int UMMA_K_BYTES = 32;           // 16 bf16 or 8 tf32 per instruction
     constexpr int MMAS_PER_STAGE = ROW_BYTES / UMMA_K_BYTES;
+    constexpr int STG_LD = kBlockN + 4;        // staging row stride (floats): +4 keeps 128-bit row writes conflict-free
+    constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
 
     extern __shared__ uint8_t smem_raw[];
     // 1024B alignment required by the 128B swizzle atoms (descriptor base_offset = 0)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + STG_BYTES);
     uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + kStages;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y, bz = blockIdx.z;
-    const int b1 = bz / p.batch2, b2 = bz % p.batch2;
-    const int m0 = m_tile * BLOCK_M;
-    const int n0 = n_tile * kBlockN;
-
-    // k-range (block-causal attention support)
-    int nkb = p.num_k_blocks;
-    if (p.causal_block > 0) {
-        const int lim = ((m0 + BLOCK_M - 1) / p.causal_block + 1) * p.causal_block;   // keys visible to the tile's last row
-        if (p.causal_skip_n) {
-            if (n0 >= lim) return;                                                    // whole tile masked: never read
-        } else {
-            const int kb = (lim + p.bk_elems - 1) / p.bk_elems;
-            if (kb < nkb) nkb = kb;
-        }
-    }
-
-    // conv tile origin
-    int img0 = 0, oy0 = 0, ox0 = 0;
-    if (p.conv) {
-        const int tx = m_tile % p.tiles_x;
-        const int t = m_tile / p.tiles_x;
-        const int ty = t % p.tiles_y;
-        img0 = (t / p.tiles_y) * p.TN;
-        oy0 = ty * p.TH;
-        ox0 = tx * p.TW;
-    }
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA)) : "memory");
@@ -186,11 +210,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);           // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // whole warp allocates kBlockN TMEM columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kBlockN)
+    if (warp == 1) {   // whole warp allocates 2 accumulator stages = 2*kBlockN TMEM columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * kBlockN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -204,21 +231,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                uint8_t* sb = sa + A_STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                if (p.conv) {
-                    const int tap = kb / p.cin_blocks;
-                    const int cb = kb - tap * p.cin_blocks;
-                    tma_load_4d(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ox0 + p.tap_dx[tap],
-                                oy0 + p.tap_dy[tap], img0);
-                } else {
-                    tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, m0, b2 * p.a_bm2, b1 * p.a_bm1);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileInfo ti = decode_tile(p, t, kBlockN);
+                if (ti.skip) continue;
+                for (int kb = 0; kb < ti.nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    if (p.conv) {
+                        const int tap = kb / p.cin_blocks;
+                        const int cb = kb - tap * p.cin_blocks;
+                        tma_load_4d(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap],
+                                    ti.oy0 + p.tap_dy[tap], ti.img0);
+                    } else {
+                        tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
+                    }
+                    tma_load_4d(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, ti.n0, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tma_load_4d(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, n0, b2 * p.b_bm2, b1 * p.b_bm1);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -226,105 +257,132 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileInfo ti = decode_tile(p, t, kBlockN);
+                if (ti.skip) continue;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator stage
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                const uint32_t sb = sa + A_STAGE_BYTES;
-                const uint64_t adesc = make_sw128_desc(sa);
-                const uint64_t bdesc = make_sw128_desc(sb);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBlockN);
+                for (int kb = 0; kb < ti.nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sb);
 #pragma unroll
-                for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-                    // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
-                    umma<kTF32>(tmem_base, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
-                                p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                        // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
+                        umma<kTF32>(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                    p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                tcgen05_commit(&tmem_full_bar[acc]);          // accumulator complete
+                ++it;
             }
-            tcgen05_commit(tmem_full_bar);                // accumulator complete
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                     // TMEM lanes [32q, 32q+32) are only visible to warps with id%4 == q
-        const int row = quarter * 32 + lane;              // row of the tile this thread owns
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
+        float* stg = staging + quarter * (32 * STG_LD);   // this warp's private staging tile [32][STG_LD]
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileInfo ti = decode_tile(p, t, kBlockN);
+            if (ti.skip) continue;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            ++it;
 
-        long long out_row_off;
-        bool row_ok;
-        int gm;                                            // logical row index (for bias_mode M)
-        if (p.conv) {
-            const int lx = row % p.TW;
-            const int t = row / p.TW;
-            const int ly = t % p.TH;
-            const int ln = t / p.TH;
-            const int img = img0 + ln, oy = oy0 + ly, ox = ox0 + lx;
-            row_ok = (img < p.Nimg) && (oy < p.OH) && (ox < p.OW);
-            gm = (img * p.OH + oy) * p.OW + ox;
-            out_row_off = (long long)gm * p.ldc;
-        } else {
-            gm = m0 + row;
-            row_ok = gm < p.M;
-            out_row_off = (long long)b1 * p.c_sb1 + (long long)b2 * p.c_sb2 + (long long)gm * p.ldc;
-        }
-        const float bias_m = (p.bias_mode == VF_BIAS_M && row_ok) ? __ldg(p.bias + gm) : 0.f;
+            // row bookkeeping: lane l owns tile row 32*quarter + l
+            const int row = quarter * 32 + lane;
+            long long my_off;
+            int my_ok, gm;
+            if (p.conv) {
+                const int lx = row % p.TW;
+                const int q = row / p.TW;
+                const int ly = q % p.TH;
+                const int ln = q / p.TH;
+                const int img = ti.img0 + ln, oy = ti.oy0 + ly, ox = ti.ox0 + lx;
+                my_ok = (img < p.Nimg) && (oy < p.OH) && (ox < p.OW);
+                gm = (img * p.OH + oy) * p.OW + ox;
+                my_off = (long long)gm * p.ldc;
+            } else {
+                gm = ti.m0 + row;
+                my_ok = gm < p.M;
+                my_off = (long long)ti.b1 * p.c_sb1 + (long long)ti.b2 * p.c_sb2 + (long long)gm * p.ldc;
+            }
+            const float bias_m = (p.bias_mode == VF_BIAS_M && my_ok) ? __ldg(p.bias + gm) : 0.f;
 
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+
+            // ---- phase 1: TMEM -> registers -> (alpha, bias, activation) -> staging row `lane`
 #pragma unroll 1
-        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-            if (!row_ok) continue;
-            const int nbase = n0 + c0;
-            if (nbase >= p.Ncols) continue;
-            float v[32];
+            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN + c0), r);
+                const int nbase = ti.n0 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(r[j]) * p.alpha;
-                if (p.bias_mode == VF_BIAS_N) x += (nbase + j < p.Ncols) ? __ldg(p.bias + nbase + j) : 0.f;
-                else x += bias_m;
-                if (p.act == VF_ACT_GELU_ERF) x = vf_gelu_erf(x);
-                v[j] = x;
-            }
-            const long long off = out_row_off + nbase;
-            const bool full = (nbase + 32 <= p.Ncols);
-            if (p.residual) {
-                if (full && ((off & 3) == 0)) {
+                for (int j = 0; j < 32; j += 4) {
+                    float v[4];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + off + j));
-                        v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+                    for (int e = 0; e < 4; ++e) {
+                        float x = __uint_as_float(r[j + e]) * p.alpha;
+                        if (p.bias_mode == VF_BIAS_N) x += (nbase + j + e < p.Ncols) ? __ldg(p.bias + nbase + j + e) : 0.f;
+                        else x += bias_m;
+                        if (p.act == VF_ACT_GELU_ERF) x = vf_gelu_erf(x);
+                        v[e] = x;
                     }
-                } else {
-                    for (int j = 0; j < 32 && nbase + j < p.Ncols; ++j) v[j] += __ldg(p.residual + off + j);
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
                 }
             }
-            if (p.C_f32) {
-                if (full && ((off & 3) == 0)) {
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld) -> hand the stage back
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+
+            // ---- phase 2: one tile row per iteration, lanes span the columns -> fully coalesced residual loads / stores
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+                const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
+                const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
+                if (!ok) continue;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(p.C_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && nbase + j < p.Ncols; ++j) p.C_f32[off + j] = v[j];
-                }
-            }
-            if (p.C_bf16) {
-                if (full && ((off & 7) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 u;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-                        u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
-                        *reinterpret_cast<uint4*>(p.C_bf16 + off + j) = u;
+                for (int c = lane * 4; c < kBlockN; c += 128) {
+                    const int n = ti.n0 + c;
+                    if (n >= p.Ncols) continue;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c);
+                    const long long off = off_row + n;
+                    if (n + 4 <= p.Ncols && ((off & 3) == 0)) {
+                        if (p.residual) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                        }
+                        if (p.C_f32) *reinterpret_cast<float4*>(p.C_f32 + off) = v;
+                        if (p.C_bf16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                            uint2 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&lo);
+                            u.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(p.C_bf16 + off) = u;
+                        }
+                    } else {
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+                        for (int e = 0; e < 4 && n + e < p.Ncols; ++e) {
+                            float x = vv[e];
+                            if (p.residual) x += __ldg(p.residual + off + e);
+                            if (p.C_f32) p.C_f32[off + e] = x;
+                            if (p.C_bf16) p.C_bf16[off + e] = __float2bfloat16(x);
+                        }
                     }
-                } else {
-                    for (int j = 0; j < 32 && nbase + j < p.Ncols; ++j) p.C_bf16[off + j] = __float2bfloat16(v[j]);
                 }
             }
+            __syncwarp();                                  // staging is reused by the next tile
         }
     }
 
@@ -333,7 +391,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBlockN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBlockN) : "memory");
     }
 }
 
@@ -391,7 +449,8 @@ unsigned make_idesc(bool tf32, int M, int N) {
 
 template <int kBlockN, int kStages, bool kTF32>
 int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
-    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + 4 * 32 * (kBlockN + 4) * 4 /*epilogue staging*/ +
+                         1024 /*align slack*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -491,9 +550,21 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         VF_CHECK_ARG(q->causal_block == 0 || (q->causal_block % bk == 0 || bk % q->causal_block == 0), "vf_tc_gemm: causal block");
         grid = dim3((q->M + BLOCK_M - 1) / BLOCK_M, (q->Ncols + block_n - 1) / block_n, q->batch1 * q->batch2);
     }
-    VF_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "vf_tc_gemm: grid too large");
+    // persistent launch: `grid` so far is the tile space (m tiles, n tiles, batches); one CTA per SM walks it, n fastest
+    prm.tiles_m = (int)grid.x;
+    prm.tiles_n = (int)grid.y;
+    const long long total = (long long)grid.x * grid.y * grid.z;
+    VF_CHECK_ARG(total > 0 && total < (1ll << 31), "vf_tc_gemm: tile count out of range");
+    prm.total_tiles = (int)total;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const dim3 pgrid((unsigned)(total < num_sms ? total : num_sms), 1, 1);
     prm.idesc = make_idesc(tf32, BLOCK_M, block_n);
     cudaStream_t st = vf_s(s);
-    if (block_n == 128) return tf32 ? launch<128, 6, true>(prm, grid, st) : launch<128, 6, false>(prm, grid, st);
-    return tf32 ? launch<64, 8, true>(prm, grid, st) : launch<64, 8, false>(prm, grid, st);
+    if (block_n == 128) return tf32 ? launch<128, 4, true>(prm, pgrid, st) : launch<128, 4, false>(prm, pgrid, st);
+    return tf32 ? launch<64, 6, true>(prm, pgrid, st) : launch<64, 6, false>(prm, pgrid, st);
 }

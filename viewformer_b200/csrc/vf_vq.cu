@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) vq_lookup_kernel(const float* __restrict_
     __shared__ float Bs[LK][LN + LPAD];
     __shared__ float zz[LM];
     __shared__ int best_i[LM];
+    __shared__ int second_i[LM];
     __shared__ double dsum_sh[8];
 
     const int tid = threadIdx.x;
@@ -37,10 +38,11 @@ __global__ void __launch_bounds__(256) vq_lookup_kernel(const float* __restrict_
     }
     __syncthreads();
 
-    float bd[4];
-    int bi[4];
+    // running best and runner-up (distance, index) per owned row; order = (smaller distance, then smaller index)
+    float bd[4], sd[4];
+    int bi[4], si[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
+    for (int i = 0; i < 4; ++i) { bd[i] = sd[i] = INFINITY; bi[i] = si[i] = 0x7fffffff; }
 
     for (int c0 = 0; c0 < K; c0 += LN) {
         float acc[4][4];
@@ -81,21 +83,58 @@ __global__ void __launch_bounds__(256) vq_lookup_kernel(const float* __restrict_
                 const int c = c0 + tx * 4 + j;
                 if (c < K) {
                     const float dist = __fadd_rn(__fsub_rn(zi, 2.0f * acc[i][j]), __ldg(esq + c));
-                    if (dist < bd[i] || (dist == bd[i] && c < bi[i])) { bd[i] = dist; bi[i] = c; }
+                    if (dist < bd[i] || (dist == bd[i] && c < bi[i])) { sd[i] = bd[i]; si[i] = bi[i]; bd[i] = dist; bi[i] = c; }
+                    else if (dist < sd[i] || (dist == sd[i] && c < si[i])) { sd[i] = dist; si[i] = c; }
                 }
             }
         }
     }
-    // reduce across the 16 threads (tx) that share rows: they are 16 consecutive lanes of one warp
+    // merge the (best, runner-up) pairs of the 16 threads (tx) that share rows: 16 consecutive lanes of one warp
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bd[i], o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi[i], o);
-            if (od < bd[i] || (od == bd[i] && oi < bi[i])) { bd[i] = od; bi[i] = oi; }
+            const float obd = __shfl_xor_sync(0xffffffffu, bd[i], o), osd = __shfl_xor_sync(0xffffffffu, sd[i], o);
+            const int obi = __shfl_xor_sync(0xffffffffu, bi[i], o), osi = __shfl_xor_sync(0xffffffffu, si[i], o);
+            if (obd < bd[i] || (obd == bd[i] && obi < bi[i])) {
+                // other's best wins; runner-up = min(my best, other's runner-up)
+                if (bd[i] < osd || (bd[i] == osd && bi[i] < osi)) { sd[i] = bd[i]; si[i] = bi[i]; } else { sd[i] = osd; si[i] = osi; }
+                bd[i] = obd; bi[i] = obi;
+            } else {
+                // my best stays; runner-up = min(my runner-up, other's best)
+                if (obd < sd[i] || (obd == sd[i] && obi < si[i])) { sd[i] = obd; si[i] = obi; }
+            }
         }
-        if (tx == 0) best_i[ty * 4 + i] = bi[i];
+        if (tx == 0) {
+            best_i[ty * 4 + i] = bi[i];
+            // near-tie: the fp32 gap is within the rounding error of a 256-term fp32 dot product -> settle it in fp64
+            const float scale = zz[ty * 4 + i] + fabsf(bd[i]) + fabsf(sd[i]);
+            second_i[ty * 4 + i] = (si[i] != 0x7fffffff && (sd[i] - bd[i]) <= 2e-5f * scale) ? si[i] : -1;
+        }
+    }
+    __syncthreads();
+    // fp64 re-score of flagged rows (direct sum of squared differences, 4 threads per row): the index returned is the
+    // exact-arithmetic nearest neighbour, ties to the smaller index (== argmax(-dist) first-index rule, utils_th.py:41)
+    {
+        const int64_t gm = m0 + lr;
+        const int cand = second_i[lr];
+        if (gm < M && cand >= 0) {           // uniform across the 4 threads of the row
+            const int b0 = best_i[lr];
+            const float* zr = z + gm * D;
+            const float* e0 = Et + (int64_t)b0 * D;
+            const float* e1 = Et + (int64_t)cand * D;
+            double d0 = 0.0, d1 = 0.0;
+            for (int d = (tid & 3); d < D; d += 4) {
+                const double zv = (double)zr[d];
+                const double a = (double)e0[d] - zv, b = (double)e1[d] - zv;
+                d0 += a * a;
+                d1 += b * b;
+            }
+            const unsigned qmask = 0xFu << (tid & 28);      // only the 4 lanes of this row take this branch together
+            d0 += __shfl_xor_sync(qmask, d0, 1); d0 += __shfl_xor_sync(qmask, d0, 2);
+            d1 += __shfl_xor_sync(qmask, d1, 1); d1 += __shfl_xor_sync(qmask, d1, 2);
+            if ((tid & 3) == 0 && (d1 < d0 || (d1 == d0 && cand < b0))) best_i[lr] = cand;
+        }
     }
     __syncthreads();
     if (tid < LM && m0 + tid < M) idx[m0 + tid] = (int64_t)best_i[tid];
@@ -215,9 +254,9 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ emb, int D, in
 
 extern "C" int vf_vq_lookup(const float* z, const float* Et, const float* esq, int64_t M, int D, int K, int64_t* idx,
                             float* quant, double* diff_sum, vf_stream_t s) {
+    if (M == 0) return VF_OK;
     VF_CHECK_ARG(z && Et && esq && idx, "vf_vq_lookup: null pointer");
     VF_CHECK_ARG(D % 16 == 0 && K > 0 && M >= 0, "vf_vq_lookup: unsupported D=%d K=%d", D, K);
-    if (M == 0) return VF_OK;
     const unsigned blocks = (unsigned)((M + LM - 1) / LM);
     vq_lookup_kernel<<<blocks, 256, 0, vf_s(s)>>>(z, Et, esq, M, D, K, idx, quant, diff_sum);
     VF_CHECK_LAUNCH("vf_vq_lookup");

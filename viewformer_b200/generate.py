@@ -83,10 +83,8 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
     if cameras.dtype != torch.float32:
         cameras = cameras.to(torch.float32)
     gt_cam = cameras[:, -1]
-    transform = None
-    if transformer_model.config.augment_poses == "relative":
-        cameras, transform = to_relative_cameras(cameras)
-    cameras = normalize_cameras(cameras)
+    relative = transformer_model.config.augment_poses == "relative"
+    cams_dev, transform = L.cameras_prepare(cameras.to(dev, non_blocking=True).contiguous(), relative)   # :99-102, one launch
 
     B, T = images.shape[:2]
     size = codebook_model.config.image_size
@@ -98,12 +96,10 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
     img_dev = images.to(device=dev, non_blocking=True) if images.device != dev else images
     side = transformer_model.token_image_size
     n_enc = T if encode_target else T - 1
-    enc_in = img_dev[:, :n_enc].reshape((B * n_enc,) + tuple(img_dev.shape[2:]))
-    if not enc_in.is_contiguous():
-        enc_in = enc_in.contiguous()
-    codes = codebook_model.encode_u8(enc_in).reshape(B, n_enc, side, side)
+    if not img_dev.is_contiguous():
+        img_dev = img_dev.contiguous()
+    codes = codebook_model.encode_u8(img_dev, first_views=n_enc).reshape(B, n_enc, side, side)
 
-    cams_dev = cameras.to(dev)
     gen_codes = transformer_model.generate_codes(codes[:, : T - 1], cams_dev)
     gen_images = codebook_model.decode_code_u8(gen_codes)
 
@@ -112,7 +108,7 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
         gen_cam = reduce_cameras(out["pose_prediction"][:, -1:], -2)
     else:
         gen_cam = cams_dev[:, :1]
-    if transform is not None:
-        gen_cam = from_relative_cameras(gen_cam, transform.to(gen_cam.device))
+    if relative:
+        gen_cam = L.cameras_from_relative(gen_cam.to(dev).contiguous(), transform)
     return dict(ground_truth_images=images[:, -1], generated_images=gen_images, ground_truth_cameras=gt_cam,
                 generated_cameras=gen_cam[:, -1], generated_codes=gen_codes)

@@ -366,10 +366,8 @@ class VQGAN:
         q = self._w["q"]
         d, k = q["emb"].shape
         counts, esum = L.vq_ema_stats(z_rows, idx, k)
-        if self.dist_world_size > 1:
-            packed = torch.cat([counts, esum.reshape(-1)])          # one NCCL call instead of the reference's two
-            torch.distributed.all_reduce(packed)
-            counts, esum = packed[:k].contiguous(), packed[k:].reshape(d, k).contiguous()
+        from .dist import allreduce_ema_stats
+        counts, esum = allreduce_ema_stats(counts, esum)            # one packed NCCL call instead of the reference's two
         q["counter"] += 1
         corr = float(1.0 - torch.pow(torch.tensor(self.decay), torch.tensor(q["counter"], dtype=torch.int64)))
         alpha = 1 - self.decay
@@ -399,10 +397,11 @@ class VQGAN:
         quant, diff, idx = self._quantize(zr)
         return quant.reshape(n, hh, ww, -1), diff, idx.reshape(n, hh, ww)
 
-    def encode_u8(self, images_u8_nhwc):
-        """uint8 NHWC images -> codes int64 [N,h,w] (evaluate_transformer.py:105-110 in one device pass)."""
+    def encode_u8(self, images_u8_nhwc, first_views=None):
+        """uint8 NHWC images -> codes int64 [N,h,w] (evaluate_transformer.py:105-110 in one device pass).
+        With ``first_views=n`` the input is [B,T,H,W,3] and views 0..n-1 of every scene are encoded ([B*n,h,w])."""
         self._need_weights()
-        x = L.u8_to_unit(self._in(images_u8_nhwc, torch.uint8))
+        x = L.u8_to_unit(self._in(images_u8_nhwc, torch.uint8), first_views)
         zr, hh, ww = self.encode_rows(x)
         _, _, idx = self._quantize(zr, want_quant=False)
         return idx.reshape(x.shape[0], hh, ww)
