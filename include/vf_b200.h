@@ -53,13 +53,22 @@ int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W,
  * x f32 [N, HW, C].  vf_groupnorm_stats: sums = double [N, groups, 2] scratch (zeroed + accumulated here),
  * mean_rstd = float [N, groups, 2] result (mean, 1/sqrt(var+eps)) consumed by vf_groupnorm_apply.
  * vf_groupnorm_apply: y = ((x-mean)*rstd*gamma+beta) [swish]; normalize=0 -> plain cast/upsample.
- *   upsample2x=1 writes y as [N, 2H, 2W, C] (needs H, W).  y_dtype VF_F32 | VF_BF16.
+ *   layout: 0 = same shape; 1 = nearest x2 upsample, y is [N, 2H, 2W, C]; 2 = space-to-depth, y is [N, H/2, W/2, 4C]
+ *   with channel block (a*2+b)*C holding pixel (2y+a, 2x+b) — the operand layout that turns the reference's
+ *   pad(0,1,0,1)+stride-2 3x3 conv (vqgan_th.py:45-49) into a stride-1 tap-table conv.  y_dtype VF_F32 | VF_BF16.
  * ---------------------------------------------------------------------------------------- */
 int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* sums, float* mean_rstd,
                        vf_stream_t s);
 int vf_groupnorm_apply(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
                        int N, int H, int W, int C, int groups, float eps, int normalize, int swish,
-                       int upsample2x, void* y, int y_dtype, vf_stream_t s);
+                       int layout, void* y, int y_dtype, vf_stream_t s);
+
+/* Exact fp32 3x3 stride-1 pad-1 convolutions for the two tiny-channel layers (vqgan_th.py:159-163 conv_in 3->128,
+ * :285-289 conv_out 128->3).  NHWC; weights [9*Cin, Cout] fp32 (k = tap*Cin + c). */
+int vf_conv3x3_small_cin(const float* x, const float* w_kn, const float* bias, int N, int H, int W, int Cin, int Cout,
+                         float* y, vf_stream_t s);
+int vf_conv3x3_small_cout(const void* x, int x_dtype, const float* w_kn, const float* bias, int N, int H, int W, int Cin,
+                          int Cout, float* y, vf_stream_t s);
 
 /* LayerNorm over the last dim — replaces tf.keras LayerNormalization at models/migt.py:225-227,292. */
 int vf_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps,

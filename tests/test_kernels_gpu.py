@@ -342,3 +342,35 @@ def test_camera_kernels_and_strided_u8(L):
     got = L.u8_to_unit(u8.cuda(), first_views=3).cpu()
     want = (u8[:, :3].float() * torch.tensor(1.0 / 255.0) * 2 - 1).reshape(9, 8, 8, 3)
     assert torch.equal(got, want)
+
+
+def test_small_channel_convs(L):
+    x = torch.randn(3, 3, 37, 70, generator=g(90))
+    w = torch.randn(128, 3, 3, 3, generator=g(91)) / 27 ** 0.5
+    b = torch.randn(128, generator=g(92))
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    got = L.conv3x3_small_cin(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w).cuda(), b.cuda())
+    report("conv_in small_cin", got.permute(0, 3, 1, 2), want, 2e-5, 1e-5)
+    x = torch.randn(2, 128, 19, 45, generator=g(93))
+    w = torch.randn(3, 128, 3, 3, generator=g(94)) / 1152 ** 0.5
+    b = torch.randn(3, generator=g(95))
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    report("conv_out small_cout f32", L.conv3x3_small_cout(xh, _w_kn(w).cuda(), b.cuda()).permute(0, 3, 1, 2), want, 2e-5, 1e-5)
+    want16 = F.conv2d(x.bfloat16().double(), w.double(), b.double(), padding=1)
+    report("conv_out small_cout bf16", L.conv3x3_small_cout(xh.bfloat16(), _w_kn(w).cuda(), b.cuda()).permute(0, 3, 1, 2), want16, 2e-5, 1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,n,hw", [(64, 128, 2, 16), (128, 128, 1, 32), (256, 256, 3, 8)])
+def test_tc_downsample_space_to_depth(L, cin, cout, n, hw):
+    """pad(0,1,0,1) + stride-2 3x3 conv (vqgan_th.py:45-49) as a stride-1 tap-table conv over the space-to-depth operand."""
+    x = torch.randn(n, cin, hw, hw, generator=g(cin))
+    w = (torch.randn(cout, cin, 3, 3, generator=g(96)) / (9 * cin) ** 0.5).bfloat16()
+    b = torch.randn(cout, generator=g(97))
+    xs = L.groupnorm(x.permute(0, 2, 3, 1).contiguous().cuda(), None, None, swish=False, out_dtype=torch.bfloat16, normalize=False, s2d=True)
+    assert list(xs.shape) == [n, hw // 2, hw // 2, 4 * cin]
+    want = F.conv2d(F.pad(x.bfloat16().double(), (0, 1, 0, 1)), w.double(), b.double(), stride=2)
+    w_nk = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous().cuda()
+    got = L.tc_conv(xs, w_nk, b.cuda(), taps=L.TAPS_S2D, coffs=L.s2d_coffs(cin), cin=cin)
+    torch.cuda.synchronize()
+    report(f"tc downsample {cin}->{cout} hw{hw}", got.permute(0, 3, 1, 2), want, 3e-3, 3e-3)

@@ -22,6 +22,7 @@ EXPORTS = [
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
+    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout",
 ]
 
 
@@ -178,7 +179,7 @@ def nhwc_to_nchw(x):
 
 
 # ----------------------------------------------------------------------------------------------- norms
-def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample=False, normalize=True):
+def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample=False, normalize=True, s2d=False):
     """x f32 [N,H,W,C] -> GroupNorm(32) [+swish] [+nearest x2] as out_dtype (vqgan_th.py:11-17,29-30)."""
     lib = load(True)
     _dev(x, torch.float32)
@@ -188,10 +189,10 @@ def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample
         sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
         stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)      # (mean, rstd)
         _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
-    oshape = (n, 2 * h, 2 * w, c) if upsample else (n, h, w, c)
+    oshape = (n, 2 * h, 2 * w, c) if upsample else ((n, h // 2, w // 2, 4 * c) if s2d else (n, h, w, c))
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
     _check(lib.vf_groupnorm_apply(_p(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
-                                  int(normalize), int(swish), int(upsample), _p(y), _dt(y), _stream()))
+                                  int(normalize), int(swish), 1 if upsample else (2 if s2d else 0), _p(y), _dt(y), _stream()))
     return y
 
 
@@ -304,6 +305,34 @@ def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_b
 
 
 TAPS_3x3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+# stride-2 conv over a space-to-depth operand: filter tap (dy,dx) in 0..2 reads phase (dy%2, dx%2) at offset (dy//2, dx//2)
+TAPS_S2D = [(dy // 2, dx // 2) for dy in (0, 1, 2) for dx in (0, 1, 2)]
+
+
+def s2d_coffs(c):
+    return [((dy % 2) * 2 + (dx % 2)) * c for dy in (0, 1, 2) for dx in (0, 1, 2)]
+
+
+def conv3x3_small_cin(x, w_kn, bias):
+    """exact fp32 conv_in (Cin=3): x f32 [N,H,W,3], w_kn [27, Cout]."""
+    lib = load(True)
+    _dev(x, torch.float32)
+    n, h, w, cin = x.shape
+    cout = w_kn.shape[1]
+    y = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
+    _check(lib.vf_conv3x3_small_cin(_p(x), _p(w_kn), _p(bias), n, h, w, cin, cout, _p(y), _stream()))
+    return y
+
+
+def conv3x3_small_cout(x, w_kn, bias):
+    """exact fp32-accumulate conv_out (128 -> 3): x f32|bf16 [N,H,W,128], w_kn [1152, 3]."""
+    lib = load(True)
+    _dev(x)
+    n, h, w, cin = x.shape
+    cout = w_kn.shape[1]
+    y = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
+    _check(lib.vf_conv3x3_small_cout(_p(x), _dt(x), _p(w_kn), _p(bias), n, h, w, cin, cout, _p(y), _stream()))
+    return y
 
 
 def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, residual=None, out=None,

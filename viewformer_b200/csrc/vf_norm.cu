@@ -110,8 +110,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     if (swish) {
         v.x = vf_swish(v.x); v.y = vf_swish(v.y); v.z = vf_swish(v.z); v.w = vf_swish(v.w);
     }
-    if (!up) {
+    if (up == 0) {
         store4<OutT>(y + i * 4, v.x, v.y, v.z, v.w);
+    } else if (up == 2) {          // space-to-depth: [N,H,W,C] -> [N,H/2,W/2,4C], block (a*2+b) <- pixel (2y+a, 2x+b)
+        const int xx = (int)(pix % W);
+        const int64_t t = pix / W;
+        const int yy = (int)(t % H);
+        const int64_t n = t / H;
+        const int64_t o = (((n * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1)) * 4 + ((yy & 1) * 2 + (xx & 1))) * C + cq * 4;
+        store4<OutT>(y + o, v.x, v.y, v.z, v.w);
     } else {
         const int xx = (int)(pix % W);
         const int64_t t = pix / W;
@@ -202,6 +209,7 @@ extern "C" int vf_groupnorm_apply(const float* x, const float* stats, const floa
                                   void* y, int y_dtype, vf_stream_t s) {
     VF_CHECK_ARG(x && y, "vf_groupnorm_apply: null pointer");
     VF_CHECK_ARG(C % 4 == 0, "vf_groupnorm_apply: C %% 4");
+    VF_CHECK_ARG(upsample2x != 2 || (H % 2 == 0 && W % 2 == 0), "vf_groupnorm_apply: space-to-depth needs even H, W");
     if (normalize) {
         VF_CHECK_ARG(stats && gamma && beta, "vf_groupnorm_apply: normalize needs stats/gamma/beta");
         VF_CHECK_ARG(C % groups == 0, "vf_groupnorm_apply: unsupported C=%d groups=%d", C, groups);

@@ -34,6 +34,8 @@ class _Conv3:
         w = w.to(device=device, dtype=torch.float32)
         self.bias = b.to(device=device, dtype=torch.float32).contiguous()
         self.tc = (not exact) and prec.use_tc and kh == 3 and cin % prec.k_align == 0 and cout % 16 == 0 and cout >= 64
+        self.small_cin = kh == 3 and cin == 3 and cout % 16 == 0 and cout <= 128     # conv_in: dedicated exact kernel
+        self.small_cout = kh == 3 and cin == 128 and cout == 3                       # conv_out: dedicated exact kernel
         if self.tc:
             self.w_nk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(prec.opd).contiguous()   # [Cout, tap*Cin+c]
         else:
@@ -231,7 +233,7 @@ class VQGAN:
                 blocks.append(rb(f"encoder.down.{lv}.block.{b}"))
                 if res[lv] in cfg.attn_resolutions:
                     attns.append(at(f"encoder.down.{lv}.attn.{len(attns)}"))
-            down = conv(f"encoder.down.{lv}.downsample.conv", exact=True) if lv != nres - 1 else None
+            down = conv(f"encoder.down.{lv}.downsample.conv") if lv != nres - 1 else None
             enc["levels"].append(dict(blocks=blocks, attns=attns, down=down))
         enc.update(mid1=rb("encoder.mid.block_1"), mida=at("encoder.mid.attn_1"), mid2=rb("encoder.mid.block_2"),
                    norm_out=gn("encoder.norm_out"), conv_out=conv("encoder.conv_out"))
@@ -266,8 +268,15 @@ class VQGAN:
 
     # ------------------------------------------------------------------ building blocks (NHWC f32 in / out)
     def _conv(self, cw, x_opd_or_f32, *, residual=None, stride=1, upsample=False):
+        if cw.tc and stride == 2:    # operand is the space-to-depth tensor [N,H/2,W/2,4C]: stride-1 tap-table conv
+            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, taps=L.TAPS_S2D, coffs=L.s2d_coffs(cw.cin), cin=cw.cin)
         if cw.tc:
             return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, residual=residual)
+        if stride == 1 and not upsample and residual is None and x_opd_or_f32.dtype == torch.float32:
+            if cw.small_cin:
+                return L.conv3x3_small_cin(x_opd_or_f32, cw.w_kn, cw.bias)
+            if cw.small_cout:
+                return L.conv3x3_small_cout(x_opd_or_f32, cw.w_kn, cw.bias)
         pad = (1, 1) if stride == 1 else (0, 0)     # Downsample: pad (0,1,0,1) then VALID stride-2 (vqgan_th.py:45-49)
         return L.simt_conv(x_opd_or_f32, cw.w_kn, cw.bias, kh=cw.k, stride=stride, pad=pad if cw.k == 3 else (0, 0),
                            upsample=upsample, residual=residual)
@@ -319,7 +328,14 @@ class VQGAN:
                 if lvw["attns"]:
                     h = self._attn(lvw["attns"][i], h)
             if lvw["down"] is not None:
-                h = self._conv(lvw["down"], h, stride=2)
+                down = lvw["down"]
+                if down.tc and h.shape[1] % 2 == 0 and h.shape[2] % 2 == 0:
+                    hs = L.groupnorm(h, None, None, swish=False, out_dtype=self.prec.opd, normalize=False, s2d=True)
+                    h = self._conv(down, hs, stride=2)
+                else:
+                    if down.tc:
+                        raise NotImplementedError("odd feature-map size in Downsample on the tensor-core path")
+                    h = self._conv(down, h, stride=2)
         h = self._resblock(e["mid1"], h)
         h = self._attn(e["mida"], h)
         h = self._resblock(e["mid2"], h)
