@@ -3,10 +3,8 @@
 set -u
 mkdir -p gpurun_out
 python -m viewformer_b200.build > gpurun_out/build.log 2>&1
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "vq_lookup" -p no:cacheprovider 2>&1 | tail -3
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py > gpurun_out/prof_step.log 2>&1
 echo "launch list rc=$?"
-python scripts/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.md 2>&1; head -30 gpurun_out/launches_summary.md
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tc_gemm -s 4 -c 2 -o gpurun_out/prof_conv -f python scripts/profile_step.py --part encode > gpurun_out/prof_conv.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.md 2>&1; head -24 gpurun_out/launches_summary.md
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tc_gemm -s 1 -c 1 -o gpurun_out/prof_conv -f python scripts/profile_step.py --part encode > gpurun_out/prof_conv.log 2>&1
 echo "full capture rc=$?"
-ls -la gpurun_out/

@@ -43,6 +43,7 @@ struct TcParams {
     __nv_bfloat16* C_bf16;
     long long ldc, c_sb1, c_sb2;
     unsigned idesc;
+    int vec_ok;                // output/residual/bias addressing is 16-byte friendly -> vector epilogue
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -318,51 +319,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             }
             const float bias_m = (p.bias_mode == VF_BIAS_M && my_ok) ? __ldg(p.bias + gm) : 0.f;
 
+            // phase-2 geometry: VPR float4 vectors span one tile row; a warp covers RPI rows per iteration
+            constexpr int VPR = kBlockN / 4;               // 32 (BLOCK_N=128) or 16 (BLOCK_N=64)
+            constexpr int RPI = 32 / VPR;                  // 1 or 2 rows per iteration
+            constexpr int ITERS = 32 / RPI;
+            const int r_sub = lane / VPR;
+            const int c_ln = (lane % VPR) * 4;
+            const int n_ln = ti.n0 + c_ln;
+            // fast path: full-width tile, 16-byte aligned rows -> vector I/O and the whole residual tile prefetched into
+            // registers BEFORE waiting for the accumulator, so its DRAM latency hides behind this tile's MMAs
+            const bool fast = p.vec_ok && (ti.n0 + kBlockN <= p.Ncols);
+            float4 resv[ITERS];
+            if (fast && p.residual) {
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i) {
+                    const int rr = i * RPI + r_sub;
+                    const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
+                    const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
+                    resv[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + off_row + n_ln)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fast && p.bias_mode == VF_BIAS_N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_ln));
+
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
 
-            // ---- phase 1: TMEM -> registers -> (alpha, bias, activation) -> staging row `lane`
+            // ---- phase 1: TMEM -> registers -> staging row `lane` (scaled by alpha)
 #pragma unroll 1
             for (int c0 = 0; c0 < kBlockN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN + c0), r);
-                const int nbase = ti.n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = __uint_as_float(r[j + e]) * p.alpha;
-                        if (p.bias_mode == VF_BIAS_N) x += (nbase + j + e < p.Ncols) ? __ldg(p.bias + nbase + j + e) : 0.f;
-                        else x += bias_m;
-                        if (p.act == VF_ACT_GELU_ERF) x = vf_gelu_erf(x);
-                        v[e] = x;
-                    }
-                    *reinterpret_cast<float4*>(stg + lane * STG_LD + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
-                }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + c0 + j) =
+                        make_float4(__uint_as_float(r[j]) * p.alpha, __uint_as_float(r[j + 1]) * p.alpha,
+                                    __uint_as_float(r[j + 2]) * p.alpha, __uint_as_float(r[j + 3]) * p.alpha);
             }
             // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld) -> hand the stage back
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
 
-            // ---- phase 2: one tile row per iteration, lanes span the columns -> fully coalesced residual loads / stores
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-                const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
-                const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
-                if (!ok) continue;
+            // ---- phase 2: lanes span the columns of a tile row -> fully coalesced stores; bias / activation / residual here
+            if (fast) {
 #pragma unroll
-                for (int c = lane * 4; c < kBlockN; c += 128) {
-                    const int n = ti.n0 + c;
-                    if (n >= p.Ncols) continue;
-                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c);
-                    const long long off = off_row + n;
-                    if (n + 4 <= p.Ncols && ((off & 3) == 0)) {
-                        if (p.residual) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off));
-                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-                        }
+                for (int i = 0; i < ITERS; ++i) {
+                    const int rr = i * RPI + r_sub;
+                    const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
+                    const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
+                    const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c_ln);
+                    if (p.bias_mode == VF_BIAS_N) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+                    else { v.x += bm; v.y += bm; v.z += bm; v.w += bm; }
+                    if (p.act == VF_ACT_GELU_ERF) { v.x = vf_gelu_erf(v.x); v.y = vf_gelu_erf(v.y); v.z = vf_gelu_erf(v.z); v.w = vf_gelu_erf(v.w); }
+                    if (p.residual) { v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w; }
+                    if (ok) {
+                        const long long off = off_row + n_ln;
                         if (p.C_f32) *reinterpret_cast<float4*>(p.C_f32 + off) = v;
                         if (p.C_bf16) {
                             __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -371,14 +384,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                             u.y = *reinterpret_cast<uint32_t*>(&hi);
                             *reinterpret_cast<uint2*>(p.C_bf16 + off) = u;
                         }
-                    } else {
-                        const float vv[4] = {v.x, v.y, v.z, v.w};
-                        for (int e = 0; e < 4 && n + e < p.Ncols; ++e) {
-                            float x = vv[e];
-                            if (p.residual) x += __ldg(p.residual + off + e);
-                            if (p.C_f32) p.C_f32[off + e] = x;
-                            if (p.C_bf16) p.C_bf16[off + e] = __float2bfloat16(x);
-                        }
+                    }
+                }
+            } else {
+                // generic path (N tails, unaligned leading dimensions): scalar, same arithmetic order
+#pragma unroll 1
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
+                    const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
+                    const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
+                    if (!ok) continue;
+                    for (int c = lane; c < kBlockN; c += 32) {
+                        const int n = ti.n0 + c;
+                        if (n >= p.Ncols) continue;
+                        float x = stg[rr * STG_LD + c];
+                        x += (p.bias_mode == VF_BIAS_N) ? __ldg(p.bias + n) : bm;
+                        if (p.act == VF_ACT_GELU_ERF) x = vf_gelu_erf(x);
+                        const long long off = off_row + n;
+                        if (p.residual) x += __ldg(p.residual + off);
+                        if (p.C_f32) p.C_f32[off] = x;
+                        if (p.C_bf16) p.C_bf16[off] = __float2bfloat16(x);
                     }
                 }
             }
@@ -564,6 +589,12 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     }
     const dim3 pgrid((unsigned)(total < num_sms ? total : num_sms), 1, 1);
     prm.idesc = make_idesc(tf32, BLOCK_M, block_n);
+    {
+        auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+        prm.vec_ok = (q->ldc % 4 == 0) && (q->c_sb1 % 4 == 0) && (q->c_sb2 % 4 == 0) && a16(q->C_f32) && a8(q->C_bf16) && a16(q->residual) &&
+                     a16(q->bias);
+    }
     cudaStream_t st = vf_s(s);
     if (block_n == 128) return tf32 ? launch<128, 4, true>(prm, pgrid, st) : launch<128, 4, false>(prm, pgrid, st);
     return tf32 ? launch<64, 6, true>(prm, pgrid, st) : launch<64, 6, false>(prm, pgrid, st);
