@@ -213,6 +213,11 @@ def run_b200(args):
 
     for _ in range(max(3, args.warmup)):
         step_resident()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_resident()                      # host-side enqueue time of one step (launch-bound check), not part of the timed region
+    host_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
     _lib.reset_launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -285,7 +290,7 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (15.7 MB images + 2.4 GB activations per step); no flush needed"},
         "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(in_bytes),
                 "d2h_bytes_per_step": int(out_pin.numel())},
-        "gpu_launches": launches,
+        "gpu_launches": launches // max(1, args.steps), "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,

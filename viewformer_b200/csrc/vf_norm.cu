@@ -76,18 +76,14 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a,
     *reinterpret_cast<uint2*>(p) = u;
 }
 
+// per-element body: normalise / swish / layout-store one channel quad
 template <typename OutT>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       int N, int H, int W, int C, int groups, float eps, int normalize,
-                                                       int swish, int up, OutT* __restrict__ y) {
+__device__ __forceinline__ void gn_apply_one(float4 v, int64_t i, const float* __restrict__ mr, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, int H, int W, int C, int groups, int normalize,
+                                             int swish, int up, OutT* __restrict__ y) {
     const int quads = C >> 2;
-    const int64_t total = (int64_t)N * H * W * quads;
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= total) return;
     const int cq = (int)(i % quads);
     const int64_t pix = i / quads;                 // n*H*W + y*W + x
-    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     if (normalize) {
         const int n = (int)(pix / ((int64_t)H * W));
         const int cpg = C / groups;
@@ -130,6 +126,27 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         store4<OutT>(y + o + C, v.x, v.y, v.z, v.w);
         store4<OutT>(y + o + W2 * C, v.x, v.y, v.z, v.w);
         store4<OutT>(y + o + W2 * C + C, v.x, v.y, v.z, v.w);
+    }
+}
+
+// 4 channel quads per thread, all four 128-bit loads issued before any use (64 B in flight per thread)
+template <typename OutT>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int N, int H, int W, int C, int groups, float eps, int normalize,
+                                                       int swish, int up, OutT* __restrict__ y) {
+    const int64_t total = (int64_t)N * H * W * (C >> 2);
+    const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = base + k * 256;
+        v[k] = __ldg(reinterpret_cast<const float4*>(x) + (i < total ? i : total - 1));     // unconditional: keeps 4 loads in flight
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = base + k * 256;
+        if (i < total) gn_apply_one<OutT>(v[k], i, mr, gamma, beta, H, W, C, groups, normalize, swish, up, y);
     }
 }
 
@@ -215,7 +232,7 @@ extern "C" int vf_groupnorm_apply(const float* x, const float* stats, const floa
         VF_CHECK_ARG(C % groups == 0, "vf_groupnorm_apply: unsupported C=%d groups=%d", C, groups);
     }
     const int64_t total = (int64_t)N * H * W * (C / 4);
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const unsigned blocks = (unsigned)((total + 1023) / 1024);
     if (y_dtype == VF_F32)
         gn_apply_kernel<float><<<blocks, 256, 0, vf_s(s)>>>(x, stats, gamma, beta, N, H, W, C, groups, eps, normalize, swish,
                                                             upsample2x, reinterpret_cast<float*>(y));

@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     const int rr = i * RPI + r_sub;
                     const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
                     const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
-                    resv[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + off_row + n_ln)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // unconditional load (out-of-range rows read row 0 and are never stored): a predicated load would make
+                    // the compiler funnel all 32 loads through one temporary and serialise their DRAM latencies
+                    const long long o = ok ? off_row + n_ln : (long long)n_ln;
+                    resv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + o));
                 }
             }
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
