@@ -4,7 +4,7 @@
 //   -> tcgen05.mma.cta_group::1 (one elected thread, fp32 accumulator in TMEM, M=128, N=BLOCK_N)
 //   -> tcgen05.ld epilogue (4 warps, one TMEM lane quarter each): alpha, bias, GELU, residual, f32/bf16 stores.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.
 // One CTA computes one 128 x BLOCK_N output tile.  GEMM operands are K-major; the convolution reads its A
 // operand straight from the NHWC activation tensor with a 4-D tensor map: for every filter tap the box
 // [TN images x TH rows x TW cols x 64 channels] shifted by (dy,dx) lands in shared memory as a 128-row K-major
@@ -21,7 +21,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;                 // one swizzle-128B row = one K block
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                // 2 warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct TcParams {
     CUtensorMap tmA, tmB;
@@ -186,8 +187,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int UMMA_K_BYTES = 32;           // 16 bf16 or 8 tf32 per instruction
     constexpr int MMAS_PER_STAGE = ROW_BYTES / UMMA_K_BYTES;
-    constexpr int STG_LD = kBlockN + 4;        // staging row stride (floats): +4 keeps 128-bit row writes conflict-free
-    constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+    constexpr int HALF_N = kBlockN / 2;        // columns per epilogue warp
+    constexpr int STG_LD = HALF_N + 4;         // staging row stride (floats): +4 keeps 128-bit row writes conflict-free
+    constexpr int STG_BYTES = NUM_EPI_WARPS * 32 * STG_LD * 4;
 
     extern __shared__ uint8_t smem_raw[];
     // 1024B alignment required by the 128B swizzle atoms (descriptor base_offset = 0)
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 4);           // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);   // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -288,9 +290,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quarter = warp & 3;                     // TMEM lanes [32q, 32q+32) are only visible to warps with id%4 == q
-        float* stg = staging + quarter * (32 * STG_LD);   // this warp's private staging tile [32][STG_LD]
+        const int col_half = (warp - 2) >> 2;             // which half of the tile's columns this warp owns
+        float* stg = staging + (warp - 2) * (32 * STG_LD);   // this warp's private staging tile [32][STG_LD]
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileInfo ti = decode_tile(p, t, kBlockN);
@@ -320,12 +323,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             const float bias_m = (p.bias_mode == VF_BIAS_M && my_ok) ? __ldg(p.bias + gm) : 0.f;
 
             // phase-2 geometry: VPR float4 vectors span one tile row; a warp covers RPI rows per iteration
-            constexpr int VPR = kBlockN / 4;               // 32 (BLOCK_N=128) or 16 (BLOCK_N=64)
-            constexpr int RPI = 32 / VPR;                  // 1 or 2 rows per iteration
+            constexpr int VPR = HALF_N / 4;                // 16 (BLOCK_N=128) or 8 (BLOCK_N=64) vectors per half row
+            constexpr int RPI = 32 / VPR;                  // 2 or 4 rows per iteration
             constexpr int ITERS = 32 / RPI;
             const int r_sub = lane / VPR;
-            const int c_ln = (lane % VPR) * 4;
-            const int n_ln = ti.n0 + c_ln;
+            const int c_ln = (lane % VPR) * 4;             // column inside this warp's half
+            const int n_ln = ti.n0 + col_half * HALF_N + c_ln;
             // fast path: full-width tile, 16-byte aligned rows -> vector I/O and the whole residual tile prefetched into
             // registers BEFORE waiting for the accumulator, so its DRAM latency hides behind this tile's MMAs
             const bool fast = p.vec_ok && (ti.n0 + kBlockN <= p.Ncols);
@@ -350,9 +353,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 
             // ---- phase 1: TMEM -> registers -> staging row `lane` (scaled by alpha)
 #pragma unroll 1
-            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            for (int c0 = 0; c0 < HALF_N; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN + c0), r);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN + col_half * HALF_N + c0), r);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * STG_LD + c0 + j) =
@@ -397,8 +400,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
                     const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
                     if (!ok) continue;
-                    for (int c = lane; c < kBlockN; c += 32) {
-                        const int n = ti.n0 + c;
+                    for (int c = lane; c < HALF_N; c += 32) {
+                        const int n = ti.n0 + col_half * HALF_N + c;
                         if (n >= p.Ncols) continue;
                         float x = stg[rr * STG_LD + c];
                         x += (p.bias_mode == VF_BIAS_N) ? __ldg(p.bias + n) : bm;
@@ -477,7 +480,7 @@ unsigned make_idesc(bool tf32, int M, int N) {
 
 template <int kBlockN, int kStages, bool kTF32>
 int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
-    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + 4 * 32 * (kBlockN + 4) * 4 /*epilogue staging*/ +
+    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ +
                          1024 /*align slack*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
