@@ -24,7 +24,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
     if (pl < lanes) {
         const float4* base = reinterpret_cast<const float4*>(x + (int64_t)n * HW * C) + cq;
-        for (int p = p0 + pl; p < p1; p += lanes) {
+        int p = p0 + pl;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {          // 4 independent 128-bit loads in flight
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldg(base + (int64_t)(p + k * lanes) * quads);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s[0] += v[k].x; s[1] += v[k].y; s[2] += v[k].z; s[3] += v[k].w;
+                ss[0] += v[k].x * v[k].x; ss[1] += v[k].y * v[k].y; ss[2] += v[k].z * v[k].z; ss[3] += v[k].w * v[k].w;
+            }
+        }
+        for (; p < p1; p += lanes) {
             const float4 v = __ldg(base + (int64_t)p * quads);
             s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
             ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
@@ -78,14 +89,12 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a,
 
 // per-element body: normalise / swish / layout-store one channel quad
 template <typename OutT>
-__device__ __forceinline__ void gn_apply_one(float4 v, int64_t i, const float* __restrict__ mr, const float* __restrict__ gamma,
-                                             const float* __restrict__ beta, int H, int W, int C, int groups, int normalize,
-                                             int swish, int up, OutT* __restrict__ y) {
-    const int quads = C >> 2;
-    const int cq = (int)(i % quads);
-    const int64_t pix = i / quads;                 // n*H*W + y*W + x
+__device__ __forceinline__ void gn_apply_one(float4 v, int64_t i, int cq, unsigned pix, const float* __restrict__ mr,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta, int H, int W, int C,
+                                             int groups, int normalize, int swish, int up, OutT* __restrict__ y) {
+    // pix = n*H*W + y*W + x (32-bit: 64-bit integer division costs more than the memory traffic of this kernel)
     if (normalize) {
-        const int n = (int)(pix / ((int64_t)H * W));
+        const int n = (int)(pix / (unsigned)(H * W));
         const int cpg = C / groups;
         const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
@@ -109,17 +118,17 @@ __device__ __forceinline__ void gn_apply_one(float4 v, int64_t i, const float* _
     if (up == 0) {
         store4<OutT>(y + i * 4, v.x, v.y, v.z, v.w);
     } else if (up == 2) {          // space-to-depth: [N,H,W,C] -> [N,H/2,W/2,4C], block (a*2+b) <- pixel (2y+a, 2x+b)
-        const int xx = (int)(pix % W);
-        const int64_t t = pix / W;
-        const int yy = (int)(t % H);
-        const int64_t n = t / H;
+        const int xx = (int)(pix % (unsigned)W);
+        const unsigned t = pix / (unsigned)W;
+        const int yy = (int)(t % (unsigned)H);
+        const int64_t n = t / (unsigned)H;
         const int64_t o = (((n * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1)) * 4 + ((yy & 1) * 2 + (xx & 1))) * C + cq * 4;
         store4<OutT>(y + o, v.x, v.y, v.z, v.w);
     } else {
-        const int xx = (int)(pix % W);
-        const int64_t t = pix / W;
-        const int yy = (int)(t % H);
-        const int64_t n = t / H;
+        const int xx = (int)(pix % (unsigned)W);
+        const unsigned t = pix / (unsigned)W;
+        const int yy = (int)(t % (unsigned)H);
+        const int64_t n = t / (unsigned)H;
         const int64_t W2 = 2 * (int64_t)W;
         const int64_t o = ((n * 2 * H + 2 * yy) * W2 + 2 * xx) * C + cq * 4;
         store4<OutT>(y + o, v.x, v.y, v.z, v.w);
@@ -135,8 +144,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int N, int H, int W, int C, int groups, float eps, int normalize,
                                                        int swish, int up, OutT* __restrict__ y) {
-    const int64_t total = (int64_t)N * H * W * (C >> 2);
+    const int quads = C >> 2;                               // 256 % quads == 0 (checked by the launcher)
+    const int64_t total = (int64_t)N * H * W * quads;
     const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int cq = threadIdx.x % quads;                      // constant across the 4 items: their stride (256) is a multiple of quads
+    const unsigned ppi = 256 / quads;                        // pixels advanced per item
+    const unsigned pix0 = blockIdx.x * (4 * ppi) + threadIdx.x / quads;
     float4 v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -146,7 +159,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t i = base + k * 256;
-        if (i < total) gn_apply_one<OutT>(v[k], i, mr, gamma, beta, H, W, C, groups, normalize, swish, up, y);
+        if (i < total) gn_apply_one<OutT>(v[k], i, cq, pix0 + k * ppi, mr, gamma, beta, H, W, C, groups, normalize, swish, up, y);
     }
 }
 
@@ -225,7 +238,8 @@ extern "C" int vf_groupnorm_apply(const float* x, const float* stats, const floa
                                   int H, int W, int C, int groups, float eps, int normalize, int swish, int upsample2x,
                                   void* y, int y_dtype, vf_stream_t s) {
     VF_CHECK_ARG(x && y, "vf_groupnorm_apply: null pointer");
-    VF_CHECK_ARG(C % 4 == 0, "vf_groupnorm_apply: C %% 4");
+    VF_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "vf_groupnorm_apply: unsupported C=%d", C);
+    VF_CHECK_ARG((int64_t)N * H * W < (1ll << 32), "vf_groupnorm_apply: too many pixels");
     VF_CHECK_ARG(upsample2x != 2 || (H % 2 == 0 && W % 2 == 0), "vf_groupnorm_apply: space-to-depth needs even H, W");
     if (normalize) {
         VF_CHECK_ARG(stats && gamma && beta, "vf_groupnorm_apply: normalize needs stats/gamma/beta");
