@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenes", type=int, default=32, help="scenes per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
-    ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -119,7 +119,19 @@ def cpu_reference_views_per_s(n_scenes, steps, warmup, vq_sd, migt_sd, vcfg, tcf
     host cores: generate_batch_predictions, 10 encodes + dense masked attention + full-sequence LM head as the
     reference executes them (evaluate_transformer.py:97-146)."""
     from oracle import vqgan_oracle as vo, migt_oracle as mo
-    cores = os.cpu_count()
+    # thread count: the fastest of a few candidates on a 2-image encode (all 128 logical CPUs of the GPU box
+    # oversubscribe MKL/oneDNN by 20x; the baseline should be the reference at its best)
+    probe = torch.rand(2, 3, IMG, IMG) * 2 - 1
+    best, cores = None, 1
+    with torch.no_grad():
+        for nt in sorted({min(os.cpu_count(), c) for c in (8, 16, 32, 64)}):
+            torch.set_num_threads(nt)
+            vo.encode(vq_sd, vcfg, probe[:1])
+            t0 = time.perf_counter()
+            vo.encode(vq_sd, vcfg, probe)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, cores = dt, nt
     torch.set_num_threads(cores)
     images, cams = synth_inputs(n_scenes, 777)
     fwd = lambda d: mo.forward(migt_sd, tcfg, d, use_localization=False)
@@ -128,8 +140,9 @@ def cpu_reference_views_per_s(n_scenes, steps, warmup, vq_sd, migt_sd, vcfg, tcf
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
+            im, cm = (images[:1], cams[:1]) if i < warmup else (images, cams)      # warm-up on one scene only
             t0 = time.perf_counter()
-            mo.generate_batch_predictions(fwd, enc, dec, tcfg, images, cams, use_localization=False)
+            mo.generate_batch_predictions(fwd, enc, dec, tcfg, im, cm, use_localization=False)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
@@ -276,7 +289,7 @@ def run_b200(args):
         n = max(1, args.cpu_scenes)
         vps, sec, cores = cpu_reference_views_per_s(n, 1, 1, vq_sd, migt_sd, vcfg, tcfg)
         cpu = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
-               "sample": f"{n} scenes x {T_VIEWS} views, 1 timed pass after 1 warm-up, torch-CPU fp32 oracle of the reference algorithm "
+               "sample": f"{n} scenes x {T_VIEWS} views, 1 timed pass after a 1-scene warm-up, best-of-{{8,16,32,64}} threads, torch-CPU fp32 oracle of the reference algorithm "
                          f"(10 encodes, dense masked attention, full LM head)"}
 
     in_bytes = images_pin.numel() + cams_pin.numel() * 4

@@ -59,6 +59,8 @@ int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W,
  * ---------------------------------------------------------------------------------------- */
 int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* sums, float* mean_rstd,
                        vf_stream_t s);
+/* (sum, sumsq) -> (mean, rstd) for `count` elements per (image, group); n_stats = images*groups */
+int vf_groupnorm_finalize(const double* sums, int n_stats, double count, float eps, float* mean_rstd, vf_stream_t s);
 int vf_groupnorm_apply(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
                        int N, int H, int W, int C, int groups, float eps, int normalize, int swish,
                        int layout, void* y, int y_dtype, vf_stream_t s);
@@ -128,6 +130,10 @@ typedef struct {
     /* epilogue */
     float alpha; const float* bias; int bias_mode; int act; const float* residual;
     float* C_f32; void* C_bf16; int64_t ldc, c_sb1, c_sb2;
+    /* optional: GroupNorm statistics of the OUTPUT fused into the epilogue (vqgan_th.py:16-17 of the NEXT layer):
+       gn_sums double [images, gn_groups, 2] is zeroed and receives (sum, sum of squares) per image and group;
+       an image = OH*OW consecutive rows (conv) or gn_rows_per_img rows (gemm).  Feed it to vf_groupnorm_finalize. */
+    double* gn_sums; int gn_groups; int gn_rows_per_img;
 } vf_tc_gemm_t;
 int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
 

@@ -374,3 +374,23 @@ def test_tc_downsample_space_to_depth(L, cin, cout, n, hw):
     got = L.tc_conv(xs, w_nk, b.cuda(), taps=L.TAPS_S2D, coffs=L.s2d_coffs(cin), cin=cin)
     torch.cuda.synchronize()
     report(f"tc downsample {cin}->{cout} hw{hw}", got.permute(0, 3, 1, 2), want, 3e-3, 3e-3)
+
+
+@pytest.mark.parametrize("cin,cout,n,hw", [(128, 128, 3, 16), (128, 256, 2, 8), (256, 512, 5, 8)])
+def test_tc_conv_fused_groupnorm_statistics(L, cin, cout, n, hw):
+    """GroupNorm(32) statistics accumulated in the conv epilogue == statistics of the stored output."""
+    x = torch.randn(n, hw, hw, cin, generator=g(cin + n)).bfloat16().cuda()
+    w = (torch.randn(cout, 9 * cin, generator=g(98)) / (9 * cin) ** 0.5).bfloat16().cuda()
+    b = torch.randn(cout, generator=g(99)).cuda()
+    res = torch.randn(n, hw, hw, cout, generator=g(100)).cuda()
+    out = L.tc_conv(x, w, b, residual=res, gn_groups=32)
+    assert hasattr(out, "_gn_sums"), "fusion expected for this shape"
+    sums = out._gn_sums[0].cpu()
+    o = out.double().cpu().reshape(n, hw * hw, 32, cout // 32)
+    want = torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1)
+    report("fused gn sums", sums, want, 1e-2, 1e-5)
+    ga, be = (1 + 0.1 * torch.randn(cout, generator=g(101))).cuda(), (0.1 * torch.randn(cout, generator=g(102))).cuda()
+    y_fused = L.groupnorm(out, ga, be, swish=True, out_dtype=torch.float32)
+    plain = out.clone()                                        # clone drops the attached statistics -> stats kernel path
+    y_plain = L.groupnorm(plain, ga, be, swish=True, out_dtype=torch.float32)
+    report("gn via fused stats vs stats kernel", y_fused, y_plain, 2e-5, 1e-5)

@@ -22,7 +22,7 @@ EXPORTS = [
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
-    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout",
+    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize",
 ]
 
 
@@ -55,6 +55,7 @@ class TcGemm(C.Structure):
         ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_mode", C.c_int), ("act", C.c_int),
         ("residual", C.c_void_p), ("C_f32", C.c_void_p), ("C_bf16", C.c_void_p),
         ("ldc", C.c_int64), ("c_sb1", C.c_int64), ("c_sb2", C.c_int64),
+        ("gn_sums", C.c_void_p), ("gn_groups", C.c_int), ("gn_rows_per_img", C.c_int),
     ]
 
 
@@ -186,9 +187,14 @@ def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample
     n, h, w, c = x.shape
     stats = None
     if normalize:
-        sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
         stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)      # (mean, rstd)
-        _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
+        fused = getattr(x, "_gn_sums", None)        # statistics already accumulated by the producing conv's epilogue
+        if fused is not None and fused[1] == groups:
+            _check(lib.vf_groupnorm_finalize(_p(fused[0]), n * groups, C.c_double(float(h * w * (c // groups))), C.c_float(eps),
+                                             _p(stats), _stream()))
+        else:
+            sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+            _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
     oshape = (n, 2 * h, 2 * w, c) if upsample else ((n, h // 2, w // 2, 4 * c) if s2d else (n, h, w, c))
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
     _check(lib.vf_groupnorm_apply(_p(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
@@ -273,7 +279,7 @@ def simt_gemm(A, B, out, *, M, N, K, a_strides, b_strides, ldc, batch=(1, 1), a_
 
 def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), alpha=1.0,
             bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0, causal_block=0,
-            causal_skip_n=False, out2=None):
+            causal_skip_n=False, out2=None, gn_rows_per_img=0, gn_groups=32):
     """tcgen05 GEMM: C[m,n] = act(alpha*sum_k A[m,k] B[n,k] + bias) + residual; A,B K-major bf16 (or f32 -> TF32).
     ``out2`` optionally receives a second copy in the other dtype (f32 + bf16 from one epilogue)."""
     lib = load(True)
@@ -300,8 +306,23 @@ def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_b
         else:
             p.C_bf16 = o.data_ptr() + c_off * 2
     p.ldc = ldc
+    sums = None
+    if gn_rows_per_img and batch == (1, 1) and gn_fusable(N, gn_groups, M, gn_rows_per_img, ldc):
+        sums = torch.empty((M // gn_rows_per_img, gn_groups, 2), dtype=torch.float64, device=out.device)
+        p.gn_sums, p.gn_groups, p.gn_rows_per_img = sums.data_ptr(), gn_groups, gn_rows_per_img
     _check(lib.vf_tc_gemm(C.byref(p), _stream()))
+    if sums is not None:
+        out._gn_sums = (sums, gn_groups)
     return out
+
+
+def gn_fusable(channels, groups, rows, rows_per_img, ldc):
+    """Shapes for which the tcgen05 epilogue can accumulate GroupNorm statistics (see vf_tc_gemm_t.gn_sums)."""
+    if channels % groups:
+        return False
+    cpg = channels // groups
+    return (cpg % 4 == 0 and cpg <= 32 and 32 % cpg == 0 and channels % 128 == 0 and rows_per_img >= 32 and rows_per_img % 32 == 0
+            and rows % rows_per_img == 0 and ldc % 4 == 0)
 
 
 TAPS_3x3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
@@ -336,7 +357,7 @@ def conv3x3_small_cout(x, w_kn, bias):
 
 
 def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, residual=None, out=None,
-            out_dtype=torch.float32, out2=None):
+            out_dtype=torch.float32, out2=None, gn_groups=0):
     """tcgen05 implicit-GEMM conv.  x [N,H,W,Ctot] bf16|f32 NHWC; w_nk [Cout, ntaps*Cin] (K-major, same dtype)."""
     lib = load(True)
     _dev(x)
@@ -367,7 +388,13 @@ def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, 
         else:
             p.C_bf16 = o.data_ptr()
     p.ldc = cout
+    sums = None
+    if gn_groups and out.dtype == torch.float32 and gn_fusable(cout, gn_groups, n * oh * ow, oh * ow, cout):
+        sums = torch.empty((n, gn_groups, 2), dtype=torch.float64, device=out.device)
+        p.gn_sums, p.gn_groups = sums.data_ptr(), gn_groups
     _check(lib.vf_tc_gemm(C.byref(p), _stream()))
+    if sums is not None:
+        out._gn_sums = (sums, gn_groups)
     return out
 
 

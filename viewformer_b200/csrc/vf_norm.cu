@@ -234,6 +234,14 @@ extern "C" int vf_groupnorm_stats(const float* x, int N, int HW, int C, int grou
     return VF_OK;
 }
 
+extern "C" int vf_groupnorm_finalize(const double* sums, int n_stats, double count, float eps, float* mean_rstd, vf_stream_t s) {
+    VF_CHECK_ARG(sums && mean_rstd && n_stats >= 0 && count > 0, "vf_groupnorm_finalize: bad args");
+    if (n_stats == 0) return VF_OK;
+    gn_finalize_kernel<<<(n_stats + 127) / 128, 128, 0, vf_s(s)>>>(sums, n_stats, count, eps, mean_rstd);
+    VF_CHECK_LAUNCH("vf_groupnorm_finalize");
+    return VF_OK;
+}
+
 extern "C" int vf_groupnorm_apply(const float* x, const float* stats, const float* gamma, const float* beta, int N,
                                   int H, int W, int C, int groups, float eps, int normalize, int swish, int upsample2x,
                                   void* y, int y_dtype, vf_stream_t s) {

@@ -45,6 +45,8 @@ struct TcParams {
     long long ldc, c_sb1, c_sb2;
     unsigned idesc;
     int vec_ok;                // output/residual/bias addressing is 16-byte friendly -> vector epilogue
+    double* gn_sums;           // optional fused GroupNorm statistics of the OUTPUT: [images][groups][2] (sum, sum of squares)
+    int gn_groups, gn_cpg, gn_rows_per_img;
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 
             // ---- phase 2: lanes span the columns of a tile row -> fully coalesced stores; bias / activation / residual here
             if (fast) {
+                float gs = 0.f, gq = 0.f;                 // fused GroupNorm statistics of this lane's 4 channels
 #pragma unroll
                 for (int i = 0; i < ITERS; ++i) {
                     const int rr = i * RPI + r_sub;
@@ -381,6 +384,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     if (p.act == VF_ACT_GELU_ERF) { v.x = vf_gelu_erf(v.x); v.y = vf_gelu_erf(v.y); v.z = vf_gelu_erf(v.z); v.w = vf_gelu_erf(v.w); }
                     if (p.residual) { v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w; }
                     if (ok) {
+                        gs += (v.x + v.y) + (v.z + v.w);
+                        gq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
                         const long long off = off_row + n_ln;
                         if (p.C_f32) *reinterpret_cast<float4*>(p.C_f32 + off) = v;
                         if (p.C_bf16) {
@@ -390,6 +395,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                             u.y = *reinterpret_cast<uint32_t*>(&hi);
                             *reinterpret_cast<uint2*>(p.C_bf16 + off) = u;
                         }
+                    }
+                }
+                if (p.gn_sums) {
+                    // the 32 rows of a warp lie in one image; lanes with equal column vector (different r_sub) and the
+                    // cpg/4 neighbouring lanes of a group are folded with shuffles, then one fp64 RED per (image, group)
+                    const unsigned okmask = __ballot_sync(0xffffffffu, my_ok);
+#pragma unroll
+                    for (int o = VPR; o < 32; o <<= 1) {
+                        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                    }
+                    const int lpg = p.gn_cpg >> 2;
+                    for (int o = 1; o < lpg; o <<= 1) {
+                        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                    }
+                    const int gm_first = __shfl_sync(0xffffffffu, gm, okmask ? (__ffs(okmask) - 1) : 0);
+                    if (okmask && r_sub == 0 && (lane % lpg) == 0) {
+                        const long long slot = ((long long)(gm_first / p.gn_rows_per_img) * p.gn_groups + n_ln / p.gn_cpg) * 2;
+                        atomicAdd(p.gn_sums + slot, (double)gs);
+                        atomicAdd(p.gn_sums + slot + 1, (double)gq);
                     }
                 }
             } else {
@@ -600,6 +626,22 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
         prm.vec_ok = (q->ldc % 4 == 0) && (q->c_sb1 % 4 == 0) && (q->c_sb2 % 4 == 0) && a16(q->C_f32) && a8(q->C_bf16) && a16(q->residual) &&
                      a16(q->bias);
+    }
+    if (q->gn_sums) {
+        const int C = q->Ncols;
+        VF_CHECK_ARG(q->gn_groups > 0 && C % q->gn_groups == 0, "vf_tc_gemm: gn_groups");
+        const int cpg = C / q->gn_groups;
+        const long long rpi = q->conv ? (long long)q->OH * q->OW : q->gn_rows_per_img;
+        const long long rows = q->conv ? (long long)q->N * q->OH * q->OW : (long long)q->M;
+        VF_CHECK_ARG(cpg % 4 == 0 && cpg <= 32 && 32 % cpg == 0 && C % block_n == 0 && prm.vec_ok && rpi >= 32 && rpi % 32 == 0 &&
+                         rows % rpi == 0 && q->batch1 * q->batch2 == 1 && (!q->conv || (prm.TW * prm.TH) % 32 == 0),
+                     "vf_tc_gemm: fused GroupNorm statistics unsupported for this shape (C=%d groups=%d rows/img=%lld)", C, q->gn_groups, rpi);
+        prm.gn_sums = q->gn_sums;
+        prm.gn_groups = q->gn_groups;
+        prm.gn_cpg = cpg;
+        prm.gn_rows_per_img = (int)rpi;
+        cudaError_t e = cudaMemsetAsync(q->gn_sums, 0, sizeof(double) * 2 * q->gn_groups * (rows / rpi), vf_s(s));
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: memset gn_sums: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     }
     cudaStream_t st = vf_s(s);
     if (block_n == 128) return tf32 ? launch<128, 4, true>(prm, pgrid, st) : launch<128, 4, false>(prm, pgrid, st);

@@ -36,7 +36,7 @@ class Linear:
 
 def gemm_nt(prec, A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0),
             alpha=1.0, bias=None, bias_mode=L.BIAS_NONE, act=L.ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0,
-            causal_block=0, causal_skip_n=False, out2=None, force_simt=False):
+            causal_block=0, causal_skip_n=False, out2=None, force_simt=False, gn_rows_per_img=0):
     """C[m,n] = act(alpha * sum_k A[m,k]*B[n,k] + bias) + residual  (both operands K-major)."""
     es = A.element_size()
     tc_ok = (prec.use_tc and not force_simt and A.dtype == B.dtype and A.dtype == prec.opd
@@ -47,7 +47,7 @@ def gemm_nt(prec, A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0
         return L.tc_gemm(A, B, out, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, batch=batch, a_bs=a_bs, b_bs=b_bs,
                          c_bs=c_bs, alpha=alpha, bias=bias, bias_mode=bias_mode, act=act, residual=residual,
                          a_off=a_off, b_off=b_off, c_off=c_off, causal_block=causal_block,
-                         causal_skip_n=causal_skip_n, out2=out2)
+                         causal_skip_n=causal_skip_n, out2=out2, gn_rows_per_img=gn_rows_per_img)
     L.simt_gemm(A, B, out, M=M, N=N, K=K, a_strides=(lda, 1), b_strides=(1, ldb), ldc=ldc, batch=batch, a_bs=a_bs,
                 b_bs=b_bs, c_bs=c_bs, alpha=alpha, bias=bias, bias_mode=bias_mode, act=act, residual=residual,
                 a_off=a_off, b_off=b_off, c_off=c_off)
@@ -56,12 +56,12 @@ def gemm_nt(prec, A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0
     return out
 
 
-def linear(prec, x_rows, lin, out_dtype, *, act=L.ACT_NONE, residual=None, out=None, force_simt=False):
+def linear(prec, x_rows, lin, out_dtype, *, act=L.ACT_NONE, residual=None, out=None, force_simt=False, gn_rows_per_img=0):
     """x_rows [M, K] (operand dtype) -> [M, N]."""
     M = x_rows.shape[0]
     if out is None:
         out = torch.empty((M, lin.n), dtype=out_dtype, device=x_rows.device)
     gemm_nt(prec, x_rows, lin.w, out, M=M, N=lin.n, K=lin.k, lda=x_rows.shape[1], ldb=lin.k, ldc=lin.n,
             bias=lin.b, bias_mode=L.BIAS_N if lin.b is not None else L.BIAS_NONE, act=act, residual=residual,
-            force_simt=force_simt)
+            force_simt=force_simt, gn_rows_per_img=gn_rows_per_img)
     return out

@@ -267,11 +267,13 @@ class VQGAN:
         self._w["pq_table"] = linear(self.exact, q["et"], self._w["post_quant_conv"], torch.float32)
 
     # ------------------------------------------------------------------ building blocks (NHWC f32 in / out)
-    def _conv(self, cw, x_opd_or_f32, *, residual=None, stride=1, upsample=False):
+    def _conv(self, cw, x_opd_or_f32, *, residual=None, stride=1, upsample=False, stats=True):
+        """``stats``: the output feeds a GroupNorm(32) — let the tcgen05 epilogue accumulate its statistics."""
+        gn = 32 if stats else 0
         if cw.tc and stride == 2:    # operand is the space-to-depth tensor [N,H/2,W/2,4C]: stride-1 tap-table conv
-            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, taps=L.TAPS_S2D, coffs=L.s2d_coffs(cw.cin), cin=cw.cin)
+            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, taps=L.TAPS_S2D, coffs=L.s2d_coffs(cw.cin), cin=cw.cin, gn_groups=gn)
         if cw.tc:
-            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, residual=residual)
+            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, residual=residual, gn_groups=gn)
         if stride == 1 and not upsample and residual is None and x_opd_or_f32.dtype == torch.float32:
             if cw.small_cin:
                 return L.conv3x3_small_cin(x_opd_or_f32, cw.w_kn, cw.bias)
@@ -314,8 +316,11 @@ class VQGAN:
         o = torch.empty((n * hw, c), dtype=prec.opd, device=x.device)
         gemm_nt(prec, p, vt, o, M=hw, N=c, K=hw, lda=hw, ldb=hw, ldc=c, batch=(n, 1), a_bs=(hw * hw, 0),
                 b_bs=(c * hw, 0), c_bs=(hw * c, 0))
-        out = linear(prec, o, aw["proj"], torch.float32, residual=x.reshape(n * hw, c))
-        return out.reshape(n, hh, ww, c)
+        out = linear(prec, o, aw["proj"], torch.float32, residual=x.reshape(n * hw, c), gn_rows_per_img=hw)
+        out4 = out.reshape(n, hh, ww, c)
+        if hasattr(out, "_gn_sums"):
+            out4._gn_sums = out._gn_sums           # fused GroupNorm statistics travel with the tensor
+        return out4
 
     # ------------------------------------------------------------------ encoder / decoder (NHWC)
     def _encoder(self, x):
@@ -340,7 +345,7 @@ class VQGAN:
         h = self._attn(e["mida"], h)
         h = self._resblock(e["mid2"], h)
         a = L.groupnorm(h, *e["norm_out"], swish=True, out_dtype=self._act_dtype(e["conv_out"]))
-        return self._conv(e["conv_out"], a)
+        return self._conv(e["conv_out"], a, stats=False)
 
     def _decoder(self, z):
         """Decoder.forward (vqgan_th.py:291-318); z f32 [N,h,w,z_channels] (post_quant_conv applied) -> f32 [N,H,W,3]."""
