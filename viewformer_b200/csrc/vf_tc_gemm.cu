@@ -634,7 +634,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         const long long rpi = q->conv ? (long long)q->OH * q->OW : q->gn_rows_per_img;
         const long long rows = q->conv ? (long long)q->N * q->OH * q->OW : (long long)q->M;
         VF_CHECK_ARG(cpg % 4 == 0 && cpg <= 32 && 32 % cpg == 0 && C % block_n == 0 && prm.vec_ok && rpi >= 32 && rpi % 32 == 0 &&
-                         rows % rpi == 0 && q->batch1 * q->batch2 == 1 && (!q->conv || (prm.TW * prm.TH) % 32 == 0),
+                         rows % rpi == 0 && (q->conv ? (prm.TW * prm.TH) % 32 == 0 : q->batch1 * q->batch2 == 1),
                      "vf_tc_gemm: fused GroupNorm statistics unsupported for this shape (C=%d groups=%d rows/img=%lld)", C, q->gn_groups, rpi);
         prm.gn_sums = q->gn_sums;
         prm.gn_groups = q->gn_groups;
