@@ -215,3 +215,27 @@ def test_generate_end_to_end_matches_oracle():
     cb16, tr16 = VQGAN(vcfg, precision="bf16").load_state_dict(vsd), MIGT(tcfg, precision="bf16").load_state_dict(tsd)
     g16 = generate_batch_predictions(tr16, cb16, images, cams)
     assert g16["generated_images"].dtype == torch.uint8 and list(g16["generated_images"].shape) == [2, 32, 32, 3]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 6e-2)])
+def test_migt_kv_cache_query_equals_full_forward(precision, tol):
+    """BASELINE config 5 path: prefill the context once, then query-only passes reproduce the full forward's last view."""
+    cfg = MIGTConfig(**SMALL_MIGT)
+    sd, model = _migt(cfg, 7, precision)
+    B, T = 3, 4
+    codes, cams, ids = _migt_inputs(cfg, B, T, seed=21)
+    with torch.no_grad():
+        want = mo.forward(sd, cfg, dict(input_ids=ids, poses=cams))["logits"][:, -1]
+    cache = model.prefill_context(codes[:, :-1], cams[:, :-1].contiguous())
+    got_codes, got_logits = model.query(cache, cams[:, -1].contiguous(), return_logits=True)
+    assert _stats(f"kv-cache logits {precision}", got_logits, want)[0] < tol
+    if precision == "fp32":
+        assert torch.equal(got_codes.cpu(), want.argmax(-1))
+    # one scene shared by many queries (stride-0 cache batch): scene 0's context, the three different query poses
+    cache1 = model.prefill_context(codes[:1, :-1], cams[:1, :-1].contiguous())
+    _, l_shared = model.query(cache1, cams[:, -1].contiguous(), return_logits=True)
+    with torch.no_grad():
+        for j in range(B):
+            cj = torch.cat([cams[:1, :-1], cams[j:j + 1, -1:]], 1)
+            wj = mo.forward(sd, cfg, dict(input_ids=ids[:1], poses=cj))["logits"][:, -1]
+            assert _stats(f"shared-cache query {j} {precision}", l_shared[j:j + 1], wj)[0] < tol

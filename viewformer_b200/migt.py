@@ -156,7 +156,7 @@ class MIGT:
         return L.migt_embed(ids, fixed_token, self._w["wte"], self._w["wpe"], pose_rows, B * T, Lt)
 
     # ------------------------------------------------------------------ transformer body
-    def _attention(self, lw, a_list, B, T, kv=None):
+    def _attention(self, lw, a_list, B, T, kv_out=None):
         """BranchingAttention (migt.py:211-217 -> branching_attention.py:82-126) on normalised streams ``a_list``
         (each [B*S, d] in operand dtype).  Stream 0 is block-causal over its own keys; stream s>=1 attends to
         stream-0 keys of strictly earlier views plus its own view in its own stream.  Returns per-stream
@@ -176,6 +176,8 @@ class MIGT:
                     b_bs=(0, 0), c_bs=(ns * S * 2 * d, 0), c_off=s * S * 2 * d, bias=lw["qk"].b, bias_mode=L.BIAS_N)
             gemm_nt(prec, lw["v"].w, a, vt, M=d, N=S, K=d, lda=d, ldb=d, ldc=ns * S, batch=(B, 1), a_bs=(0, 0),
                     b_bs=(S * d, 0), c_bs=(d * ns * S, 0), c_off=s * S, bias=lw["v"].b, bias_mode=L.BIAS_M)
+        if kv_out is not None:
+            kv_out.append((qk, vt))                      # context K (k half of qk) and V^T of this layer: the KV cache
         outs = []
         for s in range(ns):
             if s == 0:
@@ -213,11 +215,11 @@ class MIGT:
             outs.append(o)
         return outs
 
-    def _block(self, lw, xs, B, T):
+    def _block(self, lw, xs, B, T, kv_out=None):
         """Block.call (migt.py:230-238): pre-LN attention + pre-LN MLP over a list of streams (shared weights)."""
         prec = self.prec
         a = [L.layernorm(x, *lw["ln1"], out_dtype=prec.opd, eps=LN_EPS) for x in xs]
-        att = self._attention(lw, a, B, T)
+        att = self._attention(lw, a, B, T, kv_out)
         xs = [linear(prec, o, lw["proj"], torch.float32, residual=x) for o, x in zip(att, xs)]
         out = []
         for x in xs:
@@ -226,9 +228,9 @@ class MIGT:
             out.append(linear(prec, hmid, lw["fc2"], torch.float32, residual=x))
         return out
 
-    def _body(self, xs, B, T):
+    def _body(self, xs, B, T, kv_out=None):
         for lw in self._w["layers"]:
-            xs = self._block(lw, xs, B, T)
+            xs = self._block(lw, xs, B, T, kv_out)
         return xs
 
     def _lm_logits(self, h_rows_f32):
@@ -313,6 +315,74 @@ class MIGT:
         """QuaternionPoseRepresentation.reduce (migt.py:150-154, 123-129): host-side, a handful of floats."""
         from .generate import reduce_cameras
         return reduce_cameras(cameras, axis)
+
+    # ------------------------------------------------------------------ context KV cache (BASELINE config 5)
+    def prefill_context(self, codes_ctx, poses_ctx):
+        """Run the context views once and keep every layer's K / V^T.  Exact: the transformer is block-causal over
+        views, so context hidden states never depend on the query view (oracle invariant (ii)).
+        codes_ctx int [B,Tc,8,8]; poses_ctx f32 [B,Tc,7] (already relative / normalised)."""
+        if self._w is None:
+            raise RuntimeError("MIGT has no weights: call load_state_dict() first")
+        codes_ctx = torch.as_tensor(codes_ctx)
+        B, Tc = codes_ctx.shape[0], codes_ctx.shape[1]
+        d = self.config.d_model
+        ids = self._in(codes_ctx.reshape(B, Tc, -1), torch.int32)
+        poses = self._in(poses_ctx, torch.float32)
+        pe = self._pose_embed(poses.reshape(B * Tc, 7))
+        xs = [self._embed_stream(ids, 0, pe, B, Tc)]
+        kv = []
+        self._body(xs, B, Tc, kv_out=kv)
+        return dict(kv=kv, B=B, Tc=Tc)
+
+    def _query_block(self, lw, x, qk_c, vt_c, Nq, Bc, S_ctx):
+        """One transformer block for Nq mask-token query views (64 rows each) against cached context K / V^T."""
+        prec, cfg = self.prec, self.config
+        d, H = cfg.d_model, cfg.n_head
+        dh, Lt = d // H, self.n_image_tokens
+        ld = S_ctx + Lt
+        dev = x.device
+        shared = Bc == 1 and Nq > 1                       # every query reads the same scene's cache (stride-0 batch)
+        a = L.layernorm(x, *lw["ln1"], out_dtype=prec.opd, eps=LN_EPS)
+        qk_q = linear(prec, a, lw["qk"], prec.opd)                                                   # [Nq*Lt, 2d] = q | k
+        vt_q = torch.empty((Nq, d, Lt), dtype=prec.opd, device=dev)
+        gemm_nt(prec, lw["v"].w, a, vt_q, M=d, N=Lt, K=d, lda=d, ldb=d, ldc=Lt, batch=(Nq, 1), a_bs=(0, 0), b_bs=(Lt * d, 0),
+                c_bs=(d * Lt, 0), bias=lw["v"].b, bias_mode=L.BIAS_M)
+        scores = torch.empty((Nq, H, Lt, ld), dtype=torch.float32, device=dev)
+        cb = 0 if shared else S_ctx * 2 * d
+        gemm_nt(prec, qk_q, qk_c, scores, M=Lt, N=S_ctx, K=dh, lda=2 * d, ldb=2 * d, ldc=ld, batch=(Nq, H), a_bs=(Lt * 2 * d, dh),
+                b_bs=(cb, dh), c_bs=(H * Lt * ld, Lt * ld), b_off=d)                                 # vs cached context keys
+        gemm_nt(prec, qk_q, qk_q, scores, M=Lt, N=Lt, K=dh, lda=2 * d, ldb=2 * d, ldc=ld, batch=(Nq, H), a_bs=(Lt * 2 * d, dh),
+                b_bs=(Lt * 2 * d, dh), c_bs=(H * Lt * ld, Lt * ld), b_off=d, c_off=S_ctx)             # vs the view's own keys
+        p = torch.empty((Nq, H, Lt, ld), dtype=prec.opd, device=dev)
+        L.softmax_rows(scores, p, rows_total=Nq * H * Lt, rows_per_batch=Lt, cols=ld, ld_in=ld, ld_out=ld)   # all keys visible
+        o1 = torch.empty((Nq * Lt, d), dtype=torch.float32, device=dev)
+        gemm_nt(prec, p, vt_c, o1, M=Lt, N=dh, K=S_ctx, lda=ld, ldb=S_ctx, ldc=d, batch=(Nq, H), a_bs=(H * Lt * ld, Lt * ld),
+                b_bs=(0 if shared else d * S_ctx, dh * S_ctx), c_bs=(Lt * d, dh))
+        o = torch.empty((Nq * Lt, d), dtype=prec.opd, device=dev)
+        gemm_nt(prec, p, vt_q, o, M=Lt, N=dh, K=Lt, lda=ld, ldb=Lt, ldc=d, batch=(Nq, H), a_bs=(H * Lt * ld, Lt * ld),
+                b_bs=(d * Lt, dh * Lt), c_bs=(Lt * d, dh), a_off=S_ctx, residual=o1)                  # + own-view values
+        x = linear(prec, o, lw["proj"], torch.float32, residual=x)
+        m = L.layernorm(x, *lw["ln2"], out_dtype=prec.opd, eps=LN_EPS)
+        hmid = linear(prec, m, lw["fc"], prec.opd, act=L.ACT_GELU)
+        return linear(prec, hmid, lw["fc2"], torch.float32, residual=x)
+
+    def query(self, cache, query_poses, return_logits=False):
+        """Novel-view codes for query poses against a prefilled context.  query_poses f32 [Nq,7]; Nq == cache batch
+        (one query per scene) or cache batch == 1 (many queries share one scene, evaluate_transformer_multictx_allimg.py:141-173).
+        Only the 64 mask tokens of each query view are computed: 14 GFLOP/view instead of 249 at 19 context views."""
+        qp = self._in(query_poses, torch.float32).reshape(-1, 7)
+        Nq, Bc, Tc = qp.shape[0], cache["B"], cache["Tc"]
+        if not (Nq == Bc or Bc == 1):
+            raise ValueError(f"{Nq} query poses for a cache of {Bc} scenes: need one per scene, or a single shared scene")
+        Lt = self.n_image_tokens
+        S_ctx = Tc * Lt
+        x = self._embed_stream(None, self.mask_token, self._pose_embed(qp), Nq, 1)
+        for lw, (qk_c, vt_c) in zip(self._w["layers"], cache["kv"]):
+            x = self._query_block(lw, x, qk_c, vt_c, Nq, Bc, S_ctx)
+        logits = self._lm_logits(x)
+        side = self.token_image_size
+        codes = L.argmax_rows(logits).reshape(Nq, side, side)
+        return (codes, logits.reshape(Nq, side, side, -1)) if return_logits else codes
 
     # ------------------------------------------------------------------ fast inference entry points
     def generate_codes(self, codes_ctx, poses):
