@@ -138,6 +138,16 @@ typedef struct {
 int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused block-causal attention on tcgen05 (single-stream forward):  out = softmax(mask(Q K^T)) V, no 1/sqrt(dh) scale
+ * replaces: models/branching_attention.py:41-61 via models/migt.py:211-217.
+ *   qk  bf16 [B, S, 2d]  rows = tokens, columns [0,d) = q, [d,2d) = k (head h at columns h*64..h*64+63)
+ *   vt  bf16 [B, d, S]   V transposed (row = channel, contiguous over tokens)
+ *   out bf16 [B*S, d]    a token of view v attends to all tokens of views <= v; view = token / block
+ *   head dim must be 64; S % block == 0.
+ * ---------------------------------------------------------------------------------------- */
+int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * Codebook
  * replaces: models/utils_th.py:34-44 (distance, argmax(-dist), gather), :66 (diff), :70-72 (embed_code)
  *   z [M,D] f32 rows; codebook given TRANSPOSED as Et [K,D] (built once at weight load) with esq[K]=|e|^2.

@@ -394,3 +394,23 @@ def test_tc_conv_fused_groupnorm_statistics(L, cin, cout, n, hw):
     plain = out.clone()                                        # clone drops the attached statistics -> stats kernel path
     y_plain = L.groupnorm(plain, ga, be, swish=True, out_dtype=torch.float32)
     report("gn via fused stats vs stats kernel", y_fused, y_plain, 2e-5, 1e-5)
+
+
+@pytest.mark.parametrize("B,T,H,blk", [(2, 4, 3, 64), (1, 10, 2, 64), (2, 3, 2, 64), (1, 5, 1, 32)])
+def test_fused_block_causal_attention(L, B, T, H, blk):
+    """Fused tcgen05 attention == softmax(q k^T * m - 1e4 (1-m)) v of branching_attention.py:5-18,41-61 (no 1/sqrt(d))."""
+    d, S = H * 64, T * blk
+    qk = (torch.randn(B, S, 2 * d, generator=g(S + H)) * 0.6).bfloat16()
+    v = torch.randn(B, S, d, generator=g(S + H + 1)).bfloat16()
+    vt = v.permute(0, 2, 1).contiguous()
+    out = L.attn_block_causal(qk.cuda(), vt.cuda(), B, S, H, d, blk)
+    torch.cuda.synchronize()
+    q = qk[..., :d].double().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    k = qk[..., d:].double().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    vv = v.double().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    view = torch.arange(S) // blk
+    m = (view[:, None] >= view[None, :]).double()
+    w = q @ k.transpose(-1, -2)
+    w = w * m - 1e4 * (1 - m)
+    want = (torch.softmax(w, -1) @ vv).permute(0, 2, 1, 3).reshape(B * S, d)
+    report(f"fused attention B{B} T{T} H{H} blk{blk}", out.float(), want, 2e-2, 2e-2)

@@ -22,7 +22,7 @@ EXPORTS = [
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
-    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize",
+    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal",
 ]
 
 
@@ -456,6 +456,16 @@ def migt_embed(ids_i32, fixed_token, wte, wpe, pose_rows, BT, L):
     out = torch.empty((BT * L, d), dtype=torch.float32, device=wte.device)
     _check(lib.vf_migt_embed(_p(ids_i32), int(fixed_token), _p(wte), _p(wpe), _p(pose_rows), C.c_int64(BT), L, d, _p(out),
                              _stream()))
+    return out
+
+
+def attn_block_causal(qk, vt, B, S, H, d, block):
+    """Fused tcgen05 block-causal attention: qk bf16 [B,S,2d] (q|k), vt bf16 [B,d,S] -> bf16 [B*S, d]."""
+    lib = load(True)
+    _dev(qk, torch.bfloat16)
+    _dev(vt, torch.bfloat16)
+    out = torch.empty((B * S, d), dtype=torch.bfloat16, device=qk.device)
+    _check(lib.vf_attn_block_causal(_p(qk), _p(vt), B, S, H, d, block, _p(out), _stream()))
     return out
 
 

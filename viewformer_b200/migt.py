@@ -45,6 +45,7 @@ class MIGT:
         self._codebook_model = None
         self._sd = None
         self._w = None
+        self.fused_attention = True     # False: QK^T / softmax / PV as separate kernels (kept for the multi-stream / tf32 paths)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -178,6 +179,9 @@ class MIGT:
                     b_bs=(S * d, 0), c_bs=(d * ns * S, 0), c_off=s * S, bias=lw["v"].b, bias_mode=L.BIAS_M)
         if kv_out is not None:
             kv_out.append((qk, vt))                      # context K (k half of qk) and V^T of this layer: the KV cache
+        if ns == 1 and prec.opd == torch.bfloat16 and dh == 64 and self.fused_attention:
+            # single-stream forward (the generate() hot path): one fused tcgen05 kernel, no S x S tensor in HBM
+            return [L.attn_block_causal(qk, vt, B, S, H, d, Lt)]
         outs = []
         for s in range(ns):
             if s == 0:
