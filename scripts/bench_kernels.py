@@ -88,6 +88,14 @@ ms = timeit(lambda: L.tc_gemm(p, vt, o, M=S, N=64, K=S, lda=S, ldb=S, ldc=d, bat
                               c_bs=(S * d, 64), causal_block=64))
 rows.append(("attn P.V (causal k-limit)", ms, 2.0 * B * H * S * S * 64 * 0.55 / ms / 1e9, None))
 
+for (Bq, Sq) in ((32, 640), (32, 1280)):
+    qk2 = torch.randn((Bq, Sq, 2 * d), device=dev).bfloat16()
+    vt2 = torch.randn((Bq, d, Sq), device=dev).bfloat16()
+    ms = timeit(lambda: L.attn_block_causal(qk2, vt2, Bq, Sq, H, d, 64))
+    Tn = Sq // 64
+    useful = 4.0 * Bq * H * 64 * 64 * 64 * Tn * (Tn + 1) / 2          # 4*dh*L^2*T(T+1)/2 per (b,h): QK^T + PV, visible blocks only
+    rows.append((f"FUSED block-causal attention B{Bq} H12 S{Sq} (useful FLOPs)", ms, useful / ms / 1e9, None))
+
 print(f"{'kernel':58s} {'ms':>8s} {'TFLOP/s':>9s} {'%peak':>6s} {'GB/s':>8s} {'%hbm':>6s}")
 for name, ms, tf, gbs in rows:
     a = f"{tf:9.1f} {100*tf/PEAK_TF:6.1f}" if tf else " " * 16

@@ -351,6 +351,9 @@ def test_small_channel_convs(L):
     want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     got = L.conv3x3_small_cin(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w).cuda(), b.cuda())
     report("conv_in small_cin", got.permute(0, 3, 1, 2), want, 2e-5, 1e-5)
+    w64, b64 = w[:64].contiguous(), b[:64].contiguous()
+    got = L.conv3x3_small_cin(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w64).cuda(), b64.cuda())
+    report("conv_in small_cin cout64", got.permute(0, 3, 1, 2), want[:, :64], 2e-5, 1e-5)
     x = torch.randn(2, 128, 19, 45, generator=g(93))
     w = torch.randn(3, 128, 3, 3, generator=g(94)) / 1152 ** 0.5
     b = torch.randn(3, generator=g(95))

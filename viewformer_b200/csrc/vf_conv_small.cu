@@ -66,6 +66,49 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cin = 3, Cout = 128: one warp walks a run of pixels; lane l owns output channels 4l..4l+3 and keeps its 27 x 4 weights in
+// registers; the 27 inputs of a pixel are warp-uniform (broadcast loads); every store is one coalesced 512-byte row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv3x3_cin3_cout128_kernel(const float* __restrict__ x, const float* __restrict__ w_kn,
+                                                                   const float* __restrict__ bias, int N, int H, int W, int px_per_warp,
+                                                                   float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int runs_per_row = (W + px_per_warp - 1) / px_per_warp;
+    const int run = (int)(warp_global % runs_per_row);
+    const long long row = warp_global / runs_per_row;           // n*H + y
+    if (row >= (long long)N * H) return;
+    const int yy = (int)(row % H), n = (int)(row / H);
+    float4 wr[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w_kn + k * 128) + lane);
+    const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int x0 = run * px_per_warp, x1 = min(W, x0 + px_per_warp);
+    for (int xx = x0; xx < x1; xx += 2) {                       // two pixels per iteration for ILP
+        float4 a0 = b4, a1 = b4;
+        const bool two = xx + 1 < x1;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+            const bool oky = iy >= 0 && iy < H;
+            const float* p0 = x + (((long long)n * H + iy) * W + ix) * 3;
+            const bool ok0 = oky && ix >= 0 && ix < W, ok1 = oky && two && ix + 1 >= 0 && ix + 1 < W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v0 = ok0 ? __ldg(p0 + c) : 0.f;      // warp-uniform address: one broadcast transaction
+                const float v1 = ok1 ? __ldg(p0 + 3 + c) : 0.f;
+                const float4 w4 = wr[t * 3 + c];
+                a0.x = fmaf(v0, w4.x, a0.x); a0.y = fmaf(v0, w4.y, a0.y); a0.z = fmaf(v0, w4.z, a0.z); a0.w = fmaf(v0, w4.w, a0.w);
+                a1.x = fmaf(v1, w4.x, a1.x); a1.y = fmaf(v1, w4.y, a1.y); a1.z = fmaf(v1, w4.z, a1.z); a1.w = fmaf(v1, w4.w, a1.w);
+            }
+        }
+        float* o = y + (((long long)n * H + yy) * W + xx) * 128 + lane * 4;
+        *reinterpret_cast<float4*>(o) = a0;
+        if (two) *reinterpret_cast<float4*>(o + 128) = a1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small Cout (<= 4), Cin == 128: one warp walks a run of pixels along x; lane l owns input channels 4l..4l+3 and keeps
 // its 9 x 4 x COUT weights in registers; per pixel 9 coalesced 512-byte loads, COUT warp reductions.
 // ------------------------------------------------------------------------------------------------
@@ -139,6 +182,13 @@ extern "C" int vf_conv3x3_small_cin(const float* x, const float* w_kn, const flo
     VF_CHECK_ARG(x && w_kn && y, "vf_conv3x3_small_cin: null pointer");
     VF_CHECK_ARG(Cin == 3 && Cout % 16 == 0 && Cout <= 128, "vf_conv3x3_small_cin: supports Cin=3, Cout%%16==0, Cout<=128 (got %d->%d)", Cin, Cout);
     if (N == 0) return VF_OK;
+    if (Cout == 128) {
+        const int px_per_warp = W >= 64 ? 64 : W;
+        const long long warps = (long long)N * H * ((W + px_per_warp - 1) / px_per_warp);
+        conv3x3_cin3_cout128_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, vf_s(s)>>>(x, w_kn, bias, N, H, W, px_per_warp, y);
+        VF_CHECK_LAUNCH("vf_conv3x3_small_cin");
+        return VF_OK;
+    }
     dim3 grid((W + 63) / 64, H, N);
     VF_CHECK_ARG(H <= 65535 && N <= 65535, "vf_conv3x3_small_cin: grid too large");
     conv3x3_small_cin_kernel<3><<<grid, 32 * (Cout / 16), sizeof(float) * 27 * Cout, vf_s(s)>>>(x, w_kn, bias, N, H, W, Cout, y);

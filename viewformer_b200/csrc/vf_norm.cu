@@ -113,7 +113,14 @@ __device__ __forceinline__ void gn_apply_one(float4 v, int64_t i, int cq, unsign
         v.w = (v.w - mu[3]) * rs[3] * ga.w + be.w;
     }
     if (swish) {
-        v.x = vf_swish(v.x); v.y = vf_swish(v.y); v.z = vf_swish(v.z); v.w = vf_swish(v.w);
+        if constexpr (sizeof(OutT) == 2) {
+            // bf16 operand output: ex2.approx / rcp.approx (rel. error ~1e-6, far below bf16 rounding) keep this kernel
+            // memory-bound; the fp32 (exact-path) instantiation uses expf and a true division
+            v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+            v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+        } else {
+            v.x = vf_swish(v.x); v.y = vf_swish(v.y); v.z = vf_swish(v.z); v.w = vf_swish(v.w);
+        }
     }
     if (up == 0) {
         store4<OutT>(y + i * 4, v.x, v.y, v.z, v.w);
