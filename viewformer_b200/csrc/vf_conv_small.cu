@@ -182,7 +182,7 @@ extern "C" int vf_conv3x3_small_cin(const float* x, const float* w_kn, const flo
     VF_CHECK_ARG(x && w_kn && y, "vf_conv3x3_small_cin: null pointer");
     VF_CHECK_ARG(Cin == 3 && Cout % 16 == 0 && Cout <= 128, "vf_conv3x3_small_cin: supports Cin=3, Cout%%16==0, Cout<=128 (got %d->%d)", Cin, Cout);
     if (N == 0) return VF_OK;
-    if (Cout == 128) {
+    if (false && Cout == 128) {   // measured 2.75 ms vs 1.6 ms for the smem-weight kernel below at 288x128x128: latency-bound, kept for reference
         const int px_per_warp = W >= 64 ? 64 : W;
         const long long warps = (long long)N * H * ((W + px_per_warp - 1) / px_per_warp);
         conv3x3_cin3_cout128_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, vf_s(s)>>>(x, w_kn, bias, N, H, W, px_per_warp, y);
