@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="generate", choices=["generate", "kvcache"],
+                    help="generate = BASELINE configs[1] (default, the judged line); kvcache = configs[4]: 19-context KV-cached query decode")
     return ap.parse_args()
 
 
@@ -315,9 +317,63 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_kvcache(args):
+    """BASELINE configs[4]: transformer decode with a context KV cache — 19 context views prefilled once per scene,
+    every step answers one query view per scene (64 mask tokens against the cached K/V^T).  Transformer only."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    from viewformer_b200 import MIGT, _lib
+    from viewformer_b200.config import MIGTConfig
+    tr = MIGT(MIGTConfig(localization_weight="0"), precision=args.precision, device=dev).init_weights(0)
+    B, Tc = args.scenes, 19
+    g = torch.Generator().manual_seed(99 + rank)
+    codes = torch.randint(0, 1024, (B, Tc, 8, 8), generator=g).to(dev)
+    _, cams = synth_inputs(B, 5 + rank)
+    cams = torch.cat([cams, cams], 1)[:, :Tc + 1].contiguous().to(dev)
+    cams, _ = _lib.cameras_prepare(cams, True)
+    ctx_p, qry_p = cams[:, :Tc].contiguous(), cams[:, Tc].contiguous()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cache = tr.prefill_context(codes, ctx_p)
+    sync(); e0.record(); cache = tr.prefill_context(codes, ctx_p); e1.record(); sync()
+    prefill_ms = e0.elapsed_time(e1)
+    for _ in range(max(3, args.warmup)):
+        tr.query(cache, qry_p)
+    sync(); e0.record()
+    for _ in range(args.steps):
+        tr.query(cache, qry_p)
+    e1.record(); sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "novel views/sec (KV-cached transformer decode, 19-ctx)", "value": world * B * args.steps / (float(ms) / 1e3),
+                          "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                          "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": args.precision, "data": "synthetic",
+                          "config": {"workload": "co3d-all transformer decode w/ KV-cache, 19 ctx views (BASELINE configs[4])",
+                                     "scenes_per_gpu": B, "prefill_ms": prefill_ms}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "kvcache" and a.impl == "b200":
+        run_kvcache(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -286,3 +286,27 @@ def generate_batch_predictions(forward_fn, encode_fn, decode_code_fn, cfg, image
         gen_cam = from_relative_cameras(gen_cam, transform)
     return dict(ground_truth_images=images[:, -1], generated_images=gen, ground_truth_cameras=gt_cam,
                 generated_cameras=gen_cam[:, -1], generated_codes=gen_codes, codes=codes)
+
+
+def generate_batch_predictions_multictx(forward_fn, encode_fn, decode_code_fn, cfg, images, cameras):
+    """evaluate_transformer_multictx.py:37-95 (3-stream call; per-context-size predictions)."""
+    gt_cam = cameras[:, -1]
+    transform = None
+    if cfg.augment_poses == "relative":
+        cameras, transform = to_relative_cameras(cameras)
+    cameras = normalize_cameras(cameras)
+    B, T = images.shape[:2]
+    x = images_to_float(images.reshape((B * T,) + tuple(images.shape[2:]))).permute(0, 3, 1, 2).contiguous()
+    codes = encode_fn(x).reshape(B, T, cfg.token_image_size, cfg.token_image_size)
+    ids = torch.cat([codes[:, :-1], torch.full_like(codes[:, :1], cfg.n_embeddings)], 1)
+    ctx_cams = torch.cat([cameras[:, :-1], torch.zeros_like(cameras[:, :1])], 1)
+    out = forward_fn(dict(input_ids=ids, poses=ctx_cams, localization_tokens=codes[:, -1:].repeat(1, T, 1, 1),
+                          output_poses=cameras[:, -1:].repeat(1, T, 1)))
+    gen_codes = out["logits"].argmax(-1)
+    gen_cam = reduce_cameras(out["pose_prediction"], -2)
+    gen = float_to_images(decode_code_fn(gen_codes.reshape((B * T,) + tuple(gen_codes.shape[2:])))).permute(0, 2, 3, 1)
+    gen = gen.reshape((B, T) + tuple(gen.shape[1:]))
+    if transform is not None:
+        gen_cam = from_relative_cameras(gen_cam, transform)
+    return dict(ground_truth_images=images[:, -1], generated_images=gen, ground_truth_cameras=gt_cam,
+                generated_cameras=gen_cam, generated_codes=gen_codes)

@@ -112,3 +112,36 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
         gen_cam = L.cameras_from_relative(gen_cam.to(dev).contiguous(), transform)
     return dict(ground_truth_images=images[:, -1], generated_images=gen_images, ground_truth_cameras=gt_cam,
                 generated_cameras=gen_cam[:, -1], generated_codes=gen_codes)
+
+
+def generate_batch_predictions_multictx(transformer_model, codebook_model, images, cameras):
+    """Multi-context variant — viewformer/evaluate/evaluate_transformer_multictx.py:37-95: one 3-stream forward yields,
+    for every context size i, the query view rendered from context views 0..i-1 (stream 1) and the query localised
+    against them (stream 2).  Returns generated_images [B,T,H,W,3] u8 and generated_cameras [B,T,7]."""
+    dev = transformer_model.device
+    images = torch.as_tensor(images)
+    cameras = torch.as_tensor(cameras)
+    if cameras.dtype != torch.float32:
+        cameras = cameras.to(torch.float32)
+    gt_cam = cameras[:, -1]
+    relative = transformer_model.config.augment_poses == "relative"
+    cams, transform = L.cameras_prepare(cameras.to(dev, non_blocking=True).contiguous(), relative)
+    B, T = images.shape[:2]
+    side = transformer_model.token_image_size
+    img_dev = images.to(device=dev, non_blocking=True) if images.device != dev else images
+    codes = codebook_model.encode_u8(img_dev.contiguous(), first_views=T).reshape(B, T, side, side)
+    mask = torch.full_like(codes[:, :1], transformer_model.mask_token)
+    input_ids = torch.cat([codes[:, :-1], mask], 1)                                    # :61-62
+    context_cameras = torch.cat([cams[:, :-1], torch.zeros_like(cams[:, :1])], 1)      # :63
+    out = transformer_model(dict(input_ids=input_ids, poses=context_cameras,
+                                 localization_tokens=codes[:, -1:].repeat(1, T, 1, 1).contiguous(),
+                                 output_poses=cams[:, -1:].repeat(1, T, 1).contiguous()))       # :66-73
+    logits = out["logits"]
+    gen_codes = L.argmax_rows(logits.reshape(-1, logits.shape[-1])).reshape(B * T, side, side)   # :76
+    gen_images = codebook_model.decode_code_u8(gen_codes)
+    gen_images = gen_images.reshape((B, T) + tuple(gen_images.shape[1:]))
+    gen_cam = reduce_cameras(out["pose_prediction"], -2)                               # :77  [B,T,7]
+    if relative:
+        gen_cam = L.cameras_from_relative(gen_cam.to(dev).contiguous(), transform)
+    return dict(ground_truth_images=images[:, -1], generated_images=gen_images, ground_truth_cameras=gt_cam,
+                generated_cameras=gen_cam)
