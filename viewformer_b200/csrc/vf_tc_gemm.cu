@@ -15,6 +15,7 @@
 //           viewformer/models/branching_attention.py:7,18 (QK^T, PV) on the fast path.
 #include "vf_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -45,6 +46,8 @@ struct TcParams {
     long long ldc, c_sb1, c_sb2;
     unsigned idesc;
     int vec_ok;                // output/residual/bias addressing is 16-byte friendly -> vector epilogue
+    int halo;                  // conv only: 1 = load one (TH+2)x(TW+2) halo tile per 64-channel block and address the 9 taps
+                               // as row-shifted UMMA descriptors into it (9x fewer A bytes from L2); 0 = one shifted TMA box per tap
     double* gn_sums;           // optional fused GroupNorm statistics of the OUTPUT: [images][groups][2] (sum, sum of squares)
     int gn_groups, gn_cpg, gn_rows_per_img;
 };
@@ -197,11 +200,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     // 1024B alignment required by the 128B swizzle atoms (descriptor base_offset = 0)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* staging = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + STG_BYTES);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;      // [2]
+    constexpr int MAX_STAGES = 8;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + STG_BYTES);   // [MAX_STAGES]
+    uint64_t* empty_bar = full_bar + MAX_STAGES;        // [MAX_STAGES]
+    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* a_full_bar = tmem_empty_bar + 2;          // [2]  halo mode: A halo tiles
+    uint64_t* a_empty_bar = a_full_bar + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 2);
+    // halo mode carves the same operand region differently: 2 halo buffers, then a ring of B-only stages
+    constexpr int HALO_BUF_BYTES = 23552;               // >= 18*10 rows x 128 B, multiple of 1024
+    constexpr int HALO_B_STAGES = (kStages * STAGE_BYTES - 2 * HALO_BUF_BYTES) / B_STAGE_BYTES > MAX_STAGES
+                                      ? MAX_STAGES : (kStages * STAGE_BYTES - 2 * HALO_BUF_BYTES) / B_STAGE_BYTES;
+    uint8_t* halo_b_base = smem + 2 * HALO_BUF_BYTES;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -211,9 +222,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
     }
     if (threadIdx.x == 32) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&a_full_bar[a], 1);
+            mbar_init(&a_empty_bar[a], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
@@ -236,9 +251,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int ab = 0;
+            uint32_t aphase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileInfo ti = decode_tile(p, t, kBlockN);
                 if (ti.skip) continue;
+                if (p.halo) {
+                    const uint32_t halo_bytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * ROW_BYTES;
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        mbar_wait(&a_empty_bar[ab], aphase ^ 1);
+                        mbar_expect_tx(&a_full_bar[ab], halo_bytes);
+                        tma_load_4d(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
+                        if (++ab == 2) { ab = 0; aphase ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
+                            tma_load_4d(halo_b_base + stage * B_STAGE_BYTES, &p.tmB, &full_bar[stage], (tap * p.cin_blocks + cb) * p.bk_elems,
+                                        ti.n0, 0, 0);
+                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < ti.nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -263,6 +297,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            int ab_m = 0;
+            uint32_t aphase_m = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileInfo ti = decode_tile(p, t, kBlockN);
                 if (ti.skip) continue;
@@ -271,6 +307,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator stage
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBlockN);
+                if (p.halo) {
+                    // tile = TH rows of TW=8 pixels: MMA row group g (8 rows) = image row g of the tile; inside the halo tile
+                    // (pitch TW+2 rows) tap (dy,dx) starts (dy*(TW+2)+dx) rows in, consecutive groups are (TW+2) rows apart.
+                    // The 128B swizzle is a pure function of the absolute smem address (probed: scripts/desc_shift_probe.cu),
+                    // so row-shifted descriptors with base_offset 0 read exactly what TMA wrote.
+                    const uint32_t pitch = (uint32_t)(p.TW + 2);
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        mbar_wait(&a_full_bar[ab_m], aphase_m);
+                        const uint32_t a_base = smem_u32(smem + ab_m * HALO_BUF_BYTES);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&full_bar[stage], phase);
+                            tcgen05_fence_after();
+                            const uint32_t a_addr = a_base + ((uint32_t)(tap / 3) * pitch + (uint32_t)(tap % 3)) * ROW_BYTES;
+                            uint64_t adesc = make_sw128_desc(a_addr);
+                            adesc = (adesc & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((pitch * ROW_BYTES) >> 4) << 32);     // SBO = pitch rows
+                            const uint64_t bdesc = make_sw128_desc(smem_u32(halo_b_base + stage * B_STAGE_BYTES));
+#pragma unroll
+                            for (int k = 0; k < MMAS_PER_STAGE; ++k)
+                                umma<kTF32>(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                            p.idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                            tcgen05_commit(&empty_bar[stage]);
+                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        tcgen05_commit(&a_empty_bar[ab_m]);      // halo buffer free once its 36 MMAs retire
+                        if (++ab_m == 2) { ab_m = 0; aphase_m ^= 1; }
+                    }
+                    tcgen05_commit(&tmem_full_bar[acc]);
+                    ++it;
+                    continue;
+                }
                 for (int kb = 0; kb < ti.nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
@@ -559,6 +625,13 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         int TH = 128 / TW;
         if (TH > q->OH) { TH = 1; while (TH * 2 <= q->OH) TH *= 2; }
         int TN = 128 / (TW * TH);
+        // halo mode: plain stride-1 pad-1 3x3 conv on maps at least 16 rows tall -> 8x16-pixel tiles, one halo load per channel block
+        static int halo_enabled = -1;
+        if (halo_enabled < 0) { const char* e = getenv("VF_TC_HALO"); halo_enabled = (e && e[0] == '0') ? 0 : 1; }
+        bool halo = halo_enabled && q->ntaps == 9 && q->Ctot == q->Cin && q->OH == q->H && q->OW == q->W && q->OH >= 16 && q->OW >= 8;
+        for (int t = 0; halo && t < 9; ++t) halo = q->tap_dy[t] == t / 3 - 1 && q->tap_dx[t] == t % 3 - 1 && q->tap_coff[t] == 0;
+        if (halo) { TW = 8; TH = 16; TN = 1; }
+        prm.halo = halo ? 1 : 0;
         VF_CHECK_ARG(TW * TH * TN == 128 && TN <= 256, "vf_tc_gemm: cannot tile %dx%d output", q->OH, q->OW);
         prm.TW = TW; prm.TH = TH; prm.TN = TN;
         prm.tiles_x = (q->OW + TW - 1) / TW;
@@ -571,7 +644,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         for (int t = 0; t < q->ntaps; ++t) { prm.tap_dy[t] = q->tap_dy[t]; prm.tap_dx[t] = q->tap_dx[t]; prm.tap_coff[t] = q->tap_coff[t]; }
         const uint64_t dimsA[4] = {(uint64_t)q->Ctot, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->N};
         const uint64_t strA[3] = {(uint64_t)q->Ctot * es, (uint64_t)q->W * q->Ctot * es, (uint64_t)q->H * q->W * q->Ctot * es};
-        const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+        const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)(halo ? TW + 2 : TW), (uint32_t)(halo ? TH + 2 : TH), (uint32_t)TN};
         if ((rc = make_tmap(&prm.tmA, q->ab_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
         const uint64_t Ktot = (uint64_t)q->ntaps * q->Cin;
         const uint64_t dimsB[4] = {Ktot, (uint64_t)q->Ncols, 1, 1};
