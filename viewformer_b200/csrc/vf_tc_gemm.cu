@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     constexpr int UMMA_K_BYTES = 32;           // 16 bf16 or 8 tf32 per instruction
     constexpr int MMAS_PER_STAGE = ROW_BYTES / UMMA_K_BYTES;
     constexpr int HALF_N = kBlockN / 2;        // columns per epilogue warp
-    constexpr int STG_LD = 32 + 4;             // staging holds one 32-column chunk per warp; +4 keeps 128-bit row writes conflict-free
+    constexpr int STG_LD = HALF_N + 4;         // staging row stride (floats): +4 keeps 128-bit row writes conflict-free
     constexpr int STG_BYTES = NUM_EPI_WARPS * 32 * STG_LD * 4;
 
     extern __shared__ uint8_t smem_raw[];
@@ -390,100 +390,112 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             }
             const float bias_m = (p.bias_mode == VF_BIAS_M && my_ok) ? __ldg(p.bias + gm) : 0.f;
 
-            // The warp's HALF_N columns are processed in chunks of 32: TMEM -> staging (thread = row), then staging -> global
-            // (8 lanes span the 32 columns of a row, 4 rows per iteration) so every store / residual load is a full 128-byte line.
-            constexpr int NCHUNK = HALF_N / 32;            // 2 (BLOCK_N=128) or 1 (BLOCK_N=64)
-            constexpr int ITERS = 8;                       // 32 rows / 4 rows per iteration
-            const int r_sub = lane >> 3;                   // row within an iteration (0..3)
-            const int c_ln = (lane & 7) * 4;               // column inside a chunk
-            const int n_base = ti.n0 + col_half * HALF_N;
-            // fast path: full-width tile, 16-byte aligned rows -> vector I/O and the warp's whole residual tile prefetched into
+            // phase-2 geometry: VPR float4 vectors span one tile row; a warp covers RPI rows per iteration
+            constexpr int VPR = HALF_N / 4;                // 16 (BLOCK_N=128) or 8 (BLOCK_N=64) vectors per half row
+            constexpr int RPI = 32 / VPR;                  // 2 or 4 rows per iteration
+            constexpr int ITERS = 32 / RPI;
+            const int r_sub = lane / VPR;
+            const int c_ln = (lane % VPR) * 4;             // column inside this warp's half
+            const int n_ln = ti.n0 + col_half * HALF_N + c_ln;
+            // fast path: full-width tile, 16-byte aligned rows -> vector I/O and the whole residual tile prefetched into
             // registers BEFORE waiting for the accumulator, so its DRAM latency hides behind this tile's MMAs
             const bool fast = p.vec_ok && (ti.n0 + kBlockN <= p.Ncols);
-            float4 resv[NCHUNK][ITERS];
+            float4 resv[ITERS];
             if (fast && p.residual) {
 #pragma unroll
                 for (int i = 0; i < ITERS; ++i) {
-                    const int rr = i * 4 + r_sub;
+                    const int rr = i * RPI + r_sub;
                     const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
                     const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
-                    // unconditional loads (out-of-range rows read row 0 and are never stored): a predicated load would make
-                    // the compiler funnel every load through one temporary and serialise their DRAM latencies
-                    const long long o = (ok ? off_row : 0ll) + n_base + c_ln;
-#pragma unroll
-                    for (int ch = 0; ch < NCHUNK; ++ch) resv[ch][i] = __ldg(reinterpret_cast<const float4*>(p.residual + o + ch * 32));
+                    // unconditional load (out-of-range rows read row 0 and are never stored): a predicated load would make
+                    // the compiler funnel all 32 loads through one temporary and serialise their DRAM latencies
+                    const long long o = ok ? off_row + n_ln : (long long)n_ln;
+                    resv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + o));
                 }
             }
-            float4 bias4[NCHUNK];
-#pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch)
-                bias4[ch] = (fast && p.bias_mode == VF_BIAS_N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n_base + ch * 32 + c_ln))
-                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fast && p.bias_mode == VF_BIAS_N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_ln));
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
 
-            float gs[NCHUNK], gq[NCHUNK];                  // fused GroupNorm statistics of this lane's channels
+            // ---- phase 1: TMEM -> registers -> staging row `lane` (scaled by alpha)
+#pragma unroll 1
+            for (int c0 = 0; c0 < HALF_N; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN + col_half * HALF_N + c0), r);
 #pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) { gs[ch] = 0.f; gq[ch] = 0.f; }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + c0 + j) =
+                        make_float4(__uint_as_float(r[j]) * p.alpha, __uint_as_float(r[j + 1]) * p.alpha,
+                                    __uint_as_float(r[j + 2]) * p.alpha, __uint_as_float(r[j + 3]) * p.alpha);
+            }
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld) -> hand the stage back
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+
+            // ---- phase 2: lanes span the columns of a tile row -> fully coalesced stores; bias / activation / residual here
+            if (fast) {
+                float gs = 0.f, gq = 0.f;                 // fused GroupNorm statistics of this lane's 4 channels
 #pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                // ---- phase 1: TMEM -> registers -> staging row `lane` (scaled by alpha)
-                {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockN + col_half * HALF_N + ch * 32), r);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
-                            make_float4(__uint_as_float(r[j]) * p.alpha, __uint_as_float(r[j + 1]) * p.alpha,
-                                        __uint_as_float(r[j + 2]) * p.alpha, __uint_as_float(r[j + 3]) * p.alpha);
-                }
-                if (ch == NCHUNK - 1) {
-                    // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld) -> hand the stage back
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                } else {
-                    __syncwarp();
-                }
-                // ---- phase 2: bias / activation / residual, coalesced stores
-                if (fast) {
-                    const int n_ln = n_base + ch * 32 + c_ln;
-#pragma unroll
-                    for (int i = 0; i < ITERS; ++i) {
-                        const int rr = i * 4 + r_sub;
-                        const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
-                        const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
-                        const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
-                        float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c_ln);
-                        if (p.bias_mode == VF_BIAS_N) { v.x += bias4[ch].x; v.y += bias4[ch].y; v.z += bias4[ch].z; v.w += bias4[ch].w; }
-                        else { v.x += bm; v.y += bm; v.z += bm; v.w += bm; }
-                        if (p.act == VF_ACT_GELU_ERF) { v.x = vf_gelu_erf(v.x); v.y = vf_gelu_erf(v.y); v.z = vf_gelu_erf(v.z); v.w = vf_gelu_erf(v.w); }
-                        if (p.residual) { v.x += resv[ch][i].x; v.y += resv[ch][i].y; v.z += resv[ch][i].z; v.w += resv[ch][i].w; }
-                        if (ok) {
-                            gs[ch] += (v.x + v.y) + (v.z + v.w);
-                            gq[ch] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                            const long long off = off_row + n_ln;
-                            if (p.C_f32) *reinterpret_cast<float4*>(p.C_f32 + off) = v;
-                            if (p.C_bf16) {
-                                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                                uint2 u;
-                                u.x = *reinterpret_cast<uint32_t*>(&lo);
-                                u.y = *reinterpret_cast<uint32_t*>(&hi);
-                                *reinterpret_cast<uint2*>(p.C_bf16 + off) = u;
-                            }
+                for (int i = 0; i < ITERS; ++i) {
+                    const int rr = i * RPI + r_sub;
+                    const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
+                    const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
+                    const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c_ln);
+                    if (p.bias_mode == VF_BIAS_N) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+                    else { v.x += bm; v.y += bm; v.z += bm; v.w += bm; }
+                    if (p.act == VF_ACT_GELU_ERF) { v.x = vf_gelu_erf(v.x); v.y = vf_gelu_erf(v.y); v.z = vf_gelu_erf(v.z); v.w = vf_gelu_erf(v.w); }
+                    if (p.residual) { v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w; }
+                    if (ok) {
+                        gs += (v.x + v.y) + (v.z + v.w);
+                        gq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                        const long long off = off_row + n_ln;
+                        if (p.C_f32) *reinterpret_cast<float4*>(p.C_f32 + off) = v;
+                        if (p.C_bf16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                            uint2 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&lo);
+                            u.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(p.C_bf16 + off) = u;
                         }
                     }
-                } else {
-                    // generic path (N tails, unaligned leading dimensions): scalar, same arithmetic order
+                }
+                if (p.gn_sums) {
+                    // the 32 rows of a warp lie in one image; lanes with equal column vector (different r_sub) and the
+                    // cpg/4 neighbouring lanes of a group are folded with shuffles, then one fp64 RED per (image, group)
+                    const unsigned okmask = __ballot_sync(0xffffffffu, my_ok);
+#pragma unroll
+                    for (int o = VPR; o < 32; o <<= 1) {
+                        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                    }
+                    const int lpg = p.gn_cpg >> 2;
+                    for (int o = 1; o < lpg; o <<= 1) {
+                        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                    }
+                    const int gm_first = __shfl_sync(0xffffffffu, gm, okmask ? (__ffs(okmask) - 1) : 0);
+                    if (okmask && r_sub == 0 && (lane % lpg) == 0) {
+                        const long long slot = ((long long)(gm_first / p.gn_rows_per_img) * p.gn_groups + n_ln / p.gn_cpg) * 2;
+                        atomicAdd(p.gn_sums + slot, (double)gs);
+                        atomicAdd(p.gn_sums + slot + 1, (double)gq);
+                    }
+                }
+            } else {
+                // generic path (N tails, unaligned leading dimensions): scalar, same arithmetic order
 #pragma unroll 1
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
-                        const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
-                        const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
-                        const int n = n_base + ch * 32 + lane;
-                        if (!ok || n >= p.Ncols) continue;
-                        float x = stg[rr * STG_LD + lane];
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int ok = __shfl_sync(0xffffffffu, my_ok, rr);
+                    const long long off_row = __shfl_sync(0xffffffffu, my_off, rr);
+                    const float bm = __shfl_sync(0xffffffffu, bias_m, rr);
+                    if (!ok) continue;
+                    for (int c = lane; c < HALF_N; c += 32) {
+                        const int n = ti.n0 + col_half * HALF_N + c;
+                        if (n >= p.Ncols) continue;
+                        float x = stg[rr * STG_LD + c];
                         x += (p.bias_mode == VF_BIAS_N) ? __ldg(p.bias + n) : bm;
                         if (p.act == VF_ACT_GELU_ERF) x = vf_gelu_erf(x);
                         const long long off = off_row + n;
@@ -492,30 +504,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                         if (p.C_bf16) p.C_bf16[off] = __float2bfloat16(x);
                     }
                 }
-                __syncwarp();                              // staging is rewritten by the next chunk / tile
             }
-            if (fast && p.gn_sums) {
-                // the 32 rows of a warp lie in one image; lanes with equal column vector (different r_sub) and the cpg/4
-                // neighbouring lanes of a group are folded with shuffles, then one fp64 RED per (image, group, chunk)
-                const unsigned okmask = __ballot_sync(0xffffffffu, my_ok);
-                const int lpg = p.gn_cpg >> 2;
-                const int gm_first = __shfl_sync(0xffffffffu, gm, okmask ? (__ffs(okmask) - 1) : 0);
-#pragma unroll
-                for (int ch = 0; ch < NCHUNK; ++ch) {
-                    float a = gs[ch], b = gq[ch];
-                    a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
-                    a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
-                    for (int o = 1; o < lpg; o <<= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        b += __shfl_xor_sync(0xffffffffu, b, o);
-                    }
-                    if (okmask && r_sub == 0 && ((lane & 7) % lpg) == 0) {
-                        const long long slot = ((long long)(gm_first / p.gn_rows_per_img) * p.gn_groups + (n_base + ch * 32 + c_ln) / p.gn_cpg) * 2;
-                        atomicAdd(p.gn_sums + slot, (double)a);
-                        atomicAdd(p.gn_sums + slot + 1, (double)b);
-                    }
-                }
-            }
+            __syncwarp();                                  // staging is reused by the next tile
         }
     }
 
@@ -582,7 +572,7 @@ unsigned make_idesc(bool tf32, int M, int N) {
 
 template <int kBlockN, int kStages, bool kTF32>
 int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
-    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + NUM_EPI_WARPS * 32 * (32 + 4) * 4 /*epilogue staging*/ +
+    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ +
                          1024 /*align slack*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
@@ -727,6 +717,6 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: memset gn_sums: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     }
     cudaStream_t st = vf_s(s);
-    if (block_n == 128) return tf32 ? launch<128, 5, true>(prm, pgrid, st) : launch<128, 5, false>(prm, pgrid, st);
-    return tf32 ? launch<64, 7, true>(prm, pgrid, st) : launch<64, 7, false>(prm, pgrid, st);
+    if (block_n == 128) return tf32 ? launch<128, 4, true>(prm, pgrid, st) : launch<128, 4, false>(prm, pgrid, st);
+    return tf32 ? launch<64, 6, true>(prm, pgrid, st) : launch<64, 6, false>(prm, pgrid, st);
 }
