@@ -112,6 +112,51 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
     }
 }
 
+// ---- 2-CTA (cta_group::2) helpers: PTX forms follow cute/arch/copy_sm100_tma.hpp (SM100_TMA_2SM_LOAD_4D) and
+// cutlass/arch/barrier.h (umma_arrive_multicast_2x1SM, ClusterBarrier::arrive(cta_id))
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// both CTAs of the pair issue their own load; the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    uint32_t leader_bar;       // shared::cluster address of the same barrier in CTA 0 (CUTLASS clears the peer bit; mapa is explicit)
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar)), "r"(0));
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {      // arrives on the same barrier offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <bool kTF32>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kTF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128B = 1024B)
 //   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
@@ -145,11 +190,12 @@ struct TileInfo {
     bool skip;
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t, int block_n) {
+// 2-CTA mode: `t` walks PAIRS of vertically adjacent M tiles (p.tiles_m = number of pairs); CTA `rank` owns tile 2*pair + rank
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t, int block_n, int pair = 0, int rank = 0) {
     TileInfo ti;
     const int n_tile = t % p.tiles_n;
     const int r = t / p.tiles_n;
-    const int m_tile = r % p.tiles_m;
+    const int m_tile = pair ? 2 * (r % p.tiles_m) + rank : r % p.tiles_m;
     const int bz = r / p.tiles_m;
     ti.b1 = bz / p.batch2;
     ti.b2 = bz % p.batch2;
@@ -186,9 +232,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //   warp 1      MMA issuer     — accumulates tile i into TMEM stage (i & 1) while the epilogue drains stage (i-1) & 1
 //   warps 2..5  epilogue       — TMEM -> registers (alpha, bias, GELU) -> per-warp smem staging -> TMEM stage released
 //                                -> coalesced row-wise residual loads / global stores
-template <int kBlockN, int kStages, bool kTF32>
+// k2Cta: thread-block cluster of two CTAs = one `cta_group::2` MMA of M = 256: each CTA loads its own 128 A rows and HALF of the
+// B tile (the tensor cores of both SMs read B from both shared memories), accumulators stay in each CTA's own TMEM; the
+// leader CTA issues the MMAs and its tcgen05.commit arrives on both CTAs' barriers.
+template <int kBlockN, int kStages, bool kTF32, bool k2Cta>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
-    constexpr int B_STAGE_BYTES = kBlockN * ROW_BYTES;
+    constexpr int B_ROWS = k2Cta ? kBlockN / 2 : kBlockN;      // B rows held by this CTA
+    constexpr int B_STAGE_BYTES = B_ROWS * ROW_BYTES;
+    constexpr uint32_t CTAS = k2Cta ? 2 : 1;
+    const uint32_t rank = k2Cta ? cluster_ctarank() : 0;
+    const int sched_id = k2Cta ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int sched_stride = k2Cta ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int UMMA_K_BYTES = 32;           // 16 bf16 or 8 tf32 per instruction
     constexpr int MMAS_PER_STAGE = ROW_BYTES / UMMA_K_BYTES;
@@ -223,28 +277,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], CTAS);                  // 2-CTA: leader's expect_tx arrive + the peer producer's remote arrive
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&a_full_bar[a], 1);
+            mbar_init(&a_full_bar[a], CTAS);
             mbar_init(&a_empty_bar[a], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);   // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS * CTAS);   // one arrive per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp allocates 2 accumulator stages = 2*kBlockN TMEM columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * kBlockN)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (k2Cta) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * kBlockN)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * kBlockN)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (k2Cta) cluster_sync_all();               // both CTAs' barriers are initialised before any remote arrive / TMA
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // 1-CTA / 2-CTA variants of the four pipeline primitives
+    auto arm_full = [&](uint64_t* bar, uint32_t bytes_this_cta) {       // producer announces this CTA's incoming bytes
+        if constexpr (k2Cta) {
+            if (rank == 0) mbar_expect_tx(bar, bytes_this_cta * 2);     // the leader's barrier counts both CTAs' bytes ...
+            else mbar_arrive_remote(bar, 0);                            // ... and one arrive from the peer's producer
+        } else {
+            mbar_expect_tx(bar, bytes_this_cta);
+        }
+    };
+    auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+        if constexpr (k2Cta) tma_load_4d_2sm(dst, tm, bar, c0, c1, c2, c3);
+        else tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+    };
+    auto commit = [&](uint64_t* bar) {
+        if constexpr (k2Cta) tcgen05_commit_2sm(bar);
+        else tcgen05_commit(bar);
+    };
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+        if constexpr (k2Cta) umma_2sm<kTF32>(d, a, b, p.idesc, accumulate);
+        else umma<kTF32>(d, a, b, p.idesc, accumulate);
+    };
+    const int n_off = (int)rank * B_ROWS;                               // this CTA's slice of the B tile (2-CTA: half)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -253,21 +337,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             uint32_t phase = 0;
             int ab = 0;
             uint32_t aphase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileInfo ti = decode_tile(p, t, kBlockN);
+            for (int t = sched_id; t < p.total_tiles; t += sched_stride) {
+                const TileInfo ti = decode_tile(p, t, kBlockN, k2Cta, (int)rank);
                 if (ti.skip) continue;
                 if (p.halo) {
                     const uint32_t halo_bytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * ROW_BYTES;
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
                         mbar_wait(&a_empty_bar[ab], aphase ^ 1);
-                        mbar_expect_tx(&a_full_bar[ab], halo_bytes);
-                        tma_load_4d(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
+                        arm_full(&a_full_bar[ab], halo_bytes);
+                        load(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
                         if (++ab == 2) { ab = 0; aphase ^= 1; }
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
-                            mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
-                            tma_load_4d(halo_b_base + stage * B_STAGE_BYTES, &p.tmB, &full_bar[stage], (tap * p.cin_blocks + cb) * p.bk_elems,
-                                        ti.n0, 0, 0);
+                            arm_full(&full_bar[stage], B_STAGE_BYTES);
+                            load(halo_b_base + stage * B_STAGE_BYTES, &p.tmB, &full_bar[stage], (tap * p.cin_blocks + cb) * p.bk_elems,
+                                 ti.n0 + n_off, 0, 0);
                             if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -277,30 +361,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    arm_full(&full_bar[stage], STAGE_BYTES);
                     if (p.conv) {
                         const int tap = kb / p.cin_blocks;
                         const int cb = kb - tap * p.cin_blocks;
-                        tma_load_4d(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap],
-                                    ti.oy0 + p.tap_dy[tap], ti.img0);
+                        load(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap], ti.oy0 + p.tap_dy[tap],
+                             ti.img0);
                     } else {
-                        tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
+                        load(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
                     }
-                    tma_load_4d(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, ti.n0, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
+                    load(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (2-CTA: the leader CTA issues for the pair) =====================
+        if (lane == 0 && rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             int ab_m = 0;
             uint32_t aphase_m = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileInfo ti = decode_tile(p, t, kBlockN);
+            for (int t = sched_id; t < p.total_tiles; t += sched_stride) {
+                const TileInfo ti = decode_tile(p, t, kBlockN, k2Cta, 0);
                 if (ti.skip) continue;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -325,15 +409,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                             const uint64_t bdesc = make_sw128_desc(smem_u32(halo_b_base + stage * B_STAGE_BYTES));
 #pragma unroll
                             for (int k = 0; k < MMAS_PER_STAGE; ++k)
-                                umma<kTF32>(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
-                                            p.idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                            tcgen05_commit(&empty_bar[stage]);
+                                mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                    (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                            commit(&empty_bar[stage]);
                             if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
                         }
-                        tcgen05_commit(&a_empty_bar[ab_m]);      // halo buffer free once its 36 MMAs retire
+                        commit(&a_empty_bar[ab_m]);              // halo buffer free once its 36 MMAs retire
                         if (++ab_m == 2) { ab_m = 0; aphase_m ^= 1; }
                     }
-                    tcgen05_commit(&tmem_full_bar[acc]);
+                    commit(&tmem_full_bar[acc]);
                     ++it;
                     continue;
                 }
@@ -347,13 +431,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
                     for (int k = 0; k < MMAS_PER_STAGE; ++k) {
                         // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
-                        umma<kTF32>(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
-                                    p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                            (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    tcgen05_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
+                    commit(&empty_bar[stage]);               // frees the smem slot (in both CTAs) once these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(&tmem_full_bar[acc]);          // accumulator complete
+                commit(&tmem_full_bar[acc]);                  // accumulator complete
                 ++it;
             }
         }
@@ -363,8 +447,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         const int col_half = (warp - 2) >> 2;             // which half of the tile's columns this warp owns
         float* stg = staging + (warp - 2) * (32 * STG_LD);   // this warp's private staging tile [32][STG_LD]
         int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileInfo ti = decode_tile(p, t, kBlockN);
+        for (int t = sched_id; t < p.total_tiles; t += sched_stride) {
+            const TileInfo ti = decode_tile(p, t, kBlockN, k2Cta, (int)rank);
             if (ti.skip) continue;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -433,7 +517,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld) -> hand the stage back
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if (k2Cta && rank != 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);    // the leader's issuer waits for both CTAs
+                else mbar_arrive(&tmem_empty_bar[acc]);
+            }
 
             // ---- phase 2: lanes span the columns of a tile row -> fully coalesced stores; bias / activation / residual here
             if (fast) {
@@ -512,9 +599,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     // ---- teardown: everyone done with TMEM, then the allocating warp frees it
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (k2Cta) cluster_sync_all();               // no CTA leaves while its peer may still signal or read it
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBlockN) : "memory");
+        if constexpr (k2Cta)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBlockN) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBlockN) : "memory");
     }
 }
 
@@ -570,17 +661,36 @@ unsigned make_idesc(bool tf32, int M, int N) {
     return d;
 }
 
-template <int kBlockN, int kStages, bool kTF32>
+template <int kBlockN, int kStages, bool kTF32, bool k2Cta>
 int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
-    constexpr int smem = kStages * (A_STAGE_BYTES + kBlockN * ROW_BYTES) + NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ +
+    constexpr int b_rows = k2Cta ? kBlockN / 2 : kBlockN;
+    constexpr int smem = kStages * (A_STAGE_BYTES + b_rows * ROW_BYTES) + NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ +
                          1024 /*align slack*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32, k2Cta>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
         configured = true;
     }
-    tc_gemm_kernel<kBlockN, kStages, kTF32><<<grid, NUM_THREADS, smem, st>>>(prm);
+    if constexpr (k2Cta) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;      // CTA pair on one TPC
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<kBlockN, kStages, kTF32, k2Cta>, prm);
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cluster launch failed: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+    } else {
+        tc_gemm_kernel<kBlockN, kStages, kTF32, k2Cta><<<grid, NUM_THREADS, smem, st>>>(prm);
+    }
     VF_CHECK_LAUNCH("vf_tc_gemm");
     return VF_OK;
 }
@@ -614,6 +724,11 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
 
     // N tile: 128 when the problem is wide enough, else 64 (fewer wasted MMA columns / TMEM)
     const int block_n = (q->Ncols > 64) ? 128 : 64;
+    // CTA pairs (cta_group::2, M = 256 per MMA, B tile split across the pair) for the plain un-batched GEMMs and the convolutions
+    static int two_cta_enabled = -1;
+    if (two_cta_enabled < 0) { const char* e = getenv("VF_TC_2CTA"); two_cta_enabled = (e && e[0] == '0') ? 0 : 1; }
+    const bool k2 = two_cta_enabled && block_n == 128 && q->causal_block == 0 && (q->conv || q->batch1 * q->batch2 == 1);
+    const int b_box_rows = k2 ? block_n / 2 : block_n;
     dim3 grid;
     int rc;
     if (q->conv) {
@@ -649,7 +764,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         const uint64_t Ktot = (uint64_t)q->ntaps * q->Cin;
         const uint64_t dimsB[4] = {Ktot, (uint64_t)q->Ncols, 1, 1};
         const uint64_t strB[3] = {Ktot * es, Ktot * es * q->Ncols, Ktot * es * q->Ncols};
-        const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)block_n, 1, 1};
+        const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)b_box_rows, 1, 1};
         if ((rc = make_tmap(&prm.tmB, q->ab_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
         const int ntiles_img = (q->N + TN - 1) / TN;
         grid = dim3(prm.tiles_x * prm.tiles_y * ntiles_img, (q->Ncols + block_n - 1) / block_n, 1);
@@ -675,15 +790,15 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         if ((rc = make_tmap(&prm.tmA, q->ab_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
         const uint64_t dimsB[4] = {(uint64_t)q->K, (uint64_t)q->Ncols, prm.b_bm2 ? (uint64_t)q->batch2 : 1, prm.b_bm1 ? (uint64_t)q->batch1 : 1};
         const uint64_t strB[3] = {(uint64_t)q->ldb * es, prm.b_bm2 ? (uint64_t)q->b_sb2 * es : fbB, prm.b_bm1 ? (uint64_t)q->b_sb1 * es : fbB};
-        const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)block_n, 1, 1};
+        const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)b_box_rows, 1, 1};
         if ((rc = make_tmap(&prm.tmB, q->ab_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
         VF_CHECK_ARG(q->causal_block == 0 || (q->causal_block % bk == 0 || bk % q->causal_block == 0), "vf_tc_gemm: causal block");
         grid = dim3((q->M + BLOCK_M - 1) / BLOCK_M, (q->Ncols + block_n - 1) / block_n, q->batch1 * q->batch2);
     }
     // persistent launch: `grid` so far is the tile space (m tiles, n tiles, batches); one CTA per SM walks it, n fastest
-    prm.tiles_m = (int)grid.x;
+    prm.tiles_m = k2 ? (int)((grid.x + 1) / 2) : (int)grid.x;      // 2-CTA: pairs of M tiles
     prm.tiles_n = (int)grid.y;
-    const long long total = (long long)grid.x * grid.y * grid.z;
+    const long long total = (long long)prm.tiles_m * grid.y * grid.z;
     VF_CHECK_ARG(total > 0 && total < (1ll << 31), "vf_tc_gemm: tile count out of range");
     prm.total_tiles = (int)total;
     static int num_sms = 0;
@@ -692,8 +807,9 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
-    const dim3 pgrid((unsigned)(total < num_sms ? total : num_sms), 1, 1);
-    prm.idesc = make_idesc(tf32, BLOCK_M, block_n);
+    const long long sched_units = k2 ? num_sms / 2 : num_sms;       // persistent CTAs (or CTA pairs)
+    const dim3 pgrid((unsigned)((total < sched_units ? total : sched_units) * (k2 ? 2 : 1)), 1, 1);
+    prm.idesc = make_idesc(tf32, k2 ? 2 * BLOCK_M : BLOCK_M, block_n);
     {
         auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
@@ -717,6 +833,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: memset gn_sums: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     }
     cudaStream_t st = vf_s(s);
-    if (block_n == 128) return tf32 ? launch<128, 4, true>(prm, pgrid, st) : launch<128, 4, false>(prm, pgrid, st);
-    return tf32 ? launch<64, 6, true>(prm, pgrid, st) : launch<64, 6, false>(prm, pgrid, st);
+    if (k2) return tf32 ? launch<128, 6, true, true>(prm, pgrid, st) : launch<128, 6, false, true>(prm, pgrid, st);
+    if (block_n == 128) return tf32 ? launch<128, 4, true, false>(prm, pgrid, st) : launch<128, 4, false, false>(prm, pgrid, st);
+    return tf32 ? launch<64, 6, true, false>(prm, pgrid, st) : launch<64, 6, false, false>(prm, pgrid, st);
 }
