@@ -1,0 +1,26 @@
+"""Where does the MMA issuer wait?  clock64 counters around its mbarrier waits (profiling aid; VF_TC_2CTA / VF_TC_HALO select the mode)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from viewformer_b200 import _lib as L
+lib = L.load(True)
+def run(name, fn):
+    for _ in range(2): fn()
+    buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+    lib.vf_tc_debug_counters(ctypes.c_void_p(buf.data_ptr()))
+    torch.cuda.synchronize(); fn(); torch.cuda.synchronize()
+    lib.vf_tc_debug_counters(ctypes.c_void_p(0))
+    t = buf.double().cpu(); t = t[t[:, 3] > 0]
+    tot, ops, tm, tiles = t[:, 0].mean().item(), t[:, 1].mean().item(), t[:, 2].mean().item(), t[:, 3].mean().item()
+    full = buf.double().cpu()
+    prod = full[full[:, 4] > 0]
+    pw = 100 * (prod[:, 5] / prod[:, 4])
+    print(f"    producers: {prod.shape[0]} CTAs, waiting on empty barriers {pw.mean().item():5.1f}% of their time (min {pw.min().item():.1f} max {pw.max().item():.1f})")
+    print(f"{name:40s} issuers {t.shape[0]:3d} tiles/issuer {tiles:6.1f} | cycles/tile {tot/tiles:8.0f} | wait operands {100*ops/tot:5.1f}% | wait tmem_empty {100*tm/tot:5.1f}% | issuing {100*(tot-ops-tm)/tot:5.1f}%")
+n, hw, c = 288, 128, 128
+x = torch.randn((n, hw, hw, c), device="cuda").bfloat16(); w = (torch.randn((c, 9 * c), device="cuda") / 30).bfloat16()
+b = torch.zeros(c, device="cuda"); res = torch.randn((n, hw, hw, c), device="cuda"); out = torch.empty((n, hw, hw, c), device="cuda")
+run("conv 128->128 @128^2 no residual", lambda: L.tc_conv(x, w, b, out=out))
+run("conv 128->128 @128^2 + residual", lambda: L.tc_conv(x, w, b, out=out, residual=res))
+A = torch.randn((20480, 3072), device="cuda").bfloat16(); B = torch.randn((768, 3072), device="cuda").bfloat16(); o2 = torch.empty((20480, 768), device="cuda")
+run("gemm 20480x768x3072", lambda: L.tc_gemm(A, B, o2, M=20480, N=768, K=3072, lda=3072, ldb=3072, ldc=768))

@@ -34,6 +34,10 @@ def needs_build():
 
 
 def build(force=False, verbose=True):
+    if os.environ.get("VF_TC_STALL_COUNTERS") == "1":      # profiling build: clock64 stall counters in the tcgen05 kernel
+        force = True
+        if "-DVF_TC_STALL_COUNTERS" not in NVCC_FLAGS:
+            NVCC_FLAGS.append("-DVF_TC_STALL_COUNTERS")
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()

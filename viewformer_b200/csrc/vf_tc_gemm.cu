@@ -46,6 +46,7 @@ struct TcParams {
     long long ldc, c_sb1, c_sb2;
     unsigned idesc;
     int vec_ok;                // output/residual/bias addressing is 16-byte friendly -> vector epilogue
+    long long* dbg;            // profiling aid: per-CTA {total, wait_operands, wait_tmem_empty, tiles} MMA-issuer cycles (null in production)
     int halo;                  // conv only: 1 = load one (TH+2)x(TW+2) halo tile per 64-channel block and address the 9 taps
                                // as row-shifted UMMA descriptors into it (9x fewer A bytes from L2); 0 = one shifted TMA box per tap
     double* gn_sums;           // optional fused GroupNorm statistics of the OUTPUT: [images][groups][2] (sum, sum of squares)
@@ -128,9 +129,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 // both CTAs of the pair issue their own load; the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    uint32_t leader_bar;       // shared::cluster address of the same barrier in CTA 0 (CUTLASS clears the peer bit; mapa is explicit)
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar)), "r"(0));
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {      // shared::cluster address of the same location in CTA 0
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(0));
+    return ra;
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -277,11 +281,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(&full_bar[s], CTAS);                  // 2-CTA: leader's expect_tx arrive + the peer producer's remote arrive
+            mbar_init(&full_bar[s], 1);                     // 2-CTA: only the leader arrives (expect_tx of both CTAs' bytes)
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&a_full_bar[a], CTAS);
+            mbar_init(&a_full_bar[a], 1);
             mbar_init(&a_empty_bar[a], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -308,17 +312,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     // 1-CTA / 2-CTA variants of the four pipeline primitives
-    auto arm_full = [&](uint64_t* bar, uint32_t bytes_this_cta) {       // producer announces this CTA's incoming bytes
+    // 2-CTA: every load of either CTA credits its bytes to the LEADER's barrier; only the leader arms it (with both CTAs'
+    // byte count).  A peer load may land before the leader has armed the phase: the tx-count just goes negative meanwhile.
+    uint32_t lead_full = 0, lead_afull = 0;
+    if constexpr (k2Cta) { lead_full = leader_addr(full_bar); lead_afull = leader_addr(a_full_bar); }
+    auto arm_full = [&](uint64_t* bar, uint32_t bytes_this_cta) {
         if constexpr (k2Cta) {
-            if (rank == 0) mbar_expect_tx(bar, bytes_this_cta * 2);     // the leader's barrier counts both CTAs' bytes ...
-            else mbar_arrive_remote(bar, 0);                            // ... and one arrive from the peer's producer
+            if (rank == 0) mbar_expect_tx(bar, bytes_this_cta * 2);
         } else {
             mbar_expect_tx(bar, bytes_this_cta);
         }
     };
     auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
-        if constexpr (k2Cta) tma_load_4d_2sm(dst, tm, bar, c0, c1, c2, c3);
-        else tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+        if constexpr (k2Cta) {
+            const bool is_a = bar >= a_full_bar && bar < a_full_bar + 2;
+            const uint32_t lb = is_a ? lead_afull + (uint32_t)((bar - a_full_bar) * 8) : lead_full + (uint32_t)((bar - full_bar) * 8);
+            tma_load_4d_2sm(dst, tm, lb, c0, c1, c2, c3);
+        } else {
+            tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+        }
     };
     auto commit = [&](uint64_t* bar) {
         if constexpr (k2Cta) tcgen05_commit_2sm(bar);
@@ -337,6 +349,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             uint32_t phase = 0;
             int ab = 0;
             uint32_t aphase = 0;
+#ifdef VF_TC_STALL_COUNTERS
+            const bool pdbg = p.dbg != nullptr;
+#else
+            constexpr bool pdbg = false;
+#endif
+            long long pc_wait = 0, pc0 = 0;
+            const long long pc_start = pdbg ? clock64() : 0;
             for (int t = sched_id; t < p.total_tiles; t += sched_stride) {
                 const TileInfo ti = decode_tile(p, t, kBlockN, k2Cta, (int)rank);
                 if (ti.skip) continue;
@@ -348,7 +367,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                         load(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
                         if (++ab == 2) { ab = 0; aphase ^= 1; }
                         for (int tap = 0; tap < 9; ++tap) {
+                            if (pdbg) pc0 = clock64();
                             mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (pdbg) pc_wait += clock64() - pc0;
                             arm_full(&full_bar[stage], B_STAGE_BYTES);
                             load(halo_b_base + stage * B_STAGE_BYTES, &p.tmB, &full_bar[stage], (tap * p.cin_blocks + cb) * p.bk_elems,
                                  ti.n0 + n_off, 0, 0);
@@ -358,7 +379,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     continue;
                 }
                 for (int kb = 0; kb < ti.nkb; ++kb) {
+                    if (pdbg) pc0 = clock64();
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (pdbg) pc_wait += clock64() - pc0;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     arm_full(&full_bar[stage], STAGE_BYTES);
@@ -374,6 +397,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
+            if (pdbg) {
+                long long* d = p.dbg + 8 * blockIdx.x;
+                d[4] = clock64() - pc_start; d[5] = pc_wait;
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (2-CTA: the leader CTA issues for the pair) =====================
@@ -383,12 +410,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             int it = 0;
             int ab_m = 0;
             uint32_t aphase_m = 0;
+            long long c_ops = 0, c_tmem = 0, c_tiles = 0, c0 = 0;       // stall counters, only maintained when p.dbg != null
+#ifdef VF_TC_STALL_COUNTERS
+            const bool dbg = p.dbg != nullptr;
+#else
+            constexpr bool dbg = false;          // build with -DVF_TC_STALL_COUNTERS for scripts/tc_stall_probe.py
+#endif
+            const long long c_start = dbg ? clock64() : 0;
             for (int t = sched_id; t < p.total_tiles; t += sched_stride) {
                 const TileInfo ti = decode_tile(p, t, kBlockN, k2Cta, 0);
                 if (ti.skip) continue;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
+                if (dbg) c0 = clock64();
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator stage
+                if (dbg) { c_tmem += clock64() - c0; ++c_tiles; }
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBlockN);
                 if (p.halo) {
@@ -398,10 +434,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     // so row-shifted descriptors with base_offset 0 read exactly what TMA wrote.
                     const uint32_t pitch = (uint32_t)(p.TW + 2);
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        if (dbg) c0 = clock64();
                         mbar_wait(&a_full_bar[ab_m], aphase_m);
+                        if (dbg) c_ops += clock64() - c0;
                         const uint32_t a_base = smem_u32(smem + ab_m * HALO_BUF_BYTES);
                         for (int tap = 0; tap < 9; ++tap) {
+                            if (dbg) c0 = clock64();
                             mbar_wait(&full_bar[stage], phase);
+                            if (dbg) c_ops += clock64() - c0;
                             tcgen05_fence_after();
                             const uint32_t a_addr = a_base + ((uint32_t)(tap / 3) * pitch + (uint32_t)(tap % 3)) * ROW_BYTES;
                             uint64_t adesc = make_sw128_desc(a_addr);
@@ -422,7 +462,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     continue;
                 }
                 for (int kb = 0; kb < ti.nkb; ++kb) {
+                    if (dbg) c0 = clock64();
                     mbar_wait(&full_bar[stage], phase);
+                    if (dbg) c_ops += clock64() - c0;
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
@@ -439,6 +481,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                 }
                 commit(&tmem_full_bar[acc]);                  // accumulator complete
                 ++it;
+            }
+            if (dbg) {
+                long long* d = p.dbg + 8 * blockIdx.x;
+                d[0] = clock64() - c_start; d[1] = c_ops; d[2] = c_tmem; d[3] = c_tiles;
             }
         }
     } else {
@@ -697,6 +743,10 @@ int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
+static long long* g_tc_dbg = nullptr;
+// profiling aid (scripts/tc_stall_probe.py), not in the public header: MMA-issuer stall counters of the following launches ([grid][4] int64)
+extern "C" void vf_tc_debug_counters(long long* buf) { g_tc_dbg = buf; }
+
 extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     VF_CHECK_ARG(q && q->A && q->B, "vf_tc_gemm: null operand");
     VF_CHECK_ARG(q->C_f32 || q->C_bf16, "vf_tc_gemm: no output");
@@ -721,12 +771,15 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     prm.ldc = q->ldc;
     prm.causal_block = q->causal_block;
     prm.causal_skip_n = q->causal_skip_n;
+    prm.dbg = g_tc_dbg;
 
     // N tile: 128 when the problem is wide enough, else 64 (fewer wasted MMA columns / TMEM)
     const int block_n = (q->Ncols > 64) ? 128 : 64;
     // CTA pairs (cta_group::2, M = 256 per MMA, B tile split across the pair) for the plain un-batched GEMMs and the convolutions
     static int two_cta_enabled = -1;
-    if (two_cta_enabled < 0) { const char* e = getenv("VF_TC_2CTA"); two_cta_enabled = (e && e[0] == '0') ? 0 : 1; }
+    // measured in round 1 (profiles/r01_tc_kernel_analysis.md): at BLOCK_N = 128 the pair is on par with two single CTAs, so it is
+    // opt-in (VF_TC_2CTA=1) until the 256-wide tiles that make it pay are in
+    if (two_cta_enabled < 0) { const char* e = getenv("VF_TC_2CTA"); two_cta_enabled = (e && e[0] == '1') ? 1 : 0; }
     const bool k2 = two_cta_enabled && block_n == 128 && q->causal_block == 0 && (q->conv || q->batch1 * q->batch2 == 1);
     const int b_box_rows = k2 ? block_n / 2 : block_n;
     dim3 grid;
