@@ -155,6 +155,15 @@ int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, in
  * ---------------------------------------------------------------------------------------- */
 int vf_vq_lookup(const float* z, const float* Et, const float* esq, int64_t M, int D, int K,
                  int64_t* idx, float* quant, double* diff_sum, vf_stream_t s);
+/* Tensor-core lookup (same result as vf_vq_lookup):
+ *   1. vf_vq_split3: x f32 [rows,D] -> bf16 [rows,3D] = [hi|hi|lo] (codebook=0) or [hi|lo|hi] (codebook=1), hi+lo ~ x to 2^-16
+ *   2. vf_tc_gemm: scores[M,K] = -2 * A3 . B3^T + esq   (one bf16 GEMM with K = 3D; |z|^2 is common to all codes)
+ *   3. vf_vq_select: per row the approximate minimum; every code within the bf16x3 error bound tol*(|z|^2+|e|^2) of it is
+ *      re-scored in fp64 (direct squared differences), so the returned index is the exact-arithmetic nearest neighbour
+ *      (ties -> smaller index); also gathers quant and accumulates diff.  n_rescored (nullable) counts rows with > 1 candidate. */
+int vf_vq_split3(const float* x, int64_t rows, int D, int codebook, void* out_bf16, vf_stream_t s);
+int vf_vq_select(const float* scores, const float* z, const float* Et, const float* esq, int64_t M, int D, int K, float tol,
+                 int64_t* idx, float* quant, double* diff_sum, int* n_rescored, vf_stream_t s);
 int vf_gather_rows(const float* table, const int64_t* idx, int64_t M, int D, int64_t n_rows, float* out, vf_stream_t s);
 /* training statistics of QuantizeEMA (utils_th.py:47-48): counts[K] += onehot, embed_sum[D,K] += z^T onehot */
 int vf_vq_ema_stats(const float* z, const int64_t* idx, int64_t M, int D, int K,

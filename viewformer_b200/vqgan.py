@@ -254,7 +254,7 @@ class VQGAN:
         w["post_quant_conv"] = lin("post_quant_conv", self.exact)
         emb = sd["quantize.embeddings"].to(dev, torch.float32).contiguous()             # [D,K] (utils_th.py:17-18)
         et, esq = L.vq_prepare_codebook(emb)
-        w["q"] = dict(emb=emb, et=et, esq=esq,
+        w["q"] = dict(emb=emb, et=et, esq=esq, et3=L.vq_split3(et, True) if prec.use_tc else None,
                       cs=sd["quantize.ema_cluster_size_hidden"].to(dev, torch.float32).contiguous(),
                       dw=sd["quantize.ema_dw_hidden"].to(dev, torch.float32).contiguous(),
                       counter=int(sd["quantize.counter"]))
@@ -376,7 +376,11 @@ class VQGAN:
     def _quantize(self, z_rows, want_quant=True):
         """QuantizeEMA.forward (utils_th.py:32-68) on rows [M,D]; returns (quant rows | None, diff, idx)."""
         q = self._w["q"]
-        idx, quant, dsum = L.vq_lookup(z_rows, q["et"], q["esq"], want_quant=want_quant, want_diff=True)
+        if q["et3"] is not None and z_rows.shape[1] % 64 == 0:
+            # tensor-core distance GEMM (bf16x3) + exact fp64 re-score of every near-minimal candidate: same indices as the fp32 kernel
+            idx, quant, dsum = L.vq_lookup_tc(z_rows, q["et"], q["esq"], q["et3"], want_quant=want_quant, want_diff=True)
+        else:
+            idx, quant, dsum = L.vq_lookup(z_rows, q["et"], q["esq"], want_quant=want_quant, want_diff=True)
         if self.training:
             self._ema_update(z_rows, idx)
         diff = (dsum / float(z_rows.numel())).to(torch.float32).reshape(())
@@ -393,6 +397,8 @@ class VQGAN:
         corr = float(1.0 - torch.pow(torch.tensor(self.decay), torch.tensor(q["counter"], dtype=torch.int64)))
         alpha = 1 - self.decay
         L.vq_ema_update(counts, esum, alpha, corr, self.eps, q["cs"], q["dw"], q["emb"], q["et"], q["esq"])
+        if q["et3"] is not None:
+            q["et3"] = L.vq_split3(q["et"], True)
         self._refresh_decode_table()
 
     # ------------------------------------------------------------------ NHWC entry points (TF-twin convention)
