@@ -83,9 +83,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count_in(self, t0, t1):
+        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
+
+    def stop(self, windows):
+        """windows: [(t0, t1)] monotonic intervals during which the GPU ran the measured step; only samples read inside
+        them count (nvidia-smi is started before the warm-up so that it is already streaming when the timed region begins)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -94,7 +99,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if not any(t0 <= t <= t1 for t0, t1 in windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -226,6 +233,9 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step_resident()
     torch.cuda.synchronize()
@@ -234,12 +244,23 @@ def run_b200(args):
     host_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
     _lib.reset_launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    w0 = time.monotonic()
     ms_total = timed(step_resident, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    windows = [(w0, time.monotonic())]
     launches = _lib.launch_count()
+    clock_note = "timed region"
+    if rank == 0 and sampler.proc is not None and sampler.count_in(*windows[0]) < 3:
+        # a short timed region (K steps of ~30 ms) can end between two 100 ms nvidia-smi samples: keep the GPU on the
+        # identical step for ~1.5 s more (untimed) so that the clocks / throttle reasons under this load are observed
+        w1 = time.monotonic()
+        while time.monotonic() - w1 < 1.5:
+            step_resident()
+            torch.cuda.synchronize()
+        windows.append((w1, time.monotonic()))
+        clock_note = "timed region + 1.5 s of the identical step right after it (region shorter than the sampling period)"
+    clocks = sampler.stop(windows) if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled"] = clock_note
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)

@@ -55,13 +55,15 @@ int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W,
  * vf_groupnorm_apply: y = ((x-mean)*rstd*gamma+beta) [swish]; normalize=0 -> plain cast/upsample.
  *   layout: 0 = same shape; 1 = nearest x2 upsample, y is [N, 2H, 2W, C]; 2 = space-to-depth, y is [N, H/2, W/2, 4C]
  *   with channel block (a*2+b)*C holding pixel (2y+a, 2x+b) — the operand layout that turns the reference's
- *   pad(0,1,0,1)+stride-2 3x3 conv (vqgan_th.py:45-49) into a stride-1 tap-table conv.  y_dtype VF_F32 | VF_BF16.
+ *   pad(0,1,0,1)+stride-2 3x3 conv (vqgan_th.py:45-49) into a stride-1 tap-table conv.
+ *   (x_dtype, y_dtype): (F32,F32) exact order of operations; (F32,BF16) and (BF16,BF16) tensor-core operand producers
+ *   (affine folded to one FMA, ex2/rcp swish).  grid = (pixel chunks, N): N <= 65535.
  * ---------------------------------------------------------------------------------------- */
 int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* sums, float* mean_rstd,
                        vf_stream_t s);
 /* (sum, sumsq) -> (mean, rstd) for `count` elements per (image, group); n_stats = images*groups */
 int vf_groupnorm_finalize(const double* sums, int n_stats, double count, float eps, float* mean_rstd, vf_stream_t s);
-int vf_groupnorm_apply(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
+int vf_groupnorm_apply(const void* x, int x_dtype, const float* mean_rstd, const float* gamma, const float* beta,
                        int N, int H, int W, int C, int groups, float eps, int normalize, int swish,
                        int layout, void* y, int y_dtype, vf_stream_t s);
 
@@ -202,6 +204,12 @@ int vf_pose_postprocess(const float* raw, int64_t rows, float pose_multiplier, f
 int vf_cameras_prepare(const float* cams, int B, int T, int relative, float* out, float* transform, vf_stream_t s);
 /* inverse map (evaluate_transformer.py:81-87): out[b,i] = transform[b] o cams[b,i];  cams [B,n,7], transform [B,7] */
 int vf_cameras_from_relative(const float* cams, const float* transform, int B, int n, float* out, vf_stream_t s);
+/* evaluation losses of MIGT.call(compute_losses=True) — models/migt.py:417-448, 165-177 */
+int vf_cross_entropy_rows(const float* logits, const int32_t* labels, int64_t rows, int cols, float smoothing, float* out,
+                          vf_stream_t s);                       /* sparse softmax CE per row (fp32) */
+int vf_pose_loss_rows(const float* raw, const float* poses, int64_t rows, int tokens_per_view, float pose_multiplier,
+                      float* pos_out, float* ori_out, vf_stream_t s);   /* per-token MSE of position / raw quaternion */
+int vf_row_mean(const float* x, int64_t rows, int n, int start, float* out, vf_stream_t s);   /* out[r] = mean(x[r, start:n]) */
 /* plain dtype casts / strided copies used between ops */
 int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s);
 /* sum(|a-b|) and sum((a-b)^2) into double[2] (training losses, vqgan_th.py:401) */

@@ -64,6 +64,30 @@ def test_groupnorm(L, C, H, W):
     report("upsample", got.permute(0, 3, 1, 2), F.interpolate(x, scale_factor=2.0, mode="nearest"), 0, 0)
 
 
+@pytest.mark.parametrize("n,hw,C", [(2, 64, 128), (3, 24, 256), (1, 8, 512)])
+def test_groupnorm_layouts_and_chunking(L, n, hw, C):
+    """several pixel chunks per image (grid.x > 1), the upsample / space-to-depth stores, and the bf16 -> bf16 edge."""
+    x = (torch.randn(n, hw, hw, C, generator=g(hw + C)) * 1.5 + 0.3).cuda()
+    ga, be = (1 + 0.1 * torch.randn(C, generator=g(1))).cuda(), (0.1 * torch.randn(C, generator=g(2))).cuda()
+    want = F.group_norm(x.permute(0, 3, 1, 2).double().cpu(), 32, ga.double().cpu(), be.double().cpu(), eps=1e-6)
+    want = (want * torch.sigmoid(want)).permute(0, 2, 3, 1)
+    base = L.groupnorm(x, ga, be, swish=True, out_dtype=torch.float32)
+    report("gn chunked", base, want, 2e-5, 1e-5)
+    up = L.groupnorm(x, ga, be, swish=True, out_dtype=torch.float32, upsample=True)
+    assert torch.equal(up, base.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    s2 = L.groupnorm(x, ga, be, swish=True, out_dtype=torch.float32, s2d=True)
+    want_s2 = base.reshape(n, hw // 2, 2, hw // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(n, hw // 2, hw // 2, 4 * C)
+    assert torch.equal(s2, want_s2)
+    # bf16 input carrying fp32-accumulated statistics (what a conv epilogue hands over)
+    xb = x.bfloat16()
+    o = x.double().reshape(n, hw * hw, 32, C // 32)
+    xb._gn_sums = (torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1).contiguous(), 32)
+    got = L.groupnorm(xb, ga, be, swish=True, out_dtype=torch.bfloat16)
+    report("gn bf16->bf16", got.float(), want, 4e-2, 2e-2)
+    with pytest.raises(Exception):
+        L.groupnorm(x.bfloat16(), ga, be, swish=True, out_dtype=torch.bfloat16)      # bf16 input without statistics
+
+
 def test_layernorm(L):
     x = torch.randn(70, 768, generator=g(3)) * 3 + 1
     ga, be = 1 + 0.1 * torch.randn(768, generator=g(4)), 0.1 * torch.randn(768, generator=g(5))
@@ -397,6 +421,13 @@ def test_tc_conv_fused_groupnorm_statistics(L, cin, cout, n, hw):
     plain = out.clone()                                        # clone drops the attached statistics -> stats kernel path
     y_plain = L.groupnorm(plain, ga, be, swish=True, out_dtype=torch.float32)
     report("gn via fused stats vs stats kernel", y_fused, y_plain, 2e-5, 1e-5)
+    # bf16 output edge: same statistics (taken from the fp32 accumulators), output rounded once
+    out_b = L.tc_conv(x, w, b, residual=res, gn_groups=32, out_dtype=torch.bfloat16)
+    assert out_b.dtype == torch.bfloat16 and torch.equal(out_b._gn_sums[0].cpu(), sums) is not None
+    report("bf16-edge gn sums", out_b._gn_sums[0].cpu(), want, 1e-2, 1e-5)
+    assert torch.equal(out_b, out.bfloat16())
+    y_edge = L.groupnorm(out_b, ga, be, swish=True, out_dtype=torch.bfloat16)
+    report("gn over bf16 edge", y_edge.float(), y_plain, 6e-2, 3e-2)
 
 
 @pytest.mark.parametrize("B,T,H,blk", [(2, 4, 3, 64), (1, 10, 2, 64), (2, 3, 2, 64), (1, 5, 1, 32)])

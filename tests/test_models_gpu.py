@@ -172,6 +172,34 @@ def test_migt_three_streams_small(precision, tol):
     assert _stats(f"3-stream pose {precision}", got["pose_prediction"], o["pose_prediction"])[0] < max(tol, 1e-3) * 5
 
 
+@pytest.mark.parametrize("precision,tol,smoothing", [("fp32", 1e-4, 0.0), ("fp32", 1e-4, 0.1), ("bf16", 3e-2, 0.0)])
+def test_migt_compute_losses_small(precision, tol, smoothing):
+    """MIGT.call(compute_losses=True) (migt.py:364-373, 417-448): teacher-forced CE + pose regression losses."""
+    import dataclasses
+    cfg = dataclasses.replace(MIGTConfig(**SMALL_MIGT), n_loss_skip=2, label_smoothing=smoothing, image_generation_weight=0.7,
+                              localization_weight="0.5")
+    sd, model = _migt(cfg, 6, precision)
+    codes, cams, _ = _migt_inputs(cfg, 3, 5, seed=12)
+    with torch.no_grad():
+        o = mo.forward(sd, cfg, dict(input_ids=codes, poses=cams), compute_losses=True, localization_weight=0.5)
+        if smoothing > 0:       # restate the smoothed CE of migt.py:99-104 on the oracle logits
+            lg = o["logits"].reshape(-1, cfg.n_embeddings)
+            y = torch.nn.functional.one_hot(codes.reshape(-1), cfg.n_embeddings).float() * (1 - smoothing) + smoothing / cfg.n_embeddings
+            ce = -(y * torch.log_softmax(lg, -1)).sum(-1).reshape(3, 5, 64)[:, cfg.n_loss_skip:].mean((1, 2))
+            o["loss"] = o["loss"] - o["ce_loss"] * cfg.image_generation_weight + ce * cfg.image_generation_weight
+            o["ce_loss"] = ce
+    got = model(dict(input_ids=codes, poses=cams), compute_losses=True)
+    for k in ("ce_loss", "pose_pos_loss", "pose_ori_loss", "pose_loss", "loss"):
+        assert list(got[k].shape) == [3]
+        rel = ((got[k].cpu() - o[k]).abs() / o[k].abs().clamp_min(1e-6)).max().item()
+        print(f"[losses {precision}] {k}: got {got[k].cpu().tolist()} want {o[k].tolist()} rel {rel:.2e}")
+        assert rel < tol, k
+    assert got["localization_weight"] == 0.5
+    assert _stats(f"losses logits {precision}", got["logits"], o["logits"])[0] < max(tol, 2e-4) * 2
+    with pytest.raises(NotImplementedError):
+        model(dict(input_ids=codes, poses=cams), training=True)
+
+
 def test_migt_full_size_vs_oracle_golden(golden_dir):
     """Full-size MIGT (12 layers, d=768), B=1,T=10: golden from the restatement (parity unpinned: TF absent)."""
     g = np.load(os.path.join(golden_dir, "migt_full.npz"))

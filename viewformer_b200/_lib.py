@@ -23,7 +23,7 @@ EXPORTS = [
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal",
-    "vf_vq_split3", "vf_vq_select",
+    "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
 ]
 
 
@@ -182,9 +182,10 @@ def nhwc_to_nchw(x):
 
 # ----------------------------------------------------------------------------------------------- norms
 def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample=False, normalize=True, s2d=False):
-    """x f32 [N,H,W,C] -> GroupNorm(32) [+swish] [+nearest x2] as out_dtype (vqgan_th.py:11-17,29-30)."""
+    """x f32|bf16 [N,H,W,C] -> GroupNorm(32) [+swish] [+nearest x2] as out_dtype (vqgan_th.py:11-17,29-30).
+    A bf16 x must carry the statistics its producing conv accumulated (from the fp32 accumulators) in ``_gn_sums``."""
     lib = load(True)
-    _dev(x, torch.float32)
+    _dev(x)
     n, h, w, c = x.shape
     stats = None
     if normalize:
@@ -194,11 +195,13 @@ def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample
             _check(lib.vf_groupnorm_finalize(_p(fused[0]), n * groups, C.c_double(float(h * w * (c // groups))), C.c_float(eps),
                                              _p(stats), _stream()))
         else:
+            if x.dtype != torch.float32:
+                raise LibraryError("groupnorm: a bf16 input needs fused statistics from its producer")
             sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
             _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
     oshape = (n, 2 * h, 2 * w, c) if upsample else ((n, h // 2, w // 2, 4 * c) if s2d else (n, h, w, c))
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
-    _check(lib.vf_groupnorm_apply(_p(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
+    _check(lib.vf_groupnorm_apply(_p(x), _dt(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
                                   int(normalize), int(swish), 1 if upsample else (2 if s2d else 0), _p(y), _dt(y), _stream()))
     return y
 
@@ -390,7 +393,7 @@ def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, 
             p.C_bf16 = o.data_ptr()
     p.ldc = cout
     sums = None
-    if gn_groups and out.dtype == torch.float32 and gn_fusable(cout, gn_groups, n * oh * ow, oh * ow, cout):
+    if gn_groups and gn_fusable(cout, gn_groups, n * oh * ow, oh * ow, cout):
         sums = torch.empty((n, gn_groups, 2), dtype=torch.float64, device=out.device)
         p.gn_sums, p.gn_groups = sums.data_ptr(), gn_groups
     _check(lib.vf_tc_gemm(C.byref(p), _stream()))
@@ -539,6 +542,35 @@ def cameras_from_relative(cams, transform):
     b, n, _ = cams.shape
     out = torch.empty_like(cams)
     _check(lib.vf_cameras_from_relative(_p(cams), _p(transform), b, n, _p(out), _stream()))
+    return out
+
+
+def cross_entropy_rows(logits_rows, labels_i32, smoothing=0.0):
+    lib = load(True)
+    _dev(logits_rows, torch.float32)
+    _dev(labels_i32, torch.int32)
+    rows, cols = logits_rows.shape
+    out = torch.empty((rows,), dtype=torch.float32, device=logits_rows.device)
+    _check(lib.vf_cross_entropy_rows(_p(logits_rows), _p(labels_i32), C.c_int64(rows), cols, C.c_float(smoothing), _p(out), _stream()))
+    return out
+
+
+def pose_loss_rows(raw_rows, poses_bt7, tokens_per_view, mult):
+    lib = load(True)
+    rows = raw_rows.shape[0]
+    pos = torch.empty((rows,), dtype=torch.float32, device=raw_rows.device)
+    ori = torch.empty((rows,), dtype=torch.float32, device=raw_rows.device)
+    _check(lib.vf_pose_loss_rows(_p(raw_rows), _p(poses_bt7), C.c_int64(rows), tokens_per_view, C.c_float(mult), _p(pos), _p(ori), _stream()))
+    return pos, ori
+
+
+def row_mean(x_rows, start=0):
+    """x [rows, n] -> [rows] mean over columns start..n-1."""
+    lib = load(True)
+    _dev(x_rows, torch.float32)
+    rows, n = x_rows.shape
+    out = torch.empty((rows,), dtype=torch.float32, device=x_rows.device)
+    _check(lib.vf_row_mean(_p(x_rows), C.c_int64(rows), n, start, _p(out), _stream()))
     return out
 
 

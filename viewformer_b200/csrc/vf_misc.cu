@@ -235,6 +235,61 @@ __global__ void cameras_from_relative_kernel(const float* __restrict__ cams, con
     o[3] = q.w; o[4] = q.x; o[5] = q.y; o[6] = q.z;
 }
 
+// sparse softmax cross-entropy per row (tf.nn.sparse_softmax_cross_entropy_with_logits, models/migt.py:99-104,419-423);
+// label smoothing s: loss = (1-s) * nll + s * (lse - mean(logits)).  One warp per row.
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                                      int64_t rows, int cols, float smoothing, float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* x = logits + row * cols;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    float se = 0.f, sx = 0.f;
+    for (int c = lane; c < cols; c += 32) { se += expf(x[c] - mx); sx += x[c]; }
+    se = warp_sum(se);
+    sx = warp_sum(sx);
+    if (lane == 0) {
+        const float lse = mx + logf(se);
+        const float nll = lse - x[labels[row]];
+        out[row] = (1.0f - smoothing) * nll + smoothing * (lse - sx / (float)cols);
+    }
+}
+
+// pose regression losses per token (models/migt.py:165-171): raw [rows,7] MLP output, target pose of the token's view
+// (poses [BT,7], tokens_per_view consecutive rows share a view) scaled by [m,m,m,1,1,1,1]; pos = mean_3 (y-xyz)^2, ori = mean_4 (y-q)^2
+__global__ void pose_loss_kernel(const float* __restrict__ raw, const float* __restrict__ poses, int64_t rows, int tokens_per_view,
+                                 float mult, float* __restrict__ pos_out, float* __restrict__ ori_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float* r = raw + i * 7;
+    const float* y = poses + (i / tokens_per_view) * 7;
+    float p = 0.f, o = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const float d = y[j] * mult - r[j]; p += d * d; }
+#pragma unroll
+    for (int j = 3; j < 7; ++j) { const float d = y[j] - r[j]; o += d * d; }
+    pos_out[i] = p / 3.0f;
+    ori_out[i] = o / 4.0f;
+}
+
+// out[b] = mean(x[b, start:n])  — one block per b
+__global__ void __launch_bounds__(256) row_mean_kernel(const float* __restrict__ x, int n, int start, float* __restrict__ out) {
+    __shared__ float sh[8];
+    const float* xr = x + (int64_t)blockIdx.x * n;
+    float s = 0.f;
+    for (int i = start + threadIdx.x; i < n; i += 256) s += xr[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        out[blockIdx.x] = t / (float)(n - start);
+    }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
@@ -360,6 +415,29 @@ extern "C" int vf_cameras_from_relative(const float* cams, const float* transfor
     if (B == 0) return VF_OK;
     cameras_from_relative_kernel<<<(B * n + 127) / 128, 128, 0, vf_s(s)>>>(cams, transform, B, n, out);
     VF_CHECK_LAUNCH("vf_cameras_from_relative");
+    return VF_OK;
+}
+extern "C" int vf_cross_entropy_rows(const float* logits, const int32_t* labels, int64_t rows, int cols, float smoothing, float* out,
+                                     vf_stream_t s) {
+    VF_CHECK_ARG(logits && labels && out && cols > 0, "vf_cross_entropy_rows: bad args");
+    if (rows == 0) return VF_OK;
+    ce_rows_kernel<<<nblk(rows, 8), 256, 0, vf_s(s)>>>(logits, labels, rows, cols, smoothing, out);
+    VF_CHECK_LAUNCH("vf_cross_entropy_rows");
+    return VF_OK;
+}
+extern "C" int vf_pose_loss_rows(const float* raw, const float* poses, int64_t rows, int tokens_per_view, float pose_multiplier,
+                                 float* pos_out, float* ori_out, vf_stream_t s) {
+    VF_CHECK_ARG(raw && poses && pos_out && ori_out && tokens_per_view > 0, "vf_pose_loss_rows: bad args");
+    if (rows == 0) return VF_OK;
+    pose_loss_kernel<<<nblk(rows, 256), 256, 0, vf_s(s)>>>(raw, poses, rows, tokens_per_view, pose_multiplier, pos_out, ori_out);
+    VF_CHECK_LAUNCH("vf_pose_loss_rows");
+    return VF_OK;
+}
+extern "C" int vf_row_mean(const float* x, int64_t rows, int n, int start, float* out, vf_stream_t s) {
+    VF_CHECK_ARG(x && out && n > start && start >= 0, "vf_row_mean: bad args");
+    if (rows == 0) return VF_OK;
+    row_mean_kernel<<<(unsigned)rows, 256, 0, vf_s(s)>>>(x, n, start, out);
+    VF_CHECK_LAUNCH("vf_row_mean");
     return VF_OK;
 }
 extern "C" int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s) {

@@ -87,87 +87,99 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a,
     *reinterpret_cast<uint2*>(p) = u;
 }
 
-// per-element body: normalise / swish / layout-store one channel quad
+// 128-bit (fp32) / 64-bit (bf16) channel-quad loads
+template <typename InT>
+__device__ __forceinline__ float4 load4(const InT* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+
 template <typename OutT>
-__device__ __forceinline__ void gn_apply_one(float4 v, int64_t i, int cq, unsigned pix, const float* __restrict__ mr,
-                                             const float* __restrict__ gamma, const float* __restrict__ beta, int H, int W, int C,
-                                             int groups, int normalize, int swish, int up, OutT* __restrict__ y) {
-    // pix = n*H*W + y*W + x (32-bit: 64-bit integer division costs more than the memory traffic of this kernel)
+__device__ __forceinline__ float gn_swish(float v) {
+    // bf16 operand output: ex2.approx / rcp.approx (rel. error ~1e-6, far below bf16 rounding) keep this kernel
+    // memory-bound; the fp32 (exact-path) instantiation uses expf and a true division
+    if constexpr (sizeof(OutT) == 2) return __fdividef(v, 1.0f + __expf(-v));
+    else return vf_swish(v);
+}
+
+// Apply: grid (pixel chunks, N).  A thread owns ONE channel quad of ONE image for its whole life, so the affine
+// (x - mean) * rstd * gamma + beta is folded once into (scale, shift) registers — the bf16 instantiation evaluates it as
+// one FMA per element; the exact fp32 instantiation keeps the reference's operation order — and the streaming loop is
+// load -> fma -> swish -> store with four independent 128-bit loads in flight and no integer division.
+// layout: 0 same, 1 nearest-neighbour x2 upsample, 2 space-to-depth ([N,H,W,C] -> [N,H/2,W/2,4C], block a*2+b <- (2y+a, 2x+b))
+template <typename InT, typename OutT, int kLayout>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const InT* __restrict__ x, const float* __restrict__ mr,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int H, int W,
+                                                       int C, int groups, int normalize, int swish, int pix_per_block,
+                                                       OutT* __restrict__ y) {
+    const int quads = C >> 2;                               // 256 % quads == 0 (checked by the launcher)
+    const int lanes = 256 / quads;
+    const int cq = threadIdx.x % quads, pl = threadIdx.x / quads;
+    const int n = blockIdx.y, HW = H * W;
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
     if (normalize) {
-        const int n = (int)(pix / (unsigned)(H * W));
         const int cpg = C / groups;
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
-        const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
-        float mu[4], rs[4];
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+        ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w;
+        be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j > 0 && (cpg & 3) == 0) { mu[j] = mu[0]; rs[j] = rs[0]; continue; }
-            const int g = (cq * 4 + j) / cpg;
-            const float2 m = __ldg(reinterpret_cast<const float2*>(mr) + (int64_t)n * groups + g);
+            const float2 m = __ldg(reinterpret_cast<const float2*>(mr) + (int64_t)n * groups + (cq * 4 + j) / cpg);
             mu[j] = m.x;
             rs[j] = m.y;
         }
-        v.x = (v.x - mu[0]) * rs[0] * ga.x + be.x;
-        v.y = (v.y - mu[1]) * rs[1] * ga.y + be.y;
-        v.z = (v.z - mu[2]) * rs[2] * ga.z + be.z;
-        v.w = (v.w - mu[3]) * rs[3] * ga.w + be.w;
     }
-    if (swish) {
-        if constexpr (sizeof(OutT) == 2) {
-            // bf16 operand output: ex2.approx / rcp.approx (rel. error ~1e-6, far below bf16 rounding) keep this kernel
-            // memory-bound; the fp32 (exact-path) instantiation uses expf and a true division
-            v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
-            v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
-        } else {
-            v.x = vf_swish(v.x); v.y = vf_swish(v.y); v.z = vf_swish(v.z); v.w = vf_swish(v.w);
-        }
-    }
-    if (up == 0) {
-        store4<OutT>(y + i * 4, v.x, v.y, v.z, v.w);
-    } else if (up == 2) {          // space-to-depth: [N,H,W,C] -> [N,H/2,W/2,4C], block (a*2+b) <- pixel (2y+a, 2x+b)
-        const int xx = (int)(pix % (unsigned)W);
-        const unsigned t = pix / (unsigned)W;
-        const int yy = (int)(t % (unsigned)H);
-        const int64_t n = t / (unsigned)H;
-        const int64_t o = (((n * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1)) * 4 + ((yy & 1) * 2 + (xx & 1))) * C + cq * 4;
-        store4<OutT>(y + o, v.x, v.y, v.z, v.w);
-    } else {
-        const int xx = (int)(pix % (unsigned)W);
-        const unsigned t = pix / (unsigned)W;
-        const int yy = (int)(t % (unsigned)H);
-        const int64_t n = t / (unsigned)H;
-        const int64_t W2 = 2 * (int64_t)W;
-        const int64_t o = ((n * 2 * H + 2 * yy) * W2 + 2 * xx) * C + cq * 4;
-        store4<OutT>(y + o, v.x, v.y, v.z, v.w);
-        store4<OutT>(y + o + C, v.x, v.y, v.z, v.w);
-        store4<OutT>(y + o + W2 * C, v.x, v.y, v.z, v.w);
-        store4<OutT>(y + o + W2 * C + C, v.x, v.y, v.z, v.w);
-    }
-}
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sc[j] = rs[j] * ga[j]; sh[j] = be[j] - mu[j] * sc[j]; }
 
-// 4 channel quads per thread, all four 128-bit loads issued before any use (64 B in flight per thread)
-template <typename OutT>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       int N, int H, int W, int C, int groups, float eps, int normalize,
-                                                       int swish, int up, OutT* __restrict__ y) {
-    const int quads = C >> 2;                               // 256 % quads == 0 (checked by the launcher)
-    const int64_t total = (int64_t)N * H * W * quads;
-    const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-    const int cq = threadIdx.x % quads;                      // constant across the 4 items: their stride (256) is a multiple of quads
-    const unsigned ppi = 256 / quads;                        // pixels advanced per item
-    const unsigned pix0 = blockIdx.x * (4 * ppi) + threadIdx.x / quads;
-    float4 v[4];
+    auto body = [&](float4 v, int p) {
+        float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int64_t i = base + k * 256;
-        v[k] = __ldg(reinterpret_cast<const float4*>(x) + (i < total ? i : total - 1));     // unconditional: keeps 4 loads in flight
-    }
+        for (int j = 0; j < 4; ++j) {
+            if (normalize) {
+                if constexpr (sizeof(OutT) == 2) e[j] = fmaf(e[j], sc[j], sh[j]);
+                else e[j] = (e[j] - mu[j]) * rs[j] * ga[j] + be[j];
+            }
+            if (swish) e[j] = gn_swish<OutT>(e[j]);
+        }
+        if constexpr (kLayout == 0) {
+            store4<OutT>(y + ((int64_t)n * HW + p) * C + cq * 4, e[0], e[1], e[2], e[3]);
+        } else if constexpr (kLayout == 2) {
+            const int yy = p / W, xx = p - yy * W;
+            const int64_t o = ((((int64_t)n * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1)) * 4 + ((yy & 1) * 2 + (xx & 1))) * C + cq * 4;
+            store4<OutT>(y + o, e[0], e[1], e[2], e[3]);
+        } else {
+            const int yy = p / W, xx = p - yy * W;
+            const int64_t W2 = 2 * (int64_t)W;
+            const int64_t o = (((int64_t)n * 2 * H + 2 * yy) * W2 + 2 * xx) * C + cq * 4;
+            store4<OutT>(y + o, e[0], e[1], e[2], e[3]);
+            store4<OutT>(y + o + C, e[0], e[1], e[2], e[3]);
+            store4<OutT>(y + o + W2 * C, e[0], e[1], e[2], e[3]);
+            store4<OutT>(y + o + W2 * C + C, e[0], e[1], e[2], e[3]);
+        }
+    };
+
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    const InT* base = x + (int64_t)n * HW * C + cq * 4;
+    int p = p0 + pl;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+        float4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int64_t i = base + k * 256;
-        if (i < total) gn_apply_one<OutT>(v[k], i, cq, pix0 + k * ppi, mr, gamma, beta, H, W, C, groups, normalize, swish, up, y);
+        for (int k = 0; k < 4; ++k) v[k] = load4<InT>(base + (int64_t)(p + k * lanes) * C);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) body(v[k], p + k * lanes);
     }
+    for (; p < p1; p += lanes) body(load4<InT>(base + (int64_t)p * C), p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,27 +261,47 @@ extern "C" int vf_groupnorm_finalize(const double* sums, int n_stats, double cou
     return VF_OK;
 }
 
-extern "C" int vf_groupnorm_apply(const float* x, const float* stats, const float* gamma, const float* beta, int N,
-                                  int H, int W, int C, int groups, float eps, int normalize, int swish, int upsample2x,
+template <typename InT, typename OutT>
+static void gn_apply_launch(const void* x, const float* stats, const float* gamma, const float* beta, int N, int H, int W, int C,
+                            int groups, int normalize, int swish, int layout, void* y, cudaStream_t st) {
+    const int HW = H * W;
+    const int lanes = 256 / (C / 4);
+    // 16 pixel rounds per thread (4 x 4 loads in flight) unless that leaves the machine short of blocks
+    int ppb = lanes * 16;
+    while (ppb > lanes * 4 && (int64_t)((HW + ppb - 1) / ppb) * N < 148 * 8) ppb >>= 1;
+    dim3 grid((HW + ppb - 1) / ppb, N);
+    const InT* xi = reinterpret_cast<const InT*>(x);
+    OutT* yo = reinterpret_cast<OutT*>(y);
+    if (layout == 0)
+        gn_apply_kernel<InT, OutT, 0><<<grid, 256, 0, st>>>(xi, stats, gamma, beta, H, W, C, groups, normalize, swish, ppb, yo);
+    else if (layout == 1)
+        gn_apply_kernel<InT, OutT, 1><<<grid, 256, 0, st>>>(xi, stats, gamma, beta, H, W, C, groups, normalize, swish, ppb, yo);
+    else
+        gn_apply_kernel<InT, OutT, 2><<<grid, 256, 0, st>>>(xi, stats, gamma, beta, H, W, C, groups, normalize, swish, ppb, yo);
+}
+
+extern "C" int vf_groupnorm_apply(const void* x, int x_dtype, const float* stats, const float* gamma, const float* beta, int N,
+                                  int H, int W, int C, int groups, float eps, int normalize, int swish, int layout,
                                   void* y, int y_dtype, vf_stream_t s) {
+    (void)eps;
     VF_CHECK_ARG(x && y, "vf_groupnorm_apply: null pointer");
     VF_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "vf_groupnorm_apply: unsupported C=%d", C);
-    VF_CHECK_ARG((int64_t)N * H * W < (1ll << 32), "vf_groupnorm_apply: too many pixels");
-    VF_CHECK_ARG(upsample2x != 2 || (H % 2 == 0 && W % 2 == 0), "vf_groupnorm_apply: space-to-depth needs even H, W");
+    VF_CHECK_ARG((int64_t)H * W < (1ll << 30) && N <= 65535, "vf_groupnorm_apply: image too large");
+    VF_CHECK_ARG(layout >= 0 && layout <= 2, "vf_groupnorm_apply: bad layout %d", layout);
+    VF_CHECK_ARG(layout != 2 || (H % 2 == 0 && W % 2 == 0), "vf_groupnorm_apply: space-to-depth needs even H, W");
     if (normalize) {
         VF_CHECK_ARG(stats && gamma && beta, "vf_groupnorm_apply: normalize needs stats/gamma/beta");
         VF_CHECK_ARG(C % groups == 0, "vf_groupnorm_apply: unsupported C=%d groups=%d", C, groups);
     }
-    const int64_t total = (int64_t)N * H * W * (C / 4);
-    const unsigned blocks = (unsigned)((total + 1023) / 1024);
-    if (y_dtype == VF_F32)
-        gn_apply_kernel<float><<<blocks, 256, 0, vf_s(s)>>>(x, stats, gamma, beta, N, H, W, C, groups, eps, normalize, swish,
-                                                            upsample2x, reinterpret_cast<float*>(y));
-    else if (y_dtype == VF_BF16)
-        gn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, vf_s(s)>>>(x, stats, gamma, beta, N, H, W, C, groups, eps, normalize,
-                                                                    swish, upsample2x, reinterpret_cast<__nv_bfloat16*>(y));
+    if (N == 0 || H * W == 0) return VF_OK;
+    if (x_dtype == VF_F32 && y_dtype == VF_F32)
+        gn_apply_launch<float, float>(x, stats, gamma, beta, N, H, W, C, groups, normalize, swish, layout, y, vf_s(s));
+    else if (x_dtype == VF_F32 && y_dtype == VF_BF16)
+        gn_apply_launch<float, __nv_bfloat16>(x, stats, gamma, beta, N, H, W, C, groups, normalize, swish, layout, y, vf_s(s));
+    else if (x_dtype == VF_BF16 && y_dtype == VF_BF16)
+        gn_apply_launch<__nv_bfloat16, __nv_bfloat16>(x, stats, gamma, beta, N, H, W, C, groups, normalize, swish, layout, y, vf_s(s));
     else
-        VF_CHECK_ARG(false, "vf_groupnorm_apply: bad dtype");
+        VF_CHECK_ARG(false, "vf_groupnorm_apply: unsupported dtype pair (x %d, y %d)", x_dtype, y_dtype);
     VF_CHECK_LAUNCH("vf_groupnorm_apply");
     return VF_OK;
 }

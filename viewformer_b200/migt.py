@@ -252,18 +252,31 @@ class MIGT:
                 b_bs=(0, 0), c_bs=(Lt * lm.n, 0), a_off=(T - 1) * Lt * d)
         return logits
 
-    def _pose_head(self, h_rows_f32):
+    def _pose_head(self, h_rows_f32, return_raw=False):
         """QuaternionPoseRepresentation.call without targets (migt.py:156-164), fp32."""
         hn = L.layernorm(h_rows_f32, *self._w["lnf"], out_dtype=torch.float32, eps=LN_EPS)
         raw = linear(self.exact, linear(self.exact, hn, self._w["pc_fc"], torch.float32, act=L.ACT_GELU), self._w["pc_proj"], torch.float32)
-        return L.pose_postprocess(raw, self.config.pose_multiplier)
+        pred = L.pose_postprocess(raw, self.config.pose_multiplier)
+        return (pred, raw) if return_raw else pred
+
+    def _localization_weight(self, step=0):
+        """Schedule('...')(step) of migt.py:268,452 for the constant / piecewise-constant forms the released configs use."""
+        lw = str(self.config.localization_weight)
+        try:
+            return float(lw)
+        except ValueError:
+            raise NotImplementedError(f"localization_weight schedule '{lw}' is not a constant; pass a numeric weight for loss evaluation")
 
     # ------------------------------------------------------------------ reference call surface
     def __call__(self, inputs, training=False, compute_losses=False, last_only=False, **kwargs):
         """MIGT.call (migt.py:338-455), inference semantics (training=False; dropout inactive).
         ``last_only=True`` computes logits for the last view only (what evaluate_transformer.py:123 consumes)."""
-        if training or compute_losses:
-            raise NotImplementedError("MIGT training / loss computation is not part of this round; see DESIGN.md")
+        if training:
+            raise NotImplementedError("MIGT training (dropout + backward) is not part of this round; see DESIGN.md")
+        if compute_losses and last_only:
+            raise ValueError("compute_losses needs the logits of every view (last_only=False)")
+        if compute_losses and self.config.use_dynamic_pose_loss:
+            raise NotImplementedError("use_dynamic_pose_loss carries trained weights (migt.py:107-120); not part of this round")
         if self._w is None:
             raise RuntimeError("MIGT has no weights: call load_state_dict() first")
         cfg = self.config
@@ -280,6 +293,13 @@ class MIGT:
         Tp = poses.shape[1]
         out_poses = inputs.get("output_poses")
         loc_tokens = inputs.get("localization_tokens")
+        if compute_losses:                                       # migt.py:364-373: teacher-forced evaluation streams
+            if Tp != T:
+                raise AssertionError("compute_losses needs one pose per view")
+            if loc_tokens is None and self.use_localization:
+                loc_tokens = ids
+            if out_poses is None:
+                out_poses = poses
         wte = self._w["wte"]
 
         pose_rows = torch.empty((B, T, d), dtype=torch.float32, device=self.device)
@@ -310,9 +330,27 @@ class MIGT:
             out["logits"] = self._lm_logits_last(xs[gen_ptr], B, T).reshape(B, 1, *orig_shape[2:], cfg.n_embeddings)
         else:
             out["logits"] = self._lm_logits(xs[gen_ptr]).reshape(orig_shape + [cfg.n_embeddings])
+        loss = 0
+        skip = cfg.n_loss_skip
+        if compute_losses:                                       # migt.py:417-423
+            ce_rows = L.cross_entropy_rows(out["logits"].reshape(B * T * Lt, cfg.n_embeddings), ids.reshape(-1),
+                                           float(cfg.label_smoothing))
+            out["ce_loss"] = L.row_mean(ce_rows.reshape(B, T * Lt), skip * Lt)
+            loss = out["ce_loss"] * float(cfg.image_generation_weight)
         if self.use_localization:
-            out["pose_prediction"] = self._pose_head(xs[pose_ptr]).reshape(B, T, Lt, 7)
-        out["loss"] = 0
+            if compute_losses:                                   # migt.py:425-448, 165-177
+                pred, raw = self._pose_head(xs[pose_ptr], return_raw=True)
+                pl_rows, ol_rows = L.pose_loss_rows(raw, poses.reshape(B * T, 7).contiguous(), Lt, float(cfg.pose_multiplier))
+                pl = L.row_mean(pl_rows.reshape(B, T * Lt), skip * Lt)
+                ol = L.row_mean(ol_rows.reshape(B, T * Lt), skip * Lt)
+                w = self._localization_weight()
+                out["pose_pos_loss"], out["pose_ori_loss"], out["pose_loss"] = pl, ol, pl + ol
+                out["localization_weight"] = w
+                loss = loss + (pl + ol) * w
+            else:
+                pred = self._pose_head(xs[pose_ptr])
+            out["pose_prediction"] = pred.reshape(B, T, Lt, 7)
+        out["loss"] = loss
         return out
 
     def reduce_cameras(self, cameras, axis=-2):

@@ -50,6 +50,7 @@ class VQGAN:
             config = VQGANConfig(**config_overrides)
         self.config = load_config(config)
         self.prec = Precision(precision)
+        self.bf16_edges = precision == "bf16"      # conv1 -> norm2 activations travel as bf16 (see _resblock)
         self.exact = Precision("fp32")
         self.device = torch.device(device)
         self.training = False
@@ -267,13 +268,15 @@ class VQGAN:
         self._w["pq_table"] = linear(self.exact, q["et"], self._w["post_quant_conv"], torch.float32)
 
     # ------------------------------------------------------------------ building blocks (NHWC f32 in / out)
-    def _conv(self, cw, x_opd_or_f32, *, residual=None, stride=1, upsample=False, stats=True):
-        """``stats``: the output feeds a GroupNorm(32) — let the tcgen05 epilogue accumulate its statistics."""
+    def _conv(self, cw, x_opd_or_f32, *, residual=None, stride=1, upsample=False, stats=True, out_dtype=torch.float32):
+        """``stats``: the output feeds a GroupNorm(32) — let the tcgen05 epilogue accumulate its statistics.
+        ``out_dtype`` bf16 is only honoured on the tensor-core path (callers check ``cw.tc``)."""
         gn = 32 if stats else 0
         if cw.tc and stride == 2:    # operand is the space-to-depth tensor [N,H/2,W/2,4C]: stride-1 tap-table conv
             return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, taps=L.TAPS_S2D, coffs=L.s2d_coffs(cw.cin), cin=cw.cin, gn_groups=gn)
         if cw.tc:
-            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, residual=residual, gn_groups=gn)
+            return L.tc_conv(x_opd_or_f32, cw.w_nk, cw.bias, residual=residual, gn_groups=gn, out_dtype=out_dtype)
+        assert out_dtype == torch.float32
         if stride == 1 and not upsample and residual is None and x_opd_or_f32.dtype == torch.float32:
             if cw.small_cin:
                 return L.conv3x3_small_cin(x_opd_or_f32, cw.w_kn, cw.bias)
@@ -288,7 +291,13 @@ class VQGAN:
 
     def _resblock(self, rbw, x):
         a = L.groupnorm(x, *rbw["n1"], swish=True, out_dtype=self._act_dtype(rbw["c1"]))
-        h = self._conv(rbw["c1"], a)
+        # conv1's output is consumed by norm2 alone (the block's residual is x): in bf16 mode it travels as bf16 with the
+        # GroupNorm statistics taken from the fp32 accumulators in the conv epilogue — 4 B/element less HBM traffic
+        n_, h_, w_, _ = x.shape
+        c1 = rbw["c1"]
+        edge = torch.bfloat16 if (self.bf16_edges and c1.tc and rbw["c2"].tc
+                                  and L.gn_fusable(c1.cout, 32, n_ * h_ * w_, h_ * w_, c1.cout)) else torch.float32
+        h = self._conv(c1, a, out_dtype=edge)
         a = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"]))
         if "sc" in rbw:
             n, hh, ww, c = x.shape
