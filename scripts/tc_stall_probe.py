@@ -17,6 +17,9 @@ def run(name, fn):
     pw = 100 * (prod[:, 5] / prod[:, 4])
     print(f"    producers: {prod.shape[0]} CTAs, waiting on empty barriers {pw.mean().item():5.1f}% of their time (min {pw.min().item():.1f} max {pw.max().item():.1f})")
     print(f"{name:40s} issuers {t.shape[0]:3d} tiles/issuer {tiles:6.1f} | cycles/tile {tot/tiles:8.0f} | wait operands {100*ops/tot:5.1f}% | wait tmem_empty {100*tm/tot:5.1f}% | issuing {100*(tot-ops-tm)/tot:5.1f}%")
+flags = int(os.environ.get("VF_TC_DBG_FLAGS", "0"))
+lib.vf_tc_debug_flags(flags)
+print(f"debug flags = {flags} (1 no epilogue, 2 no B loads, 4 no A loads)")
 n, hw, c = 288, 128, 128
 x = torch.randn((n, hw, hw, c), device="cuda").bfloat16(); w = (torch.randn((c, 9 * c), device="cuda") / 30).bfloat16()
 b = torch.zeros(c, device="cuda"); res = torch.randn((n, hw, hw, c), device="cuda"); out = torch.empty((n, hw, hw, c), device="cuda")

@@ -10,7 +10,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvf_b200.so")
+LIB_PATH = os.environ.get("VF_B200_LIB") or os.path.join(HERE, "libvf_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1

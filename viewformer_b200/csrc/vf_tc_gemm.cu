@@ -51,6 +51,7 @@ struct TcParams {
                                // as row-shifted UMMA descriptors into it (9x fewer A bytes from L2); 0 = one shifted TMA box per tap
     double* gn_sums;           // optional fused GroupNorm statistics of the OUTPUT: [images][groups][2] (sum, sum of squares)
     int gn_groups, gn_cpg, gn_rows_per_img;
+    int dbg_flags;             // profiling builds only: 1 = no epilogue work, 2 = no B loads, 4 = no A loads (stale smem is consumed)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -67,6 +68,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// elect.sync: exactly one lane of a converged warp gets `true`; unlike `lane == 0` the compiler KNOWS a single thread is active in
+// the guarded region, so tcgen05.mma / TMA operands move to uniform registers with a plain R2UR instead of an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop around every instruction
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// non-blocking poll (never suspends the thread): used to look at the NEXT stage's barrier before this stage's MMAs are issued
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             int ab = 0;
@@ -363,16 +384,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     const uint32_t halo_bytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * ROW_BYTES;
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
                         mbar_wait(&a_empty_bar[ab], aphase ^ 1);
+#ifdef VF_TC_STALL_COUNTERS
+                        if (p.dbg_flags & 4) { mbar_arrive(&a_full_bar[ab]); } else
+#endif
+                        {
                         arm_full(&a_full_bar[ab], halo_bytes);
                         load(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
+                        }
                         if (++ab == 2) { ab = 0; aphase ^= 1; }
                         for (int tap = 0; tap < 9; ++tap) {
                             if (pdbg) pc0 = clock64();
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (pdbg) pc_wait += clock64() - pc0;
+#ifdef VF_TC_STALL_COUNTERS
+                            if (p.dbg_flags & 2) { mbar_arrive(&full_bar[stage]); } else
+#endif
+                            {
                             arm_full(&full_bar[stage], B_STAGE_BYTES);
                             load(halo_b_base + stage * B_STAGE_BYTES, &p.tmB, &full_bar[stage], (tap * p.cin_blocks + cb) * p.bk_elems,
                                  ti.n0 + n_off, 0, 0);
+                            }
                             if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -384,6 +415,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     if (pdbg) pc_wait += clock64() - pc0;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
+#ifdef VF_TC_STALL_COUNTERS
+                    if ((p.dbg_flags & 6) == 6) { mbar_arrive(&full_bar[stage]); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
+#endif
                     arm_full(&full_bar[stage], STAGE_BYTES);
                     if (p.conv) {
                         const int tap = kb / p.cin_blocks;
@@ -404,12 +438,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (2-CTA: the leader CTA issues for the pair) =====================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             int ab_m = 0;
             uint32_t aphase_m = 0;
+            // A barrier poll issued right after tcgen05.mma instructions only returns once those MMAs have drained into the tensor
+            // pipe (measured: scripts/mma_rate_probe.cu, ~220 cycles per k-block with 128-wide tiles), so the full barrier of
+            // the NEXT ring slot is polled BEFORE this slot's MMAs are issued and the blocking wait is only the fallback.
+            bool ready = false;
             long long c_ops = 0, c_tmem = 0, c_tiles = 0, c0 = 0;       // stall counters, only maintained when p.dbg != null
 #ifdef VF_TC_STALL_COUNTERS
             const bool dbg = p.dbg != nullptr;
@@ -440,8 +478,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                         const uint32_t a_base = smem_u32(smem + ab_m * HALO_BUF_BYTES);
                         for (int tap = 0; tap < 9; ++tap) {
                             if (dbg) c0 = clock64();
-                            mbar_wait(&full_bar[stage], phase);
+                            if (!ready) mbar_wait(&full_bar[stage], phase);
                             if (dbg) c_ops += clock64() - c0;
+                            {
+                                const int ns = (stage + 1 == HALO_B_STAGES) ? 0 : stage + 1;
+                                ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
+                            }
                             tcgen05_fence_after();
                             const uint32_t a_addr = a_base + ((uint32_t)(tap / 3) * pitch + (uint32_t)(tap % 3)) * ROW_BYTES;
                             uint64_t adesc = make_sw128_desc(a_addr);
@@ -463,8 +505,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                 }
                 for (int kb = 0; kb < ti.nkb; ++kb) {
                     if (dbg) c0 = clock64();
-                    mbar_wait(&full_bar[stage], phase);
+                    if (!ready) mbar_wait(&full_bar[stage], phase);
                     if (dbg) c_ops += clock64() - c0;
+                    {
+                        const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
+                        ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
+                    }
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
@@ -518,6 +564,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                 my_ok = gm < p.M;
                 my_off = (long long)ti.b1 * p.c_sb1 + (long long)ti.b2 * p.c_sb2 + (long long)gm * p.ldc;
             }
+#ifdef VF_TC_STALL_COUNTERS
+            if (p.dbg_flags & 1) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                continue;
+            }
+#endif
             const float bias_m = (p.bias_mode == VF_BIAS_M && my_ok) ? __ldg(p.bias + gm) : 0.f;
 
             // phase-2 geometry: VPR float4 vectors span one tile row; a warp covers RPI rows per iteration
@@ -744,6 +800,8 @@ int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
 }  // namespace
 
 static long long* g_tc_dbg = nullptr;
+static int g_tc_dbg_flags = 0;
+extern "C" void vf_tc_debug_flags(int f) { g_tc_dbg_flags = f; }
 // profiling aid (scripts/tc_stall_probe.py), not in the public header: MMA-issuer stall counters of the following launches ([grid][4] int64)
 extern "C" void vf_tc_debug_counters(long long* buf) { g_tc_dbg = buf; }
 
@@ -772,6 +830,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     prm.causal_block = q->causal_block;
     prm.causal_skip_n = q->causal_skip_n;
     prm.dbg = g_tc_dbg;
+    prm.dbg_flags = g_tc_dbg_flags;
 
     // N tile: 128 when the problem is wide enough, else 64 (fewer wasted MMA columns / TMEM)
     const int block_n = (q->Ncols > 64) ? 128 : 64;
