@@ -36,6 +36,12 @@ struct AttnParams {
     unsigned idesc_s, idesc_o;
 };
 
+// one elected lane; the compiler knows a single thread is active in the guarded region (plain R2UR for tcgen05 / TMA operands)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, Q_BYTES);
             tma_load_4d(sQ, &p.tmQ, q_full, 0, q0, h, b);
             int ks = 0, vs = 0;
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_wait(q_full, 0);
             tc_fence_after();
             const uint64_t qdesc = sw128_desc(smem_u32(sQ));

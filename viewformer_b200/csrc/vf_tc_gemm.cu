@@ -252,6 +252,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int KGROUP = 1;          // k-blocks per producer/consumer hand-shake (2 measured no faster: the ring gets too coarse)
+constexpr int HALO_BYTES = 23552;  // one (16+2) x (8+2) halo tile of 128-byte rows, rounded up to 1024
+constexpr int HALO_SLOTS = 6;      // weight-tile slots of the halo-mode ring
+__host__ __device__ constexpr int operand_bytes(int stages, int stage_bytes, int b_stage_bytes) {
+    return stages * stage_bytes > 2 * HALO_BYTES + HALO_SLOTS * b_stage_bytes ? stages * stage_bytes
+                                                                               : 2 * HALO_BYTES + HALO_SLOTS * b_stage_bytes;
+}
+
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 //   warp 0      TMA producer   — smem ring runs continuously across tiles
 //   warp 1      MMA issuer     — accumulates tile i into TMEM stage (i & 1) while the epilogue drains stage (i-1) & 1
@@ -278,19 +286,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     // 1024B alignment required by the 128B swizzle atoms (descriptor base_offset = 0)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* staging = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
+    constexpr int OPER_BYTES = operand_bytes(kStages, STAGE_BYTES, B_STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(smem + OPER_BYTES);
     constexpr int MAX_STAGES = 8;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + STG_BYTES);   // [MAX_STAGES]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OPER_BYTES + STG_BYTES);   // [MAX_STAGES], one per k-block GROUP
     uint64_t* empty_bar = full_bar + MAX_STAGES;        // [MAX_STAGES]
     uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
     uint64_t* a_full_bar = tmem_empty_bar + 2;          // [2]  halo mode: A halo tiles
     uint64_t* a_empty_bar = a_full_bar + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 2);
-    // halo mode carves the same operand region differently: 2 halo buffers, then a ring of B-only stages
-    constexpr int HALO_BUF_BYTES = 23552;               // >= 18*10 rows x 128 B, multiple of 1024
-    constexpr int HALO_B_STAGES = (kStages * STAGE_BYTES - 2 * HALO_BUF_BYTES) / B_STAGE_BYTES > MAX_STAGES
-                                      ? MAX_STAGES : (kStages * STAGE_BYTES - 2 * HALO_BUF_BYTES) / B_STAGE_BYTES;
+    // Hand-shake granularity: KGROUP k-blocks share one full / one empty barrier (the issuer polls the NEXT group's barrier
+    // before issuing this group's MMAs; see scripts/mma_rate_probe.cu for what a poll behind queued MMAs costs).
+    constexpr int NG = kStages / KGROUP;                // ring depth in groups (normal mode)
+    // halo mode carves the same operand region differently: 2 halo buffers, then a ring of B-only slots
+    constexpr int HALO_BUF_BYTES = HALO_BYTES;          // >= 18*10 rows x 128 B, multiple of 1024
+    constexpr int NGH = HALO_SLOTS / KGROUP;            // ring depth in groups (halo mode)
     uint8_t* halo_b_base = smem + 2 * HALO_BUF_BYTES;
 
     const int warp = threadIdx.x >> 5;
@@ -382,53 +393,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                 if (ti.skip) continue;
                 if (p.halo) {
                     const uint32_t halo_bytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * ROW_BYTES;
-                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                        mbar_wait(&a_empty_bar[ab], aphase ^ 1);
+                    const int nkb = 9 * p.cin_blocks;
+                    int tap = 0, cb = 0;
+                    for (int kb = 0; kb < nkb; kb += KGROUP) {
+                        const int n = (nkb - kb < KGROUP) ? nkb - kb : KGROUP;
+                        if (pdbg) pc0 = clock64();
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (pdbg) pc_wait += clock64() - pc0;
+                        bool b_loads = true, a_loads = true;
 #ifdef VF_TC_STALL_COUNTERS
-                        if (p.dbg_flags & 4) { mbar_arrive(&a_full_bar[ab]); } else
+                        b_loads = !(p.dbg_flags & 2);
+                        a_loads = !(p.dbg_flags & 4);
 #endif
-                        {
-                        arm_full(&a_full_bar[ab], halo_bytes);
-                        load(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
-                        }
-                        if (++ab == 2) { ab = 0; aphase ^= 1; }
-                        for (int tap = 0; tap < 9; ++tap) {
-                            if (pdbg) pc0 = clock64();
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            if (pdbg) pc_wait += clock64() - pc0;
-#ifdef VF_TC_STALL_COUNTERS
-                            if (p.dbg_flags & 2) { mbar_arrive(&full_bar[stage]); } else
-#endif
-                            {
-                            arm_full(&full_bar[stage], B_STAGE_BYTES);
-                            load(halo_b_base + stage * B_STAGE_BYTES, &p.tmB, &full_bar[stage], (tap * p.cin_blocks + cb) * p.bk_elems,
-                                 ti.n0 + n_off, 0, 0);
+                        if (b_loads) arm_full(&full_bar[stage], (uint32_t)n * B_STAGE_BYTES);
+                        else mbar_arrive(&full_bar[stage]);
+                        for (int g = 0; g < n; ++g) {
+                            if (tap == 0) {      // first tap of a channel block: its halo tile
+                                mbar_wait(&a_empty_bar[ab], aphase ^ 1);
+                                if (a_loads) {
+                                    arm_full(&a_full_bar[ab], halo_bytes);
+                                    load(smem + ab * HALO_BUF_BYTES, &p.tmA, &a_full_bar[ab], cb * p.bk_elems, ti.ox0 - 1, ti.oy0 - 1, ti.img0);
+                                } else {
+                                    mbar_arrive(&a_full_bar[ab]);
+                                }
+                                if (++ab == 2) { ab = 0; aphase ^= 1; }
                             }
-                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                            if (b_loads)
+                                load(halo_b_base + (stage * KGROUP + g) * B_STAGE_BYTES, &p.tmB, &full_bar[stage],
+                                     (tap * p.cin_blocks + cb) * p.bk_elems, ti.n0 + n_off, 0, 0);
+                            if (++tap == 9) { tap = 0; ++cb; }
                         }
+                        if (++stage == NGH) { stage = 0; phase ^= 1; }
                     }
                     continue;
                 }
-                for (int kb = 0; kb < ti.nkb; ++kb) {
+                for (int kb0 = 0; kb0 < ti.nkb; kb0 += KGROUP) {
+                    const int n = (ti.nkb - kb0 < KGROUP) ? ti.nkb - kb0 : KGROUP;
                     if (pdbg) pc0 = clock64();
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (pdbg) pc_wait += clock64() - pc0;
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
 #ifdef VF_TC_STALL_COUNTERS
-                    if ((p.dbg_flags & 6) == 6) { mbar_arrive(&full_bar[stage]); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
+                    if ((p.dbg_flags & 6) == 6) { mbar_arrive(&full_bar[stage]); if (++stage == NG) { stage = 0; phase ^= 1; } continue; }
 #endif
-                    arm_full(&full_bar[stage], STAGE_BYTES);
-                    if (p.conv) {
-                        const int tap = kb / p.cin_blocks;
-                        const int cb = kb - tap * p.cin_blocks;
-                        load(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap], ti.oy0 + p.tap_dy[tap],
-                             ti.img0);
-                    } else {
-                        load(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
+                    arm_full(&full_bar[stage], (uint32_t)n * STAGE_BYTES);
+                    for (int g = 0; g < n; ++g) {
+                        const int kb = kb0 + g;
+                        uint8_t* sa = smem + (stage * KGROUP + g) * STAGE_BYTES;
+                        uint8_t* sb = sa + A_STAGE_BYTES;
+                        if (p.conv) {
+                            const int tap = kb / p.cin_blocks;
+                            const int cb = kb - tap * p.cin_blocks;
+                            load(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap], ti.oy0 + p.tap_dy[tap],
+                                 ti.img0);
+                        } else {
+                            load(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
+                        }
+                        load(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
                     }
-                    load(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == NG) { stage = 0; phase ^= 1; }
                 }
             }
             if (pdbg) {
@@ -471,59 +493,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     // The 128B swizzle is a pure function of the absolute smem address (probed: scripts/desc_shift_probe.cu),
                     // so row-shifted descriptors with base_offset 0 read exactly what TMA wrote.
                     const uint32_t pitch = (uint32_t)(p.TW + 2);
-                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    const int nkb = 9 * p.cin_blocks;
+                    int tap = 0;
+                    uint32_t a_base = 0;
+                    for (int kb = 0; kb < nkb; kb += KGROUP) {
+                        const int n = (nkb - kb < KGROUP) ? nkb - kb : KGROUP;
                         if (dbg) c0 = clock64();
-                        mbar_wait(&a_full_bar[ab_m], aphase_m);
+                        if (!ready) mbar_wait(&full_bar[stage], phase);
                         if (dbg) c_ops += clock64() - c0;
-                        const uint32_t a_base = smem_u32(smem + ab_m * HALO_BUF_BYTES);
-                        for (int tap = 0; tap < 9; ++tap) {
-                            if (dbg) c0 = clock64();
-                            if (!ready) mbar_wait(&full_bar[stage], phase);
-                            if (dbg) c_ops += clock64() - c0;
-                            {
-                                const int ns = (stage + 1 == HALO_B_STAGES) ? 0 : stage + 1;
-                                ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
-                            }
-                            tcgen05_fence_after();
-                            const uint32_t a_addr = a_base + ((uint32_t)(tap / 3) * pitch + (uint32_t)(tap % 3)) * ROW_BYTES;
-                            uint64_t adesc = make_sw128_desc(a_addr);
-                            adesc = (adesc & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((pitch * ROW_BYTES) >> 4) << 32);     // SBO = pitch rows
-                            const uint64_t bdesc = make_sw128_desc(smem_u32(halo_b_base + stage * B_STAGE_BYTES));
-#pragma unroll
-                            for (int k = 0; k < MMAS_PER_STAGE; ++k)
-                                mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
-                                    (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                            commit(&empty_bar[stage]);
-                            if (++stage == HALO_B_STAGES) { stage = 0; phase ^= 1; }
+                        {
+                            const int ns = (stage + 1 == NGH) ? 0 : stage + 1;
+                            ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
                         }
-                        commit(&a_empty_bar[ab_m]);              // halo buffer free once its 36 MMAs retire
-                        if (++ab_m == 2) { ab_m = 0; aphase_m ^= 1; }
+                        tcgen05_fence_after();
+#pragma unroll
+                        for (int g = 0; g < KGROUP; ++g) {
+                            if (g < n) {
+                                if (tap == 0) {
+                                    if (dbg) c0 = clock64();
+                                    mbar_wait(&a_full_bar[ab_m], aphase_m);
+                                    if (dbg) c_ops += clock64() - c0;
+                                    tcgen05_fence_after();
+                                    a_base = smem_u32(smem + ab_m * HALO_BUF_BYTES);
+                                }
+                                const uint32_t a_addr = a_base + ((uint32_t)(tap / 3) * pitch + (uint32_t)(tap % 3)) * ROW_BYTES;
+                                uint64_t adesc = make_sw128_desc(a_addr);
+                                adesc = (adesc & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((pitch * ROW_BYTES) >> 4) << 32);     // SBO = pitch rows
+                                const uint64_t bdesc = make_sw128_desc(smem_u32(halo_b_base + (stage * KGROUP + g) * B_STAGE_BYTES));
+#pragma unroll
+                                for (int k = 0; k < MMAS_PER_STAGE; ++k)
+                                    mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                        (kb + g > 0 || k > 0) ? 1u : 0u);
+                                if (++tap == 9) {
+                                    tap = 0;
+                                    commit(&a_empty_bar[ab_m]);      // halo buffer free once its 36 MMAs retire
+                                    if (++ab_m == 2) { ab_m = 0; aphase_m ^= 1; }
+                                }
+                            }
+                        }
+                        commit(&empty_bar[stage]);
+                        if (++stage == NGH) { stage = 0; phase ^= 1; }
                     }
                     commit(&tmem_full_bar[acc]);
                     ++it;
                     continue;
                 }
-                for (int kb = 0; kb < ti.nkb; ++kb) {
+                for (int kb0 = 0; kb0 < ti.nkb; kb0 += KGROUP) {
+                    const int n = (ti.nkb - kb0 < KGROUP) ? ti.nkb - kb0 : KGROUP;
                     if (dbg) c0 = clock64();
                     if (!ready) mbar_wait(&full_bar[stage], phase);
                     if (dbg) c_ops += clock64() - c0;
                     {
-                        const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
+                        const int ns = (stage + 1 == NG) ? 0 : stage + 1;
                         ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
                     }
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sb);
 #pragma unroll
-                    for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-                        // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
-                        mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
-                            (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int g = 0; g < KGROUP; ++g) {
+                        if (g < n) {
+                            const uint32_t sa = smem_u32(smem + (stage * KGROUP + g) * STAGE_BYTES);
+                            const uint32_t sb = sa + A_STAGE_BYTES;
+                            const uint64_t adesc = make_sw128_desc(sa);
+                            const uint64_t bdesc = make_sw128_desc(sb);
+#pragma unroll
+                            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                                // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
+                                mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                    (kb0 + g > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
                     }
-                    commit(&empty_bar[stage]);               // frees the smem slot (in both CTAs) once these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    commit(&empty_bar[stage]);               // frees the group's smem slots (in both CTAs) once these MMAs retire
+                    if (++stage == NG) { stage = 0; phase ^= 1; }
                 }
                 commit(&tmem_full_bar[acc]);                  // accumulator complete
                 ++it;
@@ -766,8 +807,10 @@ unsigned make_idesc(bool tf32, int M, int N) {
 template <int kBlockN, int kStages, bool kTF32, bool k2Cta>
 int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
     constexpr int b_rows = k2Cta ? kBlockN / 2 : kBlockN;
-    constexpr int smem = kStages * (A_STAGE_BYTES + b_rows * ROW_BYTES) + NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ +
-                         1024 /*align slack*/ + 256 /*barriers*/;
+    constexpr int smem = operand_bytes(kStages, A_STAGE_BYTES + b_rows * ROW_BYTES, b_rows * ROW_BYTES) +
+                         NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kStages % KGROUP == 0 && HALO_SLOTS % KGROUP == 0, "ring slots must form whole groups");
+    static_assert(smem <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32, k2Cta>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
