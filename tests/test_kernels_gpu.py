@@ -256,6 +256,34 @@ def test_tc_conv3x3(L, dtype, cin, cout, n, hw):
     report(f"tc_conv {dtype} {cin}->{cout} n{n} hw{hw}", got.permute(0, 3, 1, 2), want, 3e-3, 3e-3)
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout,res,out_bf16", [(2, 64, 64, 128, 128, True, False), (1, 40, 20, 64, 256, True, False),
+                                                          (3, 32, 8, 256, 128, False, True), (1, 128, 128, 128, 128, True, False),
+                                                          (2, 33, 9, 64, 128, False, False)])
+def test_tc_conv3x3_wide_tiles(L, n, H, W, cin, cout, res, out_bf16):
+    """maps >= 32 rows tall take the wide-tile kernel (weights on the M side, 8x32-pixel patches on the N side, direct epilogue):
+    ragged heights / widths, channel tiles, residual, bf16 output and the fused GroupNorm statistics."""
+    x = torch.randn(n, cin, H, W, generator=g(H + W)).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, generator=g(43)) / (9 * cin) ** 0.5).bfloat16()
+    b = torch.randn(cout, generator=g(44))
+    r = torch.randn(n, cout, H, W, generator=g(45)) if res else None
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if res:
+        want = want + r.double()
+    w_nk = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous().cuda()
+    fus = L.gn_fusable(cout, 32, n * H * W, H * W, cout)
+    got = L.tc_conv(x.permute(0, 2, 3, 1).contiguous().cuda(), w_nk, b.cuda(),
+                    residual=r.permute(0, 2, 3, 1).contiguous().cuda() if res else None, gn_groups=32,
+                    out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    torch.cuda.synchronize()
+    tol = 2e-2 if out_bf16 else 3e-3
+    report(f"wide conv n{n} {H}x{W} {cin}->{cout}", got.float().permute(0, 3, 1, 2), want, tol, tol)
+    if fus:
+        assert hasattr(got, "_gn_sums")
+        o = want.permute(0, 2, 3, 1).reshape(n, H * W, 32, cout // 32)
+        ws = torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1)
+        report("wide conv fused gn sums", got._gn_sums[0].cpu(), ws, 0.5, 2e-3)
+
+
 # ----------------------------------------------------------------------------- codebook
 def test_vq_lookup_bit_exact_vs_reference_golden(L, golden_dir):
     import os

@@ -752,6 +752,288 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
 }
 
+
+// ==============================================================================================================
+// Wide-tile 3x3 convolution (stride 1, pad 1): operands SWAPPED with respect to tc_gemm_kernel.
+//   A (M = 128)  = a 128-channel slice of the weights  [Cout][tap*Cin + c]      (16 KB per (tap, 64-channel block))
+//   B (N = 256)  = an 8-wide x 32-tall patch of pixels, read out of ONE (8+2) x (32+2) halo tile per 64-channel block through
+//                  row-shifted SWIZZLE_128B descriptors (SBO = 10 rows), exactly like the halo mode above
+//   D            = TMEM lane = output channel, TMEM column = pixel of the patch
+// Why: a tcgen05.mma with N <= 128 keeps the issuing thread and the shared-memory read port busier than the tensor pipe
+// (scripts/mma_rate_probe.cu: every barrier poll between 4-MMA groups costs tensor time unless the MMAs are 128 cycles long);
+// N = 256 halves the operand bytes per FLOP (12 KB per 128x256x16 MMA instead of 8 KB per 128x128x16), halves the weight-tile
+// traffic per pixel, and puts 32 consecutive channels of one pixel into the 32 lanes of a warp, so the epilogue writes
+// 128-byte rows straight from registers — no shared-memory staging at all.
+// ==============================================================================================================
+struct WideParams {
+    CUtensorMap tmX;           // activations [N, H, W, Cin] bf16: box {64, 10, 34, 1}
+    CUtensorMap tmW;           // weights [Cout, 9*Cin] bf16: box {64, 128}
+    const float* bias;         // [Cout] or null
+    const float* residual;     // [N, H, W, Cout] fp32 or null
+    float* C_f32;              // [N, H, W, Cout] or null
+    __nv_bfloat16* C_bf16;     // [N, H, W, Cout] or null
+    double* gn_sums;           // [N][groups][2] or null
+    int gn_groups, gn_cpg;
+    int N, H, W, Cout, cin_blocks;
+    int tiles_x, tiles_y, tiles_c, total_tiles;
+    unsigned idesc;
+    long long* dbg;            // profiling builds: per-CTA stall counters
+    int dbg_flags;
+};
+
+constexpr int WIDE_TW = 8, WIDE_TH = 32;
+constexpr int WIDE_HALO_ROWS = (WIDE_TW + 2) * (WIDE_TH + 2);          // 340 rows of 128 B
+constexpr int WIDE_HALO_BYTES = 44032;                                  // >= 340 * 128, multiple of 1024
+constexpr int WIDE_W_SLOTS = 8;
+constexpr int WIDE_W_BYTES = 128 * ROW_BYTES;                           // one (tap, channel block) weight tile
+constexpr int WIDE_SMEM = 2 * WIDE_HALO_BYTES + WIDE_W_SLOTS * WIDE_W_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_base = smem + 2 * WIDE_HALO_BYTES;
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(w_base + WIDE_W_SLOTS * WIDE_W_BYTES);
+    uint64_t* w_empty = w_full + WIDE_W_SLOTS;
+    uint64_t* h_full = w_empty + WIDE_W_SLOTS;          // [2]
+    uint64_t* h_empty = h_full + 2;                     // [2]
+    uint64_t* tmem_full_bar = h_empty + 2;              // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmW)) : "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < WIDE_W_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&h_full[a], 1);
+            mbar_init(&h_empty[a], 1);
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // 2 accumulator stages x 256 columns = the whole TMEM
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t -> (channel tile fastest, then x, y, image): neighbouring CTAs share halo tiles and weight slices in L2
+    auto decode = [&](int t, int& c0, int& ox0, int& oy0, int& img) {
+        c0 = (t % p.tiles_c) * 128;
+        int r = t / p.tiles_c;
+        ox0 = (r % p.tiles_x) * WIDE_TW;
+        r /= p.tiles_x;
+        oy0 = (r % p.tiles_y) * WIDE_TH;
+        img = r / p.tiles_y;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int ws = 0, hb = 0;
+            uint32_t wph = 0, hph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                int c0, ox0, oy0, img;
+                decode(t, c0, ox0, oy0, img);
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    mbar_wait(&h_empty[hb], hph ^ 1);
+                    mbar_expect_tx(&h_full[hb], WIDE_HALO_ROWS * ROW_BYTES);
+                    tma_load_4d(smem + hb * WIDE_HALO_BYTES, &p.tmX, &h_full[hb], cb * 64, ox0 - 1, oy0 - 1, img);
+                    if (++hb == 2) { hb = 0; hph ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&w_empty[ws], wph ^ 1);
+                        mbar_expect_tx(&w_full[ws], WIDE_W_BYTES);
+                        tma_load_4d(w_base + ws * WIDE_W_BYTES, &p.tmW, &w_full[ws], (tap * p.cin_blocks + cb) * 64, c0, 0, 0);
+                        if (++ws == WIDE_W_SLOTS) { ws = 0; wph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            int ws = 0, hb = 0, it = 0;
+            uint32_t wph = 0, hph = 0;
+            bool ready = false;                 // next weight slot already seen full (polled ahead of the previous MMAs)
+            constexpr uint32_t PITCH = WIDE_TW + 2;
+#ifdef VF_TC_STALL_COUNTERS
+            const bool dbg = p.dbg != nullptr;
+#else
+            constexpr bool dbg = false;
+#endif
+            long long c_ops = 0, c_tmem = 0, c_tiles = 0, c0 = 0;
+            const long long c_start = dbg ? clock64() : 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                if (dbg) c0 = clock64();
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                if (dbg) { c_tmem += clock64() - c0; ++c_tiles; }
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    if (dbg) c0 = clock64();
+                    mbar_wait(&h_full[hb], hph);
+                    if (dbg) c_ops += clock64() - c0;
+                    tcgen05_fence_after();
+                    const uint32_t h_addr = smem_u32(smem + hb * WIDE_HALO_BYTES);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (dbg) c0 = clock64();
+                        if (!ready) mbar_wait(&w_full[ws], wph);
+                        if (dbg) c_ops += clock64() - c0;
+                        {
+                            const int ns = (ws + 1 == WIDE_W_SLOTS) ? 0 : ws + 1;
+                            ready = mbar_test_wait(&w_full[ns], ns == 0 ? (wph ^ 1) : wph);
+                        }
+                        tcgen05_fence_after();
+                        const uint64_t adesc = make_sw128_desc(smem_u32(w_base + ws * WIDE_W_BYTES));
+                        const uint32_t b_addr = h_addr + ((uint32_t)(tap / 3) * PITCH + (uint32_t)(tap % 3)) * ROW_BYTES;
+                        uint64_t bdesc = make_sw128_desc(b_addr);
+                        bdesc = (bdesc & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((PITCH * ROW_BYTES) >> 4) << 32);     // SBO = one halo row pitch
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        tcgen05_commit(&w_empty[ws]);
+                        if (++ws == WIDE_W_SLOTS) { ws = 0; wph ^= 1; }
+                    }
+                    tcgen05_commit(&h_empty[hb]);
+                    if (++hb == 2) { hb = 0; hph ^= 1; }
+                }
+                tcgen05_commit(&tmem_full_bar[acc]);
+                ++it;
+            }
+            if (dbg) {
+                long long* d = p.dbg + 8 * blockIdx.x;
+                d[0] = clock64() - c_start; d[1] = c_ops; d[2] = c_tmem; d[3] = c_tiles; d[4] = 1; d[5] = 0;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9): lane = output channel, register j = pixel =====================
+        const int quarter = warp & 3;                     // TMEM lanes [32q, 32q+32) = channels c0 + 32q + lane
+        const int half = (warp - 2) >> 2;                 // pixels [128*half, 128*half + 128) of the patch
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int c0, ox0, oy0, img;
+            decode(t, c0, ox0, oy0, img);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            ++it;
+            const int ch = c0 + quarter * 32 + lane;
+            const float bias = p.bias ? __ldg(p.bias + ch) : 0.f;
+            // element index of (pixel (ty, tx) of the patch, channel ch) = base + ty * row_stride + tx * Cout; 32-bit (host-checked)
+            const int base = ((img * p.H + oy0) * p.W + ox0) * p.Cout + ch;
+            const int row_stride = p.W * p.Cout;
+            const int rows_ok = p.H - oy0, cols_ok = p.W - ox0;          // valid rows / columns of this patch
+            const bool full = rows_ok >= WIDE_TH && cols_ok >= WIDE_TW;
+            const bool has_res = p.residual != nullptr;
+            // chunk c of this warp = patch rows [half*16 + 4c, +4), register j -> (row j/8, column j%8)
+            float rvA[32], rvB[32];
+            auto load_res = [&](int c, float (&rv)[32]) {
+                const int r0 = half * 16 + c * 4;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    int ty = r0 + (j >> 3), tx = j & 7;
+                    if (!full) {                          // clamp (never stored): the 32 loads stay unconditional and in flight together
+                        ty = ty < rows_ok ? ty : rows_ok - 1;
+                        tx = tx < cols_ok ? tx : cols_ok - 1;
+                    }
+                    rv[j] = __ldg(p.residual + (base + ty * row_stride + tx * p.Cout));
+                }
+            };
+            float gs = 0.f, gq = 0.f;
+            auto chunk = [&](int c, float (&rv)[32]) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128 + c * 32), r);
+                if (c == 3) {                             // all TMEM reads of this warp are done -> hand the accumulator stage back
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                const int r0 = half * 16 + c * 4;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r[j]) + bias;
+                    if (has_res) v[j] += rv[j];
+                }
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { gs += v[j]; gq = fmaf(v[j], v[j], gq); }
+                    if (p.C_f32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)      // 32 lanes = 32 consecutive channels of one pixel = one 128-byte row
+                            p.C_f32[base + (r0 + (j >> 3)) * row_stride + (j & 7) * p.Cout] = v[j];
+                    }
+                    if (p.C_bf16) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            p.C_bf16[base + (r0 + (j >> 3)) * row_stride + (j & 7) * p.Cout] = __float2bfloat16(v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ty = r0 + (j >> 3), tx = j & 7;
+                        if (ty < rows_ok && tx < cols_ok) {       // warp-uniform
+                            const int idx = base + ty * row_stride + tx * p.Cout;
+                            gs += v[j];
+                            gq = fmaf(v[j], v[j], gq);
+                            if (p.C_f32) p.C_f32[idx] = v[j];
+                            if (p.C_bf16) p.C_bf16[idx] = __float2bfloat16(v[j]);
+                        }
+                    }
+                }
+            };
+#ifdef VF_TC_STALL_COUNTERS
+            if (p.dbg_flags & 1) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                continue;
+            }
+#endif
+            if (has_res) load_res(0, rvA);                // flies behind this tile's MMAs
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            // residual rows of chunk c+1 are requested before chunk c is read out of TMEM and stored
+            if (has_res) load_res(1, rvB);
+            chunk(0, rvA);
+            if (has_res) load_res(2, rvA);
+            chunk(1, rvB);
+            if (has_res) load_res(3, rvB);
+            chunk(2, rvA);
+            chunk(3, rvB);
+            if (p.gn_sums) {
+                // lanes of one GroupNorm group are adjacent: fold them, one fp64 RED per (image, group) and warp
+                for (int o = 1; o < p.gn_cpg; o <<= 1) {
+                    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                    gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                }
+                if ((lane & (p.gn_cpg - 1)) == 0) {
+                    double* d = p.gn_sums + ((long long)img * p.gn_groups + ch / p.gn_cpg) * 2;
+                    atomicAdd(d, (double)gs);
+                    atomicAdd(d + 1, (double)gq);
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -842,8 +1124,82 @@ int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
+
 static long long* g_tc_dbg = nullptr;
 static int g_tc_dbg_flags = 0;
+// 3x3 stride-1 pad-1 bf16 convolutions on maps at least 32 rows tall go to the wide-tile kernel (VF_TC_WIDE=0 disables)
+static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
+    WideParams prm;
+    memset(&prm, 0, sizeof(prm));
+    const int es = 2;
+    const uint64_t dimsX[4] = {(uint64_t)q->Cin, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->N};
+    const uint64_t strX[3] = {(uint64_t)q->Ctot * es, (uint64_t)q->W * q->Ctot * es, (uint64_t)q->H * q->W * q->Ctot * es};
+    const uint32_t boxX[4] = {64, WIDE_TW + 2, WIDE_TH + 2, 1};
+    int rc;
+    if ((rc = make_tmap(&prm.tmX, VF_BF16, q->A, dimsX, strX, boxX)) != VF_OK) return rc;
+    const uint64_t Ktot = 9ull * q->Cin;
+    const uint64_t dimsW[4] = {Ktot, (uint64_t)q->Ncols, 1, 1};
+    const uint64_t strW[3] = {Ktot * es, Ktot * es * q->Ncols, Ktot * es * q->Ncols};
+    const uint32_t boxW[4] = {64, 128, 1, 1};
+    if ((rc = make_tmap(&prm.tmW, VF_BF16, q->B, dimsW, strW, boxW)) != VF_OK) return rc;
+    prm.bias = q->bias_mode == VF_BIAS_N ? q->bias : nullptr;
+    prm.residual = q->residual;
+    prm.C_f32 = q->C_f32;
+    prm.C_bf16 = reinterpret_cast<__nv_bfloat16*>(q->C_bf16);
+    prm.N = q->N; prm.H = q->H; prm.W = q->W; prm.Cout = q->Ncols; prm.cin_blocks = q->Cin / 64;
+    prm.tiles_x = (q->W + WIDE_TW - 1) / WIDE_TW;
+    prm.tiles_y = (q->H + WIDE_TH - 1) / WIDE_TH;
+    prm.tiles_c = q->Ncols / 128;
+    const long long total = (long long)prm.tiles_x * prm.tiles_y * prm.tiles_c * q->N;
+    VF_CHECK_ARG(total > 0 && total < (1ll << 31), "vf_tc_gemm: tile count out of range");
+    prm.total_tiles = (int)total;
+    prm.idesc = make_idesc(false, 128, 256);
+    prm.dbg = g_tc_dbg;
+    prm.dbg_flags = g_tc_dbg_flags;
+    if (q->gn_sums) {
+        const int cpg = q->Ncols / q->gn_groups;
+        prm.gn_sums = q->gn_sums;
+        prm.gn_groups = q->gn_groups;
+        prm.gn_cpg = cpg;
+        cudaError_t e = cudaMemsetAsync(q->gn_sums, 0, sizeof(double) * 2 * q->gn_groups * q->N, st);
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: memset gn_sums: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute(wide): %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+        configured = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+    tc_conv3x3_wide_kernel<<<grid, NUM_THREADS, WIDE_SMEM, st>>>(prm);
+    VF_CHECK_LAUNCH("vf_tc_gemm(wide conv)");
+    return VF_OK;
+}
+
+static bool conv_wide_eligible(const vf_tc_gemm_t* q) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("VF_TC_WIDE"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    if (!enabled || !q->conv || q->ab_dtype != VF_BF16 || q->ntaps != 9 || q->Ctot != q->Cin || q->OH != q->H || q->OW != q->W) return false;
+    if (q->Cin % 64 || q->Ncols % 128 || q->H < 32 || q->W < 8 || q->ldc != q->Ncols || q->alpha != 1.0f || q->act != VF_ACT_NONE) return false;
+    if (q->bias_mode == VF_BIAS_M) return false;
+    if ((long long)q->N * q->H * q->W * q->Ncols >= (1ll << 31)) return false;      // the epilogue indexes with 32 bits
+    for (int t = 0; t < 9; ++t)
+        if (q->tap_dy[t] != t / 3 - 1 || q->tap_dx[t] != t % 3 - 1 || q->tap_coff[t] != 0) return false;
+    if (q->gn_sums) {
+        if (q->gn_groups <= 0 || q->Ncols % q->gn_groups) return false;
+        const int cpg = q->Ncols / q->gn_groups;
+        if (cpg > 32 || (cpg & (cpg - 1)) || 32 % cpg) return false;
+    }
+    return true;
+}
+
+
 extern "C" void vf_tc_debug_flags(int f) { g_tc_dbg_flags = f; }
 // profiling aid (scripts/tc_stall_probe.py), not in the public header: MMA-issuer stall counters of the following launches ([grid][4] int64)
 extern "C" void vf_tc_debug_counters(long long* buf) { g_tc_dbg = buf; }
@@ -853,6 +1209,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     VF_CHECK_ARG(q->C_f32 || q->C_bf16, "vf_tc_gemm: no output");
     VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32, "vf_tc_gemm: bad dtype");
     VF_CHECK_ARG(q->bias_mode == VF_BIAS_NONE || q->bias, "vf_tc_gemm: bias pointer missing");
+    if (conv_wide_eligible(q)) return launch_conv_wide(q, vf_s(s));
     const bool tf32 = q->ab_dtype == VF_F32;
     const int es = tf32 ? 4 : 2;
     const int bk = ROW_BYTES / es;                       // K elements per block: 64 bf16 / 32 tf32
