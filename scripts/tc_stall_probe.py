@@ -6,6 +6,11 @@ from viewformer_b200 import _lib as L
 lib = L.load(True)
 def run(name, fn):
     for _ in range(2): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5): fn()
+    e1.record(); torch.cuda.synchronize()
+    print(f"    [{name}] {e0.elapsed_time(e1) / 5 * 1e3:.1f} us per launch (CUDA events, 5 launches)")
     buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
     lib.vf_tc_debug_counters(ctypes.c_void_p(buf.data_ptr()))
     torch.cuda.synchronize(); fn(); torch.cuda.synchronize()
@@ -27,3 +32,10 @@ run("conv 128->128 @128^2 no residual", lambda: L.tc_conv(x, w, b, out=out))
 run("conv 128->128 @128^2 + residual", lambda: L.tc_conv(x, w, b, out=out, residual=res))
 A = torch.randn((20480, 3072), device="cuda").bfloat16(); B = torch.randn((768, 3072), device="cuda").bfloat16(); o2 = torch.empty((20480, 768), device="cuda")
 run("gemm 20480x768x3072", lambda: L.tc_gemm(A, B, o2, M=20480, N=768, K=3072, lda=3072, ldb=3072, ldc=768))
+
+bias768 = torch.zeros(768, device="cuda"); res768 = torch.randn((20480, 768), device="cuda")
+run("fc2 + bias + residual", lambda: L.tc_gemm(A, B, o2, M=20480, N=768, K=3072, lda=3072, ldb=3072, ldc=768, bias=bias768, bias_mode=1, residual=res768))
+X = torch.randn((20480, 768), device="cuda").bfloat16(); Wqk = torch.randn((1536, 768), device="cuda").bfloat16(); oqk = torch.empty((20480, 1536), device="cuda", dtype=torch.bfloat16)
+run("qk -> bf16", lambda: L.tc_gemm(X, Wqk, oqk, M=20480, N=1536, K=768, lda=768, ldb=768, ldc=1536))
+oqf = torch.empty((20480, 1536), device="cuda")
+run("qk -> f32", lambda: L.tc_gemm(X, Wqk, oqf, M=20480, N=1536, K=768, lda=768, ldb=768, ldc=1536))

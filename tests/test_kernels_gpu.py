@@ -193,6 +193,26 @@ def test_tc_gemm_epilogues_bf16(L):
     _tc_case(L, torch.bfloat16, 256, 128, 192, bias_mode=1, out_dtype=torch.bfloat16, seed=11)
 
 
+def test_tc_gemm_wide_tiles(L):
+    """un-batched bf16 GEMMs with >= 256 rows and N % 128 == 0 take the wide-tile kernel (128 features x 256 rows per tile,
+    register epilogue): row tails, K tails, every epilogue combination, and a contiguous batch that flattens."""
+    _tc_case(L, torch.bfloat16, 256, 128, 64, seed=40)
+    _tc_case(L, torch.bfloat16, 1000, 768, 776, bias_mode=1, residual=True, seed=41)               # M tail (1000 = 3*256+232), K tail
+    _tc_case(L, torch.bfloat16, 300, 256, 512, bias_mode=1, act=1, out_dtype=torch.bfloat16, seed=42)   # GELU -> bf16 (fast erf)
+    _tc_case(L, torch.bfloat16, 2048, 384, 3072, bias_mode=1, act=1, seed=43)                       # GELU -> f32 (exact erf), long K
+    _tc_case(L, torch.bfloat16, 513, 128, 192, residual=True, alpha=0.25, seed=44)
+    # contiguous batch with shared weights == one flat row range (the q|k projection pattern)
+    Bn, S, d, N = 3, 192, 128, 256
+    X = torch.randn(Bn, S, d, generator=g(45)).bfloat16().cuda()
+    W = (torch.randn(N, d, generator=g(46)) / d ** 0.5).bfloat16().cuda()
+    bias = torch.randn(N, generator=g(47))
+    out = torch.empty(Bn, S, N, dtype=torch.bfloat16, device="cuda")
+    L.tc_gemm(X, W, out, M=S, N=N, K=d, lda=d, ldb=d, ldc=N, batch=(Bn, 1), a_bs=(S * d, 0), b_bs=(0, 0), c_bs=(S * N, 0),
+              bias=bias.cuda(), bias_mode=L.BIAS_N)
+    want = torch.einsum("bmk,nk->bmn", X.double().cpu(), W.double().cpu()) + bias.double()
+    report("wide gemm flattened batch", out.float(), want, 3e-2, 2e-2)
+
+
 def test_tc_gemm_batched_bf16(L):
     _tc_case(L, torch.bfloat16, 192, 128, 128, batch=(2, 3), bias_mode=1, seed=12)
 

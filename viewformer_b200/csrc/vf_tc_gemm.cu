@@ -1007,13 +1007,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             // residual rows of chunk c+1 are requested before chunk c is read out of TMEM and stored
-            if (has_res) load_res(1, rvB);
-            chunk(0, rvA);
-            if (has_res) load_res(2, rvA);
-            chunk(1, rvB);
-            if (has_res) load_res(3, rvB);
-            chunk(2, rvA);
-            chunk(3, rvB);
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc += 2) {          // two chunk bodies in the instruction stream, not four
+                if (has_res) load_res(cc + 1, rvB);
+                chunk(cc, rvA);
+                if (has_res && cc == 0) load_res(2, rvA);
+                chunk(cc + 1, rvB);
+            }
             if (p.gn_sums) {
                 // lanes of one GroupNorm group are adjacent: fold them, one fp64 RED per (image, group) and warp
                 for (int o = 1; o < p.gn_cpg; o <<= 1) {
@@ -1029,6 +1029,224 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
         }
     }
 
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+
+// ==============================================================================================================
+// Wide-tile GEMM for the un-batched linear layers, same operand swap as the wide convolution:
+//   A (M = 128) = 128 output features of the weight matrix W [Nf][K]; B (N = 256) = 256 rows (tokens) of X [M][K];
+//   D: TMEM lane = feature, column = token.  out[token][feature] = act(alpha * sum_k X W + bias[feature]) + residual.
+// 4 stages x (16 KB W + 32 KB X); epilogue straight from registers (32 lanes = 32 consecutive features = one 128-byte row).
+// ==============================================================================================================
+struct WideGemmParams {
+    CUtensorMap tmW;           // weights [Nf, K]: box {bk, 128}
+    CUtensorMap tmX;           // rows    [M, K]:  box {bk, 256}
+    const float* bias;         // [Nf] or null
+    const float* residual;     // [M, ldc] fp32 or null
+    float* C_f32;
+    __nv_bfloat16* C_bf16;
+    float alpha;
+    int act;
+    int M, Nf, ldc, num_k_blocks;
+    int tiles_f, total_tiles;
+    unsigned idesc;
+    long long* dbg;
+    int dbg_flags;
+};
+constexpr int WG_STAGES = 4;
+constexpr int WG_W_BYTES = 128 * ROW_BYTES, WG_X_BYTES = 256 * ROW_BYTES;
+constexpr int WG_STAGE_BYTES = WG_W_BYTES + WG_X_BYTES;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+// erf-GELU for bf16 outputs: Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7 on erf, far below bf16 rounding) with ex2/rcp
+// approximations — the exact erff() costs more issue slots than the MMAs of a K = 768 tile leave to the epilogue
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = 1.0f - poly * t * __expf(-z * z);          // erf(|x| / sqrt 2)
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+// kGelu / kBf16Out are compile-time so that each instantiation carries one epilogue (the fully unrolled runtime-switched version
+// was ~13k instructions and ran out of the instruction cache: 30k cycles per tile)
+template <bool kGelu, bool kBf16Out>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __grid_constant__ WideGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + WG_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + WG_STAGES;    // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmW)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmX)) : "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {          // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int f0 = (t % p.tiles_f) * 128, m0 = (t / p.tiles_f) * 256;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sw = smem + stage * WG_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+                    tma_load_4d(sw, &p.tmW, &full_bar[stage], kb * 64, f0, 0, 0);
+                    tma_load_4d(sw + WG_W_BYTES, &p.tmX, &full_bar[stage], kb * 64, m0, 0, 0);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {          // ===================== MMA issuer =====================
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            bool ready = false;
+#ifdef VF_TC_STALL_COUNTERS
+            const bool dbg = p.dbg != nullptr;
+#else
+            constexpr bool dbg = false;
+#endif
+            long long c_ops = 0, c_tmem = 0, c_tiles = 0, c0 = 0;
+            const long long c_start = dbg ? clock64() : 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                if (dbg) c0 = clock64();
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                if (dbg) { c_tmem += clock64() - c0; ++c_tiles; }
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+#pragma unroll 1
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    if (dbg) c0 = clock64();
+                    if (!ready) mbar_wait(&full_bar[stage], phase);
+                    if (dbg) c_ops += clock64() - c0;
+                    {
+                        const int ns = (stage + 1 == WG_STAGES) ? 0 : stage + 1;
+                        ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
+                    }
+                    tcgen05_fence_after();
+                    const uint32_t sw = smem_u32(smem + stage * WG_STAGE_BYTES);
+                    const uint64_t adesc = make_sw128_desc(sw), bdesc = make_sw128_desc(sw + WG_W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    tcgen05_commit(&empty_bar[stage]);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&tmem_full_bar[acc]);
+                ++it;
+            }
+            if (dbg) {
+                long long* d = p.dbg + 8 * blockIdx.x;
+                d[0] = clock64() - c_start; d[1] = c_ops; d[2] = c_tmem; d[3] = c_tiles; d[4] = 1; d[5] = 0;
+            }
+        }
+    } else {
+        // ===================== epilogue: lane = feature, register j = token =====================
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int f0 = (t % p.tiles_f) * 128, m0 = (t / p.tiles_f) * 256;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            ++it;
+            const int f = f0 + quarter * 32 + lane;
+            const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
+            const int row0 = m0 + half * 128;                        // first token of this warp's 128 columns
+            const int base = row0 * p.ldc + f;                       // 32-bit (host-checked)
+            const int rows_ok = p.M - row0;                          // tokens of this warp that exist (may be <= 0 or >= 128)
+            const bool has_res = p.residual != nullptr;
+            float rvA[32], rvB[32];
+            auto load_res = [&](int c, float (&rv)[32]) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    int r = c * 32 + j;
+                    r = r < rows_ok ? r : (rows_ok > 0 ? rows_ok - 1 : 0);        // clamped, never stored
+                    rv[j] = rows_ok > 0 ? __ldg(p.residual + (base + r * p.ldc)) : 0.f;
+                }
+            };
+            auto chunk = [&](int c, float (&rv)[32]) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128 + c * 32), r);
+                if (c == 3) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bias);
+                    if (kGelu) v[j] = kBf16Out ? gelu_erf_fast(v[j]) : vf_gelu_erf(v[j]);
+                    if (has_res) v[j] += rv[j];
+                }
+                const int cb = base + c * 32 * p.ldc;
+                if (rows_ok >= (c + 1) * 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (kBf16Out) p.C_bf16[cb + j * p.ldc] = __float2bfloat16(v[j]);
+                        else p.C_f32[cb + j * p.ldc] = v[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (c * 32 + j < rows_ok) {
+                            if (kBf16Out) p.C_bf16[cb + j * p.ldc] = __float2bfloat16(v[j]);
+                            else p.C_f32[cb + j * p.ldc] = v[j];
+                        }
+                    }
+                }
+            };
+#ifdef VF_TC_STALL_COUNTERS
+            if (p.dbg_flags & 1) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                continue;
+            }
+#endif
+            if (has_res) load_res(0, rvA);
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc += 2) {          // two chunk bodies in the instruction stream, not four
+                if (has_res) load_res(cc + 1, rvB);
+                chunk(cc, rvA);
+                if (has_res && cc == 0) load_res(2, rvA);
+                chunk(cc + 1, rvB);
+            }
+        }
+    }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -1182,6 +1400,79 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
     return VF_OK;
 }
 
+
+// un-batched bf16 linear layers (features % 128 == 0) go to the wide-tile GEMM
+static bool gemm_wide_eligible(const vf_tc_gemm_t* q, long long* M_flat) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("VF_TC_WIDE"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    if (!enabled || q->conv || q->ab_dtype != VF_BF16 || q->causal_block != 0 || q->gn_sums) return false;
+    if ((q->C_f32 != nullptr) == (q->C_bf16 != nullptr)) return false;            // exactly one output dtype per instantiation
+    if (q->bias_mode == VF_BIAS_M || q->Ncols % 128 || q->K <= 0 || (q->K * 2) % 16 || (q->lda * 2) % 16 || (q->ldb * 2) % 16) return false;
+    long long M = q->M;
+    if (q->batch2 != 1) return false;
+    if (q->batch1 > 1) {        // a batch that is really one contiguous row range with a shared B
+        if (q->b_sb1 != 0 || q->a_sb1 != (long long)q->M * q->lda || q->c_sb1 != (long long)q->M * q->ldc) return false;
+        M *= q->batch1;
+    }
+    if (M < 256 || M * (long long)q->ldc >= (1ll << 31)) return false;
+    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!a16(q->A) || !a16(q->B)) return false;
+    *M_flat = M;
+    return true;
+}
+
+static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st) {
+    WideGemmParams prm;
+    memset(&prm, 0, sizeof(prm));
+    const int es = 2;
+    int rc;
+    const uint64_t dimsW[4] = {(uint64_t)q->K, (uint64_t)q->Ncols, 1, 1};
+    const uint64_t strW[3] = {(uint64_t)q->ldb * es, (uint64_t)q->ldb * es * q->Ncols, (uint64_t)q->ldb * es * q->Ncols};
+    const uint32_t boxW[4] = {64, 128, 1, 1};
+    if ((rc = make_tmap(&prm.tmW, VF_BF16, q->B, dimsW, strW, boxW)) != VF_OK) return rc;
+    const uint64_t dimsX[4] = {(uint64_t)q->K, (uint64_t)M, 1, 1};
+    const uint64_t strX[3] = {(uint64_t)q->lda * es, (uint64_t)q->lda * es * M, (uint64_t)q->lda * es * M};
+    const uint32_t boxX[4] = {64, 256, 1, 1};
+    if ((rc = make_tmap(&prm.tmX, VF_BF16, q->A, dimsX, strX, boxX)) != VF_OK) return rc;
+    prm.bias = q->bias_mode == VF_BIAS_N ? q->bias : nullptr;
+    prm.residual = q->residual;
+    prm.C_f32 = q->C_f32;
+    prm.C_bf16 = reinterpret_cast<__nv_bfloat16*>(q->C_bf16);
+    prm.alpha = q->alpha;
+    prm.act = q->act;
+    prm.M = (int)M; prm.Nf = q->Ncols; prm.ldc = q->ldc;
+    prm.num_k_blocks = (q->K + 63) / 64;
+    prm.tiles_f = q->Ncols / 128;
+    const long long total = (long long)prm.tiles_f * ((M + 255) / 256);
+    prm.total_tiles = (int)total;
+    prm.idesc = make_idesc(false, 128, 256);
+    prm.dbg = g_tc_dbg;
+    prm.dbg_flags = g_tc_dbg_flags;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_wide_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_wide_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_wide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute(wide gemm): %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+        configured = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+    const bool gelu = q->act == VF_ACT_GELU_ERF, b16 = q->C_bf16 != nullptr;
+    if (gelu && b16) tc_gemm_wide_kernel<true, true><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
+    else if (gelu) tc_gemm_wide_kernel<true, false><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
+    else if (b16) tc_gemm_wide_kernel<false, true><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
+    else tc_gemm_wide_kernel<false, false><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
+    VF_CHECK_LAUNCH("vf_tc_gemm(wide gemm)");
+    return VF_OK;
+}
+
 static bool conv_wide_eligible(const vf_tc_gemm_t* q) {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("VF_TC_WIDE"); enabled = (e && e[0] == '0') ? 0 : 1; }
@@ -1210,6 +1501,10 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32, "vf_tc_gemm: bad dtype");
     VF_CHECK_ARG(q->bias_mode == VF_BIAS_NONE || q->bias, "vf_tc_gemm: bias pointer missing");
     if (conv_wide_eligible(q)) return launch_conv_wide(q, vf_s(s));
+    {
+        long long m_flat = 0;
+        if (gemm_wide_eligible(q, &m_flat)) return launch_gemm_wide(q, m_flat, vf_s(s));
+    }
     const bool tf32 = q->ab_dtype == VF_F32;
     const int es = tf32 ? 4 : 2;
     const int bk = ROW_BYTES / es;                       // K elements per block: 64 bf16 / 32 tf32
