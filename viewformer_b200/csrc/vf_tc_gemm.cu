@@ -781,6 +781,10 @@ struct WideParams {
     int dbg_flags;
 };
 
+// wide kernels: 16 epilogue warps (4 per TMEM lane quarter, 64 accumulator columns each): with 2 warps per scheduler the register
+// epilogue ran at ~0.25 IPC per warp (ncu: stall_wait / short scoreboard) and held every tile for 10-20k cycles
+constexpr int WIDE_EPI_WARPS = 16;
+constexpr int WIDE_THREADS = 64 + 32 * WIDE_EPI_WARPS;
 constexpr int WIDE_TW = 8, WIDE_TH = 32;
 constexpr int WIDE_HALO_ROWS = (WIDE_TW + 2) * (WIDE_TH + 2);          // 340 rows of 128 B
 constexpr int WIDE_HALO_BYTES = 44032;                                  // >= 340 * 128, multiple of 1024
@@ -788,7 +792,7 @@ constexpr int WIDE_W_SLOTS = 8;
 constexpr int WIDE_W_BYTES = 128 * ROW_BYTES;                           // one (tap, channel block) weight tile
 constexpr int WIDE_SMEM = 2 * WIDE_HALO_BYTES + WIDE_W_SLOTS * WIDE_W_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
+__global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* w_base = smem + 2 * WIDE_HALO_BYTES;
@@ -813,7 +817,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
             mbar_init(&h_full[a], 1);
             mbar_init(&h_empty[a], 1);
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+            mbar_init(&tmem_empty_bar[a], WIDE_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -918,9 +922,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9): lane = output channel, register j = pixel =====================
+        // ===================== epilogue (warps 2..17): lane = output channel, register j = pixel =====================
         const int quarter = warp & 3;                     // TMEM lanes [32q, 32q+32) = channels c0 + 32q + lane
-        const int half = (warp - 2) >> 2;                 // pixels [128*half, 128*half + 128) of the patch
+        const int grp = (warp - 2) >> 2;                  // pixels [64*grp, 64*grp + 64) of the patch = patch rows [8*grp, 8*grp + 8)
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             int c0, ox0, oy0, img;
@@ -936,10 +940,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
             const int rows_ok = p.H - oy0, cols_ok = p.W - ox0;          // valid rows / columns of this patch
             const bool full = rows_ok >= WIDE_TH && cols_ok >= WIDE_TW;
             const bool has_res = p.residual != nullptr;
-            // chunk c of this warp = patch rows [half*16 + 4c, +4), register j -> (row j/8, column j%8)
-            float rvA[32], rvB[32];
-            auto load_res = [&](int c, float (&rv)[32]) {
-                const int r0 = half * 16 + c * 4;
+            // chunk c (0, 1) of this warp = patch rows [8*grp + 4c, +4), register j -> (row j/8, column j%8)
+            float rv[32];
+            auto load_res = [&](int c) {
+                const int r0 = grp * 8 + c * 4;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     int ty = r0 + (j >> 3), tx = j & 7;
@@ -951,21 +955,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
                 }
             };
             float gs = 0.f, gq = 0.f;
-            auto chunk = [&](int c, float (&rv)[32]) {
+#ifdef VF_TC_STALL_COUNTERS
+            if (p.dbg_flags & 1) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                continue;
+            }
+#endif
+            if (has_res) load_res(0);                     // flies behind this tile's MMAs
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128 + c * 32), r);
-                if (c == 3) {                             // all TMEM reads of this warp are done -> hand the accumulator stage back
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + grp * 64 + c * 32), r);
+                if (c == 1) {                             // all TMEM reads of this warp are done -> hand the accumulator stage back
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                const int r0 = half * 16 + c * 4;
+                const int r0 = grp * 8 + c * 4;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     v[j] = __uint_as_float(r[j]) + bias;
                     if (has_res) v[j] += rv[j];
                 }
+                if (has_res && c == 0) load_res(1);       // the second chunk's residual rows fly while the first chunk is stored
                 if (full) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { gs += v[j]; gq = fmaf(v[j], v[j], gq); }
@@ -992,27 +1011,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv3x3_wide_kernel(const _
                         }
                     }
                 }
-            };
-#ifdef VF_TC_STALL_COUNTERS
-            if (p.dbg_flags & 1) {
-                mbar_wait(&tmem_full_bar[acc], acc_phase);
-                tcgen05_fence_after();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                continue;
-            }
-#endif
-            if (has_res) load_res(0, rvA);                // flies behind this tile's MMAs
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tcgen05_fence_after();
-            // residual rows of chunk c+1 are requested before chunk c is read out of TMEM and stored
-#pragma unroll 1
-            for (int cc = 0; cc < 4; cc += 2) {          // two chunk bodies in the instruction stream, not four
-                if (has_res) load_res(cc + 1, rvB);
-                chunk(cc, rvA);
-                if (has_res && cc == 0) load_res(2, rvA);
-                chunk(cc + 1, rvB);
             }
             if (p.gn_sums) {
                 // lanes of one GroupNorm group are adjacent: fold them, one fp64 RED per (image, group) and warp
@@ -1077,7 +1075,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // kGelu / kBf16Out are compile-time so that each instantiation carries one epilogue (the fully unrolled runtime-switched version
 // was ~13k instructions and ran out of the instruction cache: 30k cycles per tile)
 template <bool kGelu, bool kBf16Out>
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __grid_constant__ WideGemmParams p) {
+__global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __grid_constant__ WideGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -1094,7 +1092,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __gr
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], WIDE_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1169,9 +1167,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __gr
             }
         }
     } else {
-        // ===================== epilogue: lane = feature, register j = token =====================
+        // ===================== epilogue (warps 2..17): lane = feature, register j = token =====================
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int grp = (warp - 2) >> 2;                             // tokens [64*grp, +64) of the tile
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const int f0 = (t % p.tiles_f) * 128, m0 = (t / p.tiles_f) * 256;
@@ -1180,12 +1178,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __gr
             ++it;
             const int f = f0 + quarter * 32 + lane;
             const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
-            const int row0 = m0 + half * 128;                        // first token of this warp's 128 columns
+            const int row0 = m0 + grp * 64;                          // first token of this warp's 64 columns
             const int base = row0 * p.ldc + f;                       // 32-bit (host-checked)
-            const int rows_ok = p.M - row0;                          // tokens of this warp that exist (may be <= 0 or >= 128)
+            const int rows_ok = p.M - row0;                          // tokens of this warp that exist (may be <= 0 or >= 64)
             const bool has_res = p.residual != nullptr;
-            float rvA[32], rvB[32];
-            auto load_res = [&](int c, float (&rv)[32]) {
+            float rv[32];
+            auto load_res = [&](int c) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     int r = c * 32 + j;
@@ -1193,10 +1191,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __gr
                     rv[j] = rows_ok > 0 ? __ldg(p.residual + (base + r * p.ldc)) : 0.f;
                 }
             };
-            auto chunk = [&](int c, float (&rv)[32]) {
+#ifdef VF_TC_STALL_COUNTERS
+            if (p.dbg_flags & 1) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                continue;
+            }
+#endif
+            if (has_res) load_res(0);
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128 + c * 32), r);
-                if (c == 3) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + grp * 64 + c * 32), r);
+                if (c == 1) {
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -1208,6 +1220,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __gr
                     if (kGelu) v[j] = kBf16Out ? gelu_erf_fast(v[j]) : vf_gelu_erf(v[j]);
                     if (has_res) v[j] += rv[j];
                 }
+                if (has_res && c == 0) load_res(1);
                 const int cb = base + c * 32 * p.ldc;
                 if (rows_ok >= (c + 1) * 32) {
 #pragma unroll
@@ -1224,26 +1237,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_wide_kernel(const __gr
                         }
                     }
                 }
-            };
-#ifdef VF_TC_STALL_COUNTERS
-            if (p.dbg_flags & 1) {
-                mbar_wait(&tmem_full_bar[acc], acc_phase);
-                tcgen05_fence_after();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                continue;
-            }
-#endif
-            if (has_res) load_res(0, rvA);
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tcgen05_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < 4; cc += 2) {          // two chunk bodies in the instruction stream, not four
-                if (has_res) load_res(cc + 1, rvB);
-                chunk(cc, rvA);
-                if (has_res && cc == 0) load_res(2, rvA);
-                chunk(cc + 1, rvB);
             }
         }
     }
@@ -1395,7 +1388,7 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
     const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
-    tc_conv3x3_wide_kernel<<<grid, NUM_THREADS, WIDE_SMEM, st>>>(prm);
+    tc_conv3x3_wide_kernel<<<grid, WIDE_THREADS, WIDE_SMEM, st>>>(prm);
     VF_CHECK_LAUNCH("vf_tc_gemm(wide conv)");
     return VF_OK;
 }
@@ -1465,10 +1458,10 @@ static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st)
     }
     const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
     const bool gelu = q->act == VF_ACT_GELU_ERF, b16 = q->C_bf16 != nullptr;
-    if (gelu && b16) tc_gemm_wide_kernel<true, true><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
-    else if (gelu) tc_gemm_wide_kernel<true, false><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
-    else if (b16) tc_gemm_wide_kernel<false, true><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
-    else tc_gemm_wide_kernel<false, false><<<grid, NUM_THREADS, WG_SMEM, st>>>(prm);
+    if (gelu && b16) tc_gemm_wide_kernel<true, true><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    else if (gelu) tc_gemm_wide_kernel<true, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    else if (b16) tc_gemm_wide_kernel<false, true><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    else tc_gemm_wide_kernel<false, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
     VF_CHECK_LAUNCH("vf_tc_gemm(wide gemm)");
     return VF_OK;
 }
