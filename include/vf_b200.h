@@ -70,7 +70,8 @@ int vf_groupnorm_apply(const void* x, int x_dtype, const float* mean_rstd, const
 /* Exact fp32 3x3 stride-1 pad-1 convolutions for the two tiny-channel layers (vqgan_th.py:159-163 conv_in 3->128,
  * :285-289 conv_out 128->3).  NHWC; weights [9*Cin, Cout] fp32 (k = tap*Cin + c). */
 int vf_conv3x3_small_cin(const float* x, const float* w_kn, const float* bias, int N, int H, int W, int Cin, int Cout,
-                         float* y, vf_stream_t s);
+                         float* y, double* gn_sums /* optional [N][32][2]: GroupNorm(32) sums of y, Cout = 128 only */,
+                         vf_stream_t s);
 int vf_conv3x3_small_cout(const void* x, int x_dtype, const float* w_kn, const float* bias, int N, int H, int W, int Cin,
                           int Cout, float* y, vf_stream_t s);
 

@@ -423,6 +423,10 @@ def test_small_channel_convs(L):
     want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     got = L.conv3x3_small_cin(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w).cuda(), b.cuda())
     report("conv_in small_cin", got.permute(0, 3, 1, 2), want, 2e-5, 1e-5)
+    got = L.conv3x3_small_cin(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w).cuda(), b.cuda(), gn_groups=32)   # + fused GN sums
+    report("conv_in small_cin (+stats)", got.permute(0, 3, 1, 2), want, 2e-5, 1e-5)
+    o = want.permute(0, 2, 3, 1).reshape(3, 37 * 70, 32, 4)
+    report("conv_in fused gn sums", got._gn_sums[0].cpu(), torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1), 2e-2, 1e-5)
     w64, b64 = w[:64].contiguous(), b[:64].contiguous()
     got = L.conv3x3_small_cin(x.permute(0, 2, 3, 1).contiguous().cuda(), _w_kn(w64).cuda(), b64.cuda())
     report("conv_in small_cin cout64", got.permute(0, 3, 1, 2), want[:, :64], 2e-5, 1e-5)

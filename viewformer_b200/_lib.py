@@ -338,14 +338,20 @@ def s2d_coffs(c):
     return [((dy % 2) * 2 + (dx % 2)) * c for dy in (0, 1, 2) for dx in (0, 1, 2)]
 
 
-def conv3x3_small_cin(x, w_kn, bias):
-    """exact fp32 conv_in (Cin=3): x f32 [N,H,W,3], w_kn [27, Cout]."""
+def conv3x3_small_cin(x, w_kn, bias, gn_groups=0):
+    """exact fp32 conv_in (Cin=3): x f32 [N,H,W,3], w_kn [27, Cout].  ``gn_groups=32`` (Cout = 128) also accumulates the
+    GroupNorm statistics of the output and attaches them as ``_gn_sums`` (consumed by ``groupnorm``)."""
     lib = load(True)
     _dev(x, torch.float32)
     n, h, w, cin = x.shape
     cout = w_kn.shape[1]
     y = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
-    _check(lib.vf_conv3x3_small_cin(_p(x), _p(w_kn), _p(bias), n, h, w, cin, cout, _p(y), _stream()))
+    sums = None
+    if gn_groups == 32 and cout == 128:
+        sums = torch.empty((n, 32, 2), dtype=torch.float64, device=x.device)
+    _check(lib.vf_conv3x3_small_cin(_p(x), _p(w_kn), _p(bias), n, h, w, cin, cout, _p(y), _p(sums), _stream()))
+    if sums is not None:
+        y._gn_sums = (sums, 32)
     return y
 
 

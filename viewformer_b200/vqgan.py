@@ -279,7 +279,7 @@ class VQGAN:
         assert out_dtype == torch.float32
         if stride == 1 and not upsample and residual is None and x_opd_or_f32.dtype == torch.float32:
             if cw.small_cin:
-                return L.conv3x3_small_cin(x_opd_or_f32, cw.w_kn, cw.bias)
+                return L.conv3x3_small_cin(x_opd_or_f32, cw.w_kn, cw.bias, gn_groups=gn)
             if cw.small_cout:
                 return L.conv3x3_small_cout(x_opd_or_f32, cw.w_kn, cw.bias)
         pad = (1, 1) if stride == 1 else (0, 0)     # Downsample: pad (0,1,0,1) then VALID stride-2 (vqgan_th.py:45-49)
