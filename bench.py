@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--workload", default="generate", choices=["generate", "kvcache"],
                     help="generate = BASELINE configs[1] (default, the judged line); kvcache = configs[4]: 19-context KV-cached query decode")
     return ap.parse_args()
@@ -204,13 +205,23 @@ def run_b200(args):
     images_d, cams_d = images_h.to(dev), cams_h.to(dev)
     out_pin = torch.empty((B, IMG, IMG, 3), dtype=torch.uint8).pin_memory()
 
+    graphed = None
+    if not args.no_graph and not transformer.use_localization:
+        from viewformer_b200 import GraphedPredictions
+        graphed = GraphedPredictions(transformer, codebook, B, T_VIEWS)      # capture once; every step is one graph replay
+
     def step_resident():
+        if graphed is not None:
+            return graphed(images_d, cams_d)                  # device -> static device buffers (15.7 MB d2d) + replay
         return generate_batch_predictions(transformer, codebook, images_d, cams_d)
 
     def step_e2e():
-        img = images_pin.to(dev, non_blocking=True)
-        cam = cams_pin.to(dev, non_blocking=True)
-        r = generate_batch_predictions(transformer, codebook, img, cam)
+        if graphed is not None:
+            r = graphed(images_pin, cams_pin)                 # pinned host -> static device buffers + replay
+        else:
+            img = images_pin.to(dev, non_blocking=True)
+            cam = cams_pin.to(dev, non_blocking=True)
+            r = generate_batch_predictions(transformer, codebook, img, cam)
         out_pin.copy_(r["generated_images"], non_blocking=True)
         return r
 
@@ -247,7 +258,7 @@ def run_b200(args):
     w0 = time.monotonic()
     ms_total = timed(step_resident, args.steps)
     windows = [(w0, time.monotonic())]
-    launches = _lib.launch_count()
+    launches = _lib.launch_count() if graphed is None else graphed.launches_per_replay * args.steps
     clock_note = "timed region"
     if rank == 0 and sampler.proc is not None and sampler.count_in(*windows[0]) < 3:
         # a short timed region (K steps of ~30 ms) can end between two 100 ms nvidia-smi samples: keep the GPU on the
@@ -329,7 +340,8 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (15.7 MB images + 2.4 GB activations per step); no flush needed"},
         "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(in_bytes),
                 "d2h_bytes_per_step": int(out_pin.numel())},
-        "gpu_launches": launches // max(1, args.steps), "host_enqueue_ms_per_step": host_ms,
+        "gpu_launches": launches // max(1, args.steps), "launch_mode": "cuda graph replay (GraphedPredictions)" if graphed is not None else "eager",
+        "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,

@@ -245,6 +245,34 @@ def test_generate_end_to_end_matches_oracle():
     assert g16["generated_images"].dtype == torch.uint8 and list(g16["generated_images"].shape) == [2, 32, 32, 3]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_predictions_equal_eager(precision):
+    """CUDA-graph replay of generate() == the eager call, bit for bit, for successive different inputs (host and device)."""
+    from viewformer_b200 import VQGAN, MIGT, generate_batch_predictions, GraphedPredictions
+    vcfg = VQGANConfig(ch=64, ch_mult=[1, 2, 2, 2], attn_resolutions=[8], image_size=32, embed_dim=64, z_channels=64,
+                       n_embed=256, num_res_blocks=1)                       # stride 8 -> 4x4 tokens per view
+    tcfg = MIGTConfig(n_layer=2, n_head=4, d_model=128, sequence_size=4, n_embeddings=vcfg.n_embed, token_image_size=4,
+                      localization_weight="0")
+    vsd, tsd = synth.make_vqgan_state_dict(vcfg, 11), synth.make_migt_state_dict(tcfg, 12)
+    cb = VQGAN(vcfg, precision=precision).load_state_dict(vsd)
+    tr = MIGT(tcfg, precision=precision).load_state_dict(tsd)
+    gp = GraphedPredictions(tr, cb, 2, 3)
+    assert gp.launches_per_replay > 10
+    for seed, on_dev in ((13, False), (17, True), (19, False)):
+        images = synth.make_images_uint8(2, 3, size=32, seed=seed)
+        cams = synth.make_cameras(2, 3, seed=seed + 1)
+        want = generate_batch_predictions(tr, cb, images, cams)
+        got = gp(images.cuda() if on_dev else images.pin_memory(), cams.cuda() if on_dev else cams.pin_memory())
+        assert torch.equal(got["generated_codes"], want["generated_codes"])
+        assert torch.equal(got["generated_images"], want["generated_images"])
+        assert torch.allclose(got["generated_cameras"], want["generated_cameras"])
+    with pytest.raises(NotImplementedError):
+        GraphedPredictions(MIGT(MIGTConfig(n_layer=2, n_head=4, d_model=128, sequence_size=4, n_embeddings=256, token_image_size=4),
+                                precision=precision).load_state_dict(synth.make_migt_state_dict(
+                                    MIGTConfig(n_layer=2, n_head=4, d_model=128, sequence_size=4, n_embeddings=256, token_image_size=4), 12)),
+                           cb, 2, 3)
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 6e-2)])
 def test_migt_kv_cache_query_equals_full_forward(precision, tol):
     """BASELINE config 5 path: prefill the context once, then query-only passes reproduce the full forward's last view."""

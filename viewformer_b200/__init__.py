@@ -13,7 +13,7 @@ def __getattr__(name):   # lazy: importing the package must not require the buil
     if name in ("AutoModel", "AutoModelTH", "load_model"):
         from . import registry
         return getattr(registry, name)
-    if name in ("generate_batch_predictions", "generate_batch_predictions_multictx"):
+    if name in ("generate_batch_predictions", "generate_batch_predictions_multictx", "GraphedPredictions"):
         from . import generate
         return getattr(generate, name)
     raise AttributeError(name)
