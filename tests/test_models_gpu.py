@@ -74,7 +74,7 @@ def test_vqgan_fp32_full_size_vs_reference_golden(golden_dir):
     assert _stats("dec sub", dec[:, :, ::4, ::4], torch.from_numpy(g["dec"]))[0] < 3e-4
 
 
-@pytest.mark.parametrize("precision,pix_tol,mean_tol,code_frac", [("tf32", 2e-2, 2e-3, 0.97), ("bf16", 1.5e-1, 2e-2, 0.85)])
+@pytest.mark.parametrize("precision,pix_tol,mean_tol,code_frac", [("tf32", 2e-2, 2e-3, 0.99), ("bf16", 1e-1, 1e-2, 0.97)])
 def test_vqgan_tensor_core_path_full_size(golden_dir, precision, pix_tol, mean_tol, code_frac):
     g = np.load(os.path.join(golden_dir, "vqgan_full.npz"))
     cfg = VQGANConfig()
@@ -207,7 +207,7 @@ def test_migt_full_size_vs_oracle_golden(golden_dir):
     B, T = int(g["B"]), int(g["T"])
     codes, cams, ids = _migt_inputs(cfg, B, T, seed=5)
     want = torch.from_numpy(g["logits_last"])
-    for precision, tol, agree_min in (("fp32", 5e-4, 1.0), ("bf16", 1.5e-1, 0.9)):
+    for precision, tol, agree_min in (("fp32", 5e-4, 1.0), ("bf16", 5e-2, 0.93)):
         sd, model = _migt(cfg, 3, precision)
         last = model(dict(input_ids=ids, poses=cams), last_only=True)["logits"][:, 0]
         mx, mean = _stats(f"full logits {precision}", last[:1], want)
