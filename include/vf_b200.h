@@ -137,6 +137,14 @@ typedef struct {
        gn_sums double [images, gn_groups, 2] is zeroed and receives (sum, sum of squares) per image and group;
        an image = OH*OW consecutive rows (conv) or gn_rows_per_img rows (gemm).  Feed it to vf_groupnorm_finalize. */
     double* gn_sums; int gn_groups; int gn_rows_per_img;
+    /* optional: GroupNorm(+swish) of the INPUT applied while the operand sits in shared memory (3x3 stride-1 bf16 convs on
+       maps >= 32 rows tall, Cin % 64 == 0, Cout % 128 == 0 — the shapes of the wide-tile kernel; other shapes are rejected):
+       A then is the RAW activation (e.g. the bf16 output of the previous conv), norm_mean_rstd float [N, norm_groups, 2]
+       from vf_groupnorm_finalize, norm_gamma / norm_beta float [Cin].  Padding stays zero AFTER normalisation, as in
+       vqgan_th.py:69-78 (norm -> swish -> conv with padding=1).  Removes the separate vf_groupnorm_apply pass.
+       norm_swish: 0 = no activation, 1 = x / (1 + e^-x) in fp32 (ex2/rcp; bit-identical to vf_groupnorm_apply's bf16 output),
+       2 = packed bf16 h (1 + tanh h), h = x / 2 (one MUFU op per two elements). */
+    const float* norm_mean_rstd; const float* norm_gamma; const float* norm_beta; int norm_groups; int norm_swish;
 } vf_tc_gemm_t;
 int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
 

@@ -30,6 +30,12 @@ x = torch.randn((n, hw, hw, c), device="cuda").bfloat16(); w = (torch.randn((c, 
 b = torch.zeros(c, device="cuda"); res = torch.randn((n, hw, hw, c), device="cuda"); out = torch.empty((n, hw, hw, c), device="cuda")
 run("conv 128->128 @128^2 no residual", lambda: L.tc_conv(x, w, b, out=out))
 run("conv 128->128 @128^2 + residual", lambda: L.tc_conv(x, w, b, out=out, residual=res))
+mr = torch.zeros((n, 32, 2), device="cuda"); mr[..., 1] = 1.0
+ga, be = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+run("conv + residual + norm-on-load", lambda: L.tc_conv(x, w, b, out=out, residual=res, norm=(mr, ga, be, 32, True)))
+run("conv + norm-on-load (no residual)", lambda: L.tc_conv(x, w, b, out=out, norm=(mr, ga, be, 32, True)))
+run("conv + residual + norm-on-load, packed tanh swish", lambda: L.tc_conv(x, w, b, out=out, residual=res, norm=(mr, ga, be, 32, 2)))
+run("conv + residual + norm-on-load, no swish", lambda: L.tc_conv(x, w, b, out=out, residual=res, norm=(mr, ga, be, 32, 0)))
 A = torch.randn((20480, 3072), device="cuda").bfloat16(); B = torch.randn((768, 3072), device="cuda").bfloat16(); o2 = torch.empty((20480, 768), device="cuda")
 run("gemm 20480x768x3072", lambda: L.tc_gemm(A, B, o2, M=20480, N=768, K=3072, lda=3072, ldb=3072, ldc=768))
 

@@ -304,6 +304,40 @@ def test_tc_conv3x3_wide_tiles(L, n, H, W, cin, cout, res, out_bf16):
         report("wide conv fused gn sums", got._gn_sums[0].cpu(), ws, 0.5, 2e-3)
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 64, 64, 128, 128), (1, 40, 20, 64, 256), (2, 33, 9, 128, 128), (3, 32, 8, 256, 128)])
+def test_tc_conv_normalise_on_load(L, n, H, W, cin, cout):
+    """GroupNorm + swish applied to the conv operand inside the wide kernel == vf_groupnorm_apply followed by the conv, bit for
+    bit (same arithmetic on the same bf16 values); padding stays zero after normalisation (ragged tiles exercise the border)."""
+    xr = (torch.randn(n, H, W, cin, generator=g(H * W + cin)) * 1.3 + 0.4).cuda()
+    xb = xr.bfloat16()
+    o = xr.double().reshape(n, H * W, 32, cin // 32)
+    sums = torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1).contiguous()          # fp32-accurate statistics of the producer
+    ga, be = (1 + 0.1 * torch.randn(cin, generator=g(1))).cuda(), (0.1 * torch.randn(cin, generator=g(2))).cuda()
+    w = (torch.randn(cout, 9 * cin, generator=g(3)) / (9 * cin) ** 0.5).bfloat16().cuda()
+    b = torch.randn(cout, generator=g(4)).cuda()
+    res = torch.randn(n, H, W, cout, generator=g(5)).cuda()
+    assert L.conv_norm_fusable(xb, cout)
+    xb._gn_sums = (sums, 32)
+    a = L.groupnorm(xb, ga, be, swish=True, out_dtype=torch.bfloat16)
+    want = L.tc_conv(a, w, b, residual=res)
+    xb2 = xr.bfloat16()
+    xb2._gn_sums = (sums, 32)
+    got = L.tc_conv(xb2, w, b, residual=res, norm=(L.gn_mean_rstd(xb2), ga, be, 32, True))
+    torch.cuda.synchronize()
+    diff = (got - want).abs().max().item()
+    print(f"[norm-on-load n{n} {H}x{W} {cin}->{cout}] max |fused - (gn_apply; conv)| = {diff:.3e}")
+    assert torch.equal(got, want)
+    # and against an fp64 reference of norm -> swish -> conv (tolerance of the bf16 operand rounding)
+    xn = F.group_norm(xb.double().cpu().permute(0, 3, 1, 2), 32, ga.double().cpu(), be.double().cpu(), eps=1e-6)
+    mean = (sums[..., 0] / (H * W * cin // 32)).cpu()
+    ref = F.conv2d((xn * torch.sigmoid(xn)), w.double().cpu().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2), b.double().cpu(), padding=1)
+    report("norm-on-load vs fp64", got.permute(0, 3, 1, 2), ref + res.double().cpu().permute(0, 3, 1, 2), 5e-2, 3e-2)
+    with pytest.raises(Exception):      # shapes outside the wide kernel are rejected, not silently un-normalised
+        small = torch.randn(1, 16, 16, 64).bfloat16().cuda()
+        L.tc_conv(small, (torch.randn(128, 9 * 64) / 24).bfloat16().cuda(), None,
+                  norm=(torch.zeros(1, 32, 2, device="cuda"), torch.ones(64, device="cuda"), torch.zeros(64, device="cuda"), 32, True))
+
+
 # ----------------------------------------------------------------------------- codebook
 def test_vq_lookup_bit_exact_vs_reference_golden(L, golden_dir):
     import os

@@ -57,6 +57,8 @@ class TcGemm(C.Structure):
         ("residual", C.c_void_p), ("C_f32", C.c_void_p), ("C_bf16", C.c_void_p),
         ("ldc", C.c_int64), ("c_sb1", C.c_int64), ("c_sb2", C.c_int64),
         ("gn_sums", C.c_void_p), ("gn_groups", C.c_int), ("gn_rows_per_img", C.c_int),
+        ("norm_mean_rstd", C.c_void_p), ("norm_gamma", C.c_void_p), ("norm_beta", C.c_void_p),
+        ("norm_groups", C.c_int), ("norm_swish", C.c_int),
     ]
 
 
@@ -366,9 +368,35 @@ def conv3x3_small_cout(x, w_kn, bias):
     return y
 
 
+def conv_norm_fusable(x, cout):
+    """Shapes for which vf_tc_gemm can apply GroupNorm+swish to the conv INPUT on the fly (vf_tc_gemm_t.norm_*)."""
+    n, h, w, c = x.shape
+    return (os.environ.get("VF_TC_WIDE", "1") != "0" and x.dtype == torch.bfloat16
+            and c % 64 == 0 and cout % 128 == 0 and h >= 32 and w >= 8 and n * h * w * cout < 2 ** 31)
+
+
+def gn_mean_rstd(x, groups=32, eps=1e-6):
+    """(mean, rstd) float [N, groups, 2] of x [N,H,W,C] — from the statistics its producer fused, else one statistics pass."""
+    lib = load(True)
+    n, h, w, c = x.shape
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x.device)
+    fused = getattr(x, "_gn_sums", None)
+    if fused is not None and fused[1] == groups:
+        _check(lib.vf_groupnorm_finalize(_p(fused[0]), n * groups, C.c_double(float(h * w * (c // groups))), C.c_float(eps),
+                                         _p(stats), _stream()))
+    else:
+        if x.dtype != torch.float32:
+            raise LibraryError("gn_mean_rstd: a bf16 input needs fused statistics from its producer")
+        sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+        _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
+    return stats
+
+
 def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, residual=None, out=None,
-            out_dtype=torch.float32, out2=None, gn_groups=0):
-    """tcgen05 implicit-GEMM conv.  x [N,H,W,Ctot] bf16|f32 NHWC; w_nk [Cout, ntaps*Cin] (K-major, same dtype)."""
+            out_dtype=torch.float32, out2=None, gn_groups=0, norm=None):
+    """tcgen05 implicit-GEMM conv.  x [N,H,W,Ctot] bf16|f32 NHWC; w_nk [Cout, ntaps*Cin] (K-major, same dtype).
+    ``norm=(mean_rstd, gamma, beta, groups, swish)``: x is the RAW activation and GroupNorm(+swish) is applied to it inside the
+    kernel (only for ``conv_norm_fusable`` shapes)."""
     lib = load(True)
     _dev(x)
     n, h, w, ctot = x.shape
@@ -402,6 +430,11 @@ def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, 
     if gn_groups and gn_fusable(cout, gn_groups, n * oh * ow, oh * ow, cout):
         sums = torch.empty((n, gn_groups, 2), dtype=torch.float64, device=out.device)
         p.gn_sums, p.gn_groups = sums.data_ptr(), gn_groups
+    if norm is not None:
+        mr, gamma, beta, ngroups, swish = norm
+        _dev(mr, torch.float32); _dev(gamma, torch.float32); _dev(beta, torch.float32)
+        p.norm_mean_rstd, p.norm_gamma, p.norm_beta = mr.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+        p.norm_groups, p.norm_swish = ngroups, int(swish)      # 0 none, 1 = ex2/rcp fp32 (as vf_groupnorm_apply), 2 = packed bf16 tanh
     _check(lib.vf_tc_gemm(C.byref(p), _stream()))
     if sums is not None:
         out._gn_sums = (sums, gn_groups)

@@ -774,6 +774,10 @@ struct WideParams {
     __nv_bfloat16* C_bf16;     // [N, H, W, Cout] or null
     double* gn_sums;           // [N][groups][2] or null
     int gn_groups, gn_cpg;
+    const float2* norm_mr;     // optional GroupNorm(+swish) of the INPUT, applied to the halo tile in shared memory: (mean, rstd) [N][groups]
+    const float* norm_gamma;   // [Cin]
+    const float* norm_beta;    // [Cin]
+    int norm_groups, norm_cpg, norm_swish;
     int N, H, W, Cout, cin_blocks;
     int tiles_x, tiles_y, tiles_c, total_tiles;
     unsigned idesc;
@@ -784,15 +788,21 @@ struct WideParams {
 // wide kernels: 16 epilogue warps (4 per TMEM lane quarter, 64 accumulator columns each): with 2 warps per scheduler the register
 // epilogue ran at ~0.25 IPC per warp (ncu: stall_wait / short scoreboard) and held every tile for 10-20k cycles
 constexpr int WIDE_EPI_WARPS = 16;
+constexpr int WIDE_XFORM_WARPS = 8;           // conv only: GroupNorm + swish applied to the halo tile in place (normalise-on-load)
 constexpr int WIDE_THREADS = 64 + 32 * WIDE_EPI_WARPS;
 constexpr int WIDE_TW = 8, WIDE_TH = 32;
 constexpr int WIDE_HALO_ROWS = (WIDE_TW + 2) * (WIDE_TH + 2);          // 340 rows of 128 B
 constexpr int WIDE_HALO_BYTES = 44032;                                  // >= 340 * 128, multiple of 1024
 constexpr int WIDE_W_SLOTS = 8;
 constexpr int WIDE_W_BYTES = 128 * ROW_BYTES;                           // one (tap, channel block) weight tile
-constexpr int WIDE_SMEM = 2 * WIDE_HALO_BYTES + WIDE_W_SLOTS * WIDE_W_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int WIDE_SMEM = 2 * WIDE_HALO_BYTES + WIDE_W_SLOTS * WIDE_W_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*scale, shift*/;
 
-__global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
+// <16, false>: plain conv, 16 epilogue warps x 2 chunks; <8, true>: + 4 normalise-on-load warps, 8 epilogue warps x 4 chunks
+// (the thread count bounds the registers per thread: 704 threads left the epilogue 80 registers and spills)
+template <int kEpiWarps, bool kNorm>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps + (kNorm ? 32 * WIDE_XFORM_WARPS : 0), 1)
+tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
+    constexpr int CPW = 256 / ((kEpiWarps / 4) * 32);        // 32-pixel chunks per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* w_base = smem + 2 * WIDE_HALO_BYTES;
@@ -802,10 +812,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const 
     uint64_t* h_empty = h_full + 2;                     // [2]
     uint64_t* tmem_full_bar = h_empty + 2;              // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* h_ready = tmem_empty_bar + 2;             // [2]  halo tile normalised in place (norm mode)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 2);
+    float* ssf = reinterpret_cast<float*>(w_base + WIDE_W_SLOTS * WIDE_W_BYTES + 512);       // [2][64 scales | 64 shifts] per halo buffer
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr bool norm = kNorm;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmX)) : "memory");
@@ -816,8 +829,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const 
         for (int a = 0; a < 2; ++a) {
             mbar_init(&h_full[a], 1);
             mbar_init(&h_empty[a], 1);
+            mbar_init(&h_ready[a], WIDE_XFORM_WARPS);
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], WIDE_EPI_WARPS);
+            mbar_init(&tmem_empty_bar[a], kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -886,7 +900,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const 
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     if (dbg) c0 = clock64();
-                    mbar_wait(&h_full[hb], hph);
+                    mbar_wait(norm ? &h_ready[hb] : &h_full[hb], hph);
                     if (dbg) c_ops += clock64() - c0;
                     tcgen05_fence_after();
                     const uint32_t h_addr = smem_u32(smem + hb * WIDE_HALO_BYTES);
@@ -921,10 +935,78 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const 
                 d[0] = clock64() - c_start; d[1] = c_ops; d[2] = c_tmem; d[3] = c_tiles; d[4] = 1; d[5] = 0;
             }
         }
+    } else if (warp >= 2 + kEpiWarps) {
+        // ===================== normalise-on-load (4 warps): GroupNorm + swish of the raw halo tile, in place =====================
+        // The tile holds 340 rows (pixels of the (8+2) x (32+2) halo) of 64 bf16 channels, 128B-swizzled: physical 16-byte chunk pc
+        // of row r holds logical chunk pc ^ (r & 7) (the buffers are 1024-byte aligned).  Rows outside the image were zero-filled
+        // by TMA and must stay zero (the reference pads AFTER norm + swish, vqgan_th.py:69-78), so they are skipped.
+        if (norm) {
+            const int tid = threadIdx.x - (2 + kEpiWarps) * 32;
+            int hb = 0;
+            uint32_t hph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                int c0, ox0, oy0, img;
+                decode(t, c0, ox0, oy0, img);
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    if (tid < 64) {
+                        const int c = cb * 64 + tid;
+                        const float2 mr = __ldg(p.norm_mr + (img * p.norm_groups + c / p.norm_cpg));
+                        const float sc = mr.y * __ldg(p.norm_gamma + c);
+                        ssf[hb * 128 + tid] = sc;                                    // [hb][0..63] scale, [hb][64..127] shift
+                        ssf[hb * 128 + 64 + tid] = __ldg(p.norm_beta + c) - mr.x * sc;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * WIDE_XFORM_WARPS) : "memory");
+                    mbar_wait(&h_full[hb], hph);
+                    uint8_t* tile = smem + hb * WIDE_HALO_BYTES;
+                    const int pc = tid & 7;                      // this thread's physical 16-byte chunk in every row it visits
+                    // rows advance by 32, so (r & 7) and with it the LOGICAL chunk (= 8 channels) of this thread never change:
+                    // its 8 (scale, shift) pairs are read once per block, not once per row (that re-read was 4x the tile traffic
+                    // and competes with the MMA's operand reads for the same shared-memory port)
+                    const float* sc8 = ssf + hb * 128 + ((pc ^ ((tid >> 3) & 7)) << 3);
+                    const float4 s0 = *reinterpret_cast<const float4*>(sc8), s1 = *reinterpret_cast<const float4*>(sc8 + 4);
+                    const float4 h0 = *reinterpret_cast<const float4*>(sc8 + 64), h1 = *reinterpret_cast<const float4*>(sc8 + 68);
+                    const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll 2
+                    for (int r = tid >> 3; r < WIDE_HALO_ROWS; r += 4 * WIDE_XFORM_WARPS) {
+                        const int py = (r * 205) >> 11, px = r - py * (WIDE_TW + 2);       // r / 10 for r < 1029
+                        const int iy = oy0 - 1 + py, ix = ox0 - 1 + px;
+                        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+                        uint4* ptr = reinterpret_cast<uint4*>(tile + r * ROW_BYTES + pc * 16);
+                        const uint4 v = *ptr;
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float a = __uint_as_float(w[k] << 16), b = __uint_as_float(w[k] & 0xffff0000u);
+                            a = fmaf(a, scv[2 * k], shv[2 * k]);
+                            b = fmaf(b, scv[2 * k + 1], shv[2 * k + 1]);
+                            if (p.norm_swish == 1) {          // same arithmetic as vf_groupnorm_apply (bit-identical operand)
+                                a = __fdividef(a, 1.0f + __expf(-a));
+                                b = __fdividef(b, 1.0f + __expf(-b));
+                            }
+                            __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+                            w[k] = *reinterpret_cast<uint32_t*>(&o);
+                            if (p.norm_swish == 2) {
+                                // packed bf16: swish(y) = h * (1 + tanh(h)), h = y / 2 — ONE MUFU op per two elements instead of four
+                                uint32_t h, th;
+                                asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(w[k]), "r"(0x3f003f00u));
+                                asm("tanh.approx.bf16x2 %0, %1;" : "=r"(th) : "r"(h));
+                                asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(w[k]) : "r"(h), "r"(th));
+                            }
+                        }
+                        *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&h_ready[hb]);
+                    if (++hb == 2) { hb = 0; hph ^= 1; }
+                }
+            }
+        }
     } else {
-        // ===================== epilogue (warps 2..17): lane = output channel, register j = pixel =====================
+        // ===================== epilogue: lane = output channel, register j = pixel =====================
         const int quarter = warp & 3;                     // TMEM lanes [32q, 32q+32) = channels c0 + 32q + lane
-        const int grp = (warp - 2) >> 2;                  // pixels [64*grp, 64*grp + 64) of the patch = patch rows [8*grp, 8*grp + 8)
+        const int grp = (warp - 2) >> 2;                  // pixels [32*CPW*grp, +32*CPW) of the patch = patch rows [4*CPW*grp, +4*CPW)
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             int c0, ox0, oy0, img;
@@ -940,10 +1022,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const 
             const int rows_ok = p.H - oy0, cols_ok = p.W - ox0;          // valid rows / columns of this patch
             const bool full = rows_ok >= WIDE_TH && cols_ok >= WIDE_TW;
             const bool has_res = p.residual != nullptr;
-            // chunk c (0, 1) of this warp = patch rows [8*grp + 4c, +4), register j -> (row j/8, column j%8)
+            // chunk c of this warp = patch rows [4*CPW*grp + 4c, +4), register j -> (row j/8, column j%8)
             float rv[32];
             auto load_res = [&](int c) {
-                const int r0 = grp * 8 + c * 4;
+                const int r0 = grp * (4 * CPW) + c * 4;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     int ty = r0 + (j >> 3), tx = j & 7;
@@ -969,22 +1051,22 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_conv3x3_wide_kernel(const 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < CPW; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + grp * 64 + c * 32), r);
-                if (c == 1) {                             // all TMEM reads of this warp are done -> hand the accumulator stage back
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + grp * (32 * CPW) + c * 32), r);
+                if (c == CPW - 1) {                       // all TMEM reads of this warp are done -> hand the accumulator stage back
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                const int r0 = grp * 8 + c * 4;
+                const int r0 = grp * (4 * CPW) + c * 4;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     v[j] = __uint_as_float(r[j]) + bias;
                     if (has_res) v[j] += rv[j];
                 }
-                if (has_res && c == 0) load_res(1);       // the second chunk's residual rows fly while the first chunk is stored
+                if (has_res && c + 1 < CPW) load_res(c + 1);      // the next chunk's residual rows fly while this chunk is stored
                 if (full) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { gs += v[j]; gq = fmaf(v[j], v[j], gq); }
@@ -1304,6 +1386,7 @@ int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
                          NUM_EPI_WARPS * 32 * (kBlockN / 2 + 4) * 4 /*epilogue staging*/ + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(kStages % KGROUP == 0 && HALO_SLOTS % KGROUP == 0, "ring slots must form whole groups");
     static_assert(smem <= 232448, "shared memory budget");
+    static_assert((4 * WIDE_XFORM_WARPS) % 8 == 0, "transform rows must advance by a multiple of 8");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32, k2Cta>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1357,6 +1440,16 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
     prm.residual = q->residual;
     prm.C_f32 = q->C_f32;
     prm.C_bf16 = reinterpret_cast<__nv_bfloat16*>(q->C_bf16);
+    if (q->norm_mean_rstd) {
+        VF_CHECK_ARG(q->norm_gamma && q->norm_beta && q->norm_groups > 0 && q->Cin % q->norm_groups == 0,
+                     "vf_tc_gemm: fused input GroupNorm needs gamma, beta and a group count dividing Cin");
+        prm.norm_mr = reinterpret_cast<const float2*>(q->norm_mean_rstd);
+        prm.norm_gamma = q->norm_gamma;
+        prm.norm_beta = q->norm_beta;
+        prm.norm_groups = q->norm_groups;
+        prm.norm_cpg = q->Cin / q->norm_groups;
+        prm.norm_swish = q->norm_swish;
+    }
     prm.N = q->N; prm.H = q->H; prm.W = q->W; prm.Cout = q->Ncols; prm.cin_blocks = q->Cin / 64;
     prm.tiles_x = (q->W + WIDE_TW - 1) / WIDE_TW;
     prm.tiles_y = (q->H + WIDE_TH - 1) / WIDE_TH;
@@ -1377,7 +1470,8 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
     }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute(wide): %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
         configured = true;
     }
@@ -1388,7 +1482,8 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
     const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
-    tc_conv3x3_wide_kernel<<<grid, WIDE_THREADS, WIDE_SMEM, st>>>(prm);
+    if (prm.norm_mr) tc_conv3x3_wide_kernel<8, true><<<grid, 64 + 32 * 8 + 32 * WIDE_XFORM_WARPS, WIDE_SMEM, st>>>(prm);
+    else tc_conv3x3_wide_kernel<16, false><<<grid, 64 + 32 * 16, WIDE_SMEM, st>>>(prm);
     VF_CHECK_LAUNCH("vf_tc_gemm(wide conv)");
     return VF_OK;
 }
@@ -1494,6 +1589,8 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32, "vf_tc_gemm: bad dtype");
     VF_CHECK_ARG(q->bias_mode == VF_BIAS_NONE || q->bias, "vf_tc_gemm: bias pointer missing");
     if (conv_wide_eligible(q)) return launch_conv_wide(q, vf_s(s));
+    VF_CHECK_ARG(!q->norm_mean_rstd, "vf_tc_gemm: fused input GroupNorm is only available for 3x3 stride-1 bf16 convs on maps >= 32 rows "
+                                      "(Cin %% 64 == 0, Cout %% 128 == 0)");
     {
         long long m_flat = 0;
         if (gemm_wide_eligible(q, &m_flat)) return launch_gemm_wide(q, m_flat, vf_s(s));

@@ -16,6 +16,8 @@ precision's operand dtype.  No torch compute op is on the forward path (torch on
 import re
 from collections import OrderedDict
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -51,6 +53,10 @@ class VQGAN:
         self.config = load_config(config)
         self.prec = Precision(precision)
         self.bf16_edges = precision == "bf16"      # conv1 -> norm2 activations travel as bf16 (see _resblock)
+        # norm2 + swish fused into conv2's operand path (vf_tc_gemm_t.norm_*): bit-identical to the two-kernel path and tested, but
+        # with two halo buffers the in-place transform serialises with the TMA load (1.53-1.62 ms against 1.25 + 0.43 ms for
+        # conv + vf_groupnorm_apply at 288 x 128^2 x 128), so it is opt-in (VF_NORM_ON_LOAD=1) until a third buffer fits
+        self.norm_on_load = precision == "bf16" and os.environ.get("VF_NORM_ON_LOAD", "0") == "1"
         self.exact = Precision("fp32")
         self.device = torch.device(device)
         self.training = False
@@ -298,13 +304,20 @@ class VQGAN:
         edge = torch.bfloat16 if (self.bf16_edges and c1.tc and rbw["c2"].tc
                                   and L.gn_fusable(c1.cout, 32, n_ * h_ * w_, h_ * w_, c1.cout)) else torch.float32
         h = self._conv(c1, a, out_dtype=edge)
-        a = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"]))
+        if h.dtype == torch.bfloat16 and self.norm_on_load and L.conv_norm_fusable(h, rbw["c2"].cout):
+            # norm2 + swish applied to conv2's operand inside the kernel (while the halo tile sits in shared memory):
+            # the raw bf16 edge is read once by the conv instead of being read, normalised, written and read again
+            a, norm2 = h, (L.gn_mean_rstd(h), rbw["n2"][0], rbw["n2"][1], 32, True)
+        else:
+            a, norm2 = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"])), None
         if "sc" in rbw:
             n, hh, ww, c = x.shape
             xs = x if self.prec.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=self.prec.opd, normalize=False)
             res = linear(self.prec, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
         else:
             res = x
+        if norm2 is not None:
+            return L.tc_conv(a, rbw["c2"].w_nk, rbw["c2"].bias, residual=res, gn_groups=32, norm=norm2)
         return self._conv(rbw["c2"], a, residual=res)
 
     def _attn(self, aw, x):
