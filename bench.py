@@ -313,7 +313,7 @@ def run_b200(args):
                 peak_tf = peak_tf / 2
             # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
             # (profiles/r01_conv_tcgen05_ncu.md: 1.210 + 2.363 GB at 288 images), scaled to this launch's image count
-            traffic = (1.215308e9 + 2.362762e9) * n_img / 288.0 if args.precision == "bf16" else None
+            traffic = (1.224222e9 + 2.365118e9) * n_img / 288.0 if args.precision == "bf16" else None
             roof = {"kernel": "tc_conv3x3_wide_kernel: persistent tcgen05 implicit GEMM, 128 channels x 256 pixels per tile (3x3 conv 128->128 @128x128, %d images/launch)" % n_img,
                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "peak_source": peak_src, "launch_ms": sec * 1e3,
