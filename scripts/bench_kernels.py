@@ -72,6 +72,18 @@ gemm_case("lm head    2048x1024x768", 2048, 1024, 768)
 gn_case(288, 128, 128)
 gn_case(288, 64, 128)
 gn_case(32, 128, 128)
+# the two tiny-channel exact convolutions
+xin = torch.randn((288, 128, 128, 3), device=dev)
+win = torch.randn((27, 128), device=dev) / 5
+bin_ = torch.zeros(128, device=dev)
+ms = timeit(lambda: L.conv3x3_small_cin(xin, win, bin_, gn_groups=32))
+rows.append(("conv_in 3->128 @128^2 n=288 (+GN sums), fp32", ms, 2.0 * 288 * 128 * 128 * 27 * 128 / ms / 1e9, 288 * 128 * 128 * (12 + 512) / 1e9 / ms * 1e3))
+xo = torch.randn((32, 128, 128, 128), device=dev)
+wo = torch.randn((1152, 3), device=dev) / 30
+bo = torch.zeros(3, device=dev)
+ms = timeit(lambda: L.conv3x3_small_cout(xo, wo, bo))
+rows.append(("conv_out 128->3 @128^2 n=32, fp32", ms, 2.0 * 32 * 128 * 128 * 1152 * 3 / ms / 1e9, 32 * 128 * 128 * (512 + 12) / 1e9 / ms * 1e3))
+del xin, xo
 # attention pieces at B=32,H=12,S=640
 B, H, S, d = 32, 12, 640, 768
 qk = torch.randn((B, S, 2 * d), device=dev).bfloat16()
