@@ -294,7 +294,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: tcgen05 implicit-GEMM conv 128->128 3x3 at 128x128, the launch the encoder issues
     roof = None
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    if world == 1 or True:
+    if True:
         n_img = B * N_CTX
         opd = torch.bfloat16 if args.precision == "bf16" else torch.float32
         if args.precision != "fp32":

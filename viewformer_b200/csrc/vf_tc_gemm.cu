@@ -1,11 +1,16 @@
-// tcgen05 tensor-core GEMM and implicit-GEMM convolution for sm_100a.
+// tcgen05 tensor-core GEMMs and implicit-GEMM convolutions for sm_100a.  Three persistent kernels behind one entry point
+// (vf_tc_gemm picks by shape):
+//   tc_conv3x3_wide_kernel  3x3 stride-1 bf16 convs on maps >= 32 rows: weights on the M side, 256 pixels of one halo tile on
+//                           the N side, register epilogue (the benchmarked conv path, 0.83 of the measured bf16 peak)
+//   tc_gemm_wide_kernel     un-batched bf16 linear layers, same 128 x 256 tile shape
+//   tc_gemm_kernel          128 x (64|128) tiles: batched / causal GEMMs, tap-table and small-map convs, TF32, 2-CTA pairs
+// Common structure:
+//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  smem ring  ->  tcgen05.mma.cta_group::1 issued by ONE ELECTED thread
+//   (elect.sync, not lane == 0: see elect_one) with fp32 accumulators double-buffered in TMEM  ->  tcgen05.ld epilogue warps:
+//   alpha, bias, GELU, residual, GroupNorm statistics, f32/bf16 stores.
 //
-//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  smem ring (kStages x [A 128x128B | B BLOCK_N x128B])
-//   -> tcgen05.mma.cta_group::1 (one elected thread, fp32 accumulator in TMEM, M=128, N=BLOCK_N)
-//   -> tcgen05.ld epilogue (4 warps, one TMEM lane quarter each): alpha, bias, GELU, residual, f32/bf16 stores.
-//
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.
-// One CTA computes one 128 x BLOCK_N output tile.  GEMM operands are K-major; the convolution reads its A
+// tc_gemm_kernel warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.
+// A CTA walks 128 x BLOCK_N output tiles.  GEMM operands are K-major; the convolution reads its A
 // operand straight from the NHWC activation tensor with a 4-D tensor map: for every filter tap the box
 // [TN images x TH rows x TW cols x 64 channels] shifted by (dy,dx) lands in shared memory as a 128-row K-major
 // tile, out-of-image pixels zero-filled by TMA — no im2col buffer exists anywhere.
@@ -263,7 +268,7 @@ __host__ __device__ constexpr int operand_bytes(int stages, int stage_bytes, int
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 //   warp 0      TMA producer   — smem ring runs continuously across tiles
 //   warp 1      MMA issuer     — accumulates tile i into TMEM stage (i & 1) while the epilogue drains stage (i-1) & 1
-//   warps 2..5  epilogue       — TMEM -> registers (alpha, bias, GELU) -> per-warp smem staging -> TMEM stage released
+//   warps 2..9  epilogue       — TMEM -> registers (alpha, bias, GELU) -> per-warp smem staging -> TMEM stage released
 //                                -> coalesced row-wise residual loads / global stores
 // k2Cta: thread-block cluster of two CTAs = one `cta_group::2` MMA of M = 256: each CTA loads its own 128 A rows and HALF of the
 // B tile (the tensor cores of both SMs read B from both shared memories), accumulators stay in each CTA's own TMEM; the
