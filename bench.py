@@ -327,7 +327,7 @@ def run_b200(args):
             del x, w, o
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         vq_sd, migt_sd = codebook.state_dict(), transformer.state_dict()
         n = max(1, args.cpu_scenes)
         vps, sec, cores = cpu_reference_views_per_s(n, 1, 1, vq_sd, migt_sd, vcfg, tcfg)
