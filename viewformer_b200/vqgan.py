@@ -57,6 +57,8 @@ class VQGAN:
         # with two halo buffers the in-place transform serialises with the TMA load (1.53-1.62 ms against 1.25 + 0.43 ms for
         # conv + vf_groupnorm_apply at 288 x 128^2 x 128), so it is opt-in (VF_NORM_ON_LOAD=1) until a third buffer fits
         self.norm_on_load = precision == "bf16" and os.environ.get("VF_NORM_ON_LOAD", "0") == "1"
+        self.encoder_chunk = int(os.environ.get("VF_ENC_CHUNK", "0"))      # images per chunk of the high-resolution encoder levels (0: whole batch)
+        self.encoder_chunk_levels = int(os.environ.get("VF_ENC_CHUNK_LEVELS", "2"))
         self.exact = Precision("fp32")
         self.device = torch.device(device)
         self.training = False
@@ -345,24 +347,46 @@ class VQGAN:
         return out4
 
     # ------------------------------------------------------------------ encoder / decoder (NHWC)
+    def _encoder_level(self, lvw, h):
+        for i, rbw in enumerate(lvw["blocks"]):
+            h = self._resblock(rbw, h)
+            if lvw["attns"]:
+                h = self._attn(lvw["attns"][i], h)
+        if lvw["down"] is not None:
+            down = lvw["down"]
+            if down.tc and h.shape[1] % 2 == 0 and h.shape[2] % 2 == 0:
+                hs = L.groupnorm(h, None, None, swish=False, out_dtype=self.prec.opd, normalize=False, s2d=True)
+                h = self._conv(down, hs, stride=2)
+            else:
+                if down.tc:
+                    raise NotImplementedError("odd feature-map size in Downsample on the tensor-core path")
+                h = self._conv(down, h, stride=2)
+        return h
+
     def _encoder(self, x):
-        """Encoder.forward (vqgan_th.py:203-225); x f32 [N,H,W,3] -> f32 [N,h,w,z_channels]."""
+        """Encoder.forward (vqgan_th.py:203-225); x f32 [N,H,W,3] -> f32 [N,h,w,z_channels].
+        ``encoder_chunk`` > 0 runs conv_in and the first ``encoder_chunk_levels`` resolution levels in chunks of that many
+        images (images are independent), so that the bf16 activations between producer and consumer kernels stay inside the
+        126 MB L2 instead of streaming through HBM; the low-resolution levels run on the whole batch."""
         e = self._w["enc"]
-        h = self._conv(e["conv_in"], x)
-        for lvw in e["levels"]:
-            for i, rbw in enumerate(lvw["blocks"]):
-                h = self._resblock(rbw, h)
-                if lvw["attns"]:
-                    h = self._attn(lvw["attns"][i], h)
-            if lvw["down"] is not None:
-                down = lvw["down"]
-                if down.tc and h.shape[1] % 2 == 0 and h.shape[2] % 2 == 0:
-                    hs = L.groupnorm(h, None, None, swish=False, out_dtype=self.prec.opd, normalize=False, s2d=True)
-                    h = self._conv(down, hs, stride=2)
-                else:
-                    if down.tc:
-                        raise NotImplementedError("odd feature-map size in Downsample on the tensor-core path")
-                    h = self._conv(down, h, stride=2)
+        n = x.shape[0]
+        chunk, nlev = self.encoder_chunk, min(self.encoder_chunk_levels, len(e["levels"]))
+        if chunk > 0 and n > chunk:
+            parts = []
+            for i in range(0, n, chunk):
+                h = self._conv(e["conv_in"], x[i:i + chunk])
+                for lvw in e["levels"][:nlev]:
+                    h = self._encoder_level(lvw, h)
+                parts.append(h)
+            h = torch.cat(parts, 0)
+            if all(hasattr(p, "_gn_sums") for p in parts):          # fused GroupNorm statistics travel with the tensor
+                h._gn_sums = (torch.cat([p._gn_sums[0] for p in parts], 0), parts[0]._gn_sums[1])
+            rest = e["levels"][nlev:]
+        else:
+            h = self._conv(e["conv_in"], x)
+            rest = e["levels"]
+        for lvw in rest:
+            h = self._encoder_level(lvw, h)
         h = self._resblock(e["mid1"], h)
         h = self._attn(e["mida"], h)
         h = self._resblock(e["mid2"], h)
