@@ -42,8 +42,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenes", type=int, default=32, help="scenes per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
-    ap.add_argument("--cpu-scenes", type=int, default=8, help="scenes in the bounded CPU-baseline sample")
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "tf32", "fp32"],
+                    help="mixed (headline) = fp32-faithful encoder (bit-exact codebook indices) + bf16 tensor-core transformer / decoder; "
+                         "bf16 / tf32 = everything on the tensor-core path in that operand type; fp32 = exact CUDA-core path")
+    ap.add_argument("--also", default=None, help="comma list of further precisions timed for the side-by-side `value_by_precision` "
+                                                 "(default at N=1: the other three; at N>1: none)")
+    ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-budget-s", type=float, default=75.0, help="wall-time budget of the --impl reference arm (warm-up + steps)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--workload", default="generate", choices=["generate", "kvcache"],
@@ -123,41 +129,47 @@ def measured_peaks():
     return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(rel_path, scale):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the roofline kernel from the committed `ncu --set full` capture (metric dump
+    under profiles/), scaled by the launch's image count.  Read from the file, not a literal; None when the capture is absent."""
+    path = os.path.join(ROOT, rel_path)
+    if not os.path.exists(path):
+        return None, "no capture committed"
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        f = line.rstrip("\n").split(",")
+        if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and len(f) >= 3 and f[1] in unit:
+            tot += float(f[2]) * unit[f[1]]
+    return (tot * scale if tot else None), f"{rel_path} (ncu --set full of this kernel, 288 images/launch) x {scale:.3f}"
+
+
 # ------------------------------------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference_views_per_s(n_scenes, steps, warmup, vq_sd, migt_sd, vcfg, tcfg):
-    """The reference's algorithm (oracle restatement; the real torch/TF reference cannot travel to the GPU box) on the
-    host cores: generate_batch_predictions, 10 encodes + dense masked attention + full-sequence LM head as the
-    reference executes them (evaluate_transformer.py:97-146)."""
-    from oracle import vqgan_oracle as vo, migt_oracle as mo
-    # thread count: the fastest of a few candidates on a 2-image encode (all 128 logical CPUs of the GPU box
-    # oversubscribe MKL/oneDNN by 20x; the baseline should be the reference at its best)
-    probe = torch.rand(2, 3, IMG, IMG) * 2 - 1
-    best, cores = None, 1
-    with torch.no_grad():
-        for nt in sorted({min(os.cpu_count(), c) for c in (8, 16, 32, 64)}):
-            torch.set_num_threads(nt)
-            vo.encode(vq_sd, vcfg, probe[:1])
+def cpu_threads():
+    """All 100+ logical CPUs of the GPU box oversubscribe oneDNN/MKL (measured in round 1: 16-32 threads are fastest)."""
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+class CpuReference:
+    """The reference's algorithm on the host cores (oracle restatement; the real torch/TF reference cannot travel to the GPU box):
+    generate_batch_predictions with 10 encodes + dense masked attention + full-sequence LM head, as the reference executes them
+    (evaluate_transformer.py:97-146).  Every call is ONE scene-batch; callers bound the number of calls by wall time."""
+
+    def __init__(self, vq_sd, migt_sd, vcfg, tcfg):
+        from oracle import vqgan_oracle as vo, migt_oracle as mo
+        self.mo = mo
+        self.tcfg = tcfg
+        self.cores = cpu_threads()
+        torch.set_num_threads(self.cores)
+        self.fwd = lambda d: mo.forward(migt_sd, tcfg, d, use_localization=False)
+        self.enc = lambda x: vo.encode(vq_sd, vcfg, x)[2]
+        self.dec = lambda c: vo.decode_code(vq_sd, vcfg, c)
+
+    def __call__(self, images, cams):
+        with torch.no_grad():
             t0 = time.perf_counter()
-            vo.encode(vq_sd, vcfg, probe)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, cores = dt, nt
-    torch.set_num_threads(cores)
-    images, cams = synth_inputs(n_scenes, 777)
-    fwd = lambda d: mo.forward(migt_sd, tcfg, d, use_localization=False)
-    enc = lambda x: vo.encode(vq_sd, vcfg, x)[2]
-    dec = lambda c: vo.decode_code(vq_sd, vcfg, c)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            im, cm = (images[:1], cams[:1]) if i < warmup else (images, cams)      # warm-up on one scene only
-            t0 = time.perf_counter()
-            mo.generate_batch_predictions(fwd, enc, dec, tcfg, im, cm, use_localization=False)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    total = sum(times)
-    return n_scenes * len(times) / total, total / len(times), cores
+            out = self.mo.generate_batch_predictions(self.fwd, self.enc, self.dec, self.tcfg, images, cams, use_localization=False)
+            return out, time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -168,21 +180,72 @@ def run_reference(args):
     from oracle import synth
     vcfg, tcfg = VQGANConfig(), MIGTConfig(localization_weight="0")
     vq_sd, migt_sd = synth.make_vqgan_state_dict(vcfg, 0), synth.make_migt_state_dict(tcfg, 0)
-    n = max(1, args.cpu_scenes)
-    vps, sec, cores = cpu_reference_views_per_s(n, args.steps, min(args.warmup, 1), vq_sd, migt_sd, vcfg, tcfg)
-    sample = f"{n} scenes x {T_VIEWS} views per step (bounded sample of the {args.scenes}-scene workload), torch-CPU fp32 oracle"
+    ref = CpuReference(vq_sd, migt_sd, vcfg, tcfg)
+    n = 1                                            # scenes per step: a bounded sample of the 32-scene workload
+    images, cams = synth_inputs(max(n, 2), 777)
+    t_start = time.perf_counter()
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        ref(images[:n], cams[:n])
+    times = []
+    for i in range(args.steps):
+        _, dt = ref(images[:n], cams[:n])
+        times.append(dt)
+        if time.perf_counter() - t_start + dt > args.cpu_budget_s:      # the next step would not fit the wall-time budget
+            break
+    total = sum(times)
+    vps, sec = n * len(times) / total, total / len(times)
+    sample = (f"{n} scene x {T_VIEWS} views per step (bounded sample of the {args.scenes}-scene workload), {len(times)} of {args.steps} requested steps "
+              f"inside the {args.cpu_budget_s:.0f} s wall budget, torch-CPU fp32 oracle of the reference algorithm")
     print(json.dumps({
         "impl": "reference", "metric": "novel views/sec (128x128, 9-ctx)", "value": vps, "unit": "views/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": len(times), "steps_requested": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "interiornet-transformer generate(), 9 context views (BASELINE configs[1])", "scenes_per_step": n,
                    "localization": False},
-        "cpu_baseline": {"value": vps, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": vps, "unit": "views/s", "cores": ref.cores, "kind": "port", "sample": sample},
         "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
+def model_pair(precision, vcfg, tcfg, dev, seed=0):
+    """(codebook, transformer) of one precision mode.  ``mixed`` pairs the exact-encoder VQGAN with the bf16 transformer."""
+    from viewformer_b200 import VQGAN, MIGT
+    codebook = VQGAN(vcfg, precision=precision, device=dev).init_weights(seed)
+    transformer = MIGT(tcfg, precision="bf16" if precision == "mixed" else precision, device=dev).init_weights(seed)
+    return codebook, transformer
+
+
+def parity_block(codebook, transformer, out_timed, images_d, cams_d, vcfg, tcfg, dev):
+    """Outside the timed region, on the bench's own inputs: the timed mode against the exact fp32 CUDA-core path.
+    (a) encoder codes of all scenes (bit-exact bar), (b) transformer argmax on identical context codes, (c) decoded uint8 pixels
+    on identical codes, (d) the whole timed pipeline's generated codes against the exact pipeline's."""
+    from viewformer_b200 import VQGAN, MIGT, _lib
+    B = images_d.shape[0]
+    xvq = VQGAN(vcfg, precision="fp32", device=dev).load_state_dict(codebook.state_dict())
+    xtr = MIGT(tcfg, precision="fp32", device=dev).load_state_dict(transformer.state_dict())
+    codes_t = codebook.encode_u8(images_d, first_views=N_CTX)
+    codes_x = xvq.encode_u8(images_d, first_views=N_CTX)
+    cams, _ = _lib.cameras_prepare(cams_d.contiguous(), tcfg.augment_poses == "relative")
+    ctx = codes_x.reshape(B, N_CTX, 8, 8)
+    gen_t = transformer.generate_codes(ctx, cams)
+    gen_x = xtr.generate_codes(ctx, cams)
+    px_t = codebook.decode_code_u8(gen_x).int()
+    px_x = xvq.decode_code_u8(gen_x).int()
+    torch.cuda.synchronize()
+    pd = (px_t - px_x).abs()
+    blk = {
+        "reference_path": "fp32 CUDA-core path (vf_simt_gemm / exact kernels; bit-exact against the CPU oracle in tests/)",
+        "code_mismatches": int((codes_t != codes_x).sum()), "codes_compared": int(codes_x.numel()),
+        "generated_code_mismatches_same_context": int((gen_t != gen_x).sum()), "generated_codes_compared": int(gen_x.numel()),
+        "pixel_max_abs_diff_u8_same_codes": int(pd.max()), "pixel_mean_abs_diff_u8_same_codes": float(pd.float().mean()),
+        "pipeline_generated_code_mismatches": int((out_timed["generated_codes"] != gen_x).sum()),
+    }
+    del xvq, xtr
+    return blk, codes_x
+
+
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,11 +256,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    from viewformer_b200 import VQGAN, MIGT, generate_batch_predictions, _lib
+    from viewformer_b200 import generate_batch_predictions, _lib
     from viewformer_b200.config import VQGANConfig, MIGTConfig
     vcfg, tcfg = VQGANConfig(), MIGTConfig(localization_weight="0")
-    codebook = VQGAN(vcfg, precision=args.precision, device=dev).init_weights(0)
-    transformer = MIGT(tcfg, precision=args.precision, device=dev).init_weights(0)
+    codebook, transformer = model_pair(args.precision, vcfg, tcfg, dev)
 
     B = args.scenes
     images_h, cams_h = synth_inputs(B, 1234 + rank)
@@ -205,31 +267,33 @@ def run_b200(args):
     images_d, cams_d = images_h.to(dev), cams_h.to(dev)
     out_pin = torch.empty((B, IMG, IMG, 3), dtype=torch.uint8).pin_memory()
 
-    graphed, graph_note = None, "eager"
-    if not args.no_graph and not transformer.use_localization:
-        from viewformer_b200 import GraphedPredictions
-        try:
-            graphed = GraphedPredictions(transformer, codebook, B, T_VIEWS)  # capture once; every step is one graph replay
-            graph_note = "cuda graph replay (GraphedPredictions)"
-        except Exception as e:                                               # same kernels either way: only the launch mode changes
-            print(f"[bench] CUDA graph capture failed ({e!r}); launching eagerly", file=sys.stderr)
-            torch.cuda.synchronize()
-            graph_note = "eager (graph capture failed)"
+    def make_steps(cb, tr):
+        graphed, note = None, "eager"
+        if not args.no_graph and not tr.use_localization:
+            from viewformer_b200 import GraphedPredictions
+            try:
+                graphed = GraphedPredictions(tr, cb, B, T_VIEWS)          # capture once; every step is one graph replay
+                note = "cuda graph replay (GraphedPredictions)"
+            except Exception as e:                                        # same kernels either way: only the launch mode changes
+                print(f"[bench] CUDA graph capture failed ({e!r}); launching eagerly", file=sys.stderr)
+                torch.cuda.synchronize()
+                note = "eager (graph capture failed)"
 
-    def step_resident():
-        if graphed is not None:
-            return graphed(images_d, cams_d)                  # device -> static device buffers (15.7 MB d2d) + replay
-        return generate_batch_predictions(transformer, codebook, images_d, cams_d)
+        def resident():
+            if graphed is not None:
+                return graphed(images_d, cams_d)              # device -> static device buffers (15.7 MB d2d) + replay
+            return generate_batch_predictions(tr, cb, images_d, cams_d)
 
-    def step_e2e():
-        if graphed is not None:
-            r = graphed(images_pin, cams_pin)                 # pinned host -> static device buffers + replay
-        else:
-            img = images_pin.to(dev, non_blocking=True)
-            cam = cams_pin.to(dev, non_blocking=True)
-            r = generate_batch_predictions(transformer, codebook, img, cam)
-        out_pin.copy_(r["generated_images"], non_blocking=True)
-        return r
+        def e2e():
+            if graphed is not None:
+                r = graphed(images_pin, cams_pin)             # pinned host -> static device buffers + replay
+            else:
+                r = generate_batch_predictions(tr, cb, images_pin.to(dev, non_blocking=True), cams_pin.to(dev, non_blocking=True))
+            out_pin.copy_(r["generated_images"], non_blocking=True)
+            return r
+        return resident, e2e, graphed, note
+
+    step_resident, step_e2e, graphed, graph_note = make_steps(codebook, transformer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -281,6 +345,8 @@ def run_b200(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    out_timed = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in step_resident().items()}
+    torch.cuda.synchronize()
 
     views = world * B * args.steps
     value = views / (ms_total / 1e3)
@@ -291,64 +357,97 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: tcgen05 implicit-GEMM conv 128->128 3x3 at 128x128, the launch the encoder issues
-    roof = None
-    peak_tf, peak_hbm, peak_src = measured_peaks()
-    if True:
-        n_img = B * N_CTX
-        opd = torch.bfloat16 if args.precision == "bf16" else torch.float32
-        if args.precision != "fp32":
-            x = torch.randn((n_img, IMG, IMG, 128), device=dev).to(opd)
-            w = (torch.randn((128, 9 * 128), device=dev) / 34.0).to(opd)
-            b = torch.zeros(128, device=dev)
-            o = torch.empty((n_img, IMG, IMG, 128), device=dev)
-            for _ in range(3):
-                _lib.tc_conv(x, w, b, out=o)
-            reps = 5
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                _lib.tc_conv(x, w, b, out=o)
-            e1.record()
-            torch.cuda.synchronize()
-            sec = e0.elapsed_time(e1) / 1e3 / reps
-            flops = 2.0 * n_img * IMG * IMG * 128 * 9 * 128          # 2*M*N*K of the implicit GEMM
-            ach = flops / sec / 1e12
-            if args.precision == "tf32":
-                peak_tf = peak_tf / 2
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu capture
-            # (profiles/r01_conv_tcgen05_ncu.md: 1.210 + 2.363 GB at 288 images), scaled to this launch's image count
-            traffic = (1.224222e9 + 2.365118e9) * n_img / 288.0 if args.precision == "bf16" else None
-            roof = {"kernel": "tc_conv3x3_wide_kernel: persistent tcgen05 implicit GEMM, 128 channels x 256 pixels per tile (3x3 conv 128->128 @128x128, %d images/launch)" % n_img,
-                    "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                    "peak_source": peak_src, "launch_ms": sec * 1e3,
-                    "algorithmic_bytes_per_launch": n_img * IMG * IMG * 128 * (opd.itemsize + 4)}
-            del x, w, o
+    # ---- in-run parity of the timed mode (rank 0, outside the timed region)
+    parity, codes_exact = None, None
+    if not args.no_parity:
+        parity, codes_exact = parity_block(codebook, transformer, out_timed, images_d, cams_d, vcfg, tcfg, dev)
 
+    # ---- the other precisions, side by side (same inputs, same step, `steps` timed replays each)
+    also = args.also if args.also is not None else (",".join(p for p in ("bf16", "tf32", "fp32") if p != args.precision) if world == 1 else "")
+    by_prec = {args.precision: {"value": value / world, "ms_per_step": ms_total / args.steps,
+                                "code_mismatches_vs_fp32": None if parity is None else parity["code_mismatches"]}}
+    if world == 1:
+        for pname in [x for x in also.split(",") if x]:
+            cb2, tr2 = model_pair(pname, vcfg, tcfg, dev)
+            res2, _, g2, _ = make_steps(cb2, tr2)
+            for _ in range(3):
+                res2()
+            ms2 = timed(res2, args.steps)
+            o2 = res2()
+            entry = {"value": B * args.steps / (ms2 / 1e3), "ms_per_step": ms2 / args.steps}
+            if codes_exact is not None:
+                entry["code_mismatches_vs_fp32"] = int((cb2.encode_u8(images_d, first_views=N_CTX) != codes_exact).sum())
+            by_prec[pname] = entry
+            del cb2, tr2, res2, g2, o2
+            torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel of the TENSOR-CORE conv path: tcgen05 implicit-GEMM conv 128->128 3x3 at 128x128
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    n_img = B * N_CTX
+    x = torch.randn((n_img, IMG, IMG, 128), device=dev).to(torch.bfloat16)
+    w = (torch.randn((128, 9 * 128), device=dev) / 34.0).to(torch.bfloat16)
+    b = torch.zeros(128, device=dev)
+    o = torch.empty((n_img, IMG, IMG, 128), device=dev)
+    for _ in range(3):
+        _lib.tc_conv(x, w, b, out=o)
+    reps = 5
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.tc_conv(x, w, b, out=o)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / reps
+    flops = 2.0 * n_img * IMG * IMG * 128 * 9 * 128          # 2*M*N*K of the implicit GEMM
+    ach = flops / sec / 1e12
+    traffic, traffic_src = ncu_traffic("profiles/r01_conv_wide_ncu_nores_metrics.csv", n_img / 288.0)
+    roof = {"kernel": "tc_conv3x3_wide_kernel: persistent tcgen05 implicit GEMM, 128 channels x 256 pixels per tile (3x3 conv 128->128 @128x128, "
+                      "%d images/launch, bf16 operands)" % n_img,
+            "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": sec * 1e3,
+            "algorithmic_bytes_per_launch": n_img * IMG * IMG * 128 * (2 + 4)}
+    del x, w, o
+
+    # ---- CPU baseline: the oracle on the first scenes of THIS run's inputs; its outputs double as a parity check of the timed pipeline
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
-        vq_sd, migt_sd = codebook.state_dict(), transformer.state_dict()
-        n = max(1, args.cpu_scenes)
-        vps, sec, cores = cpu_reference_views_per_s(n, 1, 1, vq_sd, migt_sd, vcfg, tcfg)
-        cpu = {"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
-               "sample": f"{n} scenes x {T_VIEWS} views, 1 timed pass after a 1-scene warm-up, best-of-{{8,16,32,64}} threads, torch-CPU fp32 oracle of the reference algorithm "
-                         f"(10 encodes, dense masked attention, full LM head)"}
+        ref = CpuReference(codebook.state_dict(), transformer.state_dict(), vcfg, tcfg)
+        n = max(1, min(args.cpu_scenes, B))
+        ref(images_h[:1], cams_h[:1])                                 # warm-up: one scene
+        want, dt = ref(images_h[:n], cams_h[:n])
+        cpu = {"value": n / dt, "unit": "views/s", "cores": ref.cores, "kind": "port",
+               "sample": f"the first {n} of the {B} bench scenes x {T_VIEWS} views, 1 timed pass after a 1-scene warm-up, {ref.cores} threads, torch-CPU fp32 "
+                         f"oracle of the reference algorithm (10 encodes, dense masked attention, full LM head)"}
+        if parity is not None:
+            got_codes = codebook.encode_u8(images_d[:n].contiguous(), first_views=N_CTX).reshape(n, N_CTX, 8, 8).cpu()
+            parity["oracle_scenes"] = n
+            parity["oracle_code_mismatches"] = int((got_codes != want["codes"][:, :N_CTX]).sum())
+            parity["oracle_codes_compared"] = int(got_codes.numel())
+            parity["oracle_generated_code_mismatches"] = int((out_timed["generated_codes"][:n].cpu() != want["generated_codes"]).sum())
+            pdiff = (out_timed["generated_images"][:n].cpu().int() - want["generated_images"].int()).abs()
+            parity["oracle_pixel_max_abs_diff_u8"] = int(pdiff.max())
+            parity["oracle_pixel_mean_abs_diff_u8"] = float(pdiff.float().mean())
 
     in_bytes = images_pin.numel() + cams_pin.numel() * 4
     print(json.dumps({
         "metric": "novel views/sec (128x128, 9-ctx)", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "vs_baseline": None, "dtype": {"mixed": "f32 encoder (bit-exact codes) + bf16 transformer/decoder"}.get(args.precision, args.precision),
+        "data": "synthetic",
         "config": {"workload": "interiornet-transformer generate(), 9 context views, batch 32 scenes per GPU (BASELINE configs[1]): "
                                "uint8 images -> VQ-encode 9 ctx -> MIGT -> argmax -> VQ-decode -> uint8 view",
-                   "scenes_per_gpu": B, "views": T_VIEWS, "image": IMG, "localization": False, "parallelism": f"dp{world} (independent shards)",
-                   "l2": "inputs larger than L2 (15.7 MB images + 2.4 GB activations per step); no flush needed"},
+                   "precision": args.precision, "scenes_per_gpu": B, "views": T_VIEWS, "image": IMG, "localization": False,
+                   "parallelism": f"dp{world} (independent shards)",
+                   "encodes_per_scene": "9 (the reference also encodes the target view and discards it; cpu_baseline runs the reference's 10)",
+                   "l2": "inputs larger than L2 (15.7 MB images + >2 GB activations per step); no flush needed"},
         "e2e": {"value": e2e_value, "unit": "views/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(in_bytes),
                 "d2h_bytes_per_step": int(out_pin.numel())},
         "gpu_launches": launches // max(1, args.steps), "launch_mode": graph_note,
         "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
+        "parity": parity,
+        "value_by_precision": by_prec,
         "roofline": roof,
         "cpu_baseline": cpu,
     }))

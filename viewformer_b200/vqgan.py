@@ -51,12 +51,17 @@ class VQGAN:
         if config is None:
             config = VQGANConfig(**config_overrides)
         self.config = load_config(config)
-        self.prec = Precision(precision)
-        self.bf16_edges = precision == "bf16"      # conv1 -> norm2 activations travel as bf16 (see _resblock)
+        # ``mixed``: the encoder (whose output feeds the bit-exact codebook argmin) runs in the fp32-faithful ``exact`` arithmetic,
+        # the decoder (pixels within a tolerance) on the bf16 tensor-core path.  One precision name otherwise serves both halves.
+        enc_name, dec_name = {"mixed": (os.environ.get("VF_EXACT_ENCODER", "fp32"), "bf16")}.get(precision, (precision, precision))
+        self.precision = precision
+        self.enc_prec, self.dec_prec = Precision(enc_name), Precision(dec_name)
+        self.prec = self.dec_prec                  # quantizer / glue policy
+        self.bf16_edges = True                     # bf16 halves only: conv1 -> norm2 activations travel as bf16 (see _resblock)
         # norm2 + swish fused into conv2's operand path (vf_tc_gemm_t.norm_*): bit-identical to the two-kernel path and tested, but
         # with two halo buffers the in-place transform serialises with the TMA load (1.53-1.62 ms against 1.25 + 0.43 ms for
         # conv + vf_groupnorm_apply at 288 x 128^2 x 128), so it is opt-in (VF_NORM_ON_LOAD=1) until a third buffer fits
-        self.norm_on_load = precision == "bf16" and os.environ.get("VF_NORM_ON_LOAD", "0") == "1"
+        self.norm_on_load = os.environ.get("VF_NORM_ON_LOAD", "0") == "1"      # bf16 halves only
         self.encoder_chunk = int(os.environ.get("VF_ENC_CHUNK", "0"))      # images per chunk of the high-resolution encoder levels (0: whole batch)
         self.encoder_chunk_levels = int(os.environ.get("VF_ENC_CHUNK_LEVELS", "2"))
         self.exact = Precision("fp32")
@@ -74,8 +79,9 @@ class VQGAN:
         if device.type != "cuda":
             raise L.LibraryError("viewformer_b200.VQGAN runs on CUDA (sm_100a) only; there is no CPU path")
         if self._sd is not None and device != self.device:
+            sd = self.state_dict()                 # includes the live quantizer buffers (EMA updates made in train() mode)
             self.device = device
-            self.load_state_dict(self._sd)
+            self.load_state_dict(sd)
         self.device = device
         return self
 
@@ -161,6 +167,9 @@ class VQGAN:
     def init_weights(self, seed=0):
         """Random initialisation with the reference's initialisers: torch Conv2d default U(+-1/sqrt(fan_in)) for
         weights and biases, GroupNorm 1/0, codebook U(+-sqrt 3) (utils_th.py:17), EMA buffers 0."""
+        return self.load_state_dict(self._initial_state(seed))
+
+    def _initial_state(self, seed=0):
         g = torch.Generator().manual_seed(int(seed))
         sd = OrderedDict()
         shapes = self.param_shapes()
@@ -178,7 +187,7 @@ class VQGAN:
             else:
                 w = shapes[k[:-4] + "weight"]
                 sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / (w[1] * w[2] * w[3]) ** 0.5
-        return self.load_state_dict(sd)
+        return sd
 
     def load_state_dict(self, state_dict, strict=True):
         """Strict key check with the reference's ignore patterns (vqgan_th.py:346-359)."""
@@ -189,6 +198,14 @@ class VQGAN:
                 raise RuntimeError(f"Missing keys: {want - got}")
             if got - want:
                 raise RuntimeError(f"Unexpected keys: {got - want}")
+        else:                                      # non-strict: unknown keys dropped, missing keys keep their current (or initial) value
+            shapes = self.param_shapes()
+            sd = OrderedDict((k, v) for k, v in sd.items() if k in shapes)
+            missing = [k for k in shapes if k not in sd]
+            if missing:
+                cur = self.state_dict() if self._sd is not None else VQGAN(self.config, precision=self.precision, device=self.device)._initial_state(0)
+                for k in missing:
+                    sd[k] = cur[k]
         self._sd = OrderedDict((k, torch.as_tensor(v).detach().to("cpu").clone()) for k, v in sd.items())
         self._build()
         return self
@@ -206,9 +223,10 @@ class VQGAN:
     # ------------------------------------------------------------------ weight preparation (load time only)
     def _build(self):
         L.load(require_device=True)
-        sd, prec, dev = self._sd, self.prec, self.device
+        sd, dev = self._sd, self.device
         cfg = self.config
         w = {}
+        prec = None        # set to the half being built (encoder / decoder) before its weights are laid out
 
         def gn(n):
             return (sd[n + ".weight"].to(dev, torch.float32).contiguous(), sd[n + ".bias"].to(dev, torch.float32).contiguous())
@@ -221,7 +239,7 @@ class VQGAN:
             return Linear(wt.reshape(wt.shape[0], wt.shape[1]), sd[n + ".bias"], p or prec, dev)
 
         def rb(n):
-            d = dict(n1=gn(n + ".norm1"), c1=conv(n + ".conv1"), n2=gn(n + ".norm2"), c2=conv(n + ".conv2"))
+            d = dict(n1=gn(n + ".norm1"), c1=conv(n + ".conv1"), n2=gn(n + ".norm2"), c2=conv(n + ".conv2"), prec=prec)
             if (n + ".nin_shortcut.weight") in sd:
                 d["sc"] = lin(n + ".nin_shortcut")
             return d
@@ -231,11 +249,12 @@ class VQGAN:
             c = wq.shape[0]
             qk = Linear(torch.cat([wq.reshape(c, c), wk.reshape(c, c)], 0), torch.cat([sd[n + ".q.bias"], sd[n + ".k.bias"]]), prec, dev)
             return dict(norm=gn(n + ".norm"), qk=qk, v=Linear(wv.reshape(c, c), sd[n + ".v.bias"], prec, dev),
-                        proj=lin(n + ".proj_out"), c=c)
+                        proj=lin(n + ".proj_out"), c=c, prec=prec)
 
         nres = len(cfg.ch_mult)
         res = [cfg.image_size // 2 ** i for i in range(nres)]
-        enc = dict(conv_in=conv("encoder.conv_in", exact=True), levels=[])
+        prec = self.enc_prec
+        enc = dict(conv_in=conv("encoder.conv_in", exact=True), levels=[], prec=prec)
         for lv in range(nres):
             blocks, attns = [], []
             for b in range(cfg.num_res_blocks):
@@ -246,8 +265,9 @@ class VQGAN:
             enc["levels"].append(dict(blocks=blocks, attns=attns, down=down))
         enc.update(mid1=rb("encoder.mid.block_1"), mida=at("encoder.mid.attn_1"), mid2=rb("encoder.mid.block_2"),
                    norm_out=gn("encoder.norm_out"), conv_out=conv("encoder.conv_out"))
+        prec = self.dec_prec
         dec = dict(conv_in=conv("decoder.conv_in"), mid1=rb("decoder.mid.block_1"), mida=at("decoder.mid.attn_1"),
-                   mid2=rb("decoder.mid.block_2"), levels={})
+                   mid2=rb("decoder.mid.block_2"), levels={}, prec=prec)
         for lv in reversed(range(nres)):
             blocks, attns = [], []
             for b in range(cfg.num_res_blocks + 1):
@@ -263,7 +283,7 @@ class VQGAN:
         w["post_quant_conv"] = lin("post_quant_conv", self.exact)
         emb = sd["quantize.embeddings"].to(dev, torch.float32).contiguous()             # [D,K] (utils_th.py:17-18)
         et, esq = L.vq_prepare_codebook(emb)
-        w["q"] = dict(emb=emb, et=et, esq=esq, et3=L.vq_split3(et, True) if prec.use_tc else None,
+        w["q"] = dict(emb=emb, et=et, esq=esq, et3=L.vq_split3(et, True) if self.prec.use_tc else None,
                       cs=sd["quantize.ema_cluster_size_hidden"].to(dev, torch.float32).contiguous(),
                       dw=sd["quantize.ema_dw_hidden"].to(dev, torch.float32).contiguous(),
                       counter=int(sd["quantize.counter"]))
@@ -294,16 +314,18 @@ class VQGAN:
         return L.simt_conv(x_opd_or_f32, cw.w_kn, cw.bias, kh=cw.k, stride=stride, pad=pad if cw.k == 3 else (0, 0),
                            upsample=upsample, residual=residual)
 
-    def _act_dtype(self, cw):
-        return self.prec.opd if cw.tc else torch.float32
+    def _act_dtype(self, cw, prec):
+        return prec.opd if cw.tc else torch.float32
 
     def _resblock(self, rbw, x):
-        a = L.groupnorm(x, *rbw["n1"], swish=True, out_dtype=self._act_dtype(rbw["c1"]))
+        prec = rbw["prec"]
+        bf16 = prec.name == "bf16"
+        a = L.groupnorm(x, *rbw["n1"], swish=True, out_dtype=self._act_dtype(rbw["c1"], prec))
         # conv1's output is consumed by norm2 alone (the block's residual is x): in bf16 mode it travels as bf16 with the
         # GroupNorm statistics taken from the fp32 accumulators in the conv epilogue — 4 B/element less HBM traffic
         n_, h_, w_, _ = x.shape
         c1 = rbw["c1"]
-        edge = torch.bfloat16 if (self.bf16_edges and c1.tc and rbw["c2"].tc
+        edge = torch.bfloat16 if (bf16 and self.bf16_edges and c1.tc and rbw["c2"].tc
                                   and L.gn_fusable(c1.cout, 32, n_ * h_ * w_, h_ * w_, c1.cout)) else torch.float32
         h = self._conv(c1, a, out_dtype=edge)
         if h.dtype == torch.bfloat16 and self.norm_on_load and L.conv_norm_fusable(h, rbw["c2"].cout):
@@ -311,11 +333,11 @@ class VQGAN:
             # the raw bf16 edge is read once by the conv instead of being read, normalised, written and read again
             a, norm2 = h, (L.gn_mean_rstd(h), rbw["n2"][0], rbw["n2"][1], 32, True)
         else:
-            a, norm2 = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"])), None
+            a, norm2 = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"], prec)), None
         if "sc" in rbw:
             n, hh, ww, c = x.shape
-            xs = x if self.prec.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=self.prec.opd, normalize=False)
-            res = linear(self.prec, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
+            xs = x if prec.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=prec.opd, normalize=False)
+            res = linear(prec, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
         else:
             res = x
         if norm2 is not None:
@@ -324,7 +346,7 @@ class VQGAN:
 
     def _attn(self, aw, x):
         """AttnBlock (vqgan_th.py:120-144): single head over HW tokens, logits scaled by C^-0.5."""
-        prec = self.prec
+        prec = aw["prec"]
         n, hh, ww, c = x.shape
         hw = hh * ww
         a = L.groupnorm(x, *aw["norm"], swish=False, out_dtype=prec.opd).reshape(n * hw, c)
@@ -355,7 +377,7 @@ class VQGAN:
         if lvw["down"] is not None:
             down = lvw["down"]
             if down.tc and h.shape[1] % 2 == 0 and h.shape[2] % 2 == 0:
-                hs = L.groupnorm(h, None, None, swish=False, out_dtype=self.prec.opd, normalize=False, s2d=True)
+                hs = L.groupnorm(h, None, None, swish=False, out_dtype=self.enc_prec.opd, normalize=False, s2d=True)
                 h = self._conv(down, hs, stride=2)
             else:
                 if down.tc:
@@ -390,14 +412,14 @@ class VQGAN:
         h = self._resblock(e["mid1"], h)
         h = self._attn(e["mida"], h)
         h = self._resblock(e["mid2"], h)
-        a = L.groupnorm(h, *e["norm_out"], swish=True, out_dtype=self._act_dtype(e["conv_out"]))
+        a = L.groupnorm(h, *e["norm_out"], swish=True, out_dtype=self._act_dtype(e["conv_out"], self.enc_prec))
         return self._conv(e["conv_out"], a, stats=False)
 
     def _decoder(self, z):
         """Decoder.forward (vqgan_th.py:291-318); z f32 [N,h,w,z_channels] (post_quant_conv applied) -> f32 [N,H,W,3]."""
         d = self._w["dec"]
         cw = d["conv_in"]
-        zin = z if self._act_dtype(cw) == torch.float32 else L.groupnorm(z, None, None, swish=False, out_dtype=self.prec.opd, normalize=False)
+        zin = z if self._act_dtype(cw, self.dec_prec) == torch.float32 else L.groupnorm(z, None, None, swish=False, out_dtype=self.dec_prec.opd, normalize=False)
         h = self._conv(cw, zin)
         h = self._resblock(d["mid1"], h)
         h = self._attn(d["mida"], h)
@@ -411,11 +433,11 @@ class VQGAN:
             if lvw["up"] is not None:
                 up = lvw["up"]
                 if up.tc:      # nearest x2 materialised once in the operand dtype, then the tensor-core conv
-                    hu = L.groupnorm(h, None, None, swish=False, out_dtype=self.prec.opd, normalize=False, upsample=True)
+                    hu = L.groupnorm(h, None, None, swish=False, out_dtype=self.dec_prec.opd, normalize=False, upsample=True)
                     h = self._conv(up, hu)
                 else:          # exact path: upsampling folded into the conv's address arithmetic
                     h = self._conv(up, h, upsample=True)
-        a = L.groupnorm(h, *d["norm_out"], swish=True, out_dtype=self._act_dtype(d["conv_out"]))
+        a = L.groupnorm(h, *d["norm_out"], swish=True, out_dtype=self._act_dtype(d["conv_out"], self.dec_prec))
         return self._conv(d["conv_out"], a)
 
     # ------------------------------------------------------------------ quantizer
@@ -461,10 +483,16 @@ class VQGAN:
         zr = linear(self.exact, z.reshape(n * hh * ww, c), self._w["quant_conv"], torch.float32)
         return zr, hh, ww
 
+    def _check_layout(self, t, channel_axis, what):
+        if t.dim() != 4 or t.shape[channel_axis] != self.config.in_channels:
+            raise ValueError(f"{what}: expected {'NCHW' if channel_axis == 1 else 'NHWC'} images with {self.config.in_channels} channels, "
+                             f"got shape {tuple(t.shape)} (the torch flavour is NCHW, the TF flavour NHWC)")
+
     def encode_nhwc(self, x_nhwc):
         """TF-twin convention (viewformer/models/vqgan.py:291-295): NHWC in, (quant NHWC, diff, codes [N,h,w])."""
         self._need_weights()
         x = self._in(x_nhwc)
+        self._check_layout(x, 3, "encode_nhwc")
         zr, hh, ww = self.encode_rows(x)
         n = x.shape[0]
         quant, diff, idx = self._quantize(zr)
@@ -497,7 +525,9 @@ class VQGAN:
 
     def encode(self, x):
         self._need_weights()
-        x = L.nchw_to_nhwc(self._in(x))
+        x = self._in(x)
+        self._check_layout(x, 1, "encode")
+        x = L.nchw_to_nhwc(x)
         zr, hh, ww = self.encode_rows(x)
         n = x.shape[0]
         quant, diff, idx = self._quantize(zr)
