@@ -22,7 +22,7 @@ extern "C" {
 
 typedef void* vf_stream_t; /* cudaStream_t */
 
-enum { VF_F32 = 0, VF_BF16 = 1 };
+enum { VF_F32 = 0, VF_BF16 = 1, VF_F16X2 = 2 /* fp32 value as two fp16: [.., hi(C) | lo(C)], lo = fp16((v - hi) * 2^11); see vf_tc_gemm */ };
 enum { VF_ACT_NONE = 0, VF_ACT_GELU_ERF = 1 };
 enum { VF_BIAS_NONE = 0, VF_BIAS_N = 1, VF_BIAS_M = 2 };
 enum { VF_OK = 0, VF_ERR_ARG = -1, VF_ERR_CUDA = -2, VF_ERR_UNSUPPORTED = -3 };
@@ -57,7 +57,9 @@ int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W,
  *   with channel block (a*2+b)*C holding pixel (2y+a, 2x+b) — the operand layout that turns the reference's
  *   pad(0,1,0,1)+stride-2 3x3 conv (vqgan_th.py:45-49) into a stride-1 tap-table conv.
  *   (x_dtype, y_dtype): (F32,F32) exact order of operations; (F32,BF16) and (BF16,BF16) tensor-core operand producers
- *   (affine folded to one FMA, ex2/rcp swish).  grid = (pixel chunks, N): N <= 65535.
+ *   (affine folded to one FMA, ex2/rcp swish); (F32,F16X2) = the (F32,F32) arithmetic, each result stored as the
+ *   split-fp16 pair [.., hi(Cl) | lo(Cl)] (Cl = C, or 4C for layout 2) that vf_tc_gemm's exact convolution consumes.
+ *   grid = (pixel chunks, N): N <= 65535.
  * ---------------------------------------------------------------------------------------- */
 int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* sums, float* mean_rstd,
                        vf_stream_t s);

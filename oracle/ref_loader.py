@@ -82,3 +82,17 @@ def build_reference_vqgan(state_dict=None, **cfg_overrides):
     if state_dict is not None:
         model.load_state_dict(state_dict, strict=True)
     return model.eval()
+
+
+def load_reference_registry(extra_paths=()):
+    """Executes the REAL ``viewformer/models/__init__.py`` (AutoModel / AutoModelTH / load_config and the two override tables)
+    as the package ``viewformer.models``.  ``extra_paths`` are appended to the package ``__path__`` (how a maintainer's copied
+    shim modules become importable as ``viewformer.models.<shim>``)."""
+    load_reference_modules()
+    R = os.path.join(REFERENCE_ROOT, "viewformer", "models")
+    spec = importlib.util.spec_from_file_location("viewformer.models", os.path.join(R, "__init__.py"),
+                                                  submodule_search_locations=[R] + list(extra_paths))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["viewformer.models"] = m
+    spec.loader.exec_module(m)
+    return m

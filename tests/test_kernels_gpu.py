@@ -561,3 +561,86 @@ def test_vq_lookup_tensor_core_bit_exact(L, golden_dir):
     a, _, _ = L.vq_lookup_tc(zz, et, esq, et3, want_quant=False, want_diff=False)
     b, _, _ = L.vq_lookup(zz, et, esq, want_quant=False, want_diff=False)
     assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------- exact (split-fp16, chunked accumulation) convolutions
+def _split_ref(v):
+    """CPU restatement of the VF_F16X2 pair: hi = fp16(v), lo = fp16((v - hi) * 2^11)."""
+    hi = v.half()
+    lo = ((v - hi.float()) * 2048.0).half()
+    return hi, lo
+
+
+def test_split_f16x2_layouts(L):
+    x = torch.randn(2, 6, 4, 128, generator=g(7)) * 3
+    hi, lo = _split_ref(x)
+    y = L.groupnorm(x.cuda(), None, None, swish=False, out_dtype=torch.float16, normalize=False).cpu()
+    assert list(y.shape) == [2, 6, 4, 256]
+    assert torch.equal(y[..., :128], hi) and torch.equal(y[..., 128:], lo)
+    rec = y[..., :128].double() + y[..., 128:].double() / 2048.0
+    assert float(((rec - x.double()).abs() / x.abs().double().clamp_min(1e-3)).max()) < 2.0 ** -21
+    # space-to-depth: [N,H/2,W/2, hi(4C) | lo(4C)], block (a*2+b) <- pixel (2y+a, 2x+b)
+    ys = L.groupnorm(x.cuda(), None, None, swish=False, out_dtype=torch.float16, normalize=False, s2d=True).cpu()
+    assert list(ys.shape) == [2, 3, 2, 1024]
+    for a in (0, 1):
+        for b in (0, 1):
+            blk = (a * 2 + b) * 128
+            assert torch.equal(ys[..., blk:blk + 128], hi[:, a::2, b::2]) and torch.equal(ys[..., 512 + blk:512 + blk + 128], lo[:, a::2, b::2])
+    # nearest x2 upsample
+    yu = L.groupnorm(x.cuda(), None, None, swish=False, out_dtype=torch.float16, normalize=False, upsample=True).cpu()
+    assert torch.equal(yu[:, ::2, ::2], y) and torch.equal(yu[:, 1::2, 1::2], y)
+    # normalising variant == the fp32 kernel's values, split
+    ga, be = (1 + 0.1 * torch.randn(128, generator=g(8))).cuda(), (0.1 * torch.randn(128, generator=g(9))).cuda()
+    f = L.groupnorm(x.cuda(), ga, be, swish=True, out_dtype=torch.float32).cpu()
+    s = L.groupnorm(x.cuda(), ga, be, swish=True, out_dtype=torch.float16).cpu()
+    fh, fl = _split_ref(f)
+    assert torch.equal(s[..., :128], fh) and torch.equal(s[..., 128:], fl)
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout,res", [(2, 64, 64, 128, 128, True), (1, 40, 20, 64, 256, False), (2, 33, 9, 128, 128, True),
+                                                 (3, 16, 16, 256, 256, True), (5, 8, 8, 512, 256, False), (2, 4, 4, 128, 64, True)])
+def test_tc_conv_exact_split_fp16(L, n, H, W, cin, cout, res):
+    """fp32-faithful conv on the tensor cores (VF_F16X2 operands, 3 MMA passes, chunked RN accumulation) against fp64, next to the
+    fp32 CUDA-core conv of the exact path: the tensor-core result must be at least as close to fp64 as the FFMA chain."""
+    x = torch.randn(n, cin, H, W, generator=g(H + W + cin)) * 1.5
+    w = torch.randn(cout, cin, 3, 3, generator=g(143)) / (9 * cin) ** 0.5
+    b = torch.randn(cout, generator=g(144))
+    r = torch.randn(n, cout, H, W, generator=g(145)) if res else None
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if res:
+        want = want + r.double()
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    rh = r.permute(0, 2, 3, 1).contiguous().cuda() if res else None
+    xs = L.groupnorm(xh, None, None, swish=False, out_dtype=torch.float16, normalize=False)
+    ws = L.split_f16x2(w.permute(0, 2, 3, 1).reshape(cout * 9, cin).contiguous().cuda()).reshape(cout, 18 * cin)
+    got = L.tc_conv(xs, ws, b.cuda(), residual=rh, gn_groups=32)
+    ref32 = L.simt_conv(xh, w.permute(2, 3, 1, 0).reshape(9 * cin, cout).contiguous().cuda(), b.cuda(), kh=3, residual=rh)
+    torch.cuda.synchronize()
+    wantp = want.permute(0, 2, 3, 1)
+    scale = float(wantp.abs().mean())
+    e_tc = (got.double().cpu() - wantp).abs()
+    e_32 = (ref32.double().cpu() - wantp).abs()
+    print(f"[exact conv n{n} {H}x{W} {cin}->{cout}] tensor-core: max {e_tc.max() / scale:.2e} rms {e_tc.pow(2).mean().sqrt() / scale:.2e} | "
+          f"FFMA: max {e_32.max() / scale:.2e} rms {e_32.pow(2).mean().sqrt() / scale:.2e} (relative to mean |y|)")
+    assert float(e_tc.max()) / scale < 4e-6
+    assert float(e_tc.pow(2).mean().sqrt()) <= 1.5 * float(e_32.pow(2).mean().sqrt()) + 1e-9
+    if L.gn_fusable(cout, 32, n * H * W, H * W, cout):
+        assert hasattr(got, "_gn_sums")
+        o = got.double().cpu().reshape(n, H * W, 32, cout // 32)
+        report("exact conv fused gn sums", got._gn_sums[0].cpu(), torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1), 1e-2, 1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,n,hw", [(128, 128, 2, 32), (256, 256, 3, 8)])
+def test_tc_downsample_exact_split_fp16(L, cin, cout, n, hw):
+    """stride-2 Downsample conv (vqgan_th.py:45-49) on the exact path: split-fp16 space-to-depth operand + tap table."""
+    x = torch.randn(n, cin, hw, hw, generator=g(cin + 1))
+    w = torch.randn(cout, cin, 3, 3, generator=g(196)) / (9 * cin) ** 0.5
+    b = torch.randn(cout, generator=g(197))
+    want = F.conv2d(F.pad(x.double(), (0, 1, 0, 1)), w.double(), b.double(), stride=2).permute(0, 2, 3, 1)
+    xs = L.groupnorm(x.permute(0, 2, 3, 1).contiguous().cuda(), None, None, swish=False, out_dtype=torch.float16, normalize=False, s2d=True)
+    ws = L.split_f16x2(w.permute(0, 2, 3, 1).reshape(cout * 9, cin).contiguous().cuda()).reshape(cout, 18 * cin)
+    got = L.tc_conv(xs, ws, b.cuda(), taps=L.TAPS_S2D, coffs=L.s2d_coffs(cin), cin=cin)
+    torch.cuda.synchronize()
+    e = (got.double().cpu() - want).abs()
+    print(f"[exact downsample {cin}->{cout} hw{hw}] max {e.max() / want.abs().mean():.2e}")
+    assert float(e.max() / want.abs().mean()) < 4e-6

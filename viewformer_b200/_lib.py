@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VF_B200_LIB") or os.path.join(HERE, "libvf_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16X2 = 0, 1, 2     # F16X2: an fp32 value as two fp16 (hi | lo*2^11) along the channel axis — torch.float16 tensors with 2C channels
 ACT_NONE, ACT_GELU = 0, 1
 BIAS_NONE, BIAS_N, BIAS_M = 0, 1, 2
 
@@ -129,6 +129,8 @@ def _dt(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16X2
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
@@ -202,6 +204,8 @@ def groupnorm(x, gamma, beta, *, swish, out_dtype, eps=1e-6, groups=32, upsample
             sums = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
             _check(lib.vf_groupnorm_stats(_p(x), n, h * w, c, groups, C.c_float(eps), _p(sums), _p(stats), _stream()))
     oshape = (n, 2 * h, 2 * w, c) if upsample else ((n, h // 2, w // 2, 4 * c) if s2d else (n, h, w, c))
+    if out_dtype == torch.float16:          # split-fp16 pair [hi | lo] (exact tensor-core operand): twice the channels
+        oshape = oshape[:3] + (2 * oshape[3],)
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
     _check(lib.vf_groupnorm_apply(_p(x), _dt(x), _p(stats), _p(gamma), _p(beta), n, h, w, c, groups, C.c_float(eps),
                                   int(normalize), int(swish), 1 if upsample else (2 if s2d else 0), _p(y), _dt(y), _stream()))
@@ -400,14 +404,15 @@ def tc_conv(x, w_nk, bias, *, taps=TAPS_3x3, coffs=None, cin=None, out_hw=None, 
     lib = load(True)
     _dev(x)
     n, h, w, ctot = x.shape
-    cin = ctot if cin is None else cin
+    split = 2 if x.dtype == torch.float16 else 1            # exact mode: x = [hi | lo] halves, weights [Cout][tap][hi(Cin) | lo(Cin)]
+    cin = ctot // split if cin is None else cin
     cout = w_nk.shape[0]
     oh, ow = (h, w) if out_hw is None else out_hw
     if out is None:
         out = torch.empty((n, oh, ow, cout), dtype=out_dtype, device=x.device)
     p = TcGemm()
     p.conv, p.ab_dtype = 1, _dt(x)
-    assert w_nk.dtype == x.dtype and w_nk.shape[1] == len(taps) * cin
+    assert w_nk.dtype == x.dtype and w_nk.shape[1] == len(taps) * cin * split
     p.A, p.B = x.data_ptr(), w_nk.data_ptr()
     p.Ncols = cout
     p.N, p.H, p.W, p.Ctot, p.Cin, p.OH, p.OW, p.ntaps = n, h, w, ctot, cin, oh, ow, len(taps)
@@ -463,6 +468,12 @@ def vq_lookup(z_rows, et, esq, want_quant=True, want_diff=True):
     dsum = torch.zeros((1,), dtype=torch.float64, device=z_rows.device) if want_diff else None
     _check(lib.vf_vq_lookup(_p(z_rows), _p(et), _p(esq), C.c_int64(m), d, k, _p(idx), _p(quant), _p(dsum), _stream()))
     return idx, quant, dsum
+
+
+def split_f16x2(x_rows):
+    """f32 [rows, C] -> f16 [rows, 2C] = [hi | lo], hi = fp16(v), lo = fp16((v - hi) * 2^11) (weights of the exact convolution)."""
+    rows, c = x_rows.shape
+    return groupnorm(x_rows.reshape(1, 1, rows, c), None, None, swish=False, out_dtype=torch.float16, normalize=False).reshape(rows, 2 * c)
 
 
 def vq_split3(x, codebook):

@@ -7,7 +7,7 @@ unchanged.  ``localization_weight`` is a reference ``Schedule`` string (``utils/
 only "is it identically zero?" matters on the inference path, so it is kept as a string.
 """
 import json
-from dataclasses import dataclass, field, fields, asdict
+from dataclasses import dataclass, field, fields, asdict, is_dataclass
 from typing import List
 
 
@@ -105,6 +105,10 @@ def load_config(config):
     """dict / JSON path / config object -> config object (models/__init__.py:62-78)."""
     if isinstance(config, ModelConfig):
         return config
+    if is_dataclass(config) and not isinstance(config, type) and hasattr(config, "model"):
+        # a config object of the reference itself (viewformer/models/config.py dataclasses, handed over by its AutoModel*)
+        config = {f.name: getattr(config, f.name) for f in fields(config)}
+        config = {k: (str(v) if hasattr(v, "from_str") else v) for k, v in config.items()}
     if isinstance(config, str):
         with open(config) as f:
             config = json.load(f)

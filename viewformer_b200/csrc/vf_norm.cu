@@ -1,8 +1,16 @@
 // GroupNorm (two-phase: statistics, then normalise [+swish] [+nearest x2] [+cast]) and LayerNorm.
 // HBM-bound kernels: 128-bit loads, one pass each.  NHWC layout: x is [N, HW, C] fp32.
 #include "vf_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
+
+// VF_F16X2 output: an fp32 value as (hi, lo) fp16 pair, hi = fp16(v), lo = fp16((v - hi) * 2^11), stored [.., hi(C) | lo(C)]
+// — the operand format of the exact tensor-core convolution (vf_tc_gemm.cu, EXACT_LO_SCALE).  v - hi is exact in fp32.
+struct f16x2_t { __half h; };
+template <typename T> struct out_traits { static constexpr bool fast = false, split = false; };
+template <> struct out_traits<__nv_bfloat16> { static constexpr bool fast = true, split = false; };
+template <> struct out_traits<f16x2_t> { static constexpr bool fast = false, split = true; };
 
 // ---------------------------------------------------------------------------------------------
 // Statistics: per (n, group) sum and sum of squares in double.
@@ -101,11 +109,29 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
                        __uint_as_float(u.y & 0xffff0000u));
 }
 
+// hi halves at p, lo halves at p + lo_off
+__device__ __forceinline__ void store4_split(f16x2_t* p, int64_t lo_off, float a, float b, float c, float d) {
+    const float v[4] = {a, b, c, d};
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2half_rn(v[j]);
+        lo[j] = __float2half_rn((v[j] - __half2float(hi[j])) * 2048.0f);
+    }
+    uint2 uh, ul;
+    uh.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+    uh.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+    ul.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+    ul.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+    *reinterpret_cast<uint2*>(p) = uh;
+    *reinterpret_cast<uint2*>(p + lo_off) = ul;
+}
+
 template <typename OutT>
 __device__ __forceinline__ float gn_swish(float v) {
     // bf16 operand output: ex2.approx / rcp.approx (rel. error ~1e-6, far below bf16 rounding) keep this kernel
-    // memory-bound; the fp32 (exact-path) instantiation uses expf and a true division
-    if constexpr (sizeof(OutT) == 2) return __fdividef(v, 1.0f + __expf(-v));
+    // memory-bound; the fp32 and split-fp16 (exact-path) instantiations use expf and a true division
+    if constexpr (out_traits<OutT>::fast) return __fdividef(v, 1.0f + __expf(-v));
     else return vf_swish(v);
 }
 
@@ -146,12 +172,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const InT* __restrict__ x
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (normalize) {
-                if constexpr (sizeof(OutT) == 2) e[j] = fmaf(e[j], sc[j], sh[j]);
+                if constexpr (out_traits<OutT>::fast) e[j] = fmaf(e[j], sc[j], sh[j]);
                 else e[j] = (e[j] - mu[j]) * rs[j] * ga[j] + be[j];
             }
             if (swish) e[j] = gn_swish<OutT>(e[j]);
         }
-        if constexpr (kLayout == 0) {
+        if constexpr (out_traits<OutT>::split) {
+            // pixel stride doubles ([hi | lo]); the lo half starts after the LOGICAL channel count of the output layout
+            if constexpr (kLayout == 0) {
+                store4_split(y + ((int64_t)n * HW + p) * (2 * C) + cq * 4, C, e[0], e[1], e[2], e[3]);
+            } else if constexpr (kLayout == 2) {
+                const int yy = p / W, xx = p - yy * W;
+                const int64_t o = (((int64_t)n * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1)) * (8 * (int64_t)C) + ((yy & 1) * 2 + (xx & 1)) * C + cq * 4;
+                store4_split(y + o, 4 * (int64_t)C, e[0], e[1], e[2], e[3]);
+            } else {
+                const int yy = p / W, xx = p - yy * W;
+                const int64_t W2 = 2 * (int64_t)W, C2 = 2 * (int64_t)C;
+                const int64_t o = (((int64_t)n * 2 * H + 2 * yy) * W2 + 2 * xx) * C2 + cq * 4;
+                store4_split(y + o, C, e[0], e[1], e[2], e[3]);
+                store4_split(y + o + C2, C, e[0], e[1], e[2], e[3]);
+                store4_split(y + o + W2 * C2, C, e[0], e[1], e[2], e[3]);
+                store4_split(y + o + W2 * C2 + C2, C, e[0], e[1], e[2], e[3]);
+            }
+        } else if constexpr (kLayout == 0) {
             store4<OutT>(y + ((int64_t)n * HW + p) * C + cq * 4, e[0], e[1], e[2], e[3]);
         } else if constexpr (kLayout == 2) {
             const int yy = p / W, xx = p - yy * W;
@@ -300,6 +343,8 @@ extern "C" int vf_groupnorm_apply(const void* x, int x_dtype, const float* stats
         gn_apply_launch<float, __nv_bfloat16>(x, stats, gamma, beta, N, H, W, C, groups, normalize, swish, layout, y, vf_s(s));
     else if (x_dtype == VF_BF16 && y_dtype == VF_BF16)
         gn_apply_launch<__nv_bfloat16, __nv_bfloat16>(x, stats, gamma, beta, N, H, W, C, groups, normalize, swish, layout, y, vf_s(s));
+    else if (x_dtype == VF_F32 && y_dtype == VF_F16X2)
+        gn_apply_launch<float, f16x2_t>(x, stats, gamma, beta, N, H, W, C, groups, normalize, swish, layout, y, vf_s(s));
     else
         VF_CHECK_ARG(false, "vf_groupnorm_apply: unsupported dtype pair (x %d, y %d)", x_dtype, y_dtype);
     VF_CHECK_LAUNCH("vf_groupnorm_apply");

@@ -57,6 +57,10 @@ struct TcParams {
     double* gn_sums;           // optional fused GroupNorm statistics of the OUTPUT: [images][groups][2] (sum, sum of squares)
     int gn_groups, gn_cpg, gn_rows_per_img;
     int dbg_flags;             // profiling builds only: 1 = no epilogue work, 2 = no B loads, 4 = no A loads (stale smem is consumed)
+    int exact;                 // conv only: split-fp16 operands (VF_F16X2), three product passes, chunked accumulation (see EXACT_LO_SCALE)
+    int exact_kc;              // k-blocks per accumulation chunk (divides ntaps * cin_blocks)
+    int exact_clog;            // logical channels of the split activation tensor (= Ctot / 2): the lo half starts there
+    int exact_kpp;             // k-blocks per product pass = ntaps * cin_blocks
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -257,6 +261,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr float EXACT_LO_SCALE = 1.0f / 2048.0f;      // exact (VF_F16X2) mode: weight of the cross-term passes, see WideParams below
 constexpr int KGROUP = 1;          // k-blocks per producer/consumer hand-shake (2 measured no faster: the ring gets too coarse)
 constexpr int HALO_BYTES = 23552;  // one (16+2) x (8+2) halo tile of 128-byte rows, rounded up to 1024
 constexpr int HALO_SLOTS = 6;      // weight-tile slots of the halo-mode ring
@@ -445,15 +450,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                         const int kb = kb0 + g;
                         uint8_t* sa = smem + (stage * KGROUP + g) * STAGE_BYTES;
                         uint8_t* sb = sa + A_STAGE_BYTES;
+                        int kcoord_b = kb * p.bk_elems;
                         if (p.conv) {
-                            const int tap = kb / p.cin_blocks;
-                            const int cb = kb - tap * p.cin_blocks;
-                            load(sa, &p.tmA, &full_bar[stage], p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap], ti.oy0 + p.tap_dy[tap],
-                                 ti.img0);
+                            int kbr = kb, a_half = 0;
+                            if (p.exact) {       // product pass j: 0 = (lo_x, hi_w), 1 = (hi_x, lo_w), 2 = (hi_x, hi_w)
+                                const int j = kb / p.exact_kpp;
+                                kbr = kb - j * p.exact_kpp;
+                                a_half = (j == 0) ? p.exact_clog : 0;
+                                const int tap_ = kbr / p.cin_blocks, cb_ = kbr - tap_ * p.cin_blocks;
+                                kcoord_b = ((tap_ * 2 + (j == 1 ? 1 : 0)) * p.cin_blocks + cb_) * p.bk_elems;
+                            }
+                            const int tap = kbr / p.cin_blocks;
+                            const int cb = kbr - tap * p.cin_blocks;
+                            load(sa, &p.tmA, &full_bar[stage], a_half + p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap],
+                                 ti.oy0 + p.tap_dy[tap], ti.img0);
                         } else {
                             load(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
                         }
-                        load(sb, &p.tmB, &full_bar[stage], kb * p.bk_elems, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
+                        load(sb, &p.tmB, &full_bar[stage], kcoord_b, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
                     }
                     if (++stage == NG) { stage = 0; phase ^= 1; }
                 }
@@ -543,8 +557,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                     ++it;
                     continue;
                 }
+                uint32_t tmem_dd = tmem_d;
+                int in_chunk = 0;
+                bool fresh = true;
                 for (int kb0 = 0; kb0 < ti.nkb; kb0 += KGROUP) {
                     const int n = (ti.nkb - kb0 < KGROUP) ? ti.nkb - kb0 : KGROUP;
+                    if (p.exact && in_chunk == 0 && kb0 > 0) {        // next chunk: a fresh accumulator stage (the first one was opened above)
+                        const int a2 = it & 1;
+                        mbar_wait(&tmem_empty_bar[a2], ((it >> 1) & 1) ^ 1);
+                        tcgen05_fence_after();
+                        tmem_dd = tmem_base + (uint32_t)(a2 * kBlockN);
+                        fresh = true;
+                    }
                     if (dbg) c0 = clock64();
                     if (!ready) mbar_wait(&full_bar[stage], phase);
                     if (dbg) c_ops += clock64() - c0;
@@ -563,15 +587,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
                             for (int k = 0; k < MMAS_PER_STAGE; ++k) {
                                 // advance along K inside the 128B swizzle atom: +32 bytes => +2 in the (addr >> 4) field
-                                mma(tmem_d, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
-                                    (kb0 + g > 0 || k > 0) ? 1u : 0u);
+                                mma(tmem_dd, adesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)), bdesc + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                    (fresh && k == 0) ? 0u : 1u);
                             }
+                            fresh = false;
                         }
                     }
                     commit(&empty_bar[stage]);               // frees the group's smem slots (in both CTAs) once these MMAs retire
                     if (++stage == NG) { stage = 0; phase ^= 1; }
+                    if (p.exact && ++in_chunk == p.exact_kc && kb0 + KGROUP < ti.nkb) {      // chunk complete (the last one is committed below)
+                        in_chunk = 0;
+                        commit(&tmem_full_bar[it & 1]);
+                        ++it;
+                    }
                 }
-                commit(&tmem_full_bar[acc]);                  // accumulator complete
+                commit(&tmem_full_bar[it & 1]);               // accumulator (or last chunk) complete
                 ++it;
             }
             if (dbg) {
@@ -648,6 +678,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (fast && p.bias_mode == VF_BIAS_N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_ln));
 
+            if (p.exact) {
+                // ---- phase 1, exact mode: one TMEM hand-off per accumulation chunk; chunks are summed into the staging tile with RN
+                // FFMAs (cross-term passes scaled by 2^-11), see EXACT_LO_SCALE.  `it` was advanced once above: count chunks instead.
+                const int nchunks = ti.nkb / p.exact_kc, nsmall = 2 * p.exact_kpp / p.exact_kc;
+                --it;
+#pragma unroll 1
+                for (int ck = 0; ck < nchunks; ++ck) {
+                    const int a = it & 1;
+                    const uint32_t aph = (it >> 1) & 1;
+                    ++it;
+                    const float sc = (ck < nsmall ? EXACT_LO_SCALE : 1.0f) * p.alpha;
+                    mbar_wait(&tmem_full_bar[a], aph);
+                    tcgen05_fence_after();
+#pragma unroll 1
+                    for (int c0 = 0; c0 < HALF_N; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * kBlockN + col_half * HALF_N + c0), r);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD + c0 + j);
+                            float4 o = ck ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
+                            o.x = fmaf(__uint_as_float(r[j]), sc, o.x);
+                            o.y = fmaf(__uint_as_float(r[j + 1]), sc, o.y);
+                            o.z = fmaf(__uint_as_float(r[j + 2]), sc, o.z);
+                            o.w = fmaf(__uint_as_float(r[j + 3]), sc, o.w);
+                            *dst = o;
+                        }
+                    }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+                }
+            } else {
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
 
@@ -668,6 +731,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             if (lane == 0) {
                 if (k2Cta && rank != 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);    // the leader's issuer waits for both CTAs
                 else mbar_arrive(&tmem_empty_bar[acc]);
+            }
             }
 
             // ---- phase 2: lanes span the columns of a tile row -> fully coalesced stores; bias / activation / residual here
@@ -788,7 +852,19 @@ struct WideParams {
     unsigned idesc;
     long long* dbg;            // profiling builds: per-CTA stall counters
     int dbg_flags;
+    int kc;                    // exact (split-fp16) mode: filter taps per accumulation chunk (1, 3 or 9)
 };
+
+// ---- exact mode (VF_F16X2 operands): fp32-faithful convolution on the tensor cores ------------------------------------------
+// An fp32 value v travels as TWO fp16 numbers  hi = fp16(v),  lo = fp16((v - hi) * 2^11)  (22-23 significand bits; the scaling keeps
+// lo out of the fp16 subnormal range), activations as [.., hi(C) | lo(C)], weights as [Cout][tap][hi(Cin) | lo(Cin)].
+//   x * w  =  hi_x hi_w  +  2^-11 (hi_x lo_w + lo_x hi_w)  +  O(2^-22 |x w|)            -> three fp16 MMAs per product block
+// tcgen05.mma adds into its fp32 accumulator with TRUNCATION (measured: scripts/acc_rounding_probe.py, relative bias ~1.3e-8 per
+// MMA step towards zero), so a long K loop in TMEM is not fp32-faithful.  The accumulator is therefore drained every `kc` filter
+// taps (a "chunk" of kc x 4 MMA steps from a ZERO accumulator) and the chunks are summed in registers with round-to-nearest
+// FFMA, scaled by 2^-11 for the cross terms, small terms first.  Measured against fp64: rms 1.3e-7 of |y| (the fp32 FFMA chain of
+// vf_simt_gemm: 6.1e-7) — the encoder on this path reproduces the fp32 path's codebook indices (tests/test_baseline_configs_gpu.py).
+
 
 // wide kernels: 16 epilogue warps (4 per TMEM lane quarter, 64 accumulator columns each): with 2 warps per scheduler the register
 // epilogue ran at ~0.25 IPC per warp (ncu: stall_wait / short scoreboard) and held every tile for 10-20k cycles
@@ -804,9 +880,10 @@ constexpr int WIDE_SMEM = 2 * WIDE_HALO_BYTES + WIDE_W_SLOTS * WIDE_W_BYTES + 10
 
 // <16, false>: plain conv, 16 epilogue warps x 2 chunks; <8, true>: + 4 normalise-on-load warps, 8 epilogue warps x 4 chunks
 // (the thread count bounds the registers per thread: 704 threads left the epilogue 80 registers and spills)
-template <int kEpiWarps, bool kNorm>
+template <int kEpiWarps, bool kNorm, bool kExact = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps + (kNorm ? 32 * WIDE_XFORM_WARPS : 0), 1)
 tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
+    static_assert(!(kNorm && kExact), "normalise-on-load is a bf16-path feature");
     constexpr int CPW = 256 / ((kEpiWarps / 4) * 32);        // 32-pixel chunks per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -867,15 +944,20 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 int c0, ox0, oy0, img;
                 decode(t, c0, ox0, oy0, img);
-                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                // exact mode walks 3 product passes over the channel blocks: (lo_x, hi_w), (hi_x, lo_w), (hi_x, hi_w) — small terms first
+                const int nv = kExact ? 3 * p.cin_blocks : p.cin_blocks;
+                for (int v = 0; v < nv; ++v) {
+                    const int j = kExact ? v / p.cin_blocks : 0, cb = kExact ? v - j * p.cin_blocks : v;
+                    const int xblk = kExact ? ((j == 0 ? p.cin_blocks : 0) + cb) : cb;            // channel block inside [hi | lo]
                     mbar_wait(&h_empty[hb], hph ^ 1);
                     mbar_expect_tx(&h_full[hb], WIDE_HALO_ROWS * ROW_BYTES);
-                    tma_load_4d(smem + hb * WIDE_HALO_BYTES, &p.tmX, &h_full[hb], cb * 64, ox0 - 1, oy0 - 1, img);
+                    tma_load_4d(smem + hb * WIDE_HALO_BYTES, &p.tmX, &h_full[hb], xblk * 64, ox0 - 1, oy0 - 1, img);
                     if (++hb == 2) { hb = 0; hph ^= 1; }
                     for (int tap = 0; tap < 9; ++tap) {
+                        const int wblk = kExact ? (tap * 2 + (j == 1 ? 1 : 0)) * p.cin_blocks + cb : tap * p.cin_blocks + cb;
                         mbar_wait(&w_empty[ws], wph ^ 1);
                         mbar_expect_tx(&w_full[ws], WIDE_W_BYTES);
-                        tma_load_4d(w_base + ws * WIDE_W_BYTES, &p.tmW, &w_full[ws], (tap * p.cin_blocks + cb) * 64, c0, 0, 0);
+                        tma_load_4d(w_base + ws * WIDE_W_BYTES, &p.tmW, &w_full[ws], wblk * 64, c0, 0, 0);
                         if (++ws == WIDE_W_SLOTS) { ws = 0; wph ^= 1; }
                     }
                 }
@@ -896,21 +978,34 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
             long long c_ops = 0, c_tmem = 0, c_tiles = 0, c0 = 0;
             const long long c_start = dbg ? clock64() : 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                if (dbg) c0 = clock64();
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-                if (dbg) { c_tmem += clock64() - c0; ++c_tiles; }
-                tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                uint32_t tmem_d = 0;
+                bool fresh = true;                // next MMA starts a zeroed accumulator (tile start, or chunk start in exact mode)
+                auto open_acc = [&]() {
+                    const int acc = it & 1;
+                    const uint32_t acc_phase = (it >> 1) & 1;
+                    if (dbg) c0 = clock64();
+                    mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                    if (dbg) { c_tmem += clock64() - c0; ++c_tiles; }
+                    tcgen05_fence_after();
+                    tmem_d = tmem_base + (uint32_t)(acc * 256);
+                    fresh = true;
+                };
+                auto close_acc = [&]() {
+                    tcgen05_commit(&tmem_full_bar[it & 1]);
+                    ++it;
+                };
+                if (!kExact) open_acc();
+                const int nv = kExact ? 3 * p.cin_blocks : p.cin_blocks;
+                for (int cb = 0; cb < nv; ++cb) {
                     if (dbg) c0 = clock64();
                     mbar_wait(norm ? &h_ready[hb] : &h_full[hb], hph);
                     if (dbg) c_ops += clock64() - c0;
                     tcgen05_fence_after();
                     const uint32_t h_addr = smem_u32(smem + hb * WIDE_HALO_BYTES);
+                    int in_chunk = 0;
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
+                        if (kExact && in_chunk == 0) open_acc();
                         if (dbg) c0 = clock64();
                         if (!ready) mbar_wait(&w_full[ws], wph);
                         if (dbg) c_ops += clock64() - c0;
@@ -925,15 +1020,16 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         bdesc = (bdesc & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((PITCH * ROW_BYTES) >> 4) << 32);     // SBO = one halo row pitch
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                            umma<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (fresh && k == 0) ? 0u : 1u);
+                        fresh = false;
                         tcgen05_commit(&w_empty[ws]);
                         if (++ws == WIDE_W_SLOTS) { ws = 0; wph ^= 1; }
+                        if (kExact && ++in_chunk == p.kc) { in_chunk = 0; close_acc(); }
                     }
                     tcgen05_commit(&h_empty[hb]);
                     if (++hb == 2) { hb = 0; hph ^= 1; }
                 }
-                tcgen05_commit(&tmem_full_bar[acc]);
-                ++it;
+                if (!kExact) close_acc();
             }
             if (dbg) {
                 long long* d = p.dbg + 8 * blockIdx.x;
@@ -1052,6 +1148,72 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                 continue;
             }
 #endif
+            if constexpr (kExact) {
+                // chunked accumulation: every chunk arrives in a TMEM stage that started from zero; sum them here with RN FFMAs
+                // (cross-term chunks scaled by 2^-11).  (acc, acc_phase, it) above described the tile's FIRST chunk.
+                static_assert(!kExact || CPW == 2, "exact epilogue holds 2 x 32 accumulator columns per thread");
+                float a0[32], a1[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+                const int cpv = 9 / p.kc;                               // chunks per (product pass, channel block)
+                const int nchunks = 3 * p.cin_blocks * cpv, nsmall = 2 * p.cin_blocks * cpv;
+                int a = acc;
+                uint32_t aph = acc_phase;
+                --it;                                                   // undo the per-tile increment: one hand-off per chunk
+#pragma unroll 1
+                for (int ck = 0; ck < nchunks; ++ck) {
+                    a = it & 1;
+                    aph = (it >> 1) & 1;
+                    ++it;
+                    const float sc = ck < nsmall ? EXACT_LO_SCALE : 1.0f;
+                    mbar_wait(&tmem_full_bar[a], aph);
+                    tcgen05_fence_after();
+                    uint32_t r[32];
+                    const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 256 + grp * 64);
+                    tmem_ld_32x32(ta, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a0[j] = fmaf(__uint_as_float(r[j]), sc, a0[j]);
+                    tmem_ld_32x32(ta + 32, r);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a1[j] = fmaf(__uint_as_float(r[j]), sc, a1[j]);
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int r0 = grp * 8 + c * 4;
+                    if (has_res) load_res(c);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = (c == 0 ? a0[j] : a1[j]) + bias;
+                        if (has_res) v[j] += rv[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ty = r0 + (j >> 3), tx = j & 7;
+                        if (full || (ty < rows_ok && tx < cols_ok)) {       // warp-uniform
+                            const int idx = base + ty * row_stride + tx * p.Cout;
+                            gs += v[j];
+                            gq = fmaf(v[j], v[j], gq);
+                            if (p.C_f32) p.C_f32[idx] = v[j];
+                        }
+                    }
+                }
+                if (p.gn_sums) {
+                    for (int o = 1; o < p.gn_cpg; o <<= 1) {
+                        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                    }
+                    if ((lane & (p.gn_cpg - 1)) == 0) {
+                        double* d = p.gn_sums + ((long long)img * p.gn_groups + ch / p.gn_cpg) * 2;
+                        atomicAdd(d, (double)gs);
+                        atomicAdd(d + 1, (double)gq);
+                    }
+                }
+                continue;
+            }
             if (has_res) load_res(0);                     // flies behind this tile's MMAs
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
@@ -1373,10 +1535,10 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* base, const uint64_t dims[
 
 // cute::UMMA::InstrDescriptor: [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt (0 f16, 1 bf16, 2 tf32)
 // | [15] A major (0=K) | [16] B major (0=K) | [17,23) N>>3 | [24,29) M>>4
-unsigned make_idesc(bool tf32, int M, int N) {
+unsigned make_idesc(bool tf32, int M, int N, bool f16 = false) {
     unsigned d = 0;
     d |= 1u << 4;
-    const unsigned fmt = tf32 ? 2u : 1u;
+    const unsigned fmt = tf32 ? 2u : (f16 ? 0u : 1u);
     d |= fmt << 7;
     d |= fmt << 10;
     d |= (unsigned)(N >> 3) << 17;
@@ -1431,12 +1593,13 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
     WideParams prm;
     memset(&prm, 0, sizeof(prm));
     const int es = 2;
-    const uint64_t dimsX[4] = {(uint64_t)q->Cin, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->N};
+    const bool exact = q->ab_dtype == VF_F16X2;          // split fp16 operands: [hi | lo] along the channel axis (16-bit elements either way)
+    const uint64_t dimsX[4] = {(uint64_t)q->Ctot, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->N};
     const uint64_t strX[3] = {(uint64_t)q->Ctot * es, (uint64_t)q->W * q->Ctot * es, (uint64_t)q->H * q->W * q->Ctot * es};
     const uint32_t boxX[4] = {64, WIDE_TW + 2, WIDE_TH + 2, 1};
     int rc;
     if ((rc = make_tmap(&prm.tmX, VF_BF16, q->A, dimsX, strX, boxX)) != VF_OK) return rc;
-    const uint64_t Ktot = 9ull * q->Cin;
+    const uint64_t Ktot = (exact ? 18ull : 9ull) * q->Cin;
     const uint64_t dimsW[4] = {Ktot, (uint64_t)q->Ncols, 1, 1};
     const uint64_t strW[3] = {Ktot * es, Ktot * es * q->Ncols, Ktot * es * q->Ncols};
     const uint32_t boxW[4] = {64, 128, 1, 1};
@@ -1462,9 +1625,16 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
     const long long total = (long long)prm.tiles_x * prm.tiles_y * prm.tiles_c * q->N;
     VF_CHECK_ARG(total > 0 && total < (1ll << 31), "vf_tc_gemm: tile count out of range");
     prm.total_tiles = (int)total;
-    prm.idesc = make_idesc(false, 128, 256);
+    prm.idesc = make_idesc(false, 128, 256, exact);
     prm.dbg = g_tc_dbg;
     prm.dbg_flags = g_tc_dbg_flags;
+    prm.kc = 3;
+    if (exact) {
+        static int kc_env = -1;
+        if (kc_env < 0) { const char* e = getenv("VF_EXACT_KC"); kc_env = e ? atoi(e) : 3; if (kc_env != 1 && kc_env != 3 && kc_env != 9) kc_env = 3; }
+        prm.kc = kc_env;
+        VF_CHECK_ARG(!q->norm_mean_rstd && !q->C_bf16 && q->C_f32, "vf_tc_gemm: the exact (split-fp16) conv writes fp32 and has no fused input norm");
+    }
     if (q->gn_sums) {
         const int cpg = q->Ncols / q->gn_groups;
         prm.gn_sums = q->gn_sums;
@@ -1477,6 +1647,7 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute(wide): %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
         configured = true;
     }
@@ -1487,7 +1658,8 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
     const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
-    if (prm.norm_mr) tc_conv3x3_wide_kernel<8, true><<<grid, 64 + 32 * 8 + 32 * WIDE_XFORM_WARPS, WIDE_SMEM, st>>>(prm);
+    if (exact) tc_conv3x3_wide_kernel<16, false, true><<<grid, 64 + 32 * 16, WIDE_SMEM, st>>>(prm);
+    else if (prm.norm_mr) tc_conv3x3_wide_kernel<8, true><<<grid, 64 + 32 * 8 + 32 * WIDE_XFORM_WARPS, WIDE_SMEM, st>>>(prm);
     else tc_conv3x3_wide_kernel<16, false><<<grid, 64 + 32 * 16, WIDE_SMEM, st>>>(prm);
     VF_CHECK_LAUNCH("vf_tc_gemm(wide conv)");
     return VF_OK;
@@ -1569,7 +1741,8 @@ static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st)
 static bool conv_wide_eligible(const vf_tc_gemm_t* q) {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("VF_TC_WIDE"); enabled = (e && e[0] == '0') ? 0 : 1; }
-    if (!enabled || !q->conv || q->ab_dtype != VF_BF16 || q->ntaps != 9 || q->Ctot != q->Cin || q->OH != q->H || q->OW != q->W) return false;
+    if (!enabled || !q->conv || q->ntaps != 9 || q->OH != q->H || q->OW != q->W) return false;
+    if (!((q->ab_dtype == VF_BF16 && q->Ctot == q->Cin) || (q->ab_dtype == VF_F16X2 && q->Ctot == 2 * q->Cin))) return false;
     if (q->Cin % 64 || q->Ncols % 128 || q->H < 32 || q->W < 8 || q->ldc != q->Ncols || q->alpha != 1.0f || q->act != VF_ACT_NONE) return false;
     if (q->bias_mode == VF_BIAS_M) return false;
     if ((long long)q->N * q->H * q->W * q->Ncols >= (1ll << 31)) return false;      // the epilogue indexes with 32 bits
@@ -1591,7 +1764,12 @@ extern "C" void vf_tc_debug_counters(long long* buf) { g_tc_dbg = buf; }
 extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     VF_CHECK_ARG(q && q->A && q->B, "vf_tc_gemm: null operand");
     VF_CHECK_ARG(q->C_f32 || q->C_bf16, "vf_tc_gemm: no output");
-    VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32, "vf_tc_gemm: bad dtype");
+    VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32 || q->ab_dtype == VF_F16X2, "vf_tc_gemm: bad dtype");
+    const bool exact = q->ab_dtype == VF_F16X2;
+    if (exact) {
+        VF_CHECK_ARG(q->conv && q->Ctot % 2 == 0 && q->alpha == 1.0f && q->C_f32 && !q->C_bf16 && !q->norm_mean_rstd,
+                     "vf_tc_gemm: VF_F16X2 (exact split-fp16) operands are supported for convolutions with fp32 output only");
+    }
     VF_CHECK_ARG(q->bias_mode == VF_BIAS_NONE || q->bias, "vf_tc_gemm: bias pointer missing");
     if (conv_wide_eligible(q)) return launch_conv_wide(q, vf_s(s));
     VF_CHECK_ARG(!q->norm_mean_rstd, "vf_tc_gemm: fused input GroupNorm is only available for 3x3 stride-1 bf16 convs on maps >= 32 rows "
@@ -1601,6 +1779,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         if (gemm_wide_eligible(q, &m_flat)) return launch_gemm_wide(q, m_flat, vf_s(s));
     }
     const bool tf32 = q->ab_dtype == VF_F32;
+    const int tm_dtype = tf32 ? VF_F32 : VF_BF16;        // tensor-map element type (fp16 and bf16 move identically)
     const int es = tf32 ? 4 : 2;
     const int bk = ROW_BYTES / es;                       // K elements per block: 64 bf16 / 32 tf32
 
@@ -1629,7 +1808,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     // measured in round 1 (profiles/r01_tc_kernel_analysis.md): at BLOCK_N = 128 the pair is on par with two single CTAs, so it is
     // opt-in (VF_TC_2CTA=1) until the 256-wide tiles that make it pay are in
     if (two_cta_enabled < 0) { const char* e = getenv("VF_TC_2CTA"); two_cta_enabled = (e && e[0] == '1') ? 1 : 0; }
-    const bool k2 = two_cta_enabled && block_n == 128 && q->causal_block == 0 && (q->conv || q->batch1 * q->batch2 == 1);
+    const bool k2 = two_cta_enabled && !exact && block_n == 128 && q->causal_block == 0 && (q->conv || q->batch1 * q->batch2 == 1);
     const int b_box_rows = k2 ? block_n / 2 : block_n;
     dim3 grid;
     int rc;
@@ -1645,7 +1824,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         // halo mode: plain stride-1 pad-1 3x3 conv on maps at least 16 rows tall -> 8x16-pixel tiles, one halo load per channel block
         static int halo_enabled = -1;
         if (halo_enabled < 0) { const char* e = getenv("VF_TC_HALO"); halo_enabled = (e && e[0] == '0') ? 0 : 1; }
-        bool halo = halo_enabled && q->ntaps == 9 && q->Ctot == q->Cin && q->OH == q->H && q->OW == q->W && q->OH >= 16 && q->OW >= 8;
+        bool halo = halo_enabled && !exact && q->ntaps == 9 && q->Ctot == q->Cin && q->OH == q->H && q->OW == q->W && q->OH >= 16 && q->OW >= 8;
         for (int t = 0; halo && t < 9; ++t) halo = q->tap_dy[t] == t / 3 - 1 && q->tap_dx[t] == t % 3 - 1 && q->tap_coff[t] == 0;
         if (halo) { TW = 8; TH = 16; TN = 1; }
         prm.halo = halo ? 1 : 0;
@@ -1656,18 +1835,25 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         prm.OH = q->OH; prm.OW = q->OW; prm.Nimg = q->N;
         prm.cin_blocks = q->Cin / bk;
         prm.num_k_blocks = q->ntaps * prm.cin_blocks;
+        if (exact) {
+            prm.exact = 1;
+            prm.exact_kpp = prm.num_k_blocks;
+            prm.exact_clog = q->Ctot / 2;
+            prm.exact_kc = (prm.num_k_blocks % 3 == 0) ? 3 : 1;      // k-blocks (= 4 MMA steps each) per accumulation chunk
+            prm.num_k_blocks *= 3;
+        }
         prm.M = q->N * q->OH * q->OW;
         prm.batch2 = 1;
         for (int t = 0; t < q->ntaps; ++t) { prm.tap_dy[t] = q->tap_dy[t]; prm.tap_dx[t] = q->tap_dx[t]; prm.tap_coff[t] = q->tap_coff[t]; }
         const uint64_t dimsA[4] = {(uint64_t)q->Ctot, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->N};
         const uint64_t strA[3] = {(uint64_t)q->Ctot * es, (uint64_t)q->W * q->Ctot * es, (uint64_t)q->H * q->W * q->Ctot * es};
         const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)(halo ? TW + 2 : TW), (uint32_t)(halo ? TH + 2 : TH), (uint32_t)TN};
-        if ((rc = make_tmap(&prm.tmA, q->ab_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
-        const uint64_t Ktot = (uint64_t)q->ntaps * q->Cin;
+        if ((rc = make_tmap(&prm.tmA, tm_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
+        const uint64_t Ktot = (uint64_t)q->ntaps * q->Cin * (exact ? 2 : 1);
         const uint64_t dimsB[4] = {Ktot, (uint64_t)q->Ncols, 1, 1};
         const uint64_t strB[3] = {Ktot * es, Ktot * es * q->Ncols, Ktot * es * q->Ncols};
         const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)b_box_rows, 1, 1};
-        if ((rc = make_tmap(&prm.tmB, q->ab_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
+        if ((rc = make_tmap(&prm.tmB, tm_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
         const int ntiles_img = (q->N + TN - 1) / TN;
         grid = dim3(prm.tiles_x * prm.tiles_y * ntiles_img, (q->Ncols + block_n - 1) / block_n, 1);
     } else {
@@ -1689,11 +1875,11 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         const uint64_t dimsA[4] = {(uint64_t)q->K, (uint64_t)q->M, prm.a_bm2 ? (uint64_t)q->batch2 : 1, prm.a_bm1 ? (uint64_t)q->batch1 : 1};
         const uint64_t strA[3] = {(uint64_t)q->lda * es, prm.a_bm2 ? (uint64_t)q->a_sb2 * es : fbA, prm.a_bm1 ? (uint64_t)q->a_sb1 * es : fbA};
         const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)BLOCK_M, 1, 1};
-        if ((rc = make_tmap(&prm.tmA, q->ab_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
+        if ((rc = make_tmap(&prm.tmA, tm_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
         const uint64_t dimsB[4] = {(uint64_t)q->K, (uint64_t)q->Ncols, prm.b_bm2 ? (uint64_t)q->batch2 : 1, prm.b_bm1 ? (uint64_t)q->batch1 : 1};
         const uint64_t strB[3] = {(uint64_t)q->ldb * es, prm.b_bm2 ? (uint64_t)q->b_sb2 * es : fbB, prm.b_bm1 ? (uint64_t)q->b_sb1 * es : fbB};
         const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)b_box_rows, 1, 1};
-        if ((rc = make_tmap(&prm.tmB, q->ab_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
+        if ((rc = make_tmap(&prm.tmB, tm_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;
         VF_CHECK_ARG(q->causal_block == 0 || (q->causal_block % bk == 0 || bk % q->causal_block == 0), "vf_tc_gemm: causal block");
         grid = dim3((q->M + BLOCK_M - 1) / BLOCK_M, (q->Ncols + block_n - 1) / block_n, q->batch1 * q->batch2);
     }
@@ -1711,7 +1897,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     }
     const long long sched_units = k2 ? num_sms / 2 : num_sms;       // persistent CTAs (or CTA pairs)
     const dim3 pgrid((unsigned)((total < sched_units ? total : sched_units) * (k2 ? 2 : 1)), 1, 1);
-    prm.idesc = make_idesc(tf32, k2 ? 2 * BLOCK_M : BLOCK_M, block_n);
+    prm.idesc = make_idesc(tf32, k2 ? 2 * BLOCK_M : BLOCK_M, block_n, exact);
     {
         auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };

@@ -95,8 +95,18 @@ class MIGT:
                 sd[k] = torch.nn.init.trunc_normal_(torch.empty(shp), std=0.02, a=-0.04, b=0.04, generator=g)
         return self.load_state_dict(sd)
 
+    _keys_to_ignore_on_load_unexpected = [r"h\.\d+\.attn\.bias"]      # migt.py:242 (causal-mask buffers of older checkpoints)
+
     def load_state_dict(self, state_dict, strict=True):
-        sd = OrderedDict(state_dict.items())
+        import re
+        ign = [re.compile(p) for p in self._keys_to_ignore_on_load_unexpected]
+        sd = OrderedDict((k, v) for k, v in state_dict.items() if not any(r.fullmatch(k) for r in ign))
+        if not strict:
+            shapes = self.param_shapes()
+            sd = OrderedDict((k, v) for k, v in sd.items() if k in shapes)
+            if self._sd is not None:
+                for k in shapes:
+                    sd.setdefault(k, self._sd[k])
         if strict:
             want, got = set(self.expected_keys()), set(sd.keys())
             if want - got:
@@ -286,6 +296,14 @@ class MIGT:
         Lt, d = self.n_image_tokens, cfg.d_model
         ids = self._in(ids_in.reshape(B, T, -1), torch.int32)
         assert ids.shape[2] == Lt, "input_ids must hold token_image_size**2 tokens per view"
+        if kwargs.get("validate_ids", compute_losses):
+            # the embedding gather and the cross-entropy label read are unchecked on the device: ids beyond the table
+            # (or a MASK / LOC token used as a CE label) would read out of bounds -> fail here instead (one D2H sync)
+            lo, hi = int(ids.min()), int(ids.max())
+            limit = cfg.n_embeddings if compute_losses else cfg.n_embeddings + 2
+            if lo < 0 or hi >= limit:
+                raise ValueError(f"input_ids out of range [{lo}, {hi}]: " + ("cross-entropy labels must be real tokens < n_embeddings"
+                                 if compute_losses else "ids must be < n_embeddings + 2"))
         poses = torch.as_tensor(inputs["poses"])
         if poses.dtype != torch.float32:
             raise AssertionError("poses must be float32")            # tf.debugging.assert_type, migt.py:346

@@ -6,6 +6,8 @@ Three precisions, all of them CUDA (there is no CPU path):
   * ``tf32``  same kernels with fp32 operands fed to ``tcgen05.mma.kind::tf32`` (the arithmetic the reference
               itself ran on A100 with torch 1.7 / TF 2.4 defaults).
   * ``fp32``  exact CUDA-core path (FFMA), used for strict parity against the oracle.
+  * ``x3``    (VQGAN only) fp32-faithful 3x3 convolutions on the tensor cores (split-fp16 operands, 3 MMAs per product,
+              chunked accumulation); 1x1 convs / attention blocks on the fp32 CUDA-core path.  Same codebook indices as ``fp32``.
 """
 import torch
 
@@ -14,12 +16,15 @@ from . import _lib as L
 
 class Precision:
     def __init__(self, name):
-        if name not in ("bf16", "tf32", "fp32"):
-            raise ValueError(f"precision must be bf16|tf32|fp32, got {name}")
+        if name not in ("bf16", "tf32", "fp32", "x3"):
+            raise ValueError(f"precision must be bf16|tf32|fp32|x3, got {name}")
         self.name = name
         self.use_tc = name != "fp32"
-        self.opd = torch.bfloat16 if name == "bf16" else torch.float32   # dtype of GEMM operands
-        self.k_align = 64 if name == "bf16" else 32                      # channels per 128-byte K block
+        # x3: fp32-faithful tensor-core convolutions — operands travel as split fp16 pairs (torch.float16, [hi | lo] channels),
+        # three MMAs per product block, chunked accumulation (vf_tc_gemm.cu EXACT_LO_SCALE); everything else as in fp32
+        self.split = name == "x3"
+        self.opd = {"bf16": torch.bfloat16, "x3": torch.float16}.get(name, torch.float32)   # dtype of conv operands
+        self.k_align = 32 if name == "tf32" else 64                      # channels per 128-byte K block
 
     def __repr__(self):
         return f"Precision({self.name})"

@@ -38,7 +38,10 @@ class _Conv3:
         self.tc = (not exact) and prec.use_tc and kh == 3 and cin % prec.k_align == 0 and cout % 16 == 0 and cout >= 64
         self.small_cin = kh == 3 and cin == 3 and cout % 16 == 0 and cout <= 128     # conv_in: dedicated exact kernel
         self.small_cout = kh == 3 and cin == 128 and cout == 3                       # conv_out: dedicated exact kernel
-        if self.tc:
+        if self.tc and prec.split:
+            # exact mode: per tap [hi(Cin) | lo(Cin)] fp16 halves of the fp32 weights
+            self.w_nk = L.split_f16x2(w.permute(0, 2, 3, 1).reshape(cout * kh * kw, cin).contiguous()).reshape(cout, kh * kw * 2 * cin)
+        elif self.tc:
             self.w_nk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(prec.opd).contiguous()   # [Cout, tap*Cin+c]
         else:
             self.w_kn = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()                # [tap*Cin+c, Cout]
@@ -53,7 +56,7 @@ class VQGAN:
         self.config = load_config(config)
         # ``mixed``: the encoder (whose output feeds the bit-exact codebook argmin) runs in the fp32-faithful ``exact`` arithmetic,
         # the decoder (pixels within a tolerance) on the bf16 tensor-core path.  One precision name otherwise serves both halves.
-        enc_name, dec_name = {"mixed": (os.environ.get("VF_EXACT_ENCODER", "fp32"), "bf16")}.get(precision, (precision, precision))
+        enc_name, dec_name = {"mixed": (os.environ.get("VF_EXACT_ENCODER", "x3"), "bf16")}.get(precision, (precision, precision))
         self.precision = precision
         self.enc_prec, self.dec_prec = Precision(enc_name), Precision(dec_name)
         self.prec = self.dec_prec                  # quantizer / glue policy
@@ -234,12 +237,15 @@ class VQGAN:
         def conv(n, exact=False):
             return _Conv3(sd[n + ".weight"], sd[n + ".bias"], prec, dev, exact=exact)
 
+        def lprec():      # precision of the 1x1 convs / attention GEMMs of the half being built (x3: they stay on the fp32 path)
+            return self.exact if prec.split else prec
+
         def lin(n, p=None):
             wt = sd[n + ".weight"]
-            return Linear(wt.reshape(wt.shape[0], wt.shape[1]), sd[n + ".bias"], p or prec, dev)
+            return Linear(wt.reshape(wt.shape[0], wt.shape[1]), sd[n + ".bias"], p or lprec(), dev)
 
         def rb(n):
-            d = dict(n1=gn(n + ".norm1"), c1=conv(n + ".conv1"), n2=gn(n + ".norm2"), c2=conv(n + ".conv2"), prec=prec)
+            d = dict(n1=gn(n + ".norm1"), c1=conv(n + ".conv1"), n2=gn(n + ".norm2"), c2=conv(n + ".conv2"), prec=prec, lprec=lprec())
             if (n + ".nin_shortcut.weight") in sd:
                 d["sc"] = lin(n + ".nin_shortcut")
             return d
@@ -247,9 +253,9 @@ class VQGAN:
         def at(n):
             wq, wk, wv = (sd[f"{n}.{p}.weight"] for p in ("q", "k", "v"))
             c = wq.shape[0]
-            qk = Linear(torch.cat([wq.reshape(c, c), wk.reshape(c, c)], 0), torch.cat([sd[n + ".q.bias"], sd[n + ".k.bias"]]), prec, dev)
-            return dict(norm=gn(n + ".norm"), qk=qk, v=Linear(wv.reshape(c, c), sd[n + ".v.bias"], prec, dev),
-                        proj=lin(n + ".proj_out"), c=c, prec=prec)
+            qk = Linear(torch.cat([wq.reshape(c, c), wk.reshape(c, c)], 0), torch.cat([sd[n + ".q.bias"], sd[n + ".k.bias"]]), lprec(), dev)
+            return dict(norm=gn(n + ".norm"), qk=qk, v=Linear(wv.reshape(c, c), sd[n + ".v.bias"], lprec(), dev),
+                        proj=lin(n + ".proj_out"), c=c, prec=lprec())
 
         nres = len(cfg.ch_mult)
         res = [cfg.image_size // 2 ** i for i in range(nres)]
@@ -336,8 +342,9 @@ class VQGAN:
             a, norm2 = L.groupnorm(h, *rbw["n2"], swish=True, out_dtype=self._act_dtype(rbw["c2"], prec)), None
         if "sc" in rbw:
             n, hh, ww, c = x.shape
-            xs = x if prec.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=prec.opd, normalize=False)
-            res = linear(prec, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
+            lp = rbw["lprec"]
+            xs = x if lp.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=lp.opd, normalize=False)
+            res = linear(lp, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
         else:
             res = x
         if norm2 is not None:
@@ -491,8 +498,8 @@ class VQGAN:
     def encode_nhwc(self, x_nhwc):
         """TF-twin convention (viewformer/models/vqgan.py:291-295): NHWC in, (quant NHWC, diff, codes [N,h,w])."""
         self._need_weights()
+        self._check_layout(torch.as_tensor(x_nhwc), 3, "encode_nhwc")
         x = self._in(x_nhwc)
-        self._check_layout(x, 3, "encode_nhwc")
         zr, hh, ww = self.encode_rows(x)
         n = x.shape[0]
         quant, diff, idx = self._quantize(zr)
@@ -525,9 +532,8 @@ class VQGAN:
 
     def encode(self, x):
         self._need_weights()
-        x = self._in(x)
-        self._check_layout(x, 1, "encode")
-        x = L.nchw_to_nhwc(x)
+        self._check_layout(torch.as_tensor(x), 1, "encode")
+        x = L.nchw_to_nhwc(self._in(x))
         zr, hh, ww = self.encode_rows(x)
         n = x.shape[0]
         quant, diff, idx = self._quantize(zr)
