@@ -8,17 +8,16 @@ import torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scenes", type=int, default=32)
-ap.add_argument("--precision", default="bf16")
+ap.add_argument("--precision", default="mixed")
 ap.add_argument("--part", default="all", choices=["all", "encode", "migt", "decode"])
 a = ap.parse_args()
 
-from bench import synth_inputs  # noqa: E402
-from viewformer_b200 import VQGAN, MIGT, generate_batch_predictions  # noqa: E402
+from bench import synth_inputs, model_pair  # noqa: E402
+from viewformer_b200 import generate_batch_predictions  # noqa: E402
 from viewformer_b200.config import VQGANConfig, MIGTConfig  # noqa: E402
 
 dev = torch.device("cuda", 0)
-cb = VQGAN(VQGANConfig(), precision=a.precision, device=dev).init_weights(0)
-tr = MIGT(MIGTConfig(localization_weight="0"), precision=a.precision, device=dev).init_weights(0)
+cb, tr = model_pair(a.precision, VQGANConfig(), MIGTConfig(localization_weight="0"), dev)
 images, cams = synth_inputs(a.scenes, 1234)
 images, cams = images.to(dev), cams.to(dev)
 
