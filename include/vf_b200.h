@@ -177,6 +177,15 @@ int vf_vq_lookup(const float* z, const float* Et, const float* esq, int64_t M, i
 int vf_vq_split3(const float* x, int64_t rows, int D, int codebook, void* out_bf16, vf_stream_t s);
 int vf_vq_select(const float* scores, const float* z, const float* Et, const float* esq, int64_t M, int D, int K, float tol,
                  int64_t* idx, float* quant, double* diff_sum, int* n_rescored, vf_stream_t s);
+/* Fused lookup (same result as vf_vq_lookup; viewformer_b200/csrc/vf_vq_fused.cu): one tcgen05 kernel reads every z row ONCE
+ * (fp32 -> fp16 in shared memory), scores it against Eh = fp16(-2 e) [K,D] (vf_vq_prepare_codebook_f16) on CTA pairs and keeps the
+ * two best codes per row straight from TMEM — no score matrix in HBM, 4*D + 8 bytes of traffic per row.  Rows whose two best scores
+ * lie within the fp16 rounding bound (tol_factor x worst case; 0.25 recommended) are settled exactly in fp64 by a second kernel.
+ *   D % 64 == 0, D <= 256, K % 256 == 0, K <= 1024, M < 2^31.  worklist: int4[M] scratch; counter: int[2] scratch, on return
+ *   counter[0] = rows settled between two candidates, counter[1] = rows settled over all codes.  quant / diff_sum nullable. */
+int vf_vq_prepare_codebook_f16(const float* Et, int K, int D, void* Eh_f16, vf_stream_t s);
+int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const float* Et, const float* esq, int64_t M, int D, int K,
+                       float tol_factor, int64_t* idx, void* worklist, int* counter, float* quant, double* diff_sum, vf_stream_t s);
 int vf_gather_rows(const float* table, const int64_t* idx, int64_t M, int D, int64_t n_rows, float* out, vf_stream_t s);
 /* training statistics of QuantizeEMA (utils_th.py:47-48): counts[K] += onehot, embed_sum[D,K] += z^T onehot */
 int vf_vq_ema_stats(const float* z, const int64_t* idx, int64_t M, int D, int K,

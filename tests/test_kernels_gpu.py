@@ -644,3 +644,58 @@ def test_tc_downsample_exact_split_fp16(L, cin, cout, n, hw):
     e = (got.double().cpu() - want).abs()
     print(f"[exact downsample {cin}->{cout} hw{hw}] max {e.max() / want.abs().mean():.2e}")
     assert float(e.max() / want.abs().mean()) < 4e-6
+
+
+# ----------------------------------------------------------------------------- fused tcgen05 codebook lookup
+def test_vq_lookup_fused_bit_exact(L, golden_dir):
+    """One-pass fused lookup (fp16 distance GEMM on CTA pairs, top-2 from TMEM, fp64 settlement of near-ties) == the REAL
+    reference's indices on the golden rows (4096 gaussian + 512 adversarial near-ties + 64 exact codes), ragged / empty M,
+    quant + commit-loss outputs, and == the exact fp32 kernel on 40 960 random rows."""
+    import os
+    from oracle import synth
+    gd = np.load(os.path.join(golden_dir, "vq_lookup.npz"))
+    E, z = synth.make_lookup_inputs(int(gd["seed"]))
+    et, esq = L.vq_prepare_codebook(E.cuda())
+    eh = L.vq_prepare_codebook_f16(et)
+    assert torch.equal(eh.cpu(), (-2.0 * E.t()).half())
+    idx, quant, dsum, cnt = L.vq_lookup_fused(z.cuda(), et, esq, eh, return_counts=True)
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy()
+    print(f"[vq_lookup_fused] mismatches vs reference: {int((idx != gd['idx']).sum())}/{idx.size}; settled exactly: pair {int(cnt[0])}, all-codes {int(cnt[1])}")
+    assert np.array_equal(idx, gd["idx"])
+    e = E.t()[torch.from_numpy(idx)]
+    assert torch.equal(quant.cpu(), z + (e - z))
+    want = float(((e - z).double() ** 2).sum())
+    assert abs(float(dsum) - want) / want < 1e-6
+    for m in (77, 128, 129, 255, 257, 1000):
+        i2, _, _ = L.vq_lookup_fused(z[:m].contiguous().cuda(), et, esq, eh, want_quant=False, want_diff=False)
+        assert np.array_equal(i2.cpu().numpy(), gd["idx"][:m]), m
+    i0, _, _ = L.vq_lookup_fused(z[:0].contiguous().cuda(), et, esq, eh)
+    assert i0.numel() == 0
+    zz = torch.randn(40960, 256, generator=g(123)).cuda()
+    a, _, _, cnt = L.vq_lookup_fused(zz, et, esq, eh, want_quant=False, want_diff=False, return_counts=True)
+    b, _, _ = L.vq_lookup(zz, et, esq, want_quant=False, want_diff=False)
+    print(f"[vq_lookup_fused] 40960 random rows: mismatches {int((a != b).sum())}; settled exactly: pair {int(cnt[0])}, all-codes {int(cnt[1])}")
+    assert torch.equal(a, b)
+    # worst-case tolerance (tol_factor = 1): same indices, more rows take the exact pass
+    a1, _, _, cnt1 = L.vq_lookup_fused(zz, et, esq, eh, want_quant=False, want_diff=False, tol_factor=1.0, return_counts=True)
+    assert torch.equal(a1, b) and int(cnt1.sum()) >= int(cnt.sum())
+    # rows beyond fp16 range / non-finite rows go to the exact pass instead of producing garbage
+    zbig = zz[:300].clone()
+    zbig[5] *= 1e5
+    zbig[17, 3] = 7e4
+    ab, _, _ = L.vq_lookup_fused(zbig, et, esq, eh, want_quant=False, want_diff=False)
+    bb, _, _ = L.vq_lookup(zbig, et, esq, want_quant=False, want_diff=False)
+    assert torch.equal(ab, bb)
+
+
+@pytest.mark.parametrize("D,K", [(64, 256), (128, 512)])
+def test_vq_lookup_fused_small_codebooks(L, D, K):
+    E = (torch.rand(D, K, generator=g(D)) * 2 - 1) * 3 ** 0.5
+    z = torch.randn(3000, D, generator=g(K))
+    z[:200] = E.t()[torch.randint(0, K, (200,), generator=g(1))] + 1e-3 * torch.randn(200, D, generator=g(2))      # near codes
+    et, esq = L.vq_prepare_codebook(E.cuda())
+    eh = L.vq_prepare_codebook_f16(et)
+    a, qa, da = L.vq_lookup_fused(z.cuda(), et, esq, eh)
+    b, qb, db = L.vq_lookup(z.cuda(), et, esq)
+    assert torch.equal(a, b) and torch.equal(qa, qb) and abs(float(da) - float(db)) <= 1e-9 * abs(float(db))

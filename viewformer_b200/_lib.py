@@ -24,6 +24,7 @@ EXPORTS = [
     "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
+    "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused",
 ]
 
 
@@ -502,6 +503,37 @@ def vq_lookup_tc(z_rows, et, esq, et3, want_quant=True, want_diff=True, tol=1e-4
     _check(lib.vf_vq_select(_p(scores), _p(z_rows), _p(et), _p(esq), C.c_int64(m), d, k, C.c_float(tol), _p(idx), _p(quant), _p(dsum),
                             _p(nres), _stream()))
     return (idx, quant, dsum, nres) if count_rescored else (idx, quant, dsum)
+
+
+def vq_prepare_codebook_f16(et):
+    """Et f32 [K,D] -> fp16(-2 e) [K,D], the B operand of the fused lookup."""
+    lib = load(True)
+    _dev(et, torch.float32)
+    k, d = et.shape
+    eh = torch.empty((k, d), dtype=torch.float16, device=et.device)
+    _check(lib.vf_vq_prepare_codebook_f16(_p(et), k, d, _p(eh), _stream()))
+    return eh
+
+
+def vq_fused_ok(d, k):
+    return d % 64 == 0 and d <= 256 and k % 256 == 0 and k <= 1024
+
+
+def vq_lookup_fused(z_rows, et, esq, eh, want_quant=True, want_diff=True, tol_factor=0.25, return_counts=False):
+    """Fused tcgen05 lookup (vf_vq_fused.cu): z read once, top-2 from TMEM, exact fp64 settlement of near-ties.  Same outputs as
+    vq_lookup; ``return_counts`` adds the int32[2] tensor (rows settled between two candidates, rows settled over all codes)."""
+    lib = load(True)
+    _dev(z_rows, torch.float32)
+    m, d = z_rows.shape
+    k = et.shape[0]
+    idx = torch.empty((m,), dtype=torch.int64, device=z_rows.device)
+    work = torch.empty((max(m, 1), 4), dtype=torch.int32, device=z_rows.device)
+    counter = torch.empty((2,), dtype=torch.int32, device=z_rows.device)
+    quant = torch.empty((m, d), dtype=torch.float32, device=z_rows.device) if want_quant else None
+    dsum = torch.zeros((1,), dtype=torch.float64, device=z_rows.device) if want_diff else None
+    _check(lib.vf_vq_lookup_fused(_p(z_rows), _p(eh), _p(et), _p(esq), C.c_int64(m), d, k, C.c_float(tol_factor), _p(idx), _p(work),
+                                  _p(counter), _p(quant), _p(dsum), _stream()))
+    return (idx, quant, dsum, counter) if return_counts else (idx, quant, dsum)
 
 
 def gather_rows(table, idx):

@@ -218,6 +218,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 columns (half the registers of tmem_ld_32x32: the exact-mode epilogue keeps 64 running sums per thread)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 struct TileInfo {
     int m0, n0, b1, b2, img0, oy0, ox0, nkb;
@@ -1168,17 +1179,22 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                     const float sc = ck < nsmall ? EXACT_LO_SCALE : 1.0f;
                     mbar_wait(&tmem_full_bar[a], aph);
                     tcgen05_fence_after();
-                    uint32_t r[32];
                     const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 256 + grp * 64);
-                    tmem_ld_32x32(ta, r);
+                    uint32_t r[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) a0[j] = fmaf(__uint_as_float(r[j]), sc, a0[j]);
-                    tmem_ld_32x32(ta + 32, r);
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+                    for (int q = 0; q < 4; ++q) {
+                        tmem_ld_32x16(ta + 16 * q, r);
+                        if (q == 3) {                                   // all TMEM reads of this chunk are done
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+                        }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) a1[j] = fmaf(__uint_as_float(r[j]), sc, a1[j]);
+                        for (int j = 0; j < 16; ++j) {
+                            if (q < 2) a0[16 * q + j] = fmaf(__uint_as_float(r[j]), sc, a0[16 * q + j]);
+                            else a1[16 * (q - 2) + j] = fmaf(__uint_as_float(r[j]), sc, a1[16 * (q - 2) + j]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {

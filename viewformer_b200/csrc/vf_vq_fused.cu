@@ -1,0 +1,507 @@
+// Fused codebook lookup on tcgen05 (sm_100a):  idx[m] = argmin_k |z_m - e_k|^2   — viewformer/models/utils_th.py:34-41.
+//
+// HBM traffic is the algorithmic minimum: every z row (fp32, 4*D bytes) is read ONCE, one int64 index is written; the distance
+// matrix never exists outside TMEM.  Per CTA PAIR (thread-block cluster of 2 = one `cta_group::2` MMA of M = 256):
+//   converter warps   z fp32 [128 rows x D] --LDG.128--> fp16 --> 128B-swizzled K-major A tile in shared memory (double-buffered);
+//                     also |z|^2 per row and a range check (|z_i| beyond fp16 -> the row goes to the exact path)
+//   TMA producer      B stages: this CTA's HALF (128 codes x 64 k) of a 256-code sub-tile of Eh = fp16(-2 e)   [K, D] K-major
+//   MMA issuer        (leader CTA) S[256 rows, 256 codes] = A . B^T into one of two TMEM stages (fp32), 4 sub-tiles per row tile
+//   epilogue warps    TMEM -> registers: s = S + |e|^2 (fp32, shared memory table), the code index is packed into the 6 low mantissa
+//                     bits and a running (min, second min) pair per (row, 64-code set) is kept with 3 FMNMX per score
+//   merge (4 warps)   per row: best code over the 16 sets; if the runner-up lies within the fp16 rounding bound of the best the row
+//                     is queued for the exact pass (PAIR: both candidates known; FULL: a third may hide inside one set)
+// vq_rescue_kernel then settles queued rows in fp64 (direct sum of squared differences, ties to the smaller index — the same rule as
+// vf_vq_lookup / vf_vq_select), so the indices returned equal the fp32 kernels' on every input.
+//
+// Rounding model (why the tolerance is safe): fp16 operands carry 11 significand bits, |d(z.e)| <= 2^-10 sum|z_i e_i| <= 2^-10 |z||e|;
+// the score -2 z.e + |e|^2 of two codes therefore moves by at most 2^-9 |z| (|e_a| + |e_b|) against each other (worst case, all
+// roundings aligned; rms is ~40x smaller).  `tol_factor` scales that bound (1.0 = worst case; default 0.25 = ~10 sigma); index
+// packing (6 mantissa bits) and the truncating TMEM accumulation add 2^-16 |s| which is always included unscaled.
+#include "vf_tcgen05.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+using namespace vftc;
+
+constexpr int TM = 128;                 // z rows per CTA tile (256 per pair)
+constexpr int TN = 256;                 // codes per sub-tile (MMA N)
+constexpr int KB_BYTES = TM * 128;      // one A k-block: 128 rows x 128 B
+constexpr int A_BYTES = 4 * KB_BYTES;   // up to D = 256
+constexpr int B_STAGE = 128 * 128;      // this CTA's half of a (256 codes x 64 k) stage
+constexpr int B_STAGES = 4;
+constexpr int NCONV = 8, NEPI = 16;
+constexpr int THREADS = 64 + 32 * (NCONV + NEPI);      // 832
+constexpr int CONV_W0 = 2, EPI_W0 = 2 + NCONV;
+constexpr int MAXK = 1024;
+constexpr int SETS = 16;                // (sub-tile, column group) sets per row, 2 keys each
+constexpr int ZRING = 4;                // |z|^2 / range-flag ring (the merge of tile t reads them after the converters moved on)
+constexpr int SMEM = 2 * A_BYTES + B_STAGES * B_STAGE + MAXK * 4 + ZRING * TM * 4 * 2 + SETS * 2 * TM * 4 + 512 + 1024;
+
+struct VqParams {
+    CUtensorMap tmB;            // Eh [K, D] fp16: box {64, 128}
+    const float* z;             // [M, D]
+    const float* esq;           // [K]
+    long long M;
+    int D, K, kblocks, nsub;
+    long long n_pair_tiles;     // ceil(M / 256)
+    float tol_factor;
+    long long* idx;             // [M]
+    int4* worklist;             // {row, c1, c2 (-1: all codes), 0}
+    int* counter;               // [0] queued rows, [1] of which FULL
+    unsigned idesc;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cta(const void* p, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(cta));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope: the peer CTA's arrivals
+    for (uint32_t i = 0; i < (1u << 24); ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    printf("vq_fused: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void commit_2sm(uint64_t* bar) {       // arrives on the same barrier offset in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_2sm_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __grid_constant__ VqParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                          // [2][A_BYTES]
+    uint8_t* sB = sA + 2 * A_BYTES;                              // [B_STAGES][B_STAGE]
+    float* esq_s = reinterpret_cast<float*>(sB + B_STAGES * B_STAGE);            // [MAXK]
+    float* zz_s = esq_s + MAXK;                                  // [ZRING][TM]
+    int* bad_s = reinterpret_cast<int*>(zz_s + ZRING * TM);      // [ZRING][TM]
+    uint32_t* res_s = reinterpret_cast<uint32_t*>(bad_s + ZRING * TM);           // [SETS][TM][2] packed keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res_s + SETS * TM * 2);
+    uint64_t* b_full = bars;                    // [B_STAGES]  (leader's copy is the one that counts)
+    uint64_t* b_empty = b_full + B_STAGES;      // [B_STAGES]
+    uint64_t* a_ready = b_empty + B_STAGES;     // [2]  leader: 2 * NCONV arrivals
+    uint64_t* a_free = a_ready + 2;             // [2]  multicast commit
+    uint64_t* t_full = a_free + 2;              // [2]  multicast commit
+    uint64_t* t_empty = t_full + 2;             // [2]  leader: 2 * NEPI arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const long long pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) prefetch_tmap(&p.tmB);
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&a_ready[a], 2 * NCONV);
+            mbar_init(&a_free[a], 1);
+            mbar_init(&t_full[a], 1);
+            mbar_init(&t_empty[a], 2 * NEPI);
+        }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < p.K; i += THREADS) esq_s[i] = __ldg(p.esq + i);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: this CTA's half of every B stage =====================
+        if (elect_one()) {
+            const uint32_t lead_full = mapa_cta(b_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = pair0; t < p.n_pair_tiles; t += pair_stride) {
+                for (int n = 0; n < p.nsub; ++n)
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&b_empty[stage], phase ^ 1, "vq_fused(b_empty)");
+                        if (rank == 0) mbar_expect_tx(&b_full[stage], 2 * B_STAGE);
+                        tma_load_4d_2sm(sB + stage * B_STAGE, &p.tmB, lead_full + (uint32_t)(stage * 8), kb * 64, n * TN + (int)rank * 128, 0, 0);
+                        if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA issues for the pair) =====================
+        if (rank == 0 && elect_one()) {
+            int stage = 0, it = 0, tl = 0;
+            uint32_t phase = 0;
+            for (long long t = pair0; t < p.n_pair_tiles; t += pair_stride, ++tl) {
+                const int ab = tl & 1;
+                mbar_wait_cluster(&a_ready[ab], (tl >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + ab * A_BYTES);
+                for (int n = 0; n < p.nsub; ++n) {
+                    const int acc = it & 1;
+                    mbar_wait_cluster(&t_empty[acc], ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TN);
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&b_full[stage], phase, "vq_fused(b_full)");
+                        tc_fence_after();
+                        const uint64_t adesc = sw128_desc(a_addr + kb * KB_BYTES), bdesc = sw128_desc(smem_u32(sB + stage * B_STAGE));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_2sm_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        commit_2sm(&b_empty[stage]);
+                        if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    commit_2sm(&t_full[acc]);
+                    ++it;
+                }
+                commit_2sm(&a_free[ab]);
+            }
+        }
+    } else if (warp < EPI_W0) {
+        // ===================== converters: z fp32 -> fp16 swizzled A tile, |z|^2, range check =====================
+        const int cw = warp - CONV_W0;
+        const uint32_t lead_ready = mapa_cta(a_ready, 0);
+        const int kb = lane >> 3, ch = lane & 7;                  // this lane's 8 elements of a row: k = kb*64 + ch*8 ..
+        const bool lane_ok = lane * 8 < p.D;
+        int tl = 0;
+        for (long long t = pair0; t < p.n_pair_tiles; t += pair_stride, ++tl) {
+            const int ab = tl & 1;
+            mbar_wait(&a_free[ab], ((tl >> 1) & 1) ^ 1, "vq_fused(a_free)");
+            uint8_t* At = sA + ab * A_BYTES;
+            const long long row0 = t * 256 + (long long)rank * TM;
+#pragma unroll 1
+            for (int rb = 0; rb < TM / NCONV; rb += 4) {           // 4 rows of this warp in flight: 8 x LDG.128 per lane
+                float4 v[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = cw + (rb + u) * NCONV;
+                    const long long gr = row0 + r;
+                    if (gr < p.M && lane_ok) {
+                        const float4* src = reinterpret_cast<const float4*>(p.z + gr * p.D + lane * 8);
+                        v[u][0] = __ldg(src);
+                        v[u][1] = __ldg(src + 1);
+                    } else {
+                        v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = cw + (rb + u) * NCONV;
+                    const float e[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+                    float ss = 0.f, mx = 0.f;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ss = fmaf(e[2 * q], e[2 * q], ss);
+                        ss = fmaf(e[2 * q + 1], e[2 * q + 1], ss);
+                        mx = fmaxf(mx, fmaxf(fabsf(e[2 * q]), fabsf(e[2 * q + 1])));
+                        const __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
+                        w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    if (lane_ok)
+                        *reinterpret_cast<uint4*>(At + kb * KB_BYTES + r * 128 + ((ch ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    ss = warp_sum(ss);
+                    mx = warp_max(mx);
+                    if (lane == 0) {
+                        zz_s[(tl & (ZRING - 1)) * TM + r] = ss;
+                        bad_s[(tl & (ZRING - 1)) * TM + r] = !(mx < 60000.f && ss == ss);      // beyond fp16 range (or NaN): the exact pass decides this row
+                    }
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_ready + (uint32_t)(ab * 8));
+        }
+    } else {
+        // ===================== epilogue: top-2 per (row, 64-code set) straight from TMEM =====================
+        const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32)
+        const int grp = (warp - EPI_W0) >> 2;                     // columns [64g, 64g+64) of every sub-tile
+        const int row = quarter * 32 + lane;
+        const uint32_t lead_empty = mapa_cta(t_empty, 0);
+        int it = 0, tl = 0;
+        for (long long t = pair0; t < p.n_pair_tiles; t += pair_stride, ++tl) {
+            if (tl > 0) asm volatile("bar.sync 2, %0;" ::"n"(32 * NEPI) : "memory");          // previous tile's merge has read res_s
+            for (int n = 0; n < p.nsub; ++n) {
+                const int acc = it & 1;
+                mbar_wait(&t_full[acc], (it >> 1) & 1, "vq_fused(t_full)");
+                ++it;
+                tc_fence_after();
+                float m1 = __int_as_float(0x7f800000), m2 = m1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TN + grp * 64 + h * 32), r);
+                    if (h == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(lead_empty + (uint32_t)(acc * 8));
+                    }
+                    const float4* e4 = reinterpret_cast<const float4*>(esq_s + n * TN + grp * 64 + h * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 e = e4[j4];
+                        const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = j4 * 4 + q;
+                            const float s = __uint_as_float(r[j]) + ev[q];
+                            const float k = __uint_as_float((__float_as_uint(s) & 0xFFFFFFC0u) | (uint32_t)(h * 32 + j));
+                            m2 = fminf(m2, fmaxf(m1, k));
+                            m1 = fminf(m1, k);
+                        }
+                    }
+                }
+                uint32_t* dst = res_s + ((n * 4 + grp) * TM + row) * 2;
+                dst[0] = __float_as_uint(m1);
+                dst[1] = __float_as_uint(m2);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory");                        // all sets of this tile are in res_s
+            if (grp == 0) {
+                const long long gr = t * 256 + (long long)rank * TM + row;
+                if (gr < p.M) {
+                    float bv = __int_as_float(0x7f800000);
+                    int bc = 0x7fffffff, bset = -1;
+                    const int nsets = p.nsub * 4;
+                    for (int s = 0; s < nsets; ++s) {
+                        const uint32_t k = res_s[(s * TM + row) * 2];
+                        const float v = __uint_as_float(k & 0xFFFFFFC0u);
+                        const int c = (s >> 2) * TN + (s & 3) * 64 + (int)(k & 63u);
+                        if (v < bv || (v == bv && c < bc)) { bv = v; bc = c; bset = s; }
+                    }
+                    bool bad = bad_s[(tl & (ZRING - 1)) * TM + row] != 0;
+                    if (bset < 0) { bc = 0; bad = true; }                                   // every score was NaN / inf
+                    const float znorm = sqrtf(zz_s[(tl & (ZRING - 1)) * TM + row]);
+                    const float eb = sqrtf(esq_s[bc]);
+                    int within = 0, oc = -1, oset = -1;
+                    for (int s = 0; s < nsets; ++s)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t k = res_s[(s * TM + row) * 2 + q];
+                            if ((k & 0x7f800000u) == 0x7f800000u) continue;                  // empty slot (+inf)
+                            const float v = __uint_as_float(k & 0xFFFFFFC0u);
+                            const int c = (s >> 2) * TN + (s & 3) * 64 + (int)(k & 63u);
+                            if (c == bc) continue;
+                            const float tol = p.tol_factor * 0.001953125f * znorm * (eb + sqrtf(esq_s[c])) + 1.52587890625e-5f * (fabsf(v) + fabsf(bv));
+                            if (v - bv <= tol) { ++within; oc = c; oset = s; }
+                        }
+                    p.idx[gr] = (long long)bc;
+                    if (within > 0 || bad) {
+                        const bool full = bad || within > 1 || oset == bset;               // a third candidate could hide inside one set
+                        // PAIR entries fill the worklist from the front, FULL entries from the back
+                        if (full) p.worklist[p.M - 1 - atomicAdd(p.counter + 1, 1)] = make_int4((int)gr, bc, -1, 0);
+                        else p.worklist[atomicAdd(p.counter, 1)] = make_int4((int)gr, bc, oc, 0);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// Exact pass over the queued rows: fp64 direct sum of squared differences, ties to the smaller index.
+// PAIR entries (front of the worklist): one warp per entry, the two known candidates.  FULL entries (back of the worklist): one CTA per
+// entry, every thread scores K / 256 codes, block-wide argmin.
+__global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict__ z, const float* __restrict__ Et, int D, int K, long long M,
+                                                        const int4* __restrict__ worklist, const int* __restrict__ counter,
+                                                        long long* __restrict__ idx) {
+    __shared__ double sd[8];
+    __shared__ int si[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int n_pair = counter[0], n_full = counter[1];
+    for (int i = gw; i < n_pair; i += nw) {
+        const int4 e = worklist[i];
+        const float* zr = z + (long long)e.x * D;
+        double d0 = 0.0, d1 = 0.0;
+        const float* e0 = Et + (long long)e.y * D;
+        const float* e1 = Et + (long long)e.z * D;
+        for (int d = lane; d < D; d += 32) {
+            const double zv = (double)zr[d];
+            const double a = (double)e0[d] - zv, b = (double)e1[d] - zv;
+            d0 += a * a;
+            d1 += b * b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+        if (lane == 0) idx[e.x] = (long long)((d1 < d0 || (d1 == d0 && e.z < e.y)) ? e.z : e.y);
+    }
+    for (int i = blockIdx.x; i < n_full; i += gridDim.x) {
+        const int4 e = worklist[M - 1 - i];
+        const float* zr = z + (long long)e.x * D;
+        double bd = 1e300;
+        int bi = 0x7fffffff;
+        for (int c = threadIdx.x; c < K; c += 256) {
+            const float* ec = Et + (long long)c * D;
+            double dd = 0.0;
+            for (int d = 0; d < D; d += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ec + d));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(zr + d));
+                const double t0 = (double)a.x - (double)b.x, t1 = (double)a.y - (double)b.y, t2 = (double)a.z - (double)b.z, t3 = (double)a.w - (double)b.w;
+                dd += t0 * t0;
+                dd += t1 * t1;
+                dd += t2 * t2;
+                dd += t3 * t3;
+            }
+            if (dd < bd || (dd == bd && c < bi)) { bd = dd; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
+            idx[e.x] = (long long)bi;
+        }
+        __syncthreads();
+    }
+}
+
+// quant = z + (e - z) (straight-through value, utils_th.py:67) and the commit-loss sum  sum (e - z)^2  for given indices
+__global__ void __launch_bounds__(256) vq_gather_diff_kernel(const float* __restrict__ z, const float* __restrict__ Et,
+                                                             const long long* __restrict__ idx, long long M, int D,
+                                                             float* __restrict__ quant, double* __restrict__ diff_sum) {
+    __shared__ double dsum_sh[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    double ds = 0.0;
+    if (row < M) {
+        const float* e = Et + idx[row] * D;
+        const float* zr = z + row * D;
+        for (int d = lane * 4; d < D; d += 128) {
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(e + d));
+            const float4 zv = __ldg(reinterpret_cast<const float4*>(zr + d));
+            if (quant)
+                *reinterpret_cast<float4*>(quant + row * D + d) =
+                    make_float4(__fadd_rn(zv.x, __fsub_rn(ev.x, zv.x)), __fadd_rn(zv.y, __fsub_rn(ev.y, zv.y)),
+                                __fadd_rn(zv.z, __fsub_rn(ev.z, zv.z)), __fadd_rn(zv.w, __fsub_rn(ev.w, zv.w)));
+            const float a = ev.x - zv.x, b = ev.y - zv.y, c = ev.z - zv.z, dd = ev.w - zv.w;
+            ds += (double)(a * a) + (double)(b * b) + (double)(c * c) + (double)(dd * dd);
+        }
+    }
+    if (diff_sum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        if (lane == 0) dsum_sh[warp] = ds;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tsum = 0;
+            for (int w = 0; w < 8; ++w) tsum += dsum_sh[w];
+            atomicAdd(diff_sum, tsum);
+        }
+    }
+}
+
+__global__ void codebook_f16_kernel(const float* __restrict__ Et, long long n, __half* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(-2.0f * Et[i]);
+}
+
+}  // namespace
+
+extern "C" int vf_vq_prepare_codebook_f16(const float* Et, int K, int D, void* Eh_f16, vf_stream_t s) {
+    VF_CHECK_ARG(Et && Eh_f16 && K > 0 && D > 0, "vf_vq_prepare_codebook_f16: bad args");
+    const long long n = (long long)K * D;
+    codebook_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, vf_s(s)>>>(Et, n, reinterpret_cast<__half*>(Eh_f16));
+    VF_CHECK_LAUNCH("vf_vq_prepare_codebook_f16");
+    return VF_OK;
+}
+
+extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const float* Et, const float* esq, int64_t M, int D, int K,
+                                  float tol_factor, int64_t* idx, void* worklist, int* counter, float* quant, double* diff_sum,
+                                  vf_stream_t s) {
+    if (M == 0) return VF_OK;
+    VF_CHECK_ARG(z && Eh_f16 && Et && esq && idx && worklist && counter, "vf_vq_lookup_fused: null pointer");
+    VF_CHECK_ARG(D % 64 == 0 && D <= 256 && K % 256 == 0 && K <= MAXK && M < (1ll << 31),
+                 "vf_vq_lookup_fused: unsupported D=%d K=%d (D %% 64 == 0, D <= 256, K %% 256 == 0, K <= 1024)", D, K);
+    VF_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "vf_vq_lookup_fused: z must be 16-byte aligned");
+    cudaStream_t st = vf_s(s);
+    VqParams prm;
+    memset(&prm, 0, sizeof(prm));
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)K, 1, 1};
+    const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)D * 2 * K, (uint64_t)D * 2 * K};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    int rc;
+    if ((rc = make_tmap_16bit(&prm.tmB, Eh_f16, dims, str, box)) != VF_OK) return rc;
+    prm.z = z; prm.esq = esq; prm.M = M; prm.D = D; prm.K = K;
+    prm.kblocks = D / 64; prm.nsub = K / TN;
+    prm.n_pair_tiles = (M + 255) / 256;
+    prm.tol_factor = tol_factor;
+    prm.idx = reinterpret_cast<long long*>(idx);
+    prm.worklist = reinterpret_cast<int4*>(worklist);
+    prm.counter = counter;
+    prm.idesc = make_idesc_16bit(0, 256, TN);
+    cudaError_t e = cudaMemsetAsync(counter, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: memset: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+    static bool configured = false;
+    if (!configured) {
+        e = cudaFuncSetAttribute(vq_lookup_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+        configured = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    long long pairs = prm.n_pair_tiles < num_sms / 2 ? prm.n_pair_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, vq_lookup_fused_kernel, prm);
+    if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: cluster launch failed: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+    VF_CHECK_LAUNCH("vf_vq_lookup_fused");
+    vq_rescue_kernel<<<num_sms * 2, 256, 0, st>>>(z, Et, D, K, M, prm.worklist, counter, prm.idx);
+    VF_CHECK_LAUNCH("vf_vq_lookup_fused(rescue)");
+    if (quant || diff_sum) {
+        vq_gather_diff_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(z, Et, prm.idx, M, D, quant, diff_sum);
+        VF_CHECK_LAUNCH("vf_vq_lookup_fused(gather)");
+    }
+    return VF_OK;
+}

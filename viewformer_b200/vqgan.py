@@ -290,6 +290,7 @@ class VQGAN:
         emb = sd["quantize.embeddings"].to(dev, torch.float32).contiguous()             # [D,K] (utils_th.py:17-18)
         et, esq = L.vq_prepare_codebook(emb)
         w["q"] = dict(emb=emb, et=et, esq=esq, et3=L.vq_split3(et, True) if self.prec.use_tc else None,
+                      eh=L.vq_prepare_codebook_f16(et) if (self.prec.use_tc and L.vq_fused_ok(*emb.shape)) else None,
                       cs=sd["quantize.ema_cluster_size_hidden"].to(dev, torch.float32).contiguous(),
                       dw=sd["quantize.ema_dw_hidden"].to(dev, torch.float32).contiguous(),
                       counter=int(sd["quantize.counter"]))
@@ -451,7 +452,10 @@ class VQGAN:
     def _quantize(self, z_rows, want_quant=True):
         """QuantizeEMA.forward (utils_th.py:32-68) on rows [M,D]; returns (quant rows | None, diff, idx)."""
         q = self._w["q"]
-        if q["et3"] is not None and z_rows.shape[1] % 64 == 0:
+        if q["eh"] is not None and os.environ.get("VF_VQ_FUSED", "1") != "0":
+            # fused tcgen05 lookup: z read once, scores never leave TMEM, near-ties settled in fp64: same indices as the fp32 kernel
+            idx, quant, dsum = L.vq_lookup_fused(z_rows, q["et"], q["esq"], q["eh"], want_quant=want_quant, want_diff=True)
+        elif q["et3"] is not None and z_rows.shape[1] % 64 == 0:
             # tensor-core distance GEMM (bf16x3) + exact fp64 re-score of every near-minimal candidate: same indices as the fp32 kernel
             idx, quant, dsum = L.vq_lookup_tc(z_rows, q["et"], q["esq"], q["et3"], want_quant=want_quant, want_diff=True)
         else:
@@ -474,6 +478,8 @@ class VQGAN:
         L.vq_ema_update(counts, esum, alpha, corr, self.eps, q["cs"], q["dw"], q["emb"], q["et"], q["esq"])
         if q["et3"] is not None:
             q["et3"] = L.vq_split3(q["et"], True)
+        if q["eh"] is not None:
+            q["eh"] = L.vq_prepare_codebook_f16(q["et"])
         self._refresh_decode_table()
 
     # ------------------------------------------------------------------ NHWC entry points (TF-twin convention)
