@@ -147,6 +147,12 @@ typedef struct {
        norm_swish: 0 = no activation, 1 = x / (1 + e^-x) in fp32 (ex2/rcp; bit-identical to vf_groupnorm_apply's bf16 output),
        2 = packed bf16 h (1 + tanh h), h = x / 2 (one MUFU op per two elements). */
     const float* norm_mean_rstd; const float* norm_gamma; const float* norm_beta; int norm_groups; int norm_swish;
+    /* ab_dtype = VF_F16X2 ("exact" mode: fp32-faithful products on the tensor cores — three fp16 MMA passes hi.hi + 2^-11 (hi.lo +
+       lo.hi), accumulation drained from TMEM in short chunks and summed with round-to-nearest FFMAs; fp32 output only):
+         conv: A = [N,H,W, hi(Cl) | lo(Cl)] with Ctot = 2*Cl, B = [Cout][tap][hi(Cin) | lo(Cin)];
+         gemm: a row of A holds hi(K) at column 0 and lo(K) at column exact_lo_a (elements), B rows likewise at exact_lo_b;
+               K %% 64 == 0; lda / ldb are the full row strides. */
+    int64_t exact_lo_a, exact_lo_b;
 } vf_tc_gemm_t;
 int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
 

@@ -60,6 +60,7 @@ class TcGemm(C.Structure):
         ("gn_sums", C.c_void_p), ("gn_groups", C.c_int), ("gn_rows_per_img", C.c_int),
         ("norm_mean_rstd", C.c_void_p), ("norm_gamma", C.c_void_p), ("norm_beta", C.c_void_p),
         ("norm_groups", C.c_int), ("norm_swish", C.c_int),
+        ("exact_lo_a", C.c_int64), ("exact_lo_b", C.c_int64),
     ]
 
 
@@ -290,12 +291,15 @@ def simt_gemm(A, B, out, *, M, N, K, a_strides, b_strides, ldc, batch=(1, 1), a_
 
 def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), alpha=1.0,
             bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0, causal_block=0,
-            causal_skip_n=False, out2=None, gn_rows_per_img=0, gn_groups=32):
+            causal_skip_n=False, out2=None, gn_rows_per_img=0, gn_groups=32, lo_a=None, lo_b=None):
     """tcgen05 GEMM: C[m,n] = act(alpha*sum_k A[m,k] B[n,k] + bias) + residual; A,B K-major bf16 (or f32 -> TF32).
-    ``out2`` optionally receives a second copy in the other dtype (f32 + bf16 from one epilogue)."""
+    ``out2`` optionally receives a second copy in the other dtype (f32 + bf16 from one epilogue).
+    float16 operands = split-fp16 pairs (exact mode): a row holds hi(K) at column 0 and lo(K) at column ``lo_a`` / ``lo_b``."""
     lib = load(True)
     assert A.dtype == B.dtype
     p = TcGemm()
+    if A.dtype == torch.float16:
+        p.exact_lo_a, p.exact_lo_b = (K if lo_a is None else lo_a), (K if lo_b is None else lo_b)
     p.conv, p.ab_dtype = 0, _dt(A)
     p.A = A.data_ptr() + a_off * A.element_size()
     p.B = B.data_ptr() + b_off * B.element_size()

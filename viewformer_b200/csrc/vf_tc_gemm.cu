@@ -60,7 +60,8 @@ struct TcParams {
     int exact;                 // conv only: split-fp16 operands (VF_F16X2), three product passes, chunked accumulation (see EXACT_LO_SCALE)
     int exact_kc;              // k-blocks per accumulation chunk (divides ntaps * cin_blocks)
     int exact_clog;            // logical channels of the split activation tensor (= Ctot / 2): the lo half starts there
-    int exact_kpp;             // k-blocks per product pass = ntaps * cin_blocks
+    int exact_kpp;             // k-blocks per product pass = ntaps * cin_blocks (conv) or K / 64 (gemm)
+    int exact_lo_b;            // gemm only: element offset of the lo half inside a B row (exact_clog is the A side's)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -476,7 +477,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                             load(sa, &p.tmA, &full_bar[stage], a_half + p.tap_coff[tap] + cb * p.bk_elems, ti.ox0 + p.tap_dx[tap],
                                  ti.oy0 + p.tap_dy[tap], ti.img0);
                         } else {
-                            load(sa, &p.tmA, &full_bar[stage], kb * p.bk_elems, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
+                            int kcoord_a = kb * p.bk_elems;
+                            if (p.exact) {       // same three passes for a plain GEMM: A rows [hi(K) .. | lo(K) ..], B rows likewise
+                                const int j = kb / p.exact_kpp, kbr = kb - j * p.exact_kpp;
+                                kcoord_a = (j == 0 ? p.exact_clog : 0) + kbr * p.bk_elems;
+                                kcoord_b = (j == 1 ? p.exact_lo_b : 0) + kbr * p.bk_elems;
+                            }
+                            load(sa, &p.tmA, &full_bar[stage], kcoord_a, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
                         }
                         load(sb, &p.tmB, &full_bar[stage], kcoord_b, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
                     }
@@ -1196,24 +1203,31 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         }
                     }
                 }
+                // final: bias, residual, statistics, store — in 16-pixel pieces (2 patch rows) to stay inside the register budget
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int r0 = grp * 8 + c * 4;
-                    if (has_res) load_res(c);
-                    float v[32];
+                for (int pc = 0; pc < 4; ++pc) {
+                    const int r0 = grp * 8 + pc * 2;
+                    float rr[16];
+                    if (has_res) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = (c == 0 ? a0[j] : a1[j]) + bias;
-                        if (has_res) v[j] += rv[j];
+                        for (int j = 0; j < 16; ++j) {
+                            int ty = r0 + (j >> 3), tx = j & 7;
+                            if (!full) {
+                                ty = ty < rows_ok ? ty : rows_ok - 1;
+                                tx = tx < cols_ok ? tx : cols_ok - 1;
+                            }
+                            rr[j] = __ldg(p.residual + (base + ty * row_stride + tx * p.Cout));
+                        }
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
+                        float v = (pc < 2 ? a0[16 * pc + j] : a1[16 * (pc - 2) + j]) + bias;
+                        if (has_res) v += rr[j];
                         const int ty = r0 + (j >> 3), tx = j & 7;
                         if (full || (ty < rows_ok && tx < cols_ok)) {       // warp-uniform
-                            const int idx = base + ty * row_stride + tx * p.Cout;
-                            gs += v[j];
-                            gq = fmaf(v[j], v[j], gq);
-                            if (p.C_f32) p.C_f32[idx] = v[j];
+                            gs += v;
+                            gq = fmaf(v, v, gq);
+                            p.C_f32[base + ty * row_stride + tx * p.Cout] = v;
                         }
                     }
                 }
@@ -1783,8 +1797,12 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
     VF_CHECK_ARG(q->ab_dtype == VF_BF16 || q->ab_dtype == VF_F32 || q->ab_dtype == VF_F16X2, "vf_tc_gemm: bad dtype");
     const bool exact = q->ab_dtype == VF_F16X2;
     if (exact) {
-        VF_CHECK_ARG(q->conv && q->Ctot % 2 == 0 && q->alpha == 1.0f && q->C_f32 && !q->C_bf16 && !q->norm_mean_rstd,
-                     "vf_tc_gemm: VF_F16X2 (exact split-fp16) operands are supported for convolutions with fp32 output only");
+        VF_CHECK_ARG(q->C_f32 && !q->C_bf16 && !q->norm_mean_rstd && q->causal_block == 0,
+                     "vf_tc_gemm: VF_F16X2 (exact split-fp16) operands need an fp32 output and no causal / fused-norm options");
+        if (q->conv) VF_CHECK_ARG(q->Ctot % 2 == 0 && q->alpha == 1.0f, "vf_tc_gemm: exact conv needs [hi | lo] channels and alpha = 1");
+        else VF_CHECK_ARG(q->K % 64 == 0 && q->exact_lo_a >= q->K && q->exact_lo_b >= q->K && q->exact_lo_a % 8 == 0 && q->exact_lo_b % 8 == 0,
+                          "vf_tc_gemm: exact GEMM needs K %% 64 == 0 and lo-half offsets >= K (K=%d lo_a=%lld lo_b=%lld)", q->K,
+                          (long long)q->exact_lo_a, (long long)q->exact_lo_b);
     }
     VF_CHECK_ARG(q->bias_mode == VF_BIAS_NONE || q->bias, "vf_tc_gemm: bias pointer missing");
     if (conv_wide_eligible(q)) return launch_conv_wide(q, vf_s(s));
@@ -1880,6 +1898,14 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         prm.M = q->M;
         prm.batch2 = q->batch2;
         prm.num_k_blocks = (q->K + bk - 1) / bk;
+        if (exact) {
+            prm.exact = 1;
+            prm.exact_kpp = prm.num_k_blocks;
+            prm.exact_clog = (int)q->exact_lo_a;
+            prm.exact_lo_b = (int)q->exact_lo_b;
+            prm.exact_kc = prm.exact_kpp % 4 == 0 ? 4 : (prm.exact_kpp % 3 == 0 ? 3 : (prm.exact_kpp % 2 == 0 ? 2 : 1));
+            prm.num_k_blocks *= 3;
+        }
         prm.c_sb1 = q->c_sb1; prm.c_sb2 = q->c_sb2;
         // an operand with batch stride 0 is shared by every batch: its tensor map gets a size-1 batch dim and the
         // kernel multiplies the batch coordinate by 0
@@ -1888,11 +1914,11 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         prm.b_bm1 = (q->batch1 > 1 && q->b_sb1 != 0) ? 1 : 0;
         prm.b_bm2 = (q->batch2 > 1 && q->b_sb2 != 0) ? 1 : 0;
         const uint64_t fbA = (uint64_t)q->lda * es * (uint64_t)q->M, fbB = (uint64_t)q->ldb * es * (uint64_t)q->Ncols;
-        const uint64_t dimsA[4] = {(uint64_t)q->K, (uint64_t)q->M, prm.a_bm2 ? (uint64_t)q->batch2 : 1, prm.a_bm1 ? (uint64_t)q->batch1 : 1};
+        const uint64_t dimsA[4] = {(uint64_t)(exact ? q->exact_lo_a + q->K : q->K), (uint64_t)q->M, prm.a_bm2 ? (uint64_t)q->batch2 : 1, prm.a_bm1 ? (uint64_t)q->batch1 : 1};
         const uint64_t strA[3] = {(uint64_t)q->lda * es, prm.a_bm2 ? (uint64_t)q->a_sb2 * es : fbA, prm.a_bm1 ? (uint64_t)q->a_sb1 * es : fbA};
         const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)BLOCK_M, 1, 1};
         if ((rc = make_tmap(&prm.tmA, tm_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;
-        const uint64_t dimsB[4] = {(uint64_t)q->K, (uint64_t)q->Ncols, prm.b_bm2 ? (uint64_t)q->batch2 : 1, prm.b_bm1 ? (uint64_t)q->batch1 : 1};
+        const uint64_t dimsB[4] = {(uint64_t)(exact ? q->exact_lo_b + q->K : q->K), (uint64_t)q->Ncols, prm.b_bm2 ? (uint64_t)q->batch2 : 1, prm.b_bm1 ? (uint64_t)q->batch1 : 1};
         const uint64_t strB[3] = {(uint64_t)q->ldb * es, prm.b_bm2 ? (uint64_t)q->b_sb2 * es : fbB, prm.b_bm1 ? (uint64_t)q->b_sb1 * es : fbB};
         const uint32_t boxB[4] = {(uint32_t)bk, (uint32_t)b_box_rows, 1, 1};
         if ((rc = make_tmap(&prm.tmB, tm_dtype, q->B, dimsB, strB, boxB)) != VF_OK) return rc;

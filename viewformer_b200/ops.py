@@ -35,13 +35,17 @@ class Linear:
 
     def __init__(self, w_out_in, bias, prec, device):
         self.n, self.k = w_out_in.shape
-        self.w = w_out_in.to(device=device, dtype=prec.opd).contiguous()
+        if getattr(prec, "split", False):      # exact mode: rows [hi(k) | lo(k)] fp16 (vf_tc_gemm VF_F16X2)
+            self.w = L.split_f16x2(w_out_in.to(device=device, dtype=torch.float32).contiguous())
+        else:
+            self.w = w_out_in.to(device=device, dtype=prec.opd).contiguous()
+        self.ld = self.w.shape[1]              # row stride of w (2k for split operands)
         self.b = None if bias is None else bias.reshape(-1).to(device=device, dtype=torch.float32).contiguous()
 
 
 def gemm_nt(prec, A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0),
             alpha=1.0, bias=None, bias_mode=L.BIAS_NONE, act=L.ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0,
-            causal_block=0, causal_skip_n=False, out2=None, force_simt=False, gn_rows_per_img=0):
+            causal_block=0, causal_skip_n=False, out2=None, force_simt=False, gn_rows_per_img=0, lo_a=None, lo_b=None):
     """C[m,n] = act(alpha * sum_k A[m,k]*B[n,k] + bias) + residual  (both operands K-major)."""
     es = A.element_size()
     tc_ok = (prec.use_tc and not force_simt and A.dtype == B.dtype and A.dtype == prec.opd
@@ -52,7 +56,9 @@ def gemm_nt(prec, A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0
         return L.tc_gemm(A, B, out, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, batch=batch, a_bs=a_bs, b_bs=b_bs,
                          c_bs=c_bs, alpha=alpha, bias=bias, bias_mode=bias_mode, act=act, residual=residual,
                          a_off=a_off, b_off=b_off, c_off=c_off, causal_block=causal_block,
-                         causal_skip_n=causal_skip_n, out2=out2, gn_rows_per_img=gn_rows_per_img)
+                         causal_skip_n=causal_skip_n, out2=out2, gn_rows_per_img=gn_rows_per_img, lo_a=lo_a, lo_b=lo_b)
+    if A.dtype == torch.float16:
+        raise L.LibraryError("split-fp16 (exact) operands have no CUDA-core GEMM: shape not supported by vf_tc_gemm")
     L.simt_gemm(A, B, out, M=M, N=N, K=K, a_strides=(lda, 1), b_strides=(1, ldb), ldc=ldc, batch=batch, a_bs=a_bs,
                 b_bs=b_bs, c_bs=c_bs, alpha=alpha, bias=bias, bias_mode=bias_mode, act=act, residual=residual,
                 a_off=a_off, b_off=b_off, c_off=c_off)
@@ -66,7 +72,7 @@ def linear(prec, x_rows, lin, out_dtype, *, act=L.ACT_NONE, residual=None, out=N
     M = x_rows.shape[0]
     if out is None:
         out = torch.empty((M, lin.n), dtype=out_dtype, device=x_rows.device)
-    gemm_nt(prec, x_rows, lin.w, out, M=M, N=lin.n, K=lin.k, lda=x_rows.shape[1], ldb=lin.k, ldc=lin.n,
+    gemm_nt(prec, x_rows, lin.w, out, M=M, N=lin.n, K=lin.k, lda=x_rows.shape[1], ldb=lin.ld, ldc=lin.n,
             bias=lin.b, bias_mode=L.BIAS_N if lin.b is not None else L.BIAS_NONE, act=act, residual=residual,
             force_simt=force_simt, gn_rows_per_img=gn_rows_per_img)
     return out

@@ -237,8 +237,8 @@ class VQGAN:
         def conv(n, exact=False):
             return _Conv3(sd[n + ".weight"], sd[n + ".bias"], prec, dev, exact=exact)
 
-        def lprec():      # precision of the 1x1 convs / attention GEMMs of the half being built (x3: they stay on the fp32 path)
-            return self.exact if prec.split else prec
+        def lprec():      # precision of the 1x1 convs / attention GEMMs of the half being built
+            return self.exact if (prec.split and os.environ.get("VF_EXACT_GEMM", "1") == "0") else prec
 
         def lin(n, p=None):
             wt = sd[n + ".weight"]
@@ -345,7 +345,7 @@ class VQGAN:
             n, hh, ww, c = x.shape
             lp = rbw["lprec"]
             xs = x if lp.opd == torch.float32 else L.groupnorm(x, None, None, swish=False, out_dtype=lp.opd, normalize=False)
-            res = linear(lp, xs.reshape(-1, c), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
+            res = linear(lp, xs.reshape(n * hh * ww, -1), rbw["sc"], torch.float32).reshape(n, hh, ww, -1)
         else:
             res = x
         if norm2 is not None:
@@ -355,6 +355,8 @@ class VQGAN:
     def _attn(self, aw, x):
         """AttnBlock (vqgan_th.py:120-144): single head over HW tokens, logits scaled by C^-0.5."""
         prec = aw["prec"]
+        if prec.split:
+            return self._attn_exact(aw, x)
         n, hh, ww, c = x.shape
         hw = hh * ww
         a = L.groupnorm(x, *aw["norm"], swish=False, out_dtype=prec.opd).reshape(n * hw, c)
@@ -374,6 +376,35 @@ class VQGAN:
         out4 = out.reshape(n, hh, ww, c)
         if hasattr(out, "_gn_sums"):
             out4._gn_sums = out._gn_sums           # fused GroupNorm statistics travel with the tensor
+        return out4
+
+    def _attn_exact(self, aw, x):
+        """AttnBlock on the exact tensor-core path: every GEMM takes split-fp16 operands ([hi | lo] rows, vf_tc_gemm VF_F16X2) and
+        returns fp32; activations that feed another GEMM are re-split by one small elementwise pass."""
+        prec = aw["prec"]
+        n, hh, ww, c = x.shape
+        hw = hh * ww
+        f32 = torch.float32
+        a = L.groupnorm(x, *aw["norm"], swish=False, out_dtype=torch.float16).reshape(n * hw, 2 * c)
+        qk = linear(prec, a, aw["qk"], f32)                                            # [n*hw, 2c] = q | k
+        qks = L.split_f16x2(qk)                                                        # [n*hw, 4c] = hi(q|k) | lo(q|k)
+        vt = torch.empty((n, c, hw), dtype=f32, device=x.device)                       # V^T per image
+        gemm_nt(prec, aw["v"].w, a, vt, M=c, N=hw, K=c, lda=2 * c, ldb=2 * c, ldc=hw, batch=(n, 1), a_bs=(0, 0),
+                b_bs=(hw * 2 * c, 0), c_bs=(c * hw, 0), bias=aw["v"].b, bias_mode=L.BIAS_M)
+        scores = torch.empty((n, hw, hw), dtype=f32, device=x.device)
+        gemm_nt(prec, qks, qks, scores, M=hw, N=hw, K=c, lda=4 * c, ldb=4 * c, ldc=hw, batch=(n, 1), a_bs=(hw * 4 * c, 0),
+                b_bs=(hw * 4 * c, 0), c_bs=(hw * hw, 0), b_off=c, alpha=float(int(c) ** (-0.5)), lo_a=2 * c, lo_b=2 * c)
+        p = torch.empty((n, hw, hw), dtype=f32, device=x.device)
+        L.softmax_rows(scores, p, rows_total=n * hw, rows_per_batch=hw, cols=hw, ld_in=hw, ld_out=hw)
+        ps = L.split_f16x2(p.reshape(n * hw, hw))                                      # [n*hw, 2hw]
+        vts = L.split_f16x2(vt.reshape(n * c, hw))                                     # [n*c, 2hw]
+        o = torch.empty((n * hw, c), dtype=f32, device=x.device)
+        gemm_nt(prec, ps, vts, o, M=hw, N=c, K=hw, lda=2 * hw, ldb=2 * hw, ldc=c, batch=(n, 1), a_bs=(hw * 2 * hw, 0),
+                b_bs=(c * 2 * hw, 0), c_bs=(hw * c, 0))
+        out = linear(prec, L.split_f16x2(o), aw["proj"], f32, residual=x.reshape(n * hw, c), gn_rows_per_img=hw)
+        out4 = out.reshape(n, hh, ww, c)
+        if hasattr(out, "_gn_sums"):
+            out4._gn_sums = out._gn_sums
         return out4
 
     # ------------------------------------------------------------------ encoder / decoder (NHWC)
