@@ -1170,9 +1170,26 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                 // chunked accumulation: every chunk arrives in a TMEM stage that started from zero; sum them here with RN FFMAs
                 // (cross-term chunks scaled by 2^-11).  (acc, acc_phase, it) above described the tile's FIRST chunk.
                 static_assert(!kExact || CPW == 2, "exact epilogue holds 2 x 32 accumulator columns per thread");
+                // The running sums START from the residual (64 loads in flight behind the first chunk's MMAs, no extra registers); the
+                // chunk sums are then added in increasing magnitude.  18+ RN additions at the magnitude of the output cost ~1e-7
+                // relative — the same order as the single rounding of the reference's own `conv + residual`.
                 float a0[32], a1[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+                for (int j = 0; j < 32; ++j) {
+                    if (has_res) {
+                        int ty0 = grp * 8 + (j >> 3), ty1 = ty0 + 4, tx = j & 7;
+                        if (!full) {
+                            ty0 = ty0 < rows_ok ? ty0 : rows_ok - 1;
+                            ty1 = ty1 < rows_ok ? ty1 : rows_ok - 1;
+                            tx = tx < cols_ok ? tx : cols_ok - 1;
+                        }
+                        a0[j] = __ldg(p.residual + (base + ty0 * row_stride + tx * p.Cout));
+                        a1[j] = __ldg(p.residual + (base + ty1 * row_stride + tx * p.Cout));
+                    } else {
+                        a0[j] = 0.f;
+                        a1[j] = 0.f;
+                    }
+                }
                 const int cpv = 9 / p.kc;                               // chunks per (product pass, channel block)
                 const int nchunks = 3 * p.cin_blocks * cpv, nsmall = 2 * p.cin_blocks * cpv;
                 int a = acc;
@@ -1203,32 +1220,15 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         }
                     }
                 }
-                // final: bias, residual, statistics, store — in 16-pixel pieces (2 patch rows) to stay inside the register budget
+                // final: bias, statistics, store
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                    const int r0 = grp * 8 + pc * 2;
-                    float rr[16];
-                    if (has_res) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            int ty = r0 + (j >> 3), tx = j & 7;
-                            if (!full) {
-                                ty = ty < rows_ok ? ty : rows_ok - 1;
-                                tx = tx < cols_ok ? tx : cols_ok - 1;
-                            }
-                            rr[j] = __ldg(p.residual + (base + ty * row_stride + tx * p.Cout));
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v = (pc < 2 ? a0[16 * pc + j] : a1[16 * (pc - 2) + j]) + bias;
-                        if (has_res) v += rr[j];
-                        const int ty = r0 + (j >> 3), tx = j & 7;
-                        if (full || (ty < rows_ok && tx < cols_ok)) {       // warp-uniform
-                            gs += v;
-                            gq = fmaf(v, v, gq);
-                            p.C_f32[base + ty * row_stride + tx * p.Cout] = v;
-                        }
+                for (int j = 0; j < 64; ++j) {
+                    const float v = (j < 32 ? a0[j] : a1[j - 32]) + bias;
+                    const int ty = grp * 8 + (j >> 3), tx = j & 7;
+                    if (full || (ty < rows_ok && tx < cols_ok)) {       // warp-uniform
+                        gs += v;
+                        gq = fmaf(v, v, gq);
+                        p.C_f32[base + ty * row_stride + tx * p.Cout] = v;
                     }
                 }
                 if (p.gn_sums) {

@@ -33,9 +33,9 @@ constexpr int NCONV = 8, NEPI = 16;
 constexpr int THREADS = 64 + 32 * (NCONV + NEPI);      // 832
 constexpr int CONV_W0 = 2, EPI_W0 = 2 + NCONV;
 constexpr int MAXK = 1024;
-constexpr int SETS = 16;                // (sub-tile, column group) sets per row, 2 keys each
+constexpr int RES_BYTES = 4 * TM * 16;     // per tile: 4 column groups x 128 rows x (3 best keys + pad), double-buffered
 constexpr int ZRING = 4;                // |z|^2 / range-flag ring (the merge of tile t reads them after the converters moved on)
-constexpr int SMEM = 2 * A_BYTES + B_STAGES * B_STAGE + MAXK * 4 + ZRING * TM * 4 * 2 + SETS * 2 * TM * 4 + 512 + 1024;
+constexpr int SMEM = 2 * A_BYTES + B_STAGES * B_STAGE + MAXK * 4 + ZRING * TM * 4 * 2 + 2 * RES_BYTES + 512 + 1024;
 
 struct VqParams {
     CUtensorMap tmB;            // Eh [K, D] fp16: box {64, 128}
@@ -91,6 +91,27 @@ __device__ __forceinline__ void umma_2sm_f16(uint32_t tmem_d, uint64_t adesc, ui
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// explicit shared-state-space accesses: pointers derived from the aligned dynamic-smem base are "generic" to the compiler, and a
+// generic LD to shared memory is tracked on the long scoreboard like a global load
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __grid_constant__ VqParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -99,8 +120,8 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
     float* esq_s = reinterpret_cast<float*>(sB + B_STAGES * B_STAGE);            // [MAXK]
     float* zz_s = esq_s + MAXK;                                  // [ZRING][TM]
     int* bad_s = reinterpret_cast<int*>(zz_s + ZRING * TM);      // [ZRING][TM]
-    uint32_t* res_s = reinterpret_cast<uint32_t*>(bad_s + ZRING * TM);           // [SETS][TM][2] packed keys
-    uint64_t* bars = reinterpret_cast<uint64_t*>(res_s + SETS * TM * 2);
+    uint8_t* res_s = reinterpret_cast<uint8_t*>(bad_s + ZRING * TM);             // [2][4 groups][TM] x uint4 (3 best keys of the thread)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res_s + 2 * RES_BYTES);
     uint64_t* b_full = bars;                    // [B_STAGES]  (leader's copy is the one that counts)
     uint64_t* b_empty = b_full + B_STAGES;      // [B_STAGES]
     uint64_t* a_ready = b_empty + B_STAGES;     // [2]  leader: 2 * NCONV arrivals
@@ -242,15 +263,17 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
         const int grp = (warp - EPI_W0) >> 2;                     // columns [64g, 64g+64) of every sub-tile
         const int row = quarter * 32 + lane;
         const uint32_t lead_empty = mapa_cta(t_empty, 0);
+        const uint32_t esq_a = smem_u32(esq_s), res_a = smem_u32(res_s);
+        const float INF = __int_as_float(0x7f800000);
         int it = 0, tl = 0;
         for (long long t = pair0; t < p.n_pair_tiles; t += pair_stride, ++tl) {
-            if (tl > 0) asm volatile("bar.sync 2, %0;" ::"n"(32 * NEPI) : "memory");          // previous tile's merge has read res_s
+            float t1 = INF, t2 = INF, t3 = INF;                   // this thread's three best keys over its 4 sets (8-bit index: n | h | j)
             for (int n = 0; n < p.nsub; ++n) {
                 const int acc = it & 1;
                 mbar_wait(&t_full[acc], (it >> 1) & 1, "vq_fused(t_full)");
                 ++it;
                 tc_fence_after();
-                float m1 = __int_as_float(0x7f800000), m2 = m1;
+                float m1 = INF, m2 = INF;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r[32];
@@ -260,10 +283,10 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(lead_empty + (uint32_t)(acc * 8));
                     }
-                    const float4* e4 = reinterpret_cast<const float4*>(esq_s + n * TN + grp * 64 + h * 32);
+                    const uint32_t ea = esq_a + (uint32_t)((n * TN + grp * 64 + h * 32) * 4);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 e = e4[j4];
+                        const float4 e = lds_f4(ea + j4 * 16);
                         const float ev[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -275,42 +298,64 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
                         }
                     }
                 }
-                uint32_t* dst = res_s + ((n * 4 + grp) * TM + row) * 2;
-                dst[0] = __float_as_uint(m1);
-                dst[1] = __float_as_uint(m2);
+                // fold the set's two best into the thread's three best (set number into bits 6..7 of the index)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float mk = q ? m2 : m1;
+                    const float k = __uint_as_float((__float_as_uint(mk) & 0xFFFFFF3Fu) | (uint32_t)(n << 6));
+                    const float a = fmaxf(t1, k);
+                    t1 = fminf(t1, k);
+                    const float b = fmaxf(t2, a);
+                    t2 = fminf(t2, a);
+                    t3 = fminf(t3, b);
+                }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory");                        // all sets of this tile are in res_s
+            const uint32_t rbuf = res_a + (uint32_t)((tl & 1) * RES_BYTES);
+            sts_u4(rbuf + (uint32_t)((grp * TM + row) * 16), make_uint4(__float_as_uint(t1), __float_as_uint(t2), __float_as_uint(t3), 0u));
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory");                        // the tile's keys are in res_s[tl & 1]
             if (grp == 0) {
                 const long long gr = t * 256 + (long long)rank * TM + row;
                 if (gr < p.M) {
-                    float bv = __int_as_float(0x7f800000);
-                    int bc = 0x7fffffff, bset = -1;
-                    const int nsets = p.nsub * 4;
-                    for (int s = 0; s < nsets; ++s) {
-                        const uint32_t k = res_s[(s * TM + row) * 2];
-                        const float v = __uint_as_float(k & 0xFFFFFFC0u);
-                        const int c = (s >> 2) * TN + (s & 3) * 64 + (int)(k & 63u);
-                        if (v < bv || (v == bv && c < bc)) { bv = v; bc = c; bset = s; }
-                    }
-                    bool bad = bad_s[(tl & (ZRING - 1)) * TM + row] != 0;
-                    if (bset < 0) { bc = 0; bad = true; }                                   // every score was NaN / inf
-                    const float znorm = sqrtf(zz_s[(tl & (ZRING - 1)) * TM + row]);
-                    const float eb = sqrtf(esq_s[bc]);
-                    int within = 0, oc = -1, oset = -1;
-                    for (int s = 0; s < nsets; ++s)
+                    uint32_t ks[12];
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const uint32_t k = res_s[(s * TM + row) * 2 + q];
-                            if ((k & 0x7f800000u) == 0x7f800000u) continue;                  // empty slot (+inf)
-                            const float v = __uint_as_float(k & 0xFFFFFFC0u);
-                            const int c = (s >> 2) * TN + (s & 3) * 64 + (int)(k & 63u);
-                            if (c == bc) continue;
-                            const float tol = p.tol_factor * 0.001953125f * znorm * (eb + sqrtf(esq_s[c])) + 1.52587890625e-5f * (fabsf(v) + fabsf(bv));
-                            if (v - bv <= tol) { ++within; oc = c; oset = s; }
-                        }
+                    for (int g = 0; g < 4; ++g) {
+                        const uint4 v = lds_u4(rbuf + (uint32_t)((g * TM + row) * 16));
+                        ks[3 * g] = v.x; ks[3 * g + 1] = v.y; ks[3 * g + 2] = v.z;
+                    }
+                    // key -> (value, code, set): value = bits with the 8 index bits cleared, code = n*256 + g*64 + idx6, set = n*4 + g
+                    float bv = INF;
+                    int bc = 0x7fffffff, bset = -1;
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        const uint32_t k = ks[i];
+                        const float v = __uint_as_float(k & 0xFFFFFF00u);
+                        const int n = (int)((k >> 6) & 3u), g = i / 3;
+                        const int c = n * TN + g * 64 + (int)(k & 63u);
+                        if ((k & 0x7f800000u) != 0x7f800000u && (v < bv || (v == bv && c < bc))) { bv = v; bc = c; bset = n * 4 + g; }
+                    }
+                    const uint32_t zslot = (uint32_t)(((tl & (ZRING - 1)) * TM + row) * 4);
+                    bool bad = *reinterpret_cast<volatile int*>(bad_s + (tl & (ZRING - 1)) * TM + row) != 0;
+                    if (bset < 0) { bc = 0; bad = true; }                                   // every score was NaN / inf
+                    const float znorm = sqrtf(lds_f(smem_u32(zz_s) + zslot));
+                    const float eb = sqrtf(lds_f(esq_a + (uint32_t)(bc * 4)));
+                    int within = 0, oc = -1, oset = -1;
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        const uint32_t k = ks[i];
+                        if ((k & 0x7f800000u) == 0x7f800000u) continue;                      // empty slot (+inf) or NaN
+                        const float v = __uint_as_float(k & 0xFFFFFF00u);
+                        const int n = (int)((k >> 6) & 3u), g = i / 3;
+                        const int c = n * TN + g * 64 + (int)(k & 63u);
+                        if (c == bc) continue;
+                        const float slack = 6.1035156e-5f * (fabsf(v) + fabsf(bv));         // index bits + truncating accumulation
+                        const float tol = p.tol_factor * 0.001953125f * znorm * (eb + sqrtf(lds_f(esq_a + (uint32_t)(c * 4)))) + slack;
+                        if (v - bv <= tol) { ++within; oc = c; oset = n * 4 + g; }
+                    }
                     p.idx[gr] = (long long)bc;
                     if (within > 0 || bad) {
-                        const bool full = bad || within > 1 || oset == bset;               // a third candidate could hide inside one set
+                        // a code within the tolerance that is NOT among the 12 keys implies two reported keys within the tolerance in
+                        // one thread or a runner-up in the best code's own set (see the proof sketch in DESIGN.md): those rows take all codes
+                        const bool full = bad || within > 1 || oset == bset;
                         // PAIR entries fill the worklist from the front, FULL entries from the back
                         if (full) p.worklist[p.M - 1 - atomicAdd(p.counter + 1, 1)] = make_int4((int)gr, bc, -1, 0);
                         else p.worklist[atomicAdd(p.counter, 1)] = make_int4((int)gr, bc, oc, 0);
@@ -329,14 +374,24 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
     }
 }
 
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // Exact pass over the queued rows: fp64 direct sum of squared differences, ties to the smaller index.
 // PAIR entries (front of the worklist): one warp per entry, the two known candidates.  FULL entries (back of the worklist): one CTA per
 // entry, every thread scores K / 256 codes, block-wide argmin.
 __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict__ z, const float* __restrict__ Et, int D, int K, long long M,
                                                         const int4* __restrict__ worklist, const int* __restrict__ counter,
                                                         long long* __restrict__ idx) {
+    constexpr int MAXCAND = 64;
     __shared__ double sd[8];
     __shared__ int si[8];
+    __shared__ __align__(16) float zs[256];
+    __shared__ int cands[MAXCAND];
+    __shared__ int ncand;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int n_pair = counter[0], n_full = counter[1];
@@ -356,35 +411,81 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
         if (lane == 0) idx[e.x] = (long long)((d1 < d0 || (d1 == d0 && e.z < e.y)) ? e.z : e.y);
     }
+    // all-codes entries: fp32 screening of every code by the whole CTA (the reference's expanded form), then fp64 only for the codes
+    // whose fp32 score lies within the fp32 rounding bound of the minimum (almost always one or two)
     for (int i = blockIdx.x; i < n_full; i += gridDim.x) {
         const int4 e = worklist[M - 1 - i];
         const float* zr = z + (long long)e.x * D;
+        for (int d = threadIdx.x; d < D; d += 256) zs[d] = zr[d];
+        if (threadIdx.x == 0) ncand = 0;
+        __syncthreads();
+        float zz = 0.f;
+        for (int d = 0; d < D; ++d) zz = fmaf(zs[d], zs[d], zz);
+        float sc[4];                                          // K <= 1024: at most 4 codes per thread
+        float smin = INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = threadIdx.x + q * 256;
+            sc[q] = INFINITY;
+            if (c < K) {
+                const float* ec = Et + (long long)c * D;
+                float dot = 0.f, ee = 0.f;
+                for (int d = 0; d < D; d += 4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(ec + d));
+                    const float4 b = *reinterpret_cast<const float4*>(zs + d);
+                    dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+                    ee = fmaf(a.x, a.x, ee); ee = fmaf(a.y, a.y, ee); ee = fmaf(a.z, a.z, ee); ee = fmaf(a.w, a.w, ee);
+                }
+                sc[q] = ee - 2.0f * dot;
+                smin = fminf(smin, sc[q]);
+            }
+        }
+        smin = warp_min_f(smin);
+        if (lane == 0) sd[warp] = (double)smin;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = sd[0];
+            for (int w = 1; w < 8; ++w) m = sd[w] < m ? sd[w] : m;
+            sd[0] = m;
+        }
+        __syncthreads();
+        const float gmin = (float)sd[0];
+        __syncthreads();
+        const bool finite = gmin == gmin && fabsf(gmin) < INFINITY && zz == zz && zz < INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = threadIdx.x + q * 256;
+            // fp32 error of a D-term dot product: <= D * 2^-24 * |z||e| per score; 6e-5 * (|z|^2 + |s|) covers it with margin
+            const bool cand = c < K && (!finite || sc[q] - gmin <= 6e-5f * (zz + fabsf(gmin) + fabsf(sc[q])));
+            if (cand) {
+                const int slot = atomicAdd(&ncand, 1);
+                if (slot < MAXCAND) cands[slot] = c;
+            }
+        }
+        __syncthreads();
+        const int nc = ncand;
         double bd = 1e300;
         int bi = 0x7fffffff;
-        for (int c = threadIdx.x; c < K; c += 256) {
+        auto score64 = [&](int c) {
             const float* ec = Et + (long long)c * D;
             double dd = 0.0;
-            for (int d = 0; d < D; d += 4) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(ec + d));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(zr + d));
-                const double t0 = (double)a.x - (double)b.x, t1 = (double)a.y - (double)b.y, t2 = (double)a.z - (double)b.z, t3 = (double)a.w - (double)b.w;
-                dd += t0 * t0;
-                dd += t1 * t1;
-                dd += t2 * t2;
-                dd += t3 * t3;
+            for (int d = lane; d < D; d += 32) {
+                const double tt = (double)ec[d] - (double)zs[d];
+                dd += tt * tt;
             }
-            if (dd < bd || (dd == bd && c < bi)) { bd = dd; bi = c; }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            for (int o = 16; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            if (dd < bd || (dd == bd && c < bi)) { bd = dd; bi = c; }
+        };
+        if (nc <= MAXCAND) {
+            for (int k = warp; k < nc; k += 8) score64(cands[k]);
+        } else {                                              // degenerate row (all codes nearly equidistant, or non-finite): every code in fp64
+            for (int c = warp; c < K; c += 8) score64(c);
         }
         if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; ++w)
+            for (int w = 0; w < 8; ++w)
                 if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
             idx[e.x] = (long long)bi;
         }
