@@ -67,6 +67,11 @@ __device__ __forceinline__ uint32_t mapa_cta(const void* p, uint32_t cta) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// arrival without a memory payload (TMEM stage hand-back: ordered by tcgen05.fence::before_thread_sync): no cluster-scope release
+// fence — `mbarrier.arrive.release.cluster` costs an ERRBAR per warp per sub-tile (26 % of the epilogue's stall samples in ncu)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope: the peer CTA's arrivals
     for (uint32_t i = 0; i < (1u << 24); ++i) {
         uint32_t ok;
@@ -90,6 +95,11 @@ __device__ __forceinline__ void umma_2sm_f16(uint32_t tmem_d, uint64_t adesc, ui
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+
+// index bytes 0..63 as constant-bank operands: key = PRMT(score bits, index) replaces the low mantissa BYTE in one ALU instruction
+__constant__ uint32_t VQ_IDX[64] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21,
+                                    22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43,
+                                    44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63};
 
 // explicit shared-state-space accesses: pointers derived from the aligned dynamic-smem base are "generic" to the compiler, and a
 // generic LD to shared memory is tracked on the long scoreboard like a global load
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
                     if (h == 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(lead_empty + (uint32_t)(acc * 8));
+                        if (lane == 0) mbar_arrive_cluster_relaxed(lead_empty + (uint32_t)(acc * 8));
                     }
                     const uint32_t ea = esq_a + (uint32_t)((n * TN + grp * 64 + h * 32) * 4);
 #pragma unroll
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
                         for (int q = 0; q < 4; ++q) {
                             const int j = j4 * 4 + q;
                             const float s = __uint_as_float(r[j]) + ev[q];
-                            const float k = __uint_as_float((__float_as_uint(s) & 0xFFFFFFC0u) | (uint32_t)(h * 32 + j));
+                            const float k = __uint_as_float(__byte_perm(__float_as_uint(s), VQ_IDX[h * 32 + j], 0x3214));   // low byte <- index
                             m2 = fminf(m2, fmaxf(m1, k));
                             m1 = fminf(m1, k);
                         }
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const float mk = q ? m2 : m1;
-                    const float k = __uint_as_float((__float_as_uint(mk) & 0xFFFFFF3Fu) | (uint32_t)(n << 6));
+                    const float k = __uint_as_float(__float_as_uint(mk) | (uint32_t)(n << 6));       // bits 6..7 of the index byte are zero so far
                     const float a = fmaxf(t1, k);
                     t1 = fminf(t1, k);
                     const float b = fmaxf(t2, a);
@@ -391,6 +401,7 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
     __shared__ int si[8];
     __shared__ __align__(16) float zs[256];
     __shared__ int cands[MAXCAND];
+    __shared__ float scores[1024];
     __shared__ int ncand;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -421,26 +432,23 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         __syncthreads();
         float zz = 0.f;
         for (int d = 0; d < D; ++d) zz = fmaf(zs[d], zs[d], zz);
-        float sc[4];                                          // K <= 1024: at most 4 codes per thread
+        // screening: warp w scores codes w, w+8, ... with the 32 lanes across the row (coalesced 1 KB code rows), scores to smem
         float smin = INFINITY;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = threadIdx.x + q * 256;
-            sc[q] = INFINITY;
-            if (c < K) {
-                const float* ec = Et + (long long)c * D;
-                float dot = 0.f, ee = 0.f;
-                for (int d = 0; d < D; d += 4) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(ec + d));
-                    const float4 b = *reinterpret_cast<const float4*>(zs + d);
-                    dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
-                    ee = fmaf(a.x, a.x, ee); ee = fmaf(a.y, a.y, ee); ee = fmaf(a.z, a.z, ee); ee = fmaf(a.w, a.w, ee);
-                }
-                sc[q] = ee - 2.0f * dot;
-                smin = fminf(smin, sc[q]);
+        for (int c = warp; c < K; c += 8) {
+            const float* ec = Et + (long long)c * D;
+            float dot = 0.f, ee = 0.f;
+            for (int d = lane * 4; d < D; d += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ec + d));
+                const float4 b = *reinterpret_cast<const float4*>(zs + d);
+                dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+                ee = fmaf(a.x, a.x, ee); ee = fmaf(a.y, a.y, ee); ee = fmaf(a.z, a.z, ee); ee = fmaf(a.w, a.w, ee);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); ee += __shfl_xor_sync(0xffffffffu, ee, o); }
+            const float sco = ee - 2.0f * dot;
+            if (lane == 0) scores[c] = sco;
+            smin = fminf(smin, sco);
         }
-        smin = warp_min_f(smin);
         if (lane == 0) sd[warp] = (double)smin;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -452,12 +460,10 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         const float gmin = (float)sd[0];
         __syncthreads();
         const bool finite = gmin == gmin && fabsf(gmin) < INFINITY && zz == zz && zz < INFINITY;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = threadIdx.x + q * 256;
+        for (int c = threadIdx.x; c < K; c += 256) {
             // fp32 error of a D-term dot product: <= D * 2^-24 * |z||e| per score; 6e-5 * (|z|^2 + |s|) covers it with margin
-            const bool cand = c < K && (!finite || sc[q] - gmin <= 6e-5f * (zz + fabsf(gmin) + fabsf(sc[q])));
-            if (cand) {
+            const float sco = scores[c];
+            if (!finite || sco - gmin <= 6e-5f * (zz + fabsf(gmin) + fabsf(sco))) {
                 const int slot = atomicAdd(&ncand, 1);
                 if (slot < MAXCAND) cands[slot] = c;
             }
