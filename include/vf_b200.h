@@ -167,6 +167,17 @@ int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
 int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * Evaluation-side kernels
+ *   vf_resize_u8: data/_common.py:19-44 (resize_th) on uint8 NHWC images: bilinear (align_corners = False) when `bilinear`, else
+ *     torch 'nearest'; result = uint8(clamp(interp(x / 255), 0, 1) * 255).
+ *   vf_image_pair_sums: out[2n] = sum |a - b|, out[2n+1] = sum (a - b)^2 over image n (exact integers) -> MSE / MAE / RMSE / PSNR.
+ *   vf_ssim_u8: utils/metrics.py:17-73 (7x7 uniform window, VALID, sample covariance, data range 1); out[n] = mean SSIM of image n.
+ * ---------------------------------------------------------------------------------------- */
+int vf_resize_u8(const void* x_u8, int N, int H, int W, int C, int OH, int OW, int bilinear, void* y_u8, vf_stream_t s);
+int vf_image_pair_sums(const void* a_u8, const void* b_u8, int N, int64_t per_image, uint64_t* out, vf_stream_t s);
+int vf_ssim_u8(const void* a_u8, const void* b_u8, int N, int H, int W, int C, double* out, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * Codebook
  * replaces: models/utils_th.py:34-44 (distance, argmax(-dist), gather), :66 (diff), :70-72 (embed_code)
  *   z [M,D] f32 rows; codebook given TRANSPOSED as Et [K,D] (built once at weight load) with esq[K]=|e|^2.

@@ -24,7 +24,7 @@ EXPORTS = [
     "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
-    "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused",
+    "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
 ]
 
 
@@ -183,6 +183,45 @@ def nhwc_to_nchw(x):
     n, h, w, c = x.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
     _check(lib.vf_nhwc_to_nchw_f32(_p(x), _p(out), n, c, h, w, _stream()))
+    return out
+
+
+def resize_u8(x_u8, size, method=None):
+    """data/_common.py:19-44 (resize_th) for uint8 NHWC images [N,H,W,C] -> [N,size,size,C]: bilinear (align_corners=False) when
+    shrinking, nearest when growing (or the explicit ``method``)."""
+    lib = load(True)
+    _dev(x_u8, torch.uint8)
+    n, h, w, c = x_u8.shape
+    if w == size and h == size:
+        return x_u8
+    if method is None:
+        method = "nearest" if size > w else "bilinear"
+    assert method in ("nearest", "bilinear")
+    out = torch.empty((n, size, size, c), dtype=torch.uint8, device=x_u8.device)
+    _check(lib.vf_resize_u8(_p(x_u8), n, h, w, c, size, size, int(method == "bilinear"), _p(out), _stream()))
+    return out
+
+
+def image_pair_sums(a_u8, b_u8):
+    """uint8 images [N,...] x2 -> int64 [N,2] = (sum |a-b|, sum (a-b)^2) per image (exact)."""
+    lib = load(True)
+    _dev(a_u8, torch.uint8)
+    _dev(b_u8, torch.uint8)
+    assert a_u8.shape == b_u8.shape
+    n = a_u8.shape[0]
+    out = torch.empty((n, 2), dtype=torch.int64, device=a_u8.device)
+    _check(lib.vf_image_pair_sums(_p(a_u8), _p(b_u8), n, C.c_int64(a_u8[0].numel() if n else 1), _p(out), _stream()))
+    return out
+
+
+def ssim_u8(a_u8, b_u8):
+    """utils/metrics.py:17-73 on uint8 NHWC images -> float64 [N] mean SSIM per image."""
+    lib = load(True)
+    _dev(a_u8, torch.uint8)
+    _dev(b_u8, torch.uint8)
+    n, h, w, c = a_u8.shape
+    out = torch.empty((n,), dtype=torch.float64, device=a_u8.device)
+    _check(lib.vf_ssim_u8(_p(a_u8), _p(b_u8), n, h, w, c, _p(out), _stream()))
     return out
 
 

@@ -434,20 +434,29 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         for (int d = 0; d < D; ++d) zz = fmaf(zs[d], zs[d], zz);
         // screening: warp w scores codes w, w+8, ... with the 32 lanes across the row (coalesced 1 KB code rows), scores to smem
         float smin = INFINITY;
-        for (int c = warp; c < K; c += 8) {
-            const float* ec = Et + (long long)c * D;
-            float dot = 0.f, ee = 0.f;
+        for (int c0 = warp * 4; c0 < K; c0 += 32) {            // 4 codes per iteration: 8 independent 16-byte loads in flight per lane
+            float dot[4] = {0.f, 0.f, 0.f, 0.f}, ee[4] = {0.f, 0.f, 0.f, 0.f};
             for (int d = lane * 4; d < D; d += 128) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(ec + d));
                 const float4 b = *reinterpret_cast<const float4*>(zs + d);
-                dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
-                ee = fmaf(a.x, a.x, ee); ee = fmaf(a.y, a.y, ee); ee = fmaf(a.z, a.z, ee); ee = fmaf(a.w, a.w, ee);
+                float4 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = (c0 + u < K) ? __ldg(reinterpret_cast<const float4*>(Et + (long long)(c0 + u) * D + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    dot[u] = fmaf(a[u].x, b.x, dot[u]); dot[u] = fmaf(a[u].y, b.y, dot[u]); dot[u] = fmaf(a[u].z, b.z, dot[u]); dot[u] = fmaf(a[u].w, b.w, dot[u]);
+                    ee[u] = fmaf(a[u].x, a[u].x, ee[u]); ee[u] = fmaf(a[u].y, a[u].y, ee[u]); ee[u] = fmaf(a[u].z, a[u].z, ee[u]); ee[u] = fmaf(a[u].w, a[u].w, ee[u]);
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); ee += __shfl_xor_sync(0xffffffffu, ee, o); }
-            const float sco = ee - 2.0f * dot;
-            if (lane == 0) scores[c] = sco;
-            smin = fminf(smin, sco);
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o); ee[u] += __shfl_xor_sync(0xffffffffu, ee[u], o); }
+                if (c0 + u < K) {
+                    const float sco = ee[u] - 2.0f * dot[u];
+                    if (lane == 0) scores[c0 + u] = sco;
+                    smin = fminf(smin, sco);
+                }
+            }
         }
         if (lane == 0) sd[warp] = (double)smin;
         __syncthreads();
@@ -604,7 +613,7 @@ extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const floa
     e = cudaLaunchKernelEx(&cfg, vq_lookup_fused_kernel, prm);
     if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: cluster launch failed: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     VF_CHECK_LAUNCH("vf_vq_lookup_fused");
-    vq_rescue_kernel<<<num_sms * 2, 256, 0, st>>>(z, Et, D, K, M, prm.worklist, counter, prm.idx);
+    vq_rescue_kernel<<<num_sms * 8, 256, 0, st>>>(z, Et, D, K, M, prm.worklist, counter, prm.idx);
     VF_CHECK_LAUNCH("vf_vq_lookup_fused(rescue)");
     if (quant || diff_sum) {
         vq_gather_diff_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(z, Et, prm.idx, M, D, quant, diff_sum);

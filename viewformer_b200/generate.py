@@ -88,8 +88,6 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
 
     B, T = images.shape[:2]
     size = codebook_model.config.image_size
-    if images.shape[2] != size or images.shape[3] != size:
-        raise NotImplementedError("resize_tf (data/_common.py:19-62) is outside this round's scope: feed %dx%d images" % (size, size))
     use_loc = transformer_model.use_localization
     if encode_target is None:
         encode_target = use_loc
@@ -98,6 +96,9 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
     n_enc = T if encode_target else T - 1
     if not img_dev.is_contiguous():
         img_dev = img_dev.contiguous()
+    if images.shape[2] != size or images.shape[3] != size:        # resize_tf (evaluate_transformer.py:104, data/_common.py:19-62)
+        img_dev = L.resize_u8(img_dev[:, :n_enc].reshape((-1,) + tuple(img_dev.shape[2:])).contiguous(), size)
+        img_dev = img_dev.reshape((B, n_enc) + tuple(img_dev.shape[1:]))
     codes = codebook_model.encode_u8(img_dev, first_views=n_enc).reshape(B, n_enc, side, side)
 
     gen_codes = transformer_model.generate_codes(codes[:, : T - 1], cams_dev)

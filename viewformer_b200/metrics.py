@@ -1,0 +1,117 @@
+"""Evaluation metrics of the reference (viewformer/utils/metrics.py:17-230, evaluate/evaluate_transformer.py:22-67) on the GPU.
+
+Image metrics take uint8 NHWC images (what ``generate_batch_predictions`` returns) and reduce them with libvf_b200 kernels: exact
+integer sums for MSE / MAE / RMSE / PSNR, the 7x7 uniform-window SSIM of ``ssim()``.  Camera metrics are a handful of floats per
+scene and stay host-side torch (same formulas as CameraPositionError / CameraOrientationError, NaN-tolerant means, medians).
+LPIPS is out of scope (VGG weights are not available offline).
+"""
+import math
+
+import torch
+
+from . import _lib as L
+from .generate import quaternion_multiply, quaternion_conjugate, quaternion_normalize
+
+
+def _u8(x, device):
+    t = torch.as_tensor(x)
+    if t.dtype != torch.uint8:
+        raise TypeError("image metrics take uint8 images (the reference converts with tf.image.convert_image_dtype)")
+    if t.dim() == 3:
+        t = t[None]
+    return t.to(device).contiguous()
+
+
+def image_metrics(gt_images, images, device="cuda"):
+    """uint8 [N,H,W,C] x2 -> dict of per-image float64 tensors: mse, mae (range [0,1]), rmse (range [0,255]), psnr (dB), ssim."""
+    a, b = _u8(gt_images, device), _u8(images, device)
+    n = a.shape[0]
+    sums = L.image_pair_sums(a, b).to(torch.float64)
+    cnt = float(a[0].numel())
+    mse = sums[:, 1] / (cnt * 255.0 * 255.0)
+    return dict(mse=mse, mae=sums[:, 0] / (cnt * 255.0), rmse=torch.sqrt(sums[:, 1] / cnt),
+                psnr=10.0 * torch.log10(1.0 / mse),                      # tf.image.psnr(max_val = 1)
+                ssim=L.ssim_u8(a, b) if min(a.shape[1], a.shape[2]) >= 7 else torch.full((n,), float("nan"), dtype=torch.float64))
+
+
+def camera_position_error(x1, x2):
+    return torch.linalg.norm(torch.as_tensor(x1)[..., :3] - torch.as_tensor(x2)[..., :3], dim=-1)
+
+
+def camera_orientation_error(x1, x2):
+    """2 asin |vec(q1 * conj(q2))| (metrics.py:103-115)."""
+    q1 = quaternion_normalize(torch.as_tensor(x1)[..., 3:])
+    q2 = quaternion_normalize(torch.as_tensor(x2)[..., 3:])
+    diff = quaternion_multiply(q1, quaternion_conjugate(q2))
+    return 2 * torch.asin(torch.linalg.norm(diff[..., 1:], dim=-1))
+
+
+class Mean:
+    """tf.metrics.Mean with the AllowNanMean behaviour of metrics.py:76-88 (NaN samples carry zero weight)."""
+
+    def __init__(self, name):
+        self.name, self.total, self.count = name, 0.0, 0.0
+
+    def update_state(self, values):
+        v = torch.as_tensor(values, dtype=torch.float64).reshape(-1).cpu()
+        ok = ~torch.isnan(v)
+        self.total += float(v[ok].sum())
+        self.count += float(ok.sum())
+
+    def result(self):
+        return self.total / self.count if self.count else 0.0
+
+
+class Median:
+    """metrics.py:118-144."""
+
+    def __init__(self, name):
+        self.name, self.store = name, []
+
+    def update_state(self, values):
+        self.store.append(torch.as_tensor(values, dtype=torch.float64).reshape(-1).cpu())
+
+    def result(self):
+        if not self.store:
+            return 0.0
+        v = torch.sort(torch.cat(self.store)).values
+        n = len(v)
+        return float(v[(n - 1) // 2]) if n % 2 == 1 else 0.5 * float(v[n // 2 - 1] + v[n // 2])
+
+
+class Evaluator:
+    """evaluate/evaluate_transformer.py:22-67: image-generation metrics (mse, rmse, mae, psnr, ssim) and localisation metrics
+    (loc-angle, loc-dist and their medians); images are brought to a common size with the dataset resize rule first."""
+
+    def __init__(self, image_size=None, device="cuda"):
+        self.image_size, self.device = image_size, device
+        self._loc = dict(angle=Mean("loc-angle"), dist=Mean("loc-dist"), angle_med=Median("loc-angle-med"), dist_med=Median("loc-dist-med"))
+        self._img = {k: Mean(k) for k in ("mse", "rmse", "mae", "psnr", "ssim")}
+
+    def update_with_image(self, ground_truth_images, generated_images):
+        gt, gen = _u8(ground_truth_images, self.device), _u8(generated_images, self.device)
+        size = self.image_size or max(gt.shape[-2], gen.shape[-2])
+        gt, gen = L.resize_u8(gt, size), L.resize_u8(gen, size)
+        for k, v in image_metrics(gt, gen, self.device).items():
+            self._img[k].update_state(v)
+
+    def update_with_camera(self, ground_truth_cameras, generated_cameras):
+        gt, gen = torch.as_tensor(ground_truth_cameras).cpu(), torch.as_tensor(generated_cameras).cpu()
+        ang, dist = camera_orientation_error(gt, gen), camera_position_error(gt, gen)
+        self._loc["angle"].update_state(ang); self._loc["angle_med"].update_state(ang)
+        self._loc["dist"].update_state(dist); self._loc["dist_med"].update_state(dist)
+
+    def update_state(self, ground_truth_cameras=None, generated_cameras=None, ground_truth_images=None, generated_images=None):
+        if ground_truth_images is not None and generated_images is not None:
+            self.update_with_image(ground_truth_images, generated_images)
+        if ground_truth_cameras is not None and generated_cameras is not None:
+            self.update_with_camera(ground_truth_cameras, generated_cameras)
+
+    def get_progress_bar_info(self):
+        return dict(psnr=self._img["psnr"].result(), mae=self._img["mae"].result(), **{"loc-angle": self._loc["angle"].result(),
+                                                                                       "loc-dist": self._loc["dist"].result()})
+
+    def result(self):
+        out = {m.name: float(m.result()) for m in self._img.values() if m.count}
+        out.update({m.name: float(m.result()) for m in self._loc.values() if (getattr(m, "count", 0) or getattr(m, "store", None))})
+        return out

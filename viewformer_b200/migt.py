@@ -120,6 +120,25 @@ class MIGT:
     def state_dict(self):
         return OrderedDict((k, v.clone()) for k, v in self._sd.items())
 
+    # ------------------------------------------------------------------ Keras checkpoint surface (train_transformer.py:106-129)
+    def load_weights(self, filepath):
+        """Keras ``model.load_weights(<dir>/model)`` of a TF2 object-graph checkpoint (viewformer/utils/tensorflow.py:57-61), read by
+        the pure-Python TensorBundle reader (viewformer_b200/tf_checkpoint.py).  Returns a status object with ``expect_partial()``."""
+        from . import tf_checkpoint
+        self.load_state_dict(tf_checkpoint.load_state_dict(filepath, self.expected_keys()))
+
+        class _Status:
+            def expect_partial(self):
+                return self
+
+            def assert_consumed(self):
+                return self
+        return _Status()
+
+    def save_weights(self, filepath):
+        from . import tf_checkpoint
+        tf_checkpoint.write_checkpoint(filepath, {k.replace(".", "/"): v.numpy() for k, v in self.state_dict().items()})
+
     def _build(self):
         L.load(require_device=True)
         sd, prec, dev, cfg = self._sd, self.prec, self.device, self.config
@@ -375,6 +394,43 @@ class MIGT:
         """QuaternionPoseRepresentation.reduce (migt.py:150-154, 123-129): host-side, a handful of floats."""
         from .generate import reduce_cameras
         return reduce_cameras(cameras, axis)
+
+    # ------------------------------------------------------------------ Keras evaluation steps (migt.py:507-541)
+    def test_step(self, batch):
+        """(poses [B,T,7], tokens [B,T,h,w]) -> dict of scalars: losses of ``call(compute_losses=True)``, token accuracy and, with
+        a codebook attached, the PSNR between the decoded predicted and true last views (migt.py:507-530)."""
+        poses, tokens = batch
+        out = self(dict(poses=poses, input_ids=tokens), compute_losses=True, training=False)
+        res = {k: float(torch.as_tensor(v, dtype=torch.float32).mean()) for k, v in out.items()
+               if k in ("loss", "ce_loss", "pose_loss", "pose_pos_loss", "pose_ori_loss")}
+        tok = self._in(torch.as_tensor(tokens), torch.int64)
+        logits = out["logits"]
+        pred = L.argmax_rows(logits.reshape(-1, logits.shape[-1])).reshape(tok.shape)
+        skip = self.config.n_loss_skip
+        res["acc"] = float((pred[:, skip:] == tok[:, skip:]).float().mean())            # _compute_accuracy, first n_loss_skip views excluded
+        if "pose_prediction" in out:
+            from .metrics import camera_position_error, camera_orientation_error
+            pp = out["pose_prediction"][:, skip:].cpu()
+            gt = torch.as_tensor(poses)[:, skip:, None].cpu()
+            res["pose_pos_err"] = float(camera_position_error(pp, gt).mean())
+            res["pose_ori_err"] = float(camera_orientation_error(pp, gt.expand_as(pp)).nan_to_num(0.0).mean())
+        if self._codebook_model is not None:
+            from .metrics import image_metrics
+            gen = self._codebook_model.decode_code_u8(pred[:, -1])
+            gt_img = self._codebook_model.decode_code_u8(tok[:, -1])
+            res["psnr"] = float(image_metrics(gt_img, gen, self.device)["psnr"].mean())
+        return res
+
+    def predict_step(self, batch):
+        """migt.py:535-541: decoded images of the teacher-forced argmax tokens and of the true tokens (float NHWC in [-1, 1])."""
+        poses, tokens = batch
+        logits = self(dict(poses=poses, input_ids=tokens), compute_losses=True, training=False)["logits"]
+        side = self.token_image_size
+        gen = L.argmax_rows(logits.reshape(-1, logits.shape[-1])).reshape(-1, self.config.sequence_size, side, side)
+        gen = torch.where(gen < self.n_embeddings, gen, torch.zeros_like(gen))
+        tok = self._in(torch.as_tensor(tokens), torch.int64)
+        return {"decoded_image": self._codebook_model.decode_code_nhwc(gen.reshape(-1, side, side)), "latent_code": gen,
+                "ground_truth_image": self._codebook_model.decode_code_nhwc(tok.reshape(-1, side, side))}
 
     # ------------------------------------------------------------------ context KV cache (BASELINE config 5)
     def prefill_context(self, codes_ctx, poses_ctx):

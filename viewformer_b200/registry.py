@@ -31,18 +31,25 @@ AutoModelTH = AutoModel   # the torch/TF split of the reference collapses: one C
 
 def load_model(checkpoint, restore_weights=True, precision="bf16", **config_overrides):
     """checkpoint: directory holding config.json (+ a .ckpt/.pt file) or the checkpoint file itself."""
-    ckpt_file = None
+    ckpt_file, tf_prefix = None, None
     if os.path.isdir(checkpoint):
         model_dir = checkpoint
         for f in sorted(os.listdir(checkpoint)):
             if f.endswith((".ckpt", ".pt", ".pth")):
                 ckpt_file = os.path.join(checkpoint, f)
+            elif f.endswith(".index"):                       # TF2 checkpoint: <name>.index + <name>.data-*  (utils/tensorflow.py:26-31)
+                tf_prefix = os.path.join(checkpoint, f[: -len(".index")])
+    elif os.path.exists(checkpoint + ".index"):              # '<dir>/model' as the reference passes it to load_weights
+        model_dir, tf_prefix = os.path.dirname(checkpoint), checkpoint
     else:
         model_dir, ckpt_file = os.path.dirname(checkpoint), checkpoint
     with open(os.path.join(model_dir, "config.json")) as f:
         cfg = json.load(f)
     cfg.update(config_overrides)
     model = AutoModel.from_config(cfg, precision=precision)
+    if restore_weights and tf_prefix is not None and ckpt_file is None:
+        model.load_weights(tf_prefix)
+        return model
     if restore_weights:
         if ckpt_file is None:
             raise FileNotFoundError(f"no checkpoint file next to {model_dir}/config.json")
