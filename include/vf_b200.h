@@ -88,7 +88,7 @@ int vf_layernorm(const float* x, const float* gamma, const float* beta, int64_t 
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     /* A operand: conv gather (conv=1) or dense strided matrix (conv=0) */
-    const void* A; int a_dtype; int conv;
+    const void* A; int a_dtype; int conv;   /* conv: 0 dense, 1 forward conv gather, 2 data-gradient gather of a stride-2 conv */
     int N, H, W, Cin;            /* conv: input NHWC dims */
     int OH, OW, KH, KW, stride, pad_t, pad_l, upsample2x;
     int64_t a_sm, a_sk;          /* dense: element strides of A(m,k) */
@@ -165,6 +165,31 @@ int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
  *   head dim must be 64; S % block == 0.
  * ---------------------------------------------------------------------------------------- */
 int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward pass of the codebook training step (models/vqgan_th.py:395-423, 443-445), fp32.  Data gradients of convolutions and dense
+ * layers are calls to vf_simt_gemm / vf_tc_gemm with flipped / transposed weights; what has no forward twin lives here.
+ *   vf_conv_wgrad: dW[(tap*Cin + ci) * so_k + co * so_n] += sum over output pixels of X(gathered exactly as the forward conv does:
+ *     stride, pad_t / pad_l, optional nearest x2 upsampling) * dY[pixel][co]   (fp32 atomics; dW must be zeroed by the caller).
+ *     KH = KW = 1 with so_k = 1, so_n = Cin gives the [Cout, Cin] gradient of a dense layer.
+ *   vf_col_sums: out[c] += sum_rows x[row][c]  (bias gradients).
+ *   vf_groupnorm_bwd: GroupNorm(groups) [+ swish] backward of y = act(xhat*gamma + beta): dx = rstd (dg gamma - mean - xhat mean2) + add,
+ *     dgamma += sum dg xhat, dbeta += sum dg;  mean_rstd from the forward pass; gsums = double [N, groups, 2] scratch.
+ *   vf_softmax_bwd_rows: dS = P (dP - rowsum(dP P)).   vf_l1_grad: dy = scale * sign(y - x), loss_sum += sum |y - x|.
+ *   vf_lincomb3: out = a x + b y + c z (y, z nullable).   vf_sumpool2x2: [N,2H,2W,C] -> [N,H,W,C] (nearest-upsample backward).
+ *   vf_adam: torch.optim.Adam step number `step` (>= 1) on flat buffers; the gradient is multiplied by grad_scale first (1 / world size).
+ * ---------------------------------------------------------------------------------------- */
+int vf_conv_wgrad(const float* x, const float* dy, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
+                  int pad_t, int pad_l, int upsample2x, int64_t so_k, int64_t so_n, float* dw, vf_stream_t s);
+int vf_col_sums(const float* x, int64_t rows, int C, float* out, vf_stream_t s);
+int vf_groupnorm_bwd(const float* x, const float* dout, const float* mean_rstd, const float* gamma, const float* beta, int N, int HW,
+                     int C, int groups, int swish, const float* add, double* gsums, float* dgamma, float* dbeta, float* dx, vf_stream_t s);
+int vf_softmax_bwd_rows(const float* P, const float* dP, int64_t rows, int cols, float* dS, vf_stream_t s);
+int vf_l1_grad(const float* x, const float* y, int64_t n, float scale, float* dy, double* loss_sum, vf_stream_t s);
+int vf_lincomb3(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out, vf_stream_t s);
+int vf_sumpool2x2(const float* x, int N, int H, int W, int C, float* y, vf_stream_t s);
+int vf_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int step,
+            float grad_scale, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Evaluation-side kernels

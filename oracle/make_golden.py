@@ -119,6 +119,45 @@ def golden_migt():
         print("migt", tag, "logit std", float(last.std()))
 
 
+def golden_vqgan_train():
+    """Two optimisation steps of the REAL reference codebook (vqgan_th.py:395-423, 443-445; train mode: QuantizeEMA updates the
+    codebook; perceptual_weight = 0 because LPIPS weights are not available): loss, gradients and post-step weights."""
+    overrides = dict(SMALL_VQ, perceptual_weight=0.0)
+    cfg = VQGANConfig(**overrides)
+    sd = synth.make_vqgan_state_dict(cfg, 5)
+    ref = ref_loader.build_reference_vqgan(sd, **overrides)
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.9))          # configure_optimizers
+    g = torch.Generator().manual_seed(99)
+    names = [n for n, _ in ref.named_parameters()]
+    probe = {n: torch.randn(p.shape, generator=g) for n, p in ref.named_parameters()}
+    keep = ["encoder.conv_in.weight", "encoder.down.0.block.0.norm1.weight", "encoder.down.1.downsample.conv.weight", "encoder.mid.attn_1.q.weight",
+            "encoder.mid.attn_1.proj_out.bias", "quant_conv.weight", "post_quant_conv.bias", "decoder.up.1.upsample.conv.weight",
+            "decoder.up.0.block.2.conv2.weight", "decoder.up.0.block.0.nin_shortcut.weight", "decoder.conv_out.bias", "decoder.norm_out.bias"]
+    out = dict(names=np.array(names))
+    for step in range(2):
+        x = vq_images(3, cfg.image_size, 2000 + step)
+        opt.zero_grad()
+        xrec, qloss, _, codes = ref(x)
+        loss, log = ref._compute_loss(qloss, x, xrec, split="train")
+        loss.backward()
+        out[f"loss{step}"] = loss.detach().numpy()
+        out[f"rec{step}"] = log["train/rec_loss"].numpy()
+        out[f"quant{step}"] = log["train/quant_loss"].numpy()
+        out[f"codes{step}"] = codes.numpy()
+        out[f"gnorm{step}"] = np.array([float(p.grad.norm()) for _, p in ref.named_parameters()])
+        out[f"gdot{step}"] = np.array([float((p.grad * probe[n]).sum()) for n, p in ref.named_parameters()])
+        for k in keep:
+            out[f"g{step}.{k}"] = dict(ref.named_parameters())[k].grad.numpy().copy()
+        opt.step()
+        out[f"pdot{step}"] = np.array([float((p.detach() * probe[n]).sum()) for n, p in ref.named_parameters()])
+        for k in keep:
+            out[f"p{step}.{k}"] = dict(ref.named_parameters())[k].detach().numpy().copy()
+        out[f"emb{step}"] = ref.quantize.embeddings.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "vqgan_train_small.npz"), **out)
+    print("train golden: losses", float(out["loss0"]), float(out["loss1"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())

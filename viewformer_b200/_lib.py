@@ -25,6 +25,7 @@ EXPORTS = [
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
+    "vf_conv_wgrad", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
 ]
 
 
@@ -712,3 +713,94 @@ def l1_l2_sums(a, b):
     out = torch.zeros((2,), dtype=torch.float64, device=a.device)
     _check(lib.vf_l1_l2_sums(_p(a), _p(b), C.c_int64(a.numel()), _p(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------- backward pass (training step)
+def simt_conv_dgrad_s2(dy, w_dgrad_kn, in_hw):
+    """Data gradient of the stride-2 Downsample conv: dy f32 [N,OH,OW,Cout], w_dgrad_kn [9*Cout, Cin] (tap-major, NOT flipped)
+    -> dx f32 [N,H,W,Cin]."""
+    lib = load(True)
+    _dev(dy, torch.float32)
+    n, oh, ow, cout = dy.shape
+    h, w = in_hw
+    cin = w_dgrad_kn.shape[1]
+    out = torch.empty((n, h, w, cin), dtype=torch.float32, device=dy.device)
+    p = SimtGemm()
+    p.A, p.a_dtype, p.conv = dy.data_ptr(), F32, 2
+    p.N, p.H, p.W, p.Cin = n, oh, ow, cout
+    p.OH, p.OW, p.KH, p.KW, p.stride = h, w, 3, 3, 1
+    p.pad_t, p.pad_l, p.upsample2x = 0, 0, 0
+    p.B, p.b_dtype, p.b_sk, p.b_sn = w_dgrad_kn.data_ptr(), F32, cin, 1
+    p.M, p.Ncols, p.K, p.batch1, p.batch2 = n * h * w, cin, 9 * cout, 1, 1
+    p.alpha, p.act, p.bias_mode = 1.0, ACT_NONE, BIAS_NONE
+    p.C_f32, p.ldc = out.data_ptr(), cin
+    _check(lib.vf_simt_gemm(C.byref(p), _stream()))
+    return out
+
+
+def conv_wgrad(x, dy, dw, *, kh, stride=1, pad=(1, 1), upsample=False, so=None):
+    """dw (zeroed by the caller, accumulated here) [kh*kh*Cin, Cout] (or any layout via ``so`` = (stride of k, stride of co))."""
+    lib = load(True)
+    _dev(x, torch.float32); _dev(dy, torch.float32); _dev(dw, torch.float32)
+    n, h, w, cin = x.shape
+    _, oh, ow, cout = dy.shape
+    so_k, so_n = (cout, 1) if so is None else so
+    _check(lib.vf_conv_wgrad(_p(x), _p(dy), n, h, w, cin, oh, ow, cout, kh, kh, stride, pad[0], pad[1], int(upsample), C.c_int64(so_k),
+                             C.c_int64(so_n), _p(dw), _stream()))
+    return dw
+
+
+def col_sums(x_rows, out):
+    lib = load(True)
+    _dev(x_rows, torch.float32)
+    _check(lib.vf_col_sums(_p(x_rows), C.c_int64(x_rows.numel() // x_rows.shape[-1]), x_rows.shape[-1], _p(out), _stream()))
+    return out
+
+
+def groupnorm_bwd(x, dout, mean_rstd, gamma, beta, dgamma, dbeta, *, swish, groups=32, add=None):
+    lib = load(True)
+    _dev(x, torch.float32); _dev(dout, torch.float32)
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    gs = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+    _check(lib.vf_groupnorm_bwd(_p(x), _p(dout), _p(mean_rstd), _p(gamma), _p(beta), n, h * w, c, groups, int(swish), _p(add), _p(gs),
+                                _p(dgamma), _p(dbeta), _p(dx), _stream()))
+    return dx
+
+
+def softmax_bwd_rows(P, dP):
+    lib = load(True)
+    dS = torch.empty_like(P)
+    _check(lib.vf_softmax_bwd_rows(_p(P), _p(dP), C.c_int64(P.numel() // P.shape[-1]), P.shape[-1], _p(dS), _stream()))
+    return dS
+
+
+def l1_grad(x, y, scale):
+    """(dy = scale * sign(y - x), loss_sum f64[1] = sum |y - x|)"""
+    lib = load(True)
+    dy = torch.empty_like(y)
+    ls = torch.zeros((1,), dtype=torch.float64, device=y.device)
+    _check(lib.vf_l1_grad(_p(x), _p(y), C.c_int64(y.numel()), C.c_float(scale), _p(dy), _p(ls), _stream()))
+    return dy, ls
+
+
+def lincomb3(a, x, b=0.0, y=None, c=0.0, z=None, out=None):
+    lib = load(True)
+    if out is None:
+        out = torch.empty_like(x)
+    _check(lib.vf_lincomb3(C.c_float(a), _p(x), C.c_float(b), _p(y), C.c_float(c), _p(z), C.c_int64(x.numel()), _p(out), _stream()))
+    return out
+
+
+def sumpool2x2(x):
+    lib = load(True)
+    n, h2, w2, c = x.shape
+    y = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.float32, device=x.device)
+    _check(lib.vf_sumpool2x2(_p(x), n, h2 // 2, w2 // 2, c, _p(y), _stream()))
+    return y
+
+
+def adam(p, g, m, v, *, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    lib = load(True)
+    _check(lib.vf_adam(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                       int(step), C.c_float(grad_scale), _stream()))

@@ -59,7 +59,17 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const vf_simt_gemm_t p) 
             const int gk = k0 + ak0 + i;
             float v = 0.f;
             if (m_ok && gk < p.K) {
-                if (p.conv) {
+                if (p.conv == 2) {
+                    // data gradient of a stride-2 convolution (Downsample, vqgan_th.py:45-49: pad (0,1,0,1), VALID): row m is an INPUT
+                    // pixel (poy, pox) of the forward conv, A holds dY [N, H, W, Cin=Cout_fwd]; tap (kh, kw) contributes dY[(poy - kh) / 2,
+                    // (pox - kw) / 2] when both differences are even and inside dY
+                    const int ci = gk % p.Cin;
+                    const int tap = gk / p.Cin;
+                    const int kw = tap % p.KW, kh = tap / p.KW;
+                    const int ty2 = poy + p.pad_t - kh, tx2 = pox + p.pad_l - kw;
+                    if (ty2 >= 0 && tx2 >= 0 && !(ty2 & 1) && !(tx2 & 1) && (ty2 >> 1) < p.H && (tx2 >> 1) < p.W)
+                        v = ld_elem(p.A, p.a_dtype, a_boff + (((int64_t)pn * p.H + (ty2 >> 1)) * p.W + (tx2 >> 1)) * p.Cin + ci);
+                } else if (p.conv) {
                     const int ci = gk % p.Cin;
                     const int tap = gk / p.Cin;
                     const int kw = tap % p.KW, kh = tap / p.KW;

@@ -598,5 +598,25 @@ class VQGAN:
         n, hh, ww = ids.shape
         return L.nhwc_to_nchw(L.gather_rows(self._w["q"]["et"], ids.reshape(-1)).reshape(n, hh, ww, -1))
 
+    # ------------------------------------------------------------------ training (Lightning surface, vqgan_th.py:413-445)
     def configure_optimizers(self):
-        raise NotImplementedError("codebook training (VQGAN.training_step) is not part of this round; see DESIGN.md")
+        """The trainer object that owns Adam(betas=(0.5, 0.9), lr=config.learning_rate) and the flat parameter / gradient buffers."""
+        from .train import VQGANTrainer
+        if getattr(self, "_trainer", None) is None:
+            self._trainer = VQGANTrainer(self)
+        return self._trainer
+
+    def training_step(self, batch, batch_idx=0):
+        """Loss of one optimisation step on ``batch`` (f32 NCHW in [-1,1]); gradients are exchanged and Adam applied inside."""
+        return self.configure_optimizers().training_step(batch, batch_idx)
+
+    def validation_step(self, batch, batch_idx=0):
+        """vqgan_th.py:425-441: reconstruction and total loss without touching weights or the codebook."""
+        was = self.training
+        self.training = False
+        xrec, diff, _, _ = self(batch)
+        self.training = was
+        x = self._in(batch)
+        _, l1 = L.l1_grad(L.nchw_to_nhwc(x), L.nchw_to_nhwc(xrec), 0.0)
+        rec = (l1 / x.numel()).to(torch.float32).reshape(())
+        return {"val/rec_loss": rec, "val/aeloss": rec + float(self.config.codebook_weight) * diff, "reconstructed_image": xrec}
