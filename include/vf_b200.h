@@ -226,7 +226,8 @@ int vf_vq_select(const float* scores, const float* z, const float* Et, const flo
  *   D % 64 == 0, D <= 256, K % 256 == 0, K <= 1024, M < 2^31.  worklist: int4[M] scratch; counter: int[2] scratch, on return
  *   counter[0] = rows settled between two candidates, counter[1] = rows settled over all codes.  quant / diff_sum nullable. */
 int vf_vq_prepare_codebook_f16(const float* Et, int K, int D, void* Eh_f16, vf_stream_t s);
-int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const float* Et, const float* esq, int64_t M, int D, int K,
+int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const float* Et /* [K,D] */, const float* E_dk /* the same codebook as [D,K] */,
+                       const float* esq, int64_t M, int D, int K,
                        float tol_factor, int64_t* idx, void* worklist, int* counter, float* quant, double* diff_sum, vf_stream_t s);
 int vf_gather_rows(const float* table, const int64_t* idx, int64_t M, int D, int64_t n_rows, float* out, vf_stream_t s);
 /* training statistics of QuantizeEMA (utils_th.py:47-48): counts[K] += onehot, embed_sum[D,K] += z^T onehot */

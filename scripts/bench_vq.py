@@ -30,7 +30,7 @@ def timeit(fn, reps=5, warm=2):
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 for M in ([1 << 20] if only == "fused" else [18432, 1 << 17, 1 << 20]):
     z = torch.randn((M, 256), device=dev)
-    rows = [("fused tcgen05 (1 pass, fp16 pairs)", lambda: L.vq_lookup_fused(z, et, esq, eh, want_quant=False, want_diff=False))]
+    rows = [("fused tcgen05 (1 pass, fp16 pairs)", lambda: L.vq_lookup_fused(z, et, esq, eh, emb_dk=E, want_quant=False, want_diff=False))]
     if only != "fused":
         rows += [("bf16x3 GEMM + select (round 1)", lambda: L.vq_lookup_tc(z, et, esq, et3, want_quant=False, want_diff=False))]
         if M <= 1 << 17:
@@ -40,6 +40,6 @@ for M in ([1 << 20] if only == "fused" else [18432, 1 << 17, 1 << 20]):
         gbs = M * 1032 / ms / 1e6
         extra = ""
         if name.startswith("fused"):
-            _, _, _, cnt = L.vq_lookup_fused(z, et, esq, eh, want_quant=False, want_diff=False, return_counts=True)
+            _, _, _, cnt = L.vq_lookup_fused(z, et, esq, eh, emb_dk=E, want_quant=False, want_diff=False, return_counts=True)
             extra = f"  settled exactly: pair {int(cnt[0])} all-codes {int(cnt[1])}"
         print(f"VQ lookup M={M:8d} {name:36s} {ms:8.3f} ms  {gbs:8.1f} GB/s algorithmic = {100 * gbs / peaks['hbm_gbs']:5.1f}% of {peaks['hbm_gbs']:.0f} GB/s  ({2.0 * M * 1024 * 256 / ms / 1e9:7.1f} TFLOP/s){extra}")

@@ -31,19 +31,15 @@ if world > 1:
     dist.barrier()
 else:
     lmean = float(loss)
-if rank == 0:
-    if world > 1:
-        dist_state = (dist.group.WORLD)
-    # reference: the whole batch on one GPU, no process group involvement (a fresh trainer sees world size through dist: emulate by
-    # averaging manually) -> run with the default group but feed the full batch on rank 0 only via a separate 1-rank group
-    pass
 if world > 1:
-    solo_group = dist.new_group([rank])                      # every rank builds its own 1-member group; rank 0's is the one used
+    # reference run: the WHOLE batch on one GPU.  Every rank builds a 1-member group (new_group is collective) and repeats the step
+    # alone, with the EMA-statistics exchange switched off
+    groups = [dist.new_group([r]) for r in range(world)]
+    solo_group = groups[rank]
     tr1 = VQGANTrainer(VQGAN(cfg, precision="fp32", device=f"cuda:{local}").load_state_dict(sd), bucket_bytes=1 << 18, process_group=solo_group)
     from viewformer_b200 import dist as vdist
     _orig = vdist.allreduce_ema_stats
     vdist.allreduce_ema_stats = lambda c, e, group=None: (c, e)          # the solo run must not exchange EMA statistics
-    import viewformer_b200.vqgan as vq
     l1 = tr1.forward_backward(x)
     tr1.optimizer_step()
     vdist.allreduce_ema_stats = _orig

@@ -563,19 +563,21 @@ def vq_fused_ok(d, k):
     return d % 64 == 0 and d <= 256 and k % 256 == 0 and k <= 1024
 
 
-def vq_lookup_fused(z_rows, et, esq, eh, want_quant=True, want_diff=True, tol_factor=0.25, return_counts=False):
+def vq_lookup_fused(z_rows, et, esq, eh, emb_dk=None, want_quant=True, want_diff=True, tol_factor=0.25, return_counts=False):
     """Fused tcgen05 lookup (vf_vq_fused.cu): z read once, top-2 from TMEM, exact fp64 settlement of near-ties.  Same outputs as
     vq_lookup; ``return_counts`` adds the int32[2] tensor (rows settled between two candidates, rows settled over all codes)."""
     lib = load(True)
     _dev(z_rows, torch.float32)
     m, d = z_rows.shape
     k = et.shape[0]
+    if emb_dk is None:
+        emb_dk = et.t().contiguous()                         # callers that hold the reference's [D,K] layout pass it instead
     idx = torch.empty((m,), dtype=torch.int64, device=z_rows.device)
     work = torch.empty((max(m, 1), 4), dtype=torch.int32, device=z_rows.device)
     counter = torch.empty((2,), dtype=torch.int32, device=z_rows.device)
     quant = torch.empty((m, d), dtype=torch.float32, device=z_rows.device) if want_quant else None
     dsum = torch.zeros((1,), dtype=torch.float64, device=z_rows.device) if want_diff else None
-    _check(lib.vf_vq_lookup_fused(_p(z_rows), _p(eh), _p(et), _p(esq), C.c_int64(m), d, k, C.c_float(tol_factor), _p(idx), _p(work),
+    _check(lib.vf_vq_lookup_fused(_p(z_rows), _p(eh), _p(et), _p(emb_dk), _p(esq), C.c_int64(m), d, k, C.c_float(tol_factor), _p(idx), _p(work),
                                   _p(counter), _p(quant), _p(dsum), _stream()))
     return (idx, quant, dsum, counter) if return_counts else (idx, quant, dsum)
 

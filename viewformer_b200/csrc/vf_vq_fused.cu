@@ -393,7 +393,8 @@ __device__ __forceinline__ float warp_min_f(float v) {
 // Exact pass over the queued rows: fp64 direct sum of squared differences, ties to the smaller index.
 // PAIR entries (front of the worklist): one warp per entry, the two known candidates.  FULL entries (back of the worklist): one CTA per
 // entry, every thread scores K / 256 codes, block-wide argmin.
-__global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict__ z, const float* __restrict__ Et, int D, int K, long long M,
+__global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict__ z, const float* __restrict__ Et, const float* __restrict__ Edk,
+                                                        const float* __restrict__ esq, int D, int K, long long M,
                                                         const int4* __restrict__ worklist, const int* __restrict__ counter,
                                                         long long* __restrict__ idx) {
     constexpr int MAXCAND = 64;
@@ -432,32 +433,36 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         __syncthreads();
         float zz = 0.f;
         for (int d = 0; d < D; ++d) zz = fmaf(zs[d], zs[d], zz);
-        // screening: warp w scores codes w, w+8, ... with the 32 lanes across the row (coalesced 1 KB code rows), scores to smem
+        // screening: thread = code (c = tid, tid + 256, ...), the codebook read in its [D, K] layout so that a warp's 32 codes are one
+        // coalesced 128-byte row per dimension; z broadcast from shared memory; 4 x 4 independent loads in flight per thread
         float smin = INFINITY;
-        for (int c0 = warp * 4; c0 < K; c0 += 32) {            // 4 codes per iteration: 8 independent 16-byte loads in flight per lane
-            float dot[4] = {0.f, 0.f, 0.f, 0.f}, ee[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int d = lane * 4; d < D; d += 128) {
-                const float4 b = *reinterpret_cast<const float4*>(zs + d);
-                float4 a[4];
+        {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int d = 0; d < D; d += 4) {
+                float ev[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = (c0 + u < K) ? __ldg(reinterpret_cast<const float4*>(Et + (long long)(c0 + u) * D + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int dd = 0; dd < 4; ++dd)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    dot[u] = fmaf(a[u].x, b.x, dot[u]); dot[u] = fmaf(a[u].y, b.y, dot[u]); dot[u] = fmaf(a[u].z, b.z, dot[u]); dot[u] = fmaf(a[u].w, b.w, dot[u]);
-                    ee[u] = fmaf(a[u].x, a[u].x, ee[u]); ee[u] = fmaf(a[u].y, a[u].y, ee[u]); ee[u] = fmaf(a[u].z, a[u].z, ee[u]); ee[u] = fmaf(a[u].w, a[u].w, ee[u]);
-                }
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = threadIdx.x + q * 256;
+                        ev[dd][q] = c < K ? __ldg(Edk + (long long)(d + dd) * K + c) : 0.f;
+                    }
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] = fmaf(zs[d + dd], ev[dd][q], acc[q]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o); ee[u] += __shfl_xor_sync(0xffffffffu, ee[u], o); }
-                if (c0 + u < K) {
-                    const float sco = ee[u] - 2.0f * dot[u];
-                    if (lane == 0) scores[c0 + u] = sco;
+            for (int q = 0; q < 4; ++q) {
+                const int c = threadIdx.x + q * 256;
+                if (c < K) {
+                    const float sco = __ldg(esq + c) - 2.0f * acc[q];
+                    scores[c] = sco;
                     smin = fminf(smin, sco);
                 }
             }
         }
+        smin = warp_min_f(smin);
         if (lane == 0) sd[warp] = (double)smin;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -558,11 +563,11 @@ extern "C" int vf_vq_prepare_codebook_f16(const float* Et, int K, int D, void* E
     return VF_OK;
 }
 
-extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const float* Et, const float* esq, int64_t M, int D, int K,
+extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const float* Et, const float* E_dk, const float* esq, int64_t M, int D, int K,
                                   float tol_factor, int64_t* idx, void* worklist, int* counter, float* quant, double* diff_sum,
                                   vf_stream_t s) {
     if (M == 0) return VF_OK;
-    VF_CHECK_ARG(z && Eh_f16 && Et && esq && idx && worklist && counter, "vf_vq_lookup_fused: null pointer");
+    VF_CHECK_ARG(z && Eh_f16 && Et && E_dk && esq && idx && worklist && counter, "vf_vq_lookup_fused: null pointer");
     VF_CHECK_ARG(D % 64 == 0 && D <= 256 && K % 256 == 0 && K <= MAXK && M < (1ll << 31),
                  "vf_vq_lookup_fused: unsupported D=%d K=%d (D %% 64 == 0, D <= 256, K %% 256 == 0, K <= 1024)", D, K);
     VF_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "vf_vq_lookup_fused: z must be 16-byte aligned");
@@ -613,7 +618,7 @@ extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const floa
     e = cudaLaunchKernelEx(&cfg, vq_lookup_fused_kernel, prm);
     if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: cluster launch failed: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     VF_CHECK_LAUNCH("vf_vq_lookup_fused");
-    vq_rescue_kernel<<<num_sms * 8, 256, 0, st>>>(z, Et, D, K, M, prm.worklist, counter, prm.idx);
+    vq_rescue_kernel<<<num_sms * 8, 256, 0, st>>>(z, Et, E_dk, esq, D, K, M, prm.worklist, counter, prm.idx);
     VF_CHECK_LAUNCH("vf_vq_lookup_fused(rescue)");
     if (quant || diff_sum) {
         vq_gather_diff_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(z, Et, prm.idx, M, D, quant, diff_sum);

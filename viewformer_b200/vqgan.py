@@ -485,7 +485,7 @@ class VQGAN:
         q = self._w["q"]
         if q["eh"] is not None and os.environ.get("VF_VQ_FUSED", "1") != "0":
             # fused tcgen05 lookup: z read once, scores never leave TMEM, near-ties settled in fp64: same indices as the fp32 kernel
-            idx, quant, dsum = L.vq_lookup_fused(z_rows, q["et"], q["esq"], q["eh"], want_quant=want_quant, want_diff=True)
+            idx, quant, dsum = L.vq_lookup_fused(z_rows, q["et"], q["esq"], q["eh"], emb_dk=q["emb"], want_quant=want_quant, want_diff=True)
         elif q["et3"] is not None and z_rows.shape[1] % 64 == 0:
             # tensor-core distance GEMM (bf16x3) + exact fp64 re-score of every near-minimal candidate: same indices as the fp32 kernel
             idx, quant, dsum = L.vq_lookup_tc(z_rows, q["et"], q["esq"], q["et3"], want_quant=want_quant, want_diff=True)
