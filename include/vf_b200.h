@@ -190,6 +190,26 @@ int vf_lincomb3(float a, const float* x, float b, const float* y, float c, const
 int vf_sumpool2x2(const float* x, int N, int H, int W, int C, float* y, vf_stream_t s);
 int vf_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int step,
             float grad_scale, vf_stream_t s);
+/* Transformer training step (models/migt.py:464-505, models/utils.py:371-564):
+ *   vf_layernorm_bwd: LayerNorm backward over rows of D (statistics recomputed): dx (+ add), dgamma / dbeta accumulated.
+ *   vf_gelu_bwd: out = dy * d/dx gelu_erf(pre).   vf_migt_embed_bwd: backward of vf_migt_embed (scatter-add into wte / wpe / pose rows).
+ *   vf_cross_entropy_grad: dlogits = w[row] (softmax - smoothed one-hot).   vf_pose_loss_grad: gradient of vf_pose_loss_rows' (pos + ori).
+ *   vf_adamw_keras: Keras Adam update (epsilon outside the bias correction) preceded by AdamWeightDecay's p -= lr * wd * p;
+ *     the gradient is multiplied by grad_scale * clip_scale first (1 / world size, tf.clip_by_norm factor).
+ *   vf_sumsq: out += sum x^2 (per-tensor gradient norms for clip_by_norm).   vf_dropout: stateless inverted dropout, hash(seed, i). */
+int vf_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* add, int64_t rows, int D, float eps,
+                     float* dgamma, float* dbeta, float* dx, vf_stream_t s);
+int vf_gelu_bwd(const float* pre, const float* dy, int64_t n, float* out, vf_stream_t s);
+int vf_migt_embed_bwd(const float* dh, const int32_t* ids, int fixed_token, int64_t BT, int L, int d, float* dwte, float* dwpe,
+                      float* dpose, vf_stream_t s);
+int vf_cross_entropy_grad(const float* logits, const int32_t* labels, const float* row_weight, int64_t rows, int cols, float smoothing,
+                          float* dlogits, vf_stream_t s);
+int vf_pose_loss_grad(const float* raw, const float* poses, const float* row_weight, int64_t rows, int tokens_per_view,
+                      float pose_multiplier, float* draw, vf_stream_t s);
+int vf_adamw_keras(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, float clip_scale, vf_stream_t s);
+int vf_sumsq(const float* x, int64_t n, double* out, vf_stream_t s);
+int vf_dropout(const float* x, int64_t n, float rate, uint64_t seed, float* y, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Evaluation-side kernels

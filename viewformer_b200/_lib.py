@@ -26,6 +26,7 @@ EXPORTS = [
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
     "vf_conv_wgrad", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
+    "vf_layernorm_bwd", "vf_gelu_bwd", "vf_migt_embed_bwd", "vf_cross_entropy_grad", "vf_pose_loss_grad", "vf_adamw_keras", "vf_sumsq", "vf_dropout",
 ]
 
 
@@ -806,3 +807,58 @@ def adam(p, g, m, v, *, lr, beta1, beta2, eps, step, grad_scale=1.0):
     lib = load(True)
     _check(lib.vf_adam(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                        int(step), C.c_float(grad_scale), _stream()))
+
+
+def layernorm_bwd(x, dy, gamma, dgamma, dbeta, eps=1e-5, add=None):
+    lib = load(True)
+    d = x.shape[-1]
+    dx = torch.empty_like(x)
+    _check(lib.vf_layernorm_bwd(_p(x), _p(dy), _p(gamma), _p(add), C.c_int64(x.numel() // d), d, C.c_float(eps), _p(dgamma), _p(dbeta), _p(dx), _stream()))
+    return dx
+
+
+def gelu_bwd(pre, dy):
+    lib = load(True)
+    out = torch.empty_like(pre)
+    _check(lib.vf_gelu_bwd(_p(pre), _p(dy), C.c_int64(pre.numel()), _p(out), _stream()))
+    return out
+
+
+def migt_embed_bwd(dh, ids_i32, fixed_token, BT, L, dwte, dwpe, dpose):
+    lib = load(True)
+    _check(lib.vf_migt_embed_bwd(_p(dh), _p(ids_i32), int(fixed_token), C.c_int64(BT), L, dh.shape[-1], _p(dwte), _p(dwpe), _p(dpose), _stream()))
+
+
+def cross_entropy_grad(logits_rows, labels_i32, row_weight, smoothing=0.0):
+    lib = load(True)
+    rows, cols = logits_rows.shape
+    out = torch.empty_like(logits_rows)
+    _check(lib.vf_cross_entropy_grad(_p(logits_rows), _p(labels_i32), _p(row_weight), C.c_int64(rows), cols, C.c_float(smoothing), _p(out), _stream()))
+    return out
+
+
+def pose_loss_grad(raw_rows, poses_bt7, row_weight, tokens_per_view, mult):
+    lib = load(True)
+    out = torch.empty_like(raw_rows)
+    _check(lib.vf_pose_loss_grad(_p(raw_rows), _p(poses_bt7), _p(row_weight), C.c_int64(raw_rows.shape[0]), tokens_per_view, C.c_float(mult), _p(out), _stream()))
+    return out
+
+
+def adamw_keras(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, clip_scale=1.0):
+    lib = load(True)
+    _check(lib.vf_adamw_keras(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                              C.c_float(weight_decay), int(step), C.c_float(grad_scale), C.c_float(clip_scale), _stream()))
+
+
+def sumsq(x):
+    lib = load(True)
+    out = torch.zeros((1,), dtype=torch.float64, device=x.device)
+    _check(lib.vf_sumsq(_p(x), C.c_int64(x.numel()), _p(out), _stream()))
+    return out
+
+
+def dropout(x, rate, seed):
+    lib = load(True)
+    y = torch.empty_like(x)
+    _check(lib.vf_dropout(_p(x), C.c_int64(x.numel()), C.c_float(rate), C.c_uint64(int(seed) & ((1 << 64) - 1)), _p(y), _stream()))
+    return y

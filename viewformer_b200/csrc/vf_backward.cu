@@ -261,6 +261,158 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+
+// ---- transformer training step (models/migt.py:464-505): LayerNorm / GELU / embedding / loss backward, AdamWeightDecay --------------
+
+// LayerNorm backward, one warp per row (D <= 1024, D % 4 == 0): dx = rstd (dy g - mean(dy g) - xhat mean(dy g xhat)) + add;
+// dgamma / dbeta partial sums per block in shared memory, then one atomic per column and block
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+                                                            const float* __restrict__ add, long long rows, int D, float eps,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx) {
+    extern __shared__ float shs[];            // [2][D]
+    float* sg = shs;
+    float* sb = shs + D;
+    for (int i = threadIdx.x; i < 2 * D; i += 256) shs[i] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    if (row < rows) {
+        const float* xr = x + row * D;
+        const float* dr = dy + row * D;
+        float s = 0.f;
+        for (int c = lane; c < D; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / (float)D;
+        float ss = 0.f;
+        for (int c = lane; c < D; c += 32) { const float t = xr[c] - mean; ss = fmaf(t, t, ss); }
+        const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = lane; c < D; c += 32) {
+            const float xh = (xr[c] - mean) * rstd, dg = dr[c] * __ldg(gamma + c);
+            m1 += dg;
+            m2 = fmaf(dg, xh, m2);
+            atomicAdd(sb + c, dr[c]);
+            atomicAdd(sg + c, dr[c] * xh);
+        }
+        m1 = warp_sum(m1) / (float)D;
+        m2 = warp_sum(m2) / (float)D;
+        for (int c = lane; c < D; c += 32) {
+            const float xh = (xr[c] - mean) * rstd, dg = dr[c] * __ldg(gamma + c);
+            float v = rstd * (dg - m1 - xh * m2);
+            if (add) v += add[row * D + c];
+            dx[row * D + c] = v;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+        atomicAdd(dgamma + c, sg[c]);
+        atomicAdd(dbeta + c, sb[c]);
+    }
+}
+
+__global__ void gelu_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy, long long n, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float xv = pre[i];
+        const float cdf = 0.5f * (1.0f + erff(xv * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * xv * xv);
+        out[i] = dy[i] * (cdf + xv * pdf);
+    }
+}
+
+// backward of migt_embed_kernel: dh [BT*L, d] -> dwte[id] += dh (atomic scatter), dwpe[l] += dh, dpose[bt] += dh
+__global__ void embed_bwd_kernel(const float* __restrict__ dh, const int32_t* __restrict__ ids, int fixed_token, long long BT, int L, int d,
+                                 float* __restrict__ dwte, float* __restrict__ dwpe, float* __restrict__ dpose) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BT * L * d) return;
+    const int c = (int)(i % d);
+    const long long tok = i / d;
+    const int l = (int)(tok % L);
+    const long long bt = tok / L;
+    int id = ids ? ids[tok] : -1;
+    if (id < 0) id = fixed_token;
+    const float g = dh[i];
+    atomicAdd(dwte + (long long)id * d + c, g);
+    atomicAdd(dwpe + (long long)l * d + c, g);
+    if (dpose) atomicAdd(dpose + bt * d + c, g);
+}
+
+// d/dlogits of sum_rows w[row] * CE_smooth(logits[row], label[row]): w (softmax - (1-s) onehot - s/cols); one warp per row
+__global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, const float* __restrict__ w,
+                                                      long long rows, int cols, float smoothing, float* __restrict__ dlogits) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* x = logits + row * cols;
+    const float wr = w[row];
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < cols; c += 32) se += expf(x[c] - mx);
+    se = warp_sum(se);
+    const int lab = labels[row];
+    for (int c = lane; c < cols; c += 32) {
+        const float pr = expf(x[c] - mx) / se;
+        dlogits[row * cols + c] = wr * (pr - (c == lab ? 1.0f - smoothing : 0.f) - smoothing / (float)cols);
+    }
+}
+
+// d/draw of sum_rows w[row] * (pos_loss + ori_loss) (pose_loss_kernel in vf_misc.cu): pos = mean_3 (y m - r)^2, ori = mean_4 (y - r)^2
+__global__ void pose_loss_grad_kernel(const float* __restrict__ raw, const float* __restrict__ poses, const float* __restrict__ w, long long rows,
+                                      int tokens_per_view, float mult, float* __restrict__ draw) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float* r = raw + i * 7;
+    const float* y = poses + (i / tokens_per_view) * 7;
+    const float wr = w[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) draw[i * 7 + j] = wr * (-2.0f / 3.0f) * (y[j] * mult - r[j]);
+#pragma unroll
+    for (int j = 3; j < 7; ++j) draw[i * 7 + j] = wr * (-2.0f / 4.0f) * (y[j] - r[j]);
+}
+
+// Keras Adam (TF 2.4 optimizer_v2/adam.py, non-amsgrad): lr_t = lr sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2);
+// p -= lr_t m / (sqrt(v) + eps);  preceded by the decoupled decay p -= lr wd p of AdamWeightDecay (models/utils.py:507-515) when wd != 0
+__global__ void adamw_keras_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                                   float lr, float lr_t, float b1, float b2, float eps, float wd, float grad_scale, float clip_scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale * clip_scale;
+        float pi = p[i];
+        pi -= lr * wd * pi;
+        const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+        const float vi = v[i] + (gi * gi - v[i]) * (1.0f - b2);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += (double)x[i] * (double)x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        atomicAdd(out, t);
+    }
+}
+
+// inverted dropout with a counter-based hash (no state): keep = hash(seed, i) >= rate * 2^32; y = keep ? x / (1 - rate) : 0.
+// The backward pass calls it again on the gradient with the same (seed, offset).
+__device__ __forceinline__ uint32_t mix32(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (uint32_t)k;
+}
+__global__ void dropout_kernel(const float* __restrict__ x, long long n, float rate, unsigned long long seed, float* __restrict__ y) {
+    const uint32_t thr = (uint32_t)fminf(rate * 4294967296.0f, 4294967295.0f);
+    const float sc = 1.0f / (1.0f - rate);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = mix32(seed * 0x9E3779B97F4A7C15ULL + (unsigned long long)i) >= thr ? x[i] * sc : 0.f;
+}
+
 }  // namespace
 
 extern "C" int vf_conv_wgrad(const float* x, const float* dy, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
@@ -361,5 +513,74 @@ extern "C" int vf_adam(float* p, const float* g, float* m, float* v, int64_t n, 
     if (blocks > 148 * 16) blocks = 148 * 16;
     adam_kernel<<<(unsigned)blocks, 256, 0, vf_s(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
     VF_CHECK_LAUNCH("vf_adam");
+    return VF_OK;
+}
+
+static unsigned grid_for(long long n) {
+    long long b = (n + 255) / 256;
+    return (unsigned)(b > 148 * 16 ? 148 * 16 : b);
+}
+
+extern "C" int vf_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* add, int64_t rows, int D, float eps,
+                                float* dgamma, float* dbeta, float* dx, vf_stream_t s) {
+    VF_CHECK_ARG(x && dy && gamma && dgamma && dbeta && dx && D > 0 && D <= 4096, "vf_layernorm_bwd: bad args");
+    if (rows == 0) return VF_OK;
+    layernorm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 2 * D * sizeof(float), vf_s(s)>>>(x, dy, gamma, add, rows, D, eps, dgamma, dbeta, dx);
+    VF_CHECK_LAUNCH("vf_layernorm_bwd");
+    return VF_OK;
+}
+extern "C" int vf_gelu_bwd(const float* pre, const float* dy, int64_t n, float* out, vf_stream_t s) {
+    VF_CHECK_ARG(pre && dy && out, "vf_gelu_bwd: null pointer");
+    if (n == 0) return VF_OK;
+    gelu_bwd_kernel<<<grid_for(n), 256, 0, vf_s(s)>>>(pre, dy, n, out);
+    VF_CHECK_LAUNCH("vf_gelu_bwd");
+    return VF_OK;
+}
+extern "C" int vf_migt_embed_bwd(const float* dh, const int32_t* ids, int fixed_token, int64_t BT, int L, int d, float* dwte, float* dwpe,
+                                 float* dpose, vf_stream_t s) {
+    VF_CHECK_ARG(dh && dwte && dwpe, "vf_migt_embed_bwd: null pointer");
+    const long long total = BT * L * d;
+    if (total == 0) return VF_OK;
+    embed_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, vf_s(s)>>>(dh, ids, fixed_token, BT, L, d, dwte, dwpe, dpose);
+    VF_CHECK_LAUNCH("vf_migt_embed_bwd");
+    return VF_OK;
+}
+extern "C" int vf_cross_entropy_grad(const float* logits, const int32_t* labels, const float* row_weight, int64_t rows, int cols,
+                                     float smoothing, float* dlogits, vf_stream_t s) {
+    VF_CHECK_ARG(logits && labels && row_weight && dlogits && cols > 0, "vf_cross_entropy_grad: bad args");
+    if (rows == 0) return VF_OK;
+    ce_grad_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, vf_s(s)>>>(logits, labels, row_weight, rows, cols, smoothing, dlogits);
+    VF_CHECK_LAUNCH("vf_cross_entropy_grad");
+    return VF_OK;
+}
+extern "C" int vf_pose_loss_grad(const float* raw, const float* poses, const float* row_weight, int64_t rows, int tokens_per_view,
+                                 float pose_multiplier, float* draw, vf_stream_t s) {
+    VF_CHECK_ARG(raw && poses && row_weight && draw && tokens_per_view > 0, "vf_pose_loss_grad: bad args");
+    if (rows == 0) return VF_OK;
+    pose_loss_grad_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, vf_s(s)>>>(raw, poses, row_weight, rows, tokens_per_view, pose_multiplier, draw);
+    VF_CHECK_LAUNCH("vf_pose_loss_grad");
+    return VF_OK;
+}
+extern "C" int vf_adamw_keras(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int step, float grad_scale, float clip_scale, vf_stream_t s) {
+    VF_CHECK_ARG(p && g && m && v && step >= 1, "vf_adamw_keras: bad args");
+    if (n == 0) return VF_OK;
+    const float lr_t = lr * sqrtf(1.0f - powf(beta2, (float)step)) / (1.0f - powf(beta1, (float)step));
+    adamw_keras_kernel<<<grid_for(n), 256, 0, vf_s(s)>>>(p, g, m, v, n, lr, lr_t, beta1, beta2, eps, weight_decay, grad_scale, clip_scale);
+    VF_CHECK_LAUNCH("vf_adamw_keras");
+    return VF_OK;
+}
+extern "C" int vf_sumsq(const float* x, int64_t n, double* out, vf_stream_t s) {
+    VF_CHECK_ARG(x && out, "vf_sumsq: null pointer");
+    if (n == 0) return VF_OK;
+    sumsq_kernel<<<grid_for(n), 256, 0, vf_s(s)>>>(x, n, out);
+    VF_CHECK_LAUNCH("vf_sumsq");
+    return VF_OK;
+}
+extern "C" int vf_dropout(const float* x, int64_t n, float rate, uint64_t seed, float* y, vf_stream_t s) {
+    VF_CHECK_ARG(x && y && rate >= 0.f && rate < 1.f, "vf_dropout: bad args");
+    if (n == 0) return VF_OK;
+    dropout_kernel<<<grid_for(n), 256, 0, vf_s(s)>>>(x, n, rate, seed, y);
+    VF_CHECK_LAUNCH("vf_dropout");
     return VF_OK;
 }
