@@ -199,6 +199,7 @@ int vf_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, f
  *   vf_sumsq: out += sum x^2 (per-tensor gradient norms for clip_by_norm).   vf_dropout: stateless inverted dropout, hash(seed, i). */
 int vf_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* add, int64_t rows, int D, float eps,
                      float* dgamma, float* dbeta, float* dx, vf_stream_t s);
+int vf_gelu_fwd(const float* x, int64_t n, float* y, vf_stream_t s);      /* exact erf GELU (migt.py:13), kept separate so the pre-activation survives for the backward pass */
 int vf_gelu_bwd(const float* pre, const float* dy, int64_t n, float* out, vf_stream_t s);
 int vf_migt_embed_bwd(const float* dh, const int32_t* ids, int fixed_token, int64_t BT, int L, int d, float* dwte, float* dwpe,
                       float* dpose, vf_stream_t s);

@@ -158,6 +158,77 @@ def golden_vqgan_train():
     print("train golden: losses", float(out["loss0"]), float(out["loss1"]))
 
 
+def keras_adamw_reference(params, grads, m, v, step, lr, wd, betas=(0.9, 0.999), eps=1e-8):
+    """Restatement of AdamWeightDecay._resource_apply_dense (models/utils.py:507-523) on top of Keras Adam (TF 2.4
+    optimizer_v2/adam.py, non-amsgrad): decoupled decay for names without "bias" (the exclusion patterns "LayerNorm" / "layer_norm"
+    never match this model's variable names), then var -= lr_t * m / (sqrt(v) + eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t).  step is 1-based."""
+    b1, b2 = betas
+    lr_t = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+    for k in params:
+        if wd > 0 and "bias" not in k:
+            params[k] -= lr * wd * params[k]
+        m[k] += (grads[k] - m[k]) * (1 - b1)
+        v[k] += (grads[k] * grads[k] - v[k]) * (1 - b2)
+        params[k] -= lr_t * m[k] / (v[k].sqrt() + eps)
+
+
+def warmup_cosine(step, init_lr, warmup, total):
+    """WarmUp(CosineDecay) of models/utils.py:310-416 as create_optimizer builds it."""
+    import math
+    if warmup and step < warmup:
+        return init_lr * step / warmup
+    decay_steps = max(1, total - warmup)
+    t = min(max(step - warmup, 0), decay_steps) / decay_steps
+    return init_lr * 0.5 * (1 + math.cos(math.pi * t))
+
+
+MIGT_TRAIN = dict(SMALL_MIGT, dropout=0.0, weight_decay=0.01, total_steps=10, learning_rate=1e-3, label_smoothing=0.05, localization_weight="0.5",
+                  image_generation_weight=0.8, pose_multiplier=1.0)
+MIGT_TRAIN_WARMUP = 2
+
+
+def golden_migt_train():
+    """Three optimisation steps of the transformer: gradients by torch autograd through the oracle's forward (compute_losses=True,
+    dropout 0), optimizer / schedule restated above.  PARITY UNPINNED like every MIGT fixture (the reference is TensorFlow-only)."""
+    cfg = MIGTConfig(**MIGT_TRAIN)
+    sd = {k: v.clone() for k, v in synth.make_migt_state_dict(cfg, 9).items()}
+    B, T = 2, 4
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    vv = {k: torch.zeros_like(v) for k, v in sd.items()}
+    out = {}
+    KEEP = ("h.0.attn.c_attn.weight", "h.1.mlp.c_proj.bias", "h.1.ln_2.gamma", "ln_f.beta", "pose_classifier.c_proj.weight",
+            "pose_embedding.c_fc.weight", "wpe.embeddings", "h.1.attn.c_proj.weight")
+    for step in range(3):
+        codes = synth.make_codes(B, T, n_embed=cfg.n_embeddings, seed=50 + step)
+        cams = migt_oracle.normalize_cameras(migt_oracle.to_relative_cameras(synth.make_cameras(B, T, seed=60 + step))[0])
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        o = migt_oracle.forward(leaves, cfg, dict(input_ids=codes, poses=cams), compute_losses=True, localization_weight=0.5)
+        loss = o["loss"].mean()
+        loss.backward()
+        grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])) for k in sd}
+        out[f"loss{step}"] = loss.detach().numpy()
+        out[f"ce{step}"] = o["ce_loss"].detach().numpy()
+        out[f"pose{step}"] = o["pose_loss"].detach().numpy()
+        names = list(sd.keys())
+        if step == 0:
+            gen = torch.Generator().manual_seed(77)
+            probe = {k: torch.randn(sd[k].shape, generator=gen) for k in names}
+            out["names"] = np.array(names)
+        out[f"gnorm{step}"] = np.array([float(grads[k].norm()) for k in names])
+        out[f"gdot{step}"] = np.array([float((grads[k] * probe[k]).sum()) for k in names])
+        for k in KEEP:
+            out[f"g{step}.{k}"] = grads[k].numpy().astype(np.float32)
+        lr = warmup_cosine(step, cfg.learning_rate, MIGT_TRAIN_WARMUP, cfg.total_steps)
+        with torch.no_grad():
+            keras_adamw_reference(sd, grads, m, vv, step + 1, lr, cfg.weight_decay)
+        out[f"lr{step}"] = np.float32(lr)
+        out[f"pdot{step}"] = np.array([float((sd[k] * probe[k]).sum()) for k in names])
+        for k in KEEP:
+            out[f"p{step}.{k}"] = sd[k].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "migt_train_small.npz"), **out)
+    print("migt train golden: losses", [float(out[f"loss{i}"]) for i in range(3)])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -166,3 +237,5 @@ if __name__ == "__main__":
     golden_vqgan("small", SMALL_VQ, 2, 0)
     golden_vqgan("full", {}, 4, 0)
     golden_migt()
+    golden_vqgan_train()
+    golden_migt_train()

@@ -26,7 +26,7 @@ EXPORTS = [
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
     "vf_conv_wgrad", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
-    "vf_layernorm_bwd", "vf_gelu_bwd", "vf_migt_embed_bwd", "vf_cross_entropy_grad", "vf_pose_loss_grad", "vf_adamw_keras", "vf_sumsq", "vf_dropout",
+    "vf_layernorm_bwd", "vf_gelu_fwd", "vf_gelu_bwd", "vf_migt_embed_bwd", "vf_cross_entropy_grad", "vf_pose_loss_grad", "vf_adamw_keras", "vf_sumsq", "vf_dropout",
 ]
 
 
@@ -815,6 +815,13 @@ def layernorm_bwd(x, dy, gamma, dgamma, dbeta, eps=1e-5, add=None):
     dx = torch.empty_like(x)
     _check(lib.vf_layernorm_bwd(_p(x), _p(dy), _p(gamma), _p(add), C.c_int64(x.numel() // d), d, C.c_float(eps), _p(dgamma), _p(dbeta), _p(dx), _stream()))
     return dx
+
+
+def gelu(x):
+    lib = load(True)
+    y = torch.empty_like(x)
+    _check(lib.vf_gelu_fwd(_p(x), C.c_int64(x.numel()), _p(y), _stream()))
+    return y
 
 
 def gelu_bwd(pre, dy):

@@ -309,6 +309,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
 }
 
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = vf_gelu_erf(x[i]);
+}
+
 __global__ void gelu_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy, long long n, float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float xv = pre[i];
@@ -527,6 +531,13 @@ extern "C" int vf_layernorm_bwd(const float* x, const float* dy, const float* ga
     if (rows == 0) return VF_OK;
     layernorm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 2 * D * sizeof(float), vf_s(s)>>>(x, dy, gamma, add, rows, D, eps, dgamma, dbeta, dx);
     VF_CHECK_LAUNCH("vf_layernorm_bwd");
+    return VF_OK;
+}
+extern "C" int vf_gelu_fwd(const float* x, int64_t n, float* y, vf_stream_t s) {
+    VF_CHECK_ARG(x && y, "vf_gelu_fwd: null pointer");
+    if (n == 0) return VF_OK;
+    gelu_fwd_kernel<<<grid_for(n), 256, 0, vf_s(s)>>>(x, n, y);
+    VF_CHECK_LAUNCH("vf_gelu_fwd");
     return VF_OK;
 }
 extern "C" int vf_gelu_bwd(const float* pre, const float* dy, int64_t n, float* out, vf_stream_t s) {
