@@ -165,6 +165,10 @@ int vf_tc_gemm(const vf_tc_gemm_t* p, vf_stream_t s);
  *   head dim must be 64; S % block == 0.
  * ---------------------------------------------------------------------------------------- */
 int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s);
+/* Same kernel, only the query rows >= first_query (rounded down to a 128-row tile): the KV-cache decode step — the context's q|k rows and
+ * V^T columns stay in `qk` / `vt` from the prefill and the query view's are appended behind them. */
+int vf_attn_block_causal_tail(const void* qk_bf16, const void* vt_bf16, int B, int S, int H, int d, int block, int first_query,
+                              void* out_bf16, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Backward pass of the codebook training step (models/vqgan_th.py:395-423, 443-445), fp32.  Data gradients of convolutions and dense
@@ -294,10 +298,6 @@ int vf_cross_entropy_rows(const float* logits, const int32_t* labels, int64_t ro
 int vf_pose_loss_rows(const float* raw, const float* poses, int64_t rows, int tokens_per_view, float pose_multiplier,
                       float* pos_out, float* ori_out, vf_stream_t s);   /* per-token MSE of position / raw quaternion */
 int vf_row_mean(const float* x, int64_t rows, int n, int start, float* out, vf_stream_t s);   /* out[r] = mean(x[r, start:n]) */
-/* plain dtype casts / strided copies used between ops */
-int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s);
-/* sum(|a-b|) and sum((a-b)^2) into double[2] (training losses, vqgan_th.py:401) */
-int vf_l1_l2_sums(const float* a, const float* b, int64_t n, double* out2, vf_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -231,7 +231,13 @@ def forward(sd, cfg, inputs, compute_losses=False, use_localization=True, locali
     loss = 0
     if compute_losses:
         skip = cfg.n_loss_skip
-        ce = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), ids.reshape(-1).long(), reduction="none").reshape(B, T, L)
+        ls = float(getattr(cfg, "label_smoothing", 0.0))
+        flat = logits.reshape(-1, logits.shape[-1])
+        if ls > 0:      # migt.py:99-104: one-hot * (1 - s) + s / n_classes, then softmax_cross_entropy_with_logits
+            y = F.one_hot(ids.reshape(-1).long(), flat.shape[-1]).to(flat.dtype) * (1.0 - ls) + ls / flat.shape[-1]
+            ce = -(y * F.log_softmax(flat, -1)).sum(-1).reshape(B, T, L)
+        else:
+            ce = F.cross_entropy(flat, ids.reshape(-1).long(), reduction="none").reshape(B, T, L)
         ce = ce[:, skip:].mean((1, 2))
         out["ce_loss"] = ce
         loss = loss + ce * cfg.image_generation_weight

@@ -21,8 +21,8 @@ EXPORTS = [
     "vf_nchw_to_nhwc_f32", "vf_nhwc_to_nchw_f32", "vf_groupnorm_stats", "vf_groupnorm_apply", "vf_layernorm",
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
-    "vf_cast_f32_to_bf16", "vf_l1_l2_sums", "vf_cameras_prepare", "vf_cameras_from_relative",
-    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal",
+    "vf_cameras_prepare", "vf_cameras_from_relative",
+    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal", "vf_attn_block_causal_tail",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
     "vf_conv_wgrad", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
@@ -620,13 +620,15 @@ def migt_embed(ids_i32, fixed_token, wte, wpe, pose_rows, BT, L):
     return out
 
 
-def attn_block_causal(qk, vt, B, S, H, d, block):
-    """Fused tcgen05 block-causal attention: qk bf16 [B,S,2d] (q|k), vt bf16 [B,d,S] -> bf16 [B*S, d]."""
+def attn_block_causal(qk, vt, B, S, H, d, block, first_query=0, out=None):
+    """Fused tcgen05 block-causal attention: qk bf16 [B,S,2d] (q|k), vt bf16 [B,d,S] -> bf16 [B*S, d].
+    ``first_query`` > 0 computes only the query rows from that row's 128-row tile on (KV-cache decode)."""
     lib = load(True)
     _dev(qk, torch.bfloat16)
     _dev(vt, torch.bfloat16)
-    out = torch.empty((B * S, d), dtype=torch.bfloat16, device=qk.device)
-    _check(lib.vf_attn_block_causal(_p(qk), _p(vt), B, S, H, d, block, _p(out), _stream()))
+    if out is None:
+        out = torch.empty((B * S, d), dtype=torch.bfloat16, device=qk.device)
+    _check(lib.vf_attn_block_causal_tail(_p(qk), _p(vt), B, S, H, d, block, int(first_query), _p(out), _stream()))
     return out
 
 
@@ -700,21 +702,6 @@ def row_mean(x_rows, start=0):
     rows, n = x_rows.shape
     out = torch.empty((rows,), dtype=torch.float32, device=x_rows.device)
     _check(lib.vf_row_mean(_p(x_rows), C.c_int64(rows), n, start, _p(out), _stream()))
-    return out
-
-
-def cast_bf16(x):
-    lib = load(True)
-    _dev(x, torch.float32)
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _check(lib.vf_cast_f32_to_bf16(_p(x), _p(out), C.c_int64(x.numel()), _stream()))
-    return out
-
-
-def l1_l2_sums(a, b):
-    lib = load(True)
-    out = torch.zeros((2,), dtype=torch.float64, device=a.device)
-    _check(lib.vf_l1_l2_sums(_p(a), _p(b), C.c_int64(a.numel()), _p(out), _stream()))
     return out
 
 

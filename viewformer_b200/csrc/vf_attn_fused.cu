@@ -31,7 +31,7 @@ constexpr int TMEM_COLS = 512;                 // S0 [0,128) S1 [128,256) O [256
 
 struct AttnParams {
     CUtensorMap tmQ, tmK, tmV;
-    int S, H, d, block, n_qtiles;
+    int S, H, d, block, n_qtiles, qt0;      // query tiles qt0 .. qt0 + n_qtiles - 1 are computed (qt0 > 0: KV-cache query mode)
     __nv_bfloat16* out;
     unsigned idesc_s, idesc_o;
 };
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x % p.n_qtiles;
+    const int qt = p.qt0 + blockIdx.x % p.n_qtiles;
     const int bh = blockIdx.x / p.n_qtiles;
     const int h = bh % p.H, b = bh / p.H;
     const int q0 = qt * QT;
@@ -358,15 +358,27 @@ unsigned idesc_bf16(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | 
 
 }  // namespace
 
+extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, int S, int H, int d, int block, int first_query, void* out,
+                                         vf_stream_t s);
 extern "C" int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s) {
+    return vf_attn_block_causal_tail(qk, vt, B, S, H, d, block, 0, out, s);
+}
+
+// Only the query rows >= first_query (rounded down to a 128-row tile) are computed: with the context's q|k rows and V^T columns kept from
+// a prefill and the query view appended behind them, this is the KV-cache decode step (BASELINE config 5) — the same fused kernel, no
+// score matrix in HBM.  Rows of `out` below the first computed tile are left untouched.
+extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, int S, int H, int d, int block, int first_query, void* out,
+                                         vf_stream_t s) {
     VF_CHECK_ARG(qk && vt && out, "vf_attn_block_causal: null pointer");
+    VF_CHECK_ARG(first_query >= 0 && first_query < S, "vf_attn_block_causal: first_query out of range");
     VF_CHECK_ARG(H > 0 && d == H * DH, "vf_attn_block_causal: head dim must be 64 (d=%d H=%d)", d, H);
     VF_CHECK_ARG(block > 0 && S % block == 0 && S % 8 == 0, "vf_attn_block_causal: S=%d must be a multiple of block=%d and of 8", S, block);
     if (B == 0 || S == 0) return VF_OK;
     AttnParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.S = S; prm.H = H; prm.d = d; prm.block = block;
-    prm.n_qtiles = (S + QT - 1) / QT;
+    prm.qt0 = first_query / QT;
+    prm.n_qtiles = (S + QT - 1) / QT - prm.qt0;
     prm.out = reinterpret_cast<__nv_bfloat16*>(out);
     prm.idesc_s = idesc_bf16(128, 128);
     prm.idesc_o = idesc_bf16(128, 64);

@@ -290,44 +290,6 @@ __global__ void __launch_bounds__(256) row_mean_kernel(const float* __restrict__
     }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i + 3 < n) {
-        const float4 v = *reinterpret_cast<const float4*>(in + i);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&lo);
-        u.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(out + i) = u;
-    } else {
-        for (int64_t j = i; j < n; ++j) out[j] = __float2bfloat16(in[j]);
-    }
-}
-
-__global__ void __launch_bounds__(256) l1_l2_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
-                                                    double* __restrict__ out2) {
-    __shared__ double sh[2][8];
-    double s1 = 0.0, s2 = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const float d = a[i] - b[i];
-        s1 += fabsf(d);
-        s2 += (double)d * d;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { sh[0][warp] = s1; sh[1][warp] = s2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t1 = 0, t2 = 0;
-        for (int w = 0; w < 8; ++w) { t1 += sh[0][w]; t2 += sh[1][w]; }
-        atomicAdd(out2 + 0, t1);
-        atomicAdd(out2 + 1, t2);
-    }
-}
 
 }  // namespace
 
@@ -438,21 +400,5 @@ extern "C" int vf_row_mean(const float* x, int64_t rows, int n, int start, float
     if (rows == 0) return VF_OK;
     row_mean_kernel<<<(unsigned)rows, 256, 0, vf_s(s)>>>(x, n, start, out);
     VF_CHECK_LAUNCH("vf_row_mean");
-    return VF_OK;
-}
-extern "C" int vf_cast_f32_to_bf16(const float* in, void* out, int64_t n, vf_stream_t s) {
-    VF_CHECK_ARG(in && out, "vf_cast_f32_to_bf16: null");
-    if (n == 0) return VF_OK;
-    cast_bf16_kernel<<<nblk(n, 1024), 256, 0, vf_s(s)>>>(in, (__nv_bfloat16*)out, n);
-    VF_CHECK_LAUNCH("vf_cast_f32_to_bf16");
-    return VF_OK;
-}
-extern "C" int vf_l1_l2_sums(const float* a, const float* b, int64_t n, double* out2, vf_stream_t s) {
-    VF_CHECK_ARG(a && b && out2, "vf_l1_l2_sums: null");
-    if (n == 0) return VF_OK;
-    unsigned blocks = nblk(n, 256 * 8);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    l1_l2_kernel<<<blocks, 256, 0, vf_s(s)>>>(a, b, n, out2);
-    VF_CHECK_LAUNCH("vf_l1_l2_sums");
     return VF_OK;
 }

@@ -1042,7 +1042,9 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         fresh = false;
                         tcgen05_commit(&w_empty[ws]);
                         if (++ws == WIDE_W_SLOTS) { ws = 0; wph ^= 1; }
-                        if (kExact && ++in_chunk == p.kc) { in_chunk = 0; close_acc(); }
+                        // cross-term passes (scaled by 2^-11: their accumulation error is far below fp32) drain once per channel block,
+                        // the hi.hi pass every p.kc taps
+                        if (kExact && ++in_chunk == (cb < 2 * p.cin_blocks ? 9 : p.kc)) { in_chunk = 0; close_acc(); }
                     }
                     tcgen05_commit(&h_empty[hb]);
                     if (++hb == 2) { hb = 0; hph ^= 1; }
@@ -1190,8 +1192,8 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         a1[j] = 0.f;
                     }
                 }
-                const int cpv = 9 / p.kc;                               // chunks per (product pass, channel block)
-                const int nchunks = 3 * p.cin_blocks * cpv, nsmall = 2 * p.cin_blocks * cpv;
+                // chunks: one per channel block of the two cross-term passes, 9 / kc per channel block of the hi.hi pass
+                const int nsmall = 2 * p.cin_blocks, nchunks = nsmall + p.cin_blocks * (9 / p.kc);
                 int a = acc;
                 uint32_t aph = acc_phase;
                 --it;                                                   // undo the per-tile increment: one hand-off per chunk
