@@ -138,7 +138,7 @@ def ncu_traffic(rel_path, scale):
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot = 0.0
     for line in open(path):
-        f = line.rstrip("\n").split(",")
+        f = [c.strip().strip('"') for c in line.rstrip("\n").split(",")]
         if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and len(f) >= 3 and f[1] in unit:
             tot += float(f[2]) * unit[f[1]]
     return (tot * scale if tot else None), f"{rel_path} (ncu --set full of this kernel, 288 images/launch) x {scale:.3f}"
@@ -381,33 +381,65 @@ def run_b200(args):
             del cb2, tr2, res2, g2, o2
             torch.cuda.empty_cache()
 
-    # ---- roofline of the dominant kernel of the TENSOR-CORE conv path: tcgen05 implicit-GEMM conv 128->128 3x3 at 128x128
+    # ---- roofline of the dominant kernel: the 3x3 conv 128->128 @128x128 of the encoder (288 images per launch).
+    # mixed / x3: the exact split-fp16 kernel — three fp16 MMA passes per product, so the tensor pipe executes 3x the convolution's
+    # algorithmic FLOPs; `achieved` is the EXECUTED rate (what the pipe does), `achieved_algorithmic` the fp32-equivalent rate.
     peak_tf, peak_hbm, peak_src = measured_peaks()
     n_img = B * N_CTX
-    x = torch.randn((n_img, IMG, IMG, 128), device=dev).to(torch.bfloat16)
-    w = (torch.randn((128, 9 * 128), device=dev) / 34.0).to(torch.bfloat16)
+    exact = args.precision in ("mixed", "x3")
+
+    def time_launch(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / reps
+
+    xf = torch.randn((n_img, IMG, IMG, 128), device=dev)
+    wf = torch.randn((128 * 9, 128), device=dev) / 34.0
     b = torch.zeros(128, device=dev)
     o = torch.empty((n_img, IMG, IMG, 128), device=dev)
-    for _ in range(3):
-        _lib.tc_conv(x, w, b, out=o)
-    reps = 5
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        _lib.tc_conv(x, w, b, out=o)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / 1e3 / reps
+    if exact:
+        x = _lib.groupnorm(xf, None, None, swish=False, out_dtype=torch.float16, normalize=False)
+        w = _lib.split_f16x2(wf).reshape(128, 18 * 128)
+    else:
+        x, w = xf.to(torch.bfloat16), wf.reshape(128, 9 * 128).to(torch.bfloat16)
+    del xf
+    sec = time_launch(lambda: _lib.tc_conv(x, w, b, out=o))
     flops = 2.0 * n_img * IMG * IMG * 128 * 9 * 128          # 2*M*N*K of the implicit GEMM
-    ach = flops / sec / 1e12
-    traffic, traffic_src = ncu_traffic("profiles/r01_conv_wide_ncu_nores_metrics.csv", n_img / 288.0)
-    roof = {"kernel": "tc_conv3x3_wide_kernel: persistent tcgen05 implicit GEMM, 128 channels x 256 pixels per tile (3x3 conv 128->128 @128x128, "
-                      "%d images/launch, bf16 operands)" % n_img,
+    passes = 3 if exact else 1
+    ach = passes * flops / sec / 1e12
+    cap = "profiles/r02_exact_conv_wide_ncu_metrics.csv" if exact else "profiles/r01_conv_wide_ncu_nores_metrics.csv"
+    traffic, traffic_src = ncu_traffic(cap, n_img / 288.0)
+    roof = {"kernel": ("tc_conv3x3_wide_kernel<exact>: persistent tcgen05 implicit GEMM on split-fp16 operands (3 MMA passes, chunked accumulation), "
+                       if exact else "tc_conv3x3_wide_kernel: persistent tcgen05 implicit GEMM, ") +
+                      "128 channels x 256 pixels per tile (3x3 conv 128->128 @128x128, %d images/launch)" % n_img,
             "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-            "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": sec * 1e3,
-            "algorithmic_bytes_per_launch": n_img * IMG * IMG * 128 * (2 + 4)}
+            "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": sec * 1e3, "mma_passes": passes,
+            "achieved_algorithmic": flops / sec / 1e12, "frac_algorithmic": flops / sec / 1e12 / peak_tf,
+            "algorithmic_bytes_per_launch": n_img * IMG * IMG * 128 * ((4 if exact else 2) + 4)}
     del x, w, o
+
+    # ---- second roofline entry: the codebook lookup (HBM-bound by the north_star: 1032 algorithmic bytes per token)
+    Mvq = 1 << 20
+    q = codebook._w["q"]
+    zq = torch.randn((Mvq, q["et"].shape[1]), device=dev)
+    roof_vq = None
+    if q.get("eh") is not None:
+        sec_vq = time_launch(lambda: _lib.vq_lookup_fused(zq, q["et"], q["esq"], q["eh"], emb_dk=q["emb"], want_quant=False, want_diff=False), reps=3)
+        ach_vq = Mvq * (q["et"].shape[1] * 4 + 8) / sec_vq / 1e9
+        tr_vq, tr_vq_src = ncu_traffic("profiles/r02_vq_fused_ncu_metrics.csv", 1.0)
+        roof_vq = {"kernel": "vq_lookup_fused_kernel + vq_rescue_kernel: fp16 distance GEMM on CTA pairs, top-2 from TMEM, fp64 settlement of near-ties "
+                             "(z ~ N(0,1) [2^20, 256] fp32 -> int64 indices, K = 1024)",
+                   "bound": "hbm", "achieved": ach_vq, "peak": peak_hbm, "unit": "GB/s", "frac": ach_vq / peak_hbm, "traffic": tr_vq,
+                   "traffic_source": tr_vq_src, "peak_source": peak_src, "launch_ms": sec_vq * 1e3,
+                   "algorithmic_bytes_per_launch": Mvq * (q["et"].shape[1] * 4 + 8)}
+    del zq
 
     # ---- CPU baseline: the oracle on the first scenes of THIS run's inputs; its outputs double as a parity check of the timed pipeline
     cpu = None
@@ -451,6 +483,7 @@ def run_b200(args):
         "parity": parity,
         "value_by_precision": by_prec,
         "roofline": roof,
+        "roofline_vq_lookup": roof_vq,
         "cpu_baseline": cpu,
     }))
     if world > 1:

@@ -301,7 +301,8 @@ class MIGT:
         """MIGT.call (migt.py:338-455), inference semantics (training=False; dropout inactive).
         ``last_only=True`` computes logits for the last view only (what evaluate_transformer.py:123 consumes)."""
         if training:
-            raise NotImplementedError("MIGT training (dropout + backward) is not part of this round; see DESIGN.md")
+            raise NotImplementedError("the training-mode forward (dropout) lives in the optimisation step: use MIGT.train_step / "
+                                      "viewformer_b200.train_migt.MIGTTrainer")
         if compute_losses and last_only:
             raise ValueError("compute_losses needs the logits of every view (last_only=False)")
         if compute_losses and self.config.use_dynamic_pose_loss:
@@ -394,6 +395,22 @@ class MIGT:
         """QuaternionPoseRepresentation.reduce (migt.py:150-154, 123-129): host-side, a handful of floats."""
         from .generate import reduce_cameras
         return reduce_cameras(cameras, axis)
+
+    # ------------------------------------------------------------------ Keras training surface (migt.py:457-505)
+    def compile(self, optimizer=None, **kwargs):
+        """migt.py:457-462: AdamWeightDecay + 2000-step warm-up + cosine decay; the trainer owns the flat parameter / gradient buffers."""
+        from .train_migt import MIGTTrainer
+        self._trainer = optimizer if optimizer is not None else MIGTTrainer(self, **kwargs)
+        return self._trainer
+
+    def train_step(self, batch):
+        """(poses [B,T,7], tokens [B,T,h,w]) -> metrics dict; one optimisation step (forward, backward, gradient exchange, AdamW).
+        The model serves inference with the updated weights right away (they are re-laid-out for the inference kernels)."""
+        if getattr(self, "_trainer", None) is None:
+            self.compile()
+        out = self._trainer.train_step(batch)
+        self.load_state_dict(self._trainer.state_dict())
+        return out
 
     # ------------------------------------------------------------------ Keras evaluation steps (migt.py:507-541)
     def test_step(self, batch):
