@@ -536,6 +536,39 @@ def test_fused_block_causal_attention(L, B, T, H, blk):
     report(f"fused attention B{B} T{T} H{H} blk{blk}", out.float(), want, 2e-2, 2e-2)
 
 
+def _attn_reference(qk, v, B, S, H, d, blk):
+    q = qk[..., :d].double().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    k = qk[..., d:].double().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    vv = v.double().reshape(B, S, H, 64).permute(0, 2, 1, 3)
+    view = torch.arange(S) // blk
+    m = (view[:, None] >= view[None, :]).double()
+    w = q @ k.transpose(-1, -2)
+    w = w * m - 1e4 * (1 - m)
+    return (torch.softmax(w, -1) @ vv).permute(0, 2, 1, 3).reshape(B * S, d)
+
+
+@pytest.mark.parametrize("B,T,H,blk,first", [(2, 6, 2, 64, 0), (1, 20, 2, 64, 0), (2, 20, 3, 64, 19 * 64), (1, 7, 1, 64, 6 * 64)])
+def test_fused_attention_growing_logits_and_tail(L, B, T, H, blk, first):
+    """Single-pass softmax: key norms grow from view to view, so the running reference maximum has to move (and the TMEM accumulator be
+    rescaled) several times per row; `first` > 0 is the KV-cache decode call (only the last view's query rows are computed)."""
+    d, S = H * 64, T * blk
+    qk = (torch.randn(B, S, 2 * d, generator=g(S + H + 7)) * 0.5)
+    scale = (1.0 + 0.9 * (torch.arange(S) // blk).float())[None, :, None]
+    qk[..., d:] *= scale                       # later views: larger keys -> the row maximum keeps growing along the key axis
+    qk = qk.bfloat16()
+    v = torch.randn(B, S, d, generator=g(S + H + 8)).bfloat16()
+    vt = v.permute(0, 2, 1).contiguous()
+    out = torch.full((B * S, d), 7.0, dtype=torch.bfloat16, device="cuda")
+    L.attn_block_causal(qk.cuda(), vt.cuda(), B, S, H, d, blk, first_query=first, out=out)
+    torch.cuda.synchronize()
+    want = _attn_reference(qk, v, B, S, H, d, blk)
+    t0 = (first // 128) * 128
+    got = out.float().cpu().reshape(B, S, d)
+    report(f"fused attention (growing logits) B{B} T{T} H{H} first{first}", got[:, t0:].reshape(-1, d), want.reshape(B, S, d)[:, t0:].reshape(-1, d), 2e-2, 2e-2)
+    if t0 > 0:
+        assert bool((got[:, :t0] == 7.0).all()), "rows below the first computed tile must stay untouched"
+
+
 def test_vq_lookup_tensor_core_bit_exact(L, golden_dir):
     """bf16x3 tcgen05 distance GEMM + exact fp64 re-score == the reference's indices, incl. the adversarial near-ties."""
     import os

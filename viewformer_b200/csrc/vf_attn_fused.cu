@@ -4,121 +4,117 @@
 // of its own and of every earlier view; logits are NOT scaled by 1/sqrt(dh); masked logits are -1e4 in the reference,
 // whose exp underflows to exactly 0 in fp32, so masked keys are simply skipped here) for the single-stream forward.
 //
-// One CTA = 128 queries (two 64-token views) of one (batch, head).  S = Q K^T (128x128, fp32) lives in TMEM
-// (double-buffered), the softmax warps own one query row per thread (no shuffles), P is written as bf16 into a
-// 128B-swizzled K-major smem tile and fed back as the A operand of O += P V (O: 128x64 fp32 in TMEM).
-// Two passes over the visible key tiles avoid any accumulator rescaling: pass 1 finds the exact row maxima
-// (QK^T only), pass 2 recomputes S, exponentiates against the final maximum and accumulates P V and the row sums.
-// Fully masked key tiles are never loaded.
+// One CTA = 128 queries (two 64-token views) of one (batch, head); two CTAs share an SM (256 TMEM columns, ~72 KB of shared
+// memory each), so one CTA's prologue / epilogue hides behind the other's main loop.  Keys are walked ONCE in 64-key tiles:
+//   S_j = Q K_j^T   128x64 fp32 in TMEM (double-buffered)
+//   softmax warps (one query row per thread, no shuffles): row max of the tile, P_j = exp2(S_j log2e - m_ref) as packed bf16
+//   written straight back to TMEM (tcgen05.st), row sums in registers
+//   O  += P_j V_j   with P as the TMEM A operand of tcgen05.mma (no shared-memory round trip for P), O 128x64 fp32 in TMEM.
+// Online softmax with a lazy reference maximum: m_ref only moves when a tile's maximum exceeds it by more than 2^8, and only
+// then is the O accumulator rescaled in TMEM (tcgen05.ld -> scale -> tcgen05.st, after the previous P V has retired).  The
+// final O / l does not depend on which reference was used, so this is the same softmax, not an approximation.
+// Fully masked key tiles are never loaded; a 64-key tile a warp's rows cannot see costs that warp one zero store.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 softmax / epilogue.
-#include "vf_common.cuh"
-#include <cuda.h>
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 softmax / correction / epilogue.
+#include "vf_tcgen05.cuh"
 
 namespace {
+using namespace vftc;
 
 constexpr int QT = 128;            // queries per CTA
-constexpr int KT = 128;            // keys per tile
+constexpr int KT = 64;             // keys per tile (= one 128-byte swizzle row of V^T, one TMEM S buffer of 64 columns)
 constexpr int DH = 64;             // head dim (one 128-byte swizzle row)
-constexpr int KSTAGES = 3;         // K tile ring
-constexpr int VSTAGES = 2;         // V^T tile ring
+constexpr int KSTAGES = 4;         // K tile ring
+constexpr int VSTAGES = 3;         // V^T tile ring
 constexpr int Q_BYTES = QT * 128;              // 16 KB
-constexpr int K_BYTES = KT * 128;              // 16 KB
-constexpr int V_BYTES = 2 * DH * 128;          // two [64 dh rows x 64 keys] atoms = 16 KB
-constexpr int P_BYTES = 2 * QT * 128;          // two [128 q rows x 64 keys] atoms = 32 KB
+constexpr int K_BYTES = KT * 128;              // 8 KB
+constexpr int V_BYTES = DH * 128;              // [64 dh rows x 64 keys] = 8 KB
+constexpr int PS_BYTES = QT * 128;             // shared-memory P tile (kPTmem = false): [128 q rows x 64 keys] = 16 KB
 constexpr int ATTN_THREADS = 192;
-constexpr int TMEM_COLS = 512;                 // S0 [0,128) S1 [128,256) O [256,320)
+constexpr int TMEM_COLS = 256;                 // S0 [0,64) S1 [64,128) P0 [128,160) P1 [160,192) O [192,256)
+constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LAZY_LOG2 = 8.0f;              // the reference maximum moves only when a tile exceeds it by more than 2^8
 
 struct AttnParams {
     CUtensorMap tmQ, tmK, tmV;
-    int S, H, d, block, n_qtiles, qt0;      // query tiles qt0 .. qt0 + n_qtiles - 1 are computed (qt0 > 0: KV-cache query mode)
+    int S, H, d, block, n_qtiles, qt0, BH;  // query tiles qt0 .. qt0 + n_qtiles - 1 are computed (qt0 > 0: KV-cache query mode)
     __nv_bfloat16* out;
-    unsigned idesc_s, idesc_o;
+    unsigned idesc;                         // M = 128, N = 64 for both Q K^T and P V
 };
 
-// one elected lane; the compiler knows a single thread is active in the guarded region (plain R2UR for tcgen05 / TMA operands)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x (K/2) 32-bit columns, two K-adjacent 16-bit elements per column
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+          "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+          "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 22); ++i)
-        if (mbar_try_wait(bar, parity)) return;
-    printf("vf_attn: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-    __trap();
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// two back-to-back 32-column loads, one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t* q = r + 32 * h;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+              "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+              "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+              "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+            : "r"(taddr + 32 * h));
+    }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
-__global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(const __grid_constant__ AttnParams p) {
+// tile t of a CTA uses ring buffer t & 1; its k-th use completes the barrier's k-th phase (k = t >> 1)
+__device__ __forceinline__ uint32_t use_parity(int t) { return (uint32_t)(t >> 1) & 1u; }
+
+template <bool kPTmem>
+__global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + Q_BYTES;
     uint8_t* sV = sK + KSTAGES * K_BYTES;
-    uint8_t* sP = sV + VSTAGES * V_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint8_t* sP = sV + VSTAGES * V_BYTES;                  // 2 x PS_BYTES when P goes through shared memory, else empty
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (kPTmem ? 0 : 2 * PS_BYTES));
     uint64_t* q_full = bars;                 // 1
     uint64_t* k_full = bars + 1;             // KSTAGES
     uint64_t* k_empty = k_full + KSTAGES;    // KSTAGES
     uint64_t* v_full = k_empty + KSTAGES;    // VSTAGES
     uint64_t* v_empty = v_full + VSTAGES;    // VSTAGES
-    uint64_t* s_full = v_empty + VSTAGES;    // 2
-    uint64_t* s_empty = s_full + 2;          // 2
-    uint64_t* p_full = s_empty + 2;          // 2
-    uint64_t* p_empty = p_full + 2;          // 2
-    uint64_t* o_full = p_empty + 2;          // 1
+    uint64_t* s_full = v_empty + VSTAGES;    // 2: S_t written (MMA commit)
+    uint64_t* s_empty = s_full + 2;          // 2: S_t read by all four softmax warps
+    uint64_t* p_full = s_empty + 2;          // 2: P_t written by all four softmax warps
+    uint64_t* pv_done = p_full + 2;          // 2: P_t V_t retired (MMA commit): P buffer free, O stable up to tile t
+    uint64_t* o_full = pv_done + 2;          // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = p.qt0 + blockIdx.x % p.n_qtiles;
-    const int bh = blockIdx.x / p.n_qtiles;
+    // heaviest query tiles (most visible keys) first
+    const int qt = p.qt0 + p.n_qtiles - 1 - (int)(blockIdx.x / p.BH);
+    const int bh = blockIdx.x % p.BH;
     const int h = bh % p.H, b = bh / p.H;
     const int q0 = qt * QT;
     // keys visible to the tile's last valid query: views <= view(last query)
@@ -126,11 +122,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
     const int kv_lim = min(p.S, (last_q / p.block + 1) * p.block);
     const int n_kt = (kv_lim + KT - 1) / KT;
 
-    if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmQ)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmK)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmV)) : "memory");
-    }
+    if (threadIdx.x == 0) { prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV); }
     if (threadIdx.x == 32) {
         mbar_init(q_full, 1);
         for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
@@ -139,20 +131,16 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 4);       // one arrive per softmax warp
             mbar_init(&p_full[i], 4);
-            mbar_init(&p_empty[i], 1);
+            mbar_init(&pv_done[i], 1);
         }
         mbar_init(o_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_o = tmem + 256;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -161,160 +149,160 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
             tma_load_4d(sQ, &p.tmQ, q_full, 0, q0, h, b);
             int ks = 0, vs = 0;
             uint32_t kph = 0, vph = 0;
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int j = 0; j < n_kt; ++j) {
-                    mbar_wait(&k_empty[ks], kph ^ 1);
-                    mbar_expect_tx(&k_full[ks], K_BYTES);
-                    tma_load_4d(sK + ks * K_BYTES, &p.tmK, &k_full[ks], 0, j * KT, h, b);
-                    if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-                    if (pass == 1) {
-                        mbar_wait(&v_empty[vs], vph ^ 1);
-                        mbar_expect_tx(&v_full[vs], V_BYTES);
-                        uint8_t* dst = sV + vs * V_BYTES;
-                        tma_load_4d(dst, &p.tmV, &v_full[vs], j * KT, h * DH, b, 0);                    // keys [0,64) of the tile
-                        tma_load_4d(dst + DH * 128, &p.tmV, &v_full[vs], j * KT + 64, h * DH, b, 0);    // keys [64,128)
-                        if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-                    }
-                }
+            for (int j = 0; j < n_kt; ++j) {
+                mbar_wait(&k_empty[ks], kph ^ 1, "vf_attn producer(K)");
+                mbar_expect_tx(&k_full[ks], K_BYTES);
+                tma_load_4d(sK + ks * K_BYTES, &p.tmK, &k_full[ks], 0, j * KT, h, b);
+                if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+                mbar_wait(&v_empty[vs], vph ^ 1, "vf_attn producer(V)");
+                mbar_expect_tx(&v_full[vs], V_BYTES);
+                tma_load_4d(sV + vs * V_BYTES, &p.tmV, &v_full[vs], j * KT, h * DH, b, 0);
+                if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            mbar_wait(q_full, 0);
+            mbar_wait(q_full, 0, "vf_attn issuer(Q)");
             tc_fence_after();
             const uint64_t qdesc = sw128_desc(smem_u32(sQ));
-            int ks = 0, vs = 0, sb = 0, pb = 0;
-            uint32_t kph = 0, vph = 0, sph = 0, pph = 0;
-            auto issue_s = [&]() {       // S[sb] = Q K^T for the next K tile in the ring
-                mbar_wait(&k_full[ks], kph);
-                mbar_wait(&s_empty[sb], sph ^ 1);
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            auto issue_s = [&](int t) {       // S[t & 1] = Q K_t^T
+                mbar_wait(&k_full[ks], kph, "vf_attn issuer(K)");
+                if (t >= 2) mbar_wait(&s_empty[t & 1], use_parity(t - 2), "vf_attn issuer(S free)");
                 tc_fence_after();
                 const uint64_t kdesc = sw128_desc(smem_u32(sK + ks * K_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem + sb * 128, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k > 0);
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_S + (t & 1) * KT, qdesc + 2 * k, kdesc + 2 * k, p.idesc, k > 0);
                 tc_commit(&k_empty[ks]);
-                tc_commit(&s_full[sb]);
+                tc_commit(&s_full[t & 1]);
                 if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-                if (++sb == 2) { sb = 0; sph ^= 1; }
             };
-            // pass 1: row maxima only
-            for (int j = 0; j < n_kt; ++j) issue_s();
-            // pass 2: S_{j+1} is issued before P_j V_j so the softmax of tile j+1 overlaps the PV MMAs of tile j
-            issue_s();
+            issue_s(0);
             for (int j = 0; j < n_kt; ++j) {
-                if (j + 1 < n_kt) issue_s();
-                mbar_wait(&p_full[pb], pph);
-                mbar_wait(&v_full[vs], vph);
+                if (j + 1 < n_kt) issue_s(j + 1);          // the softmax of tile j+1 overlaps the P V MMAs of tile j
+                mbar_wait(&p_full[j & 1], use_parity(j), "vf_attn issuer(P)");
+                mbar_wait(&v_full[vs], vph, "vf_attn issuer(V)");
                 tc_fence_after();
-                const uint32_t pa = smem_u32(sP + pb * P_BYTES), va = smem_u32(sV + vs * V_BYTES);
+                const uint32_t va = smem_u32(sV + vs * V_BYTES);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {      // K = 128 keys = 2 atoms x 4 steps of 16
-                    const uint64_t adesc = sw128_desc(pa + (k >> 2) * (QT * 128)) + 2 * (k & 3);
-                    const uint64_t bdesc = sw128_desc(va + (k >> 2) * (DH * 128)) + 2 * (k & 3);
-                    umma_bf16(tmem_o, adesc, bdesc, p.idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {      // 64 keys = 4 steps of 16
+                    const uint64_t bdesc = sw128_desc(va) + 2 * k;
+                    if (kPTmem) umma_ts(tmem + TM_O, tmem + TM_P + (j & 1) * (KT / 2) + 8 * k, bdesc, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
+                    else umma_f16(tmem + TM_O, sw128_desc(smem_u32(sP + (j & 1) * PS_BYTES)) + 2 * k, bdesc, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
                 }
-                tc_commit(&p_empty[pb]);
+                tc_commit(&pv_done[j & 1]);
                 tc_commit(&v_empty[vs]);
-                if (++pb == 2) { pb = 0; pph ^= 1; }
                 if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
             }
             tc_commit(o_full);
         }
     } else {
-        // ===================== softmax / epilogue: thread = query row =====================
+        // ===================== softmax / correction / epilogue: thread = query row =====================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int qpos = q0 + row;
         const int vis = min(p.S, (min(qpos, p.S - 1) / p.block + 1) * p.block);     // keys [0, vis) are visible to this row
+        const int vis_lo = __reduce_min_sync(0xffffffffu, vis), vis_hi = __reduce_max_sync(0xffffffffu, vis);
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        int sb = 0, pb = 0;
-        uint32_t sph = 0, pph = 0;
-        float m = -INFINITY;
-        // ---- pass 1: exact row maximum over the visible keys
-        for (int j = 0; j < n_kt; ++j) {
-            mbar_wait(&s_full[sb], sph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < KT; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem + lane_base + sb * 128 + c0, r);
-                const int kbase = j * KT + c0;
-                if (kbase + 32 <= vis) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (kbase + i < vis) m = fmaxf(m, __uint_as_float(r[i]));
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[sb]);
-            if (++sb == 2) { sb = 0; sph ^= 1; }
-        }
-        // ---- pass 2: P = exp(S - m) (bf16, swizzled K-major smem tile), row sums
+        float m2 = -INFINITY;          // reference maximum, in log2 units (S * log2 e)
         float l = 0.f;
         for (int j = 0; j < n_kt; ++j) {
-            mbar_wait(&s_full[sb], sph);
+            const int kbase = j * KT;
+            const int sb = j & 1;
+            uint32_t pk[32];
+            mbar_wait(&s_full[sb], use_parity(j), "vf_attn softmax(S)");
             tc_fence_after();
-            mbar_wait(&p_empty[pb], pph ^ 1);
-            uint8_t* pt = sP + pb * P_BYTES;
+            if (kbase < vis_hi) {
+                uint32_t r[64];
+                tmem_ld64(tmem + lane_base + TM_S + sb * KT, r);
+                // S has been copied to registers: the buffer can take tile j + 2
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[sb]);
+                if (kbase + KT > vis_lo) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (kbase + i >= vis) r[i] = 0xff800000u;                  // -inf
+                }
+                float mt = __uint_as_float(r[0]);
+#pragma unroll
+                for (int i = 1; i < 64; ++i) mt = fmaxf(mt, __uint_as_float(r[i]));
+                mt *= LOG2E;                       // log2 e > 0: the maximum commutes with the scaling
+                if (j == 0) {
+                    m2 = mt;                       // nothing accumulated yet (every row sees key 0, so mt is finite)
+                } else {
+                    const bool grow = mt > m2 + LAZY_LOG2;
+                    if (__any_sync(0xffffffffu, grow)) {
+                        // rescale this warp's 32 accumulator rows: O *= 2^(m_old - m_new); needs P_{j-1} V_{j-1} retired
+                        const float sc = grow ? ex2(m2 - mt) : 1.0f;
+                        mbar_wait(&pv_done[(j - 1) & 1], use_parity(j - 1), "vf_attn correction");
+                        tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < KT; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem + lane_base + sb * 128 + c0, r);
-                const int kbase = j * KT + c0;
-                uint32_t packed[16];
+                        for (int c0 = 0; c0 < DH; c0 += 32) {
+                            uint32_t o[32];
+                            tmem_ld32(tmem + lane_base + TM_O + c0, o);
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float e0 = (kbase + i < vis) ? __expf(__uint_as_float(r[i]) - m) : 0.f;
-                    float e1 = (kbase + i + 1 < vis) ? __expf(__uint_as_float(r[i + 1]) - m) : 0.f;
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                            tmem_st32(tmem + lane_base + TM_O + c0, o);
+                        }
+                        tmem_wait_st();
+                        l *= sc;
+                        if (grow) m2 = mt;
+                    }
+                }
+                const float nm = -m2;
+#pragma unroll
+                for (int i = 0; i < 64; i += 2) {
+                    const float e0 = ex2(fmaf(__uint_as_float(r[i]), LOG2E, nm));          // exp2(-inf) = 0 for masked keys
+                    const float e1 = ex2(fmaf(__uint_as_float(r[i + 1]), LOG2E, nm));
                     l += e0 + e1;
-                    __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+                    pk[i >> 1] = pack_bf16(e0, e1);
                 }
-                // 32 keys = 64 bytes = four 16-byte chunks of this row; 128B swizzle: chunk' = chunk ^ (row & 7)
-                const int atom = c0 >> 6;                    // which 64-key atom
-                const int chunk0 = (c0 & 63) >> 3;           // first 16-byte chunk inside the atom's 128-byte row
-                uint8_t* rowp = pt + atom * (QT * 128) + row * 128;
+            } else {
+                // no row of this warp sees the tile
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[sb]);
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int phys = (chunk0 + cc) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(rowp + phys * 16) =
-                        make_uint4(packed[cc * 4], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                }
+                for (int i = 0; i < 32; ++i) pk[i] = 0u;
             }
-            tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the MMA
+            if (j >= 2) mbar_wait(&pv_done[sb], use_parity(j - 2), "vf_attn softmax(P free)");
+            tc_fence_after();
+            if (kPTmem) {
+                tmem_st32(tmem + lane_base + TM_P + sb * (KT / 2), pk);
+                tmem_wait_st();
+                tc_fence_before();
+            } else {
+                // 64 keys = 128 bytes = eight 16-byte chunks of this row; 128B swizzle: chunk' = chunk ^ (row & 7)
+                uint8_t* rowp = sP + sb * PS_BYTES + row * 128;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    *reinterpret_cast<uint4*>(rowp + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+                tc_fence_before();
+                fence_async_smem();
+            }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&s_empty[sb]);
-                mbar_arrive(&p_full[pb]);
-            }
-            if (++sb == 2) { sb = 0; sph ^= 1; }
-            if (++pb == 2) { pb = 0; pph ^= 1; }
+            if (lane == 0) mbar_arrive(&p_full[sb]);
         }
         // ---- epilogue: O / l -> bf16
-        mbar_wait(o_full, 0);
+        mbar_wait(o_full, 0, "vf_attn epilogue");
         tc_fence_after();
         const float inv = 1.0f / l;
         __nv_bfloat16* orow = p.out + ((long long)b * p.S + qpos) * p.d + h * DH;
 #pragma unroll 1
         for (int c0 = 0; c0 < DH; c0 += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_o + lane_base + c0, r);
+            tmem_ld32(tmem + lane_base + TM_O + c0, r);
             if (qpos < p.S) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
                     uint4 u;
-                    __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-                    __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-                    __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-                    __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-                    u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-                    u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+                    u.x = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+                    u.y = pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+                    u.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+                    u.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
                     *reinterpret_cast<uint4*>(orow + c0 + i) = u;
                 }
             }
@@ -325,36 +313,11 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_block_causal_kernel(cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        tmem_dealloc(tmem, TMEM_COLS);
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-int tmap_bf16(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint64_t strides[3], const uint32_t box[4]) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { vf_set_error("vf_attn: cuTensorMapEncodeTiled unavailable"); return VF_ERR_CUDA; }
-    cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
-    cuuint64_t gs[3] = {strides[0], strides[1], strides[2]};
-    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { vf_set_error("vf_attn: cuTensorMapEncodeTiled failed (%d)", (int)r); return VF_ERR_CUDA; }
-    return VF_OK;
-}
-unsigned idesc_bf16(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24); }
+unsigned idesc_bf16(int M, int N) { return make_idesc_16bit(1, M, N); }
 
 }  // namespace
 
@@ -376,37 +339,45 @@ extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, 
     if (B == 0 || S == 0) return VF_OK;
     AttnParams prm;
     memset(&prm, 0, sizeof(prm));
-    prm.S = S; prm.H = H; prm.d = d; prm.block = block;
+    prm.S = S; prm.H = H; prm.d = d; prm.block = block; prm.BH = B * H;
     prm.qt0 = first_query / QT;
     prm.n_qtiles = (S + QT - 1) / QT - prm.qt0;
     prm.out = reinterpret_cast<__nv_bfloat16*>(out);
-    prm.idesc_s = idesc_bf16(128, 128);
-    prm.idesc_o = idesc_bf16(128, 64);
+    prm.idesc = idesc_bf16(128, 64);
     int rc;
     const uint64_t row = (uint64_t)2 * d * 2;                  // bytes per qk row
     {   // Q / K: [B, S, 2d] viewed as (dh, S, H, B); K is the second half of every row
         const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)S, (uint64_t)H, (uint64_t)B};
         const uint64_t str[3] = {row, (uint64_t)DH * 2, row * S};
-        const uint32_t box[4] = {(uint32_t)DH, (uint32_t)QT, 1, 1};
-        if ((rc = tmap_bf16(&prm.tmQ, qk, dims, str, box)) != VF_OK) return rc;
-        if ((rc = tmap_bf16(&prm.tmK, reinterpret_cast<const __nv_bfloat16*>(qk) + d, dims, str, box)) != VF_OK) return rc;
+        const uint32_t boxq[4] = {(uint32_t)DH, (uint32_t)QT, 1, 1};
+        const uint32_t boxk[4] = {(uint32_t)DH, (uint32_t)KT, 1, 1};
+        if ((rc = make_tmap_16bit(&prm.tmQ, qk, dims, str, boxq)) != VF_OK) return rc;
+        if ((rc = make_tmap_16bit(&prm.tmK, reinterpret_cast<const __nv_bfloat16*>(qk) + d, dims, str, boxk)) != VF_OK) return rc;
     }
     {   // V^T: [B, d, S] viewed as (S, d, B, 1); one box = 64 keys x 64 dh rows
         const uint64_t dims[4] = {(uint64_t)S, (uint64_t)d, (uint64_t)B, 1};
         const uint64_t str[3] = {(uint64_t)S * 2, (uint64_t)S * 2 * d, (uint64_t)S * 2 * d * B};
-        const uint32_t box[4] = {64, (uint32_t)DH, 1, 1};
-        if ((rc = tmap_bf16(&prm.tmV, vt, dims, str, box)) != VF_OK) return rc;
+        const uint32_t box[4] = {(uint32_t)KT, (uint32_t)DH, 1, 1};
+        if ((rc = make_tmap_16bit(&prm.tmV, vt, dims, str, box)) != VF_OK) return rc;
     }
-    constexpr int smem = Q_BYTES + KSTAGES * K_BYTES + VSTAGES * V_BYTES + 2 * P_BYTES + 1024 + 256;
+    // P through TMEM (A operand of the P V MMA read from tensor memory) unless VF_ATTN_PSMEM=1 asks for the shared-memory round trip
+    static int p_smem = -1;
+    if (p_smem < 0) { const char* e = getenv("VF_ATTN_PSMEM"); p_smem = (e && e[0] == '1') ? 1 : 0; }
+    constexpr int smem_base = Q_BYTES + KSTAGES * K_BYTES + VSTAGES * V_BYTES + 1024 + 256;
+    const int smem = smem_base + (p_smem ? 2 * PS_BYTES : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_block_causal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_block_causal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_base);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_base + 2 * PS_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) { vf_set_error("vf_attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
         configured = true;
     }
     const long long ctas = (long long)B * H * prm.n_qtiles;
     VF_CHECK_ARG(ctas < (1ll << 31), "vf_attn_block_causal: grid too large");
-    attn_block_causal_kernel<<<(unsigned)ctas, ATTN_THREADS, smem, vf_s(s)>>>(prm);
+    if (p_smem) attn_block_causal_kernel<false><<<(unsigned)ctas, ATTN_THREADS, smem, vf_s(s)>>>(prm);
+    else attn_block_causal_kernel<true><<<(unsigned)ctas, ATTN_THREADS, smem, vf_s(s)>>>(prm);
     VF_CHECK_LAUNCH("vf_attn_block_causal");
     return VF_OK;
 }
