@@ -26,10 +26,9 @@ constexpr int KT = 64;             // keys per tile (= one 128-byte swizzle row 
 constexpr int DH = 64;             // head dim (one 128-byte swizzle row)
 constexpr int KSTAGES = 4;         // K tile ring
 constexpr int VSTAGES = 3;         // V^T tile ring
-constexpr int Q_BYTES = QT * 128;              // 16 KB
+constexpr int Q_BYTES = QT * 128;              // 16 KB (double-buffered: the next work item's Q streams in behind the current one)
 constexpr int K_BYTES = KT * 128;              // 8 KB
 constexpr int V_BYTES = DH * 128;              // [64 dh rows x 64 keys] = 8 KB
-constexpr int PS_BYTES = QT * 128;             // shared-memory P tile (kPTmem = false): [128 q rows x 64 keys] = 16 KB
 constexpr int ATTN_THREADS = 192;
 constexpr int TMEM_COLS = 256;                 // S0 [0,64) S1 [64,128) P0 [128,160) P1 [160,192) O [192,256)
 constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
@@ -90,17 +89,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // tile t of a CTA uses ring buffer t & 1; its k-th use completes the barrier's k-th phase (k = t >> 1)
 __device__ __forceinline__ uint32_t use_parity(int t) { return (uint32_t)(t >> 1) & 1u; }
 
-template <bool kPTmem>
 __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + Q_BYTES;
+    uint8_t* sQ = smem;                                    // [2][Q_BYTES]
+    uint8_t* sK = sQ + 2 * Q_BYTES;
     uint8_t* sV = sK + KSTAGES * K_BYTES;
-    uint8_t* sP = sV + VSTAGES * V_BYTES;                  // 2 x PS_BYTES when P goes through shared memory, else empty
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (kPTmem ? 0 : 2 * PS_BYTES));
-    uint64_t* q_full = bars;                 // 1
-    uint64_t* k_full = bars + 1;             // KSTAGES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + VSTAGES * V_BYTES);
+    uint64_t* q_full = bars;                 // 2
+    uint64_t* q_empty = q_full + 2;          // 2: the item's last Q K^T retired (MMA commit)
+    uint64_t* k_full = q_empty + 2;          // KSTAGES
     uint64_t* k_empty = k_full + KSTAGES;    // KSTAGES
     uint64_t* v_full = k_empty + KSTAGES;    // VSTAGES
     uint64_t* v_empty = v_full + VSTAGES;    // VSTAGES
@@ -108,23 +106,15 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
     uint64_t* s_empty = s_full + 2;          // 2: S_t read by all four softmax warps
     uint64_t* p_full = s_empty + 2;          // 2: P_t written by all four softmax warps
     uint64_t* pv_done = p_full + 2;          // 2: P_t V_t retired (MMA commit): P buffer free, O stable up to tile t
-    uint64_t* o_full = pv_done + 2;          // 1
+    uint64_t* o_full = pv_done + 2;          // 1: the item's last P V retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // heaviest query tiles (most visible keys) first
-    const int qt = p.qt0 + p.n_qtiles - 1 - (int)(blockIdx.x / p.BH);
-    const int bh = blockIdx.x % p.BH;
-    const int h = bh % p.H, b = bh / p.H;
-    const int q0 = qt * QT;
-    // keys visible to the tile's last valid query: views <= view(last query)
-    const int last_q = min(q0 + QT, p.S) - 1;
-    const int kv_lim = min(p.S, (last_q / p.block + 1) * p.block);
-    const int n_kt = (kv_lim + KT - 1) / KT;
+    const int n_items = p.BH * p.n_qtiles;
 
     if (threadIdx.x == 0) { prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV); }
     if (threadIdx.x == 32) {
-        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
         for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
@@ -142,170 +132,211 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // Work items = (query tile, batch*head), heaviest query tiles (most visible keys) first; a CTA walks items blockIdx.x, + gridDim.x, ...
+    // Every role derives the same sequence, so nothing has to be broadcast; tile counters run on across items (ring parities stay valid).
+    auto item_coords = [&](int item, int& b, int& h, int& q0, int& n_kt) {
+        const int qt = p.qt0 + p.n_qtiles - 1 - item / p.BH;
+        const int bh = item % p.BH;
+        h = bh % p.H; b = bh / p.H;
+        q0 = qt * QT;
+        const int last_q = min(q0 + QT, p.S) - 1;                                   // keys visible to the tile's last valid query
+        const int kv_lim = min(p.S, (last_q / p.block + 1) * p.block);
+        n_kt = (kv_lim + KT - 1) / KT;
+    };
+
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            mbar_expect_tx(q_full, Q_BYTES);
-            tma_load_4d(sQ, &p.tmQ, q_full, 0, q0, h, b);
-            int ks = 0, vs = 0;
+            int ks = 0, vs = 0, it = 0;
             uint32_t kph = 0, vph = 0;
-            for (int j = 0; j < n_kt; ++j) {
-                mbar_wait(&k_empty[ks], kph ^ 1, "vf_attn producer(K)");
-                mbar_expect_tx(&k_full[ks], K_BYTES);
-                tma_load_4d(sK + ks * K_BYTES, &p.tmK, &k_full[ks], 0, j * KT, h, b);
-                if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-                mbar_wait(&v_empty[vs], vph ^ 1, "vf_attn producer(V)");
-                mbar_expect_tx(&v_full[vs], V_BYTES);
-                tma_load_4d(sV + vs * V_BYTES, &p.tmV, &v_full[vs], j * KT, h * DH, b, 0);
-                if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                int b, h, q0, n_kt;
+                item_coords(item, b, h, q0, n_kt);
+                if (it >= 2) mbar_wait(&q_empty[it & 1], use_parity(it - 2), "vf_attn producer(Q)");
+                mbar_expect_tx(&q_full[it & 1], Q_BYTES);
+                tma_load_4d(sQ + (it & 1) * Q_BYTES, &p.tmQ, &q_full[it & 1], 0, q0, h, b);
+                for (int j = 0; j < n_kt; ++j) {
+                    mbar_wait(&k_empty[ks], kph ^ 1, "vf_attn producer(K)");
+                    mbar_expect_tx(&k_full[ks], K_BYTES);
+                    tma_load_4d(sK + ks * K_BYTES, &p.tmK, &k_full[ks], 0, j * KT, h, b);
+                    if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+                    mbar_wait(&v_empty[vs], vph ^ 1, "vf_attn producer(V)");
+                    mbar_expect_tx(&v_full[vs], V_BYTES);
+                    tma_load_4d(sV + vs * V_BYTES, &p.tmV, &v_full[vs], j * KT, h * DH, b, 0);
+                    if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            mbar_wait(q_full, 0, "vf_attn issuer(Q)");
-            tc_fence_after();
-            const uint64_t qdesc = sw128_desc(smem_u32(sQ));
             int ks = 0, vs = 0;
             uint32_t kph = 0, vph = 0;
-            auto issue_s = [&](int t) {       // S[t & 1] = Q K_t^T
+            // S tiles are issued one ahead of the P V they belong to — across item boundaries too, so the first Q K^T of the next item
+            // runs while the softmax warps are still in the epilogue of this one.  `sq` walks the (item, tile) sequence of S issues.
+            int s_item = blockIdx.x, s_it = 0, s_j = 0, s_nkt = 0, s_t = 0;
+            uint64_t s_qdesc = 0;
+            bool s_live = s_item < n_items;
+            auto s_open = [&]() {             // first tile of an item: its Q must have landed
+                int b, h, q0;
+                item_coords(s_item, b, h, q0, s_nkt);
+                mbar_wait(&q_full[s_it & 1], use_parity(s_it), "vf_attn issuer(Q)");
+                s_qdesc = sw128_desc(smem_u32(sQ + (s_it & 1) * Q_BYTES));
+            };
+            auto issue_s = [&]() {            // S[t & 1] = Q K_t^T for the next (item, tile)
+                if (s_j == 0) s_open();
                 mbar_wait(&k_full[ks], kph, "vf_attn issuer(K)");
-                if (t >= 2) mbar_wait(&s_empty[t & 1], use_parity(t - 2), "vf_attn issuer(S free)");
+                if (s_t >= 2) mbar_wait(&s_empty[s_t & 1], use_parity(s_t - 2), "vf_attn issuer(S free)");
                 tc_fence_after();
                 const uint64_t kdesc = sw128_desc(smem_u32(sK + ks * K_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_S + (t & 1) * KT, qdesc + 2 * k, kdesc + 2 * k, p.idesc, k > 0);
+                for (int k = 0; k < 4; ++k) umma_f16(tmem + TM_S + (s_t & 1) * KT, s_qdesc + 2 * k, kdesc + 2 * k, p.idesc, k > 0);
                 tc_commit(&k_empty[ks]);
-                tc_commit(&s_full[t & 1]);
+                tc_commit(&s_full[s_t & 1]);
                 if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-            };
-            issue_s(0);
-            for (int j = 0; j < n_kt; ++j) {
-                if (j + 1 < n_kt) issue_s(j + 1);          // the softmax of tile j+1 overlaps the P V MMAs of tile j
-                mbar_wait(&p_full[j & 1], use_parity(j), "vf_attn issuer(P)");
-                mbar_wait(&v_full[vs], vph, "vf_attn issuer(V)");
-                tc_fence_after();
-                const uint32_t va = smem_u32(sV + vs * V_BYTES);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {      // 64 keys = 4 steps of 16
-                    const uint64_t bdesc = sw128_desc(va) + 2 * k;
-                    if (kPTmem) umma_ts(tmem + TM_O, tmem + TM_P + (j & 1) * (KT / 2) + 8 * k, bdesc, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
-                    else umma_f16(tmem + TM_O, sw128_desc(smem_u32(sP + (j & 1) * PS_BYTES)) + 2 * k, bdesc, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
+                ++s_t;
+                if (++s_j == s_nkt) {         // item finished on the S side: its Q buffer is free once these MMAs retire
+                    tc_commit(&q_empty[s_it & 1]);
+                    s_j = 0; ++s_it; s_item += gridDim.x;
+                    s_live = s_item < n_items;
                 }
-                tc_commit(&pv_done[j & 1]);
-                tc_commit(&v_empty[vs]);
-                if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+            };
+            if (s_live) issue_s();
+            int t = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, h, q0, n_kt;
+                item_coords(item, b, h, q0, n_kt);
+                for (int j = 0; j < n_kt; ++j, ++t) {
+                    if (s_live) issue_s();                     // tile t + 1: its softmax overlaps the P V MMAs of tile t
+                    mbar_wait(&p_full[t & 1], use_parity(t), "vf_attn issuer(P)");
+                    mbar_wait(&v_full[vs], vph, "vf_attn issuer(V)");
+                    tc_fence_after();
+                    const uint32_t va = smem_u32(sV + vs * V_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {      // 64 keys = 4 steps of 16
+                        const uint64_t bdesc = sw128_desc(va) + 2 * k;
+                        umma_ts(tmem + TM_O, tmem + TM_P + (t & 1) * (KT / 2) + 8 * k, bdesc, p.idesc, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&pv_done[t & 1]);
+                    tc_commit(&v_empty[vs]);
+                    if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+                }
+                tc_commit(o_full);
             }
-            tc_commit(o_full);
         }
     } else {
         // ===================== softmax / correction / epilogue: thread = query row =====================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int qpos = q0 + row;
-        const int vis = min(p.S, (min(qpos, p.S - 1) / p.block + 1) * p.block);     // keys [0, vis) are visible to this row
-        const int vis_lo = __reduce_min_sync(0xffffffffu, vis), vis_hi = __reduce_max_sync(0xffffffffu, vis);
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        float m2 = -INFINITY;          // reference maximum, in log2 units (S * log2 e)
-        float l = 0.f;
-        for (int j = 0; j < n_kt; ++j) {
-            const int kbase = j * KT;
-            const int sb = j & 1;
-            uint32_t pk[32];
-            mbar_wait(&s_full[sb], use_parity(j), "vf_attn softmax(S)");
-            tc_fence_after();
-            if (kbase < vis_hi) {
-                uint32_t r[64];
-                tmem_ld64(tmem + lane_base + TM_S + sb * KT, r);
-                // S has been copied to registers: the buffer can take tile j + 2
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[sb]);
-                if (kbase + KT > vis_lo) {
+        int t = 0, it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            int b, h, q0, n_kt;
+            item_coords(item, b, h, q0, n_kt);
+            const int qpos = q0 + row;
+            const int vis = min(p.S, (min(qpos, p.S - 1) / p.block + 1) * p.block);     // keys [0, vis) are visible to this row
+            const int vis_lo = __reduce_min_sync(0xffffffffu, vis), vis_hi = __reduce_max_sync(0xffffffffu, vis);
+            float m2 = -INFINITY;          // reference maximum, in log2 units (S * log2 e)
+            float l = 0.f;
+            for (int j = 0; j < n_kt; ++j, ++t) {
+                const int kbase = j * KT;
+                const int sb = t & 1;
+                uint32_t pk[32];
+                mbar_wait(&s_full[sb], use_parity(t), "vf_attn softmax(S)");
+                tc_fence_after();
+                if (kbase < vis_hi) {
+                    uint32_t r[64];
+                    tmem_ld64(tmem + lane_base + TM_S + sb * KT, r);
+                    // S has been copied to registers: the buffer can take tile t + 2
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[sb]);
+                    if (kbase + KT > vis_lo) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i)
-                        if (kbase + i >= vis) r[i] = 0xff800000u;                  // -inf
-                }
-                float mt = __uint_as_float(r[0]);
-#pragma unroll
-                for (int i = 1; i < 64; ++i) mt = fmaxf(mt, __uint_as_float(r[i]));
-                mt *= LOG2E;                       // log2 e > 0: the maximum commutes with the scaling
-                if (j == 0) {
-                    m2 = mt;                       // nothing accumulated yet (every row sees key 0, so mt is finite)
-                } else {
-                    const bool grow = mt > m2 + LAZY_LOG2;
-                    if (__any_sync(0xffffffffu, grow)) {
-                        // rescale this warp's 32 accumulator rows: O *= 2^(m_old - m_new); needs P_{j-1} V_{j-1} retired
-                        const float sc = grow ? ex2(m2 - mt) : 1.0f;
-                        mbar_wait(&pv_done[(j - 1) & 1], use_parity(j - 1), "vf_attn correction");
-                        tc_fence_after();
-#pragma unroll 1
-                        for (int c0 = 0; c0 < DH; c0 += 32) {
-                            uint32_t o[32];
-                            tmem_ld32(tmem + lane_base + TM_O + c0, o);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
-                            tmem_st32(tmem + lane_base + TM_O + c0, o);
-                        }
-                        tmem_wait_st();
-                        l *= sc;
-                        if (grow) m2 = mt;
+                        for (int i = 0; i < 64; ++i)
+                            if (kbase + i >= vis) r[i] = 0xff800000u;                  // -inf
                     }
-                }
-                const float nm = -m2;
+                    // four independent chains (a single 63-deep dependent FMNMX chain costs 4 cycles per link)
+                    float mx[4];
 #pragma unroll
-                for (int i = 0; i < 64; i += 2) {
-                    const float e0 = ex2(fmaf(__uint_as_float(r[i]), LOG2E, nm));          // exp2(-inf) = 0 for masked keys
-                    const float e1 = ex2(fmaf(__uint_as_float(r[i + 1]), LOG2E, nm));
-                    l += e0 + e1;
-                    pk[i >> 1] = pack_bf16(e0, e1);
-                }
-            } else {
-                // no row of this warp sees the tile
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[sb]);
+                    for (int c = 0; c < 4; ++c) mx[c] = fmaxf(__uint_as_float(r[c]), __uint_as_float(r[4 + c]));
 #pragma unroll
-                for (int i = 0; i < 32; ++i) pk[i] = 0u;
-            }
-            if (j >= 2) mbar_wait(&pv_done[sb], use_parity(j - 2), "vf_attn softmax(P free)");
-            tc_fence_after();
-            if (kPTmem) {
+                    for (int i = 8; i < 64; i += 8) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(r[i + c]), __uint_as_float(r[i + 4 + c])));
+                    }
+                    float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * LOG2E;      // log2 e > 0: the maximum commutes with the scaling
+                    if (j == 0) {
+                        m2 = mt;                       // nothing accumulated yet (every row sees key 0, so mt is finite)
+                    } else {
+                        const bool grow = mt > m2 + LAZY_LOG2;
+                        if (__any_sync(0xffffffffu, grow)) {
+                            // rescale this warp's 32 accumulator rows: O *= 2^(m_old - m_new); needs P_{t-1} V_{t-1} retired
+                            const float sc = grow ? ex2(m2 - mt) : 1.0f;
+                            mbar_wait(&pv_done[(t - 1) & 1], use_parity(t - 1), "vf_attn correction");
+                            tc_fence_after();
+#pragma unroll 1
+                            for (int c0 = 0; c0 < DH; c0 += 32) {
+                                uint32_t o[32];
+                                tmem_ld32(tmem + lane_base + TM_O + c0, o);
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                                tmem_st32(tmem + lane_base + TM_O + c0, o);
+                            }
+                            tmem_wait_st();
+                            l *= sc;
+                            if (grow) m2 = mt;
+                        }
+                    }
+                    const float nm = -m2;
+                    float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int i = 0; i < 64; i += 2) {
+                        const float e0 = ex2(fmaf(__uint_as_float(r[i]), LOG2E, nm));          // exp2(-inf) = 0 for masked keys
+                        const float e1 = ex2(fmaf(__uint_as_float(r[i + 1]), LOG2E, nm));
+                        ls[(i >> 1) & 3] += e0 + e1;
+                        pk[i >> 1] = pack_bf16(e0, e1);
+                    }
+                    l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+                } else {
+                    // no row of this warp sees the tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[sb]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) pk[i] = 0u;
+                }
+                if (t >= 2) mbar_wait(&pv_done[sb], use_parity(t - 2), "vf_attn softmax(P free)");
+                tc_fence_after();
                 tmem_st32(tmem + lane_base + TM_P + sb * (KT / 2), pk);
                 tmem_wait_st();
                 tc_fence_before();
-            } else {
-                // 64 keys = 128 bytes = eight 16-byte chunks of this row; 128B swizzle: chunk' = chunk ^ (row & 7)
-                uint8_t* rowp = sP + sb * PS_BYTES + row * 128;
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                    *reinterpret_cast<uint4*>(rowp + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-                tc_fence_before();
-                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[sb]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[sb]);
-        }
-        // ---- epilogue: O / l -> bf16
-        mbar_wait(o_full, 0, "vf_attn epilogue");
-        tc_fence_after();
-        const float inv = 1.0f / l;
-        __nv_bfloat16* orow = p.out + ((long long)b * p.S + qpos) * p.d + h * DH;
+            // ---- epilogue: O / l -> bf16.  The next item's first P V cannot start before these warps hand over its P tile, i.e. after
+            // the accumulator has been read here, so O needs no second buffer.
+            mbar_wait(o_full, (uint32_t)it & 1u, "vf_attn epilogue");
+            tc_fence_after();
+            const float inv = 1.0f / l;
+            __nv_bfloat16* orow = p.out + ((long long)b * p.S + qpos) * p.d + h * DH;
 #pragma unroll 1
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem + lane_base + TM_O + c0, r);
-            if (qpos < p.S) {
+            for (int c0 = 0; c0 < DH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem + lane_base + TM_O + c0, r);
+                if (qpos < p.S) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 u;
-                    u.x = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-                    u.y = pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-                    u.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-                    u.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c0 + i) = u;
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 u;
+                        u.x = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+                        u.y = pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+                        u.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+                        u.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c0 + i) = u;
+                    }
                 }
             }
+            tc_fence_before();
         }
     }
 
@@ -360,24 +391,25 @@ extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, 
         const uint32_t box[4] = {(uint32_t)KT, (uint32_t)DH, 1, 1};
         if ((rc = make_tmap_16bit(&prm.tmV, vt, dims, str, box)) != VF_OK) return rc;
     }
-    // P through TMEM (A operand of the P V MMA read from tensor memory) unless VF_ATTN_PSMEM=1 asks for the shared-memory round trip
-    static int p_smem = -1;
-    if (p_smem < 0) { const char* e = getenv("VF_ATTN_PSMEM"); p_smem = (e && e[0] == '1') ? 1 : 0; }
-    constexpr int smem_base = Q_BYTES + KSTAGES * K_BYTES + VSTAGES * V_BYTES + 1024 + 256;
-    const int smem = smem_base + (p_smem ? 2 * PS_BYTES : 0);
+    constexpr int smem = 2 * Q_BYTES + KSTAGES * K_BYTES + VSTAGES * V_BYTES + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_block_causal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_base);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_base + 2 * PS_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaError_t e = cudaFuncSetAttribute(attn_block_causal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) { vf_set_error("vf_attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
         configured = true;
     }
-    const long long ctas = (long long)B * H * prm.n_qtiles;
-    VF_CHECK_ARG(ctas < (1ll << 31), "vf_attn_block_causal: grid too large");
-    if (p_smem) attn_block_causal_kernel<false><<<(unsigned)ctas, ATTN_THREADS, smem, vf_s(s)>>>(prm);
-    else attn_block_causal_kernel<true><<<(unsigned)ctas, ATTN_THREADS, smem, vf_s(s)>>>(prm);
+    const long long items = (long long)B * H * prm.n_qtiles;
+    VF_CHECK_ARG(items < (1ll << 31), "vf_attn_block_causal: too many work items");
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    // persistent: two CTAs per SM (256 TMEM columns each), every CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ...
+    const unsigned grid = (unsigned)(items < 2ll * num_sms ? items : 2ll * num_sms);
+    attn_block_causal_kernel<<<grid, ATTN_THREADS, smem, vf_s(s)>>>(prm);
     VF_CHECK_LAUNCH("vf_attn_block_causal");
     return VF_OK;
 }

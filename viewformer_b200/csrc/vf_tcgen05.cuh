@@ -1,6 +1,6 @@
 // Thin PTX wrappers for the sm_100a tensor-core pipeline: mbarriers, TMA tile loads, tcgen05.mma / commit / ld, TMEM allocation,
-// shared-memory matrix descriptors.  Header-only, used by the kernels written in round 2 (vf_vq_fused.cu, vf_attn_q.cu);
-// vf_tc_gemm.cu / vf_attn_fused.cu carry their own (identical) copies from round 1.
+// shared-memory matrix descriptors.  Header-only, used by the kernels written in round 2 (vf_vq_fused.cu, vf_attn_fused.cu);
+// vf_tc_gemm.cu carries its own (identical) copies from round 1.
 #pragma once
 #include "vf_common.cuh"
 #include <cuda.h>
@@ -39,6 +39,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU box
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const char* who = "vftc") {
+#pragma unroll 1
     for (uint32_t i = 0; i < (1u << 24); ++i)
         if (mbar_try_wait(bar, parity)) return;
     printf("%s: mbarrier timeout (block %d thread %d)\n", who, blockIdx.x, threadIdx.x);

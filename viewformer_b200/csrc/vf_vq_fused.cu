@@ -45,6 +45,7 @@ struct VqParams {
     int D, K, kblocks, nsub;
     long long n_pair_tiles;     // ceil(M / 256)
     float tol_factor;
+    int key_mul;                // 256, passed as data so the key is ONE IMAD (fma pipe) instead of a shift + add on the alu pipe
     long long* idx;             // [M]
     int4* worklist;             // {row, c1, c2 (-1: all codes), 0}
     int* counter;               // [0] queued rows, [1] of which FULL
@@ -95,11 +96,6 @@ __device__ __forceinline__ void umma_2sm_f16(uint32_t tmem_d, uint64_t adesc, ui
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-
-// index bytes 0..63 as constant-bank operands: key = PRMT(score bits, index) replaces the low mantissa BYTE in one ALU instruction
-__constant__ uint32_t VQ_IDX[64] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21,
-                                    22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43,
-                                    44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63};
 
 // explicit shared-state-space accesses: pointers derived from the aligned dynamic-smem base are "generic" to the compiler, and a
 // generic LD to shared memory is tracked on the long scoreboard like a global load
@@ -155,7 +151,31 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
         }
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < p.K; i += THREADS) esq_s[i] = __ldg(p.esq + i);
+    // Fixed-point scores: with C = 1.5 * 2^k and |score| < 2^(k-1), the fp32 sum  t = acc + (|e|^2 + C)  stays inside the binade [2^k, 2^(k+1)),
+    // so its BIT PATTERN is an order-preserving integer with step G = 2^(k-23).  key = t_bits * 256 + code index is then one IMAD, and
+    // the top-2 tracking runs on integer min / max.  k is chosen from the codebook (2^(k-1) >= 17.2 max|e|^2): rows with |z| up to
+    // 8 max|e| fit; rows beyond that go to the exact pass like rows outside the fp16 range.
+    __shared__ int esqmax_bits;
+    if (threadIdx.x == 0) esqmax_bits = 0;
+    __syncthreads();
+    {
+        float mx = 0.f;
+        for (int i = threadIdx.x; i < p.K; i += THREADS) mx = fmaxf(mx, __ldg(p.esq + i));
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0) atomicMax(&esqmax_bits, __float_as_int(mx));      // non-negative floats order like their bit patterns
+    }
+    __syncthreads();
+    const float esqmax = fmaxf(__int_as_float(esqmax_bits), 1e-30f);
+    const bool codebook_ok = esqmax < 1.0e9f;                    // every -2 e_i representable in fp16 (|e_i| <= |e| < 31623); NaN fails too
+    const int kexp = ((__float_as_int(17.2f * esqmax) >> 23) & 255) - 127 + 2;          // 2^(kexp - 1) > 17.2 max|e|^2
+    const int c_bits = ((kexp + 127) << 23) | 0x400000;          // C = 1.5 * 2^kexp
+    const float c_off = __int_as_float(c_bits);
+    const int key0 = (int)((uint32_t)c_bits << 8);               // key of score 0 and index 0: +-2^30 (exponent parity), keys never wrap
+    const float g_step = __int_as_float((kexp - 23 + 127) << 23);              // G = 2^(kexp - 23)
+    const float half_range = __int_as_float((kexp - 1 + 127) << 23);           // 2^(kexp - 1)
+    const float zcap = (half_range - esqmax) / (2.02f * sqrtf(esqmax));        // 2 |z| |e| (1 + 2^-10 ...) + |e|^2 < 2^(kexp - 1)
+    const float zz_cap = codebook_ok ? fminf(zcap * zcap, 3.6e9f) : -1.0f;     // |z_i| <= |z| < 60000: inside the fp16 range
+    for (int i = threadIdx.x; i < p.K; i += THREADS) esq_s[i] = __ldg(p.esq + i) + c_off;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -243,23 +263,23 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
                 for (int u = 0; u < 4; ++u) {
                     const int r = cw + (rb + u) * NCONV;
                     const float e[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-                    float ss = 0.f, mx = 0.f;
+                    float ss = 0.f;
                     uint32_t w[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         ss = fmaf(e[2 * q], e[2 * q], ss);
                         ss = fmaf(e[2 * q + 1], e[2 * q + 1], ss);
-                        mx = fmaxf(mx, fmaxf(fabsf(e[2 * q]), fabsf(e[2 * q + 1])));
                         const __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
                         w[q] = *reinterpret_cast<const uint32_t*>(&h);
                     }
                     if (lane_ok)
                         *reinterpret_cast<uint4*>(At + kb * KB_BYTES + r * 128 + ((ch ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     ss = warp_sum(ss);
-                    mx = warp_max(mx);
                     if (lane == 0) {
                         zz_s[(tl & (ZRING - 1)) * TM + r] = ss;
-                        bad_s[(tl & (ZRING - 1)) * TM + r] = !(mx < 60000.f && ss == ss);      // beyond fp16 range (or NaN): the exact pass decides this row
+                        // |z|^2 below the cap keeps every element inside the fp16 range and every score inside the fixed-point range;
+                        // NaN / inf fail the comparison too.  Rows that fail are decided by the exact pass.
+                        bad_s[(tl & (ZRING - 1)) * TM + r] = !(ss < zz_cap);
                     }
                 }
             }
@@ -274,16 +294,17 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
         const int row = quarter * 32 + lane;
         const uint32_t lead_empty = mapa_cta(t_empty, 0);
         const uint32_t esq_a = smem_u32(esq_s), res_a = smem_u32(res_s);
-        const float INF = __int_as_float(0x7f800000);
+        const int EMPTY = 0x7fffffff;
+        const int key_mul = p.key_mul;
         int it = 0, tl = 0;
         for (long long t = pair0; t < p.n_pair_tiles; t += pair_stride, ++tl) {
-            float t1 = INF, t2 = INF, t3 = INF;                   // this thread's three best keys over its 4 sets (8-bit index: n | h | j)
+            int t1 = EMPTY, t2 = EMPTY, t3 = EMPTY;               // this thread's three best keys over its 4 sets (8-bit index: n | h | j)
             for (int n = 0; n < p.nsub; ++n) {
                 const int acc = it & 1;
                 mbar_wait(&t_full[acc], (it >> 1) & 1, "vq_fused(t_full)");
                 ++it;
                 tc_fence_after();
-                float m1 = INF, m2 = INF;
+                int m1 = EMPTY, m2 = EMPTY;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r[32];
@@ -301,27 +322,27 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int j = j4 * 4 + q;
-                            const float s = __uint_as_float(r[j]) + ev[q];
-                            const float k = __uint_as_float(__byte_perm(__float_as_uint(s), VQ_IDX[h * 32 + j], 0x3214));   // low byte <- index
-                            m2 = fminf(m2, fmaxf(m1, k));
-                            m1 = fminf(m1, k);
+                            const int tb = __float_as_int(__uint_as_float(r[j]) + ev[q]);     // FADD (fma pipe): score + C, one binade
+                            const int k = tb * key_mul + (h * 32 + j);                        // IMAD (fma pipe): low byte = index
+                            m2 = min(m2, max(m1, k));
+                            m1 = min(m1, k);
                         }
                     }
                 }
                 // fold the set's two best into the thread's three best (set number into bits 6..7 of the index)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const float mk = q ? m2 : m1;
-                    const float k = __uint_as_float(__float_as_uint(mk) | (uint32_t)(n << 6));       // bits 6..7 of the index byte are zero so far
-                    const float a = fmaxf(t1, k);
-                    t1 = fminf(t1, k);
-                    const float b = fmaxf(t2, a);
-                    t2 = fminf(t2, a);
-                    t3 = fminf(t3, b);
+                    const int mk = q ? m2 : m1;
+                    const int k = mk == EMPTY ? EMPTY : (mk | (n << 6));                      // bits 6..7 of the index byte are zero so far
+                    const int a = max(t1, k);
+                    t1 = min(t1, k);
+                    const int b2 = max(t2, a);
+                    t2 = min(t2, a);
+                    t3 = min(t3, b2);
                 }
             }
             const uint32_t rbuf = res_a + (uint32_t)((tl & 1) * RES_BYTES);
-            sts_u4(rbuf + (uint32_t)((grp * TM + row) * 16), make_uint4(__float_as_uint(t1), __float_as_uint(t2), __float_as_uint(t3), 0u));
+            sts_u4(rbuf + (uint32_t)((grp * TM + row) * 16), make_uint4((uint32_t)t1, (uint32_t)t2, (uint32_t)t3, 0u));
             asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory");                        // the tile's keys are in res_s[tl & 1]
             if (grp == 0) {
                 const long long gr = t * 256 + (long long)rank * TM + row;
@@ -332,42 +353,55 @@ __global__ void __launch_bounds__(THREADS, 1) vq_lookup_fused_kernel(const __gri
                         const uint4 v = lds_u4(rbuf + (uint32_t)((g * TM + row) * 16));
                         ks[3 * g] = v.x; ks[3 * g + 1] = v.y; ks[3 * g + 2] = v.z;
                     }
-                    // key -> (value, code, set): value = bits with the 8 index bits cleared, code = n*256 + g*64 + idx6, set = n*4 + g
-                    float bv = INF;
+                    // key -> (value, code, set): value = ((key - key0) >> 8) * G, code = n*256 + g*64 + idx6, set = n*4 + g
+                    const float vscale = g_step * 0.00390625f;            // G / 256
+                    float bv = __int_as_float(0x7f800000);
                     int bc = 0x7fffffff, bset = -1;
 #pragma unroll
                     for (int i = 0; i < 12; ++i) {
                         const uint32_t k = ks[i];
-                        const float v = __uint_as_float(k & 0xFFFFFF00u);
+                        const float v = (float)((int)(k & 0xFFFFFF00u) - key0) * vscale;
                         const int n = (int)((k >> 6) & 3u), g = i / 3;
                         const int c = n * TN + g * 64 + (int)(k & 63u);
-                        if ((k & 0x7f800000u) != 0x7f800000u && (v < bv || (v == bv && c < bc))) { bv = v; bc = c; bset = n * 4 + g; }
+                        if (k != 0x7fffffffu && (v < bv || (v == bv && c < bc))) { bv = v; bc = c; bset = n * 4 + g; }
                     }
                     const uint32_t zslot = (uint32_t)(((tl & (ZRING - 1)) * TM + row) * 4);
                     bool bad = *reinterpret_cast<volatile int*>(bad_s + (tl & (ZRING - 1)) * TM + row) != 0;
-                    if (bset < 0) { bc = 0; bad = true; }                                   // every score was NaN / inf
+                    if (bset < 0) { bc = 0; bad = true; }
                     const float znorm = sqrtf(lds_f(smem_u32(zz_s) + zslot));
-                    const float eb = sqrtf(lds_f(esq_a + (uint32_t)(bc * 4)));
+                    const float eb = sqrtf(__ldg(p.esq + bc));
                     int within = 0, oc = -1, oset = -1;
+                    uint32_t inside = 0;                                   // bit i: key i lies inside the tolerance (the best code itself included)
 #pragma unroll
                     for (int i = 0; i < 12; ++i) {
                         const uint32_t k = ks[i];
-                        if ((k & 0x7f800000u) == 0x7f800000u) continue;                      // empty slot (+inf) or NaN
-                        const float v = __uint_as_float(k & 0xFFFFFF00u);
+                        if (k == 0x7fffffffu) continue;                                      // empty slot
+                        const float v = (float)((int)(k & 0xFFFFFF00u) - key0) * vscale;
                         const int n = (int)((k >> 6) & 3u), g = i / 3;
                         const int c = n * TN + g * 64 + (int)(k & 63u);
-                        if (c == bc) continue;
-                        const float slack = 6.1035156e-5f * (fabsf(v) + fabsf(bv));         // index bits + truncating accumulation
-                        const float tol = p.tol_factor * 0.001953125f * znorm * (eb + sqrtf(lds_f(esq_a + (uint32_t)(c * 4)))) + slack;
-                        if (v - bv <= tol) { ++within; oc = c; oset = n * 4 + g; }
+                        if (c == bc) { inside |= 1u << i; continue; }
+                        // truncating TMEM accumulation (2^-16 relative, generous) + the fixed-point step of both scores
+                        const float slack = 1.52587891e-5f * (fabsf(v) + fabsf(bv)) + 4.0f * g_step;
+                        const float tol = p.tol_factor * 0.001953125f * znorm * (eb + sqrtf(__ldg(p.esq + c))) + slack;
+                        if (v - bv <= tol) { ++within; inside |= 1u << i; oc = c; oset = n * 4 + g; }
                     }
                     p.idx[gr] = (long long)bc;
                     if (within > 0 || bad) {
-                        // a code within the tolerance that is NOT among the 12 keys implies two reported keys within the tolerance in
-                        // one thread or a runner-up in the best code's own set (see the proof sketch in DESIGN.md): those rows take all codes
-                        const bool full = bad || within > 1 || oset == bset;
-                        // PAIR entries fill the worklist from the front, FULL entries from the back
-                        if (full) p.worklist[p.M - 1 - atomicAdd(p.counter + 1, 1)] = make_int4((int)gr, bc, -1, 0);
+                        // A code inside the tolerance that is NOT among the 12 keys sits either in a set whose two reported best are both
+                        // inside the tolerance (the sets of all inside keys are masked) or behind a thread whose three reported keys are all
+                        // inside (then any of that thread's sets may hide it) — proof sketch in DESIGN.md.  One other candidate in a different
+                        // set than the best: PAIR (two known codes).  Everything else: SETS (all codes of the masked 64-code sets).
+                        uint32_t mask = 0;                                 // 64-code sets (sub-tile * 4 + column group) the exact pass looks at
+#pragma unroll
+                        for (int i = 0; i < 12; ++i)
+                            if ((inside >> i) & 1u) mask |= 1u << ((((ks[i] >> 6) & 3u) << 2) | (uint32_t)(i / 3));
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (((inside >> (3 * g)) & 7u) == 7u) mask |= 0x1111u << g;
+                        const bool pair = !bad && within == 1 && oset != bset;
+                        if (bad) mask = 0xFFFFu;
+                        // PAIR entries fill the worklist from the front, SETS entries from the back
+                        if (!pair) p.worklist[p.M - 1 - atomicAdd(p.counter + 1, 1)] = make_int4((int)gr, bc, -1, (int)mask);
                         else p.worklist[atomicAdd(p.counter, 1)] = make_int4((int)gr, bc, oc, 0);
                     }
                 }
@@ -391,8 +425,8 @@ __device__ __forceinline__ float warp_min_f(float v) {
 }
 
 // Exact pass over the queued rows: fp64 direct sum of squared differences, ties to the smaller index.
-// PAIR entries (front of the worklist): one warp per entry, the two known candidates.  FULL entries (back of the worklist): one CTA per
-// entry, every thread scores K / 256 codes, block-wide argmin.
+// PAIR entries (front of the worklist): one warp per entry, the two known candidates.  SETS entries (back of the worklist): one CTA per
+// entry, the codes of the 64-code sets named by the entry's mask (all sets for rows outside the fp16 range), block-wide argmin.
 __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict__ z, const float* __restrict__ Et, const float* __restrict__ Edk,
                                                         const float* __restrict__ esq, int D, int K, long long M,
                                                         const int4* __restrict__ worklist, const int* __restrict__ counter,
@@ -403,6 +437,7 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
     __shared__ __align__(16) float zs[256];
     __shared__ int cands[MAXCAND];
     __shared__ float scores[1024];
+    __shared__ float part[4][64];
     __shared__ int ncand;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -423,43 +458,45 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
         if (lane == 0) idx[e.x] = (long long)((d1 < d0 || (d1 == d0 && e.z < e.y)) ? e.z : e.y);
     }
-    // all-codes entries: fp32 screening of every code by the whole CTA (the reference's expanded form), then fp64 only for the codes
-    // whose fp32 score lies within the fp32 rounding bound of the minimum (almost always one or two)
+    // SETS entries: fp32 screening of the codes of the masked 64-code sets by the whole CTA (the reference's expanded form), then fp64
+    // only for the codes whose fp32 score lies within the fp32 rounding bound of the minimum (almost always one or two)
+    const int nsets = K >> 6;
     for (int i = blockIdx.x; i < n_full; i += gridDim.x) {
         const int4 e = worklist[M - 1 - i];
+        const uint32_t all_sets = nsets >= 32 ? 0xffffffffu : ((1u << nsets) - 1u);
+        const uint32_t mask = (e.w ? (uint32_t)e.w : all_sets) & all_sets;
         const float* zr = z + (long long)e.x * D;
         for (int d = threadIdx.x; d < D; d += 256) zs[d] = zr[d];
         if (threadIdx.x == 0) ncand = 0;
         __syncthreads();
         float zz = 0.f;
         for (int d = 0; d < D; ++d) zz = fmaf(zs[d], zs[d], zz);
-        // screening: thread = code (c = tid, tid + 256, ...), the codebook read in its [D, K] layout so that a warp's 32 codes are one
-        // coalesced 128-byte row per dimension; z broadcast from shared memory; 4 x 4 independent loads in flight per thread
+        // screening: thread = (code of the set, quarter of the dimensions); the codebook is read in its [D, K] layout so that a warp's 32
+        // codes are one coalesced 128-byte row per dimension; z broadcast from shared memory; 8 independent loads in flight per thread
         float smin = INFINITY;
         {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int d = 0; d < D; d += 4) {
-                float ev[4][4];
+            const int cs = threadIdx.x & 63, slice = threadIdx.x >> 6, dq = D >> 2;
+            for (uint32_t rest = mask; rest; rest &= rest - 1) {
+                const int set = __ffs(rest) - 1;
+                const int c = (set >> 2) * 256 + (set & 3) * 64 + cs;          // set = sub-tile * 4 + column group (main kernel's numbering)
+                const float* ep = Edk + (long long)(slice * dq) * K + c;
+                const float* zp = zs + slice * dq;
+                float a0 = 0.f, a1 = 0.f;
+                for (int d = 0; d < dq; d += 8) {
+                    float ev[8];
 #pragma unroll
-                for (int dd = 0; dd < 4; ++dd)
+                    for (int q = 0; q < 8; ++q) ev[q] = __ldg(ep + (long long)(d + q) * K);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = threadIdx.x + q * 256;
-                        ev[dd][q] = c < K ? __ldg(Edk + (long long)(d + dd) * K + c) : 0.f;
-                    }
-#pragma unroll
-                for (int dd = 0; dd < 4; ++dd)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = fmaf(zs[d + dd], ev[dd][q], acc[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = threadIdx.x + q * 256;
-                if (c < K) {
-                    const float sco = __ldg(esq + c) - 2.0f * acc[q];
+                    for (int q = 0; q < 8; q += 2) { a0 = fmaf(zp[d + q], ev[q], a0); a1 = fmaf(zp[d + q + 1], ev[q + 1], a1); }
+                }
+                part[slice][cs] = a0 + a1;
+                __syncthreads();
+                if (slice == 0) {
+                    const float sco = __ldg(esq + c) - 2.0f * ((part[0][cs] + part[1][cs]) + (part[2][cs] + part[3][cs]));
                     scores[c] = sco;
                     smin = fminf(smin, sco);
                 }
+                __syncthreads();
             }
         }
         smin = warp_min_f(smin);
@@ -475,6 +512,7 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         __syncthreads();
         const bool finite = gmin == gmin && fabsf(gmin) < INFINITY && zz == zz && zz < INFINITY;
         for (int c = threadIdx.x; c < K; c += 256) {
+            if (!((mask >> (((c >> 8) << 2) | ((c >> 6) & 3))) & 1u)) continue;
             // fp32 error of a D-term dot product: <= D * 2^-24 * |z||e| per score; 6e-5 * (|z|^2 + |s|) covers it with margin
             const float sco = scores[c];
             if (!finite || sco - gmin <= 6e-5f * (zz + fabsf(gmin) + fabsf(sco))) {
@@ -499,8 +537,9 @@ __global__ void __launch_bounds__(256) vq_rescue_kernel(const float* __restrict_
         };
         if (nc <= MAXCAND) {
             for (int k = warp; k < nc; k += 8) score64(cands[k]);
-        } else {                                              // degenerate row (all codes nearly equidistant, or non-finite): every code in fp64
-            for (int c = warp; c < K; c += 8) score64(c);
+        } else {                                              // degenerate row (all codes nearly equidistant, or non-finite): every masked code in fp64
+            for (int c = warp; c < K; c += 8)
+                if ((mask >> (((c >> 8) << 2) | ((c >> 6) & 3))) & 1u) score64(c);
         }
         if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
         __syncthreads();
@@ -583,6 +622,7 @@ extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const floa
     prm.kblocks = D / 64; prm.nsub = K / TN;
     prm.n_pair_tiles = (M + 255) / 256;
     prm.tol_factor = tol_factor;
+    prm.key_mul = 256;
     prm.idx = reinterpret_cast<long long*>(idx);
     prm.worklist = reinterpret_cast<int4*>(worklist);
     prm.counter = counter;
