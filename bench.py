@@ -129,7 +129,7 @@ def measured_peaks():
     return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(rel_path, scale):
+def ncu_traffic(rel_path, scale, what="288 images/launch"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the roofline kernel from the committed `ncu --set full` capture (metric dump
     under profiles/), scaled by the launch's image count.  Read from the file, not a literal; None when the capture is absent."""
     path = os.path.join(ROOT, rel_path)
@@ -141,7 +141,7 @@ def ncu_traffic(rel_path, scale):
         f = [c.strip().strip('"') for c in line.rstrip("\n").split(",")]
         if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and len(f) >= 3 and f[1] in unit:
             tot += float(f[2]) * unit[f[1]]
-    return (tot * scale if tot else None), f"{rel_path} (ncu --set full of this kernel, 288 images/launch) x {scale:.3f}"
+    return (tot * scale if tot else None), f"{rel_path} (ncu --set full of this kernel, {what}) x {scale:.3f}"
 
 
 # ------------------------------------------------------------------------------------------------- reference arm (CPU)
@@ -433,7 +433,7 @@ def run_b200(args):
     if q.get("eh") is not None:
         sec_vq = time_launch(lambda: _lib.vq_lookup_fused(zq, q["et"], q["esq"], q["eh"], emb_dk=q["emb"], want_quant=False, want_diff=False), reps=3)
         ach_vq = Mvq * (q["et"].shape[1] * 4 + 8) / sec_vq / 1e9
-        tr_vq, tr_vq_src = ncu_traffic("profiles/r02_vq_fused_ncu_metrics.csv", 1.0)
+        tr_vq, tr_vq_src = ncu_traffic("profiles/r02_vq_fused_ncu_metrics.csv", 1.0, "vq_lookup_fused_kernel at M = 2^20; the exact pass adds 0.03 GB")
         roof_vq = {"kernel": "vq_lookup_fused_kernel + vq_rescue_kernel: fp16 distance GEMM on CTA pairs, top-2 from TMEM, fp64 settlement of near-ties "
                              "(z ~ N(0,1) [2^20, 256] fp32 -> int64 indices, K = 1024)",
                    "bound": "hbm", "achieved": ach_vq, "peak": peak_hbm, "unit": "GB/s", "frac": ach_vq / peak_hbm, "traffic": tr_vq,

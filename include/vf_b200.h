@@ -197,7 +197,8 @@ int vf_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, f
 /* Transformer training step (models/migt.py:464-505, models/utils.py:371-564):
  *   vf_layernorm_bwd: LayerNorm backward over rows of D (statistics recomputed): dx (+ add), dgamma / dbeta accumulated.
  *   vf_gelu_bwd: out = dy * d/dx gelu_erf(pre).   vf_migt_embed_bwd: backward of vf_migt_embed (scatter-add into wte / wpe / pose rows).
- *   vf_cross_entropy_grad: dlogits = w[row] (softmax - smoothed one-hot).   vf_pose_loss_grad: gradient of vf_pose_loss_rows' (pos + ori).
+ *   vf_cross_entropy_grad: dlogits = w[row] (softmax - smoothed one-hot).   vf_pose_loss_grad: gradient of vf_pose_loss_rows' pos_scale * pos + ori_scale * ori
+ *     (both 1 for the plain sum; exp(-w) of DynamicLossWeightingCriterion, migt.py:107-120).
  *   vf_adamw_keras: Keras Adam update (epsilon outside the bias correction) preceded by AdamWeightDecay's p -= lr * wd * p;
  *     the gradient is multiplied by grad_scale * clip_scale first (1 / world size, tf.clip_by_norm factor).
  *   vf_sumsq: out += sum x^2 (per-tensor gradient norms for clip_by_norm).   vf_dropout: stateless inverted dropout, hash(seed, i). */
@@ -210,7 +211,7 @@ int vf_migt_embed_bwd(const float* dh, const int32_t* ids, int fixed_token, int6
 int vf_cross_entropy_grad(const float* logits, const int32_t* labels, const float* row_weight, int64_t rows, int cols, float smoothing,
                           float* dlogits, vf_stream_t s);
 int vf_pose_loss_grad(const float* raw, const float* poses, const float* row_weight, int64_t rows, int tokens_per_view,
-                      float pose_multiplier, float* draw, vf_stream_t s);
+                      float pose_multiplier, float pos_scale, float ori_scale, float* draw, vf_stream_t s);
 int vf_adamw_keras(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, float grad_scale, float clip_scale, vf_stream_t s);
 int vf_sumsq(const float* x, int64_t n, double* out, vf_stream_t s);
@@ -258,6 +259,10 @@ int vf_gather_rows(const float* table, const int64_t* idx, int64_t M, int D, int
 /* training statistics of QuantizeEMA (utils_th.py:47-48): counts[K] += onehot, embed_sum[D,K] += z^T onehot */
 int vf_vq_ema_stats(const float* z, const int64_t* idx, int64_t M, int D, int K,
                     float* counts, float* embed_sum_dk, vf_stream_t s);
+/* Quantize (utils_th.py:75-124, the gradient-trained codebook variant): gradient of beta * mean((q - sg(z))^2) with respect to the [D,K]
+ * codebook from the per-code counts / row sums of vf_vq_ema_stats: grad[d,k] = coef * (counts[k] * E[d,k] - embed_sum[d,k]). */
+int vf_vq_commit_grad(const float* embeddings_dk, const float* counts, const float* embed_sum_dk, int D, int K, float coef,
+                      float* grad_dk, vf_stream_t s);
 /* EMA update + Laplace-smoothed renormalisation (utils_th.py:55-64).  alpha = float32(1 - decay);
  * corr = 1 - decay^counter (post-increment counter), both computed by the host exactly as torch does.
  * Updates cs_hidden[K], dw_hidden[D,K], embeddings[D,K] and the derived Et[K,D], esq[K]. */

@@ -247,8 +247,15 @@ def forward(sd, cfg, inputs, compute_losses=False, use_localization=True, locali
             y = poses.unsqueeze(-2) * torch.tensor([cfg.pose_multiplier] * 3 + [1.0] * 4)
             pl = ((y[..., :3] - xyz) ** 2).mean(-1)[:, cfg.n_loss_skip:].mean((1, 2))
             ol = ((y[..., 3:] - quat) ** 2).mean(-1)[:, cfg.n_loss_skip:].mean((1, 2))
-            out["pose_pos_loss"], out["pose_ori_loss"], out["pose_loss"] = pl, ol, pl + ol
-            loss = loss + (pl + ol) * localization_weight
+            wkey = "pose_loss_weighting_criterion.pos_ori_weights"
+            if getattr(cfg, "use_dynamic_pose_loss", False) and wkey in sd:
+                # DynamicLossWeightingCriterion.call (migt.py:116-118): reduce_sum(w + exp(-w) * stack([pos, ori], -1)) — a scalar
+                w = sd[wkey]
+                pose_loss = (w + torch.exp(-w) * torch.stack([pl, ol], -1)).sum()
+            else:
+                pose_loss = pl + ol                                   # migt.py:284
+            out["pose_pos_loss"], out["pose_ori_loss"], out["pose_loss"] = pl, ol, pose_loss
+            loss = loss + pose_loss * localization_weight
         out["pose_prediction"] = pred
     out["logits"] = logits.reshape(orig_shape + [-1])
     out["loss"] = loss

@@ -58,3 +58,27 @@ def test_camera_helpers_equal_oracle():
     assert torch.allclose(G.from_relative_cameras(r1, t1), mo.from_relative_cameras(r2, t2), atol=1e-6)
     x = torch.randn(2, 3, 64, 7)
     assert torch.allclose(G.reduce_cameras(x, -2), mo.reduce_cameras(x, -2), atol=1e-6)
+
+
+def test_schedule_strings():
+    """viewformer_b200/schedules.py: the string forms of utils/schedules.py:72-247 (linear / cosine / warmup / constant)."""
+    import math
+    from viewformer_b200.schedules import parse
+    assert parse("0.5")(123) == 0.5 and parse(2)(0) == 2.0 and parse("0").is_zero() and not parse("1").is_zero()
+    lin = parse("linear(1,3,10)")
+    assert lin(0) == 1.0 and lin(5) == 2.0 and lin(10) == 3.0 and lin(50) == 3.0
+    cos = parse("cosine(2,0)").with_total_steps(8)
+    assert abs(cos(0) - 2.0) < 1e-12 and abs(cos(4) - 1.0) < 1e-12 and abs(cos(8)) < 1e-12 and abs(cos(80)) < 1e-12
+    assert abs(cos(2) - (0 + (2 - 0) * 0.5 * (math.cos(math.pi * 0.25) + 1))) < 1e-12
+    wu = parse("warmup(cosine(1,0.5,100),4)")
+    assert wu(0) == 0.0 and abs(wu(2) - 0.5 * 1.0) < 1e-12 and abs(wu(4) - 1.0) < 1e-12
+    assert abs(wu(54) - (0.5 + 0.5 * 0.5 * (math.cos(math.pi * 0.5) + 1))) < 1e-12
+    assert str(parse("warmup(1,2000)")) == "warmup(1.0,2000)" and not parse("warmup(1,2000)").is_zero()
+    assert parse("linear(0,0,5)").is_zero() and parse("warmup(0,7)").is_zero()
+    with pytest.raises(ValueError):
+        parse("cosine(1,0)")(3)                      # no horizon yet
+    with pytest.raises(ValueError):
+        parse("step(1,2)")
+    from viewformer_b200.config import MIGTConfig
+    assert MIGTConfig(localization_weight="0").use_localization is False
+    assert MIGTConfig(localization_weight="warmup(1,2000)").use_localization is True

@@ -136,3 +136,45 @@ def test_migt_training_step_matches_oracle_autograd(golden_dir):
     m2 = MIGT(cfg, precision="fp32").load_state_dict(tr.state_dict())
     out = m2(dict(input_ids=codes, poses=cams))
     assert torch.isfinite(out["logits"]).all()
+
+
+def test_migt_dynamic_pose_loss_and_weight_schedule():
+    """use_dynamic_pose_loss (DynamicLossWeightingCriterion, migt.py:107-120) + a non-constant localization_weight schedule
+    (utils/schedules.py; evaluated at the train counter, migt.py:446): loss and gradients of the trainer against torch autograd through the
+    oracle's forward at the same step; the inference-mode ``compute_losses=True`` call reports the same loss."""
+    from viewformer_b200 import MIGT
+    from viewformer_b200.train_migt import MIGTTrainer
+    from viewformer_b200.config import MIGTConfig
+    from viewformer_b200.schedules import parse
+    from oracle.make_golden import MIGT_TRAIN
+    from oracle import migt_oracle as mo
+    sched = "warmup(cosine(1,0.25,40),4)"
+    cfg = MIGTConfig(**dict(MIGT_TRAIN, use_dynamic_pose_loss=True, localization_weight=sched, total_steps=50))
+    sd = synth.make_migt_state_dict(cfg, 11)
+    sd["pose_loss_weighting_criterion.pos_ori_weights"] = torch.tensor([0.3, -1.2])
+    model = MIGT(cfg, precision="fp32").load_state_dict(sd)
+    tr = MIGTTrainer(model, warmup_steps=2, bucket_bytes=1 << 18)
+    B, T = 3, 4
+    codes = synth.make_codes(B, T, n_embed=cfg.n_embeddings, seed=91)
+    cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(B, T, seed=92))[0])
+    for step in (0, 3, 17):
+        tr.iterations = step
+        lw = parse(sched).with_total_steps(50)(step)
+        assert abs(tr.loc_weight - lw) < 1e-12
+        loss = tr.forward_backward(cams, codes)
+        torch.cuda.synchronize()
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        o = mo.forward(leaves, cfg, dict(input_ids=codes, poses=cams), compute_losses=True, localization_weight=lw)
+        ref = o["loss"].mean()
+        ref.backward()
+        print(f"[migt dynamic pose loss] step {step}: localization_weight {lw:.4f} loss {float(loss):.6f} (oracle {float(ref):.6f})")
+        assert abs(float(loss) - float(ref)) < 3e-5 * abs(float(ref))
+        grads = tr.gradients()
+        for k in ("pose_loss_weighting_criterion.pos_ori_weights", "pose_classifier.c_proj.weight", "pose_classifier.c_fc.bias", "h.1.mlp.c_fc.weight", "ln_f.gamma"):
+            want = leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])
+            err = float((grads[k] - want).abs().max() / want.abs().max().clamp_min(1e-5))
+            assert err < 3e-3, f"step {step} grad {k}: rel err {err:.3e}"
+    model._train_counter = 17
+    out = model(dict(input_ids=codes, poses=cams), compute_losses=True)
+    assert abs(float(out["loss"].mean()) - float(ref)) < 3e-5 * abs(float(ref))
+    assert abs(out["localization_weight"] - lw) < 1e-9 and abs(out["dynamic_loss_weight_ori"] + 1.2) < 1e-6

@@ -19,7 +19,7 @@ BIAS_NONE, BIAS_N, BIAS_M = 0, 1, 2
 EXPORTS = [
     "vf_last_error", "vf_version", "vf_sizeof_simt_gemm", "vf_sizeof_tc_gemm", "vf_device_check", "vf_u8_to_unit_f32", "vf_unit_f32_to_u8",
     "vf_nchw_to_nhwc_f32", "vf_nhwc_to_nchw_f32", "vf_groupnorm_stats", "vf_groupnorm_apply", "vf_layernorm",
-    "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update",
+    "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update", "vf_vq_commit_grad",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cameras_prepare", "vf_cameras_from_relative",
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal", "vf_attn_block_causal_tail",
@@ -603,6 +603,13 @@ def vq_ema_stats(z_rows, idx, k):
     return counts, esum
 
 
+def vq_commit_grad(emb_dk, counts, esum, coef, grad_dk):
+    lib = load(True)
+    d, k = emb_dk.shape
+    _check(lib.vf_vq_commit_grad(_p(emb_dk), _p(counts), _p(esum), d, k, C.c_float(coef), _p(grad_dk), _stream()))
+    return grad_dk
+
+
 def vq_ema_update(counts, esum, alpha, corr, eps, cs_hidden, dw_hidden, emb_dk, et, esq):
     lib = load(True)
     d, k = emb_dk.shape
@@ -831,10 +838,11 @@ def cross_entropy_grad(logits_rows, labels_i32, row_weight, smoothing=0.0):
     return out
 
 
-def pose_loss_grad(raw_rows, poses_bt7, row_weight, tokens_per_view, mult):
+def pose_loss_grad(raw_rows, poses_bt7, row_weight, tokens_per_view, mult, pos_scale=1.0, ori_scale=1.0):
     lib = load(True)
     out = torch.empty_like(raw_rows)
-    _check(lib.vf_pose_loss_grad(_p(raw_rows), _p(poses_bt7), _p(row_weight), C.c_int64(raw_rows.shape[0]), tokens_per_view, C.c_float(mult), _p(out), _stream()))
+    _check(lib.vf_pose_loss_grad(_p(raw_rows), _p(poses_bt7), _p(row_weight), C.c_int64(raw_rows.shape[0]), tokens_per_view, C.c_float(mult),
+                                 C.c_float(pos_scale), C.c_float(ori_scale), _p(out), _stream()))
     return out
 
 

@@ -57,11 +57,9 @@ class MIGTConfig(ModelConfig):
 
     @property
     def use_localization(self):
-        """migt.py:268-269: ``not localization_weight.is_zero()`` — constant schedules only."""
-        try:
-            return float(self.localization_weight) != 0.0
-        except (TypeError, ValueError):
-            return True
+        """migt.py:268-269: ``not localization_weight.is_zero()``."""
+        from .schedules import parse
+        return not parse(self.localization_weight).is_zero()
 
 
 @dataclass

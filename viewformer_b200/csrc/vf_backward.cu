@@ -362,16 +362,16 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ 
 
 // d/draw of sum_rows w[row] * (pos_loss + ori_loss) (pose_loss_kernel in vf_misc.cu): pos = mean_3 (y m - r)^2, ori = mean_4 (y - r)^2
 __global__ void pose_loss_grad_kernel(const float* __restrict__ raw, const float* __restrict__ poses, const float* __restrict__ w, long long rows,
-                                      int tokens_per_view, float mult, float* __restrict__ draw) {
+                                      int tokens_per_view, float mult, float pos_scale, float ori_scale, float* __restrict__ draw) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     const float* r = raw + i * 7;
     const float* y = poses + (i / tokens_per_view) * 7;
-    const float wr = w[i];
+    const float wp = w[i] * pos_scale, wo = w[i] * ori_scale;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) draw[i * 7 + j] = wr * (-2.0f / 3.0f) * (y[j] * mult - r[j]);
+    for (int j = 0; j < 3; ++j) draw[i * 7 + j] = wp * (-2.0f / 3.0f) * (y[j] * mult - r[j]);
 #pragma unroll
-    for (int j = 3; j < 7; ++j) draw[i * 7 + j] = wr * (-2.0f / 4.0f) * (y[j] - r[j]);
+    for (int j = 3; j < 7; ++j) draw[i * 7 + j] = wo * (-2.0f / 4.0f) * (y[j] - r[j]);
 }
 
 // Keras Adam (TF 2.4 optimizer_v2/adam.py, non-amsgrad): lr_t = lr sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2);
@@ -565,10 +565,10 @@ extern "C" int vf_cross_entropy_grad(const float* logits, const int32_t* labels,
     return VF_OK;
 }
 extern "C" int vf_pose_loss_grad(const float* raw, const float* poses, const float* row_weight, int64_t rows, int tokens_per_view,
-                                 float pose_multiplier, float* draw, vf_stream_t s) {
+                                 float pose_multiplier, float pos_scale, float ori_scale, float* draw, vf_stream_t s) {
     VF_CHECK_ARG(raw && poses && row_weight && draw && tokens_per_view > 0, "vf_pose_loss_grad: bad args");
     if (rows == 0) return VF_OK;
-    pose_loss_grad_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, vf_s(s)>>>(raw, poses, row_weight, rows, tokens_per_view, pose_multiplier, draw);
+    pose_loss_grad_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, vf_s(s)>>>(raw, poses, row_weight, rows, tokens_per_view, pose_multiplier, pos_scale, ori_scale, draw);
     VF_CHECK_LAUNCH("vf_pose_loss_grad");
     return VF_OK;
 }

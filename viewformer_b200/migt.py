@@ -42,6 +42,7 @@ class MIGT:
         self.mask_token = cfg.n_embeddings                 # migt.py:256
         self.localization_token = cfg.n_embeddings + 1     # migt.py:257
         self.use_localization = cfg.use_localization       # migt.py:268-269
+        self._train_counter = 0                            # Keras Model._train_counter: optimisation steps taken (migt.py:446)
         self._codebook_model = None
         self._sd = None
         self._w = None
@@ -76,6 +77,8 @@ class MIGT:
                 out[p + n + ".bias"] = (1, nf)
         out["ln_f.gamma"] = (d,)
         out["ln_f.beta"] = (d,)
+        if cfg.use_dynamic_pose_loss:
+            out["pose_loss_weighting_criterion.pos_ori_weights"] = (2,)      # DynamicLossWeightingCriterion (migt.py:107-120)
         return out
 
     def expected_keys(self):
@@ -89,6 +92,8 @@ class MIGT:
         for k, shp in self.param_shapes().items():
             if k.endswith("gamma"):
                 sd[k] = torch.ones(shp)
+            elif k.endswith("pos_ori_weights"):
+                sd[k] = torch.tensor([0.0, -3.0])                           # migt.py:114
             elif k.endswith("beta") or k.endswith("bias"):
                 sd[k] = torch.zeros(shp)
             else:
@@ -288,13 +293,22 @@ class MIGT:
         pred = L.pose_postprocess(raw, self.config.pose_multiplier)
         return (pred, raw) if return_raw else pred
 
-    def _localization_weight(self, step=0):
-        """Schedule('...')(step) of migt.py:268,452 for the constant / piecewise-constant forms the released configs use."""
-        lw = str(self.config.localization_weight)
-        try:
-            return float(lw)
-        except ValueError:
-            raise NotImplementedError(f"localization_weight schedule '{lw}' is not a constant; pass a numeric weight for loss evaluation")
+    def _localization_weight(self, step=None):
+        """``self.localization_weight(self._train_counter)`` of migt.py:268, 446: the config's schedule string evaluated at the number of
+        optimisation steps taken so far (``_train_counter``; 0 for a freshly loaded model, advanced by ``train_step``)."""
+        from .schedules import parse
+        sched = parse(self.config.localization_weight).with_total_steps(int(self.config.total_steps))
+        return float(sched(self._train_counter if step is None else step))
+
+    def _pose_loss(self, pl, ol):
+        """pose_loss_weighting_criterion (migt.py:279-284): position + orientation loss, or — use_dynamic_pose_loss — the learned
+        homoscedastic weighting  sum(w + exp(-w) * [pos, ori])  over the batch (migt.py:116-118), a scalar."""
+        if not self.config.use_dynamic_pose_loss:
+            return pl + ol, {}
+        w = self._sd["pose_loss_weighting_criterion.pos_ori_weights"].to(torch.float64)
+        pl64, ol64 = pl.double().cpu(), ol.double().cpu()
+        total = (w[0] + torch.exp(-w[0]) * pl64).sum() + (w[1] + torch.exp(-w[1]) * ol64).sum()
+        return total.to(torch.float32).to(pl.device), dict(dynamic_loss_weight_pos=float(w[0]), dynamic_loss_weight_ori=float(w[1]))
 
     # ------------------------------------------------------------------ reference call surface
     def __call__(self, inputs, training=False, compute_losses=False, last_only=False, **kwargs):
@@ -305,8 +319,6 @@ class MIGT:
                                       "viewformer_b200.train_migt.MIGTTrainer")
         if compute_losses and last_only:
             raise ValueError("compute_losses needs the logits of every view (last_only=False)")
-        if compute_losses and self.config.use_dynamic_pose_loss:
-            raise NotImplementedError("use_dynamic_pose_loss carries trained weights (migt.py:107-120); not part of this round")
         if self._w is None:
             raise RuntimeError("MIGT has no weights: call load_state_dict() first")
         cfg = self.config
@@ -382,9 +394,11 @@ class MIGT:
                 pl = L.row_mean(pl_rows.reshape(B, T * Lt), skip * Lt)
                 ol = L.row_mean(ol_rows.reshape(B, T * Lt), skip * Lt)
                 w = self._localization_weight()
-                out["pose_pos_loss"], out["pose_ori_loss"], out["pose_loss"] = pl, ol, pl + ol
+                pose_loss, wc_metrics = self._pose_loss(pl, ol)
+                out.update(wc_metrics)
+                out["pose_pos_loss"], out["pose_ori_loss"], out["pose_loss"] = pl, ol, pose_loss
                 out["localization_weight"] = w
-                loss = loss + (pl + ol) * w
+                loss = loss + pose_loss * w
             else:
                 pred = self._pose_head(xs[pose_ptr])
             out["pose_prediction"] = pred.reshape(B, T, Lt, 7)
@@ -410,6 +424,7 @@ class MIGT:
             self.compile()
         out = self._trainer.train_step(batch)
         self.load_state_dict(self._trainer.state_dict())
+        self._train_counter = self._trainer.iterations
         return out
 
     # ------------------------------------------------------------------ Keras evaluation steps (migt.py:507-541)

@@ -90,7 +90,11 @@ class VQGANTrainer:
                 conv(f"encoder.down.{lv}.downsample.conv", lvw["down"])
         rb("encoder.mid.block_1", e["mid1"]); at("encoder.mid.attn_1", e["mida"]); rb("encoder.mid.block_2", e["mid2"])
         norm("encoder.norm_out", e, "norm_out"); conv("encoder.conv_out", e["conv_out"])
-        lin("quant_conv", w["quant_conv"]); lin("post_quant_conv", w["post_quant_conv"])
+        lin("quant_conv", w["quant_conv"])
+        if self.model.quantizer == "commit":          # Quantize (utils_th.py:75-124): the codebook is an ordinary parameter
+            q = w["q"]
+            ps.append(_P("quantize.embeddings", q["emb"], lambda t, q=q: q.__setitem__("emb", t), "vec"))
+        lin("post_quant_conv", w["post_quant_conv"])
         conv("decoder.conv_in", d["conv_in"])
         rb("decoder.mid.block_1", d["mid1"]); at("decoder.mid.attn_1", d["mida"]); rb("decoder.mid.block_2", d["mid2"])
         for lv in reversed(range(len(self.cfg.ch_mult))):
@@ -360,6 +364,13 @@ class VQGANTrainer:
                     # through post_quant_conv, the straight-through estimator and the commitment term, quant_conv
                     dq = self._lin_bw("post_quant_conv", w["post_quant_conv"], quant, dy.reshape(-1, dy.shape[-1]))
                     dz = L.lincomb3(1.0, dq, 2.0 * float(cfg.codebook_weight) / z.numel(), z, -2.0 * float(cfg.codebook_weight) / z.numel(), quant)
+                    if model.quantizer == "commit":
+                        # d/dE of beta mean((q - sg(z))^2): column k gets 2 beta / numel * (count_k e_k - sum of the z rows mapped to k);
+                        # the straight-through output carries no gradient to E (utils_th.py:117)
+                        pe = P["quantize.embeddings"]
+                        counts, zsum = L.vq_ema_stats(z, idx, pe.tensor.shape[1])
+                        L.vq_commit_grad(pe.tensor, counts, zsum, 2.0 * model.beta * float(cfg.codebook_weight) / z.numel(), pe.grad)
+                        self._grad_ready(pe)
                     dy = self._lin_bw("quant_conv", w["quant_conv"], hz.reshape(-1, zc), dz).reshape(hz.shape)
             elif kind == "normconv":
                 _, nname, cname, blk, xin, st = entry
@@ -381,7 +392,10 @@ class VQGANTrainer:
         self.step_count += 1
         L.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                step=self.step_count, grad_scale=1.0 / self._world())
-        self.model._refresh_decode_table()
+        if self.model.quantizer == "commit":
+            self.model._refresh_codebook()
+        else:
+            self.model._refresh_decode_table()
 
     def training_step(self, batch, batch_idx=0):
         """vqgan_th.py:413-423 + the optimizer step Lightning runs after it.  Returns the loss of the step (0-d f32 tensor)."""

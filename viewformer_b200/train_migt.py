@@ -33,8 +33,6 @@ class MIGTTrainer:
     def __init__(self, model, betas=(0.9, 0.999), eps=1e-8, warmup_steps=2000, bucket_bytes=64 << 20, process_group=None, seed=0,
                  grad_reduce="sum"):
         cfg = model.config
-        if cfg.use_dynamic_pose_loss:
-            raise NotImplementedError("use_dynamic_pose_loss (trainable loss weights, migt.py:107-120) is not supported")
         if cfg.random_pose_multiplier != 1.0:
             raise NotImplementedError("random_pose_multiplier != 1 (pose-scale augmentation, migt.py:350-353) is not supported")
         self.model, self.cfg, self.device = model, cfg, model.device
@@ -46,15 +44,23 @@ class MIGTTrainer:
         self.grad_reduce = grad_reduce
         self.iterations = 0                                        # optimizer.iterations (0-based: the schedule sees it BEFORE the increment)
         self.use_loc = model.use_localization
-        self.loc_weight = float(cfg.localization_weight) if self.use_loc else 0.0
+        from .schedules import parse
+        self._loc_schedule = parse(cfg.localization_weight).with_total_steps(int(cfg.total_steps))
+        self.dynamic_pose = bool(cfg.use_dynamic_pose_loss) and self.use_loc
         self._build(model.state_dict())
+
+    @property
+    def loc_weight(self):
+        """localization_weight(self._train_counter) (migt.py:446): the schedule at the number of steps taken so far."""
+        return float(self._loc_schedule(self.iterations)) if self.use_loc else 0.0
 
     # ------------------------------------------------------------------ parameters
     def _build(self, sd):
         names = list(self.model.param_shapes().keys())
         # backward completion order: heads, ln_f, blocks from last to first, pose embedding, wpe, wte (tied: complete only at the very end)
         n_layer = self.cfg.n_layer
-        order = [k for k in names if k.startswith("pose_classifier.")] + [k for k in names if k.startswith("ln_f.")]
+        order = ([k for k in names if k.startswith("pose_loss_weighting_criterion.")] + [k for k in names if k.startswith("pose_classifier.")]
+                 + [k for k in names if k.startswith("ln_f.")])
         for i in reversed(range(n_layer)):
             order += [k for k in names if k.startswith(f"h.{i}.")]
         order += [k for k in names if k.startswith("pose_embedding.")] + ["wpe.embeddings", "wte.weight"]
@@ -260,13 +266,27 @@ class MIGTTrainer:
             raw = self._lin(self._gelu(pc_h), "pose_classifier.c_proj")            # [B*S, 7]
             pl_rows, ol_rows = L.pose_loss_rows(raw, poses, Lt, float(cfg.pose_multiplier))
             pl, ol = L.row_mean(pl_rows.reshape(B, S), skip * Lt), L.row_mean(ol_rows.reshape(B, S), skip * Lt)
-            loss = loss + (pl + ol) * self.loc_weight
-            self.last.update(pose_pos_loss=pl, pose_ori_loss=ol, pose_loss=pl + ol)
-            draw = L.pose_loss_grad(raw, poses, (view_ok * (self.loc_weight / denom)).contiguous(), Lt, float(cfg.pose_multiplier))
+            lw_now = self.loc_weight
+            if self.dynamic_pose:
+                # DynamicLossWeightingCriterion (migt.py:107-120): P = sum_b (w0 + e^-w0 pos_b) + (w1 + e^-w1 ori_b), a scalar added to every
+                # scene's loss; d mean(loss) / d w = lw (B - e^-w sum_b loss_b), d / d pos_b = lw e^-w0 (B times the plain-sum case)
+                wkey = "pose_loss_weighting_criterion.pos_ori_weights"
+                w01 = self.p[wkey].detach().double().cpu()
+                e0, e1 = math.exp(-float(w01[0])), math.exp(-float(w01[1]))
+                pls, ols = float(pl.double().sum()), float(ol.double().sum())
+                pose_loss = torch.full_like(pl, float(B * (w01[0] + w01[1]) + e0 * pls + e1 * ols))
+                self.g[wkey].copy_(torch.tensor([lw_now * (B - e0 * pls), lw_now * (B - e1 * ols)], dtype=torch.float32))
+                self._ready(wkey)
+                ps, os_ = e0 * B, e1 * B
+            else:
+                pose_loss, ps, os_ = pl + ol, 1.0, 1.0
+            loss = loss + pose_loss * lw_now
+            self.last.update(pose_pos_loss=pl, pose_ori_loss=ol, pose_loss=pose_loss)
+            draw = L.pose_loss_grad(raw, poses, (view_ok * (lw_now / denom)).contiguous(), Lt, float(cfg.pose_multiplier), ps, os_)
             dg_ = self._lin_bw(self._gelu(pc_h), draw, "pose_classifier.c_proj")
             dhn[2] = self._lin_bw(hn[2], L.gelu_bwd(pc_h, dg_), "pose_classifier.c_fc")
         else:
-            self._ready(*[k for k in self.order if k.startswith("pose_classifier.")])
+            self._ready(*[k for k in self.order if k.startswith("pose_classifier.") or k.startswith("pose_loss_weighting_criterion.")])
         # ln_f backward (shared parameters: accumulate over the streams that carry a loss)
         dxs = [torch.zeros_like(xs[0])] + [None] * (ns - 1)
         live = [s for s in range(ns) if dhn[s] is not None]

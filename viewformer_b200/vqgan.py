@@ -50,9 +50,14 @@ class _Conv3:
 class VQGAN:
     _ignore_checkpoint_attributes = [r"perceptual_loss\..*", r"loss\..*"]
 
-    def __init__(self, config=None, precision="bf16", device="cuda", **config_overrides):
+    def __init__(self, config=None, precision="bf16", device="cuda", quantizer="ema", beta=0.25, **config_overrides):
+        """``quantizer``: "ema" = QuantizeEMA (utils_th.py:8-72, what vqgan_th.py:331 instantiates) or "commit" = Quantize
+        (utils_th.py:75-124: the codebook is a gradient-trained parameter, loss = |sg(q) - z|^2 + beta |q - sg(z)|^2)."""
         if config is None:
             config = VQGANConfig(**config_overrides)
+        if quantizer not in ("ema", "commit"):
+            raise ValueError("quantizer must be 'ema' (QuantizeEMA) or 'commit' (Quantize, beta-weighted commitment loss)")
+        self.quantizer, self.beta = quantizer, float(beta)
         self.config = load_config(config)
         # ``mixed``: the encoder (whose output feeds the bit-exact codebook argmin) runs in the fp32-faithful ``exact`` arithmetic,
         # the decoder (pixels within a tolerance) on the bf16 tensor-core path.  One precision name otherwise serves both halves.
@@ -158,9 +163,10 @@ class VQGAN:
                 conv(f"decoder.up.{lv}.upsample.conv", cin, cin, 3)
         norm("decoder.norm_out", cin); conv("decoder.conv_out", cfg.out_ch, cin, 3)
         out["quantize.embeddings"] = (cfg.embed_dim, cfg.n_embed)
-        out["quantize.ema_cluster_size_hidden"] = (cfg.n_embed,)
-        out["quantize.ema_dw_hidden"] = (cfg.embed_dim, cfg.n_embed)
-        out["quantize.counter"] = ()
+        if self.quantizer == "ema":
+            out["quantize.ema_cluster_size_hidden"] = (cfg.n_embed,)
+            out["quantize.ema_dw_hidden"] = (cfg.embed_dim, cfg.n_embed)
+            out["quantize.counter"] = ()
         conv("quant_conv", cfg.embed_dim, cfg.z_channels, 1); conv("post_quant_conv", cfg.z_channels, cfg.embed_dim, 1)
         return out
 
@@ -178,7 +184,8 @@ class VQGAN:
         shapes = self.param_shapes()
         for k, shp in shapes.items():
             if k == "quantize.embeddings":
-                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * 3 ** 0.5
+                # QuantizeEMA: U(+-sqrt 3) (utils_th.py:17); Quantize: U(+-1/K) (utils_th.py:90-91)
+                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * (3 ** 0.5 if self.quantizer == "ema" else 1.0 / shp[1])
             elif k == "quantize.counter":
                 sd[k] = torch.tensor(0, dtype=torch.int64)
             elif k.startswith("quantize."):
@@ -206,7 +213,8 @@ class VQGAN:
             sd = OrderedDict((k, v) for k, v in sd.items() if k in shapes)
             missing = [k for k in shapes if k not in sd]
             if missing:
-                cur = self.state_dict() if self._sd is not None else VQGAN(self.config, precision=self.precision, device=self.device)._initial_state(0)
+                cur = self.state_dict() if self._sd is not None else VQGAN(self.config, precision=self.precision, device=self.device,
+                                                                          quantizer=self.quantizer, beta=self.beta)._initial_state(0)
                 for k in missing:
                     sd[k] = cur[k]
         self._sd = OrderedDict((k, torch.as_tensor(v).detach().to("cpu").clone()) for k, v in sd.items())
@@ -218,9 +226,10 @@ class VQGAN:
         if self._w is not None:     # training mutates the quantizer buffers on the device
             q = self._w["q"]
             sd["quantize.embeddings"] = q["emb"].detach().cpu().clone()
-            sd["quantize.ema_cluster_size_hidden"] = q["cs"].detach().cpu().clone()
-            sd["quantize.ema_dw_hidden"] = q["dw"].detach().cpu().clone()
-            sd["quantize.counter"] = torch.tensor(q["counter"], dtype=torch.int64)
+            if self.quantizer == "ema":
+                sd["quantize.ema_cluster_size_hidden"] = q["cs"].detach().cpu().clone()
+                sd["quantize.ema_dw_hidden"] = q["dw"].detach().cpu().clone()
+                sd["quantize.counter"] = torch.tensor(q["counter"], dtype=torch.int64)
         return sd
 
     # ------------------------------------------------------------------ weight preparation (load time only)
@@ -288,13 +297,21 @@ class VQGAN:
         w["quant_conv"] = lin("quant_conv", self.exact)
         w["post_quant_conv"] = lin("post_quant_conv", self.exact)
         emb = sd["quantize.embeddings"].to(dev, torch.float32).contiguous()             # [D,K] (utils_th.py:17-18)
-        et, esq = L.vq_prepare_codebook(emb)
-        w["q"] = dict(emb=emb, et=et, esq=esq, et3=L.vq_split3(et, True) if self.prec.use_tc else None,
-                      eh=L.vq_prepare_codebook_f16(et) if (self.prec.use_tc and L.vq_fused_ok(*emb.shape)) else None,
-                      cs=sd["quantize.ema_cluster_size_hidden"].to(dev, torch.float32).contiguous(),
-                      dw=sd["quantize.ema_dw_hidden"].to(dev, torch.float32).contiguous(),
-                      counter=int(sd["quantize.counter"]))
+        w["q"] = dict(emb=emb)
+        if self.quantizer == "ema":
+            w["q"].update(cs=sd["quantize.ema_cluster_size_hidden"].to(dev, torch.float32).contiguous(),
+                          dw=sd["quantize.ema_dw_hidden"].to(dev, torch.float32).contiguous(),
+                          counter=int(sd["quantize.counter"]))
         self._w = w
+        self._refresh_codebook()
+
+    def _refresh_codebook(self):
+        """Everything derived from the [D,K] codebook: transposed copy, |e|^2, tensor-core operand copies, the decode table.
+        Called at load time and after a gradient step on the codebook (``quantizer="commit"``)."""
+        q = self._w["q"]
+        q["et"], q["esq"] = L.vq_prepare_codebook(q["emb"])
+        q["et3"] = L.vq_split3(q["et"], True) if self.prec.use_tc else None
+        q["eh"] = L.vq_prepare_codebook_f16(q["et"]) if (self.prec.use_tc and L.vq_fused_ok(*q["emb"].shape)) else None
         self._refresh_decode_table()
 
     def _refresh_decode_table(self):
@@ -491,9 +508,12 @@ class VQGAN:
             idx, quant, dsum = L.vq_lookup_tc(z_rows, q["et"], q["esq"], q["et3"], want_quant=want_quant, want_diff=True)
         else:
             idx, quant, dsum = L.vq_lookup(z_rows, q["et"], q["esq"], want_quant=want_quant, want_diff=True)
-        if self.training:
+        if self.training and self.quantizer == "ema":
             self._ema_update(z_rows, idx)
         diff = (dsum / float(z_rows.numel())).to(torch.float32).reshape(())
+        if self.quantizer == "commit":
+            # utils_th.py:113-114: mean((sg(q) - z)^2) + beta mean((q - sg(z))^2) — one number twice, the gradients differ (train.py)
+            diff = diff + self.beta * diff
         return quant, diff, idx
 
     def _ema_update(self, z_rows, idx):
