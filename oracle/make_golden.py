@@ -158,6 +158,46 @@ def golden_vqgan_train():
     print("train golden: losses", float(out["loss0"]), float(out["loss1"]))
 
 
+def golden_vqgan_train_commit():
+    """The same two optimisation steps with the reference's OTHER quantizer, ``Quantize`` (utils_th.py:75-124: gradient-trained codebook,
+    beta = 0.25 commitment term), dropped into the real reference VQGAN in place of QuantizeEMA — both classes return
+    (quantize, loss, indices), so VQGAN.forward / _compute_loss run unchanged."""
+    overrides = dict(SMALL_VQ, perceptual_weight=0.0)
+    cfg = VQGANConfig(**overrides)
+    sd = synth.make_vqgan_state_dict(cfg, 5)
+    ref = ref_loader.build_reference_vqgan(sd, **overrides)
+    import sys
+    Quantize = sys.modules["viewformer.models.utils_th"].Quantize
+    ref.quantize = Quantize(cfg.embed_dim, cfg.n_embed, beta=0.25)
+    with torch.no_grad():
+        ref.quantize.embeddings.copy_(sd["quantize.embeddings"] * 0.5)        # a codebook at the scale of the encoder output
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.9))
+    g = torch.Generator().manual_seed(99)
+    names = [n for n, _ in ref.named_parameters()]
+    probe = {n: torch.randn(p.shape, generator=g) for n, p in ref.named_parameters()}
+    keep = ["quantize.embeddings", "quant_conv.weight", "post_quant_conv.bias", "encoder.conv_in.weight", "decoder.conv_out.bias"]
+    out = dict(names=np.array(names), emb_init=ref.quantize.embeddings.detach().numpy().copy())
+    for step in range(2):
+        x = vq_images(3, cfg.image_size, 2000 + step)
+        opt.zero_grad()
+        xrec, qloss, _, codes = ref(x)
+        loss, log = ref._compute_loss(qloss, x, xrec, split="train")
+        loss.backward()
+        out[f"loss{step}"] = loss.detach().numpy()
+        out[f"quant{step}"] = log["train/quant_loss"].numpy()
+        out[f"codes{step}"] = codes.numpy()
+        out[f"gnorm{step}"] = np.array([float(p.grad.norm()) for _, p in ref.named_parameters()])
+        out[f"gdot{step}"] = np.array([float((p.grad * probe[n]).sum()) for n, p in ref.named_parameters()])
+        for k in keep:
+            out[f"g{step}.{k}"] = dict(ref.named_parameters())[k].grad.numpy().copy()
+        opt.step()
+        for k in keep:
+            out[f"p{step}.{k}"] = dict(ref.named_parameters())[k].detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "vqgan_train_commit_small.npz"), **out)
+    print("train (commit quantizer) golden: losses", float(out["loss0"]), float(out["loss1"]), "names", len(names))
+
+
 def keras_adamw_reference(params, grads, m, v, step, lr, wd, betas=(0.9, 0.999), eps=1e-8):
     """Restatement of AdamWeightDecay._resource_apply_dense (models/utils.py:507-523) on top of Keras Adam (TF 2.4
     optimizer_v2/adam.py, non-amsgrad): decoupled decay for names without "bias" (the exclusion patterns "LayerNorm" / "layer_norm"
@@ -238,4 +278,5 @@ if __name__ == "__main__":
     golden_vqgan("full", {}, 4, 0)
     golden_migt()
     golden_vqgan_train()
+    golden_vqgan_train_commit()
     golden_migt_train()

@@ -79,6 +79,61 @@ def test_vqgan_training_step_matches_reference(golden_dir):
     assert torch.equal(m2.encode(xq)[2], model.encode(xq)[2])
 
 
+def test_vqgan_commit_quantizer_training_step_matches_reference(golden_dir):
+    """``VQGAN(quantizer="commit")`` = the reference's gradient-trained ``Quantize`` (utils_th.py:75-124, beta = 0.25) in place of QuantizeEMA:
+    two optimisation steps against tests/golden/vqgan_train_commit_small.npz (the real reference VQGAN with its own Quantize class dropped
+    in, oracle/make_golden.py) — loss (1 + beta) * mean((q - z)^2), codes, gradients of every tensor incl. the codebook, post-Adam codebook."""
+    from viewformer_b200 import VQGAN
+    from viewformer_b200.train import VQGANTrainer
+    g = np.load(os.path.join(golden_dir, "vqgan_train_commit_small.npz"))
+    cfg = VQGANConfig(**dict(SMALL_VQ, perceptual_weight=0.0))
+    sd = synth.make_vqgan_state_dict(cfg, 5)
+    sd = {k: v for k, v in sd.items() if not k.startswith("quantize.") or k == "quantize.embeddings"}
+    sd["quantize.embeddings"] = torch.from_numpy(g["emb_init"])
+    model = VQGAN(cfg, precision="fp32", quantizer="commit", beta=0.25).load_state_dict(sd)
+    assert "quantize.counter" not in model.expected_keys()
+    tr = VQGANTrainer(model, bucket_bytes=1 << 16)
+    names = [str(n) for n in g["names"]]
+    assert "quantize.embeddings" in names
+    gen = torch.Generator().manual_seed(99)
+    probe = None
+    for step in range(2):
+        x = vq_images(3, cfg.image_size, 2000 + step)
+        loss = tr.forward_backward(x)
+        torch.cuda.synchronize()
+        assert sorted(tr.launched) == list(range(len(tr.buckets)))
+        print(f"[commit-quantizer train step {step}] loss {float(loss):.6f} (ref {float(g[f'loss{step}']):.6f}) quant {float(tr.last['quant_loss']):.6f}")
+        assert np.array_equal(tr.last["codes"].cpu().numpy(), g[f"codes{step}"])
+        assert abs(float(loss) - float(g[f"loss{step}"])) < 2e-5 * max(1.0, abs(float(g[f"loss{step}"])))
+        assert abs(float(tr.last["quant_loss"]) - float(g[f"quant{step}"])) < 2e-5
+        grads = tr.export_gradients()
+        assert set(grads) == set(names)
+        if probe is None:
+            probe = {n: torch.randn(grads[n].shape, generator=gen) for n in names}
+        worst = 0.0
+        for i, n in enumerate(names):
+            gn, gd = float(grads[n].norm()), float((grads[n] * probe[n]).sum())
+            rn, rd = float(g[f"gnorm{step}"][i]), float(g[f"gdot{step}"][i])
+            e = max(abs(gn - rn), abs(gd - rd)) / max(rn, 1e-4)
+            worst = max(worst, e)
+            assert e < 3e-3, f"step {step} {n}: |g| {gn:.6e} vs {rn:.6e}, <g,probe> {gd:.6e} vs {rd:.6e}"
+        for n in [k[len(f"g{step}."):] for k in g.files if k.startswith(f"g{step}.")]:
+            ref = torch.from_numpy(g[f"g{step}.{n}"])
+            err = float((grads[n] - ref).abs().max() / ref.abs().max().clamp_min(1e-4))
+            assert err < 2e-3, f"step {step} grad {n}: max rel err {err:.3e}"
+        print(f"[commit-quantizer train step {step}] gradients: worst norm/projection rel err {worst:.2e} over {len(names)} tensors")
+        tr.optimizer_step()
+        emb = model._w["q"]["emb"].cpu()
+        ref = torch.from_numpy(g[f"p{step}.quantize.embeddings"])
+        frac_bad = float(((emb - ref).abs() > 0.05 * cfg.learning_rate).float().mean())
+        assert frac_bad < 0.02, f"step {step}: {frac_bad:.3%} codebook elements differ by more than 5% of lr after Adam"
+        # the lookup tables follow the gradient step (transposed copy, |e|^2, decode table)
+        assert torch.allclose(model._w["q"]["et"].cpu(), emb.t(), atol=0) and torch.allclose(model._w["q"]["esq"].cpu(), (emb * emb).sum(0), rtol=1e-5)
+    m2 = VQGAN(cfg, precision="fp32", quantizer="commit").load_state_dict(tr.export_state_dict())
+    xq = vq_images(2, cfg.image_size, 7)
+    assert torch.equal(m2.encode(xq)[2], model.encode(xq)[2])
+
+
 def test_migt_training_step_matches_oracle_autograd(golden_dir):
     """MIGT.train_step (migt.py:464-505): three optimisation steps against tests/golden/migt_train_small.npz — gradients from torch
     autograd through the oracle's forward, optimizer / schedule restated from models/utils.py (oracle/make_golden.py).  PARITY UNPINNED
