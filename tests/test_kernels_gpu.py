@@ -732,3 +732,21 @@ def test_vq_lookup_fused_small_codebooks(L, D, K):
     a, qa, da = L.vq_lookup_fused(z.cuda(), et, esq, eh)
     b, qb, db = L.vq_lookup(z.cuda(), et, esq)
     assert torch.equal(a, b) and torch.equal(qa, qb) and abs(float(da) - float(db)) <= 1e-9 * abs(float(db))
+
+
+def test_cta_pair_mma_path_matches_single_cta():
+    """`cta_group::2` pairs in the 128x128 tcgen05 kernel (opt-in, VF_TC_2CTA=1): same results as the single-CTA path on a GEMM and a conv
+    the wide kernels do not take (the flag is read once per process, hence the subprocesses)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, VF_TC_2CTA=flag)
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "two_cta_check.py")], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[flag] = [l for l in r.stdout.splitlines() if l.startswith(("gemm", "conv"))]
+        print(f"[VF_TC_2CTA={flag}]", " | ".join(outs[flag]))
+        for l in outs[flag]:
+            assert float(l.split()[2]) < 2e-2, l
+    # the accumulation order inside a tile is the same (K blocks in order, fp32 TMEM accumulators): identical sums
+    assert outs["0"] == outs["1"]

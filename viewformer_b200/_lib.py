@@ -124,6 +124,22 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_model_device(fn):
+    """Method decorator for the model classes: run with the model's device as the CURRENT CUDA device.  Every wrapper below launches on
+    ``torch.cuda.current_stream()`` of the current device and the library caches per-device attributes, so a model built with
+    ``device='cuda:1'`` must not run while device 0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrap(self, *a, **k):
+        dev = getattr(self, "device", None)
+        if dev is None or dev.type != "cuda" or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrap
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -140,6 +156,9 @@ def _dt(t):
 
 def _dev(t, dtype=None):
     assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor expected"
+    if t.device.index != torch.cuda.current_device():
+        raise LibraryError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: kernels launch on the "
+                           "current device's stream (the model classes switch devices themselves; raw _lib callers must use torch.cuda.device)")
     if dtype is not None:
         assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
     return t

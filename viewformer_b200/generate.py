@@ -77,6 +77,10 @@ def generate_batch_predictions(transformer_model, codebook_model, images, camera
     forward on the true codes of the target view (:134-136).  Default: encode the target only when that
     second forward is needed (skipping it does not change any returned value).
     """
+    _dev = getattr(codebook_model, "device", None)
+    if _dev is not None and _dev.type == "cuda" and _dev.index is not None and _dev.index != torch.cuda.current_device():
+        with torch.cuda.device(_dev):            # kernels launch on the current device's stream: make the models' device current
+            return generate_batch_predictions(transformer_model, codebook_model, images, cameras, encode_target=encode_target)
     dev = transformer_model.device
     images = torch.as_tensor(images)
     cameras = torch.as_tensor(cameras)
@@ -157,6 +161,10 @@ def generate_batch_predictions_multictx(transformer_model, codebook_model, image
     """Multi-context variant — viewformer/evaluate/evaluate_transformer_multictx.py:37-95: one 3-stream forward yields,
     for every context size i, the query view rendered from context views 0..i-1 (stream 1) and the query localised
     against them (stream 2).  Returns generated_images [B,T,H,W,3] u8 and generated_cameras [B,T,7]."""
+    _dev = getattr(codebook_model, "device", None)
+    if _dev is not None and _dev.type == "cuda" and _dev.index is not None and _dev.index != torch.cuda.current_device():
+        with torch.cuda.device(_dev):            # kernels launch on the current device's stream: make the models' device current
+            return generate_batch_predictions_multictx(transformer_model, codebook_model, images, cameras)
     dev = transformer_model.device
     images = torch.as_tensor(images)
     cameras = torch.as_tensor(cameras)

@@ -102,6 +102,7 @@ class MIGT:
 
     _keys_to_ignore_on_load_unexpected = [r"h\.\d+\.attn\.bias"]      # migt.py:242 (causal-mask buffers of older checkpoints)
 
+    @L.on_model_device
     def load_state_dict(self, state_dict, strict=True):
         import re
         ign = [re.compile(p) for p in self._keys_to_ignore_on_load_unexpected]
@@ -311,6 +312,7 @@ class MIGT:
         return total.to(torch.float32).to(pl.device), dict(dynamic_loss_weight_pos=float(w[0]), dynamic_loss_weight_ori=float(w[1]))
 
     # ------------------------------------------------------------------ reference call surface
+    @L.on_model_device
     def __call__(self, inputs, training=False, compute_losses=False, last_only=False, **kwargs):
         """MIGT.call (migt.py:338-455), inference semantics (training=False; dropout inactive).
         ``last_only=True`` computes logits for the last view only (what evaluate_transformer.py:123 consumes)."""
@@ -417,6 +419,7 @@ class MIGT:
         self._trainer = optimizer if optimizer is not None else MIGTTrainer(self, **kwargs)
         return self._trainer
 
+    @L.on_model_device
     def train_step(self, batch):
         """(poses [B,T,7], tokens [B,T,h,w]) -> metrics dict; one optimisation step (forward, backward, gradient exchange, AdamW).
         The model serves inference with the updated weights right away (they are re-laid-out for the inference kernels)."""
@@ -428,6 +431,7 @@ class MIGT:
         return out
 
     # ------------------------------------------------------------------ Keras evaluation steps (migt.py:507-541)
+    @L.on_model_device
     def test_step(self, batch):
         """(poses [B,T,7], tokens [B,T,h,w]) -> dict of scalars: losses of ``call(compute_losses=True)``, token accuracy and, with
         a codebook attached, the PSNR between the decoded predicted and true last views (migt.py:507-530)."""
@@ -453,6 +457,7 @@ class MIGT:
             res["psnr"] = float(image_metrics(gt_img, gen, self.device)["psnr"].mean())
         return res
 
+    @L.on_model_device
     def predict_step(self, batch):
         """migt.py:535-541: decoded images of the teacher-forced argmax tokens and of the true tokens (float NHWC in [-1, 1])."""
         poses, tokens = batch
@@ -465,6 +470,7 @@ class MIGT:
                 "ground_truth_image": self._codebook_model.decode_code_nhwc(tok.reshape(-1, side, side))}
 
     # ------------------------------------------------------------------ context KV cache (BASELINE config 5)
+    @L.on_model_device
     def prefill_context(self, codes_ctx, poses_ctx):
         """Run the context views once and keep every layer's K / V^T.  Exact: the transformer is block-causal over
         views, so context hidden states never depend on the query view (oracle invariant (ii)).
@@ -547,6 +553,7 @@ class MIGT:
         hmid = linear(prec, m, lw["fc"], prec.opd, act=L.ACT_GELU)
         return linear(prec, hmid, lw["fc2"], torch.float32, residual=xn)
 
+    @L.on_model_device
     def query(self, cache, query_poses, return_logits=False):
         """Novel-view codes for query poses against a prefilled context.  query_poses f32 [Nq,7]; Nq == cache batch
         (one query per scene) or cache batch == 1 (many queries share one scene, evaluate_transformer_multictx_allimg.py:141-173).
@@ -571,6 +578,7 @@ class MIGT:
         return (codes, logits.reshape(Nq, side, side, -1)) if return_logits else codes
 
     # ------------------------------------------------------------------ fast inference entry points
+    @L.on_model_device
     def generate_codes(self, codes_ctx, poses):
         """Context codes [B,T-1,8,8] + poses [B,T,7] (already relative/normalised) -> argmax codes of view T
         (evaluate_transformer.py:118-123 without materialising logits of the context views)."""

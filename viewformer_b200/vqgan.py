@@ -199,6 +199,7 @@ class VQGAN:
                 sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / (w[1] * w[2] * w[3]) ** 0.5
         return sd
 
+    @L.on_model_device
     def load_state_dict(self, state_dict, strict=True):
         """Strict key check with the reference's ignore patterns (vqgan_th.py:346-359)."""
         sd = OrderedDict((k, v) for k, v in state_dict.items() if not _IGNORE.match(k))
@@ -221,6 +222,7 @@ class VQGAN:
         self._build()
         return self
 
+    @L.on_model_device
     def state_dict(self):
         sd = OrderedDict((k, v.clone()) for k, v in self._sd.items())
         if self._w is not None:     # training mutates the quantizer buffers on the device
@@ -540,6 +542,7 @@ class VQGAN:
             t = t.to(device=self.device, dtype=dtype).contiguous()
         return t
 
+    @L.on_model_device
     def encode_rows(self, x_nhwc):
         """f32 NHWC images -> (z rows [N*h*w, D], h, w)"""
         z = self._encoder(x_nhwc)
@@ -552,6 +555,7 @@ class VQGAN:
             raise ValueError(f"{what}: expected {'NCHW' if channel_axis == 1 else 'NHWC'} images with {self.config.in_channels} channels, "
                              f"got shape {tuple(t.shape)} (the torch flavour is NCHW, the TF flavour NHWC)")
 
+    @L.on_model_device
     def encode_nhwc(self, x_nhwc):
         """TF-twin convention (viewformer/models/vqgan.py:291-295): NHWC in, (quant NHWC, diff, codes [N,h,w])."""
         self._need_weights()
@@ -562,6 +566,7 @@ class VQGAN:
         quant, diff, idx = self._quantize(zr)
         return quant.reshape(n, hh, ww, -1), diff, idx.reshape(n, hh, ww)
 
+    @L.on_model_device
     def encode_u8(self, images_u8_nhwc, first_views=None):
         """uint8 NHWC images -> codes int64 [N,h,w] (evaluate_transformer.py:105-110 in one device pass).
         With ``first_views=n`` the input is [B,T,H,W,3] and views 0..n-1 of every scene are encoded ([B*n,h,w])."""
@@ -571,6 +576,7 @@ class VQGAN:
         _, _, idx = self._quantize(zr, want_quant=False)
         return idx.reshape(x.shape[0], hh, ww)
 
+    @L.on_model_device
     def decode_code_nhwc(self, codes):
         self._need_weights()
         codes = self._in(codes, torch.int64)
@@ -578,6 +584,7 @@ class VQGAN:
         z = L.gather_rows(self._w["pq_table"], codes.reshape(-1)).reshape(n, hh, ww, -1)
         return self._decoder(z)
 
+    @L.on_model_device
     def decode_code_u8(self, codes):
         """codes -> uint8 NHWC images (clip, /2+.5, ->uint8; evaluate_transformer.py:127-129)."""
         return L.unit_to_u8(self.decode_code_nhwc(codes))
@@ -587,6 +594,7 @@ class VQGAN:
         if self._w is None:
             raise RuntimeError("VQGAN has no weights: call load_state_dict() first")
 
+    @L.on_model_device
     def encode(self, x):
         self._need_weights()
         self._check_layout(torch.as_tensor(x), 1, "encode")
@@ -596,6 +604,7 @@ class VQGAN:
         quant, diff, idx = self._quantize(zr)
         return L.nhwc_to_nchw(quant.reshape(n, hh, ww, -1)), diff, idx.reshape(n, hh, ww)
 
+    @L.on_model_device
     def decode(self, quant):
         self._need_weights()
         q = L.nchw_to_nhwc(self._in(quant))
@@ -603,15 +612,18 @@ class VQGAN:
         z = linear(self.exact, q.reshape(-1, c), self._w["post_quant_conv"], torch.float32).reshape(n, hh, ww, -1)
         return L.nhwc_to_nchw(self._decoder(z))
 
+    @L.on_model_device
     def decode_code(self, code_b):
         return L.nhwc_to_nchw(self.decode_code_nhwc(code_b))
 
+    @L.on_model_device
     def forward(self, input):
         quant, diff, idx = self.encode(input)
         return self.decode(quant), diff, quant, idx
 
     __call__ = forward
 
+    @L.on_model_device
     def embed_code(self, embed_id):
         """utils_th.py:70-72: ids [N,h,w] -> [N,D,h,w]."""
         ids = self._in(embed_id, torch.int64)
@@ -626,10 +638,12 @@ class VQGAN:
             self._trainer = VQGANTrainer(self)
         return self._trainer
 
+    @L.on_model_device
     def training_step(self, batch, batch_idx=0):
         """Loss of one optimisation step on ``batch`` (f32 NCHW in [-1,1]); gradients are exchanged and Adam applied inside."""
         return self.configure_optimizers().training_step(batch, batch_idx)
 
+    @L.on_model_device
     def validation_step(self, batch, batch_idx=0):
         """vqgan_th.py:425-441: reconstruction and total loss without touching weights or the codebook."""
         was = self.training
