@@ -65,5 +65,36 @@ def build(force=False, verbose=True):
     return LIB
 
 
+MODEL_LIB = os.path.join(HERE, "libvf_b200_model.so")
+
+
+def build_model_abi(force=False, verbose=True):
+    """libvf_b200_model.so: the model-level C-ABI (include/vf_b200_model.h), a C shim over the embedded interpreter (csrc/vf_model_abi.c).
+    Plain gcc; links libpython of the interpreter running this build."""
+    import sysconfig
+    src = os.path.join(CSRC, "vf_model_abi.c")
+    hdr = os.path.join(HERE, "..", "include", "vf_b200_model.h")
+    if not force and os.path.exists(MODEL_LIB) and os.path.getmtime(MODEL_LIB) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return MODEL_LIB
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    inc, libdir = sysconfig.get_config_var("INCLUDEPY"), sysconfig.get_config_var("LIBDIR")
+    ver = sysconfig.get_config_var("LDVERSION") or sysconfig.get_python_version()
+    if not gcc or not inc or not os.path.exists(os.path.join(inc, "Python.h")):
+        raise RuntimeError("building libvf_b200_model.so needs gcc and the CPython headers (Python.h)")
+    root = os.path.abspath(os.path.join(HERE, ".."))
+    cmd = [gcc, "-shared", "-fPIC", "-O2", "-Wall", src, "-I", os.path.join(root, "include"), "-I", inc,
+           f'-DVF_PYTHON_DEFAULT="{sys.executable}"', f'-DVF_REPO_ROOT_DEFAULT="{root}"',
+           "-L", libdir, f"-lpython{ver}", f"-Wl,-rpath,{libdir}", "-o", MODEL_LIB]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed for vf_model_abi.c:\n" + r.stdout)
+    if verbose:
+        if r.stdout.strip():
+            print(r.stdout)
+        print("built", MODEL_LIB)
+    return MODEL_LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    build_model_abi(force="--force" in sys.argv)
