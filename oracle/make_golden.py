@@ -158,6 +158,38 @@ def golden_vqgan_train():
     print("train golden: losses", float(out["loss0"]), float(out["loss1"]))
 
 
+def golden_vqgan_train_full():
+    """ONE optimisation step of the real reference codebook at the FULL BASELINE size (VQGANConfig defaults: 128x128 images, ch 128,
+    ch_mult [1,1,2,2,4], 1024 x 256 codebook; 67.9 M parameters), batch of 2: loss terms, codes, gradient norm and a random projection of
+    every parameter tensor, the EMA-updated codebook's projections.  Small file: no full tensors."""
+    overrides = dict(perceptual_weight=0.0)
+    cfg = VQGANConfig(**overrides)
+    sd = synth.make_vqgan_state_dict(cfg, 5)
+    ref = ref_loader.build_reference_vqgan(sd, **overrides)
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=cfg.learning_rate, betas=(0.5, 0.9))
+    g = torch.Generator().manual_seed(99)
+    names = [n for n, _ in ref.named_parameters()]
+    probe = {n: torch.randn(p.shape, generator=g) for n, p in ref.named_parameters()}
+    x = vq_images(2, cfg.image_size, 3000)
+    opt.zero_grad()
+    xrec, qloss, _, codes = ref(x)
+    loss, log = ref._compute_loss(qloss, x, xrec, split="train")
+    loss.backward()
+    out = dict(names=np.array(names), loss=loss.detach().numpy(), rec=log["train/rec_loss"].numpy(), quant=log["train/quant_loss"].numpy(),
+               codes=codes.numpy(),
+               gnorm=np.array([float(p.grad.norm()) for _, p in ref.named_parameters()]),
+               gdot=np.array([float((p.grad * probe[n]).sum()) for n, p in ref.named_parameters()]))
+    opt.step()
+    out["pdot"] = np.array([float((p.detach() * probe[n]).sum()) for n, p in ref.named_parameters()])
+    e = ref.quantize.embeddings
+    ge = torch.Generator().manual_seed(7)
+    out["emb_norm"] = np.float64(e.double().norm())
+    out["emb_dot"] = np.float64((e.double() * torch.randn(e.shape, generator=ge).double()).sum())
+    np.savez_compressed(os.path.join(OUT, "vqgan_train_full.npz"), **out)
+    print("train golden (full size): loss", float(out["loss"]), "tensors", len(names))
+
+
 def golden_vqgan_train_commit():
     """The same two optimisation steps with the reference's OTHER quantizer, ``Quantize`` (utils_th.py:75-124: gradient-trained codebook,
     beta = 0.25 commitment term), dropped into the real reference VQGAN in place of QuantizeEMA — both classes return
@@ -269,6 +301,28 @@ def golden_migt_train():
     print("migt train golden: losses", [float(out[f"loss{i}"]) for i in range(3)])
 
 
+def golden_migt_train_full():
+    """One optimisation step of the FULL-size transformer (MIGTConfig defaults: 12 layers, d = 768, 12 heads, 1024 + 2 tokens), B = 1,
+    T = 5 views, dropout 0: loss terms, gradient norm + projection of every tensor (autograd through the oracle; PARITY UNPINNED)."""
+    cfg = MIGTConfig(dropout=0.0, label_smoothing=0.1, localization_weight="0.7", total_steps=100, learning_rate=1e-4)
+    sd = {k: v.clone() for k, v in synth.make_migt_state_dict(cfg, 13).items()}
+    B, T = 1, 5
+    codes = synth.make_codes(B, T, n_embed=cfg.n_embeddings, seed=70)
+    cams = migt_oracle.normalize_cameras(migt_oracle.to_relative_cameras(synth.make_cameras(B, T, seed=71))[0])
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = migt_oracle.forward(leaves, cfg, dict(input_ids=codes, poses=cams), compute_losses=True, localization_weight=0.7)
+    loss = o["loss"].mean()
+    loss.backward()
+    names = list(sd.keys())
+    gen = torch.Generator().manual_seed(78)
+    probe = {k: torch.randn(sd[k].shape, generator=gen) for k in names}
+    grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])) for k in names}
+    out = dict(names=np.array(names), loss=loss.detach().numpy(), ce=o["ce_loss"].detach().numpy(), pose=o["pose_loss"].detach().numpy(),
+               gnorm=np.array([float(grads[k].norm()) for k in names]), gdot=np.array([float((grads[k] * probe[k]).sum()) for k in names]))
+    np.savez_compressed(os.path.join(OUT, "migt_train_full.npz"), **out)
+    print("migt train golden (full size): loss", float(out["loss"]), "tensors", len(names))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -279,4 +333,6 @@ if __name__ == "__main__":
     golden_migt()
     golden_vqgan_train()
     golden_vqgan_train_commit()
+    golden_vqgan_train_full()
     golden_migt_train()
+    golden_migt_train_full()

@@ -1,7 +1,7 @@
 /* A host with no Python code of its own, driving the model-level C-ABI (include/vf_b200_model.h).  Built and run by
  * tests/test_model_cabi.py:  cabi_host <in.bin> <out.bin>
  * in.bin : int32 n_img, B, T | uint8 images [n_img,32,32,3] | int32 ids [B,T,4,4] | float poses [B,T,7]
- * out.bin: int64 codes [n_img,4,4] | uint8 decoded [n_img,32,32,3] | int64 codes_last [B,4,4] | int64 query codes [B,4,4] */
+ * out.bin: int64 codes [n_img,8,8] | uint8 decoded [n_img,32,32,3] | int64 codes_last [B,4,4] | int64 query codes [B,4,4] */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -32,12 +32,12 @@ int main(int argc, char** argv) {
     int S, s, K, C, ts, V, mask, loc;
     CK(vf_vq_info(vq, &S, &s, &K, &C));
     CK(vf_migt_info(tr, &ts, &V, &mask, &loc));
-    if (S != 32 || s != 4 || K != 64 || C != 3 || ts != 4 || V != 64 || mask != 64) { fprintf(stderr, "unexpected model info\n"); return 4; }
+    if (S != 32 || s != 8 || K != 64 || C != 3 || ts != 4 || V != 64 || mask != 64) { fprintf(stderr, "unexpected model info\n"); return 4; }
 
     cudaStream_t st;
     CU(cudaStreamCreate(&st));
     uint8_t *d_img, *d_dec; int64_t *d_codes, *d_last, *d_q; int32_t* d_ids; float* d_pose;
-    CU(cudaMalloc((void**)&d_img, img_b)); CU(cudaMalloc((void**)&d_dec, img_b)); CU(cudaMalloc((void**)&d_codes, (size_t)n * 16 * 8));
+    CU(cudaMalloc((void**)&d_img, img_b)); CU(cudaMalloc((void**)&d_dec, img_b)); CU(cudaMalloc((void**)&d_codes, (size_t)n * 64 * 8));
     CU(cudaMalloc((void**)&d_ids, ids_b)); CU(cudaMalloc((void**)&d_pose, pose_b));
     CU(cudaMalloc((void**)&d_last, (size_t)B * 16 * 8)); CU(cudaMalloc((void**)&d_q, (size_t)B * 16 * 8));
     CU(cudaMemcpyAsync(d_img, h_img, img_b, cudaMemcpyHostToDevice, st));
@@ -62,8 +62,8 @@ int main(int argc, char** argv) {
     CK(vf_migt_prefill_context(tr, d_ctx, d_cpose, B, T - 1, &cache, st));
     CK(vf_migt_query(tr, cache, d_qpose, B, d_q, st));
 
-    int64_t* h_codes = malloc((size_t)n * 16 * 8); uint8_t* h_dec = malloc(img_b); int64_t* h_last = malloc((size_t)B * 16 * 8); int64_t* h_q = malloc((size_t)B * 16 * 8);
-    CU(cudaMemcpyAsync(h_codes, d_codes, (size_t)n * 16 * 8, cudaMemcpyDeviceToHost, st));
+    int64_t* h_codes = malloc((size_t)n * 64 * 8); uint8_t* h_dec = malloc(img_b); int64_t* h_last = malloc((size_t)B * 16 * 8); int64_t* h_q = malloc((size_t)B * 16 * 8);
+    CU(cudaMemcpyAsync(h_codes, d_codes, (size_t)n * 64 * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_dec, d_dec, img_b, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_last, d_last, (size_t)B * 16 * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_q, d_q, (size_t)B * 16 * 8, cudaMemcpyDeviceToHost, st));
@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
     CK(vf_destroy(cache)); CK(vf_destroy(tr)); CK(vf_destroy(vq));
 
     f = fopen(argv[2], "wb");
-    fwrite(h_codes, 8, (size_t)n * 16, f); fwrite(h_dec, 1, img_b, f); fwrite(h_last, 8, (size_t)B * 16, f); fwrite(h_q, 8, (size_t)B * 16, f);
+    fwrite(h_codes, 8, (size_t)n * 64, f); fwrite(h_dec, 1, img_b, f); fwrite(h_last, 8, (size_t)B * 16, f); fwrite(h_q, 8, (size_t)B * 16, f);
     fclose(f);
     printf("cabi_host ok: %d images, %d scenes x %d views; last error after the bad-handle probe: %s\n", n, B, T, vf_model_last_error());
     return 0;

@@ -60,7 +60,7 @@ def test_c_host_drives_models_through_the_model_abi(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     raw = open(fout, "rb").read()
     o = 0
-    codes = np.frombuffer(raw, np.int64, n * 16, o).reshape(n, 4, 4); o += n * 16 * 8
+    codes = np.frombuffer(raw, np.int64, n * 64, o).reshape(n, 8, 8); o += n * 64 * 8
     dec = np.frombuffer(raw, np.uint8, n * 32 * 32 * 3, o).reshape(n, 32, 32, 3); o += n * 32 * 32 * 3
     last = np.frombuffer(raw, np.int64, B * 16, o).reshape(B, 4, 4); o += B * 16 * 8
     qcodes = np.frombuffer(raw, np.int64, B * 16, o).reshape(B, 4, 4)

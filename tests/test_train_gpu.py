@@ -79,6 +79,44 @@ def test_vqgan_training_step_matches_reference(golden_dir):
     assert torch.equal(m2.encode(xq)[2], model.encode(xq)[2])
 
 
+def test_vqgan_training_step_full_size_matches_reference(golden_dir):
+    """BASELINE configs[3] model (VQGANConfig defaults, 67.9 M parameters, 128x128 images): one optimisation step on a batch of 2 against
+    the REAL reference (tests/golden/vqgan_train_full.npz): loss terms, the 128 codes, gradient norm and projection of all 342 tensors,
+    post-Adam weight projections and the EMA-updated codebook."""
+    from viewformer_b200 import VQGAN
+    from viewformer_b200.train import VQGANTrainer
+    g = np.load(os.path.join(golden_dir, "vqgan_train_full.npz"))
+    cfg = VQGANConfig(perceptual_weight=0.0)
+    model = VQGAN(cfg, precision="fp32").load_state_dict(synth.make_vqgan_state_dict(cfg, 5))
+    tr = VQGANTrainer(model)
+    names = [str(n) for n in g["names"]]
+    x = vq_images(2, cfg.image_size, 3000)
+    loss = tr.forward_backward(x)
+    torch.cuda.synchronize()
+    print(f"[full-size train step] loss {float(loss):.6f} (ref {float(g['loss']):.6f}) rec {float(tr.last['rec_loss']):.6f} quant {float(tr.last['quant_loss']):.6f}; "
+          f"{len(tr.buckets)} gradient buckets")
+    assert np.array_equal(tr.last["codes"].cpu().numpy(), g["codes"])
+    assert abs(float(loss) - float(g["loss"])) < 2e-5 * max(1.0, abs(float(g["loss"])))
+    assert abs(float(tr.last["rec_loss"]) - float(g["rec"])) < 2e-5 and abs(float(tr.last["quant_loss"]) - float(g["quant"])) < 2e-5
+    grads = tr.export_gradients()
+    assert set(grads) == set(names)
+    gen = torch.Generator().manual_seed(99)
+    probe = {n: torch.randn(grads[n].shape, generator=gen) for n in names}
+    worst = 0.0
+    for i, n in enumerate(names):
+        gn, gd = float(grads[n].norm()), float((grads[n] * probe[n]).sum())
+        rn, rd = float(g["gnorm"][i]), float(g["gdot"][i])
+        e = max(abs(gn - rn), abs(gd - rd)) / max(rn, 1e-4)
+        worst = max(worst, e)
+        assert e < 5e-3, f"{n}: |g| {gn:.6e} vs {rn:.6e}, <g,probe> {gd:.6e} vs {rd:.6e}"
+    print(f"[full-size train step] gradients: worst norm/projection rel err {worst:.2e} over {len(names)} tensors")
+    tr.optimizer_step()
+    emb = model._w["q"]["emb"].double().cpu()
+    ge = torch.Generator().manual_seed(7)
+    assert abs(float(emb.norm()) - float(g["emb_norm"])) < 1e-5 * float(g["emb_norm"])
+    assert abs(float((emb * torch.randn(emb.shape, generator=ge).double()).sum()) - float(g["emb_dot"])) < 2e-4 * float(g["emb_norm"])
+
+
 def test_vqgan_commit_quantizer_training_step_matches_reference(golden_dir):
     """``VQGAN(quantizer="commit")`` = the reference's gradient-trained ``Quantize`` (utils_th.py:75-124, beta = 0.25) in place of QuantizeEMA:
     two optimisation steps against tests/golden/vqgan_train_commit_small.npz (the real reference VQGAN with its own Quantize class dropped
@@ -236,3 +274,37 @@ def test_migt_dynamic_pose_loss_and_weight_schedule():
     out = model(dict(input_ids=codes, poses=cams), compute_losses=True)
     assert abs(float(out["loss"].mean()) - float(ref)) < 3e-5 * abs(float(ref))
     assert abs(out["localization_weight"] - lw) < 1e-9 and abs(out["dynamic_loss_weight_ori"] + 1.2) < 1e-6
+
+
+def test_migt_training_step_full_size_matches_oracle_autograd(golden_dir):
+    """Full-size transformer (MIGTConfig defaults: 12 layers, d = 768): loss terms and the gradient of all 156 tensors of one training step
+    (B = 1, T = 5, dropout 0) against torch autograd through the oracle (tests/golden/migt_train_full.npz; PARITY UNPINNED)."""
+    from viewformer_b200 import MIGT
+    from viewformer_b200.train_migt import MIGTTrainer
+    from viewformer_b200.config import MIGTConfig
+    from oracle import migt_oracle as mo
+    g = np.load(os.path.join(golden_dir, "migt_train_full.npz"))
+    cfg = MIGTConfig(dropout=0.0, label_smoothing=0.1, localization_weight="0.7", total_steps=100, learning_rate=1e-4)
+    model = MIGT(cfg, precision="fp32").load_state_dict(synth.make_migt_state_dict(cfg, 13))
+    tr = MIGTTrainer(model)
+    B, T = 1, 5
+    codes = synth.make_codes(B, T, n_embed=cfg.n_embeddings, seed=70)
+    cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(B, T, seed=71))[0])
+    loss = tr.forward_backward(cams, codes)
+    torch.cuda.synchronize()
+    print(f"[migt full-size train step] loss {float(loss):.6f} (ref {float(g['loss']):.6f})")
+    assert abs(float(loss) - float(g["loss"])) < 3e-5 * abs(float(g["loss"]))
+    np.testing.assert_allclose(tr.last["ce_loss"].cpu().numpy(), g["ce"], rtol=3e-5)
+    np.testing.assert_allclose(tr.last["pose_loss"].cpu().numpy(), g["pose"], rtol=2e-4)
+    names = [str(n) for n in g["names"]]
+    grads = tr.gradients()
+    gen = torch.Generator().manual_seed(78)
+    worst = 0.0
+    for i, n in enumerate(names):
+        pr = torch.randn(tuple(grads[n].shape), generator=gen)
+        gn, gd = float(grads[n].norm()), float((grads[n] * pr).sum())
+        rn, rd = float(g["gnorm"][i]), float(g["gdot"][i])
+        e = max(abs(gn - rn), abs(gd - rd)) / max(rn, 1e-4)
+        worst = max(worst, e)
+        assert e < 3e-3, f"{n}: |g| {gn:.6e} vs {rn:.6e}, <g,probe> {gd:.6e} vs {rd:.6e}"
+    print(f"[migt full-size train step] gradients: worst norm/projection rel err {worst:.2e} over {len(names)} tensors")
