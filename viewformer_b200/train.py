@@ -15,8 +15,14 @@ twin flat gradient buffer ordered by backward completion (decoder.conv_out first
     the backward pass has produced its last gradient — the transfers ride under the remaining backward kernels;
   * Adam is one kernel launch over the whole model.
 Activations needed by the backward pass are kept on a tape; GroupNorm+swish outputs are recomputed from the saved statistics.
+
+Arithmetic: fp32 throughout, as the reference requires.  The 3x3 stride-1 convolutions with tensor-core-sized channel counts run
+their forward pass and their data gradient on the exact split-fp16 tcgen05 kernels (fp32-faithful results from three fp16 MMA passes,
+DESIGN.md 5.3; ``VF_TRAIN_TC=0`` keeps everything on the CUDA cores); weight gradients, strided / upsampling convs and 1x1 layers use
+the fp32 CUDA-core kernels.
 """
 import math
+import os
 
 import torch
 
@@ -48,6 +54,8 @@ class VQGANTrainer:
         self._collect_params()
         self._flatten()
         self.last = {}
+        self.use_tc = os.environ.get("VF_TRAIN_TC", "1") != "0"
+        self._wsplit = {}
 
     # ------------------------------------------------------------------ parameter registry
     def _collect_params(self):
@@ -177,7 +185,31 @@ class VQGANTrainer:
                                         L._p(y), L.F32, L._stream()))
         return y
 
+    # 3x3 stride-1 convolutions whose channel counts fit the tcgen05 tiles run on the EXACT split-fp16 tensor-core path (three fp16 MMA
+    # passes, chunked accumulation: fp32-faithful results, DESIGN.md 5.3) in the forward pass and in the data gradient; everything else
+    # (conv_in / conv_out, stride-2 and upsampling convs, 1x1 layers) and every weight gradient stays on the fp32 CUDA-core kernels.
+    def _tc_ok(self, cw, stride, upsample):
+        return self.use_tc and cw.k == 3 and stride == 1 and not upsample and cw.cin % 64 == 0 and cw.cout % 64 == 0
+
+    def _split_weight(self, key, w_kn, n_out):
+        """[K, n_out] fp32 (K = tap * C + c) -> split-fp16 [n_out, tap * 2C] for L.tc_conv; cached until the next optimizer step."""
+        hit = self._wsplit.get(key)
+        if hit is None:
+            k = w_kn.shape[0]
+            c = k // 9
+            w_nk = w_kn.t().contiguous()                                        # [n_out, 9 * C]
+            hit = L.split_f16x2(w_nk.reshape(n_out * 9, c)).reshape(n_out, 9 * 2 * c)
+            self._wsplit[key] = hit
+        return hit
+
+    @staticmethod
+    def _split_act(x):
+        n, h, w, c = x.shape
+        return L.split_f16x2(x.reshape(n * h * w, c)).reshape(n, h, w, 2 * c)
+
     def _conv_fw(self, cw, a, residual=None, stride=1, upsample=False):
+        if self._tc_ok(cw, stride, upsample):
+            return L.tc_conv(self._split_act(a), self._split_weight(("fw", id(cw)), cw.w_kn, cw.cout), cw.bias, residual=residual)
         return self.model._conv(cw, a, residual=residual, stride=stride, upsample=upsample, stats=False)
 
     def _conv_bw(self, name, cw, a, dy, stride=1, upsample=False, need_dx=True):
@@ -193,6 +225,12 @@ class VQGANTrainer:
         if stride == 2:                                         # Downsample: gather form, taps not flipped
             wd = wk.permute(0, 1, 3, 2).reshape(cw.k * cw.k * cw.cout, cw.cin).contiguous()
             return L.simt_conv_dgrad_s2(dy, wd, (a.shape[1], a.shape[2]))
+        if self._tc_ok(cw, stride, upsample):
+            key = ("bw", id(cw))
+            if key not in self._wsplit:                         # a data gradient is a conv with flipped taps and swapped channel roles
+                wd = wk.flip(0, 1).permute(0, 1, 3, 2).reshape(cw.k * cw.k * cw.cout, cw.cin).contiguous()
+                self._split_weight(key, wd, cw.cin)
+            return L.tc_conv(self._split_act(dy), self._wsplit[key], None)
         wd = wk.flip(0, 1).permute(0, 1, 3, 2).reshape(cw.k * cw.k * cw.cout, cw.cin).contiguous()      # a data gradient is a conv with flipped taps
         dx = L.simt_conv(dy, wd, None, kh=cw.k, stride=1, pad=(1, 1) if cw.k == 3 else (0, 0))
         return L.sumpool2x2(dx) if upsample else dx
@@ -392,6 +430,7 @@ class VQGANTrainer:
         self.step_count += 1
         L.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                step=self.step_count, grad_scale=1.0 / self._world())
+        self._wsplit = {}                               # split-fp16 operand copies of the conv weights are stale now
         if self.model.quantizer == "commit":
             self.model._refresh_codebook()
         else:
