@@ -169,6 +169,12 @@ int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, in
  * V^T columns stay in `qk` / `vt` from the prefill and the query view's are appended behind them. */
 int vf_attn_block_causal_tail(const void* qk_bf16, const void* vt_bf16, int B, int S, int H, int d, int block, int first_query,
                               void* out_bf16, vf_stream_t s);
+/* Branching (multi-end) attention of the 3-stream forward — viewformer/models/branching_attention.py:82-126.  qk [B, n_streams*S, 2d] and
+ * vt [B, d, n_streams*S] hold the streams side by side.  stream 0: block-causal over its own keys; stream s >= 1: a query of view t attends
+ * to the stream-0 keys of views < t and to its own stream's keys of view t (one joint softmax).  out bf16 [B*S, d] = that stream's output.
+ * Streams >= 1 need block == 64.  Same fused kernel: the key-tile schedule changes, nothing is materialised in HBM. */
+int vf_attn_block_multiend(const void* qk_bf16, const void* vt_bf16, int B, int S, int n_streams, int stream, int H, int d, int block,
+                           void* out_bf16, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Backward pass of the codebook training step (models/vqgan_th.py:395-423, 443-445), fp32.  Data gradients of convolutions and dense

@@ -569,6 +569,26 @@ def test_fused_attention_growing_logits_and_tail(L, B, T, H, blk, first):
         assert bool((got[:, :t0] == 7.0).all()), "rows below the first computed tile must stay untouched"
 
 
+@pytest.mark.parametrize("B,T,H", [(2, 5, 2), (1, 10, 3), (1, 3, 1), (2, 2, 1)])
+def test_fused_multiend_attention(L, B, T, H):
+    """Fused branching attention == branching_attention.py:82-126 (oracle restatement): stream 0 block-causal, streams 1 and 2 attend to the
+    stream-0 keys of strictly earlier views plus their own view of their own stream, one joint softmax."""
+    from oracle import migt_oracle as mo
+    blk, ns = 64, 3
+    d, S = H * 64, T * blk
+    gg = g(T * 7 + H)
+    qk = (torch.randn(B, ns * S, 2 * d, generator=gg) * 0.5).bfloat16()
+    v = torch.randn(B, ns * S, d, generator=gg).bfloat16()
+    vt = v.permute(0, 2, 1).contiguous()
+    split = lambda x: [x[:, s * S:(s + 1) * S].double().reshape(B, T, blk, H, 64).permute(0, 3, 1, 2, 4) for s in range(ns)]      # [B,H,T,L,dh]
+    want = mo.causal_block_multiend_attention(split(qk[..., d:]), split(v), split(qk[..., :d]))
+    for s in range(ns):
+        out = L.attn_block_multiend(qk.cuda(), vt.cuda(), B, S, ns, s, H, d, blk)
+        torch.cuda.synchronize()
+        w = want[s].permute(0, 2, 3, 1, 4).reshape(B * S, d)
+        report(f"fused multi-end attention stream {s} B{B} T{T} H{H}", out.float(), w, 2e-2, 2e-2)
+
+
 def test_vq_lookup_tensor_core_bit_exact(L, golden_dir):
     """bf16x3 tcgen05 distance GEMM + exact fp64 re-score == the reference's indices, incl. the adversarial near-ties."""
     import os

@@ -38,6 +38,7 @@ constexpr float LAZY_LOG2 = 8.0f;              // the reference maximum moves on
 struct AttnParams {
     CUtensorMap tmQ, tmK, tmV;
     int S, H, d, block, n_qtiles, qt0, BH;  // query tiles qt0 .. qt0 + n_qtiles - 1 are computed (qt0 > 0: KV-cache query mode)
+    int stream, stream_rows;                // multi-end mode (stream > 0): rows of stream s start at s * stream_rows in qk / V^T
     __nv_bfloat16* out;
     unsigned idesc;                         // M = 128, N = 64 for both Q K^T and P V
 };
@@ -142,6 +143,21 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
         const int last_q = min(q0 + QT, p.S) - 1;                                   // keys visible to the tile's last valid query
         const int kv_lim = min(p.S, (last_q / p.block + 1) * p.block);
         n_kt = (kv_lim + KT - 1) / KT;
+        if (p.stream > 0) n_kt = q0 / KT + ((q0 + KT < p.S) ? 3 : 1);               // multi-end schedule, see tile_at
+    };
+    // Key tile j of the item whose first query is q0: row of the tile in qk / V^T and which half of the 128 query rows sees it
+    // (bit 0: rows 0..63, bit 1: rows 64..127).  Stream 0 (block-causal, branching_attention.py:41-61): tile j of stream 0, the masks
+    // come from the per-row visibility arithmetic.  Stream s >= 1 (branching_attention.py:82-126; one view per 64-key tile): a query of
+    // view t sees stream-0 keys of views < t and its own stream's keys of view t — for the tile's two views (t0, t0 + 1):
+    //   stream 0, views 0 .. t0-1 (both halves) | stream 0, view t0 (upper half) | stream s, view t0 (lower half) | stream s, view t0+1 (upper)
+    auto tile_at = [&](int q0, int j, int& krow, uint32_t& halves) {
+        if (p.stream == 0) { krow = j * KT; halves = 3u; return; }
+        const int t0 = q0 / KT;
+        const bool two = q0 + KT < p.S;
+        if (j < t0) { krow = j * KT; halves = 3u; }
+        else if (two && j == t0) { krow = t0 * KT; halves = 2u; }
+        else if (j == t0 + (two ? 1 : 0)) { krow = p.stream * p.stream_rows + t0 * KT; halves = 1u; }
+        else { krow = p.stream * p.stream_rows + (t0 + 1) * KT; halves = 2u; }
     };
 
     if (warp == 0) {
@@ -154,15 +170,18 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
                 item_coords(item, b, h, q0, n_kt);
                 if (it >= 2) mbar_wait(&q_empty[it & 1], use_parity(it - 2), "vf_attn producer(Q)");
                 mbar_expect_tx(&q_full[it & 1], Q_BYTES);
-                tma_load_4d(sQ + (it & 1) * Q_BYTES, &p.tmQ, &q_full[it & 1], 0, q0, h, b);
+                tma_load_4d(sQ + (it & 1) * Q_BYTES, &p.tmQ, &q_full[it & 1], 0, p.stream * p.stream_rows + q0, h, b);
                 for (int j = 0; j < n_kt; ++j) {
+                    int krow;
+                    uint32_t halves;
+                    tile_at(q0, j, krow, halves);
                     mbar_wait(&k_empty[ks], kph ^ 1, "vf_attn producer(K)");
                     mbar_expect_tx(&k_full[ks], K_BYTES);
-                    tma_load_4d(sK + ks * K_BYTES, &p.tmK, &k_full[ks], 0, j * KT, h, b);
+                    tma_load_4d(sK + ks * K_BYTES, &p.tmK, &k_full[ks], 0, krow, h, b);
                     if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
                     mbar_wait(&v_empty[vs], vph ^ 1, "vf_attn producer(V)");
                     mbar_expect_tx(&v_full[vs], V_BYTES);
-                    tma_load_4d(sV + vs * V_BYTES, &p.tmV, &v_full[vs], j * KT, h * DH, b, 0);
+                    tma_load_4d(sV + vs * V_BYTES, &p.tmV, &v_full[vs], krow, h * DH, b, 0);
                     if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
                 }
             }
@@ -244,14 +263,22 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
                 uint32_t pk[32];
                 mbar_wait(&s_full[sb], use_parity(t), "vf_attn softmax(S)");
                 tc_fence_after();
-                if (kbase < vis_hi) {
+                bool warp_sees = kbase < vis_hi, partial = kbase + KT > vis_lo;
+                if (p.stream > 0) {                 // multi-end: whole 64-row halves see or do not see a tile, nothing is partially masked
+                    int krow;
+                    uint32_t halves;
+                    tile_at(q0, j, krow, halves);
+                    warp_sees = ((halves >> (quarter >> 1)) & 1u) != 0 && q0 + (quarter >> 1) * KT < p.S;
+                    partial = false;
+                }
+                if (warp_sees) {
                     uint32_t r[64];
                     tmem_ld64(tmem + lane_base + TM_S + sb * KT, r);
                     // S has been copied to registers: the buffer can take tile t + 2
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_empty[sb]);
-                    if (kbase + KT > vis_lo) {
+                    if (partial) {
 #pragma unroll
                         for (int i = 0; i < 64; ++i)
                             if (kbase + i >= vis) r[i] = 0xff800000u;                  // -inf
@@ -266,8 +293,10 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
                         for (int c = 0; c < 4; ++c) mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(r[i + c]), __uint_as_float(r[i + 4 + c])));
                     }
                     float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * LOG2E;      // log2 e > 0: the maximum commutes with the scaling
-                    if (j == 0) {
-                        m2 = mt;                       // nothing accumulated yet (every row sees key 0, so mt is finite)
+                    if (__all_sync(0xffffffffu, m2 == -INFINITY)) {
+                        // first tile these rows see: nothing accumulated for them yet (their accumulator rows are exact zeros or, at the
+                        // item's first tile, not yet written), so there is nothing to rescale
+                        m2 = mt;
                     } else {
                         const bool grow = mt > m2 + LAZY_LOG2;
                         if (__any_sync(0xffffffffu, grow)) {
@@ -352,10 +381,11 @@ unsigned idesc_bf16(int M, int N) { return make_idesc_16bit(1, M, N); }
 
 }  // namespace
 
-extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, int S, int H, int d, int block, int first_query, void* out,
-                                         vf_stream_t s);
+static int attn_launch(const void* qk, const void* vt, int B, int S, int n_streams, int stream, int H, int d, int block, int first_query,
+                       void* out, vf_stream_t s);
+
 extern "C" int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s) {
-    return vf_attn_block_causal_tail(qk, vt, B, S, H, d, block, 0, out, s);
+    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, 0, out, s);
 }
 
 // Only the query rows >= first_query (rounded down to a 128-row tile) are computed: with the context's q|k rows and V^T columns kept from
@@ -363,6 +393,22 @@ extern "C" int vf_attn_block_causal(const void* qk, const void* vt, int B, int S
 // score matrix in HBM.  Rows of `out` below the first computed tile are left untouched.
 extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, int S, int H, int d, int block, int first_query, void* out,
                                          vf_stream_t s) {
+    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, first_query, out, s);
+}
+
+// Branching (multi-end) attention, branching_attention.py:82-126: qk [B, n_streams * S, 2d] and V^T [B, d, n_streams * S] hold the streams
+// side by side.  stream = 0: block-causal attention of stream 0 over its own keys (as vf_attn_block_causal, reading the first S rows);
+// stream = s >= 1: a query of view t of stream s attends to the stream-0 keys of views < t and to the stream-s keys of view t, one joint
+// softmax.  out [B * S, d] receives that stream's attention output.  Streams >= 1 need block == 64 (one view per key tile).
+extern "C" int vf_attn_block_multiend(const void* qk, const void* vt, int B, int S, int n_streams, int stream, int H, int d, int block,
+                                      void* out, vf_stream_t s) {
+    VF_CHECK_ARG(n_streams >= 1 && stream >= 0 && stream < n_streams, "vf_attn_block_multiend: stream %d of %d", stream, n_streams);
+    VF_CHECK_ARG(stream == 0 || (block == KT && S % KT == 0), "vf_attn_block_multiend: streams >= 1 need 64 tokens per view (block=%d S=%d)", block, S);
+    return attn_launch(qk, vt, B, S, n_streams, stream, H, d, block, 0, out, s);
+}
+
+static int attn_launch(const void* qk, const void* vt, int B, int S, int n_streams, int stream, int H, int d, int block, int first_query,
+                       void* out, vf_stream_t s) {
     VF_CHECK_ARG(qk && vt && out, "vf_attn_block_causal: null pointer");
     VF_CHECK_ARG(first_query >= 0 && first_query < S, "vf_attn_block_causal: first_query out of range");
     VF_CHECK_ARG(H > 0 && d == H * DH, "vf_attn_block_causal: head dim must be 64 (d=%d H=%d)", d, H);
@@ -371,6 +417,8 @@ extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, 
     AttnParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.S = S; prm.H = H; prm.d = d; prm.block = block; prm.BH = B * H;
+    prm.stream = stream; prm.stream_rows = S;
+    const uint64_t rows_all = (uint64_t)n_streams * S;          // rows of qk / columns of V^T per batch element (all streams)
     prm.qt0 = first_query / QT;
     prm.n_qtiles = (S + QT - 1) / QT - prm.qt0;
     prm.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -378,16 +426,16 @@ extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, 
     int rc;
     const uint64_t row = (uint64_t)2 * d * 2;                  // bytes per qk row
     {   // Q / K: [B, S, 2d] viewed as (dh, S, H, B); K is the second half of every row
-        const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)S, (uint64_t)H, (uint64_t)B};
-        const uint64_t str[3] = {row, (uint64_t)DH * 2, row * S};
+        const uint64_t dims[4] = {(uint64_t)DH, rows_all, (uint64_t)H, (uint64_t)B};
+        const uint64_t str[3] = {row, (uint64_t)DH * 2, row * rows_all};
         const uint32_t boxq[4] = {(uint32_t)DH, (uint32_t)QT, 1, 1};
         const uint32_t boxk[4] = {(uint32_t)DH, (uint32_t)KT, 1, 1};
         if ((rc = make_tmap_16bit(&prm.tmQ, qk, dims, str, boxq)) != VF_OK) return rc;
         if ((rc = make_tmap_16bit(&prm.tmK, reinterpret_cast<const __nv_bfloat16*>(qk) + d, dims, str, boxk)) != VF_OK) return rc;
     }
     {   // V^T: [B, d, S] viewed as (S, d, B, 1); one box = 64 keys x 64 dh rows
-        const uint64_t dims[4] = {(uint64_t)S, (uint64_t)d, (uint64_t)B, 1};
-        const uint64_t str[3] = {(uint64_t)S * 2, (uint64_t)S * 2 * d, (uint64_t)S * 2 * d * B};
+        const uint64_t dims[4] = {rows_all, (uint64_t)d, (uint64_t)B, 1};
+        const uint64_t str[3] = {rows_all * 2, rows_all * 2 * d, rows_all * 2 * d * B};
         const uint32_t box[4] = {(uint32_t)KT, (uint32_t)DH, 1, 1};
         if ((rc = make_tmap_16bit(&prm.tmV, vt, dims, str, box)) != VF_OK) return rc;
     }

@@ -217,6 +217,9 @@ class MIGT:
         if ns == 1 and prec.opd == torch.bfloat16 and dh == 64 and self.fused_attention:
             # single-stream forward (the generate() hot path): one fused tcgen05 kernel, no S x S tensor in HBM
             return [L.attn_block_causal(qk, vt, B, S, H, d, Lt)]
+        if ns > 1 and prec.opd == torch.bfloat16 and dh == 64 and Lt == 64 and self.fused_attention:
+            # 3-stream forward (multi-context generation, localisation): the same fused kernel with the multi-end key-tile schedule
+            return [L.attn_block_multiend(qk, vt, B, S, ns, s, H, d, Lt) for s in range(ns)]
         outs = []
         for s in range(ns):
             if s == 0:
