@@ -197,6 +197,15 @@ int vf_groupnorm_bwd(const float* x, const float* dout, const float* mean_rstd, 
 int vf_softmax_bwd_rows(const float* P, const float* dP, int64_t rows, int cols, float* dS, vf_stream_t s);
 int vf_l1_grad(const float* x, const float* y, int64_t n, float scale, float* dy, double* loss_sum, vf_stream_t s);
 int vf_lincomb3(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out, vf_stream_t s);
+/* Tensor-core weight gradient of a 3x3 stride-1 convolution = exact split-fp16 GEMMs with K = pixels (vf_tc_gemm, gemm mode with
+ * ntaps = batch1 = 3: tap_coff[ky] shifts the K coordinate of the activation operand by whole rows of the padded grid; the three horizontal
+ * shifts are three row blocks of the operand, so M = 3 Cin).  vf_pad_transpose_split lays an NHWC fp32 tensor out as that K-major split
+ * operand, fp16 [copies*C][2][L], over the zero-padded pixel grid of row pitch `pitch` (a multiple of 8: TMA box starts stay 16-byte
+ * aligned): column margin + ((n (H+2) + y + 1) pitch + x + 1) - (k - copies/2) of copy k; the caller clears the buffer.
+ * vf_sum_splits folds the split-K partial products: out[g*n + i] (+)= sum_s partial[(g*splits + s)*n + i]. */
+int vf_pad_transpose_split(const float* x_nhwc, int N, int H, int W, int C, int pitch, int copies, int64_t margin, int64_t L, void* out_f16,
+                           vf_stream_t s);
+int vf_sum_splits(const float* partial, int groups, int splits, int64_t n, int accumulate, float* out, vf_stream_t s);
 int vf_sumpool2x2(const float* x, int N, int H, int W, int C, float* y, vf_stream_t s);
 int vf_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, int step,
             float grad_scale, vf_stream_t s);

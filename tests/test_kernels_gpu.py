@@ -770,3 +770,30 @@ def test_cta_pair_mma_path_matches_single_cta():
             assert float(l.split()[2]) < 2e-2, l
     # the accumulation order inside a tile is the same (K blocks in order, fp32 TMEM accumulators): identical sums
     assert outs["0"] == outs["1"]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 128, 128), (3, 8, 8, 256, 128), (1, 32, 24, 128, 256), (5, 8, 8, 128, 128)])
+def test_conv_weight_gradient_on_tensor_cores(L, n, h, w, cin, cout):
+    """conv_wgrad_tc (nine exact split-fp16 GEMMs over the zero-padded, transposed pixel axis, K offsets per tap, split-K) == the fp64
+    weight gradient of a 3x3 stride-1 pad-1 convolution, and agrees with the fp32 CUDA-core atomics kernel."""
+    gg = g(n * 100 + h + cin)
+    x = torch.randn(n, h, w, cin, generator=gg)
+    dy = torch.randn(n, h, w, cout, generator=gg)
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(False)
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(xd, wt, padding=1)
+    y.backward(dy.double().permute(0, 3, 1, 2))
+    want = wt.grad.permute(2, 3, 1, 0).reshape(9 * cin, cout)             # [tap*Cin + c, Cout]
+    dw = torch.zeros(9 * cin, cout, device="cuda")
+    L.conv_wgrad_tc(x.cuda(), dy.cuda(), dw)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = float((dw.double().cpu() - want).abs().max()) / scale
+    dw32 = torch.zeros(9 * cin, cout, device="cuda")
+    L.conv_wgrad(x.cuda(), dy.cuda(), dw32, kh=3)
+    err32 = float((dw32.double().cpu() - want).abs().max()) / scale
+    print(f"[conv_wgrad_tc n{n} {h}x{w} {cin}->{cout}] max err / max|dW|: tensor-core exact {err:.2e}, fp32 atomics {err32:.2e}")
+    assert err < 5e-6 and err32 < 5e-5
+    # accumulate semantics
+    L.conv_wgrad_tc(x.cuda(), dy.cuda(), dw)
+    assert float((dw.double().cpu() - 2 * want).abs().max()) / scale < 1e-5

@@ -25,7 +25,7 @@ EXPORTS = [
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal", "vf_attn_block_causal_tail", "vf_attn_block_multiend",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
-    "vf_conv_wgrad", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
+    "vf_conv_wgrad", "vf_pad_transpose_split", "vf_sum_splits", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
     "vf_layernorm_bwd", "vf_gelu_fwd", "vf_gelu_bwd", "vf_migt_embed_bwd", "vf_cross_entropy_grad", "vf_pose_loss_grad", "vf_adamw_keras", "vf_sumsq", "vf_dropout",
 ]
 
@@ -351,7 +351,7 @@ def simt_gemm(A, B, out, *, M, N, K, a_strides, b_strides, ldc, batch=(1, 1), a_
 
 def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), alpha=1.0,
             bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, residual=None, a_off=0, b_off=0, c_off=0, causal_block=0,
-            causal_skip_n=False, out2=None, gn_rows_per_img=0, gn_groups=32, lo_a=None, lo_b=None):
+            causal_skip_n=False, out2=None, gn_rows_per_img=0, gn_groups=32, lo_a=None, lo_b=None, k_offsets=None):
     """tcgen05 GEMM: C[m,n] = act(alpha*sum_k A[m,k] B[n,k] + bias) + residual; A,B K-major bf16 (or f32 -> TF32).
     ``out2`` optionally receives a second copy in the other dtype (f32 + bf16 from one epilogue).
     float16 operands = split-fp16 pairs (exact mode): a row holds hi(K) at column 0 and lo(K) at column ``lo_a`` / ``lo_b``."""
@@ -369,6 +369,11 @@ def tc_gemm(A, B, out, *, M, N, K, lda, ldb, ldc, batch=(1, 1), a_bs=(0, 0), b_b
     p.b_sb1, p.b_sb2 = b_bs
     p.c_sb1, p.c_sb2 = c_bs
     p.causal_block, p.causal_skip_n = causal_block, int(causal_skip_n)
+    if k_offsets is not None:            # batch1 index b reads A shifted by k_offsets[b] elements along K (vf_tc_gemm_t.ntaps in gemm mode)
+        assert len(k_offsets) == batch[0] <= 9
+        p.ntaps = len(k_offsets)
+        for i, o in enumerate(k_offsets):
+            p.tap_coff[i] = int(o)
     p.alpha = alpha
     p.bias, p.bias_mode = (bias.data_ptr(), bias_mode) if bias is not None else (None, BIAS_NONE)
     p.act = act
@@ -775,6 +780,43 @@ def conv_wgrad(x, dy, dw, *, kh, stride=1, pad=(1, 1), upsample=False, so=None):
     so_k, so_n = (cout, 1) if so is None else so
     _check(lib.vf_conv_wgrad(_p(x), _p(dy), n, h, w, cin, oh, ow, cout, kh, kh, stride, pad[0], pad[1], int(upsample), C.c_int64(so_k),
                              C.c_int64(so_n), _p(dw), _stream()))
+    return dw
+
+
+def conv_wgrad_tc_ok(x, dy, kh, stride, upsample):
+    n, h, w, cin = x.shape
+    return kh == 3 and stride == 1 and not upsample and cin % 128 == 0 and dy.shape[-1] % 128 == 0 and dy.shape[1:3] == x.shape[1:3]
+
+
+def conv_wgrad_tc(x, dy, dw, *, accumulate=True):
+    """Weight gradient of a 3x3 stride-1 pad-1 convolution on the exact split-fp16 tensor-core GEMM.  x [N,H,W,Cin], dy [N,H,W,Cout] fp32;
+    dw [9*Cin, Cout] (k = (ky*3 + kx)*Cin + c).  dW[ky,kx][c, co] = sum_q xpad[c, q + (ky-1) pitch + (kx-1)] * dypad[co, q] over the
+    zero-padded pixel grid: both operands are transposed to K-major split form, the horizontal shifts are three row blocks of the activation
+    operand (M = 3 Cin), the vertical ones are K offsets of whole (8-aligned) rows, the pixel axis is split over the SMs and the partial
+    products are folded by vf_sum_splits."""
+    lib = load(True)
+    _dev(x, torch.float32); _dev(dy, torch.float32); _dev(dw, torch.float32)
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    pitch = (w + 2 + 7) // 8 * 8
+    ppad = n * (h + 2) * pitch
+    tiles = (3 * cin // 128) * (cout // 128)
+    splits = max(1, min(64, (148 + 3 * tiles - 1) // (3 * tiles)))
+    kc = (ppad + splits - 1) // splits
+    kc = (kc + 63) // 64 * 64                                  # the exact GEMM walks K in blocks of 64
+    kpad = kc * splits
+    margin = pitch + 8                                          # multiple of 8, >= pitch + 1
+    la = kpad + 2 * margin
+    lb = kpad
+    at = torch.zeros((3 * cin, 2, la), dtype=torch.float16, device=x.device)
+    bt = torch.zeros((cout, 2, lb), dtype=torch.float16, device=x.device)
+    _check(lib.vf_pad_transpose_split(_p(x), n, h, w, cin, pitch, 3, C.c_int64(margin), C.c_int64(la), _p(at), _stream()))
+    _check(lib.vf_pad_transpose_split(_p(dy), n, h, w, cout, pitch, 1, C.c_int64(0), C.c_int64(lb), _p(bt), _stream()))
+    partial = torch.empty((3, splits, 3 * cin, cout), dtype=torch.float32, device=x.device)
+    offs = [margin - pitch, margin, margin + pitch]
+    tc_gemm(at, bt, partial, M=3 * cin, N=cout, K=kc, lda=2 * la, ldb=2 * lb, ldc=cout, batch=(3, splits), a_bs=(0, kc), b_bs=(0, kc),
+            c_bs=(splits * 3 * cin * cout, 3 * cin * cout), lo_a=la, lo_b=lb, k_offsets=offs)
+    _check(lib.vf_sum_splits(_p(partial), 3, splits, C.c_int64(3 * cin * cout), int(accumulate), _p(dw), _stream()))
     return dw
 
 

@@ -10,6 +10,7 @@
 //   vf_sumpool2x2          backward of the nearest x2 upsampling
 //   vf_adam                torch.optim.Adam step (betas (0.5, 0.9) at the call site) over a flat parameter / gradient buffer
 #include "vf_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -113,10 +114,12 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
                                                            int groups, int swish, int pix_per_block, double* __restrict__ gsums,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    extern __shared__ double shg[];           // [groups][2]
+    extern __shared__ double shg[];           // [groups][2] doubles, then [2][C] floats (per-channel dbeta / dgamma of this block)
+    float* shc = reinterpret_cast<float*>(shg + 2 * groups);
     const int quads = C >> 2, lanes = 256 / quads;
     const int cq = threadIdx.x % quads, pl = threadIdx.x / quads, n = blockIdx.y, cpg = C / groups;
     for (int i = threadIdx.x; i < groups * 2; i += 256) shg[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * C; i += 256) shc[i] = 0.f;
     __syncthreads();
     float mu[4], rs[4], ga[4], be[4], s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     if (pl < lanes) {
@@ -143,14 +146,19 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = cq * 4 + j;
-            atomicAdd(dbeta + c, s1[j]);
-            atomicAdd(dgamma + c, s2[j]);
+            // the block's pixel lanes meet in shared memory first: one global atomic per (block, channel) instead of one per thread
+            atomicAdd(shc + c, s1[j]);
+            atomicAdd(shc + C + c, s2[j]);
             atomicAdd(&shg[(c / cpg) * 2 + 0], (double)(s1[j] * ga[j]));
             atomicAdd(&shg[(c / cpg) * 2 + 1], (double)(s2[j] * ga[j]));
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < groups * 2; i += 256) atomicAdd(gsums + (long long)n * groups * 2 + i, shg[i]);
+    for (int c = threadIdx.x; c < C; c += 256) {
+        atomicAdd(dbeta + c, shc[c]);
+        atomicAdd(dgamma + c, shc[C + c]);
+    }
 }
 
 // pass 2: dx = rstd * (dg*gamma - mean(dg*gamma) - xhat * mean(dg*gamma*xhat)) [+ add]
@@ -417,7 +425,83 @@ __global__ void dropout_kernel(const float* __restrict__ x, long long n, float r
         y[i] = mix32(seed * 0x9E3779B97F4A7C15ULL + (unsigned long long)i) >= thr ? x[i] * sc : 0.f;
 }
 
+// ---- operands of the tensor-core weight gradient (vf_tc_gemm, exact split-fp16 GEMM with K = pixels) ----
+// x NHWC fp32 [N,H,W,C] -> out fp16 [copies * C][2][L]: row (k * C + c) holds hi(x) at [0, L) and lo(x) at [L, 2L) (the exact GEMM's split
+// operand), indexed by the linear position q = (n (H+2) + y + 1) * pitch + x + 1 of the ZERO-PADDED image (row pitch >= W + 2).  Copy k
+// (k = 0 .. copies-1) is shifted by k - copies/2 pixels: column margin + q - (k - copies/2) <- x[n,y,x,c], so that reading copy k at
+// column margin + q yields xpad[q + (k - copies/2)].  TMA wants 16-byte aligned box starts, hence the horizontal tap shifts are baked into
+// three copies and only the vertical ones (multiples of the pitch, a multiple of 8) are left to the GEMM's K offsets.
+// Everything that is not written here (borders, pitch padding, margins, tail) must be zero — callers clear the buffer first.
+// Tile: 32 channels x 64 pixels through shared memory (coalesced 128-byte reads along C, contiguous writes along q).
+__global__ void __launch_bounds__(256) pad_transpose_split_kernel(const float* __restrict__ x, int N, int H, int W, int C, int pitch, int copies,
+                                                                  long long margin, long long L, __half* __restrict__ out) {
+    __shared__ float tile[64][33];
+    const long long p0 = (long long)blockIdx.x * 64;             // first unpadded pixel (n, y, x flattened) of the tile
+    const int c0 = blockIdx.y * 32;
+    const long long P = (long long)N * H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < 64; i += 8) {
+        const long long pix = p0 + i;
+        tile[i][lane] = (pix < P && c0 + lane < C) ? x[pix * C + c0 + lane] : 0.f;
+    }
+    __syncthreads();
+    for (int cc = warp; cc < 32; cc += 8) {
+        if (c0 + cc >= C) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            const long long pix = p0 + i;
+            if (pix >= P) continue;
+            const int xx = (int)(pix % W);
+            const long long t = pix / W;
+            const int yy = (int)(t % H);
+            const long long n = t / H;
+            const long long q = (n * (H + 2) + yy + 1) * (long long)pitch + xx + 1;
+            const float v = tile[i][cc];
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn((v - __half2float(hi)) * 2048.0f);
+            for (int k = 0; k < copies; ++k) {
+                __half* row = out + ((long long)k * C + c0 + cc) * 2 * L;
+                const long long col = margin + q - (k - copies / 2);
+                row[col] = hi;
+                row[L + col] = lo;
+            }
+        }
+    }
+}
+
+// out[g * n + i] (+)= sum_s partial[(g * splits + s) * n + i]   — folds the split-K partial products of the weight-gradient GEMM
+__global__ void sum_splits_kernel(const float* __restrict__ partial, int groups, int splits, long long n, int accumulate, float* __restrict__ out) {
+    const long long total = (long long)groups * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i / n, r = i - g * n;
+        const float* src = partial + (g * splits) * n + r;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += src[(long long)s * n];
+        out[i] = accumulate ? out[i] + acc : acc;
+    }
+}
+
 }  // namespace
+
+extern "C" int vf_pad_transpose_split(const float* x, int N, int H, int W, int C, int pitch, int copies, int64_t margin, int64_t L,
+                                      void* out_f16, vf_stream_t s) {
+    VF_CHECK_ARG(x && out_f16 && N > 0 && H > 0 && W > 0 && C > 0, "vf_pad_transpose_split: bad args");
+    VF_CHECK_ARG(pitch >= W + 2 && (copies == 1 || copies == 3) && margin >= copies / 2, "vf_pad_transpose_split: pitch / copies / margin");
+    VF_CHECK_ARG(L >= margin + (int64_t)N * (H + 2) * pitch + copies / 2, "vf_pad_transpose_split: row length L too small");
+    const long long P = (long long)N * H * W;
+    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 31) / 32));
+    pad_transpose_split_kernel<<<grid, 256, 0, vf_s(s)>>>(x, N, H, W, C, pitch, copies, margin, L, reinterpret_cast<__half*>(out_f16));
+    VF_CHECK_LAUNCH("vf_pad_transpose_split");
+    return VF_OK;
+}
+extern "C" int vf_sum_splits(const float* partial, int groups, int splits, int64_t n, int accumulate, float* out, vf_stream_t s) {
+    VF_CHECK_ARG(partial && out && groups > 0 && splits > 0 && n > 0, "vf_sum_splits: bad args");
+    { long long tot_ = (long long)groups * n; unsigned g_ = (unsigned)((tot_ + 255) / 256 < 148 * 16 ? (tot_ + 255) / 256 : 148 * 16);
+    sum_splits_kernel<<<g_, 256, 0, vf_s(s)>>>(partial, groups, splits, n, accumulate, out); }
+    VF_CHECK_LAUNCH("vf_sum_splits");
+    return VF_OK;
+}
 
 extern "C" int vf_conv_wgrad(const float* x, const float* dy, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
                              int stride, int pad_t, int pad_l, int upsample2x, int64_t so_k, int64_t so_n, float* dw, vf_stream_t s) {
@@ -459,12 +543,15 @@ extern "C" int vf_groupnorm_bwd(const float* x, const float* dout, const float* 
     cudaError_t e = cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * groups * N, vf_s(s));
     if (e != cudaSuccess) { vf_set_error("vf_groupnorm_bwd: memset: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     const int lanes = 256 / (C / 4);
-    int ppb = lanes * 16;
-    while (ppb > lanes * 4 && (long long)((HW + ppb - 1) / ppb) * N < 148 * 8) ppb >>= 1;
+    int ppb = lanes * 128;          // few, long blocks: the per-channel sums end in global atomics
+    while (ppb > lanes * 4 && (long long)((HW + ppb - 1) / ppb) * N < 148 * 4) ppb >>= 1;
     dim3 grid((HW + ppb - 1) / ppb, N);
-    gn_bwd_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, vf_s(s)>>>(x, dout, mean_rstd, gamma, beta, HW, C, groups, swish, ppb, gsums, dgamma, dbeta);
+    gn_bwd_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups + sizeof(float) * 2 * C, vf_s(s)>>>(x, dout, mean_rstd, gamma, beta, HW, C, groups, swish, ppb, gsums, dgamma, dbeta);
     VF_CHECK_LAUNCH("vf_groupnorm_bwd(stats)");
-    gn_bwd_apply_kernel<<<grid, 256, 0, vf_s(s)>>>(x, dout, mean_rstd, gamma, beta, gsums, add, HW, C, groups, swish, ppb, dx);
+    int ppb2 = lanes * 16;          // the streaming pass keeps many short blocks in flight
+    while (ppb2 > lanes * 4 && (long long)((HW + ppb2 - 1) / ppb2) * N < 148 * 8) ppb2 >>= 1;
+    dim3 grid2((HW + ppb2 - 1) / ppb2, N);
+    gn_bwd_apply_kernel<<<grid2, 256, 0, vf_s(s)>>>(x, dout, mean_rstd, gamma, beta, gsums, add, HW, C, groups, swish, ppb2, dx);
     VF_CHECK_LAUNCH("vf_groupnorm_bwd(apply)");
     return VF_OK;
 }

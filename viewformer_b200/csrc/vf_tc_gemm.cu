@@ -41,6 +41,7 @@ struct TcParams {
     // conv tiling
     int TW, TH, TN, tiles_x, tiles_y, OH, OW, Nimg, cin_blocks, bk_elems;
     int tap_dy[9], tap_dx[9], tap_coff[9];
+    int gemm_koff;             // gemm mode: tap_coff[b1] is added to the K coordinate of A for batch1 index b1 (shifted views of one operand)
     int causal_block, causal_skip_n;
     float alpha;
     const float* bias;
@@ -483,6 +484,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                                 kcoord_a = (j == 0 ? p.exact_clog : 0) + kbr * p.bk_elems;
                                 kcoord_b = (j == 1 ? p.exact_lo_b : 0) + kbr * p.bk_elems;
                             }
+                            if (p.gemm_koff) kcoord_a += p.tap_coff[ti.b1];
                             load(sa, &p.tmA, &full_bar[stage], kcoord_a, ti.m0, ti.b2 * p.a_bm2, ti.b1 * p.a_bm1);
                         }
                         load(sb, &p.tmB, &full_bar[stage], kcoord_b, ti.n0 + n_off, ti.b2 * p.b_bm2, ti.b1 * p.b_bm1);
@@ -1909,6 +1911,18 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
             prm.num_k_blocks *= 3;
         }
         prm.c_sb1 = q->c_sb1; prm.c_sb2 = q->c_sb2;
+        // ntaps > 0 in gemm mode: batch1 index b reads A shifted by tap_coff[b] >= 0 elements along K (one operand, several shifted
+        // views — the weight gradient of a 3x3 convolution over a transposed, zero-padded activation: vf_conv_wgrad_tc)
+        long long max_koff = 0;
+        if (q->ntaps > 0) {
+            VF_CHECK_ARG(q->ntaps == q->batch1 && q->ntaps <= 9, "vf_tc_gemm: gemm K offsets need ntaps == batch1 <= 9");
+            prm.gemm_koff = 1;
+            for (int t = 0; t < q->ntaps; ++t) {
+                VF_CHECK_ARG(q->tap_coff[t] >= 0 && q->tap_coff[t] % 8 == 0, "vf_tc_gemm: K offsets must be non-negative multiples of 8 (16-byte TMA box starts)");
+                prm.tap_coff[t] = q->tap_coff[t];
+                if (q->tap_coff[t] > max_koff) max_koff = q->tap_coff[t];
+            }
+        }
         // an operand with batch stride 0 is shared by every batch: its tensor map gets a size-1 batch dim and the
         // kernel multiplies the batch coordinate by 0
         prm.a_bm1 = (q->batch1 > 1 && q->a_sb1 != 0) ? 1 : 0;
@@ -1916,7 +1930,7 @@ extern "C" int vf_tc_gemm(const vf_tc_gemm_t* q, vf_stream_t s) {
         prm.b_bm1 = (q->batch1 > 1 && q->b_sb1 != 0) ? 1 : 0;
         prm.b_bm2 = (q->batch2 > 1 && q->b_sb2 != 0) ? 1 : 0;
         const uint64_t fbA = (uint64_t)q->lda * es * (uint64_t)q->M, fbB = (uint64_t)q->ldb * es * (uint64_t)q->Ncols;
-        const uint64_t dimsA[4] = {(uint64_t)(exact ? q->exact_lo_a + q->K : q->K), (uint64_t)q->M, prm.a_bm2 ? (uint64_t)q->batch2 : 1, prm.a_bm1 ? (uint64_t)q->batch1 : 1};
+        const uint64_t dimsA[4] = {(uint64_t)((exact ? q->exact_lo_a + q->K : q->K) + max_koff), (uint64_t)q->M, prm.a_bm2 ? (uint64_t)q->batch2 : 1, prm.a_bm1 ? (uint64_t)q->batch1 : 1};
         const uint64_t strA[3] = {(uint64_t)q->lda * es, prm.a_bm2 ? (uint64_t)q->a_sb2 * es : fbA, prm.a_bm1 ? (uint64_t)q->a_sb1 * es : fbA};
         const uint32_t boxA[4] = {(uint32_t)bk, (uint32_t)BLOCK_M, 1, 1};
         if ((rc = make_tmap(&prm.tmA, tm_dtype, q->A, dimsA, strA, boxA)) != VF_OK) return rc;

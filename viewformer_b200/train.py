@@ -18,8 +18,9 @@ Activations needed by the backward pass are kept on a tape; GroupNorm+swish outp
 
 Arithmetic: fp32 throughout, as the reference requires.  The 3x3 stride-1 convolutions with tensor-core-sized channel counts run
 their forward pass and their data gradient on the exact split-fp16 tcgen05 kernels (fp32-faithful results from three fp16 MMA passes,
-DESIGN.md 5.3; ``VF_TRAIN_TC=0`` keeps everything on the CUDA cores); weight gradients, strided / upsampling convs and 1x1 layers use
-the fp32 CUDA-core kernels.
+DESIGN.md 5.3; ``VF_TRAIN_TC=0`` keeps everything on the CUDA cores), and their weight gradient as nine exact GEMMs over the pixel axis
+(``_lib.conv_wgrad_tc``) when both channel counts are multiples of 128; strided / upsampling convs, 1x1 layers and the remaining weight
+gradients use the fp32 CUDA-core kernels.
 """
 import math
 import os
@@ -189,7 +190,8 @@ class VQGANTrainer:
     # passes, chunked accumulation: fp32-faithful results, DESIGN.md 5.3) in the forward pass and in the data gradient; everything else
     # (conv_in / conv_out, stride-2 and upsampling convs, 1x1 layers) and every weight gradient stays on the fp32 CUDA-core kernels.
     def _tc_ok(self, cw, stride, upsample):
-        return self.use_tc and cw.k == 3 and stride == 1 and not upsample and cw.cin % 64 == 0 and cw.cout % 64 == 0
+        """3x3 stride-1 convs, incl. the Upsample convs (nearest x2, then a stride-1 conv on the doubled map: vqgan_th.py:29-32)."""
+        return self.use_tc and cw.k == 3 and stride == 1 and cw.cin % 64 == 0 and cw.cout % 64 == 0
 
     def _split_weight(self, key, w_kn, n_out):
         """[K, n_out] fp32 (K = tap * C + c) -> split-fp16 [n_out, tap * 2C] for L.tc_conv; cached until the next optimizer step."""
@@ -209,14 +211,22 @@ class VQGANTrainer:
 
     def _conv_fw(self, cw, a, residual=None, stride=1, upsample=False):
         if self._tc_ok(cw, stride, upsample):
-            return L.tc_conv(self._split_act(a), self._split_weight(("fw", id(cw)), cw.w_kn, cw.cout), cw.bias, residual=residual)
+            a_split = (L.groupnorm(a, None, None, swish=False, out_dtype=torch.float16, normalize=False, upsample=True) if upsample
+                       else self._split_act(a))
+            return L.tc_conv(a_split, self._split_weight(("fw", id(cw)), cw.w_kn, cw.cout), cw.bias, residual=residual)
         return self.model._conv(cw, a, residual=residual, stride=stride, upsample=upsample, stats=False)
 
     def _conv_bw(self, name, cw, a, dy, stride=1, upsample=False, need_dx=True):
         """a: the conv's input (NHWC f32); dy: gradient of its output.  Accumulates dW, db; returns dx (or None)."""
         P = self.P
         pad = ((1, 1) if stride == 1 else (0, 0)) if cw.k == 3 else (0, 0)
-        L.conv_wgrad(a, dy, P[name + ".weight"].grad, kh=cw.k, stride=stride, pad=pad, upsample=upsample)
+        if self.use_tc and upsample and L.conv_wgrad_tc_ok(dy, dy, cw.k, stride, False) and cw.cin % 128 == 0:
+            a_up = L.groupnorm(a, None, None, swish=False, out_dtype=torch.float32, normalize=False, upsample=True)
+            L.conv_wgrad_tc(a_up, dy, P[name + ".weight"].grad)
+        elif self.use_tc and L.conv_wgrad_tc_ok(a, dy, cw.k, stride, upsample):
+            L.conv_wgrad_tc(a, dy, P[name + ".weight"].grad)             # exact split-fp16 GEMMs over the pixel axis (K = pixels)
+        else:
+            L.conv_wgrad(a, dy, P[name + ".weight"].grad, kh=cw.k, stride=stride, pad=pad, upsample=upsample)
         L.col_sums(dy.reshape(-1, cw.cout), P[name + ".bias"].grad)
         self._grad_ready(P[name + ".bias"]); self._grad_ready(P[name + ".weight"])
         if not need_dx:
@@ -230,7 +240,8 @@ class VQGANTrainer:
             if key not in self._wsplit:                         # a data gradient is a conv with flipped taps and swapped channel roles
                 wd = wk.flip(0, 1).permute(0, 1, 3, 2).reshape(cw.k * cw.k * cw.cout, cw.cin).contiguous()
                 self._split_weight(key, wd, cw.cin)
-            return L.tc_conv(self._split_act(dy), self._wsplit[key], None)
+            dx = L.tc_conv(self._split_act(dy), self._wsplit[key], None)
+            return L.sumpool2x2(dx) if upsample else dx
         wd = wk.flip(0, 1).permute(0, 1, 3, 2).reshape(cw.k * cw.k * cw.cout, cw.cin).contiguous()      # a data gradient is a conv with flipped taps
         dx = L.simt_conv(dy, wd, None, kh=cw.k, stride=1, pad=(1, 1) if cw.k == 3 else (0, 0))
         return L.sumpool2x2(dx) if upsample else dx
