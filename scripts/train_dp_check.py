@@ -21,6 +21,9 @@ B = 4 * world
 x = vq_images(B, cfg.image_size, 123)
 tr = VQGANTrainer(VQGAN(cfg, precision="fp32", device=f"cuda:{local}").load_state_dict(sd), bucket_bytes=1 << 18)
 loss = tr.forward_backward(x[rank * 4:(rank + 1) * 4])
+for h in tr._handles:
+    h.wait()
+g_dp = tr.flat_g.clone() / world                 # the optimizer applies the same 1 / world (DDP gradient average)
 tr.optimizer_step()
 torch.cuda.synchronize()
 mine = tr.export_state_dict()
@@ -41,14 +44,17 @@ if world > 1:
     _orig = vdist.allreduce_ema_stats
     vdist.allreduce_ema_stats = lambda c, e, group=None: (c, e)          # the solo run must not exchange EMA statistics
     l1 = tr1.forward_backward(x)
+    g_full = tr1.flat_g.clone()
     tr1.optimizer_step()
     vdist.allreduce_ema_stats = _orig
     torch.cuda.synchronize()
     solo = tr1.export_state_dict()
     if rank == 0:
         worst = max(float((mine[k].float() - solo[k].float()).abs().max()) for k in solo if solo[k].dtype.is_floating_point)
+        grel = float((g_dp - g_full).norm() / g_full.norm())
         print(f"[dp check] world {world}: mean loss over ranks {lmean:.6f} vs single-GPU full batch {float(l1):.6f}; "
-              f"max |weight difference| after one step {worst:.3e} (lr {cfg.learning_rate})")
+              f"gradient |g_dp - g_full| / |g_full| = {grel:.2e}; max |weight difference| after one Adam step {worst:.3e} (lr {cfg.learning_rate}; "
+              f"Adam's first step moves every weight by ~lr * sign(g), so elements whose true gradient is zero differ by up to lr)")
     dist.barrier()
 # ---- full-size step timing (BASELINE config 4 shape: 32 images per GPU, fp32)
 fcfg = VQGANConfig(perceptual_weight=0.0)

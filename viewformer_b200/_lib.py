@@ -783,6 +783,9 @@ def conv_wgrad(x, dy, dw, *, kh, stride=1, pad=(1, 1), upsample=False, so=None):
     return dw
 
 
+_wgrad_bufs = {}
+
+
 def conv_wgrad_tc_ok(x, dy, kh, stride, upsample):
     n, h, w, cin = x.shape
     return kh == 3 and stride == 1 and not upsample and cin % 128 == 0 and dy.shape[-1] % 128 == 0 and dy.shape[1:3] == x.shape[1:3]
@@ -808,11 +811,19 @@ def conv_wgrad_tc(x, dy, dw, *, accumulate=True):
     margin = pitch + 8                                          # multiple of 8, >= pitch + 1
     la = kpad + 2 * margin
     lb = kpad
-    at = torch.zeros((3 * cin, 2, la), dtype=torch.float16, device=x.device)
-    bt = torch.zeros((cout, 2, lb), dtype=torch.float16, device=x.device)
+    # operand buffers are cached per shape: the transposer rewrites every interior position on each call and never touches the zero
+    # borders / pitch padding / margins, so they are cleared once
+    key = (x.device, n, h, w, cin, cout)
+    bufs = _wgrad_bufs.get(key)
+    if bufs is None:
+        if len(_wgrad_bufs) >= 32:
+            _wgrad_bufs.clear()
+        bufs = (torch.zeros((3 * cin, 2, la), dtype=torch.float16, device=x.device), torch.zeros((cout, 2, lb), dtype=torch.float16, device=x.device),
+                torch.empty((3, splits, 3 * cin, cout), dtype=torch.float32, device=x.device))
+        _wgrad_bufs[key] = bufs
+    at, bt, partial = bufs
     _check(lib.vf_pad_transpose_split(_p(x), n, h, w, cin, pitch, 3, C.c_int64(margin), C.c_int64(la), _p(at), _stream()))
     _check(lib.vf_pad_transpose_split(_p(dy), n, h, w, cout, pitch, 1, C.c_int64(0), C.c_int64(lb), _p(bt), _stream()))
-    partial = torch.empty((3, splits, 3 * cin, cout), dtype=torch.float32, device=x.device)
     offs = [margin - pitch, margin, margin + pitch]
     tc_gemm(at, bt, partial, M=3 * cin, N=cout, K=kc, lda=2 * la, ldb=2 * lb, ldc=cout, batch=(3, splits), a_bs=(0, kc), b_bs=(0, kc),
             c_bs=(splits * 3 * cin * cout, 3 * cin * cout), lo_a=la, lo_b=lb, k_offsets=offs)
