@@ -761,10 +761,10 @@ def test_cta_pair_mma_path_matches_single_cta():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     for flag in ("0", "1"):
-        env = dict(os.environ, VF_TC_2CTA=flag)
+        env = dict(os.environ, VF_TC_2CTA=flag, VF_TC_WIDE2=flag)
         r = subprocess.run([sys.executable, os.path.join(root, "scripts", "two_cta_check.py")], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        outs[flag] = [l for l in r.stdout.splitlines() if l.startswith(("gemm", "conv"))]
+        outs[flag] = [l for l in r.stdout.splitlines() if l.startswith(("gemm", "conv", "wide"))]
         print(f"[VF_TC_2CTA={flag}]", " | ".join(outs[flag]))
         for l in outs[flag]:
             assert float(l.split()[2]) < 2e-2, l

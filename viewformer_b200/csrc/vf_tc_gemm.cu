@@ -160,6 +160,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope: sees the peer CTA's arrivals
+    for (uint32_t i = 0; i < (1u << 24); ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    printf("vf_tc_gemm: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
 // both CTAs of the pair issue their own load; the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
 __device__ __forceinline__ uint32_t leader_addr(const void* p) {      // shared::cluster address of the same location in CTA 0
     uint32_t ra;
@@ -1325,6 +1335,7 @@ tc_conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
 struct WideGemmParams {
     CUtensorMap tmW;           // weights [Nf, K]: box {bk, 128}
     CUtensorMap tmX;           // rows    [M, K]:  box {bk, 256}
+    CUtensorMap tmX2;          // pair kernel: the same rows with a 128-row box (each CTA loads half of the 256 rows)
     const float* bias;         // [Nf] or null
     const float* residual;     // [M, ldc] fp32 or null
     float* C_f32;
@@ -1357,7 +1368,10 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 
 // kGelu / kBf16Out are compile-time so that each instantiation carries one epilogue (the fully unrolled runtime-switched version
 // was ~13k instructions and ran out of the instruction cache: 30k cycles per tile)
-template <bool kGelu, bool kBf16Out>
+// k2Cta: a thread-block cluster of two CTAs computes a 256-feature x 256-row tile with `cta_group::2` MMAs (M = 256): each CTA loads its own
+// 128 weight rows and HALF of the 256 activation rows (32 KB per k-block instead of 48 KB — the single-CTA kernel waits for operands
+// 43-55 % of the time), the leader CTA issues the MMAs for the pair, every CTA drains its own 128 TMEM lanes.
+template <bool kGelu, bool kBf16Out, bool k2Cta>
 __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __grid_constant__ WideGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1368,6 +1382,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = k2Cta ? cluster_ctarank() : 0;
+    // work units: single CTA = one 128 x 256 tile per step; pair = one 256 x 256 tile per step (this CTA: features f0 + 128 * rank)
+    const int unit0 = k2Cta ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_stride = k2Cta ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tiles_f = k2Cta ? p.tiles_f / 2 : p.tiles_f, n_units = k2Cta ? p.total_tiles / 2 : p.total_tiles;
+    constexpr int X_ROWS = k2Cta ? 128 : 256;                       // activation rows this CTA loads per stage
+    constexpr int STAGE = WG_W_BYTES + X_ROWS * ROW_BYTES;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmW)) : "memory");
@@ -1375,15 +1395,21 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], WIDE_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], (k2Cta ? 2 : 1) * WIDE_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (k2Cta) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (k2Cta) cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -1391,11 +1417,19 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
         if (elect_one()) {          // ===================== TMA producer =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int f0 = (t % p.tiles_f) * 128, m0 = (t / p.tiles_f) * 256;
+            const uint32_t lead_full = k2Cta ? leader_addr(full_bar) : 0;
+            for (int t = unit0; t < n_units; t += unit_stride) {
+                const int f0 = (t % tiles_f) * (k2Cta ? 256 : 128) + (int)rank * 128, m0 = (t / tiles_f) * 256 + (int)rank * (k2Cta ? 128 : 0);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sw = smem + stage * WG_STAGE_BYTES;
+                    uint8_t* sw = smem + stage * STAGE;
+                    if (k2Cta) {
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE);            // both CTAs' bytes land on the leader's barrier
+                        tma_load_4d_2sm(sw, &p.tmW, lead_full + (uint32_t)(stage * 8), kb * 64, f0, 0, 0);
+                        tma_load_4d_2sm(sw + WG_W_BYTES, &p.tmX2, lead_full + (uint32_t)(stage * 8), kb * 64, m0, 0, 0);
+                        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
                     tma_load_4d(sw, &p.tmW, &full_bar[stage], kb * 64, f0, 0, 0);
                     tma_load_4d(sw + WG_W_BYTES, &p.tmX, &full_bar[stage], kb * 64, m0, 0, 0);
@@ -1404,7 +1438,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {          // ===================== MMA issuer =====================
+        if (rank == 0 && elect_one()) {          // ===================== MMA issuer (pair: the leader issues for both CTAs) =====================
             int stage = 0, it = 0;
             uint32_t phase = 0;
             bool ready = false;
@@ -1415,10 +1449,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
 #endif
             long long c_ops = 0, c_tmem = 0, c_tiles = 0, c0 = 0;
             const long long c_start = dbg ? clock64() : 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t = unit0; t < n_units; t += unit_stride) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 if (dbg) c0 = clock64();
+                if (k2Cta) mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1); else
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 if (dbg) { c_tmem += clock64() - c0; ++c_tiles; }
                 tcgen05_fence_after();
@@ -1433,15 +1468,17 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
                         ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (phase ^ 1) : phase);
                     }
                     tcgen05_fence_after();
-                    const uint32_t sw = smem_u32(smem + stage * WG_STAGE_BYTES);
+                    const uint32_t sw = smem_u32(smem + stage * STAGE);
                     const uint64_t adesc = make_sw128_desc(sw), bdesc = make_sw128_desc(sw + WG_W_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    tcgen05_commit(&empty_bar[stage]);
+                    for (int k = 0; k < 4; ++k) {
+                        if (k2Cta) umma_2sm<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        else umma<false>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    if (k2Cta) tcgen05_commit_2sm(&empty_bar[stage]); else tcgen05_commit(&empty_bar[stage]);
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(&tmem_full_bar[acc]);
+                if (k2Cta) tcgen05_commit_2sm(&tmem_full_bar[acc]); else tcgen05_commit(&tmem_full_bar[acc]);
                 ++it;
             }
             if (dbg) {
@@ -1454,8 +1491,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
         const int quarter = warp & 3;
         const int grp = (warp - 2) >> 2;                             // tokens [64*grp, +64) of the tile
         int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const int f0 = (t % p.tiles_f) * 128, m0 = (t / p.tiles_f) * 256;
+        for (int t = unit0; t < n_units; t += unit_stride) {
+            const int f0 = (t % tiles_f) * (k2Cta ? 256 : 128) + (int)rank * 128, m0 = (t / tiles_f) * 256;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             ++it;
@@ -1480,7 +1517,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
                 tcgen05_fence_after();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) { if (k2Cta && rank != 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
                 continue;
             }
 #endif
@@ -1494,7 +1531,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
                 if (c == 1) {
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    if (lane == 0) {
+                        if (k2Cta && rank != 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);       // the leader's issuer waits for both CTAs
+                        else mbar_arrive(&tmem_empty_bar[acc]);
+                    }
                 }
                 float v[32];
 #pragma unroll
@@ -1525,7 +1565,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) tc_gemm_wide_kernel(const __g
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (k2Cta) cluster_sync_all();          // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 1) {
+        if (k2Cta) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1733,6 +1777,8 @@ static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st)
     const uint64_t strX[3] = {(uint64_t)q->lda * es, (uint64_t)q->lda * es * M, (uint64_t)q->lda * es * M};
     const uint32_t boxX[4] = {64, 256, 1, 1};
     if ((rc = make_tmap(&prm.tmX, VF_BF16, q->A, dimsX, strX, boxX)) != VF_OK) return rc;
+    const uint32_t boxX2[4] = {64, 128, 1, 1};
+    if ((rc = make_tmap(&prm.tmX2, VF_BF16, q->A, dimsX, strX, boxX2)) != VF_OK) return rc;
     prm.bias = q->bias_mode == VF_BIAS_N ? q->bias : nullptr;
     prm.residual = q->residual;
     prm.C_f32 = q->C_f32;
@@ -1744,15 +1790,23 @@ static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st)
     prm.tiles_f = q->Ncols / 128;
     const long long total = (long long)prm.tiles_f * ((M + 255) / 256);
     prm.total_tiles = (int)total;
-    prm.idesc = make_idesc(false, 128, 256);
     prm.dbg = g_tc_dbg;
     prm.dbg_flags = g_tc_dbg_flags;
+    // CTA pairs (cta_group::2, 256 features x 256 rows per pair, 32 KB of operands per CTA and k-block instead of 48 KB): opt-in with
+    // VF_TC_WIDE2=1.  Measured on the MIGT linears (scripts/bench_kernels.py, round 2): on par with single CTAs (c_fc 855 vs 878, fc2 1021
+    // vs 1012, qk 1006 vs 1000, c_proj 549 vs 596 TFLOP/s) — the wide GEMM is not bound by operand ingest, so single CTAs stay the default.
+    static int pair_enabled = -1;
+    if (pair_enabled < 0) { const char* e = getenv("VF_TC_WIDE2"); pair_enabled = (e && e[0] == '1') ? 1 : 0; }
+    const bool k2 = pair_enabled && q->Ncols % 256 == 0 && prm.tiles_f % 2 == 0;
+    prm.idesc = make_idesc(false, k2 ? 256 : 128, 256);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_wide_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_wide_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_wide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        cudaError_t e = cudaSuccess;
+        auto cfg = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); };
+        cfg((const void*)tc_gemm_wide_kernel<false, false, false>); cfg((const void*)tc_gemm_wide_kernel<false, true, false>);
+        cfg((const void*)tc_gemm_wide_kernel<true, false, false>); cfg((const void*)tc_gemm_wide_kernel<true, true, false>);
+        cfg((const void*)tc_gemm_wide_kernel<false, false, true>); cfg((const void*)tc_gemm_wide_kernel<false, true, true>);
+        cfg((const void*)tc_gemm_wide_kernel<true, false, true>); cfg((const void*)tc_gemm_wide_kernel<true, true, true>);
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute(wide gemm): %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
         configured = true;
     }
@@ -1762,12 +1816,34 @@ static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st)
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
-    const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
     const bool gelu = q->act == VF_ACT_GELU_ERF, b16 = q->C_bf16 != nullptr;
-    if (gelu && b16) tc_gemm_wide_kernel<true, true><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
-    else if (gelu) tc_gemm_wide_kernel<true, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
-    else if (b16) tc_gemm_wide_kernel<false, true><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
-    else tc_gemm_wide_kernel<false, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    if (k2) {
+        const long long units = total / 2, pairs = units < num_sms / 2 ? units : num_sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(WIDE_THREADS);
+        cfg.dynamicSmemBytes = WG_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e;
+        if (gelu && b16) e = cudaLaunchKernelEx(&cfg, tc_gemm_wide_kernel<true, true, true>, prm);
+        else if (gelu) e = cudaLaunchKernelEx(&cfg, tc_gemm_wide_kernel<true, false, true>, prm);
+        else if (b16) e = cudaLaunchKernelEx(&cfg, tc_gemm_wide_kernel<false, true, true>, prm);
+        else e = cudaLaunchKernelEx(&cfg, tc_gemm_wide_kernel<false, false, true>, prm);
+        if (e != cudaSuccess) { vf_set_error("vf_tc_gemm(wide gemm): cluster launch failed: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
+        VF_CHECK_LAUNCH("vf_tc_gemm(wide gemm, pairs)");
+        return VF_OK;
+    }
+    const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+    if (gelu && b16) tc_gemm_wide_kernel<true, true, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    else if (gelu) tc_gemm_wide_kernel<true, false, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    else if (b16) tc_gemm_wide_kernel<false, true, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
+    else tc_gemm_wide_kernel<false, false, false><<<grid, WIDE_THREADS, WG_SMEM, st>>>(prm);
     VF_CHECK_LAUNCH("vf_tc_gemm(wide gemm)");
     return VF_OK;
 }
