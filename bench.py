@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured CUDA graph")
-    ap.add_argument("--workload", default="generate", choices=["generate", "kvcache"],
-                    help="generate = BASELINE configs[1] (default, the judged line); kvcache = configs[4]: 19-context KV-cached query decode")
+    ap.add_argument("--workload", default="generate", choices=["generate", "kvcache", "train"],
+                    help="generate = BASELINE configs[1] (default, the judged line); kvcache = configs[4]: 19-context KV-cached query decode; "
+                         "train = configs[3]: codebook training step (--scenes = images per GPU)")
     return ap.parse_args()
 
 
@@ -542,9 +543,58 @@ def run_kvcache(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[3]: codebook training step — forward, backward, bucketed NCCL gradient all-reduce under backward, packed
+    EMA-statistics all-reduce, Adam — on `--scenes` images per GPU (32 = 256 images over 8 GPUs).  fp32 results as the reference requires
+    (vqgan_th.py:326); the 3x3 convs run on the exact split-fp16 tensor-core kernels.  One step = one optimisation step; the batch is
+    copied from pinned host memory inside the timed region."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    from viewformer_b200 import VQGAN
+    from viewformer_b200.config import VQGANConfig
+    from viewformer_b200.train import VQGANTrainer
+    tr = VQGANTrainer(VQGAN(VQGANConfig(perceptual_weight=0.0), precision="fp32", device=dev).init_weights(0))
+    n = args.scenes
+    x = (torch.rand((n, 3, IMG, IMG), generator=torch.Generator().manual_seed(7 + rank)) * 2 - 1).pin_memory()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        loss = tr.training_step(x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync(); e0.record()
+    for _ in range(args.steps):
+        loss = tr.training_step(x)
+    e1.record(); sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "codebook training images/sec", "value": world * n * args.steps / (float(ms) / 1e3), "unit": "images/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": float(ms) / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (exact split-fp16 tensor-core convs)",
+                          "data": "synthetic", "loss": float(loss),
+                          "config": {"workload": "shapenet-srn codebook training step (BASELINE configs[3])", "images_per_gpu": n,
+                                     "gradient_buckets": len(tr.buckets), "h2d_bytes_per_step": x.numel() * 4}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.workload == "kvcache" and a.impl == "b200":
+    if a.workload == "train" and a.impl == "b200":
+        run_train(a)
+    elif a.workload == "kvcache" and a.impl == "b200":
         run_kvcache(a)
     elif a.impl == "reference":
         run_reference(a)

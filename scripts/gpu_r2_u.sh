@@ -13,5 +13,6 @@ PY
 tail -3 gpurun_out/bench_u.err
 echo "=== reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-700
 echo "=== kvcache"; timeout 600 python bench.py --workload kvcache --precision bf16 --scenes 128 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/kvcache_u.json | cut -c1-500
+echo "=== train workload"; timeout 600 python bench.py --workload train --scenes 32 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/train_u.json | cut -c1-500
 echo "=== launches"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_mixed.csv python scripts/profile_step.py --precision mixed > gpurun_out/prof_step.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches_mixed.csv > gpurun_out/launches_mixed_summary.md 2>&1; head -16 gpurun_out/launches_mixed_summary.md
