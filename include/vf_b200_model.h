@@ -10,7 +10,8 @@
  * (__cuda_array_interface__) on the caller's stream.  All arithmetic runs in the kernels of libvf_b200.so (vf_b200.h).  A host therefore
  * needs this image's Python environment at run time (VF_PYTHON_EXECUTABLE, default: the interpreter the library was built with) but no
  * Python code of its own.  Calls are serialised by the interpreter lock; one host thread at a time per process is the intended use
- * (the reference's callers are single-threaded Python).
+ * (the reference's callers are single-threaded Python).  All device work of a call is enqueued on `stream`; outputs are complete when
+ * the stream has drained (cudaStreamSynchronize / an event), exactly as with the kernels of vf_b200.h.
  *
  * Reference interfaces replaced:
  *   vf_vq_create            viewformer/utils/torch.py:9-17 (load_model), models/__init__.py:38-59 (AutoModelTH.from_config)
