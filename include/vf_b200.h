@@ -169,6 +169,10 @@ int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, in
  * V^T columns stay in `qk` / `vt` from the prefill and the query view's are appended behind them. */
 int vf_attn_block_causal_tail(const void* qk_bf16, const void* vt_bf16, int B, int S, int H, int d, int block, int first_query,
                               void* out_bf16, vf_stream_t s);
+/* KV-cache decode with an unused view slot: as vf_attn_block_causal_tail, but the 64 keys of view `skip_view` are never visited (-1: none).
+ * Lets the host keep the query view at the start of a 128-row tile whatever the number of cached context views. */
+int vf_attn_block_causal_decode(const void* qk_bf16, const void* vt_bf16, int B, int S, int H, int d, int block, int first_query,
+                                int skip_view, void* out_bf16, vf_stream_t s);
 /* Branching (multi-end) attention of the 3-stream forward — viewformer/models/branching_attention.py:82-126.  qk [B, n_streams*S, 2d] and
  * vt [B, d, n_streams*S] hold the streams side by side.  stream 0: block-causal over its own keys; stream s >= 1: a query of view t attends
  * to the stream-0 keys of views < t and to its own stream's keys of view t (one joint softmax).  out bf16 [B*S, d] = that stream's output.

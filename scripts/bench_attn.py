@@ -40,17 +40,21 @@ def main():
     except Exception:
         pass
     H, d, blk = 12, 768, 64
-    for name, B, T, first in [("bench step B32 T10", 32, 10, 0), ("config 5 forward B16 T20", 16, 20, 0), ("config 5 decode B128 T20 (last view)", 128, 20, 19 * 64)]:
+    for name, B, T, first, skip in [("bench step B32 T10", 32, 10, 0, -1), ("config 5 forward B16 T20", 16, 20, 0, -1),
+                                    ("config 5 decode B128, 19 ctx + query sharing a tile", 128, 20, 19 * 64, -1),
+                                    ("config 5 decode B128, 19 ctx + empty slot + query (MIGT layout)", 128, 21, 20 * 64, 19)]:
         S = T * blk
         g = torch.Generator().manual_seed(S)
         qk = (torch.randn(B, S, 2 * d, generator=g) * 0.6).bfloat16().cuda()
         vt = torch.randn(B, d, S, generator=g).bfloat16().cuda()
         out = torch.empty(B * S, d, dtype=torch.bfloat16, device="cuda")
-        fn = lambda: L.attn_block_causal(qk, vt, B, S, H, d, blk, first_query=first, out=out)
+        fn = lambda: L.attn_block_causal(qk, vt, B, S, H, d, blk, first_query=first, out=out, skip_view=skip)
         if a.once:
             fn(); torch.cuda.synchronize(); continue
         ms = timeit(fn)
         fl = visible_tile_flops(S, blk, first) * B * H
+        if skip >= 0:            # one 64-query view against 20 visible key tiles (the skipped slot is not work)
+            fl = 2 * 2 * 64 * (19 + 1) * 64 * 64 * B * H
         print(f"[attn] {name}: {ms * 1e3:.1f} us  useful {fl / ms / 1e9:.1f} TFLOP/s = {fl / ms / 1e9 / peak * 100:.1f}% of the measured bf16 peak ({peak:.0f})")
 
 

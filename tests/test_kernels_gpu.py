@@ -569,6 +569,32 @@ def test_fused_attention_growing_logits_and_tail(L, B, T, H, blk, first):
         assert bool((got[:, :t0] == 7.0).all()), "rows below the first computed tile must stay untouched"
 
 
+@pytest.mark.parametrize("B,Tc,H", [(2, 5, 2), (3, 19, 1), (2, 4, 2), (1, 1, 1)])
+def test_fused_attention_decode_with_empty_view_slot(L, B, Tc, H):
+    """KV-cache decode layout of MIGT.prefill_context: context views, an EMPTY view slot when their number is odd (garbage the kernel must
+    never read), the query view at the start of a 128-row tile.  Result == block-causal attention over [context | query]."""
+    blk = 64
+    d = H * 64
+    pad = Tc % 2
+    S_c = (Tc + 1) * blk                       # compact sequence: context + query
+    S_tot = (Tc + pad + 1) * blk
+    gg = g(Tc * 11 + H)
+    qk = (torch.randn(B, S_c, 2 * d, generator=gg) * 0.6).bfloat16()
+    v = torch.randn(B, S_c, d, generator=gg).bfloat16()
+    want = _attn_reference(qk, v, B, S_c, H, d, blk).reshape(B, S_c, d)[:, Tc * blk:]
+    qk_p = torch.full((B, S_tot, 2 * d), 300.0).bfloat16()                 # the empty slot holds huge values: any leak shows
+    v_p = torch.full((B, S_tot, d), -77.0).bfloat16()
+    qk_p[:, :Tc * blk] = qk[:, :Tc * blk]; v_p[:, :Tc * blk] = v[:, :Tc * blk]
+    r0 = (Tc + pad) * blk
+    qk_p[:, r0:] = qk[:, Tc * blk:]; v_p[:, r0:] = v[:, Tc * blk:]
+    out = torch.zeros((B * S_tot, d), dtype=torch.bfloat16, device="cuda")
+    L.attn_block_causal(qk_p.cuda(), v_p.permute(0, 2, 1).contiguous().cuda(), B, S_tot, H, d, blk, first_query=r0, out=out,
+                        skip_view=(Tc if pad else -1))
+    torch.cuda.synchronize()
+    got = out.float().cpu().reshape(B, S_tot, d)[:, r0:]
+    report(f"fused attention decode Tc{Tc} pad{pad}", got.reshape(-1, d), want.reshape(-1, d), 2e-2, 2e-2)
+
+
 @pytest.mark.parametrize("B,T,H", [(2, 5, 2), (1, 10, 3), (1, 3, 1), (2, 2, 1)])
 def test_fused_multiend_attention(L, B, T, H):
     """Fused branching attention == branching_attention.py:82-126 (oracle restatement): stream 0 block-causal, streams 1 and 2 attend to the

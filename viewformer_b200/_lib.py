@@ -22,7 +22,7 @@ EXPORTS = [
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update", "vf_vq_commit_grad",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cameras_prepare", "vf_cameras_from_relative",
-    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal", "vf_attn_block_causal_tail", "vf_attn_block_multiend",
+    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal", "vf_attn_block_causal_tail", "vf_attn_block_causal_decode", "vf_attn_block_multiend",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
     "vf_conv_wgrad", "vf_pad_transpose_split", "vf_sum_splits", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
@@ -651,15 +651,16 @@ def migt_embed(ids_i32, fixed_token, wte, wpe, pose_rows, BT, L):
     return out
 
 
-def attn_block_causal(qk, vt, B, S, H, d, block, first_query=0, out=None):
+def attn_block_causal(qk, vt, B, S, H, d, block, first_query=0, out=None, skip_view=-1):
     """Fused tcgen05 block-causal attention: qk bf16 [B,S,2d] (q|k), vt bf16 [B,d,S] -> bf16 [B*S, d].
-    ``first_query`` > 0 computes only the query rows from that row's 128-row tile on (KV-cache decode)."""
+    ``first_query`` > 0 computes only the query rows from that row's 128-row tile on (KV-cache decode); ``skip_view`` >= 0 leaves the
+    keys of that view out (an unused slot of the cache)."""
     lib = load(True)
     _dev(qk, torch.bfloat16)
     _dev(vt, torch.bfloat16)
     if out is None:
         out = torch.empty((B * S, d), dtype=torch.bfloat16, device=qk.device)
-    _check(lib.vf_attn_block_causal_tail(_p(qk), _p(vt), B, S, H, d, block, int(first_query), _p(out), _stream()))
+    _check(lib.vf_attn_block_causal_decode(_p(qk), _p(vt), B, S, H, d, block, int(first_query), int(skip_view), _p(out), _stream()))
     return out
 
 

@@ -39,6 +39,7 @@ struct AttnParams {
     CUtensorMap tmQ, tmK, tmV;
     int S, H, d, block, n_qtiles, qt0, BH;  // query tiles qt0 .. qt0 + n_qtiles - 1 are computed (qt0 > 0: KV-cache query mode)
     int stream, stream_rows;                // multi-end mode (stream > 0): rows of stream s start at s * stream_rows in qk / V^T
+    int skip_tile;                          // >= 0: this 64-key tile of stream 0 is never visited (an unused view slot of the KV cache)
     __nv_bfloat16* out;
     unsigned idesc;                         // M = 128, N = 64 for both Q K^T and P V
 };
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
         const int kv_lim = min(p.S, (last_q / p.block + 1) * p.block);
         n_kt = (kv_lim + KT - 1) / KT;
         if (p.stream > 0) n_kt = q0 / KT + ((q0 + KT < p.S) ? 3 : 1);               // multi-end schedule, see tile_at
+        else if (p.skip_tile >= 0 && p.skip_tile < n_kt) --n_kt;
     };
     // Key tile j of the item whose first query is q0: row of the tile in qk / V^T and which half of the 128 query rows sees it
     // (bit 0: rows 0..63, bit 1: rows 64..127).  Stream 0 (block-causal, branching_attention.py:41-61): tile j of stream 0, the masks
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
     // view t sees stream-0 keys of views < t and its own stream's keys of view t — for the tile's two views (t0, t0 + 1):
     //   stream 0, views 0 .. t0-1 (both halves) | stream 0, view t0 (upper half) | stream s, view t0 (lower half) | stream s, view t0+1 (upper)
     auto tile_at = [&](int q0, int j, int& krow, uint32_t& halves) {
-        if (p.stream == 0) { krow = j * KT; halves = 3u; return; }
+        if (p.stream == 0) { krow = ((p.skip_tile >= 0 && j >= p.skip_tile) ? j + 1 : j) * KT; halves = 3u; return; }
         const int t0 = q0 / KT;
         const bool two = q0 + KT < p.S;
         if (j < t0) { krow = j * KT; halves = 3u; }
@@ -258,16 +260,16 @@ __global__ void __launch_bounds__(ATTN_THREADS, 2) attn_block_causal_kernel(cons
             float m2 = -INFINITY;          // reference maximum, in log2 units (S * log2 e)
             float l = 0.f;
             for (int j = 0; j < n_kt; ++j, ++t) {
-                const int kbase = j * KT;
+                int kbase;
+                uint32_t halves;
+                tile_at(q0, j, kbase, halves);
                 const int sb = t & 1;
                 uint32_t pk[32];
                 mbar_wait(&s_full[sb], use_parity(t), "vf_attn softmax(S)");
                 tc_fence_after();
-                bool warp_sees = kbase < vis_hi, partial = kbase + KT > vis_lo;
+                // rows beyond the sequence (upper half of a last, half-filled query tile) are never stored: skip their arithmetic
+                bool warp_sees = kbase < vis_hi && q0 + quarter * 32 < p.S, partial = kbase + KT > vis_lo;
                 if (p.stream > 0) {                 // multi-end: whole 64-row halves see or do not see a tile, nothing is partially masked
-                    int krow;
-                    uint32_t halves;
-                    tile_at(q0, j, krow, halves);
                     warp_sees = ((halves >> (quarter >> 1)) & 1u) != 0 && q0 + (quarter >> 1) * KT < p.S;
                     partial = false;
                 }
@@ -382,10 +384,10 @@ unsigned idesc_bf16(int M, int N) { return make_idesc_16bit(1, M, N); }
 }  // namespace
 
 static int attn_launch(const void* qk, const void* vt, int B, int S, int n_streams, int stream, int H, int d, int block, int first_query,
-                       void* out, vf_stream_t s);
+                       int skip_view, void* out, vf_stream_t s);
 
 extern "C" int vf_attn_block_causal(const void* qk, const void* vt, int B, int S, int H, int d, int block, void* out, vf_stream_t s) {
-    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, 0, out, s);
+    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, 0, -1, out, s);
 }
 
 // Only the query rows >= first_query (rounded down to a 128-row tile) are computed: with the context's q|k rows and V^T columns kept from
@@ -393,7 +395,16 @@ extern "C" int vf_attn_block_causal(const void* qk, const void* vt, int B, int S
 // score matrix in HBM.  Rows of `out` below the first computed tile are left untouched.
 extern "C" int vf_attn_block_causal_tail(const void* qk, const void* vt, int B, int S, int H, int d, int block, int first_query, void* out,
                                          vf_stream_t s) {
-    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, first_query, out, s);
+    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, first_query, -1, out, s);
+}
+
+// KV-cache decode with an unused view slot: as vf_attn_block_causal_tail, but the keys of view `skip_view` (64 tokens per view) are never
+// visited.  With an odd number of cached context views the query view would share its 128-row tile with the last context view (half
+// of the tile's softmax work recomputes context rows nobody reads); leaving one slot empty puts the query view at the start of a tile.
+extern "C" int vf_attn_block_causal_decode(const void* qk, const void* vt, int B, int S, int H, int d, int block, int first_query, int skip_view,
+                                           void* out, vf_stream_t s) {
+    VF_CHECK_ARG(skip_view < 0 || block == KT, "vf_attn_block_causal_decode: skipping a view needs 64 tokens per view (block=%d)", block);
+    return attn_launch(qk, vt, B, S, 1, 0, H, d, block, first_query, skip_view, out, s);
 }
 
 // Branching (multi-end) attention, branching_attention.py:82-126: qk [B, n_streams * S, 2d] and V^T [B, d, n_streams * S] hold the streams
@@ -404,11 +415,11 @@ extern "C" int vf_attn_block_multiend(const void* qk, const void* vt, int B, int
                                       void* out, vf_stream_t s) {
     VF_CHECK_ARG(n_streams >= 1 && stream >= 0 && stream < n_streams, "vf_attn_block_multiend: stream %d of %d", stream, n_streams);
     VF_CHECK_ARG(stream == 0 || (block == KT && S % KT == 0), "vf_attn_block_multiend: streams >= 1 need 64 tokens per view (block=%d S=%d)", block, S);
-    return attn_launch(qk, vt, B, S, n_streams, stream, H, d, block, 0, out, s);
+    return attn_launch(qk, vt, B, S, n_streams, stream, H, d, block, 0, -1, out, s);
 }
 
 static int attn_launch(const void* qk, const void* vt, int B, int S, int n_streams, int stream, int H, int d, int block, int first_query,
-                       void* out, vf_stream_t s) {
+                       int skip_view, void* out, vf_stream_t s) {
     VF_CHECK_ARG(qk && vt && out, "vf_attn_block_causal: null pointer");
     VF_CHECK_ARG(first_query >= 0 && first_query < S, "vf_attn_block_causal: first_query out of range");
     VF_CHECK_ARG(H > 0 && d == H * DH, "vf_attn_block_causal: head dim must be 64 (d=%d H=%d)", d, H);
@@ -417,7 +428,7 @@ static int attn_launch(const void* qk, const void* vt, int B, int S, int n_strea
     AttnParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.S = S; prm.H = H; prm.d = d; prm.block = block; prm.BH = B * H;
-    prm.stream = stream; prm.stream_rows = S;
+    prm.stream = stream; prm.stream_rows = S; prm.skip_tile = skip_view;
     const uint64_t rows_all = (uint64_t)n_streams * S;          // rows of qk / columns of V^T per batch element (all streams)
     prm.qt0 = first_query / QT;
     prm.n_qtiles = (S + QT - 1) / QT - prm.qt0;

@@ -491,8 +491,11 @@ class MIGT:
         self._body(xs, B, Tc, kv_out=kv)
         cache = dict(kv=kv, B=B, Tc=Tc)
         Lt, H = self.n_image_tokens, self.config.n_head
-        S_tot = (Tc + 1) * Lt
-        if self.prec.opd == torch.bfloat16 and d // H == 64 and S_tot % 128 == 0 and self.fused_attention:
+        # the query view goes to the start of a 128-row tile: with an odd number of context views one view slot stays empty (its keys are
+        # skipped by the kernel), otherwise half of the decode tile's softmax work would recompute the last context view
+        pad = (Tc * Lt) % 128 // Lt if Lt == 64 else 0
+        S_tot = (Tc + pad + 1) * Lt
+        if self.prec.opd == torch.bfloat16 and d // H == 64 and ((Tc + pad) * Lt) % 128 == 0 and self.fused_attention:
             # fused decode: keep every layer's q|k rows and V^T columns in buffers with room for ONE more view, so that a query is
             # "append the view, run the fused block-causal kernel on the last 128-row tile" — no [Nq,H,64,S] score tensor in HBM
             fq, fv = [], []
@@ -503,7 +506,8 @@ class MIGT:
                 vt_c[:, :, : Tc * Lt].copy_(vt)
                 fq.append(qk_c)
                 fv.append(vt_c)
-            cache["fused"] = dict(qk=fq, vt=fv, S_tot=S_tot, out=torch.empty((B * S_tot, d), dtype=torch.bfloat16, device=self.device))
+            cache["fused"] = dict(qk=fq, vt=fv, S_tot=S_tot, q_row0=(Tc + pad) * Lt, skip_view=(Tc if pad else -1),
+                                  out=torch.empty((B * S_tot, d), dtype=torch.bfloat16, device=self.device))
         return cache
 
     def _query_block(self, lw, x, qk_c, vt_c, Nq, Bc, S_ctx):
@@ -538,20 +542,21 @@ class MIGT:
         hmid = linear(prec, m, lw["fc"], prec.opd, act=L.ACT_GELU)
         return linear(prec, hmid, lw["fc2"], torch.float32, residual=x)
 
-    def _query_block_fused(self, lw, x, qk_c, vt_c, out_buf, Nq, Tc, S_tot):
-        """Decode step of one block on the fused kernel: the query view's q|k rows / V^T columns are appended behind the cached
-        context and the block-causal kernel runs on the last 128-row tile only."""
+    def _query_block_fused(self, lw, x, qk_c, vt_c, fz, Nq):
+        """Decode step of one block on the fused kernel: the query view's q|k rows / V^T columns are written behind the cached context
+        (at the start of a 128-row tile, see prefill_context) and the block-causal kernel runs on that tile only."""
         prec, cfg = self.prec, self.config
         d, H, Lt = cfg.d_model, cfg.n_head, self.n_image_tokens
+        S_tot, r0, out_buf = fz["S_tot"], fz["q_row0"], fz["out"]
         a = L.layernorm(x, *lw["ln1"], out_dtype=prec.opd, eps=LN_EPS)
         gemm_nt(prec, a, lw["qk"].w, qk_c, M=Lt, N=2 * d, K=d, lda=d, ldb=d, ldc=2 * d, batch=(Nq, 1), a_bs=(Lt * d, 0), b_bs=(0, 0),
-                c_bs=(S_tot * 2 * d, 0), c_off=Tc * Lt * 2 * d, bias=lw["qk"].b, bias_mode=L.BIAS_N)
+                c_bs=(S_tot * 2 * d, 0), c_off=r0 * 2 * d, bias=lw["qk"].b, bias_mode=L.BIAS_N)
         gemm_nt(prec, lw["v"].w, a, vt_c, M=d, N=Lt, K=d, lda=d, ldb=d, ldc=S_tot, batch=(Nq, 1), a_bs=(0, 0), b_bs=(Lt * d, 0),
-                c_bs=(d * S_tot, 0), c_off=Tc * Lt, bias=lw["v"].b, bias_mode=L.BIAS_M)
-        L.attn_block_causal(qk_c, vt_c, Nq, S_tot, H, d, Lt, first_query=Tc * Lt, out=out_buf)
+                c_bs=(d * S_tot, 0), c_off=r0, bias=lw["v"].b, bias_mode=L.BIAS_M)
+        L.attn_block_causal(qk_c, vt_c, Nq, S_tot, H, d, Lt, first_query=r0, out=out_buf, skip_view=fz["skip_view"])
         xn = torch.empty_like(x)
         gemm_nt(prec, out_buf, lw["proj"].w, xn, M=Lt, N=d, K=d, lda=d, ldb=d, ldc=d, batch=(Nq, 1), a_bs=(S_tot * d, 0), b_bs=(0, 0),
-                c_bs=(Lt * d, 0), a_off=Tc * Lt * d, bias=lw["proj"].b, bias_mode=L.BIAS_N, residual=x)
+                c_bs=(Lt * d, 0), a_off=r0 * d, bias=lw["proj"].b, bias_mode=L.BIAS_N, residual=x)
         m = L.layernorm(xn, *lw["ln2"], out_dtype=prec.opd, eps=LN_EPS)
         hmid = linear(prec, m, lw["fc"], prec.opd, act=L.ACT_GELU)
         return linear(prec, hmid, lw["fc2"], torch.float32, residual=xn)
@@ -571,7 +576,7 @@ class MIGT:
         fz = cache.get("fused")
         if fz is not None and Nq == Bc:
             for lw, qk_c, vt_c in zip(self._w["layers"], fz["qk"], fz["vt"]):
-                x = self._query_block_fused(lw, x, qk_c, vt_c, fz["out"], Nq, Tc, fz["S_tot"])
+                x = self._query_block_fused(lw, x, qk_c, vt_c, fz, Nq)
         else:
             for lw, (qk_c, vt_c) in zip(self._w["layers"], cache["kv"]):
                 x = self._query_block(lw, x, qk_c, vt_c, Nq, Bc, S_ctx)
