@@ -61,6 +61,9 @@ int vf_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W,
  *   split-fp16 pair [.., hi(Cl) | lo(Cl)] (Cl = C, or 4C for layout 2) that vf_tc_gemm's exact convolution consumes.
  *   grid = (pixel chunks, N): N <= 65535.
  * ---------------------------------------------------------------------------------------- */
+/* fp32 [rows, C] -> split fp16 [rows, hi(C) | lo(C)] (hi = fp16(v), lo = fp16((v - hi) * 2^11)): the VF_F16X2 operand of vf_tc_gemm for
+ * tensors that do not come out of a GroupNorm pass (any C % 4 == 0). */
+int vf_split_f16x2(const float* x, int64_t rows, int C, void* out_f16, vf_stream_t s);
 int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* sums, float* mean_rstd,
                        vf_stream_t s);
 /* (sum, sumsq) -> (mean, rstd) for `count` elements per (image, group); n_stats = images*groups */
@@ -205,7 +208,8 @@ int vf_lincomb3(float a, const float* x, float b, const float* y, float c, const
  * ntaps = batch1 = 3: tap_coff[ky] shifts the K coordinate of the activation operand by whole rows of the padded grid; the three horizontal
  * shifts are three row blocks of the operand, so M = 3 Cin).  vf_pad_transpose_split lays an NHWC fp32 tensor out as that K-major split
  * operand, fp16 [copies*C][2][L], over the zero-padded pixel grid of row pitch `pitch` (a multiple of 8: TMA box starts stay 16-byte
- * aligned): column margin + ((n (H+2) + y + 1) pitch + x + 1) - (k - copies/2) of copy k; the caller clears the buffer.
+ * aligned): column margin + ((n (H+2) + y + 1) pitch + x + 1) - (k - copies/2) of copy k; pitch = 0 (copies = 1): plain transpose, column
+ * margin + pixel index (weight gradient of a dense layer: K = rows); the caller clears the buffer.
  * vf_sum_splits folds the split-K partial products: out[g*n + i] (+)= sum_s partial[(g*splits + s)*n + i]. */
 int vf_pad_transpose_split(const float* x_nhwc, int N, int H, int W, int C, int pitch, int copies, int64_t margin, int64_t L, void* out_f16,
                            vf_stream_t s);

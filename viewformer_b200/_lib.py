@@ -22,7 +22,7 @@ EXPORTS = [
     "vf_simt_gemm", "vf_tc_gemm", "vf_vq_lookup", "vf_gather_rows", "vf_vq_ema_stats", "vf_vq_ema_update", "vf_vq_commit_grad",
     "vf_vq_prepare_codebook", "vf_migt_embed", "vf_softmax_rows", "vf_argmax_rows", "vf_pose_postprocess",
     "vf_cameras_prepare", "vf_cameras_from_relative",
-    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_attn_block_causal", "vf_attn_block_causal_tail", "vf_attn_block_causal_decode", "vf_attn_block_multiend",
+    "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_split_f16x2", "vf_attn_block_causal", "vf_attn_block_causal_tail", "vf_attn_block_causal_decode", "vf_attn_block_multiend",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
     "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
     "vf_conv_wgrad", "vf_pad_transpose_split", "vf_sum_splits", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
@@ -542,8 +542,12 @@ def vq_lookup(z_rows, et, esq, want_quant=True, want_diff=True):
 
 def split_f16x2(x_rows):
     """f32 [rows, C] -> f16 [rows, 2C] = [hi | lo], hi = fp16(v), lo = fp16((v - hi) * 2^11) (weights of the exact convolution)."""
+    lib = load(True)
+    _dev(x_rows, torch.float32)
     rows, c = x_rows.shape
-    return groupnorm(x_rows.reshape(1, 1, rows, c), None, None, swish=False, out_dtype=torch.float16, normalize=False).reshape(rows, 2 * c)
+    out = torch.empty((rows, 2 * c), dtype=torch.float16, device=x_rows.device)
+    _check(lib.vf_split_f16x2(_p(x_rows), C.c_int64(rows), c, _p(out), _stream()))
+    return out
 
 
 def vq_split3(x, codebook):
@@ -830,6 +834,38 @@ def conv_wgrad_tc(x, dy, dw, *, accumulate=True):
             c_bs=(splits * 3 * cin * cout, 3 * cin * cout), lo_a=la, lo_b=lb, k_offsets=offs)
     _check(lib.vf_sum_splits(_p(partial), 3, splits, C.c_int64(3 * cin * cout), int(accumulate), _p(dw), _stream()))
     return dw
+
+
+def dense_wgrad_tc_ok(k, n):
+    return k % 128 == 0 and n % 128 == 0
+
+
+def dense_wgrad_tc(x_rows, dy_rows, dw_kn, *, accumulate=True):
+    """dW[k, n] (+)= sum_m x[m, k] dy[m, n] on the exact split-fp16 tensor-core GEMM (K = rows): both operands are transposed to K-major
+    split form (vf_pad_transpose_split, plain mode), the row axis is split over the SMs, vf_sum_splits folds the partial products."""
+    lib = load(True)
+    _dev(x_rows, torch.float32); _dev(dy_rows, torch.float32); _dev(dw_kn, torch.float32)
+    m, k = x_rows.shape
+    n = dy_rows.shape[1]
+    tiles = (k // 128) * (n // 128)
+    splits = max(1, min(32, (148 + tiles - 1) // tiles))
+    kc = ((m + splits - 1) // splits + 63) // 64 * 64
+    lm = kc * splits
+    key = ("dense", x_rows.device, m, k, n)
+    bufs = _wgrad_bufs.get(key)
+    if bufs is None:
+        if len(_wgrad_bufs) >= 32:
+            _wgrad_bufs.clear()
+        bufs = (torch.zeros((k, 2, lm), dtype=torch.float16, device=x_rows.device), torch.zeros((n, 2, lm), dtype=torch.float16, device=x_rows.device),
+                torch.empty((splits, k, n), dtype=torch.float32, device=x_rows.device))
+        _wgrad_bufs[key] = bufs
+    at, bt, partial = bufs
+    _check(lib.vf_pad_transpose_split(_p(x_rows), 1, 1, m, k, 0, 1, C.c_int64(0), C.c_int64(lm), _p(at), _stream()))
+    _check(lib.vf_pad_transpose_split(_p(dy_rows), 1, 1, m, n, 0, 1, C.c_int64(0), C.c_int64(lm), _p(bt), _stream()))
+    tc_gemm(at, bt, partial, M=k, N=n, K=kc, lda=2 * lm, ldb=2 * lm, ldc=n, batch=(1, splits), a_bs=(0, kc), b_bs=(0, kc),
+            c_bs=(0, k * n), lo_a=lm, lo_b=lm)
+    _check(lib.vf_sum_splits(_p(partial), 1, splits, C.c_int64(k * n), int(accumulate), _p(dw_kn), _stream()))
+    return dw_kn
 
 
 def col_sums(x_rows, out):

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) pad_transpose_split_kernel(const float* _
             const long long t = pix / W;
             const int yy = (int)(t % H);
             const long long n = t / H;
-            const long long q = (n * (H + 2) + yy + 1) * (long long)pitch + xx + 1;
+            const long long q = pitch ? (n * (H + 2) + yy + 1) * (long long)pitch + xx + 1 : pix;      // pitch 0: plain transpose
             const float v = tile[i][cc];
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn((v - __half2float(hi)) * 2048.0f);
@@ -487,8 +487,9 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int groups,
 extern "C" int vf_pad_transpose_split(const float* x, int N, int H, int W, int C, int pitch, int copies, int64_t margin, int64_t L,
                                       void* out_f16, vf_stream_t s) {
     VF_CHECK_ARG(x && out_f16 && N > 0 && H > 0 && W > 0 && C > 0, "vf_pad_transpose_split: bad args");
-    VF_CHECK_ARG(pitch >= W + 2 && (copies == 1 || copies == 3) && margin >= copies / 2, "vf_pad_transpose_split: pitch / copies / margin");
-    VF_CHECK_ARG(L >= margin + (int64_t)N * (H + 2) * pitch + copies / 2, "vf_pad_transpose_split: row length L too small");
+    VF_CHECK_ARG((pitch >= W + 2 || (pitch == 0 && copies == 1)) && (copies == 1 || copies == 3) && margin >= copies / 2,
+                 "vf_pad_transpose_split: pitch / copies / margin");
+    VF_CHECK_ARG(L >= margin + (pitch ? (int64_t)N * (H + 2) * pitch : (int64_t)N * H * W) + copies / 2, "vf_pad_transpose_split: row length L too small");
     const long long P = (long long)N * H * W;
     dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 31) / 32));
     pad_transpose_split_kernel<<<grid, 256, 0, vf_s(s)>>>(x, N, H, W, C, pitch, copies, margin, L, reinterpret_cast<__half*>(out_f16));

@@ -272,7 +272,37 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// fp32 [rows, C] -> split fp16 [rows, hi(C) | lo(C)] for any C % 4 == 0: the operand form of the exact tensor-core GEMM
+__global__ void split_rows_kernel(const float* __restrict__ x, long long quads_total, int quads_per_row, __half* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads_total; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const long long r = i / quads_per_row;
+        const int q = (int)(i - r * quads_per_row);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        __half hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2half_rn(e[j]);
+            lo[j] = __float2half_rn((e[j] - __half2float(hi[j])) * 2048.0f);
+        }
+        __half* o = out + r * (8LL * quads_per_row) + 4 * q;
+        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(o + 4 * quads_per_row) = *reinterpret_cast<const uint2*>(lo);
+    }
+}
+
 }  // namespace
+
+extern "C" int vf_split_f16x2(const float* x, int64_t rows, int C, void* out_f16, vf_stream_t s) {
+    VF_CHECK_ARG(x && out_f16 && C > 0 && C % 4 == 0, "vf_split_f16x2: C must be a positive multiple of 4 (C=%d)", C);
+    if (rows == 0) return VF_OK;
+    const long long quads = rows * (C / 4);
+    long long blocks = (quads + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, vf_s(s)>>>(x, quads, C / 4, reinterpret_cast<__half*>(out_f16));
+    VF_CHECK_LAUNCH("vf_split_f16x2");
+    return VF_OK;
+}
 
 extern "C" int vf_groupnorm_stats(const float* x, int N, int HW, int C, int groups, float eps, double* stats, float* mean_rstd,
                                   vf_stream_t s) {

@@ -6,7 +6,8 @@
               output, MLP output) from a stateless hash generator
     loss      mean over the batch of  image_generation_weight * CE(stream 1 logits, tokens)[views >= n_loss_skip]
               + localization_weight * (position MSE + orientation MSE of the stream-2 pose head)
-    backward  hand-written: dense layers through vf_simt_gemm (strided, batched per (scene, head)), vf_conv_wgrad for weight
+    backward  hand-written: dense layers on the exact split-fp16 tensor-core GEMM (forward, data and weight gradient; VF_TRAIN_TC=0: the
+              fp32 CUDA-core kernels), attention through vf_simt_gemm (strided, batched per (scene, head)), vf_conv_wgrad for the remaining weight
               gradients, LayerNorm / GELU / softmax / embedding / loss kernels of vf_backward.cu
     update    per-tensor tf.clip_by_norm when gradient_clip_val > 0 (migt.py:486-487), AdamWeightDecay = Keras Adam preceded by the
               decoupled decay lr*wd*p for every variable whose name has no "bias" (models/utils.py:424, 507-515 — LayerNorm gamma /
@@ -20,6 +21,7 @@ Parameters are kept in the reference's own layouts (Conv1D weight [in, out], bia
 into ``viewformer_b200.MIGT`` for inference.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -43,6 +45,8 @@ class MIGTTrainer:
         assert grad_reduce in ("sum", "mean")
         self.grad_reduce = grad_reduce
         self.iterations = 0                                        # optimizer.iterations (0-based: the schedule sees it BEFORE the increment)
+        self.use_tc = os.environ.get("VF_TRAIN_TC", "1") != "0"
+        self._wsplit = {}                                          # split-fp16 operand copies of the weights, rebuilt after every step
         self.use_loc = model.use_localization
         from .schedules import parse
         self._loc_schedule = parse(cfg.localization_weight).with_total_steps(int(cfg.total_steps))
@@ -119,9 +123,29 @@ class MIGTTrainer:
                 raise RuntimeError(f"gradient of {k} signalled twice")
 
     # ------------------------------------------------------------------ dense layer (Conv1D: x @ W[in,out] + b[1,out])
+    # Dense layers whose sizes fit the tensor-core tiles run forward, data gradient and weight gradient on the exact split-fp16 GEMM
+    # (fp32-faithful: three fp16 MMA passes, chunked accumulation — DESIGN.md 5.3); VF_TRAIN_TC=0 keeps everything on the CUDA cores.
+    def _tc_dense_ok(self, k, n):
+        return self.use_tc and k % 128 == 0 and n % 128 == 0
+
+    def _wsplit_get(self, key, make):
+        hit = self._wsplit.get(key)
+        if hit is None:
+            hit = self._wsplit[key] = L.split_f16x2(make())
+        return hit
+
+    def _dense_fw_tc(self, x, W_nk_key, W_nk_make, n, k, bias=None, residual=None):
+        """x [M, k] fp32 @ W^T with W given K-major ([n, k]) -> [M, n] fp32."""
+        out = torch.empty((x.shape[0], n), dtype=torch.float32, device=x.device)
+        L.tc_gemm(L.split_f16x2(x), self._wsplit_get(W_nk_key, W_nk_make), out, M=x.shape[0], N=n, K=k, lda=2 * k, ldb=2 * k, ldc=n,
+                  bias=bias, bias_mode=L.BIAS_N if bias is not None else L.BIAS_NONE, residual=residual, lo_a=k, lo_b=k)
+        return out
+
     def _lin(self, x, name, act=L.ACT_NONE, residual=None):
         W, b = self.p[name + ".weight"], self.p[name + ".bias"]
         k, n = W.shape
+        if act == L.ACT_NONE and self._tc_dense_ok(k, n):
+            return self._dense_fw_tc(x, ("fw", name), lambda: W.t().contiguous(), n, k, bias=b.reshape(-1), residual=residual)
         out = torch.empty((x.shape[0], n), dtype=torch.float32, device=x.device)
         L.simt_gemm(x, W, out, M=x.shape[0], N=n, K=k, a_strides=(k, 1), b_strides=(n, 1), ldc=n, bias=b.reshape(-1), bias_mode=L.BIAS_N,
                     act=act, residual=residual)
@@ -131,11 +155,17 @@ class MIGTTrainer:
         W = self.p[name + ".weight"]
         k, n = W.shape
         m = x.shape[0]
-        L.conv_wgrad(x.reshape(1, m, 1, k), dy.reshape(1, m, 1, n), self.g[name + ".weight"], kh=1, pad=(0, 0), so=(n, 1))
+        tc = self._tc_dense_ok(k, n)
+        if tc:
+            L.dense_wgrad_tc(x, dy, self.g[name + ".weight"])
+        else:
+            L.conv_wgrad(x.reshape(1, m, 1, k), dy.reshape(1, m, 1, n), self.g[name + ".weight"], kh=1, pad=(0, 0), so=(n, 1))
         L.col_sums(dy, self.g[name + ".bias"].reshape(-1))
         self._ready(name + ".bias", name + ".weight")
         if not need_dx:
             return None
+        if tc:                                  # dx = dy W^T: W [k, n] is already K-major for this product
+            return self._dense_fw_tc(dy, ("bw", name), lambda: W.contiguous(), k, n, residual=residual)
         dx = torch.empty((m, k), dtype=torch.float32, device=x.device)
         L.simt_gemm(dy, W, dx, M=m, N=k, K=n, a_strides=(n, 1), b_strides=(1, n), ldc=k, residual=residual)
         return dx
@@ -249,8 +279,12 @@ class MIGTTrainer:
         hn = [self._ln(x, "ln_f") for x in xs]
         denom = float(B * (T - skip) * Lt)
         view_ok = (torch.arange(T, device=dev) >= skip).to(torch.float32).repeat_interleave(Lt).repeat(B)        # [B*S] row mask
-        logits = torch.empty((B * S, V), dtype=torch.float32, device=dev)
-        L.simt_gemm(hn[1], wte, logits, M=B * S, N=V, K=d, a_strides=(d, 1), b_strides=(1, d), ldc=V)             # tied head, first V rows (:417)
+        head_tc = self._tc_dense_ok(d, V)
+        if head_tc:                                                                                                # tied head, first V rows (:417)
+            logits = self._dense_fw_tc(hn[1], ("fw", "wte"), lambda: wte[:V].contiguous(), V, d)
+        else:
+            logits = torch.empty((B * S, V), dtype=torch.float32, device=dev)
+            L.simt_gemm(hn[1], wte, logits, M=B * S, N=V, K=d, a_strides=(d, 1), b_strides=(1, d), ldc=V)
         ce_rows = L.cross_entropy_rows(logits, ids.reshape(-1), float(cfg.label_smoothing))
         ce = L.row_mean(ce_rows.reshape(B, S), skip * Lt)
         loss = ce * float(cfg.image_generation_weight)
@@ -258,9 +292,13 @@ class MIGTTrainer:
         dhn = [None] * ns
         dlog = L.cross_entropy_grad(logits, ids.reshape(-1), (view_ok * (float(cfg.image_generation_weight) / denom)).contiguous(), float(cfg.label_smoothing))
         # tied LM head backward: d hn1 = dlogits wte[:V];  d wte[:V] += dlogits^T hn1
-        dhn[1] = torch.empty_like(hn[1])
-        L.simt_gemm(dlog, wte, dhn[1], M=B * S, N=d, K=V, a_strides=(V, 1), b_strides=(d, 1), ldc=d)
-        L.conv_wgrad(dlog.reshape(1, B * S, 1, V), hn[1].reshape(1, B * S, 1, d), g["wte.weight"], kh=1, pad=(0, 0), so=(d, 1))
+        if head_tc:
+            dhn[1] = self._dense_fw_tc(dlog, ("bw", "wte"), lambda: wte[:V].t().contiguous(), d, V)
+            L.dense_wgrad_tc(dlog, hn[1], g["wte.weight"][:V])
+        else:
+            dhn[1] = torch.empty_like(hn[1])
+            L.simt_gemm(dlog, wte, dhn[1], M=B * S, N=d, K=V, a_strides=(V, 1), b_strides=(d, 1), ldc=d)
+            L.conv_wgrad(dlog.reshape(1, B * S, 1, V), hn[1].reshape(1, B * S, 1, d), g["wte.weight"], kh=1, pad=(0, 0), so=(d, 1))
         if self.use_loc:
             pc_h = self._lin(hn[2], "pose_classifier.c_fc")
             raw = self._lin(self._gelu(pc_h), "pose_classifier.c_proj")            # [B*S, 7]
@@ -341,10 +379,16 @@ class MIGTTrainer:
         W = self.p[name + ".weight"]
         k, n = W.shape
         m = x.shape[0]
-        L.conv_wgrad(x.reshape(1, m, 1, k), dy.reshape(1, m, 1, n), self.g[name + ".weight"], kh=1, pad=(0, 0), so=(n, 1))
+        tc = self._tc_dense_ok(k, n)
+        if tc:
+            L.dense_wgrad_tc(x, dy, self.g[name + ".weight"])
+        else:
+            L.conv_wgrad(x.reshape(1, m, 1, k), dy.reshape(1, m, 1, n), self.g[name + ".weight"], kh=1, pad=(0, 0), so=(n, 1))
         L.col_sums(dy, self.g[name + ".bias"].reshape(-1))
         if last:
             self._ready(name + ".bias", name + ".weight")
+        if tc:
+            return self._dense_fw_tc(dy, ("bw", name), lambda: W.contiguous(), k, n)
         dx = torch.empty((m, k), dtype=torch.float32, device=x.device)
         L.simt_gemm(dy, W, dx, M=m, N=k, K=n, a_strides=(n, 1), b_strides=(1, n), ldc=k)
         return dx
@@ -365,6 +409,7 @@ class MIGTTrainer:
         self._handles = []
         lr = self.learning_rate()
         self.iterations += 1
+        self._wsplit = {}
         wd = float(self.cfg.weight_decay)
         clip = float(self.cfg.gradient_clip_val or 0.0)
         gs = 1.0 / self._world() if self.grad_reduce == "mean" else 1.0
