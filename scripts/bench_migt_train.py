@@ -1,5 +1,5 @@
 """Full-size transformer training step timing (MIGTConfig defaults: 12 layers, d = 768; B scenes x 20 views x 64 tokens)."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle import synth, migt_oracle as mo

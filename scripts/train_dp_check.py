@@ -1,7 +1,7 @@
 """Data-parallel codebook training step: N ranks x (B/N) images must reproduce 1 rank x B images (gradient average over NCCL,
 packed EMA-statistics all-reduce).  Run under torchrun (NCCL); rank 0 also runs the full batch alone and compares.
 Also times a full-size step (config 4 shape: 32 images per GPU)."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist

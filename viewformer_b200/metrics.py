@@ -5,7 +5,6 @@ integer sums for MSE / MAE / RMSE / PSNR, the 7x7 uniform-window SSIM of ``ssim(
 scene and stay host-side torch (same formulas as CameraPositionError / CameraOrientationError, NaN-tolerant means, medians).
 LPIPS is out of scope (VGG weights are not available offline).
 """
-import math
 
 import torch
 
