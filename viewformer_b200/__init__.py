@@ -22,4 +22,16 @@ def __getattr__(name):   # lazy: importing the package must not require the buil
     if name in ("Evaluator", "image_metrics"):
         from . import metrics
         return getattr(metrics, name)
+    if name in ("VQGANTrainer",):
+        from .train import VQGANTrainer
+        return VQGANTrainer
+    if name in ("MIGTTrainer",):
+        from .train_migt import MIGTTrainer
+        return MIGTTrainer
+    if name in ("LatentCodeTransformer", "write_token_dataset", "load_token_dataset", "read_tfrecords", "TFRecordWriter"):
+        from . import data
+        return getattr(data, name)
+    if name in ("compat", "schedules", "tf_checkpoint", "cabi", "metrics", "data", "evaluate", "generate", "registry", "train", "train_migt"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
