@@ -82,3 +82,21 @@ def test_schedule_strings():
     from viewformer_b200.config import MIGTConfig
     assert MIGTConfig(localization_weight="0").use_localization is False
     assert MIGTConfig(localization_weight="warmup(1,2000)").use_localization is True
+
+
+def test_bench_reads_roofline_traffic_from_committed_captures():
+    """bench.py's `roofline.traffic` / `roofline_vq_lookup.traffic` are parsed from the ncu metric dumps under profiles/ (not literals):
+    the files it names must be present and yield the kernels' DRAM bytes."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vf_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    conv, src = bench.ncu_traffic("profiles/r02_exact_conv_wide_ncu_metrics.csv", 1.0)
+    assert conv is not None and 4.5e9 < conv < 5.2e9, (conv, src)               # algorithmic: 288 x 16384 x 128 x 8 B = 4.83 GB
+    vq, src = bench.ncu_traffic("profiles/r02_vq_fused_ncu_metrics.csv", 1.0, "vq")
+    assert vq is not None and 1.05e9 < vq < 1.2e9, (vq, src)                      # algorithmic: 2^20 x 1032 B = 1.08 GB
+    bf16, _ = bench.ncu_traffic("profiles/r01_conv_wide_ncu_nores_metrics.csv", 1.0)
+    assert bf16 is not None and 3.3e9 < bf16 < 3.9e9
+    none, why = bench.ncu_traffic("profiles/does_not_exist.csv", 1.0)
+    assert none is None and "no capture" in why
