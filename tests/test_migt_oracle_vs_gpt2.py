@@ -55,3 +55,37 @@ def test_oracle_block_equals_hf_gpt2_block(d, n_head, T):
     err = float((got - want).abs().max())
     print(f"[oracle block vs HF GPT2Block d={d} heads={n_head} T={T}] max abs diff {err:.2e}")
     assert err < 2e-5
+
+
+@pytest.mark.parametrize("d,n_head,T,L", [(64, 4, 5, 4), (96, 3, 3, 8)])
+def test_oracle_block_causal_mask_equals_hf_gpt2_block_with_block_mask(d, n_head, T, L):
+    """L tokens per view: the oracle's block-causal attention (branching_attention.py:41-61: a token sees every token of its own and of
+    earlier views, masked logits -1e4) against HF's GPT2Block handed the same visibility as an additive mask — pins the mask SHAPE of the
+    restatement (view >= view, not token >= token) to an independent implementation."""
+    g = torch.Generator().manual_seed(d + T + L)
+    p = "h.0."
+    sd = {}
+    for name, (nx, nf) in (("attn.c_attn", (d, 3 * d)), ("attn.c_proj", (d, d)), ("mlp.c_fc", (d, 4 * d)), ("mlp.c_proj", (4 * d, d))):
+        sd[p + name + ".weight"] = torch.randn(nx, nf, generator=g) * 0.08
+        sd[p + name + ".bias"] = torch.randn(1, nf, generator=g) * 0.05
+    for ln in ("ln_1", "ln_2"):
+        sd[p + ln + ".gamma"] = 1 + 0.1 * torch.randn(d, generator=g)
+        sd[p + ln + ".beta"] = 0.1 * torch.randn(d, generator=g)
+    x = torch.randn(2, T, L, d, generator=g)
+    S = T * L
+    view = torch.arange(S) // L
+    visible = view[:, None] >= view[None, :]
+    add_mask = torch.where(visible, 0.0, torch.finfo(torch.float32).min)[None, None].expand(2, 1, S, S)
+    with torch.no_grad():
+        got = mo.block(sd, p, [x], n_head)[0].reshape(2, S, d)
+        out = _gpt2_block(d, n_head, sd, p)(x.reshape(2, S, d), attention_mask=add_mask)
+        want = out[0] if isinstance(out, (tuple, list)) else out
+    err = float((got - want).abs().max())
+    print(f"[oracle block-causal vs HF GPT2Block + block mask d={d} heads={n_head} T={T} L={L}] max abs diff {err:.2e}")
+    assert err < 2e-5
+    # and it is NOT ordinary token-causal attention: with the token-causal mask HF's output differs
+    with torch.no_grad():
+        tok = torch.full((S, S), torch.finfo(torch.float32).min).triu(1)[None, None].expand(2, 1, S, S)
+        out_t = _gpt2_block(d, n_head, sd, p)(x.reshape(2, S, d), attention_mask=tok)
+        out_t = out_t[0] if isinstance(out_t, (tuple, list)) else out_t
+    assert float((got - out_t).abs().max()) > 1e-3
