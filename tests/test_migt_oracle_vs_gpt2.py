@@ -89,3 +89,49 @@ def test_oracle_block_causal_mask_equals_hf_gpt2_block_with_block_mask(d, n_head
         out_t = _gpt2_block(d, n_head, sd, p)(x.reshape(2, S, d), attention_mask=tok)
         out_t = out_t[0] if isinstance(out_t, (tuple, list)) else out_t
     assert float((got - out_t).abs().max()) > 1e-3
+
+
+def test_oracle_forward_body_equals_hf_gpt2_model():
+    """Whole single-stream body (migt.py:338-417 with use_localization off): N blocks, ln_f and the tied LM head sliced to n_embeddings,
+    against transformers' GPT2Model fed the oracle's own input embedding (token + per-view position + pose embedding) through
+    `inputs_embeds` with its wpe zeroed and the block-causal visibility as the attention mask.  Pins the layer stacking, the final
+    LayerNorm and the `[..., :n_embeddings]` logits of the restatement to the third-party model."""
+    from transformers import GPT2Config, GPT2Model
+    from oracle import synth
+    from viewformer_b200.config import MIGTConfig
+    cfg = MIGTConfig(n_layer=3, n_head=4, d_model=64, sequence_size=5, n_embeddings=40, token_image_size=2, localization_weight="0")
+    sd = synth.make_migt_state_dict(cfg, 3)
+    B, T, L, d, V = 2, 5, 4, 64, 40
+    ids = torch.randint(0, V + 1, (B, T, 2, 2), generator=torch.Generator().manual_seed(1))      # includes the mask token V
+    poses = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(B, T, seed=2))[0])
+    with torch.no_grad():
+        out = mo.forward(sd, cfg, dict(input_ids=ids, poses=poses), use_localization=False)
+        # the oracle's input embedding, restated from its three terms (migt.py:362-386)
+        emb = sd["wte.weight"][ids.reshape(B, T, L)] + sd["wpe.embeddings"][:L][None, None] + \
+            mo.mlp(sd, "pose_embedding", mo.pose_model_input(cfg, poses.float())).unsqueeze(-2)
+        hf_cfg = GPT2Config(n_embd=d, n_head=4, n_layer=3, n_positions=T * L, vocab_size=V + 2, activation_function="gelu",
+                            layer_norm_epsilon=1e-5, scale_attn_weights=False, attn_pdrop=0.0, resid_pdrop=0.0, embd_pdrop=0.0)
+        hf_cfg._attn_implementation = "eager"
+        hf = GPT2Model(hf_cfg).eval()
+        hf.wpe.weight.zero_()
+        for i, blk in enumerate(hf.h):
+            p = f"h.{i}."
+            w, b = sd[p + "attn.c_attn.weight"], sd[p + "attn.c_attn.bias"].reshape(-1)
+            blk.attn.c_attn.weight.copy_(torch.cat([w[:, d:2 * d], w[:, 2 * d:], w[:, :d]], 1)); blk.attn.c_attn.bias.copy_(torch.cat([b[d:2 * d], b[2 * d:], b[:d]]))
+            blk.attn.c_proj.weight.copy_(sd[p + "attn.c_proj.weight"]); blk.attn.c_proj.bias.copy_(sd[p + "attn.c_proj.bias"].reshape(-1))
+            blk.mlp.c_fc.weight.copy_(sd[p + "mlp.c_fc.weight"]); blk.mlp.c_fc.bias.copy_(sd[p + "mlp.c_fc.bias"].reshape(-1))
+            blk.mlp.c_proj.weight.copy_(sd[p + "mlp.c_proj.weight"]); blk.mlp.c_proj.bias.copy_(sd[p + "mlp.c_proj.bias"].reshape(-1))
+            blk.ln_1.weight.copy_(sd[p + "ln_1.gamma"]); blk.ln_1.bias.copy_(sd[p + "ln_1.beta"])
+            blk.ln_2.weight.copy_(sd[p + "ln_2.gamma"]); blk.ln_2.bias.copy_(sd[p + "ln_2.beta"])
+        hf.ln_f.weight.copy_(sd["ln_f.gamma"]); hf.ln_f.bias.copy_(sd["ln_f.beta"])
+        S = T * L
+        view = torch.arange(S) // L
+        add_mask = torch.where(view[:, None] >= view[None, :], 0.0, torch.finfo(torch.float32).min)[None, None].expand(B, 1, S, S)
+        hid = hf(inputs_embeds=emb.reshape(B, S, d), attention_mask=add_mask).last_hidden_state
+        want_logits = (hid @ sd["wte.weight"].t())[..., :V]
+    got_hid = out["hidden_states"][0].reshape(B, S, d)
+    e_h = float((got_hid - hid).abs().max())
+    e_l = float((out["logits"].reshape(B, S, V) - want_logits).abs().max())
+    print(f"[oracle forward vs HF GPT2Model] hidden max abs diff {e_h:.2e}, logits {e_l:.2e}")
+    assert float(hid.abs().max()) > 0.5 and float(want_logits.std()) > 1e-3 and torch.isfinite(want_logits).all()      # not a vacuous match
+    assert e_h < 5e-5 and e_l < 5e-5
