@@ -13,8 +13,10 @@ Contents
                      + ``utils_th.py`` (pinned against the real reference by
                      ``tests/test_oracle_vs_reference.py`` and by the golden fixtures).
 ``migt_oracle.py``   torch-CPU restatement of ``viewformer/models/migt.py`` +
-                     ``branching_attention.py`` — **parity unpinned**: the reference
-                     transformer is TensorFlow-only and TF is not installable here.
+                     ``branching_attention.py`` — pinned to the reference's own sources
+                     executed over ``tf_shim.py`` (TensorFlow itself is not installable here).
+``tf_shim.py``       torch-backed stand-in for the TensorFlow ops the reference's transformer
+                     files call, so that those files run unmodified (container only).
 ``vq_lookup.c``      plain-C restatement of the codebook nearest-neighbour search
                      (integer index output), built by ``oracle/Makefile``.
 ``synth.py``         deterministic synthetic weights / inputs shared by tests & bench.

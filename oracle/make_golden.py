@@ -5,8 +5,9 @@
 VQGAN fixtures are produced by the unmodified reference modules loaded from /root/reference
 (oracle/ref_loader.py); weights and inputs come from oracle/synth.py so that the GPU box (which has no
 /root/reference) can rebuild the same state_dict and compare its outputs with these files.
-MIGT fixtures come from the restatement (oracle/migt_oracle.py) — the TF reference cannot run —
-and are regression pins only ("parity unpinned").
+MIGT fixtures (migt_small / migt_full / migt_train_*) are written from the restatement (oracle/migt_oracle.py) and REPRODUCED by the
+reference's own TensorFlow sources executed over oracle/tf_shim.py (tests/test_reference_on_shim.py); migt_reference_shim.npz is written
+directly from that reference-on-shim run.
 """
 import os
 import sys
@@ -261,7 +262,8 @@ MIGT_TRAIN_WARMUP = 2
 
 def golden_migt_train():
     """Three optimisation steps of the transformer: gradients by torch autograd through the oracle's forward (compute_losses=True,
-    dropout 0), optimizer / schedule restated above.  PARITY UNPINNED like every MIGT fixture (the reference is TensorFlow-only)."""
+    dropout 0), optimizer / schedule restated above.  Reproduced by three calls of the reference's own MIGT.train_step executed over
+    oracle/tf_shim.py (tests/test_reference_on_shim.py)."""
     cfg = MIGTConfig(**MIGT_TRAIN)
     sd = {k: v.clone() for k, v in synth.make_migt_state_dict(cfg, 9).items()}
     B, T = 2, 4
@@ -303,7 +305,8 @@ def golden_migt_train():
 
 def golden_migt_train_full():
     """One optimisation step of the FULL-size transformer (MIGTConfig defaults: 12 layers, d = 768, 12 heads, 1024 + 2 tokens), B = 1,
-    T = 5 views, dropout 0: loss terms, gradient norm + projection of every tensor (autograd through the oracle; PARITY UNPINNED)."""
+    T = 5 views, dropout 0: loss terms, gradient norm + projection of every tensor (autograd through the oracle; reproduced by the
+    reference's own train_step over oracle/tf_shim.py, tests/test_reference_on_shim.py)."""
     cfg = MIGTConfig(dropout=0.0, label_smoothing=0.1, localization_weight="0.7", total_steps=100, learning_rate=1e-4)
     sd = {k: v.clone() for k, v in synth.make_migt_state_dict(cfg, 13).items()}
     B, T = 1, 5
@@ -323,6 +326,62 @@ def golden_migt_train_full():
     print("migt train golden (full size): loss", float(out["loss"]), "tensors", len(names))
 
 
+REF_SHIM_CASES = [
+    ("generate", {}), ("localize", {}), ("losses", {}), ("explicit", {}),
+    ("generate", dict(localization_weight="0")),
+    ("losses", dict(label_smoothing=0.1, pose_multiplier=0.3, image_generation_weight=0.7, localization_weight="cosine(2.0,0.5,100)")),
+    ("losses", dict(use_dynamic_pose_loss=True)),
+]
+REF_SHIM_BASE = dict(n_layer=2, n_head=4, d_model=64, sequence_size=4, n_embeddings=40, token_image_size=2, n_loss_skip=1)
+
+
+def ref_shim_inputs(cfg, variant, B=2, T=4):
+    codes = synth.make_codes(B, T, n_embed=cfg.n_embeddings, side=cfg.token_image_size, seed=5)
+    cams = migt_oracle.normalize_cameras(migt_oracle.to_relative_cameras(synth.make_cameras(B, T, seed=6))[0])
+    if variant == "generate":
+        return dict(input_ids=torch.cat([codes[:, :-1], torch.full_like(codes[:, :1], cfg.n_embeddings)], 1), poses=cams), False
+    if variant == "localize":
+        return dict(input_ids=codes, poses=cams[:, :-1]), False
+    if variant == "losses":
+        return dict(input_ids=codes, poses=cams), True
+    return dict(input_ids=codes, poses=cams, output_poses=cams.flip(1).contiguous(), localization_tokens=codes.flip(0).contiguous()), False
+
+
+def golden_migt_reference_shim():
+    """Outputs of the REFERENCE's own migt.py / branching_attention.py executed over oracle/tf_shim.py (TensorFlow cannot be installed;
+    see that file) for seven call patterns of MIGT.call, plus generate_batch_predictions of evaluate_transformer.py with the real torch
+    codebook.  tests/test_oracle_pinned.py compares the oracle with this file wherever /root/reference is absent."""
+    out = {}
+    for i, (variant, extra) in enumerate(REF_SHIM_CASES):
+        kw = dict(REF_SHIM_BASE, **extra)
+        cfg = MIGTConfig(**kw)
+        sd = synth.make_migt_state_dict(cfg, 3)
+        dyn = [0.3, -2.0] if kw.get("use_dynamic_pose_loss") else None
+        model = ref_loader.build_reference_migt(sd, dynamic_pose_weights=dyn, **kw)
+        inputs, losses = ref_shim_inputs(cfg, variant)
+        model._train_counter.assign(7)
+        with torch.no_grad():
+            r = model({k: v.clone() for k, v in inputs.items()}, compute_losses=losses, training=False)
+        for k in ("logits", "loss", "pose_prediction", "ce_loss", "pose_loss", "pose_pos_loss", "pose_ori_loss", "localization_weight"):
+            if k in r:
+                out[f"c{i}.{k}"] = torch.as_tensor(r[k]).detach().float().numpy()
+        out[f"c{i}.n_streams"] = np.int64(len(r["hidden_states"]))
+    ev, _ = ref_loader.load_reference_evaluate()
+    vcfg = VQGANConfig(**SMALL_VQ)
+    vq = ref_loader.build_reference_vqgan(synth.make_vqgan_state_dict(vcfg, 0), **SMALL_VQ)
+    kw = dict(REF_SHIM_BASE, n_embeddings=vcfg.n_embed, token_image_size=8)
+    cfg = MIGTConfig(**kw)
+    model = ref_loader.build_reference_migt(synth.make_migt_state_dict(cfg, 3), **kw)
+    images = synth.make_images_uint8(2, 4, size=vcfg.image_size, seed=11)
+    cams = synth.make_cameras(2, 4, seed=12)
+    with torch.no_grad():
+        r = ev.generate_batch_predictions(model, ref_loader.ReferenceCodebookNHWC(vq), images.clone(), cams.clone())
+    out["gen.images"] = torch.as_tensor(r["generated_images"]).numpy()
+    out["gen.cameras"] = torch.as_tensor(r["generated_cameras"]).float().numpy()
+    np.savez_compressed(os.path.join(OUT, "migt_reference_shim.npz"), **out)
+    print("reference-on-shim golden:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -336,3 +395,4 @@ if __name__ == "__main__":
     golden_vqgan_train_full()
     golden_migt_train()
     golden_migt_train_full()
+    golden_migt_reference_shim()

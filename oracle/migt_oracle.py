@@ -1,11 +1,15 @@
 """TEST INFRASTRUCTURE — torch-CPU restatement of the reference TensorFlow MIGT transformer.
 
-**PARITY UNPINNED**: the reference transformer exists only in TensorFlow/Keras
-(viewformer/models/migt.py) and TensorFlow cannot be installed here (no network, TF 2.4.1 has no
-cp312 wheel); the reference ships no tests or golden vectors for it.  This file restates the
-published algorithm line by line; it is cross-checked only by the structural invariants of
-SURVEY.md §8(c) (tests/test_oracle_pinned.py): single-stream == three-stream logits at the last
-view, and context hidden states independent of the query view.
+Pinned to the reference's own SOURCE, not to TensorFlow's kernels: the reference transformer exists only in
+TensorFlow/Keras (viewformer/models/migt.py) and TensorFlow cannot be installed here (no network, TF 2.4.1 has
+no cp312 wheel), and the reference ships no tests or golden vectors for it.  tests/test_reference_on_shim.py
+therefore executes the reference's files unmodified from /root/reference over oracle/tf_shim.py (a torch-backed
+restatement of the ~70 TensorFlow leaf ops they call) and requires this restatement to reproduce MIGT.call,
+MIGT.train_step (GradientTape + AdamWeightDecay under WarmUp/CosineDecay) and generate_batch_predictions of both
+evaluation scripts to 1e-6; tests/golden/migt_reference_shim.npz carries outputs of that run to machines without
+/root/reference.  Further cross-checks: transformers' GPT2Block / GPT2Model (tests/test_migt_oracle_vs_gpt2.py)
+and the structural invariants of SURVEY.md §8(c) (tests/test_oracle_pinned.py).  What is not exercised anywhere:
+TensorFlow's own floating-point evaluation order.
 
 Follows (file:line in /root/reference):
   viewformer/models/migt.py:13-14      GELU = exact erf form, LayerNorm eps 1e-5

@@ -96,3 +96,118 @@ def load_reference_registry(extra_paths=()):
     sys.modules["viewformer.models"] = m
     spec.loader.exec_module(m)
     return m
+
+
+# ----------------------------------------------------------------------------------------------- the TensorFlow half, on oracle/tf_shim.py
+def migt_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "viewformer", "models", "migt.py"))
+
+
+def load_reference_migt():
+    """Executes the reference's transformer sources UNMODIFIED from /root/reference — models/migt.py, models/branching_attention.py,
+    models/utils.py (WarmUp, AdamWeightDecay, create_optimizer), utils/tensorflow.py (shape_list), utils/geometry_tf.py,
+    utils/metrics.py, utils/schedules.py — with oracle/tf_shim.py answering ``import tensorflow``.  Returns the ``migt`` module."""
+    if "migt" in _cache:
+        return _cache["migt"]
+    if not migt_available():
+        raise RuntimeError("reference sources not present at %s" % REFERENCE_ROOT)
+    from oracle import tf_shim
+    tf_shim.install()
+    load_reference_registry()                                       # the real viewformer.models package (config, registry)
+    R = os.path.join(REFERENCE_ROOT, "viewformer")
+    # (utils/__init__.py itself is not executed: it pulls tqdm / requests download helpers that are not on this path)
+    sys.modules["viewformer.utils"].__path__ = [os.path.join(R, "utils")]
+    for name in ("geometry_tf", "tensorflow", "metrics"):
+        _load("viewformer.utils." + name, os.path.join(R, "utils", name + ".py"))
+        setattr(sys.modules["viewformer.utils"], name, sys.modules["viewformer.utils." + name])
+    m = importlib.import_module("viewformer.models.migt")           # resolves .branching_attention / .config / .utils from the real directory
+    _cache["migt"] = m
+    return m
+
+
+_TF_NAME = {"wpe.embeddings": "wpe/embeddings"}
+
+
+def build_reference_migt(state_dict, dynamic_pose_weights=None, **cfg_overrides):
+    """The real reference MIGT (constructed by its own __init__, which runs one forward to create the variables) with every variable
+    overwritten from ``state_dict`` (keys of viewformer_b200.MIGT / oracle.synth: 'h.0.attn.c_attn.weight', 'wpe.embeddings', ...).
+    Variable names come from the shim's call-time scopes ('migt/h.0/attn/c_attn/weight:0'); each state_dict key must match exactly one."""
+    migt = load_reference_migt()
+    cfg_mod = sys.modules["viewformer.models.config"]
+    sched = sys.modules["viewformer.utils.schedules"]
+    kw = dict(cfg_overrides)
+    if isinstance(kw.get("localization_weight"), (str, int, float)):
+        kw["localization_weight"] = sched.Schedule.from_str(str(kw["localization_weight"]))
+    model = migt.MIGT(cfg_mod.MIGTConfig(**kw))
+    variables = {v.name[:-2]: v for v in model.variables}           # strip ':0'
+    used = set()
+    for key, val in state_dict.items():
+        suffix = "/" + key.replace(".", "/")
+        # layer names contain dots ('h.0'): compare with dots turned into slashes on both sides
+        hits = [n for n in variables if ("/" + n.replace(".", "/")).endswith(suffix)]
+        if not hits and key.startswith("pose_classifier.") and not model.use_localization:
+            continue                                                # the pose head is never called, Keras never builds its variables
+        if len(hits) != 1:
+            raise KeyError(f"state_dict key {key} matches {hits} among the reference's variables")
+        v = variables[hits[0]]
+        if tuple(v.shape) != tuple(val.shape):
+            raise ValueError(f"{key}: reference variable {hits[0]} has shape {tuple(v.shape)}, state_dict {tuple(val.shape)}")
+        v.assign(val)
+        used.add(hits[0])
+    left = sorted(set(variables) - used)
+    if dynamic_pose_weights is not None:
+        variables["pos_ori_weights"].assign(torch.as_tensor(dynamic_pose_weights, dtype=torch.float32))
+        left = [n for n in left if n != "pos_ori_weights"]
+    left = [n for n in left if n != "pos_ori_weights"]              # keeps its initial [0, -3] unless given
+    if left:
+        raise KeyError(f"reference variables without a state_dict entry: {left}")
+    return model
+
+
+def load_reference_evaluate():
+    """The reference's evaluation callers, executed unmodified on the shim: evaluate/evaluate_transformer.py (generate_batch_predictions,
+    to_relative_cameras, from_relative_cameras, normalize_cameras) and evaluate/evaluate_transformer_multictx.py.  Argument-parsing
+    decorators (aparse.click / ConditionalType) and the dataset loader table are stubbed — they are not on the path."""
+    if "evaluate" in _cache:
+        return _cache["evaluate"]
+    load_reference_migt()
+    R = os.path.join(REFERENCE_ROOT, "viewformer")
+    ap = sys.modules["aparse"]
+    if not hasattr(ap, "click"):
+        click = types.SimpleNamespace(command=lambda *a, **k: (lambda f: f))
+        ap.click = click
+        ap.ConditionalType = lambda name, table, default=None: typing.Any
+    common = _load("viewformer.utils._common", os.path.join(R, "utils", "_common.py"))
+    for n in ("SplitIndices", "unique", "batch_slice", "batch_len", "single", "dict_replace", "is_torch_model"):
+        if hasattr(common, n):
+            setattr(sys.modules["viewformer.utils"], n, getattr(common, n))
+    for pkg, sub in (("viewformer.data", "data"), ("viewformer.evaluate", "evaluate")):
+        if pkg not in sys.modules:
+            p = types.ModuleType(pkg)
+            p.__path__ = []
+            sys.modules[pkg] = p
+    loaders = types.ModuleType("viewformer.data.loaders")
+    loaders.get_loaders = lambda: {}
+    sys.modules["viewformer.data.loaders"] = loaders
+    _load("viewformer.data._common", os.path.join(R, "data", "_common.py"))
+    ev = _load("viewformer.evaluate.evaluate_transformer", os.path.join(R, "evaluate", "evaluate_transformer.py"))
+    mc = _load("viewformer.evaluate.evaluate_transformer_multictx", os.path.join(R, "evaluate", "evaluate_transformer_multictx.py"))
+    _cache["evaluate"] = (ev, mc)
+    return _cache["evaluate"]
+
+
+class ReferenceCodebookNHWC:
+    """The real reference torch codebook (vqgan_th.VQGAN, NCHW) behind the TF-flavour calls the evaluation scripts make
+    (models/vqgan.py:284-301: NHWC images in, NHWC images out) — a pure layout adapter."""
+
+    def __init__(self, vqgan):
+        self.model, self.config = vqgan, vqgan.config
+
+    def encode(self, x):
+        with torch.no_grad():
+            q, diff, codes = self.model.encode(torch.as_tensor(x).as_subclass(torch.Tensor).permute(0, 3, 1, 2).contiguous())
+        return q.permute(0, 2, 3, 1), diff, codes
+
+    def decode_code(self, codes, training=False):
+        with torch.no_grad():
+            return self.model.decode_code(torch.as_tensor(codes).as_subclass(torch.Tensor).long()).permute(0, 2, 3, 1).contiguous()

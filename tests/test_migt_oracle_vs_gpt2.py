@@ -1,4 +1,4 @@
-"""Hardening of the (unpinned) MIGT oracle: the reference transformer is a GPT-2 derivative (models/migt.py:59-96 Conv1D / MLP,
+"""Third-party cross-check of the MIGT oracle (its pin to the reference's own code is tests/test_reference_on_shim.py): the reference transformer is a GPT-2 derivative (models/migt.py:59-96 Conv1D / MLP,
 :182-238 attention + pre-LN block are the HF TFGPT2 layers with the (v,q,k) split, no 1/sqrt(d) scale and block-causal masking).
 With ONE token per view (token_image_size = 1) block-causal attention degenerates to ordinary causal attention, so the oracle's
 `block()` must reproduce `transformers`' torch GPT2Block (scale_attn_weights=False, exact-erf GELU, LayerNorm eps 1e-5) once the

@@ -201,7 +201,8 @@ def test_migt_compute_losses_small(precision, tol, smoothing):
 
 
 def test_migt_full_size_vs_oracle_golden(golden_dir):
-    """Full-size MIGT (12 layers, d=768), B=1,T=10: golden from the restatement (parity unpinned: TF absent)."""
+    """Full-size MIGT (12 layers, d=768), B=1,T=10: golden from the restatement, reproduced by the reference's own MIGT.call over
+    oracle/tf_shim.py (tests/test_reference_on_shim.py)."""
     g = np.load(os.path.join(golden_dir, "migt_full.npz"))
     cfg = MIGTConfig()
     B, T = int(g["B"]), int(g["T"])

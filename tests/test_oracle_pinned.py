@@ -124,3 +124,45 @@ def test_camera_helpers_round_trip():
     assert rel[:, 0, :3].abs().max() < 1e-6 and (rel[:, 0, 3] - 1).abs().max() < 1e-6
     back = mo.from_relative_cameras(rel, tr)
     assert (back - cams).abs().max() < 1e-5
+
+
+def test_oracle_matches_reference_on_shim_fixture(golden_dir):
+    """tests/golden/migt_reference_shim.npz holds outputs of the reference's OWN migt.py / branching_attention.py /
+    evaluate_transformer.py executed over oracle/tf_shim.py (written by oracle/make_golden.py::golden_migt_reference_shim in the
+    container, where tests/test_reference_on_shim.py runs the same comparison live).  The restatement must reproduce every array."""
+    from oracle.make_golden import REF_SHIM_CASES, REF_SHIM_BASE, ref_shim_inputs
+    from oracle import vqgan_oracle
+    g = _g(golden_dir, "migt_reference_shim.npz")
+    for i, (variant, extra) in enumerate(REF_SHIM_CASES):
+        kw = dict(REF_SHIM_BASE, **extra)
+        cfg = MIGTConfig(**kw)
+        sd = synth.make_migt_state_dict(cfg, 3)
+        if kw.get("use_dynamic_pose_loss"):
+            sd["pose_loss_weighting_criterion.pos_ori_weights"] = torch.tensor([0.3, -2.0])
+        inputs, losses = ref_shim_inputs(cfg, variant)
+        use_loc = str(kw.get("localization_weight", "1")) != "0"
+        lw = float(g[f"c{i}.localization_weight"]) if f"c{i}.localization_weight" in g.files else 1.0
+        with torch.no_grad():
+            o = mo.forward(sd, cfg, inputs, compute_losses=losses, use_localization=use_loc, localization_weight=lw)
+        assert len(o["hidden_states"]) == int(g[f"c{i}.n_streams"])
+        keys = [k[len(f"c{i}."):] for k in g.files if k.startswith(f"c{i}.") and not k.endswith(("n_streams", "localization_weight"))]
+        assert "logits" in keys and ("pose_prediction" in keys) == use_loc and ("pose_prediction" in o) == use_loc
+        for k in keys:
+            want = torch.from_numpy(g[f"c{i}.{k}"])
+            got = torch.as_tensor(o[k]).float()
+            assert got.shape == want.shape, (i, k)
+            assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max())), (i, variant, k)
+    # generate_batch_predictions of evaluate_transformer.py (real torch codebook + MIGT on the shim) vs the two oracles chained
+    vcfg = VQGANConfig(**SMALL_VQ)
+    vsd = synth.make_vqgan_state_dict(vcfg, 0)
+    kw = dict(REF_SHIM_BASE, n_embeddings=vcfg.n_embed, token_image_size=8)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    images = synth.make_images_uint8(2, 4, size=vcfg.image_size, seed=11)
+    cams = synth.make_cameras(2, 4, seed=12)
+    with torch.no_grad():
+        o = mo.generate_batch_predictions(lambda inp: mo.forward(sd, cfg, inp), lambda x: vo.encode(vsd, vcfg, x)[-1],
+                                          lambda c: vo.decode_code(vsd, vcfg, c), cfg, images, cams)
+    diff = (o["generated_images"].int() - torch.from_numpy(g["gen.images"]).int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3        # uint8 views: the codebook restatement may round one LSB apart
+    assert float((o["generated_cameras"] - torch.from_numpy(g["gen.cameras"])).abs().max()) < 1e-5

@@ -1,0 +1,306 @@
+"""The reference's OWN transformer sources executed here (container only): viewformer/models/migt.py, models/branching_attention.py,
+models/utils.py (create_optimizer, WarmUp, AdamWeightDecay), utils/{tensorflow,geometry_tf,metrics,schedules}.py and
+evaluate/evaluate_transformer{,_multictx}.py are loaded UNMODIFIED from /root/reference with oracle/tf_shim.py answering
+``import tensorflow`` (TensorFlow 2.4.1 cannot be installed: no cp312 wheel, no network).  Every line of model wiring is the
+reference's; the shim restates only leaf tensor ops, and its own semantics are checked below against TensorFlow's documented behaviour.
+
+What this pins:
+  * oracle/migt_oracle.py::forward == MIGT.call (migt.py:338-455) for the generate() call, the localisation call, compute_losses with
+    label smoothing / pose multiplier / schedules / dynamic pose weights, explicit output_poses + localization_tokens, use_localization off;
+  * the COMMITTED fixtures the GPU parity tests consume (tests/golden/migt_small.npz, migt_full.npz, migt_train_small.npz,
+    migt_train_full.npz) are reproduced by the reference's code: forward, MIGT.train_step (GradientTape, clip, AdamWeightDecay under
+    WarmUp(CosineDecay)) — so CUDA == fixture (tests -m gpu) and fixture == reference (here) close the chain;
+  * generate_batch_predictions of both evaluation scripts == the oracle's restatements.
+Skipped where /root/reference does not exist (the GPU box); tests/test_oracle_pinned.py::test_oracle_matches_reference_on_shim_fixture
+checks the oracle against outputs of this setup committed as tests/golden/migt_reference_shim.npz everywhere."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader, synth, migt_oracle as mo
+from viewformer_b200.config import MIGTConfig, VQGANConfig
+
+pytestmark = pytest.mark.skipif(not ref_loader.migt_available(), reason="reference sources not present (container-only test)")
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SMALL = dict(n_layer=2, n_head=4, d_model=64, sequence_size=4, n_embeddings=40, token_image_size=2, n_loss_skip=1)
+
+
+@pytest.fixture(scope="module")
+def tf():
+    from oracle import tf_shim
+    tf_shim.install()
+    ref_loader.load_reference_migt()
+    yield sys.modules["tensorflow"]
+    tf_shim.uninstall()                       # later test modules must not see a `tensorflow` in sys.modules
+
+
+def _var(model, key):
+    suffix = "/" + key.replace(".", "/")
+    hits = [v for v in model.variables if ("/" + v.name[:-2].replace(".", "/")).endswith(suffix)]
+    assert len(hits) == 1, (key, [v.name for v in hits])
+    return hits[0]
+
+
+# ------------------------------------------------------------------------------------------------ the shim's own semantics
+def test_shim_ops_follow_documented_tensorflow_semantics(tf):
+    x = tf.reshape(tf.range(24), [2, 3, 4])
+    assert x.shape.as_list() == [2, 3, 4] and tf.shape(x).tolist() == [2, 3, 4] and tf.rank(x) == 3
+    a, b = tf.split(x, 2, axis=-1)                                   # an int = NUMBER of equal parts (torch.split: size of a part)
+    assert a.shape == (2, 3, 2) and b[0, 0].tolist() == [2, 3]
+    p, q = tf.split(x, (1, 3), axis=-1)
+    assert p.shape == (2, 3, 1) and q.shape == (2, 3, 3)
+    assert tf.repeat(tf.range(3), 2).tolist() == [0, 0, 1, 1, 2, 2]  # element-wise, not tiling
+    assert tf.tile(tf.range(3), [2]).tolist() == [0, 1, 2, 0, 1, 2]
+    assert tf.one_hot([0, 2], 3).tolist() == [[1, 0, 0], [0, 0, 1]]
+    assert tf.gather(tf.constant([[1., 2.], [3., 4.], [5., 6.]]), tf.constant([[2, 0]])).tolist() == [[[5, 6], [1, 2]]]
+    assert tf.constant(3).dtype == tf.int32 and tf.constant(3.0).dtype == tf.float32 and tf.constant(3, "float32").dtype == tf.float32
+    assert tf.constant(np.zeros(2, np.uint8)).dtype == tf.uint8       # numpy arrays keep their dtype
+    g = tf.constant([3.0, 4.0])
+    assert torch.allclose(tf.clip_by_norm(g, 1.0), torch.tensor([0.6, 0.8])) and torch.equal(tf.clip_by_norm(g, 10.0), torch.tensor([3.0, 4.0]))
+    assert torch.allclose(tf.linalg.l2_normalize(g, axis=-1), torch.tensor([0.6, 0.8]))
+    assert torch.equal(tf.linalg.l2_normalize(tf.zeros([2]), axis=-1, epsilon=1e-12), torch.zeros(2))      # x * rsqrt(max(sum x^2, eps))
+    u8 = tf.constant(np.array([0, 1, 128, 255], np.uint8))
+    f = tf.image.convert_image_dtype(u8, tf.float32)
+    assert torch.equal(f, u8.float() * torch.tensor(1 / 255, dtype=torch.float32))
+    assert tf.image.convert_image_dtype(tf.constant([0.0, 0.5, 0.999, 1.0]), tf.uint8).tolist() == [0, 127, 255, 255]    # x * 255.5, truncated
+    logits = tf.constant([[1.0, 2.0, 3.0]])
+    lp = torch.log_softmax(logits, -1)
+    assert torch.allclose(tf.nn.sparse_softmax_cross_entropy_with_logits(tf.constant([2]), logits), -lp[:, 2])
+    assert torch.allclose(tf.nn.softmax_cross_entropy_with_logits(tf.constant([[0.5, 0.5, 0.0]]), logits), -(0.5 * lp[:, 0] + 0.5 * lp[:, 1]))
+    assert torch.allclose(tf.losses.mse(tf.constant([[1.0, 3.0]]), tf.constant([[0.0, 0.0]])), torch.tensor([5.0]))
+    assert torch.allclose(tf.nn.gelu(tf.constant([1.0])), torch.tensor([0.8413447]))                       # exact erf form
+    assert torch.equal(tf.matmul(tf.ones([2, 3]), tf.ones([4, 3]), transpose_b=True), torch.full((2, 4), 3.0))
+    assert tf.ones(tf.shape(tf.zeros([5, 2]))[0], "float32").shape == (5,)                                  # scalar shape -> 1-D
+    init = tf.keras.initializers.TruncatedNormal(0.02)                # positional argument = MEAN (stddev stays 0.05), as in Keras
+    w = init([4000])
+    assert abs(float(w.mean()) - 0.02) < 5e-3 and float((w - 0.02).abs().max()) <= 0.1 + 1e-6
+    ln = tf.keras.layers.LayerNormalization(epsilon=1e-5, name="ln")
+    y = ln(tf.constant([[1.0, 2.0, 3.0, 6.0]]))
+    assert abs(float(y.mean())) < 1e-6 and [v.name for v in ln.variables] == ["ln/gamma:0", "ln/beta:0"]
+    sched = tf.keras.experimental.CosineDecay(2.0, 10)
+    assert abs(float(sched(0)) - 2.0) < 1e-6 and abs(float(sched(5)) - 1.0) < 1e-6 and abs(float(sched(20))) < 1e-6
+
+
+def test_shim_adam_matches_torch_adam(tf):
+    """The Adam base under the reference's AdamWeightDecay: Keras' epsilon-outside-the-bias-correction form.  Against torch.optim.Adam,
+    whose epsilon sits inside (eps_hat = eps * sqrt(1 - b2^t)), the two agree when eps is negligible."""
+    w = tf.Variable(torch.linspace(-1, 1, 7))
+    opt = tf.keras.optimizers.Adam(learning_rate=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-12)
+    p = torch.nn.Parameter(torch.linspace(-1, 1, 7))
+    ref = torch.optim.Adam([p], lr=0.01, betas=(0.9, 0.999), eps=1e-12)
+    for step in range(4):
+        g = torch.sin(torch.arange(7.0) + step)
+        opt.apply_gradients([(g, w)])
+        p.grad = g.clone()
+        ref.step()
+    assert float((w.detach() - p.detach()).abs().max()) < 1e-6 and int(opt.iterations) == 4
+
+
+# ------------------------------------------------------------------------------------------------ MIGT.call == oracle.forward
+def _inputs(cfg, variant, B=2, T=4):
+    codes = synth.make_codes(B, T, n_embed=cfg.n_embeddings, side=cfg.token_image_size, seed=5)
+    cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(B, T, seed=6))[0])
+    if variant == "generate":           # last view masked (evaluate_transformer.py:120-123)
+        return dict(input_ids=torch.cat([codes[:, :-1], torch.full_like(codes[:, :1], cfg.n_embeddings)], 1), poses=cams), False
+    if variant == "localize":           # one pose fewer than views (evaluate_transformer.py:135-137)
+        return dict(input_ids=codes, poses=cams[:, :-1]), False
+    if variant == "losses":
+        return dict(input_ids=codes, poses=cams), True
+    if variant == "explicit":           # the multictx call (evaluate_transformer_multictx.py:61-72)
+        return dict(input_ids=codes, poses=cams, output_poses=cams.flip(1).contiguous(), localization_tokens=codes.flip(0).contiguous()), False
+    raise ValueError(variant)
+
+
+CASES = [("generate", {}), ("localize", {}), ("losses", {}), ("explicit", {}),
+         ("generate", dict(localization_weight="0")), ("losses", dict(localization_weight="0")),
+         ("losses", dict(label_smoothing=0.1, pose_multiplier=0.3, image_generation_weight=0.7, localization_weight="cosine(2.0,0.5,100)")),
+         ("losses", dict(use_dynamic_pose_loss=True, localization_weight="warmup(linear(1.0,0.2,50),10)")),
+         ("generate", dict(token_image_size=4, n_head=2, sequence_size=6))]
+
+
+@pytest.mark.parametrize("variant,extra", CASES)
+def test_reference_call_equals_oracle_forward(tf, variant, extra):
+    kw = dict(SMALL, **extra)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    dyn = [0.3, -2.0] if kw.get("use_dynamic_pose_loss") else None
+    model = ref_loader.build_reference_migt(sd, dynamic_pose_weights=dyn, **kw)
+    if dyn is not None:
+        sd = dict(sd, **{"pose_loss_weighting_criterion.pos_ori_weights": torch.tensor(dyn)})
+    inputs, losses = _inputs(cfg, variant, T=cfg.sequence_size)
+    step = 7
+    model._train_counter.assign(step)
+    with torch.no_grad():
+        r = model({k: v.clone() for k, v in inputs.items()}, compute_losses=losses, training=False)
+        lw = float(model.localization_weight(step)) if model.use_localization else 0.0
+        o = mo.forward(sd, cfg, inputs, compute_losses=losses, use_localization=model.use_localization, localization_weight=lw)
+    assert len(r["hidden_states"]) == len(o["hidden_states"])
+    keys = ["logits", "loss"] + [k for k in ("pose_prediction", "ce_loss", "pose_loss", "pose_pos_loss", "pose_ori_loss") if k in r]
+    assert all(k in o for k in keys) and ("pose_prediction" in r) == ("pose_prediction" in o)
+    for k in keys:
+        a, b = torch.as_tensor(r[k]).float(), torch.as_tensor(o[k]).float()
+        assert a.shape == b.shape and torch.isfinite(a).all(), k
+        assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max())), (k, float((a - b).abs().max()))
+    for a, b in zip(r["hidden_states"], o["hidden_states"]):
+        assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
+    if losses and model.use_localization:
+        assert abs(float(r["localization_weight"]) - lw) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ committed fixtures == reference
+@pytest.mark.parametrize("tag,overrides,B,T", [("small", dict(n_layer=2, n_head=4, d_model=128, sequence_size=4, n_loss_skip=1), 2, 4), ("full", {}, 1, 10)])
+def test_reference_reproduces_committed_forward_fixture(tf, tag, overrides, B, T):
+    """tests/golden/migt_{small,full}.npz (what tests/test_models_gpu.py compares the CUDA transformer with; `full` = the 12-layer,
+    d = 768 BASELINE model) recomputed by the reference's MIGT.call + reduce_cameras."""
+    G = np.load(os.path.join(GOLDEN, f"migt_{tag}.npz"))
+    cfg = MIGTConfig(**overrides)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    model = ref_loader.build_reference_migt(sd, **overrides)
+    codes = synth.make_codes(B, T, seed=5)
+    cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(B, T, seed=6))[0])
+    ids = torch.cat([codes[:, :-1], torch.full_like(codes[:, :1], cfg.n_embeddings)], 1)
+    with torch.no_grad():
+        last = model(dict(input_ids=ids, poses=cams), training=False)["logits"][:, -1]
+        o2 = model(dict(input_ids=codes, poses=cams[:, :-1]), training=False)
+        pose = model.reduce_cameras(o2["pose_prediction"][:, -1:], -2)
+    assert float((last[:1] - torch.from_numpy(G["logits_last"])).abs().max()) < 2e-5
+    assert np.array_equal(last.argmax(-1).numpy(), G["argmax_last"])
+    assert float((pose - torch.from_numpy(G["pose_last"])).abs().max()) < 1e-6
+
+
+def test_reference_train_step_reproduces_committed_train_fixture(tf):
+    """Three calls of the reference's MIGT.train_step — GradientTape over its forward, per-tensor clip, its own create_optimizer →
+    AdamWeightDecay under WarmUp(CosineDecay) — land on the post-step weights of tests/golden/migt_train_small.npz, the file the CUDA
+    trainer is compared with in tests/test_train_gpu.py."""
+    from oracle import make_golden as mg
+    kw = dict(mg.MIGT_TRAIN)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 9)
+    model = ref_loader.build_reference_migt(sd, **kw)
+    utils = sys.modules["viewformer.models.utils"]
+    opt, _ = utils.create_optimizer(cfg.learning_rate, num_train_steps=cfg.total_steps, num_warmup_steps=mg.MIGT_TRAIN_WARMUP,
+                                    weight_decay_rate=cfg.weight_decay)
+    assert type(opt).__name__ == "AdamWeightDecay"
+    model.compile(optimizer=opt)
+    G = np.load(os.path.join(GOLDEN, "migt_train_small.npz"))
+    names = [str(n) for n in G["names"]]
+    gen = torch.Generator().manual_seed(77)
+    probe = {k: torch.randn(sd[k].shape, generator=gen) for k in names}
+    keep = [k[3:] for k in G.files if k.startswith("p0.")]
+    assert len(keep) >= 6
+    losses = []
+    for step in range(3):
+        codes = synth.make_codes(2, 4, n_embed=cfg.n_embeddings, seed=50 + step)
+        cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(2, 4, seed=60 + step))[0])
+        model._train_counter.assign(step)
+        metrics = model.train_step((cams, codes))
+        losses.append(float(metrics["loss"]))                        # running mean of the per-step losses (tf.metrics.Mean)
+        pdot = np.array([float((_var(model, k).detach() * probe[k]).sum()) for k in names])
+        assert np.max(np.abs(pdot - G[f"pdot{step}"]) / (np.abs(G[f"pdot{step}"]) + 1e-3)) < 2e-5, step
+        for k in keep:
+            assert float((_var(model, k).detach() - torch.from_numpy(G[f"p{step}.{k}"])).abs().max()) < 1e-6, (step, k)
+    want = np.cumsum([float(G[f"loss{i}"]) for i in range(3)]) / np.arange(1, 4)
+    assert np.allclose(losses, want, rtol=1e-5)
+    assert int(opt.iterations) == 3
+
+
+class _RecordingOptimizer:
+    """Captures what MIGT.train_step hands to apply_gradients (after its clipping)."""
+
+    def apply_gradients(self, grads_and_vars):
+        self.pairs = [(g, v) for g, v in grads_and_vars]
+
+
+def test_reference_train_step_gradients_full_size(tf):
+    """The 12-layer, d = 768 model (MIGTConfig defaults), label smoothing 0.1, localization weight 0.7: loss terms and the gradient of
+    every tensor as the reference's train_step computes them == tests/golden/migt_train_full.npz (norm and a random projection)."""
+    kw = dict(dropout=0.0, label_smoothing=0.1, localization_weight="0.7", total_steps=100, learning_rate=1e-4)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 13)
+    model = ref_loader.build_reference_migt(sd, **kw)
+    rec = _RecordingOptimizer()
+    model.compile(optimizer=rec)
+    codes = synth.make_codes(1, 5, n_embed=cfg.n_embeddings, seed=70)
+    cams = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(1, 5, seed=71))[0])
+    metrics = model.train_step((cams, codes))
+    G = np.load(os.path.join(GOLDEN, "migt_train_full.npz"))
+    names = [str(n) for n in G["names"]]
+    assert abs(float(metrics["loss"]) - float(G["loss"])) < 1e-5 * abs(float(G["loss"]))
+    assert abs(float(metrics["ce_loss"]) - float(G["ce"].mean())) < 1e-5 and abs(float(metrics["pose_loss"]) - float(G["pose"].mean())) < 1e-5
+    grads = {id(v): g for g, v in rec.pairs}
+    gen = torch.Generator().manual_seed(78)
+    probe = {k: torch.randn(sd[k].shape, generator=gen) for k in names}
+    for i, k in enumerate(names):
+        g = grads[id(_var(model, k))]
+        g = torch.zeros_like(sd[k]) if g is None else g
+        assert abs(float(g.norm()) - G["gnorm"][i]) <= 2e-4 * G["gnorm"][i] + 1e-7, k
+        assert abs(float((g * probe[k]).sum()) - G["gdot"][i]) <= 2e-4 * G["gnorm"][i] * float(probe[k].norm()) + 1e-7, k
+
+
+def test_reference_dynamic_pose_weights_gradient(tf):
+    """use_dynamic_pose_loss: the learned (pos, ori) log-weights are trainable variables of the reference model; their gradient through
+    DynamicLossWeightingCriterion (migt.py:107-120) == autograd through the oracle."""
+    kw = dict(SMALL, dropout=0.0, use_dynamic_pose_loss=True, localization_weight="0.5")
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 4)
+    model = ref_loader.build_reference_migt(sd, dynamic_pose_weights=[0.2, -1.5], **kw)
+    rec = _RecordingOptimizer()
+    model.compile(optimizer=rec)
+    inputs, _ = _inputs(cfg, "losses")
+    model.train_step((inputs["poses"], inputs["input_ids"]))
+    g_ref = [g for g, v in rec.pairs if v.name.startswith("pos_ori_weights")]
+    assert len(g_ref) == 1
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    leaves["pose_loss_weighting_criterion.pos_ori_weights"] = torch.tensor([0.2, -1.5], requires_grad=True)
+    o = mo.forward(leaves, cfg, inputs, compute_losses=True, localization_weight=0.5)
+    o["loss"].mean().backward()
+    assert float((g_ref[0] - leaves["pose_loss_weighting_criterion.pos_ori_weights"].grad).abs().max()) < 1e-6
+    gw = [g for g, v in rec.pairs if v.name.endswith("h.0/attn/c_attn/weight:0")][0]
+    assert float((gw - leaves["h.0.attn.c_attn.weight"].grad).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ the evaluation callers
+@pytest.mark.parametrize("augment,loc", [("relative", "1"), ("relative", "0"), ("no", "1")])
+def test_reference_generate_batch_predictions_equal_oracle(tf, augment, loc):
+    """evaluate_transformer.py:97-146 and evaluate_transformer_multictx.py:37-95 run as shipped — with the REAL reference torch codebook
+    behind an NHWC adapter and the real MIGT on the shim — against oracle.generate_batch_predictions{,_multictx}: uint8 views, codes and
+    cameras identical."""
+    from oracle import make_golden as mg
+    ev, mc = ref_loader.load_reference_evaluate()
+    vcfg = VQGANConfig(**mg.SMALL_VQ)
+    vq = ref_loader.build_reference_vqgan(synth.make_vqgan_state_dict(vcfg, 0), **mg.SMALL_VQ)
+    kw = dict(n_layer=2, n_head=4, d_model=64, sequence_size=4, n_embeddings=vcfg.n_embed, token_image_size=8, n_loss_skip=1,
+              augment_poses=augment, localization_weight=loc)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    model = ref_loader.build_reference_migt(sd, **kw)
+    images = synth.make_images_uint8(2, 4, size=vcfg.image_size, seed=11)
+    cams = synth.make_cameras(2, 4, seed=12)
+    codebook = ref_loader.ReferenceCodebookNHWC(vq)
+    use_loc = model.use_localization
+
+    def fwd(inp):
+        return mo.forward(sd, cfg, inp, use_localization=use_loc)
+
+    def enc(x):
+        return vq.encode(x)[-1]
+    with torch.no_grad():
+        r = ev.generate_batch_predictions(model, codebook, images.clone(), cams.clone())
+        o = mo.generate_batch_predictions(fwd, enc, vq.decode_code, cfg, images, cams, use_localization=use_loc)
+    assert r["generated_images"].dtype == torch.uint8 and tuple(r["generated_images"].shape) == (2, 32, 32, 3)
+    assert float(r["generated_images"].float().std()) > 5
+    for k in ("ground_truth_images", "generated_images"):
+        assert torch.equal(torch.as_tensor(r[k]).as_subclass(torch.Tensor), o[k]), k
+    for k in ("ground_truth_cameras", "generated_cameras"):
+        assert float((r[k] - o[k]).abs().max()) < 1e-6, k
+    if use_loc:                                                       # the 3-stream script needs the pose head
+        with torch.no_grad():
+            r = mc.generate_batch_predictions(model, codebook, images.clone(), cams.clone())
+            o = mo.generate_batch_predictions_multictx(fwd, enc, vq.decode_code, cfg, images, cams)
+        assert tuple(r["generated_images"].shape) == (2, 4, 32, 32, 3)
+        assert torch.equal(torch.as_tensor(r["generated_images"]).as_subclass(torch.Tensor), o["generated_images"])
+        assert float((r["generated_cameras"] - o["generated_cameras"]).abs().max()) < 1e-6

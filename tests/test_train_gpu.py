@@ -177,8 +177,8 @@ def test_vqgan_commit_quantizer_training_step_matches_reference(golden_dir):
 
 def test_migt_training_step_matches_oracle_autograd(golden_dir):
     """MIGT.train_step (migt.py:464-505): three optimisation steps against tests/golden/migt_train_small.npz — gradients from torch
-    autograd through the oracle's forward, optimizer / schedule restated from models/utils.py (oracle/make_golden.py).  PARITY UNPINNED
-    like every MIGT fixture (TensorFlow reference cannot run); the oracle's block is cross-checked against HF GPT-2 on the CPU."""
+    autograd through the oracle's forward, optimizer / schedule restated from models/utils.py (oracle/make_golden.py).  The fixture is
+    reproduced by the reference's own MIGT.train_step executed over oracle/tf_shim.py (tests/test_reference_on_shim.py, CPU, container)."""
     from viewformer_b200 import MIGT
     from viewformer_b200.train_migt import MIGTTrainer
     from viewformer_b200.config import MIGTConfig
@@ -278,7 +278,8 @@ def test_migt_dynamic_pose_loss_and_weight_schedule():
 
 def test_migt_training_step_full_size_matches_oracle_autograd(golden_dir):
     """Full-size transformer (MIGTConfig defaults: 12 layers, d = 768): loss terms and the gradient of all 156 tensors of one training step
-    (B = 1, T = 5, dropout 0) against torch autograd through the oracle (tests/golden/migt_train_full.npz; PARITY UNPINNED)."""
+    (B = 1, T = 5, dropout 0) against torch autograd through the oracle (tests/golden/migt_train_full.npz, reproduced by the reference's own
+    train_step over oracle/tf_shim.py in tests/test_reference_on_shim.py)."""
     from viewformer_b200 import MIGT
     from viewformer_b200.train_migt import MIGTTrainer
     from viewformer_b200.config import MIGTConfig
