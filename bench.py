@@ -33,6 +33,8 @@ import torch  # noqa: E402
 N_CTX = 9
 T_VIEWS = N_CTX + 1
 IMG = 128
+WORKLOAD = ("interiornet-transformer generate(), 9 context views, batch 32 scenes per GPU (BASELINE configs[1]): "
+            "uint8 images -> VQ-encode 9 ctx -> MIGT -> argmax -> VQ-decode -> uint8 view")     # identical in both arms
 
 
 def parse():
@@ -202,8 +204,9 @@ def run_reference(args):
         "impl": "reference", "metric": "novel views/sec (128x128, 9-ctx)", "value": vps, "unit": "views/s", "n_gpus": args.gpus,
         "steps": len(times), "steps_requested": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "interiornet-transformer generate(), 9 context views (BASELINE configs[1])", "scenes_per_step": n,
-                   "localization": False},
+        "config": {"workload": WORKLOAD, "precision": "fp32", "scenes_per_step": n, "views": T_VIEWS, "image": IMG, "localization": False,
+                   "encodes_per_scene": "10 (the reference encodes the target view too, evaluate_transformer.py:109-116)",
+                   "sample": f"bounded sample: {n} of the workload's {args.scenes} scenes per step"},
         "cpu_baseline": {"value": vps, "unit": "views/s", "cores": ref.cores, "kind": "port", "sample": sample},
         "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -474,8 +477,7 @@ def run_b200(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"mixed": "f32 encoder (bit-exact codes) + bf16 transformer/decoder"}.get(args.precision, args.precision),
         "data": "synthetic",
-        "config": {"workload": "interiornet-transformer generate(), 9 context views, batch 32 scenes per GPU (BASELINE configs[1]): "
-                               "uint8 images -> VQ-encode 9 ctx -> MIGT -> argmax -> VQ-decode -> uint8 view",
+        "config": {"workload": WORKLOAD,
                    "precision": args.precision, "scenes_per_gpu": B, "views": T_VIEWS, "image": IMG, "localization": False,
                    "parallelism": f"dp{world} (independent shards)",
                    "encodes_per_scene": "9 (the reference also encodes the target view and discards it; cpu_baseline runs the reference's 10)",
