@@ -139,15 +139,21 @@ def _block_entries(block):
         pos += vlen
 
 
-def _read_block(data, offset, size):
+def _read_block(data, offset, size, verify=False):
+    """Block contents; every block is followed by a 5-byte trailer: compression type + masked crc32c(contents + type)."""
+    if offset + size + 5 > len(data):
+        raise ValueError("SSTable block handle points past the end of the file")
     ctype = data[offset + size]
     if ctype != 0:
         raise NotImplementedError("compressed SSTable block (type %d): TensorFlow writes checkpoint indices uncompressed" % ctype)
+    if verify and struct.unpack_from("<I", data, offset + size + 1)[0] != masked_crc(data[offset:offset + size + 1]):
+        raise ValueError(f"SSTable block at offset {offset}: crc32c mismatch")
     return data[offset:offset + size]
 
 
-def read_index(prefix):
-    """``<prefix>.index`` -> {key: value bytes} (values are serialized BundleHeaderProto / BundleEntryProto)."""
+def read_index(prefix, verify=False):
+    """``<prefix>.index`` -> {key: value bytes} (values are serialized BundleHeaderProto / BundleEntryProto).  ``verify`` checks the
+    crc32c trailer of every table block (LevelDB's ``verify_checksums``; off by default as in TensorFlow's BundleReader)."""
     with open(prefix + ".index", "rb") as f:
         data = f.read()
     if len(data) < 48 or struct.unpack_from("<Q", data, len(data) - 8)[0] != _MAGIC:
@@ -159,10 +165,10 @@ def read_index(prefix):
     ioff, pos = _varint(footer, pos)       # index block handle
     isize, pos = _varint(footer, pos)
     out = {}
-    for _, handle in _block_entries(_read_block(data, ioff, isize)):
+    for _, handle in _block_entries(_read_block(data, ioff, isize, verify)):
         boff, p = _varint(handle, 0)
         bsize, p = _varint(handle, p)
-        for k, v in _block_entries(_read_block(data, boff, bsize)):
+        for k, v in _block_entries(_read_block(data, boff, bsize, verify)):
             out[k.decode("utf-8", "surrogateescape")] = v
     return out
 
