@@ -80,3 +80,27 @@ def test_latent_code_transformer_rebatches_across_scenes():
         assert cb.calls == [5, 5, 5]                          # 15 frames encoded in full batches of 5 across scene boundaries
     finally:
         L.resize_u8 = orig
+
+
+def test_frames_feature_png_roundtrip(tmp_path):
+    """The raw-dataset side of generate-codes (commands/generate_codes.py:58-66): scenes carry `frames` as a bytes_list of encoded
+    images; decode_frames turns them into the uint8 [T,H,W,3] array LatentCodeTransformer takes (PNG is lossless, so exact)."""
+    import io
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(4)
+    frames = rng.integers(0, 256, (3, 20, 24, 3), dtype=np.uint8)
+    blobs = []
+    for f in frames:
+        buf = io.BytesIO()
+        PIL.fromarray(f).save(buf, format="PNG")
+        blobs.append(buf.getvalue())
+    cams = rng.standard_normal((3, 7)).astype(np.float32)
+    path = str(tmp_path / "raw.tfrecord")
+    with D.TFRecordWriter(path) as w:
+        w.write(D.encode_example(dict(frames=blobs, cameras=cams)))
+    (rec,) = list(D.read_tfrecords(path, verify=True))
+    ex = D.decode_example(rec)
+    assert list(ex["frames"]) == blobs
+    got = D.decode_frames(ex["frames"])
+    assert got.dtype == np.uint8 and got.shape == frames.shape and np.array_equal(got, frames)
+    assert np.array_equal(np.asarray(ex["cameras"], np.float32).reshape(3, 7), cams)
