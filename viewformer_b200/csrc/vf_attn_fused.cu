@@ -451,7 +451,8 @@ static int attn_launch(const void* qk, const void* vt, int B, int S, int n_strea
         if ((rc = make_tmap_16bit(&prm.tmV, vt, dims, str, box)) != VF_OK) return rc;
     }
     constexpr int smem = 2 * Q_BYTES + KSTAGES * K_BYTES + VSTAGES * V_BYTES + 1024 + 256;
-    static bool configured = false;
+    static vf_per_device_flag configured_pd;          // function attributes are per device
+    bool& configured = configured_pd.current();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_block_causal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_block_causal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

@@ -9,6 +9,19 @@
 
 void vf_set_error(const char* fmt, ...);
 
+// One-time configuration that belongs to a DEVICE, not to the process: cudaFuncSetAttribute acts on the current device's context, so a
+// second device used by the same process needs its own call.  Usage:
+//     static vf_per_device_flag flag;  bool& configured = flag.current();  if (!configured) { ...; configured = true; }
+struct vf_per_device_flag {
+    static constexpr int kMaxDevices = 64;
+    bool done[kMaxDevices] = {};
+    bool& current() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+        return done[d];
+    }
+};
+
 #define VF_CHECK_ARG(cond, ...)                                  \
     do {                                                         \
         if (!(cond)) {                                           \

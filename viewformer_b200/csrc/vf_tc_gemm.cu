@@ -1632,7 +1632,8 @@ int launch(const TcParams& prm, dim3 grid, cudaStream_t st) {
     static_assert(kStages % KGROUP == 0 && HALO_SLOTS % KGROUP == 0, "ring slots must form whole groups");
     static_assert(smem <= 232448, "shared memory budget");
     static_assert((4 * WIDE_XFORM_WARPS) % 8 == 0, "transform rows must advance by a multiple of 8");
-    static bool configured = false;
+    static vf_per_device_flag configured_pd;          // function attributes are per device
+    bool& configured = configured_pd.current();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<kBlockN, kStages, kTF32, k2Cta>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
@@ -1721,7 +1722,8 @@ static int launch_conv_wide(const vf_tc_gemm_t* q, cudaStream_t st) {
         cudaError_t e = cudaMemsetAsync(q->gn_sums, 0, sizeof(double) * 2 * q->gn_groups * q->N, st);
         if (e != cudaSuccess) { vf_set_error("vf_tc_gemm: memset gn_sums: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     }
-    static bool configured = false;
+    static vf_per_device_flag configured_pd;          // function attributes are per device
+    bool& configured = configured_pd.current();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv3x3_wide_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
@@ -1799,7 +1801,8 @@ static int launch_gemm_wide(const vf_tc_gemm_t* q, long long M, cudaStream_t st)
     if (pair_enabled < 0) { const char* e = getenv("VF_TC_WIDE2"); pair_enabled = (e && e[0] == '1') ? 1 : 0; }
     const bool k2 = pair_enabled && q->Ncols % 256 == 0 && prm.tiles_f % 2 == 0;
     prm.idesc = make_idesc(false, k2 ? 256 : 128, 256);
-    static bool configured = false;
+    static vf_per_device_flag configured_pd;          // function attributes are per device
+    bool& configured = configured_pd.current();
     if (!configured) {
         cudaError_t e = cudaSuccess;
         auto cfg = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM); };

@@ -629,7 +629,8 @@ extern "C" int vf_vq_lookup_fused(const float* z, const void* Eh_f16, const floa
     prm.idesc = make_idesc_16bit(0, 256, TN);
     cudaError_t e = cudaMemsetAsync(counter, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: memset: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
-    static bool configured = false;
+    static vf_per_device_flag configured_pd;          // function attributes are per device
+    bool& configured = configured_pd.current();
     if (!configured) {
         e = cudaFuncSetAttribute(vq_lookup_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) { vf_set_error("vf_vq_lookup_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
