@@ -246,10 +246,13 @@ int vf_dropout(const float* x, int64_t n, float rate, uint64_t seed, float* y, v
  *     torch 'nearest'; result = uint8(clamp(interp(x / 255), 0, 1) * 255).
  *   vf_image_pair_sums: out[2n] = sum |a - b|, out[2n+1] = sum (a - b)^2 over image n (exact integers) -> MSE / MAE / RMSE / PSNR.
  *   vf_ssim_u8: utils/metrics.py:17-73 (7x7 uniform window, VALID, sample covariance, data range 1); out[n] = mean SSIM of image n.
+ *   vf_ssim_u8_k: the same with explicit K1 / K2 — utils/metrics.py:176-184 (SSIMMetric, the one the evaluators use) calls
+ *     ssim(gt, images, 1), i.e. K1 = 1, so C1 = 1 instead of 1e-4.
  * ---------------------------------------------------------------------------------------- */
 int vf_resize_u8(const void* x_u8, int N, int H, int W, int C, int OH, int OW, int bilinear, void* y_u8, vf_stream_t s);
 int vf_image_pair_sums(const void* a_u8, const void* b_u8, int N, int64_t per_image, uint64_t* out, vf_stream_t s);
 int vf_ssim_u8(const void* a_u8, const void* b_u8, int N, int H, int W, int C, double* out, vf_stream_t s);
+int vf_ssim_u8_k(const void* a_u8, const void* b_u8, int N, int H, int W, int C, double K1, double K2, double* out, vf_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * Codebook

@@ -382,6 +382,52 @@ def golden_migt_reference_shim():
     print("reference-on-shim golden:", len(out), "arrays")
 
 
+EVALUATOR_CASES = [  # (tag, n, gt size, generated size, Evaluator(image_size), seed)
+    ("same", 5, 64, 64, None, 21),          # no resize: integer-exact inputs on both sides
+    ("up", 3, 96, 48, None, 22),            # generated image upsampled bilinearly to the ground truth's size (evaluate_transformer.py:42-45)
+    ("down", 3, 96, 48, 32, 22),            # both brought down to Evaluator(image_size=32)
+]
+
+
+def evaluator_cameras(seed=23, n=7):
+    gt = synth.make_cameras(1, n, seed=seed)[0]
+    g = torch.Generator().manual_seed(seed + 1)
+    gen = gt.clone()
+    gen[:, :3] += 0.3 * torch.randn((n, 3), generator=g)
+    gen[:, 3:] += 0.2 * torch.randn((n, 4), generator=g)              # un-normalised on purpose: the metric normalises
+    return gt, gen
+
+
+def golden_evaluator_reference_shim():
+    """The reference's own Evaluator (evaluate/evaluate_transformer.py:22-67) and metric classes (utils/metrics.py) executed over
+    oracle/tf_shim.py on integer-built synthetic images (oracle/synth.py::make_metric_pair): the numbers viewformer_b200.metrics.Evaluator
+    has to reproduce on the GPU.  LPIPS is replaced by zeros (VGG weights are not available offline) and not stored."""
+    ev, _ = ref_loader.load_reference_evaluate()                      # installs oracle/tf_shim.py as `tensorflow`
+    import tensorflow as tf
+    metrics = sys.modules["viewformer.utils.metrics"]
+    metrics.LPIPSMetric._lpips_pool["vgg"] = lambda a, b: torch.zeros(a.shape[0])
+    out = {}
+    for tag, n, gs, ns, image_size, seed in EVALUATOR_CASES:
+        gt, gen = synth.make_metric_pair(n, gs, ns, seed)
+        E = ev.Evaluator(image_size)
+        E.update_with_image(tf.convert_to_tensor(gt.numpy()), tf.convert_to_tensor(gen.numpy()))
+        r = E.result()
+        for k in ("mse", "rmse", "mae", "psnr", "ssim"):
+            out[f"{tag}.{k}"] = np.float64(r[k])
+        out[f"{tag}.input_sums"] = np.asarray([int(gt.sum()), int(gen.sum())], np.int64)      # guards the regeneration of the inputs
+    gt_c, gen_c = evaluator_cameras()
+    E = ev.Evaluator()
+    E.update_with_camera(tf.convert_to_tensor(gt_c.numpy()), tf.convert_to_tensor(gen_c.numpy()))
+    r = E.result()
+    for k in ("loc-angle", "loc-dist", "loc-angle-med", "loc-dist-med"):
+        out[f"cam.{k}"] = np.float64(r[k])
+    # the function-level ssim() with its default K1 (what image_metrics()['ssim'] returns) next to SSIMMetric's K1 = 1
+    gt, gen = synth.make_metric_pair(5, 64, 64, 21)
+    out["same.ssim_default_k1"] = np.float64(torch.as_tensor(metrics.ssim(gt.float().numpy() / 255, gen.float().numpy() / 255)).double().mean())
+    np.savez_compressed(os.path.join(OUT, "evaluator_reference_shim.npz"), **out)
+    print("evaluator golden:", {k: float(v) for k, v in out.items() if not k.endswith("sums")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -396,3 +442,4 @@ if __name__ == "__main__":
     golden_migt_train()
     golden_migt_train_full()
     golden_migt_reference_shim()
+    golden_evaluator_reference_shim()

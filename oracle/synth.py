@@ -212,6 +212,20 @@ def make_images_uint8(n_scenes, n_views, size=128, seed=1234, smooth=True):
     return x.permute(0, 2, 3, 1).reshape(n_scenes, n_views, size, size, 3).contiguous()
 
 
+def make_metric_pair(n, gt_size, gen_size, seed):
+    """(ground truth uint8 [n,gt_size,gt_size,3], generated uint8 [n,gen_size,gen_size,3]) for the evaluation-metric fixtures: blocky
+    images plus noise, built with integer ops only (randint / repeat / clamp) so that every machine regenerates the same bytes.
+    ``gen_size`` must divide ``gt_size``; the generated image is the subsampled ground truth plus U{-20..20} noise."""
+    assert gt_size % 8 == 0 and gt_size % gen_size == 0
+    g = _gen(seed)
+    lo = torch.randint(0, 256, (n, 8, 8, 3), generator=g)
+    gt = lo.repeat_interleave(gt_size // 8, 1).repeat_interleave(gt_size // 8, 2)
+    gt = (gt + torch.randint(-12, 13, gt.shape, generator=g)).clamp(0, 255)
+    k = gt_size // gen_size
+    gen = (gt[:, ::k, ::k] + torch.randint(-20, 21, (n, gen_size, gen_size, 3), generator=g)).clamp(0, 255)
+    return gt.to(torch.uint8).contiguous(), gen.to(torch.uint8).contiguous()
+
+
 def make_cameras(n_scenes, n_views, seed=4321):
     """f32 [B,T,7] = xyz ~ N(0,1) | unit quaternion with w>=0."""
     g = _gen(seed)

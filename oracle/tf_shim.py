@@ -415,6 +415,24 @@ class Metric(Mean):
     pass
 
 
+class _MeanMetricWrapper(Mean):
+    """tf.keras.metrics.MeanMetricWrapper: both arguments are CAST to the metric's dtype (float32) — uint8 images are not rescaled —
+    the wrapped function reduces the last axis, and the running mean is taken over what is left."""
+    _fn = None
+
+    def update_state(self, y_true, y_pred, sample_weight=None):
+        a, b = _t(y_true).to(torch.float32), _t(y_pred).to(torch.float32)
+        super().update_state(type(self)._fn(a, b), sample_weight)
+
+
+class MeanSquaredError(_MeanMetricWrapper):
+    _fn = staticmethod(lambda a, b: ((b - a) ** 2).mean(-1))
+
+
+class MeanAbsoluteError(_MeanMetricWrapper):
+    _fn = staticmethod(lambda a, b: (b - a).abs().mean(-1))
+
+
 class GradientTape:
     def __enter__(self):
         return self
@@ -646,6 +664,25 @@ def _top_k(x, k=1, sorted=True, name=None):
     return r.values, r.indices.to(torch.int32)
 
 
+def _depthwise_conv2d(input, filter, strides, padding, data_format=None, dilations=None, name=None):
+    """tf.nn.depthwise_conv2d: input NHWC, filter [fh, fw, in_channels, channel_multiplier]; output channel k*mult + q is
+    in-channel k filtered with filter[:, :, k, q] (cross-correlation, like every TF conv).  VALID padding only (utils/metrics.py:37)."""
+    x, w = _t(input), _t(filter)
+    if padding != "VALID" or (data_format not in (None, "NHWC")) or dilations not in (None, [1, 1], (1, 1)):
+        raise NotImplementedError("shim depthwise_conv2d: VALID / NHWC only")
+    fh, fw, cin, mult = w.shape
+    wt = w.permute(2, 3, 0, 1).reshape(cin * mult, 1, fh, fw)          # torch grouped conv: out channel g*mult + q <- group g
+    y = F.conv2d(x.permute(0, 3, 1, 2), wt.to(_dtype(x.dtype)), stride=(int(strides[1]), int(strides[2])), groups=cin)
+    return _t(y.permute(0, 2, 3, 1))
+
+
+def _psnr(a, b, max_val, name=None):
+    """tf.image.psnr: 20*log10(max_val) - 10*log10(mean((a-b)^2 over the last three axes)), computed in float32."""
+    a, b = _t(a).to(torch.float32), _t(b).to(torch.float32)
+    mse = ((a - b) ** 2).mean(dim=(-3, -2, -1))
+    return _t(20.0 * torch.log(torch.as_tensor(float(max_val))) / np.log(10.0) - 10.0 / np.log(10.0) * torch.log(mse))
+
+
 def _mod(name):
     import importlib.machinery
     m = types.ModuleType(name)
@@ -728,6 +765,7 @@ def build():
     tf.nn.compute_average_loss = lambda per_example_loss, sample_weight=None, global_batch_size=None: per_example_loss.sum() / (global_batch_size or per_example_loss.shape[0])
     tf.nn.l2_normalize = _l2_normalize
     tf.nn.top_k = _top_k
+    tf.nn.depthwise_conv2d = _depthwise_conv2d
 
     tf.random = _mod("tensorflow.random")
     tf.random.uniform = _random_uniform
@@ -746,6 +784,7 @@ def build():
 
     tf.image = _mod("tensorflow.image")
     tf.image.convert_image_dtype = _convert_image_dtype
+    tf.image.psnr = _psnr
 
     tf.io = _mod("tensorflow.io")
     tf.io.gfile = _mod("tensorflow.io.gfile")
@@ -760,6 +799,7 @@ def build():
     keras.initializers.TruncatedNormal = TruncatedNormal
     keras.metrics = _mod("tensorflow.keras.metrics")
     keras.metrics.Mean, keras.metrics.Metric = Mean, Metric
+    keras.metrics.MeanSquaredError, keras.metrics.MeanAbsoluteError = MeanSquaredError, MeanAbsoluteError
     keras.optimizers = _mod("tensorflow.keras.optimizers")
     keras.optimizers.Adam = Adam
     keras.optimizers.schedules = _mod("tensorflow.keras.optimizers.schedules")

@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: config parsing, registry, strict state-dict checks, camera maths."""
 import json
+import os
 
 import pytest
 import torch
@@ -100,3 +101,22 @@ def test_bench_reads_roofline_traffic_from_committed_captures():
     assert bf16 is not None and 3.3e9 < bf16 < 3.9e9
     none, why = bench.ncu_traffic("profiles/does_not_exist.csv", 1.0)
     assert none is None and "no capture" in why
+
+
+def test_camera_metrics_match_the_reference_evaluator_fixture(golden_dir):
+    """The host-side half of viewformer_b200.metrics.Evaluator (camera errors, running means, medians) against numbers produced by the
+    reference's own Evaluator (evaluate_transformer.py:22-67, utils/metrics.py:91-170) over oracle/tf_shim.py
+    (tests/golden/evaluator_reference_shim.npz, oracle/make_golden.py).  The image half runs on the GPU (tests/test_vs_reference_evaluator_gpu.py)."""
+    import numpy as np
+    from oracle import make_golden as G
+    from viewformer_b200.metrics import Evaluator
+    g = np.load(os.path.join(golden_dir, "evaluator_reference_shim.npz"))
+    gt, gen = G.evaluator_cameras()
+    ev = Evaluator()                                    # no device is touched until an image arrives
+    ev.update_with_camera(gt[:4], gen[:4])              # two updates: the running state must accumulate
+    ev.update_with_camera(gt[4:], gen[4:])
+    r = ev.result()
+    for k in ("loc-angle", "loc-dist", "loc-angle-med", "loc-dist-med"):
+        assert abs(r[k] - float(g["cam." + k])) < 2e-6 * max(1.0, abs(r[k])), k
+    info = ev.get_progress_bar_info()
+    assert set(info) == {"img_psnr", "cam_loc", "cam_ang"} and abs(info["cam_loc"] - r["loc-dist"]) < 1e-12

@@ -304,3 +304,93 @@ def test_reference_generate_batch_predictions_equal_oracle(tf, augment, loc):
         assert tuple(r["generated_images"].shape) == (2, 4, 32, 32, 3)
         assert torch.equal(torch.as_tensor(r["generated_images"]).as_subclass(torch.Tensor), o["generated_images"])
         assert float((r["generated_cameras"] - o["generated_cameras"]).abs().max()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------- evaluation metrics (utils/metrics.py, Evaluator)
+def test_shim_image_ops_follow_documented_tensorflow_semantics(tf):
+    """The leaf ops utils/metrics.py adds to the shim's surface: tf.nn.depthwise_conv2d (NHWC, filter [fh,fw,in,mult], output channel
+    k*mult + q), tf.image.psnr, tf.image.convert_image_dtype(uint8 -> float = /255), Keras MeanSquaredError (CAST, no rescale)."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 5, 6, 3)).astype(np.float32)
+    w = rng.standard_normal((2, 3, 3, 2)).astype(np.float32)
+    y = tf.nn.depthwise_conv2d(tf.constant(x), tf.constant(w), strides=[1, 1, 1, 1], padding="VALID").numpy()
+    want = np.zeros((2, 4, 4, 6), np.float32)
+    for k in range(3):
+        for q in range(2):
+            for i in range(4):
+                for j in range(4):
+                    want[:, i, j, k * 2 + q] = (x[:, i:i + 2, j:j + 3, k] * w[:, :, k, q]).sum((1, 2))
+    assert y.shape == want.shape and np.allclose(y, want, atol=1e-5)
+    a = rng.integers(0, 256, (2, 8, 8, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (2, 8, 8, 3), dtype=np.uint8)
+    fa, fb = tf.image.convert_image_dtype(a, "float32"), tf.image.convert_image_dtype(b, "float32")
+    assert fa.dtype == tf.float32 and np.allclose(fa.numpy(), a / 255.0, atol=1e-7)
+    mse = ((a / 255.0 - b / 255.0) ** 2).mean((1, 2, 3))
+    assert np.allclose(tf.image.psnr(fa, fb, 1).numpy(), 10 * np.log10(1 / mse), atol=1e-4)
+    m = tf.keras.metrics.MeanSquaredError("mse")
+    m.update_state(a, b)
+    assert abs(float(m.result()) - ((a.astype(np.float64) - b) ** 2).mean()) < 1e-2               # 0..255 scale: uint8 is cast, not rescaled
+    m = tf.keras.metrics.MeanAbsoluteError("mae")
+    m.update_state(a, b)
+    assert abs(float(m.result()) - np.abs(a.astype(np.float64) - b).mean()) < 1e-3
+
+
+def _reference_evaluator():
+    ev, _ = ref_loader.load_reference_evaluate()
+    metrics = sys.modules["viewformer.utils.metrics"]
+    metrics.LPIPSMetric._lpips_pool["vgg"] = lambda a, b: torch.zeros(a.shape[0])       # LPIPS needs VGG weights: not on this path
+    return ev, metrics
+
+
+def test_evaluator_fixture_is_what_the_reference_evaluator_computes(golden_dir):
+    """tests/golden/evaluator_reference_shim.npz (what viewformer_b200.metrics.Evaluator is held to on the GPU,
+    tests/test_vs_reference_evaluator_gpu.py) is reproduced by the reference's own Evaluator (evaluate_transformer.py:22-67)."""
+    import tensorflow as tf
+    from oracle import make_golden as G
+    ev, _ = _reference_evaluator()
+    g = np.load(os.path.join(golden_dir, "evaluator_reference_shim.npz"))
+    for tag, n, gs, ns, image_size, seed in G.EVALUATOR_CASES:
+        gt, gen = synth.make_metric_pair(n, gs, ns, seed)
+        assert [int(gt.sum()), int(gen.sum())] == g[f"{tag}.input_sums"].tolist()
+        E = ev.Evaluator(image_size)
+        E.update_with_image(tf.convert_to_tensor(gt.numpy()), tf.convert_to_tensor(gen.numpy()))
+        r = E.result()
+        for k in ("mse", "rmse", "mae", "psnr", "ssim"):
+            assert abs(r[k] - float(g[f"{tag}.{k}"])) <= 1e-6 * abs(r[k]), (tag, k)
+    # what follows from HOW the reference calls its metrics: mse / mae on the 0..255 scale, rmse^2 == mse
+    assert abs(float(g["same.mse"]) - float(g["same.rmse"]) ** 2) < 1e-3 * float(g["same.mse"]) and float(g["same.mae"]) > 1.0
+
+
+def test_ssim_of_the_gpu_tests_and_the_k1_quirk_follow_the_reference():
+    """(a) the fp64 restatement tests/test_eval_gpu.py::ssim_ref that the CUDA kernel is compared with equals the reference's ssim()
+    (utils/metrics.py:17-73) with its default K1 = 0.01; (b) SSIMMetric — the class the evaluators use — passes 1 as the THIRD positional
+    argument, which is K1, not the data range (metrics.py:183): its value is ssim(K1 = 1), measurably different."""
+    import importlib
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    T = importlib.import_module("test_eval_gpu")
+    _, metrics = _reference_evaluator()
+    gt, gen = synth.make_metric_pair(4, 64, 64, 5)
+    A, B = gt.float() / 255, gen.float() / 255
+    ref_default = torch.as_tensor(metrics.ssim(A.numpy(), B.numpy())).double()
+    assert torch.allclose(T.ssim_ref(A, B), ref_default, atol=2e-6)
+    m = metrics.SSIMMetric()
+    m.update_state(gt.numpy(), gen.numpy())
+    ref_k1 = torch.as_tensor(metrics.ssim(A.numpy(), B.numpy(), 1)).double().mean()
+    assert abs(float(m.result()) - float(ref_k1)) < 1e-6
+    assert abs(float(ref_k1) - float(ref_default.mean())) > 1e-4
+
+
+def test_allow_nan_mean_counts_nan_as_zero_with_full_weight_like_the_reference():
+    """metrics.py:76-88 replaces NaN by 0 and then computes the weight from is_nan of the CLEANED values: a NaN camera error counts as 0
+    with weight 1.  viewformer_b200.metrics.Mean(nan="zero") reproduces that for loc-angle / loc-dist."""
+    import tensorflow as tf
+    from viewformer_b200.metrics import Evaluator
+    _, metrics = _reference_evaluator()
+    a = torch.tensor([[0., 0, 0, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0, 0], [2, 0, 0, 1, 0, 0, 0]])
+    b = torch.tensor([[3., 4, 0, 1, 0, 0, 0], [float("nan"), 1, 1, 1, 0, 0, 0], [2, 0, 1, 1, 0, 0, 0]])
+    m = metrics.CameraPositionError()
+    m.update_state(tf.convert_to_tensor(a.numpy()), tf.convert_to_tensor(b.numpy()))
+    assert abs(float(m.result()) - 2.0) < 1e-6                                           # (5 + 0 + 1) / 3, not (5 + 1) / 2
+    ours = Evaluator()
+    ours.update_with_camera(a, b)
+    assert abs(ours.result()["loc-dist"] - 2.0) < 1e-6

@@ -24,7 +24,7 @@ EXPORTS = [
     "vf_cameras_prepare", "vf_cameras_from_relative",
     "vf_conv3x3_small_cin", "vf_conv3x3_small_cout", "vf_groupnorm_finalize", "vf_split_f16x2", "vf_attn_block_causal", "vf_attn_block_causal_tail", "vf_attn_block_causal_decode", "vf_attn_block_multiend",
     "vf_vq_split3", "vf_vq_select", "vf_cross_entropy_rows", "vf_pose_loss_rows", "vf_row_mean",
-    "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8",
+    "vf_vq_prepare_codebook_f16", "vf_vq_lookup_fused", "vf_resize_u8", "vf_image_pair_sums", "vf_ssim_u8", "vf_ssim_u8_k",
     "vf_conv_wgrad", "vf_pad_transpose_split", "vf_sum_splits", "vf_col_sums", "vf_groupnorm_bwd", "vf_softmax_bwd_rows", "vf_l1_grad", "vf_lincomb3", "vf_sumpool2x2", "vf_adam",
     "vf_layernorm_bwd", "vf_gelu_fwd", "vf_gelu_bwd", "vf_migt_embed_bwd", "vf_cross_entropy_grad", "vf_pose_loss_grad", "vf_adamw_keras", "vf_sumsq", "vf_dropout",
 ]
@@ -235,14 +235,19 @@ def image_pair_sums(a_u8, b_u8):
     return out
 
 
-def ssim_u8(a_u8, b_u8):
-    """utils/metrics.py:17-73 on uint8 NHWC images -> float64 [N] mean SSIM per image."""
+def ssim_u8(a_u8, b_u8, k1=None, k2=None):
+    """utils/metrics.py:17-73 on uint8 NHWC images -> float64 [N] mean SSIM per image.  ``k1`` / ``k2``: the K1 / K2 of ``ssim()``
+    (defaults 0.01 / 0.03); the reference's SSIMMetric passes K1 = 1 (metrics.py:183)."""
     lib = load(True)
     _dev(a_u8, torch.uint8)
     _dev(b_u8, torch.uint8)
     n, h, w, c = a_u8.shape
     out = torch.empty((n,), dtype=torch.float64, device=a_u8.device)
-    _check(lib.vf_ssim_u8(_p(a_u8), _p(b_u8), n, h, w, c, _p(out), _stream()))
+    if k1 is None and k2 is None:
+        _check(lib.vf_ssim_u8(_p(a_u8), _p(b_u8), n, h, w, c, _p(out), _stream()))
+    else:
+        _check(lib.vf_ssim_u8_k(_p(a_u8), _p(b_u8), n, h, w, c, C.c_double(0.01 if k1 is None else float(k1)),
+                                C.c_double(0.03 if k2 is None else float(k2)), _p(out), _stream()))
     return out
 
 

@@ -3,7 +3,7 @@
 //                       (bilinear align_corners=False when shrinking, nearest when growing) -> clamp -> * 255 -> uint8 (truncation)
 //   vf_image_pair_sums  per-image sum |a-b| and sum (a-b)^2 over uint8 images: MSE / MAE / RMSE / PSNR follow exactly on the host
 //                       (viewformer/utils/metrics.py:173-205, tf.image.psnr)
-//   vf_ssim_u8          viewformer/utils/metrics.py:17-73: 7x7 uniform window, VALID, sample covariance, K1 = 0.01, K2 = 0.03,
+//   vf_ssim_u8[_k]      viewformer/utils/metrics.py:17-73: 7x7 uniform window, VALID, sample covariance, K1 = 0.01, K2 = 0.03 (or the caller's),
 //                       data range 1, mean over (H-6) x (W-6) x C
 #include "vf_common.cuh"
 
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(256) pair_sums_kernel(const uint8_t* __restric
 
 // grid (chunks, N): every thread strides over the (H-6)(W-6)C window positions of one image; integer window sums are exact
 __global__ void __launch_bounds__(256) ssim_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int H, int W, int C,
-                                                      double* __restrict__ out) {
+                                                      float C1, float C2, double* __restrict__ out) {
     __shared__ double sh[8];
     const int OH = H - 6, OW = W - 6;
     const long long total = (long long)OH * OW * C;
     const uint8_t* pa = a + (long long)blockIdx.y * H * W * C;
     const uint8_t* pb = b + (long long)blockIdx.y * H * W * C;
-    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f, cov_norm = 49.f / 48.f;
+    const float cov_norm = 49.f / 48.f;                   // C1 = (K1 R)^2, C2 = (K2 R)^2 with data range R = 1 come from the caller
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int c = (int)(i % C);
@@ -134,15 +134,23 @@ extern "C" int vf_image_pair_sums(const void* a, const void* b, int N, int64_t p
     return VF_OK;
 }
 
-extern "C" int vf_ssim_u8(const void* a, const void* b, int N, int H, int W, int C, double* out, vf_stream_t s) {
+extern "C" int vf_ssim_u8_k(const void* a, const void* b, int N, int H, int W, int C, double K1, double K2, double* out, vf_stream_t s) {
     VF_CHECK_ARG(a && b && out && N >= 0 && H >= 7 && W >= 7 && C > 0 && N <= 65535, "vf_ssim_u8: bad args (images must be at least 7x7)");
+    VF_CHECK_ARG(K1 >= 0.0 && K1 <= 1e3, "vf_ssim_u8: K1 out of range");
+    VF_CHECK_ARG(K2 >= 0.0 && K2 <= 1e3, "vf_ssim_u8: K2 out of range");
     if (N == 0) return VF_OK;
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * N, vf_s(s));
     if (e != cudaSuccess) { vf_set_error("vf_ssim_u8: memset: %s", cudaGetErrorString(e)); return VF_ERR_CUDA; }
     const long long total = (long long)(H - 6) * (W - 6) * C;
     int chunks = (int)((total + 255) / 256);
     if (chunks > 64) chunks = 64;
-    ssim_u8_kernel<<<dim3(chunks, N), 256, 0, vf_s(s)>>>(reinterpret_cast<const uint8_t*>(a), reinterpret_cast<const uint8_t*>(b), H, W, C, out);
+    const float k1 = (float)K1, k2 = (float)K2;
+    ssim_u8_kernel<<<dim3(chunks, N), 256, 0, vf_s(s)>>>(reinterpret_cast<const uint8_t*>(a), reinterpret_cast<const uint8_t*>(b), H, W, C,
+                                                         k1 * k1, k2 * k2, out);
     VF_CHECK_LAUNCH("vf_ssim_u8");
     return VF_OK;
+}
+
+extern "C" int vf_ssim_u8(const void* a, const void* b, int N, int H, int W, int C, double* out, vf_stream_t s) {
+    return vf_ssim_u8_k(a, b, N, H, W, C, 0.01, 0.03, out, s);          // the defaults of ssim() (metrics.py:17)
 }

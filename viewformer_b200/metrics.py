@@ -21,8 +21,9 @@ def _u8(x, device):
     return t.to(device).contiguous()
 
 
-def image_metrics(gt_images, images, device="cuda"):
-    """uint8 [N,H,W,C] x2 -> dict of per-image float64 tensors: mse, mae (range [0,1]), rmse (range [0,255]), psnr (dB), ssim."""
+def image_metrics(gt_images, images, device="cuda", ssim_k1=None):
+    """uint8 [N,H,W,C] x2 -> dict of per-image float64 tensors: mse, mae (range [0,1]), rmse (range [0,255]), psnr (dB), ssim.
+    ``ssim_k1``: K1 of ``ssim()`` (metrics.py:17; default 0.01).  The reference's SSIMMetric passes 1 (metrics.py:183)."""
     a, b = _u8(gt_images, device), _u8(images, device)
     n = a.shape[0]
     sums = L.image_pair_sums(a, b).to(torch.float64)
@@ -30,7 +31,8 @@ def image_metrics(gt_images, images, device="cuda"):
     mse = sums[:, 1] / (cnt * 255.0 * 255.0)
     return dict(mse=mse, mae=sums[:, 0] / (cnt * 255.0), rmse=torch.sqrt(sums[:, 1] / cnt),
                 psnr=10.0 * torch.log10(1.0 / mse),                      # tf.image.psnr(max_val = 1)
-                ssim=L.ssim_u8(a, b) if min(a.shape[1], a.shape[2]) >= 7 else torch.full((n,), float("nan"), dtype=torch.float64))
+                ssim=(L.ssim_u8(a, b, k1=ssim_k1) if min(a.shape[1], a.shape[2]) >= 7
+                      else torch.full((n,), float("nan"), dtype=torch.float64)))
 
 
 def camera_position_error(x1, x2):
@@ -46,16 +48,19 @@ def camera_orientation_error(x1, x2):
 
 
 class Mean:
-    """tf.metrics.Mean with the AllowNanMean behaviour of metrics.py:76-88 (NaN samples carry zero weight)."""
+    """Running mean.  ``nan="skip"``: NaN samples carry no weight (image metrics of images too small for a 7x7 window).
+    ``nan="zero"``: what the reference's AllowNanMean (metrics.py:76-88) actually computes for the camera errors — it replaces NaN
+    by 0 and THEN derives the weight from is_nan of the cleaned values, so a NaN sample counts as an error of 0 with full weight."""
 
-    def __init__(self, name):
-        self.name, self.total, self.count = name, 0.0, 0.0
+    def __init__(self, name, nan="skip"):
+        assert nan in ("skip", "zero")
+        self.name, self.total, self.count, self.nan = name, 0.0, 0.0, nan
 
     def update_state(self, values):
         v = torch.as_tensor(values, dtype=torch.float64).reshape(-1).cpu()
         ok = ~torch.isnan(v)
         self.total += float(v[ok].sum())
-        self.count += float(ok.sum())
+        self.count += float(ok.sum()) if self.nan == "skip" else float(v.numel())
 
     def result(self):
         return self.total / self.count if self.count else 0.0
@@ -80,18 +85,27 @@ class Median:
 
 class Evaluator:
     """evaluate/evaluate_transformer.py:22-67: image-generation metrics (mse, rmse, mae, psnr, ssim) and localisation metrics
-    (loc-angle, loc-dist and their medians); images are brought to a common size with the dataset resize rule first."""
+    (loc-angle, loc-dist and their medians); images are brought to a common size with the dataset resize rule first.
+
+    The numbers are the ones the reference's Evaluator reports, including what follows from HOW it calls its metric classes
+    (pinned by running the reference's Evaluator itself, tests/test_reference_on_shim.py and tests/golden/evaluator_reference_shim.npz):
+    ``mse`` / ``mae`` are Keras MeanSquaredError / MeanAbsoluteError on the uint8 images CAST to float (0..255 scale, not [0,1]);
+    ``ssim`` is ``SSIMMetric``, which passes 1 as the third positional argument of ``ssim()`` — K1 = 1, not the data range
+    (metrics.py:183); ground truth is resized with the default rule, the generated image bilinearly (evaluate_transformer.py:42-45)."""
 
     def __init__(self, image_size=None, device="cuda"):
         self.image_size, self.device = image_size, device
-        self._loc = dict(angle=Mean("loc-angle"), dist=Mean("loc-dist"), angle_med=Median("loc-angle-med"), dist_med=Median("loc-dist-med"))
+        self._loc = dict(angle=Mean("loc-angle", nan="zero"), dist=Mean("loc-dist", nan="zero"), angle_med=Median("loc-angle-med"),
+                         dist_med=Median("loc-dist-med"))
         self._img = {k: Mean(k) for k in ("mse", "rmse", "mae", "psnr", "ssim")}
 
     def update_with_image(self, ground_truth_images, generated_images):
         gt, gen = _u8(ground_truth_images, self.device), _u8(generated_images, self.device)
         size = self.image_size or max(gt.shape[-2], gen.shape[-2])
-        gt, gen = L.resize_u8(gt, size), L.resize_u8(gen, size)
-        for k, v in image_metrics(gt, gen, self.device).items():
+        gt, gen = L.resize_u8(gt, size), L.resize_u8(gen, size, method="bilinear")
+        m = image_metrics(gt, gen, self.device, ssim_k1=1.0)
+        m["mse"], m["mae"] = m["mse"] * (255.0 * 255.0), m["mae"] * 255.0
+        for k, v in m.items():
             self._img[k].update_state(v)
 
     def update_with_camera(self, ground_truth_cameras, generated_cameras):
@@ -107,8 +121,8 @@ class Evaluator:
             self.update_with_camera(ground_truth_cameras, generated_cameras)
 
     def get_progress_bar_info(self):
-        return dict(psnr=self._img["psnr"].result(), mae=self._img["mae"].result(), **{"loc-angle": self._loc["angle"].result(),
-                                                                                       "loc-dist": self._loc["dist"].result()})
+        """evaluate_transformer.py:56-61 (img_lpips is absent: LPIPS needs VGG weights that are not available offline)."""
+        return dict(img_psnr=self._img["psnr"].result(), cam_loc=self._loc["dist"].result(), cam_ang=self._loc["angle"].result())
 
     def result(self):
         out = {m.name: float(m.result()) for m in self._img.values() if m.count}
