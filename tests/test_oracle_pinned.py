@@ -166,3 +166,33 @@ def test_oracle_matches_reference_on_shim_fixture(golden_dir):
     diff = (o["generated_images"].int() - torch.from_numpy(g["gen.images"]).int()).abs()
     assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3        # uint8 views: the codebook restatement may round one LSB apart
     assert float((o["generated_cameras"] - torch.from_numpy(g["gen.cameras"])).abs().max()) < 1e-5
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_schedules_equal_the_reference_module():
+    """viewformer_b200/schedules.py against the reference's utils/schedules.py (pure Python, imported as shipped): same parse, same string
+    form, same is_zero, same values on a grid of steps — localization_weight schedules of MIGT (migt.py:280-283, :446).  One deliberate
+    difference: warmup(cosine(a,b),n).with_total_steps(T) raises TypeError in the reference (WarmupSchedule does not forward the horizon to
+    its inner schedule); here the horizon is forwarded and the schedule evaluates."""
+    import sys
+    ref_loader.load_reference_modules()
+    R = sys.modules["viewformer.utils.schedules"]
+    from viewformer_b200.schedules import parse
+    cases = ["0", "1", "0.5", "2.5e-1", " 3 ", "linear(1,3,10)", "linear(0,0,5)", "linear(1,2)", "cosine(2,0)", "cosine(0,0)", "cosine(2.0,0.5,100)",
+             "warmup(1,2000)", "warmup(0,7)", "warmup(cosine(1,0.5,100),4)", "warmup(linear(0,2,50),10)", "warmup(warmup(1,3),5)"]
+    steps = (0, 1, 2, 4, 5, 10, 54, 100, 150, 199, 200, 1000, 2000, 5000)
+    for c in cases:
+        r, o = R.Schedule.from_str(c), parse(c)
+        assert r is not None and str(r) == str(o) and r.is_zero() == o.is_zero(), c
+        r, o = r.with_total_steps(200), o.with_total_steps(200)
+        assert str(r) == str(o), c
+        for t in steps:
+            rv, ov = float(r(t, "float64")), float(o(t))
+            assert abs(rv - ov) <= 1e-6 * max(1.0, abs(rv)), (c, t, rv, ov)         # the reference computes in float32 inside
+    assert R.Schedule.from_str("step(1,2)") is None
+    with pytest.raises(ValueError):
+        parse("step(1,2)")
+    nested = "warmup(cosine(1,0.5),4)"
+    with pytest.raises(TypeError):
+        R.Schedule.from_str(nested).with_total_steps(200)(3)
+    assert abs(float(parse(nested).with_total_steps(200)(3)) - 0.75) < 1e-9
