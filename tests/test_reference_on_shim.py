@@ -306,6 +306,36 @@ def test_reference_generate_batch_predictions_equal_oracle(tf, augment, loc):
         assert float((r["generated_cameras"] - o["generated_cameras"]).abs().max()) < 1e-6
 
 
+def test_reference_allimg_script_equals_oracle(tf):
+    """evaluate_transformer_multictx_allimg.py:15-88 as shipped (encode_images, transformer_predict, run_with_batchsize, decode_code):
+    what viewformer_b200.evaluate mirrors and tests/test_eval_gpu.py::test_transformer_predict_and_steps_match_oracle compares with
+    oracle.generate_batch_predictions_multictx.  The script blanks the LAST context camera with zeros where the multictx script keeps
+    it (allimg:28 vs multictx:64) — the outputs must not depend on it (the query streams only see strictly earlier views)."""
+    from oracle import make_golden as mg
+    ref_loader.load_reference_evaluate()
+    R = os.path.join(ref_loader.REFERENCE_ROOT, "viewformer", "evaluate", "evaluate_transformer_multictx_allimg.py")
+    al = ref_loader._load("viewformer.evaluate.evaluate_transformer_multictx_allimg", R)
+    vcfg = VQGANConfig(**mg.SMALL_VQ)
+    vq = ref_loader.build_reference_vqgan(synth.make_vqgan_state_dict(vcfg, 0), **mg.SMALL_VQ)
+    kw = dict(n_layer=2, n_head=4, d_model=64, sequence_size=4, n_embeddings=vcfg.n_embed, token_image_size=8, n_loss_skip=1)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    model = ref_loader.build_reference_migt(sd, **kw)
+    codebook = ref_loader.ReferenceCodebookNHWC(vq)
+    images = synth.make_images_uint8(3, 4, size=vcfg.image_size, seed=41)
+    cams = synth.make_cameras(3, 4, seed=42)
+    with torch.no_grad():
+        codes = al.encode_images(images.clone(), codebook_model=codebook)
+        gen_cams, gen_codes = al.run_with_batchsize(al.transformer_predict, 2, cams.clone(), codes, transformer_model=model)
+        gen_images = al.decode_code(gen_codes, codebook_model=codebook)
+        o = mo.generate_batch_predictions_multictx(lambda d: mo.forward(sd, cfg, d), lambda x: vq.encode(x)[-1], vq.decode_code, cfg, images, cams)
+        want_codes = vq.encode(mo.images_to_float(images.reshape(-1, *images.shape[2:])).permute(0, 3, 1, 2).contiguous())[-1].reshape(3, 4, 8, 8)
+    assert tuple(codes.shape) == (3, 4, 8, 8) and torch.equal(torch.as_tensor(codes).long(), want_codes.long())
+    assert torch.equal(torch.as_tensor(gen_codes).long(), o["generated_codes"].long())
+    assert float((torch.as_tensor(gen_cams) - o["generated_cameras"]).abs().max()) < 1e-6
+    assert torch.equal(torch.as_tensor(gen_images).as_subclass(torch.Tensor), o["generated_images"])
+
+
 # ---------------------------------------------------------------------------------------- evaluation metrics (utils/metrics.py, Evaluator)
 def test_shim_image_ops_follow_documented_tensorflow_semantics(tf):
     """The leaf ops utils/metrics.py adds to the shim's surface: tf.nn.depthwise_conv2d (NHWC, filter [fh,fw,in,mult], output channel
