@@ -43,8 +43,11 @@ def test_token_dataset_windows_and_sharding(tmp_path):
             sid = int(t[b, 0, 0, 0])
             assert (t[b] == sid).all() and torch.allclose(p[b].mean(), torch.tensor(100.0 * sid), atol=3.0)     # a window never mixes scenes
             assert len({tuple(v.tolist()) for v in p[b]}) == seq                                             # distinct views
-    capped = list(D.load_token_dataset(str(tmp_path), 1, seq, 2, split="train", repeat=1, max_samples_per_environment=1))
+    capped = list(D.load_token_dataset(str(tmp_path), 1, seq, 2, split="train", repeat=1, max_windows_per_environment=1))
     assert len(capped) == sum(1 for t in [9, 4, 13, 3, 8, 8, 8, 21] if t >= seq)
+    # the reference's own knob: take(k) on a one-sample dataset (tfrecord_dataset.py:177-181) -> k >= 1 keeps everything, 0 nothing
+    assert len(list(D.load_token_dataset(str(tmp_path), 1, seq, 2, split="train", repeat=1, max_samples_per_environment=1))) == n_windows
+    assert len(list(D.load_token_dataset(str(tmp_path), 1, seq, 2, split="train", repeat=1, max_samples_per_environment=0))) == 0
     r0 = list(D.load_token_dataset(str(tmp_path), 2, seq, 2, split="train", repeat=1, rank=0, world=2))
     r1 = list(D.load_token_dataset(str(tmp_path), 2, seq, 2, split="train", repeat=1, rank=1, world=2))
     s0 = {int(t[b, 0, 0, 0]) for _, t in r0 for b in range(t.shape[0])}

@@ -193,9 +193,14 @@ def write_token_dataset(path, split, scenes, token_image_size, scenes_per_shard=
 
 
 def load_token_dataset(path, batch_size, sequence_size, token_image_size, split="train", repeat=None, max_samples_per_environment=-1,
-                       seed=0, rank=0, world=1, shuffle_buffer=1000, drop_last=True):
+                       seed=0, rank=0, world=1, shuffle_buffer=1000, drop_last=True, max_windows_per_environment=None):
     """Generator of (poses f32 [B,sequence_size,7], tokens int64 [B,sequence_size,h,w]) torch batches (data/tfrecord_dataset.py:134-197).
-    ``batch_size`` is the GLOBAL batch; every rank yields batch_size // world samples from its own shard of the files."""
+    ``batch_size`` is the GLOBAL batch; every rank yields batch_size // world samples from its own shard of the files.
+
+    ``max_samples_per_environment`` does what the reference's does: ``.take(k)`` is applied to the dataset built from ONE window of
+    ``sequence_size`` views (tfrecord_dataset.py:177-181), which holds exactly one sample — so k < 0 and every k >= 1 keep all windows of
+    every scene and k == 0 yields nothing.  ``max_windows_per_environment`` is the limit the name suggests (at most that many windows per
+    scene); it has no counterpart in the reference."""
     files = []
     for p in path.split(","):
         files += sorted(os.path.join(p, f) for f in os.listdir(p) if f.endswith(".tfrecord") and f"-{split}-" in f)
@@ -225,8 +230,10 @@ def load_token_dataset(path, batch_size, sequence_size, token_image_size, split=
                 idx = list(range(len(poses)))
                 rng.shuffle(idx)                                   # "Shuffle train environments" (applied to every split, as in the reference)
                 n_win = len(idx) // sequence_size
-                if max_samples_per_environment >= 0:
-                    n_win = min(n_win, max_samples_per_environment)
+                if max_samples_per_environment == 0:
+                    n_win = 0
+                if max_windows_per_environment is not None:
+                    n_win = min(n_win, max(0, int(max_windows_per_environment)))
                 for wi in range(n_win):
                     sel = idx[wi * sequence_size:(wi + 1) * sequence_size]
                     buf.append((poses[sel], tokens[sel]))
