@@ -48,6 +48,14 @@ def test_token_dataset_windows_and_sharding(tmp_path):
     # the reference's own knob: take(k) on a one-sample dataset (tfrecord_dataset.py:177-181) -> k >= 1 keeps everything, 0 nothing
     assert len(list(D.load_token_dataset(str(tmp_path), 1, seq, 2, split="train", repeat=1, max_samples_per_environment=1))) == n_windows
     assert len(list(D.load_token_dataset(str(tmp_path), 1, seq, 2, split="train", repeat=1, max_samples_per_environment=0))) == 0
+    # the training transform (train_transformer.py:113: partial(process_batch, augment=config.augment_poses)) is applied per window
+    import functools
+    rel = list(D.load_token_dataset(str(tmp_path), 2, seq, 2, split="train", repeat=1, seed=3, transform=functools.partial(D.process_batch, augment="relative")))
+    assert len(rel) == len(batches)
+    for p, t in rel:
+        assert p.dtype == torch.float32 and p.shape == (2, seq, 7) and t.dtype == torch.int64
+        assert float(p[:, 0, :3].abs().max()) < 1e-5 and torch.allclose(p[:, 0, 3:], torch.tensor([1.0, 0, 0, 0]).expand(2, 4), atol=1e-5)   # first view = identity
+        assert float((p[..., 3:].norm(dim=-1) - 1).abs().max()) < 1e-5 and bool((p[..., 3] >= 0).all())
     r0 = list(D.load_token_dataset(str(tmp_path), 2, seq, 2, split="train", repeat=1, rank=0, world=2))
     r1 = list(D.load_token_dataset(str(tmp_path), 2, seq, 2, split="train", repeat=1, rank=1, world=2))
     s0 = {int(t[b, 0, 0, 0]) for _, t in r0 for b in range(t.shape[0])}

@@ -336,6 +336,42 @@ def test_reference_allimg_script_equals_oracle(tf):
     assert torch.equal(torch.as_tensor(gen_images).as_subclass(torch.Tensor), o["generated_images"])
 
 
+def test_process_batch_equals_the_reference_function(tf):
+    """train/train_transformer.py:31-64 (the pose augmentation mapped over every training sample): the function's own source text,
+    cut out of the reference file with ast (the script around it needs the whole Keras training stack to import) and executed over the
+    shim with the reference's geometry_tf, against viewformer_b200.data.process_batch — every augment mode, both splits, random modes
+    under the same seed (the shim draws from torch's global generator, in the order the reference's expressions are evaluated)."""
+    import ast
+    import math
+    from viewformer_b200.data import process_batch
+    ref_loader.load_reference_migt()
+    geometry = sys.modules["viewformer.utils.geometry_tf"]
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "viewformer", "train", "train_transformer.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "process_batch"]
+    assert len(fn) == 1
+    ns = dict(tf=tf, geometry=geometry, math=math)
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    ref_fn = ns["process_batch"]
+    cams = synth.make_cameras(3, 5, seed=8)                             # [B, T, 7]: the loader maps over [T, 7] windows, batches also work
+    toks = synth.make_codes(3, 5, n_embed=16, side=2, seed=9)
+    for x in (cams[0], cams):
+        for augment in ("relative", "no", "simple", "advanced"):
+            for split in ("train", "test"):
+                torch.manual_seed(123)
+                want, wt = ref_fn(tf.constant(x.numpy()), toks, augment, split)
+                torch.manual_seed(123)
+                got, gt = process_batch(x.clone(), toks, augment, split)
+                assert gt is toks and wt is toks
+                assert float((torch.as_tensor(want) - got).abs().max()) < 2e-6, (augment, split)
+                assert bool((got[..., 3] >= 0).all()) and float((got[..., 3:].norm(dim=-1) - 1).abs().max()) < 1e-5
+                if augment in ("simple", "advanced"):                    # random modes act on the train split only
+                    same = float((got - process_batch(x.clone(), toks, "no", split)[0]).abs().max()) < 1e-6
+                    assert same == (split != "train")
+    with pytest.raises(ValueError):
+        process_batch(cams[0], toks, "bogus", "train")
+
+
 # ---------------------------------------------------------------------------------------- evaluation metrics (utils/metrics.py, Evaluator)
 def test_shim_image_ops_follow_documented_tensorflow_semantics(tf):
     """The leaf ops utils/metrics.py adds to the shim's surface: tf.nn.depthwise_conv2d (NHWC, filter [fh,fw,in,mult], output channel

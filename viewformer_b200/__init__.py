@@ -28,7 +28,7 @@ def __getattr__(name):   # lazy: importing the package must not require the buil
     if name in ("MIGTTrainer",):
         from .train_migt import MIGTTrainer
         return MIGTTrainer
-    if name in ("LatentCodeTransformer", "write_token_dataset", "load_token_dataset", "read_tfrecords", "TFRecordWriter"):
+    if name in ("LatentCodeTransformer", "write_token_dataset", "load_token_dataset", "read_tfrecords", "TFRecordWriter", "process_batch"):
         from . import data
         return getattr(data, name)
     if name in ("compat", "schedules", "tf_checkpoint", "cabi", "metrics", "data", "evaluate", "generate", "registry", "train", "train_migt"):

@@ -173,6 +173,58 @@ class LatentCodeTransformer:
         yield from emit()
 
 
+# ----------------------------------------------------------------------------------------------- pose augmentation of the training loader
+def _axis_quaternion(axis, angle):
+    """utils/geometry_tf.py:16-33 (make_quaternion_x / _y): (cos(a/2), sin(a/2) * axis)."""
+    angle = torch.as_tensor(angle)
+    return torch.cat([torch.cos(angle / 2)[..., None], torch.sin(angle / 2)[..., None] * torch.tensor(axis, dtype=angle.dtype)], -1)
+
+
+def process_batch(cameras, tokens, augment, split, generator=None):
+    """train/train_transformer.py:31-64 — what the reference maps over every training sample (``transform=partial(process_batch,
+    augment=config.augment_poses)``): 'relative' re-expresses the poses in the frame of the first view; 'simple' / 'advanced' (train split
+    only) add one random translation ~ N(0, I) and one random rotation (y(U[0,2pi)) * x(U[0,pi/8)) * y(U[0,2pi)), resp. y(U[0,2pi))) to
+    the whole window; 'no' leaves them; every branch ends with quaternion normalisation and the w >= 0 sign convention.  Host-side torch
+    on the loader's tensors (a few floats per sample; the reference runs it inside tf.data on the CPU as well).  Random numbers are
+    drawn in the reference's order — translation first, then the angles as Python evaluates the nested calls — from ``generator`` (or
+    torch's global generator)."""
+    import math
+    from .generate import quaternion_multiply, quaternion_conjugate, quaternion_rotate, quaternion_normalize, quaternion_remove_sign
+    cameras = torch.as_tensor(cameras)
+    xyz, quaternion = cameras[..., :3], cameras[..., 3:]
+    dt = xyz.dtype
+
+    def normal():
+        return torch.randn((1, 3), dtype=dt, generator=generator)
+
+    def uniform(hi):
+        return torch.rand((1,), dtype=dt, generator=generator) * hi
+
+    if augment == "relative":
+        rotation_inverse = quaternion_conjugate(quaternion[..., :1, :])
+        xyz = quaternion_rotate(xyz - xyz[..., :1, :], rotation_inverse.expand_as(quaternion))
+        quaternion = quaternion_multiply(rotation_inverse.expand_as(quaternion), quaternion)
+    elif augment == "no" or split != "train":
+        pass
+    elif augment == "simple":
+        xyz = xyz + normal()
+        qy1 = _axis_quaternion([0.0, 1.0, 0.0], uniform(2 * math.pi))
+        qx = _axis_quaternion([1.0, 0.0, 0.0], uniform(math.pi / 8))
+        qy2 = _axis_quaternion([0.0, 1.0, 0.0], uniform(2 * math.pi))
+        rotation = quaternion_multiply(qy1, quaternion_multiply(qx, qy2))
+        xyz = quaternion_rotate(xyz, rotation.expand(*xyz.shape[:-1], 4))
+        quaternion = quaternion_multiply(quaternion, rotation.expand_as(quaternion))
+    elif augment == "advanced":
+        xyz = xyz + normal()
+        rotation = _axis_quaternion([0.0, 1.0, 0.0], uniform(2 * math.pi))
+        xyz = quaternion_rotate(xyz, rotation.expand(*xyz.shape[:-1], 4))
+        quaternion = quaternion_multiply(quaternion, rotation.expand_as(quaternion))
+    else:
+        raise ValueError(f"Augment {augment} is not supported")
+    quaternion = quaternion_remove_sign(quaternion_normalize(quaternion))
+    return torch.cat([xyz, quaternion], -1), tokens
+
+
 # ----------------------------------------------------------------------------------------------- token dataset
 def write_token_dataset(path, split, scenes, token_image_size, scenes_per_shard=64, name="b200-codes"):
     """Scenes of dict(cameras [T,7], codes [T,h,w]) -> ``<path>/<name>-<split>-<shard>-of-<n>.tfrecord`` + info.json."""
@@ -193,14 +245,15 @@ def write_token_dataset(path, split, scenes, token_image_size, scenes_per_shard=
 
 
 def load_token_dataset(path, batch_size, sequence_size, token_image_size, split="train", repeat=None, max_samples_per_environment=-1,
-                       seed=0, rank=0, world=1, shuffle_buffer=1000, drop_last=True, max_windows_per_environment=None):
+                       seed=0, rank=0, world=1, shuffle_buffer=1000, drop_last=True, max_windows_per_environment=None, transform=None):
     """Generator of (poses f32 [B,sequence_size,7], tokens int64 [B,sequence_size,h,w]) torch batches (data/tfrecord_dataset.py:134-197).
     ``batch_size`` is the GLOBAL batch; every rank yields batch_size // world samples from its own shard of the files.
 
     ``max_samples_per_environment`` does what the reference's does: ``.take(k)`` is applied to the dataset built from ONE window of
     ``sequence_size`` views (tfrecord_dataset.py:177-181), which holds exactly one sample — so k < 0 and every k >= 1 keep all windows of
     every scene and k == 0 yields nothing.  ``max_windows_per_environment`` is the limit the name suggests (at most that many windows per
-    scene); it has no counterpart in the reference."""
+    scene); it has no counterpart in the reference.  ``transform(cameras [S,7], tokens [S,h,w], split=...)`` is applied to every window,
+    like the reference's ``env_d.map(partial(transform, split=...))`` — e.g. ``functools.partial(process_batch, augment=cfg.augment_poses)``."""
     files = []
     for p in path.split(","):
         files += sorted(os.path.join(p, f) for f in os.listdir(p) if f.endswith(".tfrecord") and f"-{split}-" in f)
@@ -236,7 +289,11 @@ def load_token_dataset(path, batch_size, sequence_size, token_image_size, split=
                     n_win = min(n_win, max(0, int(max_windows_per_environment)))
                 for wi in range(n_win):
                     sel = idx[wi * sequence_size:(wi + 1) * sequence_size]
-                    buf.append((poses[sel], tokens[sel]))
+                    sample = (poses[sel], tokens[sel])
+                    if transform is not None:
+                        p_t, t_t = transform(torch.from_numpy(sample[0]), torch.from_numpy(sample[1]), split="train" if split == "train" else "test")
+                        sample = (np.asarray(p_t, dtype=np.float32), np.asarray(t_t))
+                    buf.append(sample)
                 yield from drain(False)
         yield from drain(True)
         if batch and not drop_last:
