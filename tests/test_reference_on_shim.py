@@ -408,10 +408,9 @@ def _reference_evaluator():
     return ev, metrics
 
 
-def test_evaluator_fixture_is_what_the_reference_evaluator_computes(golden_dir):
+def test_evaluator_fixture_is_what_the_reference_evaluator_computes(tf, golden_dir):
     """tests/golden/evaluator_reference_shim.npz (what viewformer_b200.metrics.Evaluator is held to on the GPU,
     tests/test_vs_reference_evaluator_gpu.py) is reproduced by the reference's own Evaluator (evaluate_transformer.py:22-67)."""
-    import tensorflow as tf
     from oracle import make_golden as G
     ev, _ = _reference_evaluator()
     g = np.load(os.path.join(golden_dir, "evaluator_reference_shim.npz"))
@@ -427,7 +426,7 @@ def test_evaluator_fixture_is_what_the_reference_evaluator_computes(golden_dir):
     assert abs(float(g["same.mse"]) - float(g["same.rmse"]) ** 2) < 1e-3 * float(g["same.mse"]) and float(g["same.mae"]) > 1.0
 
 
-def test_ssim_of_the_gpu_tests_and_the_k1_quirk_follow_the_reference():
+def test_ssim_of_the_gpu_tests_and_the_k1_quirk_follow_the_reference(tf):
     """(a) the fp64 restatement tests/test_eval_gpu.py::ssim_ref that the CUDA kernel is compared with equals the reference's ssim()
     (utils/metrics.py:17-73) with its default K1 = 0.01; (b) SSIMMetric — the class the evaluators use — passes 1 as the THIRD positional
     argument, which is K1, not the data range (metrics.py:183): its value is ssim(K1 = 1), measurably different."""
@@ -446,10 +445,9 @@ def test_ssim_of_the_gpu_tests_and_the_k1_quirk_follow_the_reference():
     assert abs(float(ref_k1) - float(ref_default.mean())) > 1e-4
 
 
-def test_allow_nan_mean_counts_nan_as_zero_with_full_weight_like_the_reference():
+def test_allow_nan_mean_counts_nan_as_zero_with_full_weight_like_the_reference(tf):
     """metrics.py:76-88 replaces NaN by 0 and then computes the weight from is_nan of the CLEANED values: a NaN camera error counts as 0
     with weight 1.  viewformer_b200.metrics.Mean(nan="zero") reproduces that for loc-angle / loc-dist."""
-    import tensorflow as tf
     from viewformer_b200.metrics import Evaluator
     _, metrics = _reference_evaluator()
     a = torch.tensor([[0., 0, 0, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0, 0], [2, 0, 0, 1, 0, 0, 0]])
@@ -460,3 +458,30 @@ def test_allow_nan_mean_counts_nan_as_zero_with_full_weight_like_the_reference()
     ours = Evaluator()
     ours.update_with_camera(a, b)
     assert abs(ours.result()["loc-dist"] - 2.0) < 1e-6
+
+
+def test_multi_context_evaluator_equals_the_reference_class(tf):
+    """evaluate_transformer_multictx.py:13-34 as shipped against viewformer_b200.metrics.MultiContextEvaluator: same ctxNN keys, same
+    camera statistics per context size (the image half of each Evaluator needs the GPU: tests/test_vs_reference_evaluator_gpu.py)."""
+    from viewformer_b200.metrics import MultiContextEvaluator
+    _reference_evaluator()
+    _, mc = ref_loader.load_reference_evaluate()
+    B, T = 4, 4
+    gt_cams = synth.make_cameras(1, B, seed=31)[0]                                     # [B, 7] the target view's camera
+    g = torch.Generator().manual_seed(32)
+    gen_cams = gt_cams[:, None].repeat(1, T, 1) + 0.2 * torch.randn((B, T, 7), generator=g)
+    gt_img, _ = synth.make_metric_pair(B, 16, 16, 33)
+    gen_img = torch.stack([synth.make_metric_pair(B, 16, 16, 40 + i)[1] for i in range(T)], 1)
+    ref = mc.MultiContextEvaluator(T)
+    ref.update_state(tf.convert_to_tensor(gt_cams.numpy()), tf.convert_to_tensor(gen_cams.numpy()), tf.convert_to_tensor(gt_img.numpy()),
+                     tf.convert_to_tensor(gen_img.numpy()))
+    ours = MultiContextEvaluator(T)
+    ours.update_state(gt_cams, gen_cams)                                               # cameras only: nothing touches the device
+    r, o = ref.result(), ours.result()
+    assert list(r) == list(o) == ["ctx01", "ctx02", "ctx03"]
+    for k in r:
+        for m in ("loc-angle", "loc-dist", "loc-angle-med", "loc-dist-med"):
+            assert abs(float(r[k][m]) - o[k][m]) < 2e-6 * max(1.0, abs(o[k][m])), (k, m)
+    assert set(ours.get_progress_bar_info()) == {"img_psnr", "cam_loc", "cam_ang"}
+    assert abs(float(ref.get_progress_bar_info()["cam_loc"]) - ours.get_progress_bar_info()["cam_loc"]) < 2e-6
+

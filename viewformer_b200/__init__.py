@@ -19,7 +19,7 @@ def __getattr__(name):   # lazy: importing the package must not require the buil
     if name in ("transformer_predict", "run_with_batchsize", "encode_images", "decode_code"):
         from . import evaluate
         return getattr(evaluate, name)
-    if name in ("Evaluator", "image_metrics"):
+    if name in ("Evaluator", "MultiContextEvaluator", "image_metrics"):
         from . import metrics
         return getattr(metrics, name)
     if name in ("VQGANTrainer",):

@@ -128,3 +128,27 @@ class Evaluator:
         out = {m.name: float(m.result()) for m in self._img.values() if m.count}
         out.update({m.name: float(m.result()) for m in self._loc.values() if (getattr(m, "count", 0) or getattr(m, "store", None))})
         return out
+
+
+class MultiContextEvaluator:
+    """evaluate/evaluate_transformer_multictx.py:13-34: one Evaluator per context size.  ``generated_images`` [B,T,H,W,3] /
+    ``generated_cameras`` [B,T,7] hold the prediction made from the first i views at index i; index 0 (no context) is skipped and
+    the result is keyed ``ctx01`` ... ``ctx{T-1}``."""
+
+    def __init__(self, sequence_size, image_size=None, device="cuda"):
+        self.sequence_size = sequence_size
+        self._evaluators = [Evaluator(image_size=image_size, device=device) for _ in range(sequence_size - 1)]
+
+    def update_state(self, ground_truth_cameras=None, generated_cameras=None, ground_truth_images=None, generated_images=None):
+        n = generated_images.shape[1] if generated_images is not None else generated_cameras.shape[1]
+        for i in range(1, n):
+            self._evaluators[i - 1].update_state(ground_truth_cameras, None if generated_cameras is None else generated_cameras[:, i],
+                                                 ground_truth_images, None if generated_images is None else generated_images[:, i])
+
+    def get_progress_bar_info(self):
+        return self._evaluators[-1].get_progress_bar_info()
+
+    def result(self):
+        from collections import OrderedDict
+        return OrderedDict((f"ctx{i + 1:02d}", x.result()) for i, x in enumerate(self._evaluators))
+
