@@ -485,3 +485,26 @@ def test_multi_context_evaluator_equals_the_reference_class(tf):
     assert set(ours.get_progress_bar_info()) == {"img_psnr", "cam_loc", "cam_ang"}
     assert abs(float(ref.get_progress_bar_info()["cam_loc"]) - ours.get_progress_bar_info()["cam_loc"]) < 2e-6
 
+
+def test_checkpoint_object_paths_are_the_reference_models_attribute_names(tf):
+    """A TF2 object-based checkpoint (what model.save_weights writes and utils/tensorflow.py:57-61 loads) is keyed by the Python
+    attribute names along the path from the model to each variable.  Walks the REAL reference MIGT object along
+    tf_checkpoint.object_paths(key)[0] for every state_dict key and requires the variable found there to be the one the key names
+    (found independently by its Keras variable name) — this is what caught 'wpe' (a variable hanging off the model itself, not
+    wpe/embeddings) and pose_criterion/pose_classifier (not pose_classifier at the root)."""
+    from viewformer_b200 import tf_checkpoint as tfc
+    kw = dict(SMALL, use_dynamic_pose_loss=True)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    model = ref_loader.build_reference_migt(sd, dynamic_pose_weights=[0.3, -2.0], **kw)
+    assert "pose_loss_weighting_criterion.pos_ori_weights" in sd
+    for k, v in sd.items():
+        obj = model
+        for part in tfc.object_paths(k)[0].split("/"):
+            obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+        assert tuple(obj.shape) == tuple(v.shape), k
+        assert obj is _var(model, k), k                                # same variable object as the one found by name
+        assert float((torch.as_tensor(obj).detach() - v).abs().max()) == 0.0
+    # the literal dotted form is NOT an attribute path of the real model for these two groups
+    assert not hasattr(model, "pose_classifier") and not hasattr(model.wpe, "embeddings")
+

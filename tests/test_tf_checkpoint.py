@@ -71,6 +71,20 @@ def test_migt_state_dict_roundtrip_through_tf_container(tmp_path):
     assert ck.resolve("h/1/mlp/c_fc/weight") == "h/1/mlp/c_fc/weight" + tfc.VAR_SUFFIX
     with pytest.raises(RuntimeError, match="Missing keys"):
         tfc.load_state_dict(prefix, ["h.5.ln_1.gamma"])
+    # the file is laid out like the reference's Keras model tracks its variables (attribute names, tfc.object_paths): wpe hangs off the
+    # root, the pose classifier is a child of pose_criterion
+    assert ck.resolve("wpe") == "wpe" + tfc.VAR_SUFFIX and ck.resolve("pose_criterion/pose_classifier/c_fc/weight")
+    with pytest.raises(KeyError):
+        ck.resolve("pose_classifier/c_fc/weight")
+    # ... while files written with the older literal layout (wpe/embeddings, pose_classifier at the root) — or a Keras file seen through
+    # add_weight's dependency name 'embeddings' — still load
+    old = str(tmp_path / "old" / "model")
+    tfc.write_checkpoint(old, {k.replace(".", "/"): v.numpy() for k, v in sd.items()})
+    got = tfc.load_state_dict(old, m.expected_keys())
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    alt = str(tmp_path / "alt" / "model")
+    tfc.write_checkpoint(alt, {("embeddings" if k == "wpe.embeddings" else tfc.object_paths(k)[0]): v.numpy() for k, v in sd.items()})
+    assert torch.equal(tfc.load_state_dict(alt, ["wpe.embeddings"])["wpe.embeddings"], sd["wpe.embeddings"])
 
 
 def test_reader_on_a_table_assembled_byte_by_byte_from_the_leveldb_format(tmp_path):

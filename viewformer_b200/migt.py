@@ -143,7 +143,8 @@ class MIGT:
 
     def save_weights(self, filepath):
         from . import tf_checkpoint
-        tf_checkpoint.write_checkpoint(filepath, {k.replace(".", "/"): v.numpy() for k, v in self.state_dict().items()})
+        # object paths = the reference model's attribute names (wpe at the root, pose_classifier under pose_criterion): tf_checkpoint.object_paths
+        tf_checkpoint.write_checkpoint(filepath, {tf_checkpoint.object_paths(k)[0]: v.numpy() for k, v in self.state_dict().items()})
 
     def _build(self):
         L.load(require_device=True)

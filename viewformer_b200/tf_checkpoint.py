@@ -293,21 +293,40 @@ class Checkpoint:
         return attrs["VARIABLE_VALUE"]
 
 
+def object_paths(key):
+    """Object-graph paths under which the reference's Keras MIGT tracks the variable of state_dict key ``key`` — the Python attribute
+    names a TF2 object-based checkpoint is keyed by — most specific first (checked against the attributes of the real model object in
+    tests/test_reference_on_shim.py).  Almost always 'a.b.c' -> 'a/b/c' (h/<i>/attn/c_attn/weight, ln_f/gamma, wte/weight ...); two are not:
+      * ``wpe.embeddings``: MIGT.build does ``self.wpe = self.add_weight(name="embeddings", ...)`` on the MODEL (migt.py:305-315), so the
+        variable hangs directly off the root, as 'wpe' (attribute) and 'embeddings' (add_weight's dependency name);
+      * ``pose_classifier.*``: the MLP is owned by ``self.pose_criterion`` (QuaternionPoseRepresentation, migt.py:136, :277).
+    The literal 'a/b/c' form stays last so that files written by earlier versions of this package still load."""
+    base = key.replace(".", "/")
+    if key == "wpe.embeddings":
+        return ["wpe", "embeddings", base]
+    if key.startswith("pose_classifier."):
+        return ["pose_criterion/" + base, base]
+    return [base]
+
+
 def load_state_dict(prefix, expected_keys, strict=True):
-    """{state_dict key: torch tensor} for ``expected_keys`` ('h.0.attn.c_attn.weight' <-> object path 'h/0/attn/c_attn/weight').
-    Falls back to the literal checkpoint key '<path>/.ATTRIBUTES/VARIABLE_VALUE' when the file carries no object graph."""
+    """{state_dict key: torch tensor} for ``expected_keys`` ('h.0.attn.c_attn.weight' <-> object path 'h/0/attn/c_attn/weight', see
+    ``object_paths``).  Falls back to the literal checkpoint key '<path>/.ATTRIBUTES/VARIABLE_VALUE' when the file carries no object graph."""
     import torch
     ck = Checkpoint(prefix)
     nodes = ck.object_graph() if OBJECT_GRAPH_KEY in ck.entries else None
     out, missing = {}, []
     for k in expected_keys:
-        path = k.replace(".", "/")
-        try:
-            key = ck.resolve(path, nodes) if nodes is not None else path + VAR_SUFFIX
-            if key not in ck.entries:
-                raise KeyError(key)
-            out[k] = torch.from_numpy(ck.tensor(key))
-        except KeyError:
+        for path in object_paths(k):
+            try:
+                key = ck.resolve(path, nodes) if nodes is not None else path + VAR_SUFFIX
+                if key not in ck.entries:
+                    raise KeyError(key)
+                out[k] = torch.from_numpy(ck.tensor(key))
+                break
+            except KeyError:
+                continue
+        else:
             missing.append(k)
     if missing and strict:
         raise RuntimeError(f"Missing keys in TF checkpoint {prefix}: {missing[:8]}{' ...' if len(missing) > 8 else ''}")
