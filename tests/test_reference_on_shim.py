@@ -497,7 +497,10 @@ def test_checkpoint_object_paths_are_the_reference_models_attribute_names(tf):
     cfg = MIGTConfig(**kw)
     sd = synth.make_migt_state_dict(cfg, 3)
     model = ref_loader.build_reference_migt(sd, dynamic_pose_weights=[0.3, -2.0], **kw)
-    assert "pose_loss_weighting_criterion.pos_ori_weights" in sd
+    obj = model                                                        # the dynamic pose-loss weights travel outside synth's state dict
+    for part in tfc.object_paths("pose_loss_weighting_criterion.pos_ori_weights")[0].split("/"):
+        obj = getattr(obj, part)
+    assert tuple(obj.shape) == (2,) and torch.as_tensor(obj).detach().tolist() == pytest.approx([0.3, -2.0])
     for k, v in sd.items():
         obj = model
         for part in tfc.object_paths(k)[0].split("/"):
