@@ -196,3 +196,24 @@ def test_schedules_equal_the_reference_module():
     with pytest.raises(TypeError):
         R.Schedule.from_str(nested).with_total_steps(200)(3)
     assert abs(float(parse(nested).with_total_steps(200)(3)) - 0.75) < 1e-9
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_config_fields_and_defaults_equal_the_reference_dataclasses():
+    """viewformer_b200/config.py against models/config.py:62-119 imported as shipped: the same field names (= the config.json schema of
+    the published checkpoints) and the same defaults; `localization_weight` is kept as the string and parsed where it is used."""
+    import dataclasses
+    import sys
+    from viewformer_b200 import config as C
+    ref_loader.load_reference_modules()
+    RC = sys.modules["viewformer.models.config"]
+    for name in ("VQGANConfig", "MIGTConfig"):
+        r, o = getattr(RC, name), getattr(C, name)
+        rf, of = {f.name for f in dataclasses.fields(r)}, {f.name for f in dataclasses.fields(o)}
+        assert rf - of <= {"model"} and not (of - rf), (name, rf ^ of)
+        ri, oi = r(), o()
+        assert ri.model == oi.model and ri.model_type == oi.model_type
+        for k in sorted(rf & of):
+            assert str(getattr(ri, k)) == str(getattr(oi, k)) or k == "localization_weight", (name, k)
+    assert str(RC.MIGTConfig().localization_weight) == "1.0" and C.MIGTConfig().localization_weight == "1"
+    assert RC.VQGANConfig().stride == C.VQGANConfig().stride == 16
