@@ -120,3 +120,31 @@ def test_camera_metrics_match_the_reference_evaluator_fixture(golden_dir):
         assert abs(r[k] - float(g["cam." + k])) < 2e-6 * max(1.0, abs(r[k])), k
     info = ev.get_progress_bar_info()
     assert set(info) == {"img_psnr", "cam_loc", "cam_ang"} and abs(info["cam_loc"] - r["loc-dist"]) < 1e-12
+
+
+def test_bench_json_contract_of_both_arms():
+    """The keys the driver reads: (a) the committed line of the B200 arm (profiles/, produced on a B200 by this bench.py), (b) the
+    reference arm run live here on the host cores with a tiny wall budget (`bench.py --impl reference`: the CPU oracle, bounded)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.load(open(os.path.join(root, "profiles", "r02_bench_n1_mixed_v6.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity"):
+        assert k in line, k
+    assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None and line["data"] == "synthetic"
+    assert "workload" in line["config"] and not any(k in line["config"] for k in ("model", "global_batch", "seq_len"))
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["bound"] in ("hbm", "tensor")
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and line["gpu_launches"] > 0 and line["parity"]["code_mismatches"] == 0
+    assert abs(line["value"] - line["config"]["scenes_per_gpu"] * line["n_gpus"] / (line["ms_per_step"] / 1e3)) < 1e-6 * line["value"]
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-budget-s", "5"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"] and ref["higher_is_better"] is True
+    assert ref["config"]["workload"] == __import__("importlib").import_module("bench").WORKLOAD
+    assert ref["e2e"] == {"value": ref["value"], "unit": ref["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert ref["cpu_baseline"]["value"] == ref["value"] and ref["cpu_baseline"]["kind"] == "port" and ref["cpu_baseline"]["cores"] >= 1
+    assert ref["steps"] == 1 and ref["value"] > 0
