@@ -841,10 +841,6 @@ def conv_wgrad_tc(x, dy, dw, *, accumulate=True):
     return dw
 
 
-def dense_wgrad_tc_ok(k, n):
-    return k % 128 == 0 and n % 128 == 0
-
-
 def dense_wgrad_tc(x_rows, dy_rows, dw_kn, *, accumulate=True):
     """dW[k, n] (+)= sum_m x[m, k] dy[m, n] on the exact split-fp16 tensor-core GEMM (K = rows): both operands are transposed to K-major
     split form (vf_pad_transpose_split, plain mode), the row axis is split over the SMs, vf_sum_splits folds the partial products."""
