@@ -511,3 +511,35 @@ def test_checkpoint_object_paths_are_the_reference_models_attribute_names(tf):
     # the literal dotted form is NOT an attribute path of the real model for these two groups
     assert not hasattr(model, "pose_classifier") and not hasattr(model.wpe, "embeddings")
 
+
+def test_codebook_evaluation_script_equals_oracle_and_fixture(tf, golden_dir):
+    """evaluate/evaluate_codebook.py as shipped: its generate_batch_predictions (encode -> decode round trip, BASELINE configs[0]) with the
+    REAL torch codebook equals the oracle's encode / decode_code / float_to_images chain — what viewformer_b200.evaluate
+    .generate_codebook_predictions is compared with on the GPU — and its Evaluator reports the image numbers of the committed fixture."""
+    from oracle import make_golden as mg
+    ref_loader.load_reference_evaluate()
+    _reference_evaluator()
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "viewformer", "evaluate", "evaluate_codebook.py")
+    ec = ref_loader._load("viewformer.evaluate.evaluate_codebook", path)
+    vcfg = VQGANConfig(**mg.SMALL_VQ)
+    vsd = synth.make_vqgan_state_dict(vcfg, 0)
+    vq = ref_loader.build_reference_vqgan(vsd, **mg.SMALL_VQ)
+    for size in (vcfg.image_size, 48):                                  # 48 -> 32: the dataset resize rule in front of the encoder
+        images = synth.make_images_uint8(1, 3, size=size, seed=51)[0]
+        with torch.no_grad():
+            r = ec.generate_batch_predictions(ref_loader.ReferenceCodebookNHWC(vq), tf.convert_to_tensor(images.numpy()))
+            x = images if size == vcfg.image_size else torch.from_numpy(sys.modules["viewformer.data._common"].resize(images.numpy(), vcfg.image_size))
+            codes = vq.encode(mo.images_to_float(x).permute(0, 3, 1, 2).contiguous())[-1]
+            want = mo.float_to_images(vq.decode_code(codes).permute(0, 2, 3, 1))
+        assert torch.equal(torch.as_tensor(r["generated_images"]).as_subclass(torch.Tensor), want)
+        assert torch.equal(torch.as_tensor(r["ground_truth_images"]).as_subclass(torch.Tensor), images)
+    g = np.load(os.path.join(golden_dir, "evaluator_reference_shim.npz"))
+    gt, gen = synth.make_metric_pair(5, 64, 64, 21)
+    E = ec.Evaluator()
+    E.update_state(tf.convert_to_tensor(gt.numpy()), tf.convert_to_tensor(gen.numpy()))
+    r = E.result()
+    assert list(r) == ["mse", "rmse", "mae", "psnr", "lpips", "ssim"]
+    for k in ("mse", "rmse", "mae", "psnr", "ssim"):
+        assert abs(r[k] - float(g["same." + k])) <= 1e-6 * abs(r[k])
+    assert abs(E.get_progress_bar_info()["img_rgbl1"] - r["mae"]) < 1e-9
+

@@ -57,3 +57,34 @@ def test_evaluator_cameras_and_images_together(golden_dir):
     assert abs(r["psnr"] - float(g["same.psnr"])) < 1e-5 * r["psnr"]
     info = ev.get_progress_bar_info()
     assert set(info) == {"img_psnr", "cam_loc", "cam_ang"} and abs(info["img_psnr"] - r["psnr"]) < 1e-12
+
+
+def test_codebook_round_trip_and_its_evaluator(golden_dir):
+    """evaluate/evaluate_codebook.py:66-76 (BASELINE configs[0]: encode -> decode round trip) through viewformer_b200.evaluate
+    .generate_codebook_predictions, against the oracle chain that the reference script itself reproduces on the CPU
+    (tests/test_reference_on_shim.py::test_codebook_evaluation_script_equals_oracle_and_fixture); CodebookEvaluator = the image half."""
+    import torch
+    from oracle import vqgan_oracle as vo, migt_oracle as mo
+    from oracle.make_golden import SMALL_VQ
+    from viewformer_b200 import VQGAN, generate_codebook_predictions
+    from viewformer_b200.config import VQGANConfig
+    from viewformer_b200.metrics import CodebookEvaluator
+    vcfg = VQGANConfig(**SMALL_VQ)
+    vsd = synth.make_vqgan_state_dict(vcfg, 0)
+    cb = VQGAN(vcfg, precision="fp32").load_state_dict(vsd)
+    images = synth.make_images_uint8(1, 3, size=vcfg.image_size, seed=51)[0]
+    with torch.no_grad():
+        codes = vo.encode(vsd, vcfg, mo.images_to_float(images).permute(0, 3, 1, 2).contiguous())[2]
+        want = mo.float_to_images(vo.decode_code(vsd, vcfg, codes).permute(0, 2, 3, 1))
+    r = generate_codebook_predictions(cb, images)
+    assert torch.equal(r["codes"].cpu(), codes) and torch.equal(torch.as_tensor(r["ground_truth_images"]), images)
+    assert r["generated_images"].dtype == torch.uint8 and int((r["generated_images"].cpu().int() - want.int()).abs().max()) <= 1
+    g = np.load(os.path.join(golden_dir, "evaluator_reference_shim.npz"))
+    gt, gen = synth.make_metric_pair(5, 64, 64, 21)
+    ev = CodebookEvaluator()
+    ev.update_state(gt, gen)
+    res = ev.result()
+    assert set(res) == {"mse", "rmse", "mae", "psnr", "ssim"}
+    for k in res:
+        assert abs(res[k] - float(g["same." + k])) <= 1e-5 * abs(res[k]) + (2e-5 if k == "ssim" else 0.0), k
+    assert abs(ev.get_progress_bar_info()["img_rgbl1"] - res["mae"]) < 1e-12

@@ -16,10 +16,10 @@ def __getattr__(name):   # lazy: importing the package must not require the buil
     if name in ("generate_batch_predictions", "generate_batch_predictions_multictx", "GraphedPredictions"):
         from . import generate
         return getattr(generate, name)
-    if name in ("transformer_predict", "run_with_batchsize", "encode_images", "decode_code"):
+    if name in ("transformer_predict", "run_with_batchsize", "encode_images", "decode_code", "generate_codebook_predictions"):
         from . import evaluate
         return getattr(evaluate, name)
-    if name in ("Evaluator", "MultiContextEvaluator", "image_metrics"):
+    if name in ("Evaluator", "CodebookEvaluator", "MultiContextEvaluator", "image_metrics"):
         from . import metrics
         return getattr(metrics, name)
     if name in ("VQGANTrainer",):

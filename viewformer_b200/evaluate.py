@@ -3,6 +3,8 @@
     transformer_predict   evaluate_transformer_multictx_allimg.py:15-48   3-stream call: per context size, the query view and its pose
     run_with_batchsize    evaluate_transformer_multictx_allimg.py:51-62
     encode_images / decode_code   :65-80  uint8 frames -> codes (with the dataset resize rule), codes -> uint8 images
+    generate_codebook_predictions   evaluate_codebook.py:66-76 (its ``generate_batch_predictions``): the codebook's encode -> decode round trip
+                                    (BASELINE.json configs[0])
 """
 import torch
 
@@ -59,3 +61,12 @@ def decode_code(codes, *, codebook_model):
     lead = codes.shape[:-2]
     img = codebook_model.decode_code_u8(codes.reshape((-1,) + tuple(codes.shape[-2:])))
     return img.reshape(tuple(lead) + tuple(img.shape[-3:]))
+
+
+def generate_codebook_predictions(codebook_model, images):
+    """evaluate/evaluate_codebook.py:66-76: uint8 images [N,H,W,3] -> resize to the codebook's size -> encode -> decode_code -> clip ->
+    uint8; returns dict(ground_truth_images = the inputs as given, generated_images uint8 [N,S,S,3], codes int64 [N,h,w])."""
+    images = torch.as_tensor(images)
+    codes = encode_images(images, codebook_model=codebook_model)
+    return dict(ground_truth_images=images, generated_images=decode_code(codes, codebook_model=codebook_model), codes=codes)
+

@@ -130,6 +130,19 @@ class Evaluator:
         return out
 
 
+class CodebookEvaluator(Evaluator):
+    """evaluate/evaluate_codebook.py:18-49: the image half only, ``update_state(ground_truth_images, generated_images)``."""
+
+    def update_state(self, ground_truth_images, generated_images):
+        self.update_with_image(ground_truth_images, generated_images)
+
+    def get_progress_bar_info(self):
+        return dict(img_rgbl1=self._img["mae"].result())          # + img_lpips in the reference (LPIPS is not available offline)
+
+    def result(self):
+        return {m.name: float(m.result()) for m in self._img.values() if m.count}
+
+
 class MultiContextEvaluator:
     """evaluate/evaluate_transformer_multictx.py:13-34: one Evaluator per context size.  ``generated_images`` [B,T,H,W,3] /
     ``generated_cameras`` [B,T,7] hold the prediction made from the first i views at index i; index 0 (no context) is skipped and
