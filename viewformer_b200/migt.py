@@ -442,7 +442,8 @@ class MIGT:
         poses, tokens = batch
         out = self(dict(poses=poses, input_ids=tokens), compute_losses=True, training=False)
         res = {k: float(torch.as_tensor(v, dtype=torch.float32).mean()) for k, v in out.items()
-               if k in ("loss", "ce_loss", "pose_loss", "pose_pos_loss", "pose_ori_loss")}
+               if k in ("loss", "ce_loss", "pose_loss", "pose_pos_loss", "pose_ori_loss", "localization_weight", "dynamic_loss_weight_pos",
+                        "dynamic_loss_weight_ori")}                  # every output that has a Keras metric of its name (migt.py:260-283, :510-512)
         tok = self._in(torch.as_tensor(tokens), torch.int64)
         logits = out["logits"]
         pred = L.argmax_rows(logits.reshape(-1, logits.shape[-1])).reshape(tok.shape)
