@@ -543,3 +543,31 @@ def test_codebook_evaluation_script_equals_oracle_and_fixture(tf, golden_dir):
         assert abs(r[k] - float(g["same." + k])) <= 1e-6 * abs(r[k])
     assert abs(E.get_progress_bar_info()["img_rgbl1"] - r["mae"]) < 1e-9
 
+
+def test_reference_test_step_and_predict_step_equal_the_oracle_expectations(tf):
+    """migt.py:507-541 as shipped, with the real torch codebook attached: the quantities tests/test_eval_gpu.py holds MIGT.test_step /
+    predict_step to (mean loss of call(compute_losses=True), token accuracy beyond the first n_loss_skip views, teacher-forced argmax
+    tokens and their decoded images) are what the reference's own steps return."""
+    from oracle import make_golden as mg
+    vcfg = VQGANConfig(**mg.SMALL_VQ)
+    vq = ref_loader.build_reference_vqgan(synth.make_vqgan_state_dict(vcfg, 0), **mg.SMALL_VQ)
+    kw = dict(n_layer=2, n_head=4, d_model=64, sequence_size=4, n_embeddings=vcfg.n_embed, token_image_size=8, n_loss_skip=1)
+    cfg = MIGTConfig(**kw)
+    sd = synth.make_migt_state_dict(cfg, 3)
+    model = ref_loader.build_reference_migt(sd, **kw)
+    model.codebook_model = ref_loader.ReferenceCodebookNHWC(vq)
+    codes = synth.make_codes(3, 4, n_embed=cfg.n_embeddings, side=8, seed=5)
+    rel = mo.normalize_cameras(mo.to_relative_cameras(synth.make_cameras(3, 4, seed=6))[0])
+    with torch.no_grad():
+        o = mo.forward(sd, cfg, dict(input_ids=codes, poses=rel), compute_losses=True)
+        for m in model.metrics:
+            m.reset_states()
+        res = model.test_step((tf.constant(rel.numpy()), codes.clone()))
+        ps = model.predict_step((tf.constant(rel.numpy()), codes.clone()))
+    assert {"loss", "ce_loss", "acc", "localization_weight", "psnr", "pose_loss", "pose_pos_loss", "pose_ori_loss", "pose_pos_err", "pose_ori_err"} <= set(res)
+    assert abs(float(res["loss"]) - float(o["loss"].mean())) < 1e-5 * abs(float(o["loss"].mean()))
+    acc = float((o["logits"].argmax(-1)[:, 1:] == codes[:, 1:]).float().mean())
+    assert abs(float(res["acc"]) - acc) < 1e-6 and float(res["psnr"]) > 0
+    assert torch.equal(torch.as_tensor(ps["latent_code"]).long(), o["logits"].argmax(-1))
+    assert tuple(ps["decoded_image"].shape) == (12, 32, 32, 3) and tuple(ps["ground_truth_image"].shape) == (12, 32, 32, 3)
+
